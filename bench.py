@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on its config: Mrays/s incoherent closest-hit,
+synthetic 1M-triangle random-soup mesh, 16M-ray batch of diffuse bounce rays (config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the closest-hit path over one 16,777,216-ray batch.
+  value  : rays already resident in HBM, K launches timed with CUDA events on the launching
+           stream (rrt_intersect_device), max over ranks.
+  e2e    : the same batch through the host-buffer C-ABI call a Rust `impl Primitive` binds
+           (rrt_intersect): pinned host rays -> H2D -> kernel -> D2H hits inside the timed region.
+  N > 1  : the path shards by rays/pixels with no exchange; every rank holds the scene and traces
+           its own 16M-ray batch (weak scaling, no data-path collective).
+`--impl reference` times the CPU restatement of the reference's own BVH path (oracle/, all host
+threads) on bounded samples of the same workload — the Rust reference cannot be built here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_TRIS = 1 << 20
+N_RAYS = 1 << 24
+METRIC = "Mrays/s incoherent closest-hit"
+UNIT = "Mrays/s"
+# Algorithmic bytes per ray (SURVEY.md §8d / DESIGN.md §5): fp32 record sizes ray 32 B + hit 16 B
+# + 32 B per node visited + 36 B per triangle tested, with the mean node / triangle counts measured
+# by the oracle on the Tier-F HLBVH (max_prims_in_node 4, near-first order, true closest-hit
+# culling) on this exact workload — a property of the workload, not of the GPU kernel.
+NV_C3 = 122.98
+NT_C3 = 20.02
+BYTES_PER_RAY = 32 + 16 + 32 * NV_C3 + 36 * NT_C3
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "config 3: synthetic 1M-triangle random-soup mesh (v0~U[0,1]^3, edges U[-0.01,0.01]^3, seed 3), "
+                    "16,777,216 incoherent cosine-weighted bounce rays per batch (seed 4+rank), t_max=inf, closest hit",
+        "n_triangles": N_TRIS,
+        "rays_per_step_per_gpu": N_RAYS,
+        "max_prims_in_node": 4,
+        "tier": "F (true closest hit, ties -> lowest prim id)",
+        "l2_policy": "inputs larger than L2: 1 GiB of rays + 0.5 GiB of hits stream per step (126 MB L2)",
+        "parallelism": f"ray-sharded x{n_gpus}, scene replicated, no data-path collective",
+    }
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    f = ROOT / "profiles" / "traffic.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["closest_hit_dram_bytes_per_launch_16M"])
+        except Exception:
+            return None
+    return None
+
+
+def cpu_oracle_rate(p, idx, rays_sample, threads=None):
+    """Times the CPU restatement (oracle, Tier F) on `rays_sample`; returns (Mrays/s, threads, stats)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    threads = threads or O.hardware_threads()
+    scene = O.soup_scene(p, idx, O.TIER_F, 4)
+    scene.intersect(rays_sample[: min(len(rays_sample), 1 << 16)], nthreads=threads)  # warm
+    t0 = time.perf_counter()
+    r = scene.intersect(rays_sample, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(rays_sample) / dt / 1e6, threads, r["stats"], scene
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (restated in oracle/, see its header)
+    with every host thread, on bounded samples of config 3.  Rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    from rs_ray_toy_b200 import synth
+    threads = O.hardware_threads()
+    p, idx = synth.soup_triangles(N_TRIS)
+    scene = O.soup_scene(p, idx, O.TIER_F, 4)
+    probe = synth.bounce_rays(p, idx, 1 << 17, seed=synth.SEED_C3_RAYS)
+    t0 = time.perf_counter()
+    scene.intersect(probe, nthreads=threads)
+    rate = len(probe) / (time.perf_counter() - t0)
+    steps_total = args.steps + args.warmup
+    per_step = int(min(N_RAYS, max(1 << 16, rate * 120.0 / max(1, steps_total))))  # whole run ~2 min
+    rays = synth.bounce_rays(p, idx, per_step, seed=synth.SEED_C3_RAYS)
+    for _ in range(args.warmup):
+        scene.intersect(rays, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scene.intersect(rays, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt / 1e6
+    sample = f"{per_step} rays per step of the 16,777,216-ray batch (same generator and seed), full 1M-triangle scene"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement (C++ f64, oracle/) of bvh.rs HLBVH + traversal with Q1/Q2/Q3 fixed; the Rust "
+                "reference needs a nightly toolchain and un-vendored crates and cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=N_RAYS, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from rs_ray_toy_b200 import synth
+    from rs_ray_toy_b200.aggregate import HIT_DTYPE, RAY_DTYPE, Context, pack_rays, soup_aggregate
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_rays = args.rays
+
+    ctx = Context(local_rank)
+    p, idx = synth.soup_triangles(N_TRIS)
+    agg = soup_aggregate(ctx, p, idx, 4)
+    stats = agg.stats()
+    rays_np = synth.bounce_rays(p, idx, n_rays, seed=synth.SEED_C3_RAYS + rank)
+    h_rays = ctx.pinned_empty(n_rays, RAY_DTYPE)
+    h_rays[:] = pack_rays(rays_np)
+    h_hits = ctx.pinned_empty(n_rays, HIT_DTYPE)
+    del rays_np
+
+    d_rays = torch.empty(n_rays * 8, dtype=torch.float64, device="cuda")
+    d_hits = torch.empty(n_rays * 4, dtype=torch.float64, device="cuda")
+    d_rays.copy_(torch.from_numpy(h_rays.view(np.float64)), non_blocking=False)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        agg.intersect_device(n_rays, d_rays.data_ptr(), d_hits.data_ptr(), stream.cuda_stream)
+
+    # ---- device-resident timing: K launches, CUDA events on the launching stream ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = ctx.launch_count
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step_device()
+            ev[i + 1].record(stream)
+        barrier()
+    launches = ctx.launch_count - launches0
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n_rays * world * args.steps / (total_ms_max * 1e-3) / 1e6
+    n_hit = int((d_hits.view(torch.int64)[0::4] & 0xFFFFFFFF != 0xFFFFFFFF).sum().item())
+
+    # ---- end to end: host buffers through rrt_intersect (H2D + kernel + D2H per step) ----
+    for _ in range(2):
+        agg.intersect(h_rays, out=h_hits)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        agg.intersect(h_rays, out=h_hits)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_rays * world * args.steps / float(t.item()) / 1e6
+    e2e_hit = int((h_hits["prim_id"] != 0xFFFFFFFF).sum())
+    if e2e_hit != n_hit:
+        raise SystemExit(f"bench.py: host path and device path disagree ({e2e_hit} vs {n_hit} hits)")
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kernel_ms = float(np.mean(per_launch_ms))
+        achieved = n_rays * BYTES_PER_RAY / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 deciding arithmetic (Moller-Trumbore / quadratic), fp32 box culling", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 64, "d2h_bytes_per_step": n_rays * 32,
+                    "api": "rrt_intersect (pinned host rays -> hits), 1 Mi-ray chunks on 3 streams"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "trace_kernel<closest>",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
+                         "nodes_visited_per_ray_oracle": NV_C3, "prims_tested_per_ray_oracle": NT_C3,
+                         "compulsory_dram_bytes_per_ray": 64 + 32 + stats["device_bytes"] / n_rays},
+            "hit_fraction": n_hit / n_rays,
+            "scene": stats,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_sample = 1 << 22
+            sample = synth.bounce_rays(p, idx, n_sample, seed=synth.SEED_C3_RAYS)
+            rate, threads, st, _ = cpu_oracle_rate(p, idx, sample)
+            # size-check: ~10-30 s of CPU work; one more pass if the first was very short
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {n_sample} rays of the batch generator (seed 4), full 1M-triangle scene, "
+                                              "oracle Tier F (C++ f64 restatement, std::thread x cores)",
+                                    "nodes_visited_per_ray": float(st[1]) / float(st[0]),
+                                    "prims_tested_per_ray": float(st[2]) / float(st[0])}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

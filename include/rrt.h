@@ -1,0 +1,129 @@
+/* rrt.h — C ABI of librrt_sm100.so, the B200 (sm_100a) ray-intersection and path-tracing core
+ * that stands behind rs_ray_toy's aggregate seam.
+ *
+ * Every entry point names the reference interface it replaces (file:line under
+ * pppKin/rs_ray_toy `src/`).  Plain pointers and sizes only; no C++ / torch / Rust types.
+ * All functions return RRT_OK (0) or a negative rrt_status; rrt_last_error() gives the text of
+ * the last failure on the calling thread.  No exception or panic crosses this boundary
+ * (the reference reports the same conditions with assert!/panic!, e.g. bvh.rs:319, scene.rs:70).
+ *
+ * Threading: an rrt_scene is immutable after rrt_scene_commit(); intersect / render calls on it
+ * are stream-ordered and may be issued from several host threads (the reference's
+ * `Primitive: Send + Sync`, primitives.rs:14).
+ */
+#ifndef RRT_H_
+#define RRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rrt_status {
+    RRT_OK = 0,
+    RRT_ERR_INVALID = -1,     /* bad argument / call order                                      */
+    RRT_ERR_CUDA = -2,        /* CUDA runtime failure (text in rrt_last_error)                  */
+    RRT_ERR_UNSUPPORTED = -3, /* reference feature outside the hot-path scope       */
+    RRT_ERR_EMPTY = -4,       /* BVHAccel::new on zero primitives (bvh.rs:319 asserts)          */
+    RRT_ERR_IO = -5           /* scene.json / .obj could not be read or parsed                  */
+} rrt_status;
+
+typedef struct rrt_ctx rrt_ctx;     /* one per CUDA device                                       */
+typedef struct rrt_scene rrt_scene; /* the GPU aggregate: replaces BVHAccel behind Arc<dyn Primitive> */
+
+/* geometry.rs:73-79 `Ray{o,d,t_max,time,medium}` — f64 like the reference; `medium` is out of
+ * scope.  d is used as given (the aggregate never renormalises it, bvh.rs:186).  64 bytes.      */
+typedef struct rrt_ray {
+    double o[3];
+    double d[3];
+    double t_max;
+    double time;
+} rrt_ray;
+
+/* What BVHAccel::intersect hands back through `r.t_max` and `si` (bvh.rs:183-236,
+ * primitives.rs:56-57): the primitive that won, its hit distance and surface parameters.
+ * prim_id indexes the primitive list in the order it was added (= the Vec passed to
+ * BVHAccel::new, renderprocess.rs:1299); RRT_NO_HIT when the ray escaped.
+ * (u,v): triangle barycentrics of triangle.rs:245-256, or the sphere's (phi/phi_max, theta
+ * fraction) of sphere.rs:195-198.  32 bytes.                                                    */
+#define RRT_NO_HIT 0xFFFFFFFFu
+typedef struct rrt_hit {
+    uint32_t prim_id;
+    uint32_t reserved;
+    double t;
+    double u;
+    double v;
+} rrt_hit;
+
+/* BVHSplitMethod (bvh.rs:111-114) plus the parity tier.                         */
+typedef enum rrt_build_flags {
+    RRT_BUILD_FAST = 0,    /* Tier F: own SAH tree, true closest hit, ties -> lowest prim id     */
+    RRT_BUILD_LITERAL = 1  /* Tier L: the reference's HLBVH topology and accept rules, quirks kept */
+} rrt_build_flags;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int rrt_create(int device_ordinal, rrt_ctx** out);
+void rrt_destroy(rrt_ctx* ctx);
+const char* rrt_last_error(void);
+/* Number of kernels launched by this library on `ctx` since creation (bench.py's gpu_launches). */
+uint64_t rrt_launch_count(const rrt_ctx* ctx);
+/* Pinned host memory for ray / hit batches (cudaHostAlloc); plain malloc'd buffers also work.   */
+int rrt_host_alloc(rrt_ctx* ctx, size_t bytes, void** out);
+int rrt_host_free(rrt_ctx* ctx, void* p);
+
+/* ---- scene assembly: what make_aggregate builds (renderprocess.rs:1178-1304) --------------- */
+int rrt_scene_begin(rrt_ctx* ctx, rrt_scene** out);
+void rrt_scene_destroy(rrt_scene* scene);
+
+/* create_triangle_mesh (shape/triangle.rs:131-165): vertex positions p[3*nv] (f64), 0-based
+ * vertex indices vi[3*ntri]; optional normals n[3*nn] with ni[3*ntri], optional uv[2*nuv] with
+ * uvi[3*ntri] (null when absent).  The obj-level transform is NOT applied to vertices, exactly
+ * like the reference (Q7, renderprocess.rs:884-903).  Returns the mesh handle in *mesh_id.     */
+int rrt_scene_add_mesh(rrt_scene* scene, uint32_t nv, const double* p, uint32_t ntri, const uint32_t* vi,
+                       uint32_t nn, const double* n, const uint32_t* ni, uint32_t nuv, const double* uv,
+                       const uint32_t* uvi, uint32_t* mesh_id);
+
+/* One GeometricPrimitive per mesh triangle (renderprocess.rs:1255-1263), appended to the
+ * primitive list once per instance transform (TransformedPrimitive, primitives.rs:27-30) or
+ * once bare when n_instances == 0.  instance_m / instance_minv: n_instances 4x4 row-major
+ * matrices and their inverses (Transform carries both, transform.rs:177-180).                  */
+int rrt_scene_add_triangles(rrt_scene* scene, uint32_t mesh_id, uint32_t material_id, uint32_t n_instances,
+                            const double* instance_m, const double* instance_minv);
+
+/* Sphere::new (shape/sphere.rs:28-47) wrapped in a GeometricPrimitive, appended bare or once per
+ * instance like the triangles above (renderprocess.rs:1187-1227).                              */
+int rrt_scene_add_sphere(rrt_scene* scene, const double* obj_to_world_m, const double* obj_to_world_minv,
+                         double radius, double z_min, double z_max, double phi_max_deg, uint32_t material_id,
+                         uint32_t n_instances, const double* instance_m, const double* instance_minv);
+
+/* BVHAccel::new(prims, max_prims_in_node, split_method) (bvh.rs:307-363): host build, flatten to
+ * the linear SoA layout, upload to HBM.                                                         */
+int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t build_flags);
+int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out);
+/* Primitive::world_bound (bvh.rs:177-182): out6 = p_min, p_max.                                 */
+int rrt_world_bound(const rrt_scene* scene, double out6[6]);
+/* Build statistics: nodes, leaves, max depth, bytes uploaded, host build seconds (x1e6).        */
+int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* Scene::intersect -> BVHAccel::intersect (scene.rs:69-72, bvh.rs:183-236) over a batch.
+ * rays / hits are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t,
+ * 0 = default stream).                                                                          */
+int rrt_intersect_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits,
+                         void* cuda_stream);
+/* Scene::intersect_p -> BVHAccel::intersect_p (scene.rs:75-80, bvh.rs:123-174): occluded[i] = 1
+ * when any primitive is hit within (0, t_max].                                                  */
+int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded,
+                           void* cuda_stream);
+/* Same two calls with HOST buffers: chunked, double-buffered H2D -> kernel -> D2H; returns when
+ * `hits` / `occluded` are complete.  This is the call a Rust `impl Primitive for GpuAggregate`
+ * binds.                                                                       */
+int rrt_intersect(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, rrt_hit* hits);
+int rrt_intersect_p(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, uint8_t* occluded);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRT_H_ */

@@ -1,0 +1,369 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rt_geom.hpp).
+//
+// C entry points so that tests/ (ctypes) and bench.py's cpu_baseline leg can drive the
+// CPU restatement.  Nothing in the product links or loads this file.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rt_bvh.hpp"
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+Xform xf_from(const double* m16, const double* inv16) {
+    Xform t;
+    std::memcpy(t.m.m, m16, 16 * sizeof(double));
+    std::memcpy(t.inv.m, inv16, 16 * sizeof(double));
+    return t;
+}
+Quirks quirks_from_mask(uint32_t mask) {
+    Quirks q;
+    q.fix_q1 = mask & 1u;
+    q.fix_q2 = mask & 2u;
+    q.fix_q3 = mask & 4u;
+    q.fix_q4 = mask & 8u;
+    q.fix_q5b = mask & 16u;
+    q.fix_q6 = mask & 32u;
+    q.fix_q8 = mask & 64u;
+    q.fix_q9 = mask & 128u;
+    return q;
+}
+struct Scene {
+    Geometry geom;
+    BVH bvh;
+    bool built = false;
+};
+template <class F>
+void parallel_for(uint64_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 1024) {
+        f(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    uint64_t per = (n + nthreads - 1) / nthreads;
+    for (int i = 0; i < nthreads; ++i) {
+        uint64_t b = per * i, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e, i); });
+    }
+    for (auto& t : th) t.join();
+}
+}  // namespace
+
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+// quirk_mask: bit i set = fix Q(1,2,3,4,5b,6,8,9)[i]; 0 = literal reference, 0xFF = Tier F.
+void* orc_scene_new(uint32_t quirk_mask) {
+    Scene* s = new Scene();
+    s->geom.q = quirks_from_mask(quirk_mask);
+    return s;
+}
+void orc_scene_free(void* s) { delete (Scene*)s; }
+
+// create_triangle_mesh (triangle.rs:131-165).  Index arrays are 0-based; pass n=0 / null
+// for absent normals / uvs.  Returns the mesh index.
+int32_t orc_add_mesh(void* sp, uint32_t nv, const double* p, uint32_t ntri, const uint32_t* vi, uint32_t nn,
+                     const double* n, const uint32_t* ni, uint32_t nuv, const double* uv, const uint32_t* uvi) {
+    Scene* s = (Scene*)sp;
+    TriMesh m;
+    m.p.resize(nv);
+    for (uint32_t i = 0; i < nv; ++i) m.p[i] = V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    m.vi.assign(vi, vi + 3 * (size_t)ntri);
+    if (nn && n) {
+        m.n.resize(nn);
+        for (uint32_t i = 0; i < nn; ++i) m.n[i] = V3(n[3 * i], n[3 * i + 1], n[3 * i + 2]);
+        if (ni) m.ni.assign(ni, ni + 3 * (size_t)ntri);
+    }
+    if (nuv && uv) {
+        m.uv.resize(nuv);
+        for (uint32_t i = 0; i < nuv; ++i) m.uv[i] = P2(uv[2 * i], uv[2 * i + 1]);
+        if (uvi) m.uvi.assign(uvi, uvi + 3 * (size_t)ntri);
+    }
+    s->geom.meshes.push_back(std::move(m));
+    return (int32_t)s->geom.meshes.size() - 1;
+}
+
+// Sphere::new (sphere.rs:28-47); o2w given as matrix + inverse (Transform carries both).
+int32_t orc_add_sphere(void* sp, const double* m16, const double* inv16, double radius, double z_min, double z_max,
+                       double phi_max_deg) {
+    Scene* s = (Scene*)sp;
+    Xform o2w = xf_from(m16, inv16);
+    s->geom.spheres.push_back(sphere_new(o2w, xf_inverse(o2w), radius, z_min, z_max, phi_max_deg));
+    return (int32_t)s->geom.spheres.size() - 1;
+}
+
+// One GeometricPrimitive per mesh triangle (renderprocess.rs:1255-1263). Returns first geo index.
+int32_t orc_add_geo_triangles(void* sp, int32_t mesh, int32_t material) {
+    Scene* s = (Scene*)sp;
+    int32_t first = (int32_t)s->geom.geos.size();
+    size_t nt = s->geom.meshes[mesh].n_triangles();
+    for (size_t i = 0; i < nt; ++i) s->geom.geos.push_back(GeoPrim{SHAPE_TRIANGLE, mesh, (int32_t)i, material});
+    return first;
+}
+int32_t orc_add_geo_sphere(void* sp, int32_t sphere, int32_t material) {
+    Scene* s = (Scene*)sp;
+    s->geom.geos.push_back(GeoPrim{SHAPE_SPHERE, sphere, 0, material});
+    return (int32_t)s->geom.geos.size() - 1;
+}
+int32_t orc_add_xform(void* sp, const double* m16, const double* inv16) {
+    Scene* s = (Scene*)sp;
+    s->geom.xforms.push_back(xf_from(m16, inv16));
+    return (int32_t)s->geom.xforms.size() - 1;
+}
+// Append `count` top-level primitives geo = first_geo..first_geo+count, wrapped in a
+// TransformedPrimitive when xf >= 0 (renderprocess.rs:1265-1281).
+void orc_add_prims(void* sp, int32_t first_geo, int32_t count, int32_t xf) {
+    Scene* s = (Scene*)sp;
+    for (int32_t i = 0; i < count; ++i) s->geom.prims.push_back(Prim{first_geo + i, xf});
+}
+uint32_t orc_num_prims(void* sp) { return (uint32_t)((Scene*)sp)->geom.prims.size(); }
+
+// BVHAccel::new(prims, max_prims_in_node, HLBVH).  0 = ok.
+int32_t orc_build(void* sp, uint32_t max_prims_in_node) {
+    Scene* s = (Scene*)sp;
+    try {
+        s->bvh.build(&s->geom, max_prims_in_node);
+        s->built = true;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+uint32_t orc_num_nodes(void* sp) { return (uint32_t)((Scene*)sp)->bvh.nodes.size(); }
+uint32_t orc_num_ordered(void* sp) { return (uint32_t)((Scene*)sp)->bvh.ordered.size(); }
+// bounds6[n*6] (lo,hi), meta[n*3] (offset, n_primitives, axis), ordered[num_ordered]
+void orc_get_nodes(void* sp, double* bounds6, uint32_t* meta3, uint32_t* ordered) {
+    Scene* s = (Scene*)sp;
+    for (size_t i = 0; i < s->bvh.nodes.size(); ++i) {
+        const LinearNode& n = s->bvh.nodes[i];
+        if (bounds6) {
+            double* b = bounds6 + 6 * i;
+            b[0] = n.bounds.lo.x; b[1] = n.bounds.lo.y; b[2] = n.bounds.lo.z;
+            b[3] = n.bounds.hi.x; b[4] = n.bounds.hi.y; b[5] = n.bounds.hi.z;
+        }
+        if (meta3) {
+            meta3[3 * i] = n.offset;
+            meta3[3 * i + 1] = n.n_primitives;
+            meta3[3 * i + 2] = n.axis;
+        }
+    }
+    if (ordered) std::memcpy(ordered, s->bvh.ordered.data(), s->bvh.ordered.size() * sizeof(uint32_t));
+}
+void orc_world_bound(void* sp, double* out6) {
+    B3 b = ((Scene*)sp)->bvh.world_bound();
+    out6[0] = b.lo.x; out6[1] = b.lo.y; out6[2] = b.lo.z;
+    out6[3] = b.hi.x; out6[4] = b.hi.y; out6[5] = b.hi.z;
+}
+
+// Scene::intersect over a batch (scene.rs:69-72 -> bvh.rs:183-236).
+// rays: n x 7 doubles (o, d, t_max) — d is used as given, like the reference's aggregate.
+// Outputs (any may be null): prim[n] (orig prim id, -1 miss), t[n], uv[n*2],
+// geom_out[n*9] = hit point p, geometric normal n, shading normal ns (world space).
+// stats5: rays, nodes_visited, prims_tested, max_stack, stack_overflow.
+int32_t orc_intersect(void* sp, uint64_t n, const double* rays, int32_t* prim, double* t, double* uv,
+                      double* geom_out, uint64_t* stats5, int32_t nthreads) {
+    Scene* s = (Scene*)sp;
+    if (!s->built) {
+        g_err = "orc_intersect: scene not built";
+        return -1;
+    }
+    std::vector<TraversalStats> st(std::max(1, nthreads));
+    std::atomic<int> failed{0};
+    std::string err;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int tid) {
+        try {
+            for (uint64_t i = b; i < e; ++i) {
+                const double* rr = rays + 7 * i;
+                Ray r;
+                r.o = V3(rr[0], rr[1], rr[2]);
+                r.d = V3(rr[3], rr[4], rr[5]);
+                r.t_max = rr[6];
+                HitRecord h;
+                SI si;
+                bool hit = s->bvh.intersect(r, &h, geom_out ? &si : nullptr, &st[tid]);
+                if (prim) prim[i] = hit ? h.prim : -1;
+                if (t) t[i] = hit ? h.t : 0.0;
+                if (uv) {
+                    uv[2 * i] = hit ? h.u : 0.0;
+                    uv[2 * i + 1] = hit ? h.v : 0.0;
+                }
+                if (geom_out) {
+                    double* g = geom_out + 9 * i;
+                    if (hit) {
+                        g[0] = si.p.x; g[1] = si.p.y; g[2] = si.p.z;
+                        g[3] = si.n.x; g[4] = si.n.y; g[5] = si.n.z;
+                        g[6] = si.sh.n.x; g[7] = si.sh.n.y; g[8] = si.sh.n.z;
+                    } else {
+                        for (int k = 0; k < 9; ++k) g[k] = 0.0;
+                    }
+                }
+            }
+        } catch (const std::exception& ex) {
+            if (!failed.exchange(1)) err = ex.what();
+        }
+    });
+    if (failed) {
+        g_err = err;
+        return -1;
+    }
+    if (stats5) {
+        TraversalStats tot;
+        for (auto& x : st) {
+            tot.rays += x.rays;
+            tot.nodes_visited += x.nodes_visited;
+            tot.prims_tested += x.prims_tested;
+            tot.max_stack = std::max(tot.max_stack, x.max_stack);
+            tot.stack_overflow += x.stack_overflow;
+        }
+        stats5[0] = tot.rays; stats5[1] = tot.nodes_visited; stats5[2] = tot.prims_tested;
+        stats5[3] = tot.max_stack; stats5[4] = tot.stack_overflow;
+    }
+    return 0;
+}
+
+// Scene::intersect_p over a batch (scene.rs:75-80 -> bvh.rs:123-174).
+int32_t orc_intersect_p(void* sp, uint64_t n, const double* rays, uint8_t* occluded, uint64_t* stats5,
+                        int32_t nthreads) {
+    Scene* s = (Scene*)sp;
+    if (!s->built) {
+        g_err = "orc_intersect_p: scene not built";
+        return -1;
+    }
+    std::vector<TraversalStats> st(std::max(1, nthreads));
+    std::atomic<int> failed{0};
+    std::string err;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int tid) {
+        try {
+            for (uint64_t i = b; i < e; ++i) {
+                const double* rr = rays + 7 * i;
+                Ray r;
+                r.o = V3(rr[0], rr[1], rr[2]);
+                r.d = V3(rr[3], rr[4], rr[5]);
+                r.t_max = rr[6];
+                occluded[i] = s->bvh.intersect_p(r, &st[tid]) ? 1 : 0;
+            }
+        } catch (const std::exception& ex) {
+            if (!failed.exchange(1)) err = ex.what();
+        }
+    });
+    if (failed) {
+        g_err = err;
+        return -1;
+    }
+    if (stats5) {
+        TraversalStats tot;
+        for (auto& x : st) {
+            tot.rays += x.rays;
+            tot.nodes_visited += x.nodes_visited;
+            tot.prims_tested += x.prims_tested;
+            tot.max_stack = std::max(tot.max_stack, x.max_stack);
+            tot.stack_overflow += x.stack_overflow;
+        }
+        stats5[0] = tot.rays; stats5[1] = tot.nodes_visited; stats5[2] = tot.prims_tested;
+        stats5[3] = tot.max_stack; stats5[4] = tot.stack_overflow;
+    }
+    return 0;
+}
+
+// Brute force over every top-level primitive (no BVH): the topology-independent checker.
+// Same accept rules as the Tier-F traversal (closest t, ties -> lowest prim id).
+int32_t orc_brute_force(void* sp, uint64_t n, const double* rays, int32_t* prim, double* t, int32_t nthreads) {
+    Scene* s = (Scene*)sp;
+    const Geometry& g = s->geom;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            const double* rr = rays + 7 * i;
+            Ray r;
+            r.o = V3(rr[0], rr[1], rr[2]);
+            r.d = V3(rr[3], rr[4], rr[5]);
+            r.t_max = rr[6];
+            int32_t best = -1;
+            for (size_t pi = 0; pi < g.prims.size(); ++pi) {
+                Ray q = r;
+                double u, v;
+                if (g.prim_intersect(g.prims[pi], q, &u, &v, nullptr, false)) {
+                    if (best < 0 || q.t_max < r.t_max) {
+                        best = (int32_t)pi;
+                        r.t_max = q.t_max;
+                    }
+                }
+            }
+            prim[i] = best;
+            t[i] = best >= 0 ? r.t_max : 0.0;
+        }
+    });
+    return 0;
+}
+
+// ---- known-answer-test hooks (geometry.rs tests, bvh.rs helpers) -------------------------
+void orc_kat_vec3(const double* a3, const double* b3, double s, double* out) {
+    V3 a(a3[0], a3[1], a3[2]), b(b3[0], b3[1], b3[2]);
+    out[0] = length_sq(a);
+    V3 m = a * s;
+    out[1] = m.x; out[2] = m.y; out[3] = m.z;
+    out[4] = dot(a, b);
+    V3 c = cross(a, b);
+    out[5] = c.x; out[6] = c.y; out[7] = c.z;
+}
+void orc_kat_bounds(const double* p1, const double* p2, const double* p3, double* out10) {
+    B3 b = b3_new(V3(p1[0], p1[1], p1[2]), V3(p2[0], p2[1], p2[2]));
+    b = b3_union(b, V3(p3[0], p3[1], p3[2]));
+    out10[0] = b.lo.x; out10[1] = b.lo.y; out10[2] = b.lo.z;
+    out10[3] = b.hi.x; out10[4] = b.hi.y; out10[5] = b.hi.z;
+    V3 c;
+    double r;
+    b3_bounding_sphere(b, &c, &r);
+    out10[6] = c.x; out10[7] = c.y; out10[8] = c.z; out10[9] = r;
+}
+uint32_t orc_kat_left_shift3(uint32_t x) { return left_shift3(x); }
+uint32_t orc_kat_morton(double x, double y, double z) { return encode_morton3(V3(x, y, z)); }
+void orc_kat_radix_sort(uint32_t n, uint32_t* idx, uint32_t* codes) {
+    std::vector<MortonPrim> v(n);
+    for (uint32_t i = 0; i < n; ++i) v[i] = MortonPrim{idx[i], codes[i]};
+    radix_sort(v);
+    for (uint32_t i = 0; i < n; ++i) {
+        idx[i] = v[i].primitive_index;
+        codes[i] = v[i].morton_code;
+    }
+}
+// make_to_world (renderprocess.rs:242-252): translate * rotate(angle, normalize(axis)) * scale
+void orc_make_to_world(const double* pos3, const double* axis3, double angle_deg, const double* scale3, double* m16,
+                       double* inv16) {
+    V3 axis = normalize_vec(V3(axis3[0], axis3[1], axis3[2]));
+    Xform t = xf_mul(xf_mul(xf_translate(V3(pos3[0], pos3[1], pos3[2])), xf_rotate(angle_deg, axis)),
+                     xf_scale(scale3[0], scale3[1], scale3[2]));
+    std::memcpy(m16, t.m.m, sizeof(t.m.m));
+    std::memcpy(inv16, t.inv.m, sizeof(t.inv.m));
+}
+void orc_m44_inverse(const double* m16, double* out16) {
+    M44 m;
+    std::memcpy(m.m, m16, sizeof(m.m));
+    M44 r = m44_inverse(m);
+    std::memcpy(out16, r.m, sizeof(r.m));
+}
+// Ray::new_od helper: returns the normalised direction exactly as the reference would.
+void orc_normalize(const double* v3, double* out3) {
+    V3 n = normalize_vec(V3(v3[0], v3[1], v3[2]));
+    out3[0] = n.x; out3[1] = n.y; out3[2] = n.z;
+}
+// Single-primitive tests (primitives.rs test_primitive / sphere.rs test_sphere).
+int32_t orc_prim_intersect_p(void* sp, uint32_t prim, const double* ray7) {
+    Scene* s = (Scene*)sp;
+    Ray r;
+    r.o = V3(ray7[0], ray7[1], ray7[2]);
+    r.d = V3(ray7[3], ray7[4], ray7[5]);
+    r.t_max = ray7[6];
+    return s->geom.prim_intersect_p(s->geom.prims[prim], r) ? 1 : 0;
+}
+int32_t orc_hardware_threads() { return (int32_t)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+"""Builds librrt_sm100.so in-tree with nvcc for sm_100a (no other architecture, no JIT cache).
+
+`python -m rs_ray_toy_b200.build` or `build_library()`; `__graft_entry__.build()` calls this.
+The .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "librrt_sm100.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "-shared",
+    "-Xcompiler", "-fPIC,-O3,-pthread,-Wall,-Wno-unused-function",
+    "--fmad=true",  # fp32 culling may fuse; every f64 op that decides a result uses explicit __d*_rn
+    "-Xptxas", "-v",
+]
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
+
+
+def is_stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*")) + [PKG.parent / "include" / "rrt.h", Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not is_stale():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        if LIB.exists():
+            return LIB  # GPU box without a toolchain: use the prebuilt library that travelled with the repo
+        raise RuntimeError("nvcc not found and no prebuilt librrt_sm100.so")
+    tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-o", str(tmp), *map(str, sources()), "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    (PKG / "ptxas_report.txt").write_text(r.stdout + r.stderr)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

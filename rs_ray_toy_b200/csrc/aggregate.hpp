@@ -1,0 +1,55 @@
+// The GPU aggregate: device-resident tree + primitive records and the launchers of the
+// closest-hit / any-hit kernels.  Host-visible part (no CUDA types in the interface besides
+// the opaque stream pointer) so capi.cpp can be compiled by the plain host compiler.
+#pragma once
+#include <cstdint>
+#include <string>
+
+#include "../../include/rrt.h"
+#include "bvh_sah.hpp"
+#include "host_scene.hpp"
+
+namespace rrt {
+
+struct AggregateStats {
+    uint64_t n_nodes = 0, n_leaves = 0, max_depth = 0, device_bytes = 0, build_usec = 0, n_records = 0,
+             wide_records = 0, n_prims = 0;
+};
+
+// Kernel-side view, passed by value to every launch.
+struct AggView {
+    const void* nodes;   // Node64[]
+    const void* prims;   // PrimRec48[] or PrimRec96[]
+    double world_lo[3];  // tight world box of the tree, used to pull far-away origins close
+    double world_hi[3];
+    double scene_scale;  // max |coordinate| of the world box
+    int32_t root;        // interior node index of the root (always 0)
+    int32_t wide;        // 1 => PrimRec96
+};
+
+class DeviceAggregate {
+  public:
+    DeviceAggregate() = default;
+    ~DeviceAggregate();
+    DeviceAggregate(const DeviceAggregate&) = delete;
+    DeviceAggregate& operator=(const DeviceAggregate&) = delete;
+
+    // Bake primitives to world space, build the SAH tree, pack Node64 / PrimRec and upload.
+    // Returns an rrt_status; on failure *err holds the reason.
+    int build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err);
+
+    int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err) const;
+    int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err) const;
+
+    const AggView& view() const { return view_; }
+    const AggregateStats& stats() const { return stats_; }
+
+  private:
+    AggView view_{};
+    AggregateStats stats_{};
+    void* d_nodes_ = nullptr;
+    void* d_prims_ = nullptr;
+    int device_ = 0;
+};
+
+}  // namespace rrt

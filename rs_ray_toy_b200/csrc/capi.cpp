@@ -1,0 +1,354 @@
+// C ABI of librrt_sm100.so (include/rrt.h): context, scene assembly, and the batch
+// intersect entry points that stand where Scene::intersect / intersect_p
+// (src/scene.rs:69-80) stand in the reference.  No exception leaves this file.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "aggregate.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(const char* what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return RRT_ERR_CUDA;
+}
+#define CAPI_CUDA(call)                                   \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(#call, e_); \
+    } while (0)
+
+constexpr int kSlots = 3;                  // pipeline depth of the host-buffer calls
+constexpr uint64_t kChunkRays = 1u << 20;  // 64 MiB of rays per slot
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    rrt_ray* d_rays = nullptr;
+    void* d_out = nullptr;  // rrt_hit[kChunkRays] (also large enough for the any-hit bytes)
+};
+
+}  // namespace
+
+struct rrt_ctx {
+    int device = 0;
+    std::atomic<uint64_t> launches{0};
+    std::mutex host_path_mutex;  // the staging slots are shared by host-buffer calls
+    Slot slots[kSlots];
+    bool slots_ready = false;
+
+    int ensure_slots() {
+        if (slots_ready) return RRT_OK;
+        CAPI_CUDA(cudaSetDevice(device));
+        for (auto& s : slots) {
+            CAPI_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CAPI_CUDA(cudaMalloc(&s.d_rays, kChunkRays * sizeof(rrt_ray)));
+            CAPI_CUDA(cudaMalloc(&s.d_out, kChunkRays * sizeof(rrt_hit)));
+        }
+        slots_ready = true;
+        return RRT_OK;
+    }
+    ~rrt_ctx() {
+        cudaSetDevice(device);
+        for (auto& s : slots) {
+            if (s.d_rays) cudaFree(s.d_rays);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+    }
+};
+
+struct rrt_scene {
+    rrt_ctx* ctx = nullptr;
+    rrt::HostScene host;
+    std::unique_ptr<rrt::DeviceAggregate> agg;
+    bool committed = false;
+    uint32_t build_flags = 0;
+};
+
+namespace {
+
+rrt::Transform xf_from(const double* m, const double* inv) {
+    rrt::Transform t;
+    std::memcpy(t.m.m, m, sizeof(double) * 16);
+    std::memcpy(t.inv.m, inv, sizeof(double) * 16);
+    return t;
+}
+
+template <bool ANY>
+int host_batch(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, void* out) {
+    if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "scene is not committed");
+    if (n == 0) return RRT_OK;
+    if (!rays || !out) return fail(RRT_ERR_INVALID, "null ray / output buffer");
+    rrt_ctx* ctx = scene->ctx;
+    std::lock_guard<std::mutex> lock(ctx->host_path_mutex);
+    int rc = ctx->ensure_slots();
+    if (rc != RRT_OK) return rc;
+    CAPI_CUDA(cudaSetDevice(ctx->device));
+    const size_t out_elem = ANY ? sizeof(uint8_t) : sizeof(rrt_hit);
+    std::string err;
+    uint64_t done = 0;
+    int k = 0;
+    while (done < n) {
+        Slot& s = ctx->slots[k % kSlots];
+        uint64_t cnt = n - done < kChunkRays ? n - done : kChunkRays;
+        // a slot is reused only after its previous D2H has drained (stream order)
+        CAPI_CUDA(cudaMemcpyAsync(s.d_rays, rays + done, cnt * sizeof(rrt_ray), cudaMemcpyHostToDevice, s.stream));
+        if (ANY)
+            rc = scene->agg->any_hit(cnt, s.d_rays, static_cast<uint8_t*>(s.d_out), s.stream, &err);
+        else
+            rc = scene->agg->closest_hit(cnt, s.d_rays, static_cast<rrt_hit*>(s.d_out), s.stream, &err);
+        if (rc != RRT_OK) return fail(rc, err);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        CAPI_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + done * out_elem, s.d_out, cnt * out_elem,
+                                  cudaMemcpyDeviceToHost, s.stream));
+        done += cnt;
+        ++k;
+    }
+    for (auto& s : ctx->slots) CAPI_CUDA(cudaStreamSynchronize(s.stream));
+    return RRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rrt_last_error(void) { return g_last_error.c_str(); }
+
+int rrt_create(int device_ordinal, rrt_ctx** out) {
+    if (!out) return fail(RRT_ERR_INVALID, "rrt_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail("cudaGetDeviceCount", e);
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return fail(RRT_ERR_INVALID, "rrt_create: no CUDA device " + std::to_string(device_ordinal) +
+                                         " (this library has no CPU path)");
+    cudaDeviceProp prop;
+    CAPI_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10)
+        return fail(RRT_ERR_UNSUPPORTED, std::string("rrt_create: built for sm_100a only, device is ") + prop.name);
+    CAPI_CUDA(cudaSetDevice(device_ordinal));
+    rrt_ctx* c = new (std::nothrow) rrt_ctx();
+    if (!c) return fail(RRT_ERR_INVALID, "out of host memory");
+    c->device = device_ordinal;
+    *out = c;
+    return RRT_OK;
+}
+
+void rrt_destroy(rrt_ctx* ctx) { delete ctx; }
+
+uint64_t rrt_launch_count(const rrt_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int rrt_host_alloc(rrt_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return fail(RRT_ERR_INVALID, "rrt_host_alloc: null argument");
+    CAPI_CUDA(cudaSetDevice(ctx->device));
+    CAPI_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return RRT_OK;
+}
+int rrt_host_free(rrt_ctx* ctx, void* p) {
+    if (!ctx) return fail(RRT_ERR_INVALID, "rrt_host_free: null ctx");
+    CAPI_CUDA(cudaFreeHost(p));
+    return RRT_OK;
+}
+
+int rrt_scene_begin(rrt_ctx* ctx, rrt_scene** out) {
+    if (!ctx || !out) return fail(RRT_ERR_INVALID, "rrt_scene_begin: null argument");
+    rrt_scene* s = new (std::nothrow) rrt_scene();
+    if (!s) return fail(RRT_ERR_INVALID, "out of host memory");
+    s->ctx = ctx;
+    *out = s;
+    return RRT_OK;
+}
+void rrt_scene_destroy(rrt_scene* scene) {
+    if (scene) cudaSetDevice(scene->ctx->device);
+    delete scene;
+}
+
+int rrt_scene_add_mesh(rrt_scene* scene, uint32_t nv, const double* p, uint32_t ntri, const uint32_t* vi, uint32_t nn,
+                       const double* n, const uint32_t* ni, uint32_t nuv, const double* uv, const uint32_t* uvi,
+                       uint32_t* mesh_id) {
+    if (!scene || scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_add_mesh: scene missing or committed");
+    if (!p || !vi || nv == 0 || ntri == 0) return fail(RRT_ERR_INVALID, "rrt_scene_add_mesh: empty mesh");
+    try {
+        rrt::TriangleMesh m;
+        m.p.assign(p, p + 3 * (size_t)nv);
+        m.vi.assign(vi, vi + 3 * (size_t)ntri);
+        for (uint32_t x : m.vi)
+            if (x >= nv) return fail(RRT_ERR_INVALID, "rrt_scene_add_mesh: vertex index out of range");
+        if (nn && n && ni) {
+            m.n.assign(n, n + 3 * (size_t)nn);
+            m.ni.assign(ni, ni + 3 * (size_t)ntri);
+            for (uint32_t x : m.ni)
+                if (x >= nn) return fail(RRT_ERR_INVALID, "rrt_scene_add_mesh: normal index out of range");
+        }
+        if (nuv && uv && uvi) {
+            m.uv.assign(uv, uv + 2 * (size_t)nuv);
+            m.uvi.assign(uvi, uvi + 3 * (size_t)ntri);
+            for (uint32_t x : m.uvi)
+                if (x >= nuv) return fail(RRT_ERR_INVALID, "rrt_scene_add_mesh: uv index out of range");
+        }
+        scene->host.meshes.push_back(std::move(m));
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    if (mesh_id) *mesh_id = (uint32_t)scene->host.meshes.size() - 1;
+    return RRT_OK;
+}
+
+int rrt_scene_add_triangles(rrt_scene* scene, uint32_t mesh_id, uint32_t material_id, uint32_t n_instances,
+                            const double* instance_m, const double* instance_minv) {
+    if (!scene || scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_add_triangles: scene missing or committed");
+    if (mesh_id >= scene->host.meshes.size()) return fail(RRT_ERR_INVALID, "rrt_scene_add_triangles: bad mesh id");
+    if (n_instances && (!instance_m || !instance_minv))
+        return fail(RRT_ERR_INVALID, "rrt_scene_add_triangles: instance matrices missing");
+    try {
+        const uint32_t nt = scene->host.meshes[mesh_id].n_triangles();
+        auto& prims = scene->host.prims;
+        if (n_instances == 0) {
+            for (uint32_t t = 0; t < nt; ++t) prims.push_back({rrt::SHAPE_TRIANGLE, mesh_id, t, -1, material_id});
+        } else {
+            // renderprocess.rs:1265-1281: for each instance, every triangle of the mesh
+            for (uint32_t i = 0; i < n_instances; ++i) {
+                scene->host.instances.push_back(xf_from(instance_m + 16 * (size_t)i, instance_minv + 16 * (size_t)i));
+                int32_t xi = (int32_t)scene->host.instances.size() - 1;
+                for (uint32_t t = 0; t < nt; ++t) prims.push_back({rrt::SHAPE_TRIANGLE, mesh_id, t, xi, material_id});
+            }
+        }
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
+int rrt_scene_add_sphere(rrt_scene* scene, const double* obj_to_world_m, const double* obj_to_world_minv, double radius,
+                         double z_min, double z_max, double phi_max_deg, uint32_t material_id, uint32_t n_instances,
+                         const double* instance_m, const double* instance_minv) {
+    if (!scene || scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_add_sphere: scene missing or committed");
+    if (n_instances && (!instance_m || !instance_minv))
+        return fail(RRT_ERR_INVALID, "rrt_scene_add_sphere: instance matrices missing");
+    try {
+        rrt::Sphere s;
+        s.obj_to_world = (obj_to_world_m && obj_to_world_minv) ? xf_from(obj_to_world_m, obj_to_world_minv)
+                                                               : rrt::Transform::identity();
+        s.radius = radius;
+        s.z_min = z_min;
+        s.z_max = z_max;
+        s.phi_max_deg = phi_max_deg;
+        scene->host.spheres.push_back(s);
+        uint32_t sid = (uint32_t)scene->host.spheres.size() - 1;
+        auto& prims = scene->host.prims;
+        if (n_instances == 0) {
+            prims.push_back({rrt::SHAPE_SPHERE, sid, 0, -1, material_id});
+        } else {
+            for (uint32_t i = 0; i < n_instances; ++i) {
+                scene->host.instances.push_back(xf_from(instance_m + 16 * (size_t)i, instance_minv + 16 * (size_t)i));
+                prims.push_back({rrt::SHAPE_SPHERE, sid, 0, (int32_t)scene->host.instances.size() - 1, material_id});
+            }
+        }
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
+int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t build_flags) {
+    if (!scene) return fail(RRT_ERR_INVALID, "rrt_scene_commit: null scene");
+    if (scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_commit: already committed");
+    if (build_flags != RRT_BUILD_FAST)
+        return fail(RRT_ERR_UNSUPPORTED,
+                    "rrt_scene_commit: only RRT_BUILD_FAST (Tier F) runs on the device; the literal tier lives in the "
+                    "test oracle (DESIGN.md)");
+    try {
+        std::string err;
+        scene->agg.reset(new rrt::DeviceAggregate());
+        int rc = scene->agg->build(scene->ctx->device, scene->host, max_prims_in_node, &err);
+        if (rc != RRT_OK) {
+            scene->agg.reset();
+            return fail(rc, err);
+        }
+    } catch (const std::exception& e) {
+        scene->agg.reset();
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    scene->build_flags = build_flags;
+    scene->committed = true;
+    return RRT_OK;
+}
+
+int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out) {
+    if (!scene || !out) return fail(RRT_ERR_INVALID, "rrt_scene_num_prims: null argument");
+    *out = (uint32_t)scene->host.prims.size();
+    return RRT_OK;
+}
+
+int rrt_world_bound(const rrt_scene* scene, double out6[6]) {
+    if (!scene || !out6) return fail(RRT_ERR_INVALID, "rrt_world_bound: null argument");
+    if (scene->host.prims.empty()) return fail(RRT_ERR_EMPTY, "rrt_world_bound: no primitives");
+    // BVHAccel::world_bound = root bounds = union of every Primitive::world_bound (bvh.rs:177-182)
+    rrt::Aabb b;
+    for (size_t i = 0; i < scene->host.prims.size(); ++i) b.grow(scene->host.reference_world_bound(i));
+    for (int k = 0; k < 3; ++k) {
+        out6[k] = b.lo[k];
+        out6[3 + k] = b.hi[k];
+    }
+    return RRT_OK;
+}
+
+int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]) {
+    if (!scene || !out8 || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_stats: scene not committed");
+    const rrt::AggregateStats& s = scene->agg->stats();
+    out8[0] = s.n_nodes;
+    out8[1] = s.n_leaves;
+    out8[2] = s.max_depth;
+    out8[3] = s.device_bytes;
+    out8[4] = s.build_usec;
+    out8[5] = s.n_records;
+    out8[6] = s.wide_records;
+    out8[7] = s.n_prims;
+    return RRT_OK;
+}
+
+int rrt_intersect_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* cuda_stream) {
+    if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_intersect_device: scene is not committed");
+    if (n == 0) return RRT_OK;
+    if (!d_rays || !d_hits) return fail(RRT_ERR_INVALID, "rrt_intersect_device: null buffer");
+    std::string err;
+    int rc = scene->agg->closest_hit(n, d_rays, d_hits, cuda_stream, &err);
+    if (rc != RRT_OK) return fail(rc, err);
+    scene->ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return RRT_OK;
+}
+
+int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded,
+                           void* cuda_stream) {
+    if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_intersect_p_device: scene is not committed");
+    if (n == 0) return RRT_OK;
+    if (!d_rays || !d_occluded) return fail(RRT_ERR_INVALID, "rrt_intersect_p_device: null buffer");
+    std::string err;
+    int rc = scene->agg->any_hit(n, d_rays, d_occluded, cuda_stream, &err);
+    if (rc != RRT_OK) return fail(rc, err);
+    scene->ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return RRT_OK;
+}
+
+int rrt_intersect(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, rrt_hit* hits) {
+    return host_batch<false>(scene, n, rays, hits);
+}
+int rrt_intersect_p(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, uint8_t* occluded) {
+    return host_batch<true>(scene, n, rays, occluded);
+}
+
+}  // extern "C"

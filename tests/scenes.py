@@ -1,0 +1,89 @@
+"""Scene builders shared by the parity tests: the SAME arrays go to the CPU oracle and to
+the CUDA library (through its C ABI), so any disagreement is arithmetic, not input."""
+import numpy as np
+
+import oracle_lib as O
+from rs_ray_toy_b200 import synth, transform
+
+
+def soup(n_tris, edge=0.01, seed=synth.SEED_C3_SOUP):
+    return synth.soup_triangles(n_tris, edge, seed)
+
+
+def oracle_soup(p, idx, tier=O.TIER_F, max_prims=4):
+    return O.soup_scene(p, idx, tier, max_prims)
+
+
+def gpu_soup(ctx, p, idx, max_prims=4):
+    from rs_ray_toy_b200.aggregate import soup_aggregate
+    return soup_aggregate(ctx, p, idx, max_prims)
+
+
+def cube_instances(n, extent=50.0, seed=synth.SEED_C2_INSTANCES):
+    prm = synth.instance_params(n, extent, seed)
+    return transform.make_to_world_batch(prm["world_pos"], prm["axis"], prm["angle"])
+
+
+def oracle_cubes(m, inv, tier=O.TIER_F, max_prims=4):
+    """config 2: samples/cube.obj instanced n times (renderprocess.rs:1228-1282)."""
+    s = O.OracleScene(tier)
+    mesh = s.add_mesh(synth.CUBE_P, synth.CUBE_VI, synth.CUBE_N, synth.CUBE_NI)
+    g0 = s.add_geo_triangles(mesh)
+    for i in range(m.shape[0]):
+        s.add_prims(g0, 12, s.add_xform(m[i], inv[i]))
+    s.build(max_prims)
+    return s
+
+
+def gpu_cubes(ctx, m, inv, max_prims=4):
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    a = GpuAggregate(ctx)
+    mesh = a.add_mesh(synth.CUBE_P, synth.CUBE_VI, synth.CUBE_N, synth.CUBE_NI)
+    a.add_triangles(mesh, 0, instances=(m, inv))
+    return a.commit(max_prims)
+
+
+def sphere_instances(n, extent=50.0, seed=synth.SEED_C4_SPHERES):
+    prm = synth.instance_params(n, extent, seed, rotate=False)
+    return transform.make_to_world_batch(prm["world_pos"], prm["axis"], prm["angle"])
+
+
+def oracle_spheres(m, inv, radius=0.5, tier=O.TIER_F, max_prims=4):
+    """config 4: an identity sphere placed through instances[] (Q5a)."""
+    s = O.OracleScene(tier)
+    sp = s.add_sphere(None, None, radius)
+    g = s.add_geo_sphere(sp)
+    for i in range(m.shape[0]):
+        s.add_prims(g, 1, s.add_xform(m[i], inv[i]))
+    s.build(max_prims)
+    return s
+
+
+def gpu_spheres(ctx, m, inv, radius=0.5, max_prims=4):
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    a = GpuAggregate(ctx)
+    a.add_sphere(radius=radius, instances=(m, inv))
+    return a.commit(max_prims)
+
+
+def compare_closest(hits, ref_prim, ref_t, rel_tie=1e-6, rel_t=1e-5):
+    """north_star's bar: primitive index bit-exact except rays whose two best candidates tie
+    within 1e-6 relative (none of those appear unless t differs); t within 1e-5 relative.
+    Returns a dict of counts; asserts nothing."""
+    gp = hits["prim_id"].astype(np.int64)
+    gp[gp == 0xFFFFFFFF] = -1
+    same = gp == ref_prim
+    hit = ref_prim >= 0
+    both = hit & (gp >= 0)
+    dt = np.zeros(len(gp))
+    dt[both] = np.abs(hits["t"][both] - ref_t[both]) / np.maximum(np.abs(ref_t[both]), 1e-300)
+    ties = (~same) & both & (dt <= rel_tie)
+    return {
+        "n": len(gp),
+        "mismatch": int((~same).sum()),
+        "mismatch_excl_ties": int(((~same) & ~ties).sum()),
+        "t_bad": int((both & same & (dt > rel_t)).sum()),
+        "t_exact": int((both & same & (hits["t"] == ref_t)).sum()),
+        "hits": int(hit.sum()),
+        "max_rel_dt": float(dt[both & same].max()) if (both & same).any() else 0.0,
+    }

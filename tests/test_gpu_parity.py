@@ -1,0 +1,182 @@
+"""-m gpu: the CUDA aggregate (through the C ABI) against the CPU oracle and the committed
+golden vectors.  Bar (BASELINE.json north_star): closest-hit primitive index bit-exact except
+rays whose candidates tie within 1e-6 relative; t within 1e-5 relative (the kernels decide in
+f64 with the reference's operation order, so t, u, v are expected to be bit-identical and the
+tests record how many are); any-hit flags bit-exact."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import golden_cases
+import scenes
+from rs_ray_toy_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REL_T = 1e-5
+REL_TIE = 1e-6
+
+
+def _assert_closest(hits, prim, t, uv=None):
+    c = scenes.compare_closest(hits, prim, t, REL_TIE, REL_T)
+    assert c["mismatch_excl_ties"] == 0, c
+    assert c["t_bad"] == 0, c
+    if uv is not None:
+        ok = (hits["prim_id"].astype(np.int64) == prim) & (prim >= 0)
+        assert np.allclose(hits["u"][ok], uv[ok, 0], rtol=1e-5, atol=1e-9)
+        assert np.allclose(hits["v"][ok], uv[ok, 1], rtol=1e-5, atol=1e-9)
+    return c
+
+
+@pytest.mark.parametrize("name", list(golden_cases.CASES))
+def test_golden_closest_and_any_hit(ctx, name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    agg, rays = golden_cases.build_gpu(ctx, name)
+    assert (rays == g["rays"]).all()
+    hits = agg.intersect(rays)
+    c = _assert_closest(hits, g["prim"], g["t"], g["uv"])
+    assert c["mismatch"] == 0, c                    # no ties in the fixtures: exact
+    assert c["t_exact"] == c["hits"], c              # f64 deciding arithmetic: same bits
+    occ = agg.intersect_p(golden_cases.shadow_rays(name, rays))
+    assert (occ == g["occluded"]).all()
+
+
+def test_soup_vs_oracle_200k(ctx):
+    import oracle_lib as O
+    p, idx = scenes.soup(200000)
+    rays = synth.bounce_rays(p, idx, 200000, seed=41)
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    hits = agg.intersect(rays)
+    c = _assert_closest(hits, ref["prim"], ref["t"], ref["uv"])
+    assert c["hits"] > 50000
+    sh = synth.shadow_rays_from(rays, (0.5, 0.5, 1.5))
+    occ_ref, _ = scenes.oracle_soup(p, idx).intersect_p(sh)
+    assert (agg.intersect_p(sh) == occ_ref).all()
+
+
+def test_edge_cases(ctx):
+    import oracle_lib as O
+    p, idx = scenes.soup(5000)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    ref = scenes.oracle_soup(p, idx)
+    # empty batch
+    assert agg.intersect(np.zeros((0, 7))).shape == (0,)
+    assert agg.intersect_p(np.zeros((0, 7))).shape == (0,)
+    # ragged sizes around the block / chunk boundaries, finite t_max, far origins, axis-parallel
+    # directions (zero components -> infinite slabs), rays pointing away
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 127, 129, 1000):
+        rays = synth.bounce_rays(p, idx, n, seed=100 + n)
+        rays[:, 6] = np.where(rng.random(n) < 0.5, rng.uniform(0.001, 0.3, n), np.inf)
+        r = ref.intersect(rays)
+        _assert_closest(agg.intersect(rays), r["prim"], r["t"])
+    rays = np.zeros((600, 7))
+    rays[:, 6] = np.inf
+    rays[:200, 0:3] = rng.uniform(-1000, 1000, (200, 3))           # far outside the world box
+    tgt = rng.uniform(0, 1, (200, 3))
+    d = tgt - rays[:200, 0:3]
+    rays[:200, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[200:400, 0:3] = rng.uniform(0, 1, (200, 3))                # axis-parallel
+    ax = rng.integers(0, 3, 200)
+    rays[200 + np.arange(200), 3 + ax] = rng.choice([-1.0, 1.0], 200)
+    rays[400:, 0:3] = rng.uniform(2, 3, (200, 3))                   # pointing away
+    rays[400:, 3:6] = np.array([1.0, 0.0, 0.0])
+    r = ref.intersect(rays)
+    c = _assert_closest(agg.intersect(rays), r["prim"], r["t"])
+    assert c["hits"] > 50
+    occ_ref, _ = ref.intersect_p(rays)
+    assert (agg.intersect_p(rays) == occ_ref).all()
+    # unnormalised directions: t scales, the hit does not change
+    rays2 = synth.bounce_rays(p, idx, 2000, seed=77)
+    rays2[:, 3:6] *= 3.0
+    r = ref.intersect(rays2)
+    _assert_closest(agg.intersect(rays2), r["prim"], r["t"])
+
+
+def test_single_primitive_and_one_leaf_scenes(ctx):
+    import oracle_lib as O
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    for ntri in (1, 3, 4, 5):
+        p, idx = scenes.soup(ntri, edge=0.3, seed=9)
+        agg = scenes.gpu_soup(ctx, p, idx)
+        ref = scenes.oracle_soup(p, idx)
+        rays = synth.camera_like_rays(3000, (0.5, 0.5, -2.0), 0.6, seed=3)
+        rays[:, 0:3] += 0.0
+        rays[:, 3:6] = (np.random.default_rng(1).uniform(0, 1, (3000, 3)) - rays[:, 0:3])
+        rays[:, 3:6] /= np.linalg.norm(rays[:, 3:6], axis=1, keepdims=True)
+        r = ref.intersect(rays)
+        _assert_closest(agg.intersect(rays), r["prim"], r["t"])
+
+
+def test_empty_scene_is_an_error(ctx):
+    from rs_ray_toy_b200 import capi
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    a = GpuAggregate(ctx)
+    with pytest.raises(capi.RrtError) as e:
+        a.commit()
+    assert e.value.status == capi.RRT_ERR_EMPTY     # bvh.rs:319 asserts
+
+
+def test_instanced_cubes_c2_vs_oracle(ctx):
+    m, inv = scenes.cube_instances(10000)            # config 2's 120,000 TransformedPrimitives
+    agg = scenes.gpu_cubes(ctx, m, inv)
+    ref = scenes.oracle_cubes(m, inv)
+    assert agg.num_prims == 120000
+    assert np.allclose(agg.world_bound(), ref.world_bound(), rtol=0, atol=0)
+    rays = synth.camera_like_rays(300000, (0.0, 0.0, -200.0), 50.0)
+    r = ref.intersect(rays)
+    c = _assert_closest(agg.intersect(rays), r["prim"], r["t"])
+    assert c["hits"] > 100000
+
+
+def test_sphere_field_c4_vs_oracle(ctx):
+    m, inv = scenes.sphere_instances(100000)          # config 4's sphere field
+    agg = scenes.gpu_spheres(ctx, m, inv)
+    ref = scenes.oracle_spheres(m, inv)
+    rays = synth.camera_like_rays(300000, (0.0, 0.0, -120.0), 50.0)
+    r = ref.intersect(rays)
+    c = _assert_closest(agg.intersect(rays), r["prim"], r["t"])
+    assert c["hits"] > 100000
+    # secondary rays leaving sphere surfaces: the self-hit policy (Q8) must agree
+    hit = r["prim"] >= 0
+    o = rays[hit, 0:3] + rays[hit, 3:6] * r["t"][hit, None]
+    centre = m[r["prim"][hit], 0:3, 3]
+    nrm = (o - centre) / 0.5
+    rng = np.random.default_rng(2)
+    d = synth.random_unit_vectors(o.shape[0], rng)
+    d[np.sum(d * nrm, axis=1) < 0] *= -1.0
+    sec = np.concatenate([o, d, np.full((o.shape[0], 1), np.inf)], axis=1)
+    r2 = ref.intersect(sec)
+    _assert_closest(agg.intersect(sec), r2["prim"], r2["t"])
+    occ_ref, _ = ref.intersect_p(sec)
+    assert (agg.intersect_p(sec) == occ_ref).all()
+
+
+def test_full_size_properties_c3(ctx):
+    """BASELINE config 3 at full size (1M triangles, 16M rays) through size-independent
+    properties: (1) a 64k-ray slice equals the oracle; (2) re-tracing every hit ray with
+    t_max = t*(1+1e-9) returns the same primitive and t (idempotence of closest hit);
+    (3) with t_max = t*(1-1e-6) the winner disappears: the new hit, if any, is farther... no —
+    must be a miss or a hit with t' < t_max; (4) any-hit == (closest-hit found something)."""
+    p, idx = scenes.soup(1 << 20)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    n = 1 << 24
+    rays = synth.bounce_rays(p, idx, n)
+    hits = agg.intersect(rays)
+    hit = hits["prim_id"] != 0xFFFFFFFF
+    assert 0.3 < hit.mean() < 1.0
+    ref = scenes.oracle_soup(p, idx).intersect(rays[: 1 << 16])
+    _assert_closest(hits[: 1 << 16], ref["prim"], ref["t"], ref["uv"])
+    occ = agg.intersect_p(rays)
+    assert (occ.astype(bool) == hit).all()
+    again = rays.copy()
+    again[hit, 6] = hits["t"][hit] * (1.0 + 1e-9)
+    h2 = agg.intersect(again)
+    assert (h2["prim_id"] == hits["prim_id"]).all() and (h2["t"][hit] == hits["t"][hit]).all()
+    short = rays[hit].copy()
+    short[:, 6] = hits["t"][hit] * (1.0 - 1e-6)
+    h3 = agg.intersect(short)
+    got = h3["prim_id"] != 0xFFFFFFFF
+    assert not got.any(), int(got.sum())   # nothing lies in front of the closest hit
