@@ -43,12 +43,12 @@ NT_C3 = 20.02
 BYTES_PER_RAY = 32 + 16 + 32 * NV_C3 + 36 * NT_C3
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, n_rays=N_RAYS):
     return {
         "workload": "config 3: synthetic 1M-triangle random-soup mesh (v0~U[0,1]^3, edges U[-0.01,0.01]^3, seed 3), "
                     "16,777,216 incoherent cosine-weighted bounce rays per batch (seed 4+rank), t_max=inf, closest hit",
         "n_triangles": N_TRIS,
-        "rays_per_step_per_gpu": N_RAYS,
+        "rays_per_step_per_gpu": n_rays,
         "max_prims_in_node": 4,
         "tier": "F (true closest hit, ties -> lowest prim id)",
         "l2_policy": "inputs larger than L2: 1 GiB of rays + 0.5 GiB of hits stream per step (126 MB L2)",
@@ -284,13 +284,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 deciding arithmetic (Moller-Trumbore / quadratic), fp32 box culling", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, n_rays),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 64, "d2h_bytes_per_step": n_rays * 32,
                     "api": "rrt_intersect (pinned host rays -> hits), 1 Mi-ray chunks on 3 streams"},
+            "launches_per_step": launches / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "trace_kernel<closest>",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "trace_kernel<closest> (+4 ray-sort launches per step, inside the timed region)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
                          "nodes_visited_per_ray_oracle": NV_C3, "prims_tested_per_ray_oracle": NT_C3,
                          "compulsory_dram_bytes_per_ray": 64 + 32 + stats["device_bytes"] / n_rays},

@@ -36,23 +36,35 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """`defines` / `out` build an experiment variant (tools/sweep.py); the product is the default call."""
+    global LIB
+    if out is None and not force and not is_stale():
         return LIB
+    if out is not None:
+        saved, LIB = LIB, Path(out)
+        try:
+            return _build(verbose, defines)
+        finally:
+            LIB = saved
+    return _build(verbose, defines)
+
+
+def _build(verbose, defines):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         if LIB.exists():
             return LIB  # GPU box without a toolchain: use the prebuilt library that travelled with the repo
         raise RuntimeError("nvcc not found and no prebuilt librrt_sm100.so")
     tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-o", str(tmp), *map(str, sources()), "-lcudart"]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(PKG.parent / "include"), "-o", str(tmp), *map(str, sources()), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    (PKG / "ptxas_report.txt").write_text(r.stdout + r.stderr)
+    (LIB.parent / (LIB.stem + "_ptxas.txt")).write_text(r.stdout + r.stderr)
     os.replace(tmp, LIB)
     return LIB
 

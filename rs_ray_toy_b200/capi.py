@@ -10,7 +10,9 @@ import re
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "librrt_sm100.so"
+import os
+# RRT_LIB selects an experiment build of the same library (tools/sweep.py); default = the product
+LIB_PATH = Path(os.environ["RRT_LIB"]) if os.environ.get("RRT_LIB") else PKG / "librrt_sm100.so"
 HEADER = PKG.parent / "include" / "rrt.h"
 
 RRT_OK = 0

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -27,7 +28,6 @@ namespace {
 
 constexpr int kStack = 64;
 constexpr int kBlock = 128;
-constexpr int32_t kSentinel = INT32_MIN;
 
 struct D3 {
     double x, y, z;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a
 
 // Brings a ray whose origin lies far outside the world box close to it (in f64), so that the
 // fp32 traversal copy keeps |o| comparable to the scene and the host-side box widening holds.
-__device__ __forceinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_max, double* t_shift, RayF* rf) {
+__device__ __forceinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_max, float* t_shift, RayF* rf) {
     double ts = 0.0;
     bool outside = o.x < A.world_lo[0] || o.x > A.world_hi[0] || o.y < A.world_lo[1] || o.y > A.world_hi[1] ||
                    o.z < A.world_lo[2] || o.z > A.world_hi[2];
@@ -176,7 +176,10 @@ __device__ __forceinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double
         double len = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
         ts = fmax(0.0, t0 - A.scene_scale / len);
     }
-    *t_shift = ts;
+    // the shift is kept as an fp32 value (rounded toward the origin) so the walk can carry it in one register
+    const float tsf = __double2float_rd(ts);
+    ts = (double)tsf;
+    *t_shift = tsf;
     double sx = o.x + d.x * ts, sy = o.y + d.y * ts, sz = o.z + d.z * ts;
     rf->idx = safe_inv(d.x);
     rf->idy = safe_inv(d.y);
@@ -187,63 +190,191 @@ __device__ __forceinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double
     return true;
 }
 
+// Surface parameters of the winning record.  Sphere hit, sphere.rs:157-198 for a full sphere: the hit point is taken
+// on the ray the shape was handed (the instance-space ray, Q5a), phi = atan2(y, x) wrapped to
+// [0, 2pi), u = phi / phi_max, v = (theta - theta_min) / (theta_max - theta_min) with
+// theta_min = acos(-1), theta_max = acos(1).  Only the winning record pays for this.
+template <bool WIDE>
+__device__ __noinline__ void hit_params(const AggView& A, uint32_t rec, D3 o, D3 d, double t, double* u, double* v) {
+    D3 a, b, c;
+    uint32_t pid, kind, inst = 0xFFFFFFFFu;
+    load_prim<WIDE>(A.prims, rec, &a, &b, &c, &pid, &kind);
+    if (kind == PRIM_TRIANGLE) {
+        // the walk keeps only (t, record); the barycentrics of the winner are recomputed here with
+        // the same operations, hence the same bits (triangle.rs:245-256)
+        double tt;
+        tri_test(o, d, a, b, c, &tt, u, v);
+        return;
+    }
+    if (!WIDE) inst = static_cast<const PrimRec48*>(A.prims)[rec].words[8];
+    else inst = static_cast<const PrimRec96*>(A.prims)[rec].pad[0];
+    D3 lo = o, ld = d;
+    if (inst != 0xFFFFFFFFu) {
+        // Transform::t(ray) with world_to_primitive (transform.rs:451-502), row by row
+        const double* m = A.inst_w2p + 12 * (size_t)inst;
+        lo = {__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], o.x), __dmul_rn(m[1], o.y)), __dmul_rn(m[2], o.z)), m[3]),
+              __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[4], o.x), __dmul_rn(m[5], o.y)), __dmul_rn(m[6], o.z)), m[7]),
+              __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[8], o.x), __dmul_rn(m[9], o.y)), __dmul_rn(m[10], o.z)), m[11])};
+        ld = {__dadd_rn(__dadd_rn(__dmul_rn(m[0], d.x), __dmul_rn(m[1], d.y)), __dmul_rn(m[2], d.z)),
+              __dadd_rn(__dadd_rn(__dmul_rn(m[4], d.x), __dmul_rn(m[5], d.y)), __dmul_rn(m[6], d.z)),
+              __dadd_rn(__dadd_rn(__dmul_rn(m[8], d.x), __dmul_rn(m[9], d.y)), __dmul_rn(m[10], d.z))};
+    }
+    const double radius = b.x;
+    double px = __dadd_rn(lo.x, __dmul_rn(ld.x, t)), py = __dadd_rn(lo.y, __dmul_rn(ld.y, t)),
+           pz = __dadd_rn(lo.z, __dmul_rn(ld.z, t));
+    if (px == 0.0 && py == 0.0) px = __dmul_rn(1e-5, radius);
+    double phi = atan2(py, px);
+    const double kPi = 3.14159265358979323846;
+    if (phi < 0.0) phi = __dadd_rn(phi, __dmul_rn(2.0, kPi));
+    const double phi_max = __dmul_rn(360.0, kPi / 180.0);
+    *u = __ddiv_rn(phi, phi_max);
+    double cz = __ddiv_rn(pz, radius);
+    cz = cz < -1.0 ? -1.0 : (cz > 1.0 ? 1.0 : cz);
+    double theta = acos(cz);
+    const double theta_min = kPi, theta_max = 0.0;  // acos(-1), acos(1)
+    *v = __ddiv_rn(__dsub_rn(theta, theta_min), __dsub_rn(theta_max, theta_min));
+}
+
+// ---------------------------------------------------------------------------------------------
+// The traversal kernel.  Persistent warps pull rays from a global cursor; every lane owns one ray
+// at a time.  Control flow is kept warp-uniform (all 32 lanes vote on every loop exit):
+//   * interior phase: lanes walk Node64 records; a lane that reaches a leaf parks it ("postponed
+//     leaf") and keeps walking speculatively until every lane that has work holds a leaf
+//     (Aila & Laine's speculative while-while) — box tests done while waiting are never wasted
+//     on correctness: they can only visit subtrees a later, closer hit would have culled;
+//   * leaf phase: every parked leaf is tested in f64;
+//   * refill: when at least kRefill lanes have finished their ray the warp takes that many new
+//     rays with one atomicAdd (rays are Morton-sorted by sort_rays, so neighbours in the queue
+//     are neighbours in space and the refilled lanes re-join warm cache lines).
+// ---------------------------------------------------------------------------------------------
+constexpr int32_t kDone = 0x7fffffff;  // "stack empty": a positive value no node index reaches
+constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 means "none parked"
+#ifndef RRT_REFILL
+#define RRT_REFILL 8
+#endif
+#ifndef RRT_MINBLOCKS
+#define RRT_MINBLOCKS 1
+#endif
+constexpr int kRefill = RRT_REFILL;
+
 template <bool ANY, bool WIDE>
-__global__ void __launch_bounds__(kBlock) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
-                                                        rrt_hit* __restrict__ hits, uint8_t* __restrict__ occluded) {
-    uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const double2* rp = reinterpret_cast<const double2*>(rays + i);
-    double2 q0 = __ldcs(rp), q1 = __ldcs(rp + 1), q2 = __ldcs(rp + 2), q3 = __ldcs(rp + 3);
-    const D3 o = {q0.x, q0.y, q1.x};
-    const D3 d = {q1.y, q2.x, q2.y};
-    double best_t = q3.x;
-    uint32_t best_id = RRT_NO_HIT;
-    double best_u = 0.0, best_v = 0.0;
+__global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
+                                                        rrt_hit* __restrict__ hits, uint8_t* __restrict__ occluded,
+                                                        const uint32_t* __restrict__ perm,
+                                                        const uint32_t* __restrict__ use_perm,
+                                                        unsigned long long* __restrict__ cursor) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
+    const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
+
+    int32_t stack[kStack];
+    int sp = 0;
+    int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
+    int32_t leaf = kNoLeaf;   // parked leaf reference
+    bool have_ray = false;
+    bool exhausted = false;   // the global queue is empty (warp-uniform)
+    uint64_t ray_index = 0;
+    D3 o = {0, 0, 0}, d = {0, 0, 0};
+    RayF rf = {0, 0, 0, 0, 0, 0};
+    double best_t = 0.0;
+    float t_shift = 0.0f, tcull = 0.0f;
+    uint32_t best_id = RRT_NO_HIT, best_rec = 0;
     bool found = false;
 
-    double t_shift;
-    RayF rf;
-    bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
-    if (live) {
-        const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
-        int32_t stack[kStack];
-        int sp = 0;
-        stack[sp++] = kSentinel;
-        int32_t node = A.root;
-        float tcull = __double2float_ru(best_t - t_shift);
-        while (node != kSentinel) {
-            // ---- interior nodes: one 64-byte fetch tests both children ----
-            while (node >= 0) {
+    for (;;) {
+        // ---- retire finished rays, refill idle lanes ----
+        const bool finished = have_ray && node == kDone && leaf == kNoLeaf;
+        if (finished) {
+            if (ANY) {
+                occluded[ray_index] = found ? 1 : 0;
+            } else {
+                double bu = 0.0, bv = 0.0;
+                const bool got = best_id != RRT_NO_HIT;
+                if (got) hit_params<WIDE>(A, best_rec, o, d, best_t, &bu, &bv);
+                double2* hp = reinterpret_cast<double2*>(hits + ray_index);
+                double2 w0, w1;
+                w0.x = __hiloint2double(0, (int)best_id);
+                w0.y = got ? best_t : 0.0;
+                w1.x = bu;
+                w1.y = bv;
+                __stcs(hp, w0);
+                __stcs(hp + 1, w1);
+            }
+            have_ray = false;
+        }
+        const unsigned idle = __ballot_sync(FULL, !have_ray);
+        if (idle != 0u && !exhausted && (__popc(idle) >= kRefill)) {
+            const int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned long long)want >= n) exhausted = true;
+            if (!have_ray) {
+                const unsigned long long q = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (q < n) {
+                    ray_index = permuted ? (uint64_t)__ldg(perm + q) : (uint64_t)q;
+                    const double2* rp = reinterpret_cast<const double2*>(rays + ray_index);
+                    const double2 q0 = __ldcs(rp), q1 = __ldcs(rp + 1), q2 = __ldcs(rp + 2), q3 = __ldcs(rp + 3);
+                    o = {q0.x, q0.y, q1.x};
+                    d = {q1.y, q2.x, q2.y};
+                    best_t = q3.x;
+                    best_id = RRT_NO_HIT;
+                    found = false;
+                    have_ray = true;
+                    sp = 0;
+                    leaf = kNoLeaf;
+                    const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
+                    node = live ? A.root : kDone;
+                    tcull = __double2float_ru(best_t - (double)t_shift);
+                }
+            }
+        }
+        if (__ballot_sync(FULL, have_ray) == 0u) {
+            if (exhausted) break;
+            continue;  // fewer than kRefill idle lanes cannot happen here (all 32 are idle)
+        }
+
+        // ---- interior phase ----
+        for (;;) {
+            const bool walking = node >= 0 && node != kDone;
+            if (walking) {
                 const float4* np = reinterpret_cast<const float4*>(nodes + node);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), nz = __ldg(np + 2);
                 const int4 ch = __ldg(reinterpret_cast<const int4*>(np) + 3);
                 float tn0, tn1;
-                bool h0 = slab(rf, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, tcull, &tn0);
-                bool h1 = slab(rf, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, tcull, &tn1);
+                const bool h0 = slab(rf, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, tcull, &tn0);
+                const bool h1 = slab(rf, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, tcull, &tn1);
                 if (h0 && h1) {
-                    bool swap = !ANY && (tn1 < tn0);
-                    int32_t near_c = swap ? ch.y : ch.x;
-                    int32_t far_c = swap ? ch.x : ch.y;
-                    stack[sp++] = far_c;
-                    node = near_c;
+                    const bool swap = !ANY && (tn1 < tn0);
+                    stack[sp++] = swap ? ch.x : ch.y;
+                    node = swap ? ch.y : ch.x;
                 } else if (h0) {
                     node = ch.x;
                 } else if (h1) {
                     node = ch.y;
                 } else {
-                    node = stack[--sp];
+                    node = sp > 0 ? stack[--sp] : kDone;
                 }
             }
-            if (node == kSentinel) break;
-            // ---- leaf: a contiguous run of primitive records ----
-            {
-                uint32_t ref = ~(uint32_t)node;
-                uint32_t first = ref >> 3, cnt = (ref & 7u) + 1u;
+            if (node < 0 && leaf == kNoLeaf) {  // park the first leaf, keep walking
+                leaf = node;
+                node = sp > 0 ? stack[--sp] : kDone;
+            }
+            // leave when no lane is still looking for its first leaf
+            if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
+        }
+
+        // ---- leaf phase ----
+        while (__any_sync(FULL, leaf != kNoLeaf)) {
+            if (leaf != kNoLeaf) {
+                const uint32_t ref = ~(uint32_t)leaf;
+                const uint32_t first = ref >> 3, cnt = (ref & 7u) + 1u;
                 for (uint32_t k = 0; k < cnt; ++k) {
                     D3 a, b, c;
                     uint32_t pid, kind;
                     load_prim<WIDE>(A.prims, first + k, &a, &b, &c, &pid, &kind);
-                    double t, u = 0.0, v = 0.0;
+                    double t, u, v;
                     bool hit;
                     if (kind == PRIM_TRIANGLE) {
                         hit = tri_test(o, d, a, b, c, &t, &u, &v) && !(t > best_t);
@@ -259,30 +390,171 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(AggView A, uint64_t n, co
                         if (t < best_t || best_id == RRT_NO_HIT || pid < best_id) {
                             best_t = t;
                             best_id = pid;
-                            best_u = u;
-                            best_v = v;
-                            tcull = __double2float_ru(best_t - t_shift);
+                            best_rec = first + k;
+                            tcull = __double2float_ru(best_t - (double)t_shift);
                         }
                     }
                 }
-                if (ANY && found) break;
-                node = stack[--sp];
+                leaf = kNoLeaf;
+                if (ANY && found) {
+                    node = kDone;
+                    sp = 0;
+                } else if (node < 0) {  // the walk had already reached another leaf
+                    leaf = node;
+                    node = sp > 0 ? stack[--sp] : kDone;
+                }
             }
         }
     }
-    if (ANY) {
-        occluded[i] = found ? 1 : 0;
-    } else {
-        double2* hp = reinterpret_cast<double2*>(hits + i);
-        bool got = best_id != RRT_NO_HIT;
-        double2 w0, w1;
-        w0.x = __hiloint2double(0, (int)best_id);
-        w0.y = got ? best_t : 0.0;
-        w1.x = got ? best_u : 0.0;
-        w1.y = got ? best_v : 0.0;
-        __stcs(hp, w0);
-        __stcs(hp + 1, w1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ray sorting: a counting sort of ray indices by the Morton code of the ray origin (7 bits per
+// axis inside the world box, + the direction octant).  Incoherent batches become queues whose
+// neighbours start in the same ~1/128 cell, which is what keeps a warp's 32 walks on the same
+// cache lines.  Batches that are already coherent (camera rays: one origin -> one huge bin)
+// are detected by the largest bin and left in input order (use_perm = 0).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortBits = 7;
+constexpr uint32_t kSortBins = (1u << (3 * kSortBits)) * 8u;
+
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 10 bits -> every third bit
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r) {
+    const double2* rp = reinterpret_cast<const double2*>(r);
+    const double2 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
+    const double o[3] = {q0.x, q0.y, q1.x};
+    const double dd[3] = {q1.y, q2.x, q2.y};
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double ext = A.world_hi[k] - A.world_lo[k];
+        double f = ext > 0.0 ? (o[k] - A.world_lo[k]) / ext : 0.0;
+        f = f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f);
+        if (!(f == f)) f = 0.0;
+        uint32_t q = (uint32_t)(f * (double)(1u << kSortBits));
+        c[k] = q >= (1u << kSortBits) ? (1u << kSortBits) - 1u : q;
     }
+    const uint32_t cell = spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2);
+    const uint32_t oct = (dd[0] < 0.0 ? 1u : 0u) | (dd[1] < 0.0 ? 2u : 0u) | (dd[2] < 0.0 ? 4u : 0u);
+    if (A.sort_mode == 0) return cell;
+    if (A.sort_mode == 2) return (oct << (3 * kSortBits)) | cell;
+    return (cell << 3) | oct;
+}
+
+__global__ void __launch_bounds__(256) sort_count_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
+                                                          uint32_t* __restrict__ bins, uint32_t* __restrict__ key_out,
+                                                          uint32_t* __restrict__ rank_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t key = valid ? ray_key(A, rays + i) : 0xFFFFFFFFu;
+    // one atomic per distinct key per warp
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && (int)lane == leader) base = atomicAdd(bins + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) {
+        key_out[i] = key;
+        rank_out[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    }
+}
+
+// Exclusive scan of the bins in three small launches (per-block sums, scan of the sums, apply).
+constexpr int kScanBlock = 1024;
+__global__ void __launch_bounds__(kScanBlock) scan_block_kernel(uint32_t* __restrict__ bins, uint32_t nbins,
+                                                                 uint32_t* __restrict__ block_sums,
+                                                                 uint32_t* __restrict__ max_bin) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+    const uint32_t v = i < nbins ? bins[i] : 0u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if ((int)lane >= off) x += y;
+    }
+    uint32_t m = v;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 31) warp_sums[warp] = x;
+    if (lane == 0 && m > 0) atomicMax(max_bin, m);
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+            if ((int)lane >= off) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (warp > 0 ? warp_sums[warp - 1] : 0u);
+    if (i < nbins) bins[i] = incl - v;  // exclusive within the block
+    if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t nblocks,
+                                                                const uint32_t* __restrict__ max_bin, uint64_t n,
+                                                                uint32_t* __restrict__ use_perm) {
+    // nblocks <= kScanBlock * 16: a serial carry over chunks of kScanBlock
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        // coherent batches (one bin holding > 1/64 of the rays, and at least 4096) keep input order
+        const uint32_t mb = *max_bin;
+        *use_perm = ((uint64_t)mb * 64u > n && mb >= 4096u) ? 0u : 1u;
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nblocks; base += kScanBlock) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if ((int)lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+                if ((int)lane >= off) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp > 0 ? warp_sums[warp - 1] : 0u) + carry;
+        if (i < nblocks) block_sums[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) carry = incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t n, const uint32_t* __restrict__ bins,
+                                                            const uint32_t* __restrict__ block_sums,
+                                                            const uint32_t* __restrict__ key,
+                                                            const uint32_t* __restrict__ rank,
+                                                            const uint32_t* __restrict__ use_perm,
+                                                            uint32_t* __restrict__ perm) {
+    if (*use_perm == 0u) return;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key[i];
+    perm[bins[k] + block_sums[k / kScanBlock] + rank[i]] = (uint32_t)i;
 }
 
 inline float round_down(double v) {
@@ -316,6 +588,15 @@ bool fp32_exact(const double* v, int n) {
 DeviceAggregate::~DeviceAggregate() {
     if (d_nodes_) cudaFree(d_nodes_);
     if (d_prims_) cudaFree(d_prims_);
+    if (d_inst_) cudaFree(d_inst_);
+    Workspace& w = ws_;
+    if (w.d_bins) cudaFree(w.d_bins);
+    if (w.d_block_sums) cudaFree(w.d_block_sums);
+    if (w.d_small) cudaFree(w.d_small);
+    if (w.d_key) cudaFree(w.d_key);
+    if (w.d_rank) cudaFree(w.d_rank);
+    if (w.d_perm) cudaFree(w.d_perm);
+    if (w.last_use) cudaEventDestroy(w.last_use);
 }
 
 int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err) {
@@ -422,6 +703,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                 std::memcpy(r.v, world[pi].v, sizeof(double) * 9);
                 r.prim_id = pi;
                 r.kind = pr.kind == SHAPE_TRIANGLE ? PRIM_TRIANGLE : PRIM_SPHERE;
+                r.pad[0] = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
                 rec96.push_back(r);
             } else {
                 PrimRec48 r;
@@ -439,6 +721,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                     r.sph.radius = world[pi].v[3];
                     r.sph.prim_id = pi;
                     r.sph.kind = PRIM_SPHERE;
+                    r.sph.instance = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
                 }
                 rec48.push_back(r);
             }
@@ -459,25 +742,17 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             out.c1_loz = lo[2]; out.c1_hiz = hi[2];
         }
     };
-    auto set_empty = [&](Node64& out, int which) {
-        // inverted box: tmin = +inf > tmax = -inf for every ray
-        float inf = INFINITY;
-        if (which == 0) {
-            out.c0_lox = out.c0_loy = out.c0_loz = inf; out.c0_hix = out.c0_hiy = out.c0_hiz = -inf;
-        } else {
-            out.c1_lox = out.c1_loy = out.c1_loz = inf; out.c1_hix = out.c1_hiy = out.c1_hiz = -inf;
-        }
-    };
     {
         const Bvh2Node& root = tree.nodes[tree.root];
         if (root.count > 0) {
-            // the whole scene fits one leaf: a root with one real child and one empty child
+            // the whole scene fits one leaf: the root's two children both reference that leaf
+            // (a candidate tested twice cannot change a closest or an any hit)
             Node64 r;
             std::memset(&r, 0, sizeof(r));
             set_child(r, 0, root.box);
-            set_empty(r, 1);
+            set_child(r, 1, root.box);
             r.child0 = emit_leaf(root);
-            r.child1 = kEmptyChild;
+            r.child1 = r.child0;
             nodes.push_back(r);
         } else {
             // explicit stack DFS: (tree node, slot of the Node64 to fill)
@@ -529,6 +804,18 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     RRT_CUDA(cudaMemcpy(d_nodes_, nodes.data(), node_bytes, cudaMemcpyHostToDevice));
     RRT_CUDA(cudaMemcpy(d_prims_, wide ? (const void*)rec96.data() : (const void*)rec48.data(), prim_bytes,
                         cudaMemcpyHostToDevice));
+    bool has_spheres = false;
+    for (const Primitive& pr : scene.prims) has_spheres |= pr.kind == SHAPE_SPHERE;
+    if (has_spheres && !scene.instances.empty()) {
+        std::vector<double> w2p(12 * scene.instances.size());
+        for (size_t i = 0; i < scene.instances.size(); ++i)
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 4; ++c) w2p[12 * i + 4 * r + c] = scene.instances[i].inv.m[r][c];
+        RRT_CUDA(cudaMalloc(&d_inst_, w2p.size() * sizeof(double)));
+        RRT_CUDA(cudaMemcpy(d_inst_, w2p.data(), w2p.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    view_.inst_w2p = static_cast<const double*>(d_inst_);
+    view_.has_spheres = has_spheres ? 1 : 0;
     view_.nodes = d_nodes_;
     view_.prims = d_prims_;
     for (int k = 0; k < 3; ++k) {
@@ -538,6 +825,9 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     view_.scene_scale = scale;
     view_.root = 0;
     view_.wide = wide ? 1 : 0;
+    view_.sort_mode = 1;
+    if (const char* e = std::getenv("RRT_SORT_MODE")) view_.sort_mode = atoi(e);
+    if (const char* e = std::getenv("RRT_SORT")) sort_rays_ = atoi(e) != 0;
     stats_.n_nodes = nodes.size();
     stats_.n_leaves = tree.n_leaves;
     stats_.max_depth = tree.max_depth;
@@ -555,38 +845,86 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     return RRT_OK;
 }
 
-int DeviceAggregate::closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream,
-                                 std::string* err) const {
-    if (n == 0) return RRT_OK;
-    uint64_t blocks = (n + kBlock - 1) / kBlock;
-    if (blocks > 0x7fffffffull) {
-        if (err) *err = "batch too large for one launch";
-        return RRT_ERR_INVALID;
+int DeviceAggregate::ensure_workspace(uint64_t n, std::string* err) const {
+    Workspace& w = ws_;
+    if (!w.d_small) {
+        RRT_CUDA(cudaMalloc(&w.d_bins, (size_t)kSortBins * sizeof(uint32_t)));
+        RRT_CUDA(cudaMalloc(&w.d_block_sums, (size_t)(kSortBins / kScanBlock) * sizeof(uint32_t)));
+        RRT_CUDA(cudaMalloc(&w.d_small, 64));
+        RRT_CUDA(cudaEventCreateWithFlags(&w.last_use, cudaEventDisableTiming));
+        int dev = 0, sms = 0;
+        RRT_CUDA(cudaGetDevice(&dev));
+        RRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        w.n_sms = sms;
     }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (view_.wide)
-        trace_kernel<false, true><<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, d_hits, nullptr);
-    else
-        trace_kernel<false, false><<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, d_hits, nullptr);
-    RRT_CUDA(cudaGetLastError());
+    if (n > w.capacity) {
+        if (w.d_key) cudaFree(w.d_key);
+        if (w.d_rank) cudaFree(w.d_rank);
+        if (w.d_perm) cudaFree(w.d_perm);
+        w.d_key = w.d_rank = w.d_perm = nullptr;
+        w.capacity = 0;
+        RRT_CUDA(cudaMalloc(&w.d_key, n * sizeof(uint32_t)));
+        RRT_CUDA(cudaMalloc(&w.d_rank, n * sizeof(uint32_t)));
+        RRT_CUDA(cudaMalloc(&w.d_perm, n * sizeof(uint32_t)));
+        w.capacity = n;
+    }
     return RRT_OK;
 }
 
-int DeviceAggregate::any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream,
-                             std::string* err) const {
+template <bool ANY>
+int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, uint8_t* d_occ, void* stream,
+                           std::string* err, int* launches) const {
     if (n == 0) return RRT_OK;
-    uint64_t blocks = (n + kBlock - 1) / kBlock;
-    if (blocks > 0x7fffffffull) {
-        if (err) *err = "batch too large for one launch";
+    if (n >= (1ull << 32)) {
+        if (err) *err = "batch too large for one call (2^32 rays)";
         return RRT_ERR_INVALID;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (view_.wide)
-        trace_kernel<true, true><<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, nullptr, d_occluded);
-    else
-        trace_kernel<true, false><<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, nullptr, d_occluded);
+    std::lock_guard<std::mutex> lock(ws_mutex_);
+    int rc = ensure_workspace(n, err);
+    if (rc != RRT_OK) return rc;
+    Workspace& w = ws_;
+    // the scratch buffers are shared by every call on this aggregate: order this call after the last one
+    if (w.used) RRT_CUDA(cudaStreamWaitEvent(s, w.last_use, 0));
+    uint32_t* small = static_cast<uint32_t*>(w.d_small);  // [0..1] cursor, [2] max_bin, [3] use_perm
+    RRT_CUDA(cudaMemsetAsync(small, 0, 64, s));
+    const bool sorting = sort_rays_ && n >= 4096;
+    int count = 0;
+    if (sorting) {
+        RRT_CUDA(cudaMemsetAsync(w.d_bins, 0, (size_t)kSortBins * sizeof(uint32_t), s));
+        const unsigned sb = (unsigned)((n + 255) / 256);
+        sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank);
+        scan_block_kernel<<<kSortBins / kScanBlock, kScanBlock, 0, s>>>(w.d_bins, kSortBins, w.d_block_sums, small + 2);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, kSortBins / kScanBlock, small + 2, n, small + 3);
+        sort_scatter_kernel<<<sb, 256, 0, s>>>(n, w.d_bins, w.d_block_sums, w.d_key, w.d_rank, small + 3, w.d_perm);
+        count += 4;
+    }
+    auto kernel = view_.wide ? trace_kernel<ANY, true> : trace_kernel<ANY, false>;
+    int per_sm = 0;
+    RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t blocks = (uint64_t)w.n_sms * (uint64_t)per_sm;
+    const uint64_t needed = (n + kBlock - 1) / kBlock;
+    if (blocks > needed) blocks = needed;
+    kernel<<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
+                                               sorting ? small + 3 : nullptr,
+                                               reinterpret_cast<unsigned long long*>(small));
+    count += 1;
     RRT_CUDA(cudaGetLastError());
+    RRT_CUDA(cudaEventRecord(w.last_use, s));
+    w.used = true;
+    if (launches) *launches = count;
     return RRT_OK;
+}
+
+int DeviceAggregate::closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,
+                                 int* launches) const {
+    return trace<false>(n, d_rays, d_hits, nullptr, stream, err, launches);
+}
+
+int DeviceAggregate::any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
+                             int* launches) const {
+    return trace<true>(n, d_rays, nullptr, d_occluded, stream, err, launches);
 }
 
 }  // namespace rrt

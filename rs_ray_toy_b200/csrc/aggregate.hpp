@@ -3,6 +3,7 @@
 // the opaque stream pointer) so capi.cpp can be compiled by the plain host compiler.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 
 #include "../../include/rrt.h"
@@ -20,11 +21,14 @@ struct AggregateStats {
 struct AggView {
     const void* nodes;   // Node64[]
     const void* prims;   // PrimRec48[] or PrimRec96[]
+    const double* inst_w2p;  // world->primitive 3x4 (row-major f64) per instance; sphere (u,v) only
     double world_lo[3];  // tight world box of the tree, used to pull far-away origins close
     double world_hi[3];
     double scene_scale;  // max |coordinate| of the world box
     int32_t root;        // interior node index of the root (always 0)
     int32_t wide;        // 1 => PrimRec96
+    int32_t has_spheres;
+    int32_t sort_mode;   // ray-queue key: 0 cell, 1 cell|octant, 2 octant|cell
 };
 
 class DeviceAggregate {
@@ -38,17 +42,37 @@ class DeviceAggregate {
     // Returns an rrt_status; on failure *err holds the reason.
     int build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err);
 
-    int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err) const;
-    int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err) const;
+    // Asynchronous on `stream`; *launches (optional) receives the number of kernels launched.
+    int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,
+                    int* launches = nullptr) const;
+    int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
+                int* launches = nullptr) const;
 
     const AggView& view() const { return view_; }
     const AggregateStats& stats() const { return stats_; }
 
   private:
+    // Scratch for the ray sort + the persistent kernel's cursor, shared by all calls (stream-ordered).
+    struct Workspace {
+        uint32_t *d_bins = nullptr, *d_block_sums = nullptr, *d_key = nullptr, *d_rank = nullptr, *d_perm = nullptr;
+        void* d_small = nullptr;
+        uint64_t capacity = 0;
+        struct CUevent_st* last_use = nullptr;
+        bool used = false;
+        int n_sms = 0;
+    };
+    int ensure_workspace(uint64_t n, std::string* err) const;
+    template <bool ANY>
+    int trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, uint8_t* d_occ, void* stream, std::string* err,
+              int* launches) const;
+    mutable Workspace ws_;
+    mutable std::mutex ws_mutex_;
+    bool sort_rays_ = true;
     AggView view_{};
     AggregateStats stats_{};
     void* d_nodes_ = nullptr;
     void* d_prims_ = nullptr;
+    void* d_inst_ = nullptr;
     int device_ = 0;
 };
 

@@ -106,12 +106,13 @@ int host_batch(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, void* ou
         uint64_t cnt = n - done < kChunkRays ? n - done : kChunkRays;
         // a slot is reused only after its previous D2H has drained (stream order)
         CAPI_CUDA(cudaMemcpyAsync(s.d_rays, rays + done, cnt * sizeof(rrt_ray), cudaMemcpyHostToDevice, s.stream));
+        int launched = 0;
         if (ANY)
-            rc = scene->agg->any_hit(cnt, s.d_rays, static_cast<uint8_t*>(s.d_out), s.stream, &err);
+            rc = scene->agg->any_hit(cnt, s.d_rays, static_cast<uint8_t*>(s.d_out), s.stream, &err, &launched);
         else
-            rc = scene->agg->closest_hit(cnt, s.d_rays, static_cast<rrt_hit*>(s.d_out), s.stream, &err);
+            rc = scene->agg->closest_hit(cnt, s.d_rays, static_cast<rrt_hit*>(s.d_out), s.stream, &err, &launched);
         if (rc != RRT_OK) return fail(rc, err);
-        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
         CAPI_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + done * out_elem, s.d_out, cnt * out_elem,
                                   cudaMemcpyDeviceToHost, s.stream));
         done += cnt;
@@ -326,9 +327,10 @@ int rrt_intersect_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_ra
     if (n == 0) return RRT_OK;
     if (!d_rays || !d_hits) return fail(RRT_ERR_INVALID, "rrt_intersect_device: null buffer");
     std::string err;
-    int rc = scene->agg->closest_hit(n, d_rays, d_hits, cuda_stream, &err);
+    int launched = 0;
+    int rc = scene->agg->closest_hit(n, d_rays, d_hits, cuda_stream, &err, &launched);
     if (rc != RRT_OK) return fail(rc, err);
-    scene->ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    scene->ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
     return RRT_OK;
 }
 
@@ -338,9 +340,10 @@ int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_
     if (n == 0) return RRT_OK;
     if (!d_rays || !d_occluded) return fail(RRT_ERR_INVALID, "rrt_intersect_p_device: null buffer");
     std::string err;
-    int rc = scene->agg->any_hit(n, d_rays, d_occluded, cuda_stream, &err);
+    int launched = 0;
+    int rc = scene->agg->any_hit(n, d_rays, d_occluded, cuda_stream, &err, &launched);
     if (rc != RRT_OK) return fail(rc, err);
-    scene->ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    scene->ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
     return RRT_OK;
 }
 

@@ -27,7 +27,6 @@ struct RRT_ALIGN(16) Node64 {
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
 // Leaf reference: ~((first_record << 3) | (count - 1)), count in 1..8.
-constexpr int32_t kEmptyChild = INT32_MIN;  // never intersected (its box is inverted)
 inline
 #if defined(__CUDACC__)
     __host__ __device__
@@ -55,7 +54,7 @@ struct RRT_ALIGN(16) PrimRec48 {
         struct {
             double c[3];
             double radius;
-            uint32_t pad;
+            uint32_t instance;  // index into the instance table, 0xFFFFFFFF = bare
             uint32_t prim_id;
             uint32_t kind;
             uint32_t pad2;

@@ -78,7 +78,9 @@ def compare_closest(hits, ref_prim, ref_t, rel_tie=1e-6, rel_t=1e-5):
     dt = np.zeros(len(gp))
     dt[both] = np.abs(hits["t"][both] - ref_t[both]) / np.maximum(np.abs(ref_t[both]), 1e-300)
     ties = (~same) & both & (dt <= rel_tie)
+    bad = np.nonzero((~same) & ~ties)[0][:5]
     return {
+        "examples": [(int(i), int(gp[i]), int(ref_prim[i]), float(hits["t"][i]), float(ref_t[i])) for i in bad],
         "n": len(gp),
         "mismatch": int((~same).sum()),
         "mismatch_excl_ties": int(((~same) & ~ties).sum()),
