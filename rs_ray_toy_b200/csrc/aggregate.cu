@@ -253,7 +253,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_REFILL 8
 #endif
 #ifndef RRT_MINBLOCKS
-#define RRT_MINBLOCKS 1
+#define RRT_MINBLOCKS 8
 #endif
 constexpr int kRefill = RRT_REFILL;
 
@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
 // cache lines.  Batches that are already coherent (camera rays: one origin -> one huge bin)
 // are detected by the largest bin and left in input order (use_perm = 0).
 // ---------------------------------------------------------------------------------------------
-constexpr int kSortBits = 7;
+#ifndef RRT_SORTBITS
+#define RRT_SORTBITS 7
+#endif
+constexpr int kSortBits = RRT_SORTBITS;
 constexpr uint32_t kSortBins = (1u << (3 * kSortBits)) * 8u;
 
 __device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 10 bits -> every third bit
@@ -825,7 +828,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     view_.scene_scale = scale;
     view_.root = 0;
     view_.wide = wide ? 1 : 0;
-    view_.sort_mode = 1;
+    view_.sort_mode = 0;
     if (const char* e = std::getenv("RRT_SORT_MODE")) view_.sort_mode = atoi(e);
     if (const char* e = std::getenv("RRT_SORT")) sort_rays_ = atoi(e) != 0;
     stats_.n_nodes = nodes.size();
