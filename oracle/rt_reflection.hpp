@@ -1,0 +1,586 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rt_geom.hpp).
+//
+// Restates reflection.rs (Bsdf, BxDFs, Fresnel), microfacet.rs (TrowbridgeReitz), the in-scope
+// materials (material/{matte,plastic,metal,mirror,glass}.rs) and the RGB Spectrum<3>
+// (spectrum.rs:2146-2230, :2700-2748) of pppKin/rs_ray_toy.  Quirks kept literally: Q15
+// (Bsdf::sample_f), Q16 (Plastic gates its specular lobe on kd).
+#pragma once
+#include <vector>
+
+#include "rt_sampling.hpp"
+#include "rt_shapes.hpp"
+
+namespace orc {
+
+// Spectrum<3> (RGB).  All operators componentwise, true divisions (spectrum.rs:2232-2330).
+struct Rgb {
+    double c[3] = {0, 0, 0};
+    Rgb() = default;
+    explicit Rgb(double v) { c[0] = c[1] = c[2] = v; }
+    Rgb(double r, double g, double b) {
+        c[0] = r;
+        c[1] = g;
+        c[2] = b;
+    }
+    bool is_black() const { return c[0] == 0.0 && c[1] == 0.0 && c[2] == 0.0; }
+    bool has_nan() const { return c[0] != c[0] || c[1] != c[1] || c[2] != c[2]; }
+    // spectrum.rs:2733-2736
+    double y() const { return 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]; }
+    double max_component_value() const { return rmax(rmax(c[0], c[1]), c[2]); }
+    Rgb clamp(double lo, double hi) const { return Rgb(clamp_t(c[0], lo, hi), clamp_t(c[1], lo, hi), clamp_t(c[2], lo, hi)); }
+    Rgb sqrt() const { return Rgb(std::sqrt(c[0]), std::sqrt(c[1]), std::sqrt(c[2])); }
+};
+inline Rgb operator+(Rgb a, Rgb b) { return Rgb(a.c[0] + b.c[0], a.c[1] + b.c[1], a.c[2] + b.c[2]); }
+inline Rgb operator-(Rgb a, Rgb b) { return Rgb(a.c[0] - b.c[0], a.c[1] - b.c[1], a.c[2] - b.c[2]); }
+inline Rgb operator*(Rgb a, Rgb b) { return Rgb(a.c[0] * b.c[0], a.c[1] * b.c[1], a.c[2] * b.c[2]); }
+inline Rgb operator/(Rgb a, Rgb b) { return Rgb(a.c[0] / b.c[0], a.c[1] / b.c[1], a.c[2] / b.c[2]); }
+inline Rgb operator*(Rgb a, double s) { return Rgb(a.c[0] * s, a.c[1] * s, a.c[2] * s); }
+inline Rgb operator/(Rgb a, double s) { return Rgb(a.c[0] / s, a.c[1] / s, a.c[2] / s); }
+inline Rgb& operator+=(Rgb& a, Rgb b) { return a = a + b; }
+inline Rgb& operator*=(Rgb& a, Rgb b) { return a = a * b; }
+inline Rgb& operator*=(Rgb& a, double s) { return a = a * s; }
+inline Rgb& operator/=(Rgb& a, double s) { return a = a / s; }
+// spectrum.rs:2075-2090
+inline void xyz_to_rgb(const double xyz[3], double rgb[3]) {
+    rgb[0] = 3.240479 * xyz[0] - 1.537150 * xyz[1] - 0.498535 * xyz[2];
+    rgb[1] = -0.969256 * xyz[0] + 1.875991 * xyz[1] + 0.041556 * xyz[2];
+    rgb[2] = 0.055648 * xyz[0] - 0.204043 * xyz[1] + 1.057311 * xyz[2];
+}
+inline void rgb_to_xyz(const double rgb[3], double xyz[3]) {
+    xyz[0] = 0.412453 * rgb[0] + 0.357580 * rgb[1] + 0.180423 * rgb[2];
+    xyz[1] = 0.212671 * rgb[0] + 0.715160 * rgb[1] + 0.072169 * rgb[2];
+    xyz[2] = 0.019334 * rgb[0] + 0.119193 * rgb[1] + 0.950227 * rgb[2];
+}
+
+// ---- reflection.rs helpers (:30-143) -------------------------------------------------------------
+inline double cos_theta(V3 w) { return w.z; }
+inline double cos2_theta(V3 w) { return w.z * w.z; }
+inline double abs_cos_theta(V3 w) { return std::fabs(w.z); }
+inline double sin2_theta(V3 w) { return rmax(0.0, 1.0 - cos2_theta(w)); }
+inline double sin_theta(V3 w) { return std::sqrt(sin2_theta(w)); }
+inline double tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }
+inline double tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+inline double cos_phi(V3 w) {
+    double s = sin_theta(w);
+    return s == 0.0 ? 1.0 : clamp_t(w.x / s, -1.0, 1.0);
+}
+inline double sin_phi(V3 w) {
+    double s = sin_theta(w);
+    return s == 0.0 ? 0.0 : clamp_t(w.y / s, -1.0, 1.0);
+}
+inline double cos2_phi(V3 w) { return cos_phi(w) * cos_phi(w); }
+inline double sin2_phi(V3 w) { return sin_phi(w) * sin_phi(w); }
+inline V3 reflect(V3 wo, V3 n) { return -wo + n * 2.0 * dot(wo, n); }
+inline bool refract(V3 wi, V3 n, double eta, V3* wt) {
+    double cos_theta_i = dot(n, wi);
+    double sin2_theta_i = rmax(0.0, 1.0 - cos_theta_i * cos_theta_i);
+    double sin2_theta_t = eta * eta * sin2_theta_i;
+    if (sin2_theta_t >= 1.0) return false;
+    double cos_theta_t = std::sqrt(1.0 - sin2_theta_t);
+    *wt = -wi * eta + n * (eta * cos_theta_i - cos_theta_t);
+    return true;
+}
+inline bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0; }
+
+// reflection.rs:145-168
+inline double fr_dielectric(double cos_theta_i, double eta_i, double eta_t) {
+    cos_theta_i = clamp_t(cos_theta_i, -1.0, 1.0);
+    bool entering = cos_theta_i > 0.0;
+    if (!entering) {
+        std::swap(eta_i, eta_t);
+        cos_theta_i = std::fabs(cos_theta_i);
+    }
+    double sin_theta_i = std::sqrt(rmax(0.0, 1.0 - cos_theta_i * cos_theta_i));
+    double sin_theta_t = eta_i / eta_t * sin_theta_i;
+    if (sin_theta_t >= 1.0) return 1.0;
+    double cos_theta_t = std::sqrt(rmax(0.0, 1.0 - sin_theta_t * sin_theta_t));
+    double r_parl = ((eta_t * cos_theta_i) - (eta_i * cos_theta_t)) / ((eta_t * cos_theta_i) + (eta_i * cos_theta_t));
+    double r_perp = ((eta_i * cos_theta_i) - (eta_t * cos_theta_t)) / ((eta_i * cos_theta_i) + (eta_t * cos_theta_t));
+    return (r_parl * r_parl + r_perp * r_perp) / 2.0;
+}
+// reflection.rs:170-195
+inline Rgb fr_conductor(double cos_theta_i, Rgb eta_i, Rgb eta_t, Rgb k) {
+    cos_theta_i = clamp_t(cos_theta_i, -1.0, 1.0);
+    Rgb eta = eta_t / eta_i, eta_k = k / eta_i;
+    double cos2 = cos_theta_i * cos_theta_i, sin2 = 1.0 - cos2;
+    Rgb eta_2 = eta * eta, eta_k2 = eta_k * eta_k;
+    Rgb t0 = eta_2 - eta_k2 - Rgb(sin2);
+    Rgb a2_plus_b2 = (t0 * t0 + eta_2 * eta_k2 * Rgb(4.0)).sqrt();
+    Rgb t1 = a2_plus_b2 + Rgb(cos2);
+    Rgb a = ((a2_plus_b2 + t0) * 0.5).sqrt();
+    Rgb t2 = a * 2.0 * cos_theta_i;
+    Rgb rs = (t1 - t2) / (t1 + t2);
+    Rgb t3 = a2_plus_b2 * cos2 + Rgb(sin2 * sin2);
+    Rgb t4 = t2 * sin2;
+    Rgb rp = rs * (t3 - t4) / (t3 + t4);
+    return (rp + rs) * Rgb(0.5);
+}
+
+// ---- microfacet.rs ----------------------------------------------------------------------------------
+// microfacet.rs:12-20
+inline double roughness_to_alpha(double roughness) {
+    roughness = rmax(roughness, 1e-3);
+    double x = std::log(roughness);
+    return 1.62142 + 0.819955 * x + 0.1734 * x * x + 0.0171201 * x * x * x + 0.000640711 * x * x * x * x;
+}
+// TrowbridgeReitzDistribution (microfacet.rs:253-425), sample_visible_area = true everywhere in scope
+struct TrowbridgeReitz {
+    double alpha_x = 0, alpha_y = 0;
+    double d(V3 wh) const {
+        double tan2 = tan2_theta(wh);
+        if (std::isinf(tan2)) return 0.0;
+        double cos4 = cos2_theta(wh) * cos2_theta(wh);
+        double e = (cos2_phi(wh) / (alpha_x * alpha_x) + sin2_phi(wh) / (alpha_y * alpha_y)) * tan2;
+        return 1.0 / (PI * alpha_x * alpha_y * cos4 * (1.0 + e) * (1.0 + e));
+    }
+    double lambda(V3 w) const {
+        double abs_tan = std::fabs(tan_theta(w));
+        if (std::isinf(abs_tan)) return 0.0;
+        double alpha = std::sqrt(cos2_phi(w) * (alpha_x * alpha_x) + sin2_phi(w) * (alpha_y * alpha_y));
+        double a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
+        return (-1.0 + std::sqrt(1.0 + a2t2)) / 2.0;
+    }
+    double g1(V3 w) const { return 1.0 / (1.0 + lambda(w)); }
+    double g(V3 wo, V3 wi) const { return 1.0 / (1.0 + lambda(wo) + lambda(wi)); }
+    double pdf(V3 wo, V3 wh) const { return d(wh) * g1(wo) * absdot(wo, wh) / abs_cos_theta(wo); }
+    // microfacet.rs:270-313
+    static void sample11(double cos_t, double u1, double u2, double* slope_x, double* slope_y) {
+        if (cos_t > 0.9999) {
+            double r = std::sqrt(u1 / (1.0 - u1));
+            double phi = 6.28318530718 * u2;
+            *slope_x = r * std::cos(phi);
+            *slope_y = r * std::sin(phi);
+            return;
+        }
+        double sin_t = std::sqrt(rmax(0.0, 1.0 - cos_t * cos_t));
+        double tan_t = sin_t / cos_t;
+        double a = 1.0 / tan_t;
+        double g1 = 2.0 / (1.0 + std::sqrt(1.0 + 1.0 / (a * a)));
+        a = 2.0 * u1 / g1 - 1.0;
+        double tmp = 1.0 / (a * a - 1.0);
+        if (tmp > 1e10) tmp = 1e10;
+        double b = tan_t;
+        double dd = std::sqrt(rmax(b * b * tmp * tmp - (a * a - b * b) * tmp, 0.0));
+        double sx1 = b * tmp - dd, sx2 = b * tmp + dd;
+        *slope_x = (a < 0.0 || sx2 > 1.0 / tan_t) ? sx1 : sx2;
+        double s, nu2;
+        if (u2 > 0.5) {
+            s = 1.0;
+            nu2 = 2.0 * (u2 - 0.5);
+        } else {
+            s = -1.0;
+            nu2 = 2.0 * (0.5 - u2);
+        }
+        double z = (nu2 * (nu2 * (nu2 * 0.27385 - 0.73369) + 0.46341)) /
+                   (nu2 * (nu2 * (nu2 * 0.093073 + 0.309420) - 1.0) + 0.597999);
+        *slope_y = s * z * std::sqrt(1.0 + *slope_x * *slope_x);
+    }
+    // microfacet.rs:315-362
+    static V3 sample_visible(V3 wi, double ax, double ay, double u1, double u2) {
+        V3 ws = normalize_vec(V3(ax * wi.x, ay * wi.y, wi.z));
+        double sx = 0, sy = 0;
+        sample11(cos_theta(ws), u1, u2, &sx, &sy);
+        double tmp = cos_phi(ws) * sx - sin_phi(ws) * sy;
+        sy = sin_phi(ws) * sx + cos_phi(ws) * sy;
+        sx = tmp;
+        sx *= ax;
+        sy *= ay;
+        return normalize_vec(V3(-sx, -sy, 1.0));
+    }
+    V3 sample_wh(V3 wo, P2 u) const {
+        if (wo.z < 0.0) return -sample_visible(-wo, alpha_x, alpha_y, u.x, u.y);
+        return sample_visible(wo, alpha_x, alpha_y, u.x, u.y);
+    }
+};
+
+// ---- BxDFs ---------------------------------------------------------------------------------------------
+enum : uint8_t {
+    BXDF_REFLECTION = 1,
+    BXDF_TRANSMISSION = 2,
+    BXDF_DIFFUSE = 4,
+    BXDF_GLOSSY = 8,
+    BXDF_SPECULAR = 16,
+    BXDF_ALL = 31,
+    BXDF_NONE = 0
+};
+enum FresnelKind : uint8_t { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
+struct Fresnel {
+    uint8_t kind = FR_NOOP;
+    double eta_i = 1, eta_t = 1;   // dielectric
+    Rgb c_eta_i, c_eta_t, c_k;     // conductor
+    // reflection.rs:603-619
+    Rgb evaluate(double cos_i) const {
+        if (kind == FR_DIELECTRIC) return Rgb(fr_dielectric(cos_i, eta_i, eta_t));
+        if (kind == FR_CONDUCTOR) return fr_conductor(std::fabs(cos_i), c_eta_i, c_eta_t, c_k);
+        return Rgb(1.0);
+    }
+};
+enum BxdfKind : uint8_t {
+    BX_LAMBERTIAN = 0,
+    BX_OREN_NAYAR,
+    BX_MICROFACET_REFL,
+    BX_SPECULAR_REFL,
+    BX_SPECULAR_TRANS,
+    BX_FRESNEL_SPECULAR
+};
+struct Bxdf {
+    uint8_t kind = BX_LAMBERTIAN;
+    Rgb r, t;
+    double a = 0, b = 0;          // Oren–Nayar
+    double eta_a = 1, eta_b = 1;  // specular transmission / fresnel specular
+    TrowbridgeReitz distrib;
+    Fresnel fresnel;
+
+    uint8_t type() const {
+        switch (kind) {
+            case BX_LAMBERTIAN:
+            case BX_OREN_NAYAR: return BXDF_DIFFUSE | BXDF_REFLECTION;
+            case BX_MICROFACET_REFL: return BXDF_GLOSSY | BXDF_REFLECTION;
+            case BX_SPECULAR_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
+            case BX_SPECULAR_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
+            default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
+        }
+    }
+    bool match_flags(uint8_t flags) const { return (type() & flags) == type(); }
+    bool is_refl() const { return (type() & BXDF_REFLECTION) > 0; }
+    bool is_trans() const { return (type() & BXDF_TRANSMISSION) > 0; }
+    bool is_spec() const { return (type() & BXDF_SPECULAR) > 0; }
+
+    Rgb f(V3 wo, V3 wi) const {
+        switch (kind) {
+            case BX_LAMBERTIAN: return r / PI;
+            case BX_OREN_NAYAR: {  // reflection.rs:916-941
+                double sin_i = sin_theta(wi), sin_o = sin_theta(wo), max_cos = 0.0;
+                if (sin_i > 1e-4 && sin_o > 1e-4) {
+                    double d_cos = cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo);
+                    max_cos = rmax(d_cos, 0.0);
+                }
+                double sin_alpha, tan_beta;
+                if (abs_cos_theta(wi) > abs_cos_theta(wo)) {
+                    sin_alpha = sin_o;
+                    tan_beta = sin_i / abs_cos_theta(wi);
+                } else {
+                    sin_alpha = sin_i;
+                    tan_beta = sin_o / abs_cos_theta(wo);
+                }
+                return r / PI * (a + b * max_cos * sin_alpha * tan_beta);
+            }
+            case BX_MICROFACET_REFL: {  // reflection.rs:970-990
+                double cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
+                V3 wh = wi + wo;
+                if (cos_i == 0.0 || cos_o == 0.0) return Rgb();
+                if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return Rgb();
+                wh = normalize_vec(wh);
+                Rgb fr = fresnel.evaluate(dot(wi, faceforward(wh, V3(0.0, 0.0, 1.0))));
+                return r * distrib.d(wh) * distrib.g(wo, wi) * fr / (4.0 * cos_i * cos_o);
+            }
+            default: return Rgb();
+        }
+    }
+    double pdf(V3 wo, V3 wi) const {
+        switch (kind) {
+            case BX_LAMBERTIAN:
+            case BX_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / PI : 0.0;  // reflection.rs:480-486
+            case BX_MICROFACET_REFL: {
+                if (!same_hemisphere(wo, wi)) return 0.0;
+                V3 wh = normalize_vec(wo + wi);
+                return distrib.pdf(wo, wh) / (4.0 * dot(wo, wh));
+            }
+            default: return 0.0;
+        }
+    }
+    // Leaves *pdf untouched on the early-outs, like the reference (Bsdf::sample_f zeroes it first).
+    Rgb sample_f(V3 wo, V3* wi, P2 u, double* pdf, uint8_t* sampled_type) const {
+        switch (kind) {
+            case BX_LAMBERTIAN:
+            case BX_OREN_NAYAR: {  // reflection.rs:428-443
+                *wi = cosine_sample_hemisphere(u);
+                if (wo.z < 0.0) wi->z *= -1.0;
+                *pdf = this->pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case BX_MICROFACET_REFL: {  // reflection.rs:991-1015
+                if (wo.z == 0.0) return Rgb();
+                V3 wh = distrib.sample_wh(wo, u);
+                if (dot(wo, wh) < 0.0) return Rgb();
+                *wi = reflect(wo, wh);
+                if (!same_hemisphere(wo, *wi)) return Rgb();
+                *pdf = distrib.pdf(wo, wh) / (4.0 * dot(wo, wh));
+                return f(wo, *wi);
+            }
+            case BX_SPECULAR_REFL: {  // reflection.rs:638-649
+                *wi = V3(-wo.x, -wo.y, wo.z);
+                *pdf = 1.0;
+                return fresnel.evaluate(cos_theta(*wi)) * r / abs_cos_theta(*wi);
+            }
+            case BX_SPECULAR_TRANS: {  // reflection.rs:686-714 (mode == Radiance)
+                bool entering = cos_theta(wo) > 0.0;
+                double ei = entering ? eta_a : eta_b, et = entering ? eta_b : eta_a;
+                if (!refract(wo, faceforward(V3(0.0, 0.0, 1.0), wo), ei / et, wi)) return Rgb();
+                *pdf = 1.0;
+                Rgb ft = t * (Rgb(1.0) - Rgb(fr_dielectric(cos_theta(*wi), eta_a, eta_b)));
+                ft *= (ei * ei) / (et * et);
+                return ft / abs_cos_theta(*wi);
+            }
+            default: {  // FresnelSpecular, reflection.rs:751-797
+                double fr = fr_dielectric(cos_theta(wo), eta_a, eta_b);
+                if (u.x < fr) {
+                    *wi = V3(-wo.x, -wo.y, wo.z);
+                    *sampled_type = BXDF_SPECULAR | BXDF_REFLECTION;
+                    *pdf = fr;
+                    return r * fr / abs_cos_theta(*wi);
+                }
+                bool entering = cos_theta(wo) > 0.0;
+                double ei = entering ? eta_a : eta_b, et = entering ? eta_b : eta_a;
+                if (!refract(wo, faceforward(V3(0.0, 0.0, 1.0), wo), ei / et, wi)) return Rgb();
+                Rgb ft = t * (1.0 - fr);
+                ft *= (ei * ei) / (et * et);
+                *sampled_type = BXDF_SPECULAR | BXDF_TRANSMISSION;
+                *pdf = 1.0 - fr;
+                return ft / abs_cos_theta(*wi);
+            }
+        }
+    }
+};
+
+// reflection.rs:205-404
+struct Bsdf {
+    double eta = 1.0;
+    V3 ns, ng, ss, ts;
+    int n_bxdfs = 0;
+    Bxdf bxdfs[8];
+    bool present = false;  // si.bsdf = Some(..)
+
+    void init(const SI& si, double eta_) {
+        eta = eta_;
+        ns = si.sh.n;
+        ss = normalize_vec(si.sh.dpdu);
+        ng = si.n;
+        ts = cross(ns, ss);
+        n_bxdfs = 0;
+        present = true;
+    }
+    void add(const Bxdf& b) { bxdfs[n_bxdfs++] = b; }
+    int num_components(uint8_t flags) const {
+        int n = 0;
+        for (int i = 0; i < n_bxdfs; ++i) n += bxdfs[i].match_flags(flags) ? 1 : 0;
+        return n;
+    }
+    V3 world_to_local(V3 v) const { return V3(dot(v, ss), dot(v, ts), dot(v, ns)); }
+    V3 local_to_world(V3 v) const {
+        return V3(ss.x * v.x + ts.x * v.y + ns.x * v.z, ss.y * v.x + ts.y * v.y + ns.y * v.z,
+                  ss.z * v.x + ts.z * v.y + ns.z * v.z);
+    }
+    Rgb f(V3 wo_w, V3 wi_w, uint8_t flags) const {
+        V3 wi = world_to_local(wi_w), wo = world_to_local(wo_w);
+        if (wo.z == 0.0) return Rgb();
+        bool reflect_ = dot(wi_w, ng) * dot(wo_w, ng) > 0.0;
+        Rgb f;
+        for (int i = 0; i < n_bxdfs; ++i) {
+            const Bxdf& b = bxdfs[i];
+            if (b.match_flags(flags) && ((reflect_ && b.is_refl()) || (!reflect_ && b.is_trans()))) f += b.f(wo, wi);
+        }
+        return f;
+    }
+    double pdf(V3 wo_w, V3 wi_w, uint8_t flags) const {
+        if (n_bxdfs == 0) return 0.0;
+        V3 wo = world_to_local(wo_w), wi = world_to_local(wi_w);
+        if (wo.z == 0.0) return 0.0;
+        double p = 0.0;
+        int matching = 0;
+        for (int i = 0; i < n_bxdfs; ++i)
+            if (bxdfs[i].match_flags(flags)) {
+                matching += 1;
+                p += bxdfs[i].pdf(wo, wi);
+            }
+        return matching > 0 ? p / (double)matching : 0.0;
+    }
+    // reflection.rs:302-381 — Q15 kept: pdfs of the other lobes are added only when the chosen lobe
+    // is NOT reflective; the recomputed multi-lobe f is discarded (shadowed `let mut f`).
+    Rgb sample_f(V3 wo_w, V3* wi_w, P2 u, double* pdf, uint8_t flags, uint8_t* sampled_type) const {
+        int matching = num_components(flags);
+        if (matching == 0) {
+            *pdf = 0.0;
+            *sampled_type = BXDF_NONE;
+            return Rgb();
+        }
+        int comp = (int)std::min<uint64_t>(rust_as_u64(std::floor(u.x * (double)matching)), (uint64_t)matching);
+        int count = comp, chosen = -1;
+        for (int i = 0; i < n_bxdfs; ++i)
+            if (bxdfs[i].match_flags(flags)) {
+                if (count == 0) {
+                    chosen = i;
+                    break;
+                }
+                count -= 1;
+            }
+        if (chosen < 0) throw std::runtime_error("oracle: Did not Choose Any BxDF (reference would panic)");
+        const Bxdf& bx = bxdfs[chosen];
+        P2 ur(rmin(u.x * (double)matching - (double)comp, ONE_MINUS_EPSILON), u.y);
+        V3 wi, wo = world_to_local(wo_w);
+        if (wo.z == 0.0) return Rgb();
+        *pdf = 0.0;
+        *sampled_type = bx.type();
+        Rgb f = bx.sample_f(wo, &wi, ur, pdf, sampled_type);
+        if (*pdf == 0.0) {
+            *sampled_type = BXDF_NONE;
+            return Rgb();
+        }
+        *wi_w = local_to_world(wi);
+        if (!bx.is_refl() && matching > 1) {
+            for (int i = 0; i < n_bxdfs; ++i)
+                if (i != chosen && bxdfs[i].match_flags(flags)) *pdf += bxdfs[i].pdf(wo, wi);
+        }
+        if (matching > 1) *pdf /= (double)matching;
+        return f;
+    }
+};
+
+// ---- materials (material/*.rs) with constant-valued parameters -------------------------------------
+enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4, MAT_NONE = 5 };
+struct Material {
+    uint32_t kind = MAT_MATTE;
+    Rgb kd = Rgb(0.5), ks = Rgb(0.25), kr = Rgb(0.9), kt = Rgb(1.0);
+    Rgb eta_rgb, k_rgb;      // metal
+    double sigma = 0.0;      // matte
+    double roughness = 0.1;  // plastic / metal
+    double u_roughness = -1.0, v_roughness = -1.0;  // metal: < 0 = None; glass: value
+    double eta = 1.5;        // glass index
+    bool remap_roughness = false;
+};
+// Fills si-dependent Bsdf exactly as the material's compute_scattering_functions would
+// (bump maps are out of scope).  `allow_multiple_lobes` as passed by the integrator.
+inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_lobes, Bsdf* bsdf) {
+    bsdf->present = false;
+    switch (m.kind) {
+        case MAT_MATTE: {  // matte.rs:36-61
+            Rgb r = m.kd.clamp(0.0, kInf);
+            double sig = clamp_t(m.sigma, 0.0, 90.0);
+            bsdf->init(si, 1.0);
+            if (!r.is_black()) {
+                Bxdf b;
+                b.r = r;
+                if (sig == 0.0) {
+                    b.kind = BX_LAMBERTIAN;
+                } else {
+                    b.kind = BX_OREN_NAYAR;  // reflection.rs:906-912
+                    double s = radians(sig);
+                    double sigma2 = s * s;
+                    b.a = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
+                    b.b = 0.45 * sigma2 / (sigma2 + 0.09);
+                }
+                bsdf->add(b);
+            }
+            return;
+        }
+        case MAT_PLASTIC: {  // plastic.rs:42-73 (Q16)
+            bsdf->init(si, 1.0);
+            Rgb kd = m.kd.clamp(0.0, kInf);
+            if (!kd.is_black()) {
+                Bxdf b;
+                b.kind = BX_LAMBERTIAN;
+                b.r = kd;
+                bsdf->add(b);
+            }
+            Rgb ks = m.ks.clamp(0.0, kInf);
+            if (!kd.is_black()) {
+                Bxdf b;
+                b.kind = BX_MICROFACET_REFL;
+                b.r = ks;
+                double rough = m.roughness;
+                if (m.remap_roughness) rough = roughness_to_alpha(rough);
+                b.distrib.alpha_x = b.distrib.alpha_y = rough;
+                b.fresnel.kind = FR_DIELECTRIC;
+                b.fresnel.eta_i = 1.5;
+                b.fresnel.eta_t = 1.0;
+                bsdf->add(b);
+            }
+            return;
+        }
+        case MAT_METAL: {  // metal.rs:48-90
+            bsdf->init(si, 1.0);
+            double ur = m.u_roughness >= 0.0 ? m.u_roughness : m.roughness;
+            double vr = m.v_roughness >= 0.0 ? m.v_roughness : m.roughness;
+            if (m.remap_roughness) {
+                ur = roughness_to_alpha(ur);
+                vr = roughness_to_alpha(vr);
+            }
+            Bxdf b;
+            b.kind = BX_MICROFACET_REFL;
+            b.r = Rgb(1.0);
+            b.distrib.alpha_x = ur;
+            b.distrib.alpha_y = vr;
+            b.fresnel.kind = FR_CONDUCTOR;
+            b.fresnel.c_eta_i = Rgb(1.0);
+            b.fresnel.c_eta_t = m.eta_rgb;
+            b.fresnel.c_k = m.k_rgb;
+            bsdf->add(b);
+            return;
+        }
+        case MAT_MIRROR: {  // mirror.rs:28-48
+            Rgb r = m.kr.clamp(0.0, kInf);
+            bsdf->init(si, 1.0);
+            if (!r.is_black()) {
+                Bxdf b;
+                b.kind = BX_SPECULAR_REFL;
+                b.r = r;
+                b.fresnel.kind = FR_NOOP;
+                bsdf->add(b);
+            }
+            return;
+        }
+        case MAT_GLASS: {  // glass.rs:52-113; rough transmission (MicrofacetTransmission) is out of scope
+            double eta = m.eta, ur = rmax(m.u_roughness, 0.0), vr = rmax(m.v_roughness, 0.0);
+            Rgb r = m.kr.clamp(0.0, kInf), t = m.kt.clamp(0.0, kInf);
+            bsdf->init(si, eta);
+            if (r.is_black() && t.is_black()) {
+                bsdf->present = false;
+                return;
+            }
+            bool is_specular = ur == 0.0 && vr == 0.0;
+            if (is_specular && allow_multiple_lobes) {
+                Bxdf b;
+                b.kind = BX_FRESNEL_SPECULAR;
+                b.r = r;
+                b.t = t;
+                b.eta_a = 1.0;
+                b.eta_b = eta;
+                bsdf->add(b);
+                return;
+            }
+            if (!is_specular) throw std::runtime_error("oracle: rough glass (MicrofacetTransmission) is out of scope");
+            if (!r.is_black()) {
+                Bxdf b;
+                b.kind = BX_SPECULAR_REFL;
+                b.r = r;
+                b.fresnel.kind = FR_DIELECTRIC;
+                b.fresnel.eta_i = 1.0;
+                b.fresnel.eta_t = eta;
+                bsdf->add(b);
+            }
+            if (!t.is_black()) {
+                Bxdf b;
+                b.kind = BX_SPECULAR_TRANS;
+                b.t = t;
+                b.eta_a = 1.0;
+                b.eta_b = eta;
+                bsdf->add(b);
+            }
+            return;
+        }
+        default: return;  // no material: si.bsdf stays None
+    }
+}
+
+// ---- lights (lights/{point,distant}.rs) -------------------------------------------------------------
+enum LightKind : uint32_t { LIGHT_POINT = 0, LIGHT_DISTANT = 1 };
+struct Light {
+    uint32_t kind = LIGHT_POINT;
+    Rgb intensity;        // point: I ; distant: L (already l * scale)
+    V3 p_light;           // point: always (0,0,0) in the reference (Q17, renderprocess.rs:996)
+    V3 w_light;           // distant: normalised light_to_world(from - to)
+    V3 world_center;      // distant
+    double world_radius = 0;
+};
+
+}  // namespace orc

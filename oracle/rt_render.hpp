@@ -1,0 +1,311 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see rt_geom.hpp).
+//
+// Restates the render loop and the Li estimators of pppKin/rs_ray_toy:
+//   integrator/mod.rs:48-139 (si_render), :359-558 (uniform_sample_one_light / estimate_direct),
+//   integrator/path.rs:51-226 (PathIntegrator::li), integrator/directlighting.rs:72-132,
+//   lights/{point,distant}.rs, lights/mod.rs:64-66 (VisibilityTester::unoccluded),
+//   interaction.rs:60-77 (spawn_ray / spawn_ray_to_si).
+// Ray differentials are carried by the camera but never consumed: every in-scope texture is
+// constant, so compute_differentials (interaction.rs:223-284) has no
+// observable effect and is not restated.  Media and BSSRDFs are out of scope (always None).
+#pragma once
+#include <atomic>
+#include <thread>
+
+#include "rt_bvh.hpp"
+#include "rt_camera.hpp"
+
+namespace orc {
+
+enum IntegratorKind : uint32_t { INTEGRATOR_PATH = 0, INTEGRATOR_DIRECT = 1 };
+
+struct RenderStats {
+    uint64_t camera_rays = 0, extension_rays = 0, shadow_rays = 0, bounces = 0, zero_weight = 0, asserts = 0;
+    TraversalStats closest, any;
+};
+
+// One record per camera ray (pixel order, sample order): what Scene::intersect returned.
+struct HitDump {
+    int32_t px, py, sample, prim;
+    double t, weight;
+};
+
+struct RenderScene {
+    const Geometry* geom = nullptr;
+    const BVH* bvh = nullptr;
+    std::vector<Material> materials;
+    std::vector<Light> lights;
+    bool fix_q9 = false;
+
+    // Scene::intersect (scene.rs:69-72)
+    bool intersect(Ray& r, SI* si, RenderStats* st) const {
+        HitRecord h;
+        return bvh->intersect(r, &h, si, st ? &st->closest : nullptr);
+    }
+    bool intersect_with_record(Ray& r, SI* si, HitRecord* h, RenderStats* st) const {
+        return bvh->intersect(r, h, si, st ? &st->closest : nullptr);
+    }
+    // VisibilityTester::unoccluded (lights/mod.rs:64-66) over spawn_ray_to_si (interaction.rs:66-77):
+    // p_error is always zero, so both offset origins are the points themselves (geometry.rs:721-749).
+    bool unoccluded(V3 p0, V3 p1, RenderStats* st) const {
+        V3 d = p1 - p0;
+        Ray r;
+        if (fix_q9) {
+            r.o = p0;
+            r.d = d;  // Tier F: t parametrises the segment, t_max = 1 - eps reaches just short of the light
+            r.t_max = 1.0 - SHADOW_EPSILON;
+        } else {
+            r = ray_new(p0, d, 1.0 - SHADOW_EPSILON, 0.0);  // Q9: d normalised, t_max left at 1 - eps
+        }
+        if (st) st->shadow_rays += 1;
+        return !bvh->intersect_p(r, st ? &st->any : nullptr);
+    }
+    // Light::sample_li (point.rs:55-77, distant.rs:69-93)
+    Rgb sample_li(const Light& l, V3 p, V3* wi, double* pdf, V3* p1) const {
+        if (l.kind == LIGHT_POINT) {
+            *wi = normalize_vec(l.p_light - p);
+            *pdf = 1.0;
+            *p1 = l.p_light;
+            return l.intensity / length_sq(l.p_light - p);
+        }
+        *wi = l.w_light;
+        *pdf = 1.0;
+        *p1 = p + l.w_light * (2.0 * l.world_radius);
+        return l.intensity;
+    }
+    // estimate_direct (integrator/mod.rs:403-558) — both in-scope lights are delta lights, so the
+    // BSDF-sampling half (:484-556) never runs.
+    Rgb estimate_direct(const SI& si, const Bsdf& bsdf, const Light& light, RenderStats* st) const {
+        const uint8_t flags = BXDF_ALL & ~BXDF_SPECULAR;
+        Rgb ld;
+        V3 wi, p1;
+        double light_pdf = 0.0;
+        Rgb li = sample_li(light, si.p, &wi, &light_pdf, &p1);
+        if (light_pdf > 0.0 && !li.is_black()) {
+            Rgb f;
+            if (bsdf.present) f = bsdf.f(si.wo, wi, flags) * absdot(wi, si.sh.n);
+            if (!f.is_black()) {
+                if (!unoccluded(si.p, p1, st)) li = Rgb();
+                if (!li.is_black()) ld += f * li / light_pdf;
+            }
+        }
+        return ld;
+    }
+    // uniform_sample_one_light (integrator/mod.rs:359-401)
+    Rgb uniform_sample_one_light(const SI& si, const Bsdf& bsdf, HaltonSampler& sampler, const Distribution1D* distrib,
+                                 RenderStats* st) const {
+        size_t n_lights = lights.size();
+        if (n_lights == 0) return Rgb();
+        size_t light_num;
+        double light_pdf = 0.0;
+        if (distrib) {
+            light_num = distrib->sample_discrete(sampler.get_1d(), &light_pdf);
+            if (light_pdf == 0.0) return Rgb();
+        } else {
+            light_num = std::min<size_t>((size_t)rust_as_u64(sampler.get_1d() * (double)n_lights), n_lights - 1);
+            light_pdf = 1.0 / (double)n_lights;
+        }
+        sampler.get_2d();  // u_light (delta lights ignore it)
+        sampler.get_2d();  // u_scattering
+        return estimate_direct(si, bsdf, lights[light_num], st) / light_pdf;
+    }
+};
+
+struct Integrator {
+    uint32_t kind = INTEGRATOR_PATH;
+    uint32_t max_depth = 5;
+    double rr_threshold = 1.0;
+    Distribution1D light_distrib;  // path.rs:47-49: uniform over the lights
+
+    // PathIntegrator::li (path.rs:51-226)
+    Rgb li_path(const RenderScene& sc, Ray ray, HaltonSampler& sampler, RenderStats* st, HitRecord* first_hit) const {
+        Rgb l, beta(1.0);
+        bool specular_bounce = false;
+        uint64_t bounces = 0;
+        double eta_scale = 1.0;
+        for (;;) {
+            SI isect;
+            HitRecord rec;
+            if (st) st->extension_rays += 1;
+            bool found = sc.intersect_with_record(ray, &isect, &rec, st);
+            if (bounces == 0 && first_hit) *first_hit = rec;
+            (void)specular_bounce;  // isect.le() == 0 (Q22) and there are no infinite lights in scope
+            if (!found || bounces >= max_depth) break;
+            Bsdf bsdf;
+            material_bsdf(sc.materials[sc.geom->geos[isect.geo].material], isect, true, &bsdf);
+            if (!bsdf.present) {
+                // path.rs:101-106: `bounces -= 1` on usize — wraps in release, panics in debug (Q21)
+                if (st) st->asserts += 1;
+                break;
+            }
+            if (bsdf.num_components(BXDF_ALL & ~BXDF_SPECULAR) > 0) {
+                Rgb ld = beta * sc.uniform_sample_one_light(isect, bsdf, sampler, &light_distrib, st);
+                l += ld;
+            }
+            V3 wo = -ray.d, wi;
+            double pdf = 0.0;
+            uint8_t flags = 0;
+            Rgb f = bsdf.sample_f(wo, &wi, sampler.get_2d(), &pdf, BXDF_ALL, &flags);
+            if (f.is_black() || pdf == 0.0) break;
+            beta *= f * absdot(wi, isect.sh.n) / pdf;
+            if (!(beta.y() > 0.0) || !std::isfinite(beta.y())) {
+                if (st) st->asserts += 1;  // path.rs:146-147 assert!: the reference would panic here
+                break;
+            }
+            specular_bounce = (flags & BXDF_SPECULAR) != 0;
+            if ((flags & BXDF_SPECULAR) > 0 && (flags & BXDF_TRANSMISSION) > 0) {
+                double eta = bsdf.eta;
+                eta_scale *= (dot(wo, isect.n) > 0.0) ? (eta * eta) : 1.0 / (eta * eta);
+            }
+            ray = ray_new_od(isect.p, wi);  // spawn_ray (interaction.rs:60-62): no offset (Q8)
+            Rgb rr_beta = beta * eta_scale;
+            if (rr_beta.max_component_value() < rr_threshold && bounces > 3) {
+                double q = rmax(1.0 - rr_beta.max_component_value(), 0.05);
+                if (sampler.get_1d() < q) break;
+                beta /= 1.0 - q;
+            }
+            bounces += 1;
+            if (st) st->bounces += 1;
+        }
+        return l;
+    }
+    // DirectLightingIntegrator::li with UniformSampleOne (directlighting.rs:72-132).  The specular
+    // recursion (integrator/mod.rs:150-301) is followed without ray differentials.
+    Rgb li_direct(const RenderScene& sc, Ray ray, HaltonSampler& sampler, uint32_t depth, RenderStats* st,
+                  HitRecord* first_hit) const {
+        Rgb l;
+        SI isect;
+        HitRecord rec;
+        if (st) st->extension_rays += 1;
+        bool found = sc.intersect_with_record(ray, &isect, &rec, st);
+        if (first_hit) *first_hit = rec;
+        if (!found) return l;  // Light::le of point / distant lights is zero
+        Bsdf bsdf;
+        material_bsdf(sc.materials[sc.geom->geos[isect.geo].material], isect, false, &bsdf);
+        if (!bsdf.present) return li_direct(sc, ray_new_od(isect.p, ray.d), sampler, depth, st, nullptr);
+        if (!sc.lights.empty()) l += sc.uniform_sample_one_light(isect, bsdf, sampler, nullptr, st);
+        if (depth + 1 < max_depth) {
+            for (int pass = 0; pass < 2; ++pass) {
+                uint8_t ty = BXDF_SPECULAR | (pass == 0 ? BXDF_REFLECTION : BXDF_TRANSMISSION);
+                V3 wi;
+                double pdf = 0.0;
+                uint8_t sampled = 0;
+                Rgb f = bsdf.sample_f(isect.wo, &wi, sampler.get_2d(), &pdf, ty, &sampled);
+                V3 ns = isect.sh.n;
+                if (pdf > 0.0 && !f.is_black() && absdot(wi, ns) != 0.0)
+                    l += f * li_direct(sc, ray_new_od(isect.p, wi), sampler, depth + 1, st, nullptr) * absdot(wi, ns) / pdf;
+            }
+        }
+        return l;
+    }
+};
+
+struct RenderJob {
+    RenderScene scene;
+    Film film;
+    RealisticCamera camera;
+    Integrator integrator;
+    HaltonParams halton;
+    std::vector<uint16_t> perms;
+    uint64_t samples_per_pixel = 16;  // `nsamp`: nsamp - 1 samples are rendered (Q10)
+    RenderStats stats;
+    std::vector<HitDump> dump;
+    bool want_dump = false;
+
+    // SamplerIntegrator::si_render (integrator/mod.rs:48-139).  `tile_mod` / `tile_rank` deal the
+    // 16x16 tiles to ranks (tile index = ty * n_tiles_x + tx); (1, 0) renders everything.
+    // `crop`: optional pixel rectangle (x0,y0,x1,y1) — only those pixels are sampled (CPU baseline).
+    void render(int nthreads, uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop_px) {
+        integrator.light_distrib = Distribution1D(std::vector<double>(scene.lights.size(), 1.0));
+        int64_t sb[4];
+        film.sample_bounds(sb);
+        const int64_t tile_size = 16;
+        int64_t n_tiles_x = (sb[2] - sb[0] + tile_size - 1) / tile_size, n_tiles_y = (sb[3] - sb[1] + tile_size - 1) / tile_size;
+        int64_t n_tiles = n_tiles_x * n_tiles_y;
+        std::atomic<int64_t> next{0};
+        std::vector<RenderStats> tstats(std::max(1, nthreads));
+        std::vector<std::vector<HitDump>> tdump(std::max(1, nthreads));
+        std::vector<FilmTile*> done_tiles((size_t)n_tiles, nullptr);
+        auto worker = [&](int tid) {
+            RenderStats& st = tstats[tid];
+            for (;;) {
+                int64_t t = next.fetch_add(1);
+                if (t >= n_tiles) break;
+                if ((uint64_t)t % tile_mod != tile_rank) continue;
+                int64_t tx = t % n_tiles_x, ty = t / n_tiles_x;
+                int64_t tb[4] = {sb[0] + tx * tile_size, sb[1] + ty * tile_size, 0, 0};
+                tb[2] = std::min(tb[0] + tile_size, sb[2]);
+                tb[3] = std::min(tb[1] + tile_size, sb[3]);
+                if (crop_px && (tb[2] <= crop_px[0] || tb[0] >= crop_px[2] || tb[3] <= crop_px[1] || tb[1] >= crop_px[3])) continue;
+                HaltonSampler sampler;
+                sampler.hp = &halton;
+                sampler.perms = perms.data();
+                sampler.samples_per_pixel = samples_per_pixel;
+                FilmTile* tile = new FilmTile(film, tb);
+                for (int64_t py = tb[1]; py < tb[3]; ++py)
+                    for (int64_t px = tb[0]; px < tb[2]; ++px) {
+                        sampler.start_pixel(px, py);
+                        // pixel_bounds = full resolution (renderprocess.rs:1410)
+                        if (!(px >= 0 && px < film.xres && py >= 0 && py < film.yres)) continue;
+                        if (crop_px && !(px >= crop_px[0] && px < crop_px[2] && py >= crop_px[1] && py < crop_px[3])) continue;
+                        while (sampler.start_next_sample()) {
+                            CameraSample cs;
+                            P2 a = sampler.get_2d();
+                            cs.p_film = P2((double)px + a.x, (double)py + a.y);
+                            P2 b = sampler.get_2d();
+                            cs.p_lens = P2(b.x + 0.5, b.y + 0.5);  // Q11
+                            cs.time = sampler.get_1d() + 0.5;
+                            RayDiff rd;
+                            double w = camera.generate_ray_differential(cs, &rd);
+                            Rgb l;
+                            HitRecord first;
+                            if (w > 0.0) {
+                                st.camera_rays += 1;
+                                if (integrator.kind == INTEGRATOR_PATH)
+                                    l = integrator.li_path(scene, rd.ray, sampler, &st, &first);
+                                else
+                                    l = integrator.li_direct(scene, rd.ray, sampler, 1, &st, &first);
+                            } else {
+                                st.zero_weight += 1;
+                            }
+                            if (l.has_nan() || l.y() < -1e-5 || std::isinf(l.y())) l = Rgb();
+                            if (want_dump)
+                                tdump[tid].push_back(HitDump{(int32_t)px, (int32_t)py, (int32_t)sampler.current_sample_index,
+                                                             w > 0.0 ? first.prim : -2, w > 0.0 && first.prim >= 0 ? first.t : 0.0, w});
+                            tile->add_sample(cs.p_film, l, w);
+                        }
+                    }
+                done_tiles[(size_t)t] = tile;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int i = 0; i < std::max(1, nthreads); ++i) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+        // merge in tile order: deterministic f64 sums for pixels shared by several tiles
+        for (int64_t t = 0; t < n_tiles; ++t)
+            if (done_tiles[(size_t)t]) {
+                done_tiles[(size_t)t]->merge_into(film);
+                delete done_tiles[(size_t)t];
+            }
+        for (auto& s : tstats) {
+            stats.camera_rays += s.camera_rays;
+            stats.extension_rays += s.extension_rays;
+            stats.shadow_rays += s.shadow_rays;
+            stats.bounces += s.bounces;
+            stats.zero_weight += s.zero_weight;
+            stats.asserts += s.asserts;
+            for (TraversalStats* pair : {&stats.closest, &stats.any}) {
+                TraversalStats& src = (pair == &stats.closest) ? s.closest : s.any;
+                pair->rays += src.rays;
+                pair->nodes_visited += src.nodes_visited;
+                pair->prims_tested += src.prims_tested;
+                pair->max_stack = std::max(pair->max_stack, src.max_stack);
+                pair->stack_overflow += src.stack_overflow;
+            }
+        }
+        if (want_dump)
+            for (auto& d : tdump) dump.insert(dump.end(), d.begin(), d.end());
+    }
+};
+
+}  // namespace orc

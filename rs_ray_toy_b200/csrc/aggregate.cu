@@ -95,6 +95,18 @@ __device__ __forceinline__ bool sphere_test(D3 o, D3 d, D3 c, double radius, dou
     return true;
 }
 
+// One 256-bit load (LDG.E.256 on sm_100a): half a Node64 per request instead of a quarter.
+struct F8 {
+    float a, b, c, d, e, f, g, h;
+};
+__device__ __forceinline__ F8 ldg256(const void* p) {
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d), "=f"(r.e), "=f"(r.f), "=f"(r.g), "=f"(r.h)
+                 : "l"(p));
+    return r;
+}
+
 struct RayF {
     float idx, idy, idz;     // 1/d (fp32)
     float oidx, oidy, oidz;  // o * (1/d)
@@ -256,6 +268,10 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_MINBLOCKS 8
 #endif
 constexpr int kRefill = RRT_REFILL;
+#ifndef RRT_SSTACK
+#define RRT_SSTACK 16
+#endif
+constexpr int kSmemStack = RRT_SSTACK;
 
 template <bool ANY, bool WIDE>
 __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
@@ -268,7 +284,27 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
     const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
     const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
 
-    int32_t stack[kStack];
+    // Traversal stack: the first kSmemStack levels live in shared memory, laid out [level][thread]
+    // so that 32 lanes at 32 different depths still hit 32 different banks (one wavefront per
+    // push/pop); deeper levels spill to a per-thread local array.
+    __shared__ int32_t sstack[kSmemStack * kBlock];
+    int32_t lstack[kStack - kSmemStack];
+    int32_t* const my_stack = sstack + threadIdx.x;
+#define RRT_PUSH(v)                                            \
+    do {                                                       \
+        if (sp < kSmemStack) my_stack[sp * kBlock] = (v);      \
+        else lstack[sp - kSmemStack] = (v);                    \
+        ++sp;                                                  \
+    } while (0)
+#define RRT_POP(dst)                                                                     \
+    do {                                                                                 \
+        if (sp > 0) {                                                                    \
+            --sp;                                                                        \
+            (dst) = sp < kSmemStack ? my_stack[sp * kBlock] : lstack[sp - kSmemStack];   \
+        } else {                                                                         \
+            (dst) = kDone;                                                               \
+        }                                                                                \
+    } while (0)
     int sp = 0;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
     int32_t leaf = kNoLeaf;   // parked leaf reference
@@ -339,27 +375,28 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
         for (;;) {
             const bool walking = node >= 0 && node != kDone;
             if (walking) {
-                const float4* np = reinterpret_cast<const float4*>(nodes + node);
-                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), nz = __ldg(np + 2);
-                const int4 ch = __ldg(reinterpret_cast<const int4*>(np) + 3);
+                const char* np = reinterpret_cast<const char*>(nodes + node);
+                const F8 lo = ldg256(np);        // c0 x/y slabs, c1 x/y slabs
+                const F8 hi = ldg256(np + 32);   // z slabs of both, child references
+                const int32_t ch_x = __float_as_int(hi.e), ch_y = __float_as_int(hi.f);
                 float tn0, tn1;
-                const bool h0 = slab(rf, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, tcull, &tn0);
-                const bool h1 = slab(rf, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, tcull, &tn1);
+                const bool h0 = slab(rf, lo.a, lo.b, lo.c, lo.d, hi.a, hi.b, tcull, &tn0);
+                const bool h1 = slab(rf, lo.e, lo.f, lo.g, lo.h, hi.c, hi.d, tcull, &tn1);
                 if (h0 && h1) {
                     const bool swap = !ANY && (tn1 < tn0);
-                    stack[sp++] = swap ? ch.x : ch.y;
-                    node = swap ? ch.y : ch.x;
+                    RRT_PUSH(swap ? ch_x : ch_y);
+                    node = swap ? ch_y : ch_x;
                 } else if (h0) {
-                    node = ch.x;
+                    node = ch_x;
                 } else if (h1) {
-                    node = ch.y;
+                    node = ch_y;
                 } else {
-                    node = sp > 0 ? stack[--sp] : kDone;
+                    RRT_POP(node);
                 }
             }
             if (node < 0 && leaf == kNoLeaf) {  // park the first leaf, keep walking
                 leaf = node;
-                node = sp > 0 ? stack[--sp] : kDone;
+                RRT_POP(node);
             }
             // leave when no lane is still looking for its first leaf
             if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
@@ -401,7 +438,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                     sp = 0;
                 } else if (node < 0) {  // the walk had already reached another leaf
                     leaf = node;
-                    node = sp > 0 ? stack[--sp] : kDone;
+                    RRT_POP(node);
                 }
             }
         }
@@ -841,10 +878,13 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     stats_.build_usec =
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
     // L1-heavy kernels: no shared memory is used, give the whole carve-out to L1.
-    cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(trace_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(trace_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    // the only shared memory is the short stack; everything else of the 256 KB stays L1
+    int carve = (int)((RRT_MINBLOCKS * kSmemStack * kBlock * 4 * 100 + 227 * 1024 - 1) / (227 * 1024)) + 4;
+    if (carve > 100) carve = 100;
+    cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(trace_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(trace_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     return RRT_OK;
 }
 
