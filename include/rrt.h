@@ -123,6 +123,92 @@ int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_
 int rrt_intersect(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, rrt_hit* hits);
 int rrt_intersect_p(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, uint8_t* occluded);
 
+/* ---- the render loop ------------------------------------------------------------------------
+ * What deploy_render builds and runs (renderprocess.rs:92-105): make_scene + make_integrator,
+ * then Integrator::render -> SamplerIntegrator::si_render (integrator/mod.rs:48-139), executed
+ * as a wavefront of generate / extend / shade / shadow / accumulate kernels.                    */
+
+/* Material::compute_scattering_functions inputs with constant-valued textures
+ * (material/{matte,plastic,metal,mirror,glass}.rs; make_materials, renderprocess.rs:664-871).   */
+typedef enum rrt_material_kind {
+    RRT_MAT_MATTE = 0, RRT_MAT_PLASTIC = 1, RRT_MAT_METAL = 2, RRT_MAT_MIRROR = 3, RRT_MAT_GLASS = 4
+} rrt_material_kind;
+typedef struct rrt_material {
+    uint32_t kind;
+    uint32_t remap_roughness;
+    double kd[3], ks[3], kr[3], kt[3];
+    double metal_eta[3], metal_k[3];  /* FresnelConductor eta / k (default: copper)             */
+    double sigma;                     /* Matte: Oren-Nayar sigma in degrees                     */
+    double roughness;                 /* Plastic / Metal                                        */
+    double u_roughness, v_roughness;  /* Metal: < 0 = None (use roughness); Glass: values       */
+    double eta;                       /* Glass index                                            */
+} rrt_material;
+
+/* lights/point.rs, lights/distant.rs (make_light, renderprocess.rs:967-1053).                   */
+typedef enum rrt_light_kind { RRT_LIGHT_POINT = 0, RRT_LIGHT_DISTANT = 1 } rrt_light_kind;
+typedef struct rrt_light {
+    uint32_t kind;
+    uint32_t pad;
+    double intensity[3];  /* point: I ("spectrum"); distant: l * scale                          */
+    double dir[3];        /* distant: from - to                                                 */
+    double to_world[16];  /* light_to_world matrix, row-major (unused by point lights: Q17)     */
+} rrt_light;
+
+typedef enum rrt_filter_kind { RRT_FILTER_BOX = 0, RRT_FILTER_GAUSSIAN = 1, RRT_FILTER_TRIANGLE = 2 } rrt_filter_kind;
+typedef enum rrt_integrator_kind { RRT_INTEGRATOR_PATH = 0, RRT_INTEGRATOR_DIRECT = 1 } rrt_integrator_kind;
+
+/* make_film / make_camera / make_sampler / make_integrator arguments (renderprocess.rs:1306-1499). */
+typedef struct rrt_render_desc {
+    /* Film */
+    int64_t xres, yres;
+    double diagonal_mm, scale, max_sample_luminance;
+    uint32_t filter_kind, pad0;
+    double filter_radius[2], filter_alpha;
+    /* Camera (RealisticCamera) */
+    double cam_pos[3], cam_look[3], cam_up[3];
+    double shutter_open, shutter_close, aperture_diameter, focus_distance;
+    uint32_t simple_weighting, n_lens_values;
+    const double* lens_data;          /* 4 values per element interface, millimetres            */
+    /* Sampler (HaltonSampler) */
+    uint64_t nsamp;                   /* the reference renders nsamp - 1 samples per pixel (Q10) */
+    uint32_t sample_at_center, pad1;
+    uint64_t seed;                    /* digit-permutation seed (0 = identity); DESIGN.md §6    */
+    /* Integrator */
+    uint32_t integrator_kind, max_depth;
+    double rr_threshold;
+} rrt_render_desc;
+
+typedef struct rrt_render rrt_render; /* Box<dyn Integrator> + its film, camera and sampler      */
+
+int rrt_scene_set_materials(rrt_scene* scene, uint32_t n, const rrt_material* materials);
+int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
+/* deploy_render's loader: parses scene.json (+ the .obj files it names, relative to it) into a
+ * committed scene and the integrator that renders it.  `overrides_json` (may be NULL) replaces
+ * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */
+int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
+                        rrt_render** render);
+/* make_integrator for an assembled scene.                                                       */
+int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out);
+void rrt_render_destroy(rrt_render* render);
+/* Integrator::render for the 16x16 sample tiles t with t % tile_mod == tile_rank
+ * (integrator/mod.rs:55-71; tile index = tile_y * n_tiles_x + tile_x).  (1, 0) renders the frame.
+ * `crop` (may be NULL) = pixel rectangle x0,y0,x1,y1 to sample.  Accumulates into the film;
+ * returns after the device finished.                                                            */
+int rrt_render_run(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop);
+int rrt_render_clear(rrt_render* render);
+/* Film::write_image up to the float image (film.rs:323-366): rgb[yres*xres*3]; raw (may be NULL)
+ * [yres*xres*4] = pixel xyz + filter_weight_sum as the reference's Film would hold them.        */
+int rrt_render_read_film(rrt_render* render, double* rgb, double* raw);
+/* Device pointer to the accumulation film (4 f64 per pixel: RGB contribution sum, filter weight sum)
+ * for a multi-GPU gather/reduce; *n_doubles = 4 * xres * yres.                                   */
+int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_doubles);
+/* out16: camera rays, extension rays, shadow rays, bounces, zero-weight samples, samples, kernels
+ * launched, render microseconds, ...                                                            */
+int rrt_render_stats(const rrt_render* render, uint64_t out16[16]);
+/* First-hit record of every camera sample of the last run, in launch order: 6 doubles per sample
+ * (pixel x, pixel y, sample number, prim id or -1 miss / -2 zero weight, t, ray weight).         */
+int rrt_render_hit_dump(rrt_render* render, int enable, double* out, uint64_t capacity, uint64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 //
 // C entry points so that tests/ (ctypes) and bench.py's cpu_baseline leg can drive the
 // CPU restatement.  Nothing in the product links or loads this file.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -365,5 +366,256 @@ int32_t orc_prim_intersect_p(void* sp, uint32_t prim, const double* ray7) {
     return s->geom.prim_intersect_p(s->geom.prims[prim], r) ? 1 : 0;
 }
 int32_t orc_hardware_threads() { return (int32_t)std::thread::hardware_concurrency(); }
+
+}  // extern "C"
+
+// ================================ rendering ==================================================
+#include "rt_render.hpp"
+
+namespace {
+struct RenderSetup {
+    std::vector<Material> materials;
+    std::vector<Light> light_specs;  // distant: w_light holds the raw (from - to) until render time
+    std::vector<Xform> light_xf;
+};
+std::vector<std::pair<void*, RenderSetup>> g_setups;
+RenderSetup& setup_of(void* s) {
+    for (auto& p : g_setups)
+        if (p.first == s) return p.second;
+    g_setups.emplace_back(s, RenderSetup());
+    return g_setups.back().second;
+}
+}  // namespace
+
+extern "C" {
+
+// Material table.  26 doubles per material:
+//  0 kind (MaterialKind) | 1-3 kd | 4-6 ks | 7-9 kr | 10-12 kt | 13-15 metal eta | 16-18 metal k |
+//  19 sigma | 20 roughness | 21 u_roughness (<0 = None) | 22 v_roughness | 23 glass eta | 24 remap | 25 pad
+void orc_set_materials(void* sp, uint32_t n, const double* m) {
+    RenderSetup& rs = setup_of(sp);
+    rs.materials.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        const double* a = m + 26 * (size_t)i;
+        Material mat;
+        mat.kind = (uint32_t)a[0];
+        mat.kd = Rgb(a[1], a[2], a[3]);
+        mat.ks = Rgb(a[4], a[5], a[6]);
+        mat.kr = Rgb(a[7], a[8], a[9]);
+        mat.kt = Rgb(a[10], a[11], a[12]);
+        mat.eta_rgb = Rgb(a[13], a[14], a[15]);
+        mat.k_rgb = Rgb(a[16], a[17], a[18]);
+        mat.sigma = a[19];
+        mat.roughness = a[20];
+        mat.u_roughness = a[21];
+        mat.v_roughness = a[22];
+        mat.eta = a[23];
+        mat.remap_roughness = a[24] != 0.0;
+        rs.materials.push_back(mat);
+    }
+}
+// Lights.  24 doubles per light: 0 kind | 1-3 I or L | 4-6 point: p_light, distant: from - to |
+// 7-22 light_to_world m (row-major) | 23 pad.  (The inverse is not needed: vectors use m.)
+void orc_set_lights(void* sp, uint32_t n, const double* l) {
+    RenderSetup& rs = setup_of(sp);
+    rs.light_specs.clear();
+    rs.light_xf.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        const double* a = l + 24 * (size_t)i;
+        Light lt;
+        lt.kind = (uint32_t)a[0];
+        lt.intensity = Rgb(a[1], a[2], a[3]);
+        lt.p_light = V3(a[4], a[5], a[6]);
+        lt.w_light = V3(a[4], a[5], a[6]);
+        Xform x;
+        std::memcpy(x.m.m, a + 7, 16 * sizeof(double));
+        x.inv = x.m;  // unused
+        rs.light_specs.push_back(lt);
+        rs.light_xf.push_back(x);
+    }
+}
+
+// params (doubles):
+//  0 xres 1 yres 2 diagonal_mm 3 filter kind 4 rx 5 ry 6 alpha 7 scale 8 max_sample_luminance
+//  9-11 camera world_pos 12-14 look 15-17 up 18 shutter_open 19 shutter_close 20 aperture_diameter
+//  21 focus_distance 22 simple_weighting 23 nsamp 24 sample_at_center 25 seed 26 integrator kind
+//  27 max_depth 28 rr_threshold 29 tile_mod 30 tile_rank 31 crop flag 32-35 crop x0 y0 x1 y1 36 want_dump
+// outputs: rgb[3*npix] (Film::write_image values before the PNG quantisation), raw[4*npix]
+// (xyz + filter_weight_sum), stats[16], dump (6 doubles per camera sample, capacity dump_cap).
+int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_t n_lens_values, double* rgb,
+                   double* raw, uint64_t* stats16, double* dump, uint64_t dump_cap, uint64_t* dump_count,
+                   int32_t nthreads) {
+    Scene* s = (Scene*)sp;
+    if (!s->built) {
+        g_err = "orc_render: scene not built";
+        return -1;
+    }
+    try {
+        RenderSetup& rs = setup_of(sp);
+        RenderJob job;
+        job.scene.geom = &s->geom;
+        job.scene.bvh = &s->bvh;
+        job.scene.materials = rs.materials;
+        job.scene.fix_q9 = s->geom.q.fix_q9;
+        for (const GeoPrim& g : s->geom.geos)
+            if (g.material < 0 || (size_t)g.material >= rs.materials.size()) throw std::runtime_error("material index out of range");
+        B3 wb = s->bvh.world_bound();
+        for (size_t i = 0; i < rs.light_specs.size(); ++i) {
+            Light lt = rs.light_specs[i];
+            if (lt.kind == LIGHT_POINT) {
+                lt.p_light = V3(0.0, 0.0, 0.0);  // Q17: PointLight::new(.., Point3f::default(), ..), light_to_world unused
+            } else {
+                lt.w_light = normalize_vec(xf_vector(rs.light_xf[i], lt.w_light));  // distant.rs:30
+                b3_bounding_sphere(wb, &lt.world_center, &lt.world_radius);
+            }
+            job.scene.lights.push_back(lt);
+        }
+        Filter f;
+        f.kind = (uint32_t)prm[3];
+        f.rx = prm[4];
+        f.ry = prm[5];
+        f.alpha = prm[6];
+        job.film.init((int64_t)prm[0], (int64_t)prm[1], prm[2], f, prm[7], prm[8]);
+        Xform to_camera = xf_look_at(V3(prm[9], prm[10], prm[11]), V3(prm[12], prm[13], prm[14]), V3(prm[15], prm[16], prm[17]));
+        std::vector<double> lens(lens_data, lens_data + n_lens_values);
+        job.camera.init(xf_inverse(to_camera), prm[18], prm[19], prm[20], prm[21], &job.film, lens, prm[22] != 0.0,
+                        std::max(1, nthreads));
+        job.samples_per_pixel = (uint64_t)prm[23];
+        job.halton.init(job.film.crop[2] - job.film.crop[0], job.film.crop[3] - job.film.crop[1], prm[24] != 0.0);
+        job.perms = compute_radical_inverse_permutations((uint64_t)prm[25]);
+        job.integrator.kind = (uint32_t)prm[26];
+        job.integrator.max_depth = (uint32_t)prm[27];
+        job.integrator.rr_threshold = prm[28];
+        job.want_dump = prm[36] != 0.0 && dump != nullptr;
+        int64_t crop[4] = {(int64_t)prm[32], (int64_t)prm[33], (int64_t)prm[34], (int64_t)prm[35]};
+        job.render(std::max(1, nthreads), std::max<uint32_t>(1, (uint32_t)prm[29]), (uint32_t)prm[30],
+                   prm[31] != 0.0 ? crop : nullptr);
+        size_t npix = job.film.pixels.size();
+        if (rgb) film_to_rgb(job.film, rgb);
+        if (raw)
+            for (size_t i = 0; i < npix; ++i) {
+                raw[4 * i] = job.film.pixels[i].xyz[0];
+                raw[4 * i + 1] = job.film.pixels[i].xyz[1];
+                raw[4 * i + 2] = job.film.pixels[i].xyz[2];
+                raw[4 * i + 3] = job.film.pixels[i].filter_weight_sum;
+            }
+        if (stats16) {
+            const RenderStats& st = job.stats;
+            uint64_t v[16] = {st.camera_rays, st.extension_rays, st.shadow_rays, st.bounces, st.zero_weight, st.asserts,
+                              st.closest.rays, st.closest.nodes_visited, st.closest.prims_tested, st.closest.max_stack,
+                              st.any.rays, st.any.nodes_visited, st.any.prims_tested, st.any.max_stack,
+                              st.closest.stack_overflow + st.any.stack_overflow, 0};
+            std::memcpy(stats16, v, sizeof(v));
+        }
+        if (dump_count) *dump_count = job.dump.size();
+        if (job.want_dump) {
+            std::sort(job.dump.begin(), job.dump.end(), [](const HitDump& a, const HitDump& b) {
+                if (a.py != b.py) return a.py < b.py;
+                if (a.px != b.px) return a.px < b.px;
+                return a.sample < b.sample;
+            });
+            uint64_t n = std::min<uint64_t>(dump_cap, job.dump.size());
+            for (uint64_t i = 0; i < n; ++i) {
+                const HitDump& d = job.dump[i];
+                double* o = dump + 6 * i;
+                o[0] = d.px; o[1] = d.py; o[2] = d.sample; o[3] = d.prim; o[4] = d.t; o[5] = d.weight;
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Camera-only probe: the CameraSample, world ray and weight of every sample of one pixel
+// (13 doubles per sample: p_film 2, p_lens 2, time, o 3, d 3, weight, halton index as double).
+int32_t orc_camera_samples(const double* prm, const double* lens_data, uint32_t n_lens_values, int64_t px, int64_t py,
+                           double* out, uint32_t max_samples, int32_t nthreads) {
+    try {
+        Film film;
+        Filter f;
+        f.kind = (uint32_t)prm[3];
+        f.rx = prm[4];
+        f.ry = prm[5];
+        f.alpha = prm[6];
+        film.init((int64_t)prm[0], (int64_t)prm[1], prm[2], f, prm[7], prm[8]);
+        RealisticCamera cam;
+        Xform to_camera = xf_look_at(V3(prm[9], prm[10], prm[11]), V3(prm[12], prm[13], prm[14]), V3(prm[15], prm[16], prm[17]));
+        std::vector<double> lens(lens_data, lens_data + n_lens_values);
+        cam.init(xf_inverse(to_camera), prm[18], prm[19], prm[20], prm[21], &film, lens, prm[22] != 0.0, std::max(1, nthreads));
+        HaltonParams hp;
+        hp.init(film.crop[2] - film.crop[0], film.crop[3] - film.crop[1], prm[24] != 0.0);
+        std::vector<uint16_t> perms = compute_radical_inverse_permutations((uint64_t)prm[25]);
+        HaltonSampler sm;
+        sm.hp = &hp;
+        sm.perms = perms.data();
+        sm.samples_per_pixel = (uint64_t)prm[23];
+        sm.start_pixel(px, py);
+        uint32_t k = 0;
+        while (sm.start_next_sample() && k < max_samples) {
+            CameraSample cs;
+            P2 a = sm.get_2d();
+            cs.p_film = P2((double)px + a.x, (double)py + a.y);
+            P2 b = sm.get_2d();
+            cs.p_lens = P2(b.x + 0.5, b.y + 0.5);
+            cs.time = sm.get_1d() + 0.5;
+            RayDiff rd;
+            double w = cam.generate_ray_differential(cs, &rd);
+            double* o = out + 13 * (size_t)k;
+            o[0] = cs.p_film.x; o[1] = cs.p_film.y; o[2] = cs.p_lens.x; o[3] = cs.p_lens.y; o[4] = cs.time;
+            o[5] = rd.ray.o.x; o[6] = rd.ray.o.y; o[7] = rd.ray.o.z; o[8] = rd.ray.d.x; o[9] = rd.ray.d.y; o[10] = rd.ray.d.z;
+            o[11] = w; o[12] = (double)sm.interval_sample_index;
+            ++k;
+        }
+        return (int32_t)k;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Halton KAT hooks (lowdiscrepancy.rs / halton.rs)
+double orc_radical_inverse(int32_t base_index, uint64_t a) { return radical_inverse(base_index, a); }
+double orc_scrambled_radical_inverse(int32_t base_index, uint64_t a, uint64_t seed) {
+    std::vector<uint16_t> perms = compute_radical_inverse_permutations(seed);
+    return scrambled_radical_inverse(base_index, a, perms.data() + prime_table().sums[base_index]);
+}
+uint64_t orc_halton_index(int64_t xres, int64_t yres, int64_t px, int64_t py, uint64_t sample_num, uint64_t* stride) {
+    HaltonParams hp;
+    hp.init(xres, yres, false);
+    if (stride) *stride = hp.sample_stride;
+    return hp.offset_for_pixel(px, py) + sample_num * hp.sample_stride;
+}
+void orc_halton_perms(uint64_t seed, uint16_t* out, uint32_t n) {
+    std::vector<uint16_t> perms = compute_radical_inverse_permutations(seed);
+    std::memcpy(out, perms.data(), std::min<size_t>(n, perms.size()) * sizeof(uint16_t));
+}
+// BSDF probe for unit tests: evaluates f, pdf and one sample of a material's Bsdf in a frame with
+// shading normal +z, dpdu +x.  out: f(3), pdf, sample f(3), wi(3), pdf, sampled_type
+void orc_bsdf_probe(const double* m26, const double* wo3, const double* wi3, const double* u2, int32_t allow_multiple,
+                    double* out12) {
+    Material mat;
+    const double* a = m26;
+    mat.kind = (uint32_t)a[0];
+    mat.kd = Rgb(a[1], a[2], a[3]); mat.ks = Rgb(a[4], a[5], a[6]); mat.kr = Rgb(a[7], a[8], a[9]);
+    mat.kt = Rgb(a[10], a[11], a[12]); mat.eta_rgb = Rgb(a[13], a[14], a[15]); mat.k_rgb = Rgb(a[16], a[17], a[18]);
+    mat.sigma = a[19]; mat.roughness = a[20]; mat.u_roughness = a[21]; mat.v_roughness = a[22]; mat.eta = a[23];
+    mat.remap_roughness = a[24] != 0.0;
+    SI si = si_new(V3(0, 0, 0), P2(0, 0), V3(wo3[0], wo3[1], wo3[2]), V3(1, 0, 0), V3(0, 1, 0), V3(), V3(), 0.0);
+    Bsdf b;
+    material_bsdf(mat, si, allow_multiple != 0, &b);
+    V3 wo(wo3[0], wo3[1], wo3[2]), wi(wi3[0], wi3[1], wi3[2]);
+    Rgb f = b.f(wo, wi, BXDF_ALL);
+    out12[0] = f.c[0]; out12[1] = f.c[1]; out12[2] = f.c[2];
+    out12[3] = b.pdf(wo, wi, BXDF_ALL);
+    V3 swi;
+    double pdf = 0.0;
+    uint8_t ty = 0;
+    Rgb sf = b.sample_f(wo, &swi, P2(u2[0], u2[1]), &pdf, BXDF_ALL, &ty);
+    out12[4] = sf.c[0]; out12[5] = sf.c[1]; out12[6] = sf.c[2];
+    out12[7] = swi.x; out12[8] = swi.y; out12[9] = swi.z;
+    out12[10] = pdf; out12[11] = (double)ty;
+}
 
 }  // extern "C"

@@ -265,7 +265,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_REFILL 8
 #endif
 #ifndef RRT_MINBLOCKS
-#define RRT_MINBLOCKS 8
+#define RRT_MINBLOCKS 7
 #endif
 constexpr int kRefill = RRT_REFILL;
 #ifndef RRT_SSTACK

@@ -1,0 +1,312 @@
+"""Oracle-side restatement (Python; TEST INFRASTRUCTURE) of the reference's scene description
+loader: src/renderprocess.rs (schema subset of SURVEY.md Appendix C) and src/objparser.rs.
+It feeds the C++ oracle through oracle_lib.  The product has its own loader in C++
+(rs_ray_toy_b200/csrc/scene_json.cpp); the parity tests run both on the same files."""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+
+import oracle_lib as O
+
+MAT_KIND = {"MatteMaterial": 0, "PlasticMaterial": 1, "MetalMaterial": 2, "MirrorMaterial": 3, "GlassMaterial": 4}
+FILTER_KIND = {"BoxFilter": 0, "GaussianFilter": 1, "TriangleFilter": 2}
+
+
+def copper_rgb():
+    """COPPER_N / COPPER_K as RGB (material/metal.rs tables through RGBSpectrum::from_sampled,
+    spectrum.rs:2701-2727); values in tests/golden/copper_rgb.json (make_copper_rgb.py)."""
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "copper_rgb.json").read_text())
+    return g["eta"], g["k"]
+
+
+def parse_obj(path):
+    """objparser.rs:83-247: v / vt / vn / f only, first three vertices of a face, 1-based indices;
+    `vn` is normalised on read (:130); index triples are kept only when every one is in range."""
+    p, uv, n, vi, ni, uvi = [], [], [], [], [], []
+    for line in Path(path).read_text().splitlines():
+        sp = line.split()
+        if not sp:
+            continue
+        if sp[0] == "v":
+            p.append([float(sp[1]), float(sp[2]), float(sp[3])])
+        elif sp[0] == "vt":
+            uv.append([float(sp[1]), float(sp[2]) if len(sp) > 2 else 0.0])
+        elif sp[0] == "vn":
+            v = np.array([float(sp[1]), float(sp[2]), float(sp[3])])
+            n.append((v / math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])).tolist())
+        elif sp[0] == "f":
+            if len(sp) < 4:
+                raise ValueError("ParseObjError: Failed to get face element")
+            el = []
+            for tok in sp[1:4]:
+                parts = []
+                for s in tok.split("/"):
+                    try:
+                        parts.append(int(s) - 1 if int(s) >= 0 and s.isdigit() else None)
+                    except ValueError:
+                        parts.append(None)
+                parts = (parts + [None, None, None])[:3]
+                el.append(parts)
+            if all(e[0] is not None for e in el):
+                vi += [e[0] for e in el]
+                if all(e[1] is not None for e in el) and uv and all(e[1] < len(uv) for e in el):
+                    uvi += [e[1] for e in el]
+                if all(e[2] is not None for e in el) and n and all(e[2] < len(n) for e in el):
+                    ni += [e[2] for e in el]
+    ntri = len(vi) // 3
+    return dict(
+        p=np.array(p, dtype=np.float64).reshape(-1, 3), vi=np.array(vi, dtype=np.uint32).reshape(-1, 3),
+        n=np.array(n, dtype=np.float64).reshape(-1, 3) if n else None,
+        ni=np.array(ni, dtype=np.uint32).reshape(-1, 3) if len(ni) == 3 * ntri and ntri else None,
+        uv=np.array(uv, dtype=np.float64).reshape(-1, 2) if uv else None,
+        uvi=np.array(uvi, dtype=np.uint32).reshape(-1, 3) if len(uvi) == 3 * ntri and ntri else None)
+
+
+def _xyz(cfg, key, default):
+    v = cfg.get(key)
+    if isinstance(v, list) and len(v) >= 3:
+        return [float(v[0]), float(v[1]), float(v[2])]
+    return list(default)
+
+
+def to_world(cfg):
+    """make_to_world (renderprocess.rs:242-252)."""
+    return O.make_to_world(_xyz(cfg, "world_pos", (0, 0, 0)), _xyz(cfg, "rotation_axis", (0, 0, 0)),
+                           float(cfg.get("rotation_angle", 0.0)), _xyz(cfg, "scale", (1, 1, 1)))
+
+
+def _spectrum(cfg, key, default):
+    v = cfg.get(key)
+    if isinstance(v, dict) and isinstance(v.get("values"), list):
+        return [float(x) for x in v["values"][:3]]
+    return [float(default)] * 3 if not isinstance(default, (list, tuple)) else list(default)
+
+
+class Textures:
+    """Only what the in-scope materials can reach: a BilerpTexture whose corners agree is a
+    constant (the loader reads v10 and v11 from key "v01", renderprocess.rs:326-329,439-442)."""
+
+    def __init__(self, cfg):
+        self.f, self.rgb = {}, {}
+        for t in cfg.get("float_texture", []) or []:
+            if t.get("texture_type") == "BilerpTexture":
+                v00, v01 = float(t.get("v00", 0.0)), float(t.get("v01", 1.0))
+                if v00 == v01:
+                    self.f[t.get("texture_name", "DefaultTextureName")] = v00
+        for t in cfg.get("rgb_texture", []) or []:
+            if t.get("texture_type") == "BilerpTexture":
+                v00, v01 = _spectrum(t, "v00", 0.0), _spectrum(t, "v01", 1.0)
+                if v00 == v01:
+                    self.rgb[t.get("texture_name", "DefaultTextureName")] = v00
+
+    def fval(self, cfg, key, default):
+        name = cfg.get(key)
+        if isinstance(name, str):
+            if name not in self.f:
+                raise ValueError(f"float texture {name!r} is outside the restated subset")
+            return self.f[name]
+        return default
+
+    def rgbval(self, cfg, key, default):
+        name = cfg.get(key)
+        if isinstance(name, str) and name in self.rgb:
+            return self.rgb[name]
+        return [default] * 3 if not isinstance(default, (list, tuple)) else list(default)
+
+
+def material_row(cfg, tex: Textures):
+    """make_materials (renderprocess.rs:664-871) -> the oracle's 26-double material record."""
+    kind = MAT_KIND.get(cfg.get("material_type", ""))
+    if kind is None:
+        return None
+    r = np.zeros(26)
+    r[0] = kind
+    r[21] = r[22] = -1.0
+    cu_n, cu_k = copper_rgb()
+    if kind == 0:
+        r[1:4] = tex.rgbval(cfg, "kd", 0.5)
+        r[19] = tex.fval(cfg, "sigma", 0.0)
+    elif kind == 1:
+        r[1:4] = tex.rgbval(cfg, "kd", 0.25)
+        r[4:7] = tex.rgbval(cfg, "ks", 0.25)
+        r[20] = tex.fval(cfg, "roughness", 0.1)
+    elif kind == 2:
+        r[13:16] = tex.rgbval(cfg, "eta", cu_n)
+        r[16:19] = tex.rgbval(cfg, "k", cu_k)
+        r[20] = tex.fval(cfg, "roughness", 0.01)
+        r[21] = tex.fval(cfg, "u_roughness", -1.0)
+        r[22] = tex.fval(cfg, "v_roughness", -1.0)
+    elif kind == 3:
+        r[7:10] = tex.rgbval(cfg, "kr", 0.9)
+    elif kind == 4:
+        r[7:10] = tex.rgbval(cfg, "kr", 1.0)
+        r[10:13] = tex.rgbval(cfg, "kt", 1.0)
+        r[23] = tex.fval(cfg, "eta", 1.5)
+        r[21] = tex.fval(cfg, "u_roughness", 0.0)
+        r[22] = tex.fval(cfg, "v_roughness", 0.0)
+    r[24] = 1.0 if cfg.get("remap_roughness", False) else 0.0
+    return r
+
+
+def light_row(cfg):
+    """make_light (renderprocess.rs:967-1053): point and distant."""
+    r = np.zeros(24)
+    m, _ = to_world(cfg)
+    r[7:23] = m.reshape(16)
+    t = cfg.get("light_type")
+    if t == "point":
+        r[0] = 0
+        r[1:4] = _spectrum(cfg, "spectrum", 1.0)
+    elif t == "distant":
+        r[0] = 1
+        l, sc = np.array(_spectrum(cfg, "l", 1.0)), np.array(_spectrum(cfg, "scale", 1.0))
+        r[1:4] = l * sc
+        r[4:7] = np.array(_xyz(cfg, "from", (0, 0, 0))) - np.array(_xyz(cfg, "to", (0, 0, 1)))
+    else:
+        raise ValueError(f"light type {t!r} is outside the restated subset")
+    return r
+
+
+def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=False):
+    """make_film / make_camera / make_sampler / make_integrator (renderprocess.rs:1306-1499)."""
+    film, cam, smp, integ = cfg["Film"], cfg["Camera"], cfg["Sampler"], cfg["Integrator"]
+    p = np.zeros(40)
+    p[0], p[1] = int(film.get("xres", 1280)), int(film.get("yres", 720))
+    p[2] = float(film.get("diagonal", 35.0))
+    flt = film["Filter"]
+    ftype = flt.get("filter_type", "BoxFilter")
+    kind = FILTER_KIND.get(ftype, 0)
+    rad = flt.get("radius")
+    default_r = (0.5, 0.5) if kind == 0 else (2.0, 2.0)
+    rx, ry = (float(rad[0]), float(rad[1])) if isinstance(rad, list) and len(rad) >= 2 else default_r
+    p[3], p[4], p[5], p[6] = kind, rx, ry, float(flt.get("alpha", 2.0))
+    p[7] = float(film.get("scale", 1.0))
+    p[8] = float(film.get("max_sample_luminance", math.inf))
+    p[9:12] = _xyz(cam, "world_pos", (0, 0, 0))
+    p[12:15] = _xyz(cam, "look", (1, 1, 1))
+    p[15:18] = _xyz(cam, "up", (0, 0, 1))
+    p[18], p[19] = float(cam.get("shutter_open", 0.0)), float(cam.get("shutter_close", 1.0))
+    p[20], p[21] = float(cam.get("aperture_diameter", 1.0)), float(cam.get("focus_distance", 10.0))
+    p[22] = 1.0 if cam.get("simple_weighting", True) else 0.0
+    if smp.get("sampler_type") != "HaltonSampler":
+        raise ValueError("only HaltonSampler is reproducible (SURVEY.md Q12)")
+    p[23] = int(smp.get("nsamp", 16))
+    p[24] = 1.0 if smp.get("sample_at_center", False) else 0.0
+    p[25] = seed
+    it = integ.get("integrator_type", "AO")
+    if it == "Path":
+        p[26], p[27], p[28] = 0, int(integ.get("max_depth", 5)), float(integ.get("rr_threshold", 1.0))
+    elif it == "DirectLighting":
+        if integ.get("light_strategy", "one") == "all":
+            raise ValueError("light_strategy 'all' is outside the restated subset")
+        p[26], p[27], p[28] = 1, int(integ.get("max_depth", 5)), 1.0
+    else:
+        raise ValueError(f"integrator {it!r} is outside the restated subset")
+    p[29], p[30] = tile_mod, tile_rank
+    if crop is not None:
+        p[31] = 1.0
+        p[32:36] = crop
+    p[36] = 1.0 if want_dump else 0.0
+    lens = np.array(cam["lens_data"], dtype=np.float64).reshape(-1)
+    return p, lens
+
+
+class LoadedScene:
+    def __init__(self, cfg, root: Path, tier=O.TIER_F):
+        self.cfg = cfg
+        self.scene = O.OracleScene(tier)
+        tex = Textures(cfg)
+        rows, self.mat_index = [], {}
+        for m in cfg.get("materials", []) or []:
+            row = material_row(m, tex)
+            if row is not None:
+                self.mat_index[m.get("material_name", "DefaultMaterialName")] = len(rows)
+                rows.append(row)
+        self.materials = np.array(rows).reshape(-1, 26)
+        meshes = {}
+        for o in cfg.get("objs", []) or []:
+            meshes[o.get("obj_name", "DefaultObjName")] = parse_obj(root / o.get("filename", "DefaultObj"))
+        s = self.scene
+        agg = cfg["Aggregate"]
+        for prim in agg.get("primitives", []) or []:
+            mat = self.mat_index.get(prim.get("material_name", "DefaultMaterialName"))
+            inst = prim.get("instances")
+            if prim.get("primitive_type") == "sphere":
+                if mat is None:
+                    continue
+                m, inv = to_world(prim)
+                radius = float(prim.get("radius", 1.0))
+                sp = s.add_sphere(m, inv, radius, float(prim.get("z_min", -radius)), float(prim.get("z_max", radius)),
+                                  float(prim.get("phi_max", 360.0)))
+                g = s.add_geo_sphere(sp, mat)
+                if isinstance(inst, list):
+                    for ic in inst:
+                        im, iinv = to_world(ic)
+                        s.add_prims(g, 1, s.add_xform(im, iinv))
+                else:
+                    s.add_prims(g, 1, -1)
+            elif prim.get("primitive_type") == "triangle":
+                mesh = meshes.get(prim.get("obj_name", "DefaultObjName"))
+                if mesh is None or mat is None:
+                    continue
+                mid = s.add_mesh(mesh["p"], mesh["vi"], mesh["n"], mesh["ni"], mesh["uv"], mesh["uvi"])
+                g0 = s.add_geo_triangles(mid, mat)
+                nt = mesh["vi"].shape[0]
+                if isinstance(inst, list):
+                    for ic in inst:
+                        im, iinv = to_world(ic)
+                        s.add_prims(g0, nt, s.add_xform(im, iinv))
+                else:
+                    s.add_prims(g0, nt, -1)
+        s.build(int(agg.get("max_prims_in_node", 4)))
+        self.lights = np.array([light_row(l) for l in (cfg.get("lights", []) or [])]).reshape(-1, 24)
+        L = O.lib()
+        L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_set_materials(s.h, self.materials.shape[0], self.materials.ctypes.data)
+        L.orc_set_lights(s.h, self.lights.shape[0], self.lights.ctypes.data)
+
+    def render(self, seed=1, nthreads=None, tile_mod=1, tile_rank=0, crop=None, want_dump=False):
+        prm, lens = render_params(self.cfg, seed, tile_mod, tile_rank, crop, want_dump)
+        return oracle_render(self.scene, prm, lens, nthreads, want_dump)
+
+
+def oracle_render(scene, prm, lens, nthreads=None, want_dump=False):
+    L = O.lib()
+    L.orc_render.restype = C.c_int32
+    L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32]
+    xres, yres = int(prm[0]), int(prm[1])
+    npix = xres * yres
+    rgb = np.zeros((yres, xres, 3))
+    raw = np.zeros((yres, xres, 4))
+    stats = np.zeros(16, dtype=np.uint64)
+    cap = npix * max(1, int(prm[23]) - 1) if want_dump else 0
+    dump = np.zeros((max(cap, 1), 6))
+    cnt = C.c_uint64(0)
+    nthreads = O.hardware_threads() if nthreads is None else nthreads
+    rc = L.orc_render(scene.h, prm.ctypes.data, lens.ctypes.data, lens.shape[0], rgb.ctypes.data, raw.ctypes.data,
+                      stats.ctypes.data, dump.ctypes.data if want_dump else None, cap, C.byref(cnt), nthreads)
+    if rc != 0:
+        raise RuntimeError(L.orc_last_error().decode())
+    names = ["camera_rays", "extension_rays", "shadow_rays", "bounces", "zero_weight", "asserts", "closest_rays",
+             "closest_nodes", "closest_prims", "closest_max_stack", "any_rays", "any_nodes", "any_prims", "any_max_stack",
+             "stack_overflow", "_"]
+    out = {"rgb": rgb, "raw": raw, "stats": {k: int(v) for k, v in zip(names, stats)}}
+    if want_dump:
+        out["dump"] = dump[: min(cap, cnt.value)]
+    return out
+
+
+def load(path, overrides=None, tier=O.TIER_F) -> LoadedScene:
+    path = Path(path)
+    cfg = json.loads(path.read_text())
+    for k, v in (overrides or {}).items():
+        cfg[k] = copy.deepcopy(v)
+    return LoadedScene(cfg, path.parent, tier)
