@@ -187,6 +187,10 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
  * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */
 int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
                         rrt_render** render);
+/* Host-only view of what the loader reads (no device is touched): out8 = primitives, meshes,
+ * spheres, instances, materials, lights, max_prims_in_node, lens values; desc = the render
+ * description (lens_data pointer left NULL).  Used by the CPU test-suite and by tooling.          */
+int rrt_scene_json_probe(const char* path, const char* overrides_json, uint64_t out8[8], rrt_render_desc* desc);
 /* make_integrator for an assembled scene.                                                       */
 int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out);
 void rrt_render_destroy(rrt_render* render);

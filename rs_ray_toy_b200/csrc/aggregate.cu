@@ -278,8 +278,10 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                                                         rrt_hit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                         const uint32_t* __restrict__ perm,
                                                         const uint32_t* __restrict__ use_perm,
-                                                        unsigned long long* __restrict__ cursor) {
+                                                        unsigned long long* __restrict__ cursor,
+                                                        const uint32_t* __restrict__ n_dev) {
     const unsigned FULL = 0xffffffffu;
+    if (n_dev) n = *n_dev;  // wavefront queues: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
     const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
     const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
@@ -490,7 +492,9 @@ __device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r) 
 
 __global__ void __launch_bounds__(256) sort_count_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
                                                           uint32_t* __restrict__ bins, uint32_t* __restrict__ key_out,
-                                                          uint32_t* __restrict__ rank_out) {
+                                                          uint32_t* __restrict__ rank_out,
+                                                          const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = *n_dev;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t key = valid ? ray_key(A, rays + i) : 0xFFFFFFFFu;
@@ -544,7 +548,9 @@ __global__ void __launch_bounds__(kScanBlock) scan_block_kernel(uint32_t* __rest
 }
 __global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t nblocks,
                                                                 const uint32_t* __restrict__ max_bin, uint64_t n,
-                                                                uint32_t* __restrict__ use_perm) {
+                                                                uint32_t* __restrict__ use_perm,
+                                                                const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = *n_dev;
     // nblocks <= kScanBlock * 16: a serial carry over chunks of kScanBlock
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t* __restr
         carry = 0;
         // coherent batches (one bin holding > 1/64 of the rays, and at least 4096) keep input order
         const uint32_t mb = *max_bin;
-        *use_perm = ((uint64_t)mb * 64u > n && mb >= 4096u) ? 0u : 1u;
+        *use_perm = (((uint64_t)mb * 64u > n && mb >= 4096u) || n < 4096u) ? 0u : 1u;
     }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -589,7 +595,9 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t n, const uin
                                                             const uint32_t* __restrict__ key,
                                                             const uint32_t* __restrict__ rank,
                                                             const uint32_t* __restrict__ use_perm,
-                                                            uint32_t* __restrict__ perm) {
+                                                            uint32_t* __restrict__ perm,
+                                                            const uint32_t* __restrict__ n_dev) {
+    if (n_dev) n = *n_dev;
     if (*use_perm == 0u) return;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -916,7 +924,7 @@ int DeviceAggregate::ensure_workspace(uint64_t n, std::string* err) const {
 
 template <bool ANY>
 int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, uint8_t* d_occ, void* stream,
-                           std::string* err, int* launches) const {
+                           std::string* err, int* launches, const uint32_t* n_dev) const {
     if (n == 0) return RRT_OK;
     if (n >= (1ull << 32)) {
         if (err) *err = "batch too large for one call (2^32 rays)";
@@ -936,10 +944,11 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     if (sorting) {
         RRT_CUDA(cudaMemsetAsync(w.d_bins, 0, (size_t)kSortBins * sizeof(uint32_t), s));
         const unsigned sb = (unsigned)((n + 255) / 256);
-        sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank);
+        sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank, n_dev);
         scan_block_kernel<<<kSortBins / kScanBlock, kScanBlock, 0, s>>>(w.d_bins, kSortBins, w.d_block_sums, small + 2);
-        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, kSortBins / kScanBlock, small + 2, n, small + 3);
-        sort_scatter_kernel<<<sb, 256, 0, s>>>(n, w.d_bins, w.d_block_sums, w.d_key, w.d_rank, small + 3, w.d_perm);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, kSortBins / kScanBlock, small + 2, n, small + 3, n_dev);
+        sort_scatter_kernel<<<sb, 256, 0, s>>>(n, w.d_bins, w.d_block_sums, w.d_key, w.d_rank, small + 3, w.d_perm,
+                                               n_dev);
         count += 4;
     }
     auto kernel = view_.wide ? trace_kernel<ANY, true> : trace_kernel<ANY, false>;
@@ -951,7 +960,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     if (blocks > needed) blocks = needed;
     kernel<<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
                                                sorting ? small + 3 : nullptr,
-                                               reinterpret_cast<unsigned long long*>(small));
+                                               reinterpret_cast<unsigned long long*>(small), n_dev);
     count += 1;
     RRT_CUDA(cudaGetLastError());
     RRT_CUDA(cudaEventRecord(w.last_use, s));
@@ -962,12 +971,20 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
 
 int DeviceAggregate::closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,
                                  int* launches) const {
-    return trace<false>(n, d_rays, d_hits, nullptr, stream, err, launches);
+    return trace<false>(n, d_rays, d_hits, nullptr, stream, err, launches, nullptr);
+}
+int DeviceAggregate::closest_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays,
+                                          rrt_hit* d_hits, void* stream, std::string* err, int* launches) const {
+    return trace<false>(capacity, d_rays, d_hits, nullptr, stream, err, launches, d_count);
+}
+int DeviceAggregate::any_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays,
+                                      uint8_t* d_occluded, void* stream, std::string* err, int* launches) const {
+    return trace<true>(capacity, d_rays, nullptr, d_occluded, stream, err, launches, d_count);
 }
 
 int DeviceAggregate::any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
                              int* launches) const {
-    return trace<true>(n, d_rays, nullptr, d_occluded, stream, err, launches);
+    return trace<true>(n, d_rays, nullptr, d_occluded, stream, err, launches, nullptr);
 }
 
 }  // namespace rrt

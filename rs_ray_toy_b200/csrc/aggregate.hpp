@@ -48,6 +48,13 @@ class DeviceAggregate {
     int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
                 int* launches = nullptr) const;
 
+    // Wavefront queues: the number of rays is read from device memory (*d_count <= capacity), so a
+    // whole bounce loop can be enqueued without a host round trip.
+    int closest_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, rrt_hit* d_hits,
+                             void* stream, std::string* err, int* launches = nullptr) const;
+    int any_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, uint8_t* d_occluded,
+                         void* stream, std::string* err, int* launches = nullptr) const;
+
     const AggView& view() const { return view_; }
     const AggregateStats& stats() const { return stats_; }
 
@@ -64,7 +71,7 @@ class DeviceAggregate {
     int ensure_workspace(uint64_t n, std::string* err) const;
     template <bool ANY>
     int trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, uint8_t* d_occ, void* stream, std::string* err,
-              int* launches) const;
+              int* launches, const uint32_t* n_dev) const;
     mutable Workspace ws_;
     mutable std::mutex ws_mutex_;
     bool sort_rays_ = true;

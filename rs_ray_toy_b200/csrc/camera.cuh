@@ -1,0 +1,187 @@
+// RealisticCamera (src/camera.rs) and the Film geometry it needs (src/film.rs:188-208), as
+// __host__ __device__ code: the generate kernel traces up to five lens-system rays per camera
+// sample on the device, and the same functions run the camera set-up (thick-lens focus on the
+// host, exit-pupil bounds as a device reduction — 64 x 1,048,576 lens traces, camera.rs:123-133).
+//
+// Kept literally: Q11 (p_lens and time get +0.5 from the sampler), Q18
+// (exit-pupil slab index `(r / (d/2)) as usize * len`, Bounds2::expand shifting both corners,
+// Bounds2f::default() = [(0,0),(0,0)], zero-weight samples still reach the film).
+#pragma once
+#include "halton.cuh"
+
+namespace rrt {
+
+constexpr int kMaxLensElements = 32;
+constexpr int kExitPupilSlabs = 64;
+
+struct LensElement {
+    double curvature_radius, thickness, eta, aperture_radius;
+};
+struct Bounds2 {
+    double x0, y0, x1, y1;
+};
+struct RayD {
+    V3 o, d;
+};
+
+struct CameraData {
+    M34 camera_to_world;
+    LensElement el[kMaxLensElements];
+    Bounds2 exit_pupil[kExitPupilSlabs];
+    Bounds2 physical_extent;  // Film::get_physical_extent (film.rs:200-208)
+    double film_diagonal;     // metres
+    double shutter_open, shutter_close;
+    int64_t xres, yres;
+    int32_t n_elements, simple_weighting;
+};
+
+RRT_HD double lens_rear_z(const CameraData& c) { return c.el[c.n_elements - 1].thickness; }
+RRT_HD double lens_front_z(const CameraData& c) {
+    double z = 0.0;
+    for (int i = 0; i < c.n_elements; ++i) z += c.el[i].thickness;
+    return z;
+}
+// Ray::new_od / Ray::new normalise d (geometry.rs:1841-1858); Transform::scale(1,1,-1).t(ray)
+// maps o and d and normalises d twice (transform.rs:525-537)
+RRT_HD RayD flip_z(RayD r) {
+    RayD o;
+    o.o = v3(r.o.x, r.o.y, -r.o.z);
+    o.d = normalize(normalize(v3(r.d.x, r.d.y, -r.d.z)));
+    return o;
+}
+RRT_HD bool refract(V3 wi, V3 n, double eta, V3* wt) {  // reflection.rs:120-134
+    double cos_i = dot(n, wi);
+    double sin2_i = rmax(0.0, 1.0 - cos_i * cos_i);
+    double sin2_t = eta * eta * sin2_i;
+    if (sin2_t >= 1.0) return false;
+    double cos_t = sqrt(1.0 - sin2_t);
+    *wt = -wi * eta + n * (eta * cos_i - cos_t);
+    return true;
+}
+// camera.rs:221-253
+RRT_HD bool intersect_spherical_element(double radius, double z_center, const RayD& ray, double* t, V3* n) {
+    V3 o = ray.o - v3(0.0, 0.0, z_center);
+    double a = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+    double b = 2.0 * (ray.d.x * o.x + ray.d.y * o.y + ray.d.z * o.z);
+    double c = o.x * o.x + o.y * o.y + o.z * o.z - radius * radius;
+    double t0 = 0.0, t1 = 0.0;
+    if (!quadratic(a, b, c, &t0, &t1)) return false;
+    bool use_closer = (ray.d.z > 0.0) != (radius < 0.0);
+    *t = use_closer ? rmin(t0, t1) : rmax(t0, t1);
+    if (*t < 0.0) return false;
+    *n = o + ray.d * *t;
+    *n = faceforward(normalize_n(*n), -ray.d);
+    return true;
+}
+// camera.rs:156-219
+RRT_HD bool trace_lenses_from_film(const CameraData& c, const RayD& r_camera, RayD* r_out) {
+    double element_z = 0.0;
+    RayD r = flip_z(r_camera);
+    for (int i = c.n_elements - 1; i >= 0; --i) {
+        const LensElement e = c.el[i];
+        element_z -= e.thickness;
+        double t = 0.0;
+        V3 n = v3(0, 0, 0);
+        const bool is_stop = e.curvature_radius == 0.0;
+        if (is_stop) {
+            if (r.d.z >= 0.0) return false;
+            t = (element_z - r.o.z) / r.d.z;
+        } else {
+            if (!intersect_spherical_element(e.curvature_radius, element_z + e.curvature_radius, r, &t, &n)) return false;
+        }
+        V3 p = r.o + r.d * t;
+        double r2 = p.x * p.x + p.y * p.y;
+        if (r2 >= e.aperture_radius * e.aperture_radius) return false;
+        r.o = p;
+        if (!is_stop) {
+            V3 w;
+            double eta_i = e.eta;
+            double eta_t = (i > 0 && c.el[i - 1].eta != 0.0) ? c.el[i - 1].eta : 1.0;
+            if (!refract(normalize(-r.d), n, eta_i / eta_t, &w)) return false;
+            r.d = w;
+        }
+    }
+    *r_out = flip_z(r);
+    return true;
+}
+// camera.rs:254-308
+RRT_HD bool trace_lenses_from_scene(const CameraData& c, const RayD& r_camera, RayD* r_out) {
+    double element_z = -lens_front_z(c);
+    RayD r = flip_z(r_camera);
+    for (int i = 0; i < c.n_elements; ++i) {
+        const LensElement e = c.el[i];
+        double t = 0.0;
+        V3 n = v3(0, 0, 0);
+        const bool is_stop = e.curvature_radius == 0.0;
+        if (is_stop) {
+            t = (element_z - r.o.z) / r.d.z;
+        } else {
+            if (!intersect_spherical_element(e.curvature_radius, element_z + e.curvature_radius, r, &t, &n)) return false;
+        }
+        V3 p = r.o + r.d * t;
+        double r2 = p.x * p.x + p.y * p.y;
+        if (r2 >= e.aperture_radius * e.aperture_radius) return false;
+        r.o = p;
+        if (!is_stop) {
+            V3 wt;
+            double eta_i = (i == 0 || c.el[i - 1].eta == 0.0) ? 1.0 : c.el[i - 1].eta;
+            double eta_t = e.eta != 0.0 ? e.eta : 1.0;
+            if (!refract(-normalize(r.d), n, eta_i / eta_t, &wt)) return false;
+            r.d = wt;
+        }
+        element_z += e.thickness;
+    }
+    *r_out = flip_z(r);
+    return true;
+}
+// camera.rs:492-527
+RRT_HD void sample_exit_pupil(const CameraData& c, double fx, double fy, P2 lens_sample, V3* p_rear, double* area) {
+    double r_film = sqrt(fx * fx + fy * fy);
+    uint64_t r_index = as_u64(r_film / (c.film_diagonal / 2.0)) * (uint64_t)kExitPupilSlabs;  // Q18
+    if (r_index > (uint64_t)kExitPupilSlabs - 1) r_index = kExitPupilSlabs - 1;
+    const Bounds2 pb = c.exit_pupil[r_index];
+    double lx = lerpd(lens_sample.x, pb.x0, pb.x1), ly = lerpd(lens_sample.y, pb.y0, pb.y1);
+    double sin_t = r_film != 0.0 ? fy / r_film : 0.0;
+    double cos_t = r_film != 0.0 ? fx / r_film : 1.0;
+    *p_rear = v3(cos_t * lx - sin_t * ly, sin_t * lx + cos_t * ly, lens_rear_z(c));
+    *area = (pb.x1 - pb.x0) * (pb.y1 - pb.y0);
+}
+// RealisticCamera::generate_ray (camera.rs:534-580): world-space ray + weight
+RRT_HD double generate_ray(const CameraData& c, P2 p_film_raster, P2 p_lens, RayD* ray) {
+    P2 s = {p_film_raster.x / (double)c.xres, p_film_raster.y / (double)c.yres};
+    double px = lerpd(s.x, c.physical_extent.x0, c.physical_extent.x1);
+    double py = lerpd(s.y, c.physical_extent.y0, c.physical_extent.y1);
+    V3 p_film = v3(-px, py, 0.0);
+    V3 p_rear;
+    double area;
+    sample_exit_pupil(c, p_film.x, p_film.y, p_lens, &p_rear, &area);
+    RayD r_film;
+    r_film.o = p_film;
+    r_film.d = normalize(p_rear - p_film);
+    RayD r;
+    if (!trace_lenses_from_film(c, r_film, &r)) return 0.0;
+    // camera_to_world.t(ray) normalises d twice; generate_ray normalises it once more
+    ray->o = xf_point(c.camera_to_world, r.o);
+    ray->d = normalize(normalize(normalize(xf_vector(c.camera_to_world, r.d))));
+    double cos_t = normalize(r_film.d).z;
+    double cos4 = (cos_t * cos_t) * (cos_t * cos_t);
+    if (c.simple_weighting) return cos4 * area / ((c.exit_pupil[0].x1 - c.exit_pupil[0].x0) * (c.exit_pupil[0].y1 - c.exit_pupil[0].y0));
+    return (c.shutter_close - c.shutter_open) * (cos4 * area) / lens_rear_z(c) * lens_rear_z(c);
+}
+// RealisticCamera::generate_ray_differential (camera.rs:582-628).  The differentials themselves
+// feed only texture filtering (out of scope: constant textures); what survives is the weight,
+// which is zero unless one of the +-0.05 px shifted rays in x AND in y also makes it through.
+RRT_HD double generate_ray_weighted(const CameraData& c, P2 p_film, P2 p_lens, RayD* ray) {
+    const double wt = generate_ray(c, p_film, p_lens, ray);
+    if (wt == 0.0) return 0.0;
+    RayD tmp;
+    double wtx = generate_ray(c, P2{p_film.x + 0.05, p_film.y}, p_lens, &tmp);
+    if (wtx == 0.0) wtx = generate_ray(c, P2{p_film.x + -0.05, p_film.y}, p_lens, &tmp);
+    if (wtx == 0.0) return 0.0;
+    double wty = generate_ray(c, P2{p_film.x, p_film.y + 0.05}, p_lens, &tmp);
+    if (wty == 0.0) wty = generate_ray(c, P2{p_film.x, p_film.y + -0.05}, p_lens, &tmp);
+    if (wty == 0.0) return 0.0;
+    return wt;
+}
+
+}  // namespace rrt

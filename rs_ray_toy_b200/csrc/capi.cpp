@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "aggregate.hpp"
+#include "render.hpp"
+#include "scene_json.hpp"
 
 namespace {
 
@@ -73,9 +75,16 @@ struct rrt_ctx {
 struct rrt_scene {
     rrt_ctx* ctx = nullptr;
     rrt::HostScene host;
+    std::vector<rrt_material> materials;
+    std::vector<rrt_light> lights;
     std::unique_ptr<rrt::DeviceAggregate> agg;
     bool committed = false;
     uint32_t build_flags = 0;
+};
+
+struct rrt_render {
+    rrt_scene* scene = nullptr;
+    rrt::Renderer renderer;
 };
 
 namespace {
@@ -345,6 +354,148 @@ int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_
     if (rc != RRT_OK) return fail(rc, err);
     scene->ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
     return RRT_OK;
+}
+
+// ---- the render loop ---------------------------------------------------------------------------
+int rrt_scene_set_materials(rrt_scene* scene, uint32_t n, const rrt_material* materials) {
+    if (!scene || (n && !materials)) return fail(RRT_ERR_INVALID, "rrt_scene_set_materials: null argument");
+    try {
+        scene->materials.assign(materials, materials + n);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights) {
+    if (!scene || (n && !lights)) return fail(RRT_ERR_INVALID, "rrt_scene_set_lights: null argument");
+    try {
+        scene->lights.assign(lights, lights + n);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
+int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out) {
+    if (!scene || !desc || !out) return fail(RRT_ERR_INVALID, "rrt_render_create: null argument");
+    *out = nullptr;
+    if (!scene->committed) return fail(RRT_ERR_INVALID, "rrt_render_create: scene is not committed");
+    try {
+        double wb[6];
+        int rc = rrt_world_bound(scene, wb);
+        if (rc != RRT_OK) return rc;
+        std::unique_ptr<rrt_render> r(new rrt_render());
+        r->scene = scene;
+        std::string err;
+        rc = r->renderer.create(scene->ctx->device, scene->host, scene->agg.get(), scene->materials, scene->lights, wb, *desc,
+                                &err);
+        if (rc != RRT_OK) return fail(rc, err);
+        scene->ctx->launches.fetch_add(r->renderer.stats().launches, std::memory_order_relaxed);
+        *out = r.release();
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+void rrt_render_destroy(rrt_render* render) { delete render; }
+
+int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
+                        rrt_render** render) {
+    if (!ctx || !path || !scene) return fail(RRT_ERR_INVALID, "rrt_scene_load_json: null argument");
+    *scene = nullptr;
+    if (render) *render = nullptr;
+    rrt::LoadedScene loaded;
+    try {
+        rrt::load_scene_json(path, overrides_json ? overrides_json : "", seed, &loaded);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_IO, e.what());
+    }
+    rrt_scene* s = nullptr;
+    int rc = rrt_scene_begin(ctx, &s);
+    if (rc != RRT_OK) return rc;
+    s->host = std::move(loaded.scene);
+    s->materials = loaded.materials;
+    s->lights = loaded.lights;
+    rc = rrt_scene_commit(s, loaded.max_prims_in_node, RRT_BUILD_FAST);
+    if (rc != RRT_OK) {
+        rrt_scene_destroy(s);
+        return rc;
+    }
+    if (render) {
+        loaded.desc.lens_data = loaded.lens_data.data();
+        rc = rrt_render_create(s, &loaded.desc, render);
+        if (rc != RRT_OK) {
+            rrt_scene_destroy(s);
+            return rc;
+        }
+    }
+    *scene = s;
+    return RRT_OK;
+}
+
+int rrt_scene_json_probe(const char* path, const char* overrides_json, uint64_t out8[8], rrt_render_desc* desc) {
+    if (!path || !out8) return fail(RRT_ERR_INVALID, "rrt_scene_json_probe: null argument");
+    try {
+        rrt::LoadedScene l;
+        rrt::load_scene_json(path, overrides_json ? overrides_json : "", 0, &l);
+        out8[0] = l.scene.prims.size();
+        out8[1] = l.scene.meshes.size();
+        out8[2] = l.scene.spheres.size();
+        out8[3] = l.scene.instances.size();
+        out8[4] = l.materials.size();
+        out8[5] = l.lights.size();
+        out8[6] = l.max_prims_in_node;
+        out8[7] = l.lens_data.size();
+        if (desc) {
+            *desc = l.desc;
+            desc->lens_data = nullptr;
+        }
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_IO, e.what());
+    }
+    return RRT_OK;
+}
+
+int rrt_render_run(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop) {
+    if (!render) return fail(RRT_ERR_INVALID, "rrt_render_run: null render");
+    std::string err;
+    const uint64_t before = render->renderer.stats().launches;
+    int rc = render->renderer.run(tile_mod, tile_rank, crop, &err);
+    if (rc != RRT_OK) return fail(rc, err);
+    render->scene->ctx->launches.fetch_add(render->renderer.stats().launches - before, std::memory_order_relaxed);
+    return RRT_OK;
+}
+int rrt_render_clear(rrt_render* render) {
+    if (!render) return fail(RRT_ERR_INVALID, "rrt_render_clear: null render");
+    std::string err;
+    int rc = render->renderer.clear(&err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_render_read_film(rrt_render* render, double* rgb, double* raw) {
+    if (!render) return fail(RRT_ERR_INVALID, "rrt_render_read_film: null render");
+    std::string err;
+    int rc = render->renderer.read_film(rgb, raw, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_doubles) {
+    if (!render || !d_film || !n_doubles) return fail(RRT_ERR_INVALID, "rrt_render_film_device: null argument");
+    *d_film = render->renderer.film_device();
+    *n_doubles = render->renderer.film_doubles();
+    return RRT_OK;
+}
+int rrt_render_stats(const rrt_render* render, uint64_t out16[16]) {
+    if (!render || !out16) return fail(RRT_ERR_INVALID, "rrt_render_stats: null argument");
+    const rrt::RenderStats& s = render->renderer.stats();
+    const uint64_t v[16] = {s.camera_rays, s.extension_rays, s.shadow_rays, s.bounces, s.zero_weight, s.samples,
+                            s.launches, s.render_usec, s.setup_usec, s.chunks, 0, 0, 0, 0, 0, 0};
+    std::memcpy(out16, v, sizeof(v));
+    return RRT_OK;
+}
+int rrt_render_hit_dump(rrt_render* render, int enable, double* out, uint64_t capacity, uint64_t* count) {
+    if (!render) return fail(RRT_ERR_INVALID, "rrt_render_hit_dump: null render");
+    std::string err;
+    int rc = render->renderer.hit_dump(enable, out, capacity, count, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
 }
 
 int rrt_intersect(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, rrt_hit* hits) {

@@ -1,0 +1,1046 @@
+// The wavefront path tracer: SamplerIntegrator::si_render (src/integrator/mod.rs:48-139) with
+// PathIntegrator::li (src/integrator/path.rs:51-226) or DirectLightingIntegrator::li
+// (src/integrator/directlighting.rs:72-132) restructured as a pipeline of kernels over
+// persistent queues in HBM:
+//
+//   generate  : Halton camera sample (halton.cuh) -> lens-system trace (camera.cuh) -> extension ray
+//   extend    : closest hit of every queued ray          (aggregate.cu, device-side ray count)
+//   shade     : hit -> surface frame -> BSDF; one light sample -> shadow ray + its contribution;
+//               BSDF sample -> next extension ray; Russian roulette           (shading.cuh)
+//   shadow    : any hit of every shadow ray               (aggregate.cu)
+//   resolve   : unoccluded contributions are added to their path's radiance
+//   deposit   : FilmTile::add_sample through the filter table, per-pixel f64 atomics
+//
+// A chunk of up to kChunk camera samples runs generate, then max_depth + 1 rounds of
+// extend/shade/shadow/resolve, then deposit; every count lives on the device, so the whole frame
+// is one stream of launches with no host synchronisation until the end.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "camera.cuh"
+#include "render.hpp"
+#include "shading.cuh"
+
+namespace rrt {
+namespace {
+
+constexpr uint32_t kChunk = 1u << 21;  // camera samples in flight
+constexpr int kTile = 16;              // integrator/mod.rs:55
+
+#define RND_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            return RRT_ERR_CUDA;                                                \
+        }                                                                       \
+    } while (0)
+
+struct FilmParams {
+    int64_t xres, yres;
+    int64_t sb[4];   // sample bounds (film.rs:188-199)
+    double rx, ry, inv_rx, inv_ry;
+    double max_sample_luminance;
+    double table[256];  // film.rs:163-174
+};
+
+struct IntegratorParams {
+    uint32_t kind, max_depth;
+    double rr_threshold;
+    uint32_t n_lights, n_samples;  // n_samples = nsamp - 1 rendered samples per pixel (Q10)
+    double light_pdf;              // Distribution1D::discrete_pdf of the uniform distribution
+    double light_cdf[17];          // up to 16 lights (path.rs:47-49, sampling.rs:10-40)
+};
+
+// Per camera sample state (one record per slot of the chunk)
+struct Path {
+    V3 o, d;
+    Rgb beta, L;
+    double eta_scale, pfx, pfy, weight;
+    uint64_t hidx;
+    uint32_t dim, bounces;
+    int32_t px, py;
+    uint32_t sample, state;  // state: 0 = no sample in this slot, 1 = alive, 2 = finished
+    int32_t first_prim;
+    uint32_t pad;
+    double first_t;
+};
+
+struct Queues {
+    rrt_ray* ext_rays[2];
+    uint32_t* ext_path[2];
+    rrt_hit* hits;
+    rrt_ray* sh_rays;
+    uint32_t* sh_path;
+    Rgb* sh_contrib;
+    uint8_t* sh_occluded;
+    uint32_t* counters;  // [0] ext cur, [1] ext next, [2] shadow, [4..] statistics
+};
+
+struct Frame {
+    const uint32_t* tiles;  // tile ids of this rank
+    uint32_t n_tiles, n_tiles_x;
+    int64_t crop[4];
+    uint32_t use_crop, pad;
+};
+
+__device__ __forceinline__ void write_ray(rrt_ray* r, V3 o, V3 d, double t_max) {
+    double2* p = reinterpret_cast<double2*>(r);
+    p[0] = make_double2(o.x, o.y);
+    p[1] = make_double2(o.z, d.x);
+    p[2] = make_double2(d.y, d.z);
+    p[3] = make_double2(t_max, 0.0);
+}
+// warp-aggregated append: one atomic per warp
+__device__ __forceinline__ uint32_t queue_slot(uint32_t* counter, bool want) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0u) return 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- generate ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) generate_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms,
+                                                        FilmParams film, IntegratorParams ip, Frame fr, uint64_t base,
+                                                        uint32_t count, Path* __restrict__ paths, Queues q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool emit = false;
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 0);
+    if (i < count) {
+        const uint64_t s = base + i;
+        const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
+        const uint32_t tslot = (uint32_t)(s / per_tile);
+        const uint32_t within = (uint32_t)(s % per_tile);
+        const uint32_t pix = within / ip.n_samples, sn = within % ip.n_samples + 1u;  // sample numbers 1..nsamp-1 (Q10)
+        const uint32_t tile = fr.tiles[tslot];
+        const int64_t px = film.sb[0] + (int64_t)(tile % fr.n_tiles_x) * kTile + (pix % kTile);
+        const int64_t py = film.sb[1] + (int64_t)(tile / fr.n_tiles_x) * kTile + (pix / kTile);
+        Path p;
+        p.state = 0;
+        bool valid = px < film.sb[2] && py < film.sb[3] && px >= 0 && px < film.xres && py >= 0 && py < film.yres;
+        if (valid && fr.use_crop) valid = px >= fr.crop[0] && px < fr.crop[2] && py >= fr.crop[1] && py < fr.crop[3];
+        if (valid) {
+            const uint64_t hidx = halton_index(ht, px, py, sn);
+            // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
+            const P2 pf = {(double)px + halton_sample(ht, perms, hidx, 0), (double)py + halton_sample(ht, perms, hidx, 1)};
+            const P2 pl = {halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+            RayD ray;
+            ray.o = v3(0, 0, 0);
+            ray.d = v3(0, 0, 0);
+            const double w = generate_ray_weighted(cam, pf, pl, &ray);
+            p.o = ray.o;
+            p.d = ray.d;
+            p.beta = rgb(1.0);
+            p.L = rgb(0.0);
+            p.eta_scale = 1.0;
+            p.pfx = pf.x;
+            p.pfy = pf.y;
+            p.weight = w;
+            p.hidx = hidx;
+            p.dim = 5;
+            p.bounces = 0;
+            p.px = (int32_t)px;
+            p.py = (int32_t)py;
+            p.sample = sn;
+            p.first_prim = w > 0.0 ? -1 : -2;
+            p.first_t = 0.0;
+            p.pad = 0;
+            if (w > 0.0) {
+                p.state = 1;
+                emit = true;
+                ro = ray.o;
+                rd = ray.d;
+                atomicAdd(q.counters + 4, 1u);  // camera rays
+            } else {
+                p.state = 2;
+                atomicAdd(q.counters + 8, 1u);  // zero-weight samples
+            }
+        }
+        paths[i] = p;
+    }
+    const uint32_t slot = queue_slot(q.counters + 0, emit);
+    if (emit) {
+        write_ray(q.ext_rays[0] + slot, ro, rd, kInfD);
+        q.ext_path[0][slot] = i;
+    }
+}
+
+// ---- shade ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double next_1d(const HaltonTables& ht, const uint16_t* perms, Path& p) {
+    return halton_sample(ht, perms, p.hidx, p.dim++);
+}
+__device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* perms, Path& p) {
+    P2 u = {halton_sample(ht, perms, p.hidx, p.dim), halton_sample(ht, perms, p.hidx, p.dim + 1)};
+    p.dim += 2;
+    return u;
+}
+
+__global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
+                                                     IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = q.counters[cur];
+    bool emit_ext = false, emit_sh = false;
+    V3 eo = v3(0, 0, 0), ed = v3(0, 0, 0), so = v3(0, 0, 0), sd = v3(0, 0, 0);
+    Rgb contrib = rgb(0.0);
+    uint32_t pid = 0;
+    if (qi < n) {
+        pid = q.ext_path[cur][qi];
+        Path p = paths[pid];
+        const rrt_hit h = q.hits[qi];
+        const bool found = h.prim_id != RRT_NO_HIT;
+        if (p.bounces == 0) {
+            p.first_prim = found ? (int32_t)h.prim_id : -1;
+            p.first_t = found ? h.t : 0.0;
+        }
+        // path.rs:79-93: no emitted radiance in scope (Q22, no infinite lights); stop on escape / depth
+        bool alive = found && !(ip.kind == RRT_INTEGRATOR_PATH && p.bounces >= ip.max_depth);
+        if (alive) {
+            Surface s;
+            make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
+            Bsdf bsdf;
+            make_bsdf(sc.materials[s.material], s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
+            if (!bsdf.present) {
+                alive = false;  // path.rs:101-106 (usize underflow in the reference, Q21): the path ends here
+            } else {
+                // ---- uniform_sample_one_light (integrator/mod.rs:359-401) ----
+                const bool do_nee = ip.kind == RRT_INTEGRATOR_DIRECT || bsdf_num_components(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0;
+                if (do_nee && ip.n_lights > 0) {
+                    const double ul = next_1d(ht, perms, p);
+                    uint32_t light_num;
+                    if (ip.kind == RRT_INTEGRATOR_PATH) {
+                        // Distribution1D::sample_discrete (sampling.rs:87-122): bisection over the CDF
+                        uint32_t first = 0, len = ip.n_lights + 1;
+                        while (len > 0) {
+                            uint32_t half = len >> 1, middle = first + half;
+                            if (ip.light_cdf[middle] <= ul) {
+                                first = middle + 1;
+                                len -= half + 1;
+                            } else {
+                                len = half;
+                            }
+                        }
+                        light_num = first == 0 ? 0 : first - 1;
+                        if (light_num > ip.n_lights - 1) light_num = ip.n_lights - 1;
+                    } else {
+                        uint64_t k = as_u64(ul * (double)ip.n_lights);
+                        light_num = k > ip.n_lights - 1 ? ip.n_lights - 1 : (uint32_t)k;
+                    }
+                    p.dim += 4;  // u_light, u_scattering: drawn, unused by delta lights
+                    // ---- estimate_direct (integrator/mod.rs:403-481), delta lights only ----
+                    const LightRec lt = sc.lights[light_num];
+                    V3 wi, p1;
+                    Rgb li;
+                    if (lt.kind == RRT_LIGHT_POINT) {  // point.rs:55-77
+                        wi = normalize(lt.p_light - s.p);
+                        p1 = lt.p_light;
+                        li = lt.intensity / length_sq(lt.p_light - s.p);
+                    } else {  // distant.rs:69-93
+                        wi = lt.w_light;
+                        p1 = s.p + lt.w_light * (2.0 * lt.world_radius);
+                        li = lt.intensity;
+                    }
+                    if (!is_black(li)) {
+                        const Rgb f = bsdf_f(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR) * absdot(wi, s.shn);
+                        if (!is_black(f)) {
+                            // ld = f * li / light_pdf(=1), then / the light-choice pdf, then * beta
+                            Rgb ld = (f * li / 1.0) / ip.light_pdf;
+                            contrib = ip.kind == RRT_INTEGRATOR_PATH ? p.beta * ld : ld;
+                            emit_sh = true;
+                            so = s.p;
+                            sd = p1 - s.p;  // Q9 fixed: t runs over the segment, t_max = 1 - eps
+                        }
+                    }
+                }
+                if (ip.kind == RRT_INTEGRATOR_DIRECT) {
+                    alive = false;  // the specular recursion is outside the device scope (checked at create)
+                } else {
+                    // ---- BSDF sampling (path.rs:126-163) ----
+                    const V3 wo = -p.d;
+                    V3 wi = v3(0, 0, 0);
+                    double pdf = 0.0;
+                    uint32_t flags = 0;
+                    const P2 u = next_2d(ht, perms, p);
+                    const Rgb f = bsdf_sample_f(bsdf, wo, &wi, u, &pdf, BXDF_ALL, &flags);
+                    if (is_black(f) || pdf == 0.0) {
+                        alive = false;
+                    } else {
+                        p.beta = p.beta * (f * absdot(wi, s.shn) / pdf);
+                        const double by = lum(p.beta);
+                        if (!(by > 0.0) || isinf(by) || by != by) {
+                            alive = false;  // path.rs:146-147: the reference asserts (would panic)
+                        } else {
+                            if ((flags & BXDF_SPECULAR) && (flags & BXDF_TRANSMISSION)) {
+                                const double eta = bsdf.eta;
+                                p.eta_scale *= dot(wo, s.n) > 0.0 ? (eta * eta) : 1.0 / (eta * eta);
+                            }
+                            p.o = s.p;           // spawn_ray: origin on the surface, no offset (Q8)
+                            p.d = normalize(wi);  // Ray::new_od normalises
+                            const Rgb rr_beta = p.beta * p.eta_scale;
+                            if (max_component(rr_beta) < ip.rr_threshold && p.bounces > 3) {
+                                const double qq = rmax(1.0 - max_component(rr_beta), 0.05);
+                                if (next_1d(ht, perms, p) < qq)
+                                    alive = false;
+                                else
+                                    p.beta = p.beta / (1.0 - qq);
+                            }
+                            if (alive) {
+                                p.bounces += 1;
+                                emit_ext = true;
+                                eo = p.o;
+                                ed = p.d;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!alive) p.state = 2;
+        paths[pid] = p;
+    }
+    const uint32_t es = queue_slot(q.counters + (cur ^ 1), emit_ext);
+    if (emit_ext) {
+        write_ray(q.ext_rays[cur ^ 1] + es, eo, ed, kInfD);
+        q.ext_path[cur ^ 1][es] = pid;
+    }
+    const uint32_t ss = queue_slot(q.counters + 2, emit_sh);
+    if (emit_sh) {
+        write_ray(q.sh_rays + ss, so, sd, 1.0 - kShadowEps);
+        q.sh_path[ss] = pid;
+        q.sh_contrib[ss] = contrib;
+    }
+}
+
+// Unoccluded light samples join their path's radiance (`l += ld`, path.rs:121 / directlighting.rs:113)
+__global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, Queues q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.counters[2]) return;
+    if (q.sh_occluded[i]) return;
+    Path& p = paths[q.sh_path[i]];
+    p.L = p.L + q.sh_contrib[i];
+}
+
+// Between rounds: statistics, then the next round's queue becomes current and the others empty.
+__global__ void advance_kernel(Queues q, int cur) {
+    q.counters[5] += q.counters[cur];  // extension rays traced
+    q.counters[6] += q.counters[2];    // shadow rays traced
+    q.counters[7] += q.counters[cur ^ 1];  // bounces
+    q.counters[cur] = 0;
+    q.counters[2] = 0;
+}
+
+// FilmTile::add_sample (film.rs:77-130) straight into the frame's film: radiance guards of
+// integrator/mod.rs:105-122, luminance clamp, filter-table splat.  4 doubles per pixel:
+// sum of L * weight * filter (RGB) and sum of filter weights.
+__global__ void __launch_bounds__(256) deposit_kernel(FilmParams film, const Path* __restrict__ paths, uint32_t count,
+                                                       double* __restrict__ pixels, double* __restrict__ dump, uint64_t dump_base) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Path p = paths[i];
+    if (p.state == 0) return;
+    Rgb l = p.L;
+    if (has_nan(l) || lum(l) < -1e-5 || isinf(lum(l))) l = rgb(0.0);
+    if (lum(l) > film.max_sample_luminance) l = l * (film.max_sample_luminance / lum(l));
+    const double dx = p.pfx - 0.5, dy = p.pfy - 0.5;
+    int64_t p0x = as_i64(ceil(dx - film.rx)), p0y = as_i64(ceil(dy - film.ry));
+    int64_t p1x = as_i64(dx + film.rx) + 1, p1y = as_i64(dy + film.ry) + 1;  // Q14: truncation toward zero
+    p0x = p0x > 0 ? p0x : 0;
+    p0y = p0y > 0 ? p0y : 0;
+    p1x = p1x < film.xres ? p1x : film.xres;
+    p1y = p1y < film.yres ? p1y : film.yres;
+    const Rgb lw = l * p.weight;
+    for (int64_t y = p0y; y < p1y; ++y) {
+        const double fy = fabs(((double)y - dy) * film.inv_ry * 16.0);
+        int64_t iy = as_i64(floor(fy));
+        iy = iy < 15 ? iy : 15;
+        for (int64_t x = p0x; x < p1x; ++x) {
+            const double fx = fabs(((double)x - dx) * film.inv_rx * 16.0);
+            int64_t ix = as_i64(floor(fx));
+            ix = ix < 15 ? ix : 15;
+            const double w = film.table[iy * 16 + ix];
+            double* px = pixels + 4 * (size_t)(y * film.xres + x);
+            const Rgb c = lw * w;
+            atomicAdd(px + 0, c.r);
+            atomicAdd(px + 1, c.g);
+            atomicAdd(px + 2, c.b);
+            atomicAdd(px + 3, w);
+        }
+    }
+    if (dump) {
+        double* o = dump + 6 * (dump_base + i);
+        o[0] = p.px;
+        o[1] = p.py;
+        o[2] = p.sample;
+        o[3] = p.first_prim;
+        o[4] = p.first_t;
+        o[5] = p.weight;
+    }
+}
+
+// RealisticCamera::bound_exit_pupil (camera.rs:442-488) for all 64 film slabs at once: every
+// (slab, sample) pair is one lens trace; successful rear-element points are min/max-reduced.
+// The reference's running `inside(pupil_bounds)` shortcut cannot change the box (a point inside
+// it does not grow it), so the result is the box of {(0,0)} and the successful points.
+__device__ __forceinline__ void atomic_min_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) > v) {
+        unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void atomic_max_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) < v) {
+        unsigned long long prev = atomicCAS(p, old, (unsigned long long)__double_as_longlong(v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+__global__ void __launch_bounds__(256) exit_pupil_kernel(CameraData cam, HaltonTables ht, double* __restrict__ bounds4,
+                                                          unsigned long long* __restrict__ n_exiting) {
+    const int slab = blockIdx.y;
+    const uint64_t n_samples = 1024ull * 1024ull;
+    const double x0 = (double)slab / (double)kExitPupilSlabs * cam.film_diagonal / 2.0;
+    const double x1 = (double)(slab + 1) / (double)kExitPupilSlabs * cam.film_diagonal / 2.0;
+    const double rear_radius = cam.el[cam.n_elements - 1].aperture_radius;
+    const double lo = -1.5 * rear_radius, hi = 1.5 * rear_radius;
+    double bx0 = 0.0, by0 = 0.0, bx1 = 0.0, by1 = 0.0;
+    unsigned long long cnt = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+        const V3 p_film = v3(lerpd(((double)i + 0.5) / (double)n_samples, x0, x1), 0.0, 0.0);
+        const double u0 = radical_inverse(ht, 0, i), u1 = radical_inverse(ht, 1, i);
+        const V3 p_rear = v3(lerpd(u0, lo, hi), lerpd(u1, lo, hi), lens_rear_z(cam));
+        RayD r, out;
+        r.o = p_film;
+        r.d = normalize(p_rear - p_film);
+        if (trace_lenses_from_film(cam, r, &out)) {
+            bx0 = fmin(bx0, p_rear.x);
+            by0 = fmin(by0, p_rear.y);
+            bx1 = fmax(bx1, p_rear.x);
+            by1 = fmax(by1, p_rear.y);
+            cnt += 1;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, off));
+        by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, off));
+        bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, off));
+        by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, off));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_min_double(bounds4 + 4 * slab + 0, bx0);
+        atomic_min_double(bounds4 + 4 * slab + 1, by0);
+        atomic_max_double(bounds4 + 4 * slab + 2, bx1);
+        atomic_max_double(bounds4 + 4 * slab + 3, by1);
+        atomicAdd(n_exiting + slab, cnt);
+    }
+}
+
+template <class T>
+int upload(const std::vector<T>& v, void** d, std::string* err) {
+    *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    RND_CUDA(cudaMalloc(d, bytes));
+    if (!v.empty()) RND_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return RRT_OK;
+}
+
+M34 m34_of(const Mat4& m) {
+    M34 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) r.m[4 * i + j] = m.m[i][j];
+    return r;
+}
+Rgb rgb_of(const double* c) { return Rgb{c[0], c[1], c[2]}; }
+
+// camera_to_world of Transform::inverse(Transform::look_at(..)) (transform.rs:352-390)
+bool look_at_inverse(const double pos[3], const double look[3], const double up[3], Mat4* camera_to_world, std::string* err);
+
+}  // namespace
+
+struct Renderer::Impl {
+    const DeviceAggregate* agg = nullptr;
+    int device = 0;
+    CameraData cam{};
+    HaltonTables ht{};
+    FilmParams film{};
+    IntegratorParams ip{};
+    ShadeScene sc{};
+    double film_scale = 1.0;
+    std::vector<void*> allocations;
+    uint16_t* d_perms = nullptr;
+    Path* d_paths = nullptr;
+    Queues q{};
+    uint32_t* d_tiles = nullptr;
+    uint32_t tiles_capacity = 0;
+    double* d_dump = nullptr;
+    uint64_t dump_capacity = 0, dump_count = 0;
+    bool dump_enabled = false;
+    cudaStream_t stream = nullptr;
+
+    template <class T>
+    int up(const std::vector<T>& v, const T** out, std::string* err) {
+        void* d = nullptr;
+        int rc = upload(v, &d, err);
+        if (rc != RRT_OK) return rc;
+        allocations.push_back(d);
+        *out = static_cast<const T*>(d);
+        return RRT_OK;
+    }
+};
+
+Renderer::~Renderer() {
+    if (!impl_) return;
+    cudaSetDevice(impl_->device);
+    for (void* p : impl_->allocations) cudaFree(p);
+    if (impl_->d_tiles) cudaFree(impl_->d_tiles);
+    if (impl_->d_dump) cudaFree(impl_->d_dump);
+    if (d_film_) cudaFree(d_film_);
+    if (impl_->stream) cudaStreamDestroy(impl_->stream);
+    delete impl_;
+}
+
+namespace {
+bool look_at_inverse(const double pos[3], const double look[3], const double up[3], Mat4* c2w, std::string* err) {
+    // Transform::look_at builds camera_to_world column by column, then stores
+    // Transform{m: inverse(camera_to_world), m_inv: camera_to_world}; make_camera passes
+    // Transform::inverse(&to_camera), i.e. m = camera_to_world (renderprocess.rs:1372,1387).
+    V3 dir = normalize(v3(look[0] - pos[0], look[1] - pos[1], look[2] - pos[2]));
+    V3 upn = normalize(v3(up[0], up[1], up[2]));
+    V3 c = cross(upn, dir);
+    if (length(c) == 0.0) {
+        // transform.rs:362-370: the reference logs and falls back to the identity transform
+        double id[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+        std::memcpy(c2w->m, id, sizeof(id));
+        (void)err;
+        return true;
+    }
+    V3 right = normalize(c);
+    V3 new_up = cross(dir, right);
+    double m[4][4] = {{right.x, new_up.x, dir.x, pos[0]}, {right.y, new_up.y, dir.y, pos[1]},
+                      {right.z, new_up.z, dir.z, pos[2]}, {0.0, 0.0, 0.0, 1.0}};
+    std::memcpy(c2w->m, m, sizeof(m));
+    return true;
+}
+}  // namespace
+
+int Renderer::create(int device, const HostScene& scene, const DeviceAggregate* agg, const std::vector<rrt_material>& materials,
+                     const std::vector<rrt_light>& lights, const double wb[6], const rrt_render_desc& d, std::string* err) {
+    auto t_start = std::chrono::steady_clock::now();
+    if (d.xres <= 0 || d.yres <= 0 || d.xres > 32768 || d.yres > 32768) {
+        if (err) *err = "Film resolution out of range";
+        return RRT_ERR_INVALID;
+    }
+    if (!d.lens_data || d.n_lens_values < 4 || d.n_lens_values % 4 != 0 || d.n_lens_values / 4 > (uint32_t)kMaxLensElements) {
+        if (err) *err = "Camera lens_data must hold 4 values per element (camera.rs:77), at most 32 elements";
+        return RRT_ERR_INVALID;
+    }
+    if (d.nsamp < 1) {
+        if (err) *err = "HaltonSampler nsamp must be >= 1";
+        return RRT_ERR_INVALID;
+    }
+    if (lights.size() > 16) {
+        if (err) *err = "more than 16 lights";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    if (materials.empty()) {
+        if (err) *err = "no materials set (rrt_scene_set_materials)";
+        return RRT_ERR_INVALID;
+    }
+    for (const Primitive& p : scene.prims)
+        if (p.material >= materials.size()) {
+            if (err) *err = "primitive refers to a material that was not set";
+            return RRT_ERR_INVALID;
+        }
+    bool specular_material = false;
+    for (const rrt_material& m : materials) {
+        if (m.kind > RRT_MAT_GLASS) {
+            if (err) *err = "material kind outside the hot-path scope";
+            return RRT_ERR_UNSUPPORTED;
+        }
+        if (m.kind == RRT_MAT_GLASS && (m.u_roughness > 0.0 || m.v_roughness > 0.0)) {
+            if (err) *err = "rough glass (MicrofacetTransmission) is outside the hot-path scope";
+            return RRT_ERR_UNSUPPORTED;
+        }
+        specular_material |= m.kind == RRT_MAT_MIRROR || m.kind == RRT_MAT_GLASS;
+    }
+    if (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.max_depth > 1 && specular_material) {
+        if (err) *err = "DirectLighting's specular recursion (integrator/mod.rs:150-301) is outside the hot-path scope";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    if (d.integrator_kind > RRT_INTEGRATOR_DIRECT) {
+        if (err) *err = "integrator kind outside the hot-path scope";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    RND_CUDA(cudaSetDevice(device));
+    impl_ = new Impl();
+    Impl& I = *impl_;
+    I.agg = agg;
+    I.device = device;
+    xres_ = d.xres;
+    yres_ = d.yres;
+    RND_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
+
+    // ---- Film (film.rs:143-208) ----
+    FilmParams& F = I.film;
+    F.xres = d.xres;
+    F.yres = d.yres;
+    F.rx = d.filter_radius[0];
+    F.ry = d.filter_radius[1];
+    F.inv_rx = 1.0 / F.rx;
+    F.inv_ry = 1.0 / F.ry;
+    F.max_sample_luminance = d.max_sample_luminance;
+    I.film_scale = d.scale;
+    {
+        const double ex = std::exp(-d.filter_alpha * F.rx * F.rx), ey = std::exp(-d.filter_alpha * F.ry * F.ry);
+        int off = 0;
+        for (int y = 0; y < 16; ++y)
+            for (int x = 0; x < 16; ++x) {
+                // Q14: p.x is assigned twice, p.y stays 0 (film.rs:169-170)
+                double px = ((double)y + 0.5) * F.ry / 16.0, py = 0.0;
+                double v = 1.0;
+                if (d.filter_kind == RRT_FILTER_TRIANGLE)
+                    v = std::fmax(0.0, F.rx - std::fabs(px)) * std::fmax(0.0, F.ry - std::fabs(py));
+                else if (d.filter_kind == RRT_FILTER_GAUSSIAN)
+                    v = std::fmax(0.0, std::exp(-d.filter_alpha * px * px) - ex) * std::fmax(0.0, std::exp(-d.filter_alpha * py * py) - ey);
+                F.table[off++] = v;
+            }
+        double p1x = std::floor(0.0 + 0.5 - F.rx), p1y = std::floor(0.0 + 0.5 - F.ry);
+        double p2x = std::ceil((double)d.xres - 0.5 + F.rx), p2y = std::ceil((double)d.yres - 0.5 + F.ry);
+        F.sb[0] = std::min(as_i64(p1x), as_i64(p2x));
+        F.sb[1] = std::min(as_i64(p1y), as_i64(p2y));
+        F.sb[2] = std::max(as_i64(p1x), as_i64(p2x));
+        F.sb[3] = std::max(as_i64(p1y), as_i64(p2y));
+    }
+    RND_CUDA(cudaMalloc(&d_film_, film_doubles() * sizeof(double)));
+    RND_CUDA(cudaMemset(d_film_, 0, film_doubles() * sizeof(double)));
+
+    // ---- Sampler (halton.rs:23-59) ----
+    I.ht = make_halton_tables(d.xres, d.yres, d.sample_at_center != 0);
+    {
+        std::vector<uint16_t> perms = make_halton_permutations(I.ht, d.seed);
+        const uint16_t* dp = nullptr;
+        int rc = I.up(perms, &dp, err);
+        if (rc != RRT_OK) return rc;
+        I.d_perms = const_cast<uint16_t*>(dp);
+    }
+
+    // ---- Camera (camera.rs:66-135) ----
+    CameraData& C = I.cam;
+    {
+        Mat4 c2w;
+        if (!look_at_inverse(d.cam_pos, d.cam_look, d.cam_up, &c2w, err)) return RRT_ERR_INVALID;
+        C.camera_to_world = m34_of(c2w);
+        C.n_elements = (int32_t)(d.n_lens_values / 4);
+        for (int i = 0; i < C.n_elements; ++i) {
+            const double* l = d.lens_data + 4 * i;
+            double ar = l[3];
+            if (l[0] == 0.0 && !(d.aperture_diameter > l[3])) ar = d.aperture_diameter;
+            C.el[i] = LensElement{l[0] * 0.001, l[1] * 0.001, l[2], ar * 0.001 / 2.0};
+        }
+        C.film_diagonal = d.diagonal_mm * 0.001;
+        C.shutter_open = d.shutter_open;
+        C.shutter_close = d.shutter_close;
+        C.xres = d.xres;
+        C.yres = d.yres;
+        C.simple_weighting = d.simple_weighting ? 1 : 0;
+        const double aspect = (double)d.yres / (double)d.xres;
+        const double x = std::sqrt(C.film_diagonal * C.film_diagonal / (1.0 + aspect * aspect));
+        const double y = aspect * x;
+        C.physical_extent = Bounds2{-x / 2.0, -y / 2.0, x / 2.0, y / 2.0};
+        // focus_thick_lens (camera.rs:327-378); focus_binary_search only feeds a log line
+        {
+            const double xx = 0.001 * C.film_diagonal;
+            RayD r_scene{v3(xx, 0.0, lens_front_z(C) + 1.0), v3(0.0, 0.0, -1.0)}, r_film;
+            if (!trace_lenses_from_scene(C, r_scene, &r_film)) {
+                if (err) *err = "Unable to trace ray from scene to film for thick lens approximation (camera.rs:337)";
+                return RRT_ERR_INVALID;
+            }
+            auto cardinal = [](const RayD& rin, const RayD& rout, double* pz, double* fz) {
+                double tf = -rout.o.x / rout.d.x;
+                *fz = -(rout.o.z + rout.d.z * tf);
+                double tp = (rin.o.x - rout.o.x) / rout.d.x;
+                *pz = -(rout.o.z + rout.d.z * tp);
+            };
+            double pz[2], fz[2];
+            cardinal(r_scene, r_film, &pz[0], &fz[0]);
+            RayD r_film2{v3(xx, 0.0, lens_rear_z(C) - 1.0), v3(0.0, 0.0, 1.0)}, r_scene2;
+            if (!trace_lenses_from_film(C, r_film2, &r_scene2)) {
+                if (err) *err = "Unable to trace ray from film to scene for thick lens approximation (camera.rs:345)";
+                return RRT_ERR_INVALID;
+            }
+            cardinal(r_film2, r_scene2, &pz[1], &fz[1]);
+            const double f = fz[0] - pz[0], z = -d.focus_distance;
+            const double c = (pz[1] - z - pz[0]) * (pz[1] - z - 4.0 * f - pz[0]);
+            if (!(c > 0.0)) {
+                if (err) *err = "focus_distance is too short for the lens configuration (camera.rs:370 asserts)";
+                return RRT_ERR_INVALID;
+            }
+            const double delta = 0.5 * (pz[1] - z + pz[0] - std::sqrt(c));
+            C.el[C.n_elements - 1].thickness = C.el[C.n_elements - 1].thickness + delta;
+        }
+        // exit-pupil bounds: 64 slabs x 1,048,576 lens traces on the device
+        double* d_bounds = nullptr;
+        unsigned long long* d_cnt = nullptr;
+        RND_CUDA(cudaMalloc(&d_bounds, 4 * kExitPupilSlabs * sizeof(double)));
+        RND_CUDA(cudaMalloc(&d_cnt, kExitPupilSlabs * sizeof(unsigned long long)));
+        RND_CUDA(cudaMemsetAsync(d_bounds, 0, 4 * kExitPupilSlabs * sizeof(double), I.stream));
+        RND_CUDA(cudaMemsetAsync(d_cnt, 0, kExitPupilSlabs * sizeof(unsigned long long), I.stream));
+        exit_pupil_kernel<<<dim3(128, kExitPupilSlabs), 256, 0, I.stream>>>(C, I.ht, d_bounds, d_cnt);
+        stats_.launches += 1;
+        double hb[4 * kExitPupilSlabs];
+        unsigned long long hc[kExitPupilSlabs];
+        RND_CUDA(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, I.stream));
+        RND_CUDA(cudaMemcpyAsync(hc, d_cnt, sizeof(hc), cudaMemcpyDeviceToHost, I.stream));
+        RND_CUDA(cudaStreamSynchronize(I.stream));
+        cudaFree(d_bounds);
+        cudaFree(d_cnt);
+        const double rear = C.el[C.n_elements - 1].aperture_radius;
+        const double lo = -1.5 * rear, hi = 1.5 * rear;
+        const double ddx = hi - lo, ddy = hi - lo;
+        const double delta = 2.0 * std::sqrt(ddx * ddx + ddy * ddy) / std::sqrt((double)(1024 * 1024));
+        for (int s = 0; s < kExitPupilSlabs; ++s) {
+            if (hc[s] == 0) {
+                C.exit_pupil[s] = Bounds2{lo, lo, hi, hi};
+            } else {
+                // Q18: Bounds2::expand subtracts delta from both corners (geometry.rs:1448-1454)
+                double ax = hb[4 * s] - delta, ay = hb[4 * s + 1] - delta, bx = hb[4 * s + 2] - delta, by = hb[4 * s + 3] - delta;
+                C.exit_pupil[s] = Bounds2{std::min(ax, bx), std::min(ay, by), std::max(ax, bx), std::max(ay, by)};
+            }
+        }
+    }
+
+    // ---- Integrator ----
+    IntegratorParams& P = I.ip;
+    P.kind = d.integrator_kind;
+    P.max_depth = d.max_depth;
+    P.rr_threshold = d.rr_threshold;
+    P.n_lights = (uint32_t)lights.size();
+    P.n_samples = (uint32_t)(d.nsamp - 1);
+    {
+        const size_t n = lights.size();
+        for (double& c : P.light_cdf) c = 0.0;
+        P.light_pdf = n ? 1.0 / (double)n : 0.0;
+        if (n && d.integrator_kind == RRT_INTEGRATOR_PATH) {
+            // Distribution1D::new(vec![1.0; n]) (sampling.rs:17-40)
+            std::vector<double> cdf(n + 1, 0.0);
+            for (size_t i = 1; i <= n; ++i) cdf[i] = cdf[i - 1] + 1.0 / (double)n;
+            const double func_int = cdf[n];
+            for (size_t i = 1; i <= n; ++i) cdf[i] /= func_int;
+            for (size_t i = 0; i <= n; ++i) P.light_cdf[i] = cdf[i];
+            P.light_pdf = 1.0 / (func_int * (double)n);  // sampling.rs:113-116
+        }
+    }
+
+    // ---- shading tables ----
+    {
+        std::vector<PrimInfo> prims(scene.prims.size());
+        for (size_t i = 0; i < scene.prims.size(); ++i) {
+            const Primitive& p = scene.prims[i];
+            PrimInfo pi{};
+            pi.kind = p.kind == SHAPE_TRIANGLE ? 0u : 1u;
+            pi.material = p.material;
+            pi.instance = p.instance;
+            pi.shape = p.shape;
+            pi.tri = p.tri;
+            prims[i] = pi;
+        }
+        std::vector<MeshInfo> meshes(scene.meshes.size());
+        std::vector<double> mp, mn, muv;
+        std::vector<uint32_t> mvi, mni, muvi;
+        for (size_t i = 0; i < scene.meshes.size(); ++i) {
+            const TriangleMesh& m = scene.meshes[i];
+            MeshInfo mi{};
+            mi.p_off = mp.size() / 3;
+            mi.vi_off = mvi.size();
+            mi.n_off = mn.size() / 3;
+            mi.ni_off = mni.size();
+            mi.uv_off = muv.size() / 2;
+            mi.uvi_off = muvi.size();
+            mi.has_n = m.n.empty() ? 0 : 1;
+            mi.has_ni = m.ni.empty() ? 0 : 1;
+            mi.has_uv = m.uv.empty() ? 0 : 1;
+            mi.has_uvi = m.uvi.empty() ? 0 : 1;
+            mp.insert(mp.end(), m.p.begin(), m.p.end());
+            mvi.insert(mvi.end(), m.vi.begin(), m.vi.end());
+            mn.insert(mn.end(), m.n.begin(), m.n.end());
+            mni.insert(mni.end(), m.ni.begin(), m.ni.end());
+            muv.insert(muv.end(), m.uv.begin(), m.uv.end());
+            muvi.insert(muvi.end(), m.uvi.begin(), m.uvi.end());
+            meshes[i] = mi;
+        }
+        std::vector<SphereInfo> spheres(scene.spheres.size());
+        for (size_t i = 0; i < scene.spheres.size(); ++i) {
+            const Sphere& s = scene.spheres[i];
+            SphereInfo si{};
+            si.o2w = m34_of(s.obj_to_world.m);
+            si.w2o = m34_of(s.obj_to_world.inv);
+            si.radius = s.radius;
+            // Sphere::new (sphere.rs:28-47)
+            si.theta_min = std::acos(clampd(std::fmin(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
+            si.theta_max = std::acos(clampd(std::fmax(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
+            si.phi_max = clampd(s.phi_max_deg, 0.0, 360.0) * (kPi / 180.0);
+            spheres[i] = si;
+        }
+        std::vector<InstanceXf> inst(scene.instances.size());
+        for (size_t i = 0; i < scene.instances.size(); ++i) {
+            inst[i].m = m34_of(scene.instances[i].m);
+            inst[i].inv = m34_of(scene.instances[i].inv);
+            inst[i].is_identity = scene.instances[i].is_identity() ? 1 : 0;
+        }
+        std::vector<MaterialRec> mats(materials.size());
+        for (size_t i = 0; i < materials.size(); ++i) {
+            const rrt_material& m = materials[i];
+            MaterialRec r{};
+            r.kind = m.kind;
+            r.remap_roughness = m.remap_roughness;
+            r.kd = rgb_of(m.kd);
+            r.ks = rgb_of(m.ks);
+            r.kr = rgb_of(m.kr);
+            r.kt = rgb_of(m.kt);
+            r.metal_eta = rgb_of(m.metal_eta);
+            r.metal_k = rgb_of(m.metal_k);
+            r.sigma = m.sigma;
+            r.roughness = m.roughness;
+            r.u_roughness = m.u_roughness;
+            r.v_roughness = m.v_roughness;
+            r.eta = m.eta;
+            mats[i] = r;
+        }
+        std::vector<LightRec> lts(lights.size());
+        // Bounds3f::bounding_sphere of the scene bound (geometry.rs:1656-1668)
+        const V3 lo = v3(wb[0], wb[1], wb[2]), hi = v3(wb[3], wb[4], wb[5]);
+        const V3 center = (lo + hi) / 2.0;
+        const bool inside = center.x >= lo.x && center.x <= hi.x && center.y >= lo.y && center.y <= hi.y && center.z >= lo.z && center.z <= hi.z;
+        const double radius = inside ? length(center - hi) : 0.0;
+        for (size_t i = 0; i < lights.size(); ++i) {
+            const rrt_light& l = lights[i];
+            LightRec r{};
+            r.kind = l.kind;
+            r.intensity = rgb_of(l.intensity);
+            r.p_light = v3(0.0, 0.0, 0.0);  // Q17: PointLight::new(.., Point3f::default(), ..) (renderprocess.rs:996)
+            if (l.kind == RRT_LIGHT_DISTANT) {
+                Mat4 m;
+                std::memcpy(m.m, l.to_world, sizeof(m.m));
+                r.w_light = normalize(xf_vector(m34_of(m), v3(l.dir[0], l.dir[1], l.dir[2])));  // distant.rs:30
+                r.world_radius = radius;
+            } else if (l.kind != RRT_LIGHT_POINT) {
+                if (err) *err = "light kind outside the hot-path scope";
+                return RRT_ERR_UNSUPPORTED;
+            }
+            lts[i] = r;
+        }
+        ShadeScene& S = I.sc;
+        int rc;
+        if ((rc = I.up(prims, &S.prims, err)) != RRT_OK) return rc;
+        if ((rc = I.up(meshes, &S.meshes, err)) != RRT_OK) return rc;
+        if ((rc = I.up(mp, &S.mesh_p, err)) != RRT_OK) return rc;
+        if ((rc = I.up(mvi, &S.mesh_vi, err)) != RRT_OK) return rc;
+        if ((rc = I.up(mn, &S.mesh_n, err)) != RRT_OK) return rc;
+        if ((rc = I.up(mni, &S.mesh_ni, err)) != RRT_OK) return rc;
+        if ((rc = I.up(muv, &S.mesh_uv, err)) != RRT_OK) return rc;
+        if ((rc = I.up(muvi, &S.mesh_uvi, err)) != RRT_OK) return rc;
+        if ((rc = I.up(spheres, &S.spheres, err)) != RRT_OK) return rc;
+        if ((rc = I.up(inst, &S.instances, err)) != RRT_OK) return rc;
+        if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
+        if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
+        S.n_lights = (uint32_t)lts.size();
+    }
+
+    // ---- path state + queues ----
+    auto dev_alloc = [&](void** p, size_t bytes) -> int {
+        RND_CUDA(cudaMalloc(p, bytes));
+        I.allocations.push_back(*p);
+        return RRT_OK;
+    };
+    int rc;
+    if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kChunk * sizeof(Path))) != RRT_OK) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc((void**)&I.q.ext_rays[k], (size_t)kChunk * sizeof(rrt_ray))) != RRT_OK) return rc;
+        if ((rc = dev_alloc((void**)&I.q.ext_path[k], (size_t)kChunk * sizeof(uint32_t))) != RRT_OK) return rc;
+    }
+    if ((rc = dev_alloc((void**)&I.q.hits, (size_t)kChunk * sizeof(rrt_hit))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_rays, (size_t)kChunk * sizeof(rrt_ray))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_path, (size_t)kChunk * sizeof(uint32_t))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_contrib, (size_t)kChunk * sizeof(Rgb))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_occluded, (size_t)kChunk)) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.counters, 64 * sizeof(uint32_t))) != RRT_OK) return rc;
+    RND_CUDA(cudaMemset(I.q.counters, 0, 64 * sizeof(uint32_t)));
+    stats_.setup_usec =
+        (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
+    return RRT_OK;
+}
+
+int Renderer::clear(std::string* err) {
+    if (!impl_) return RRT_ERR_INVALID;
+    RND_CUDA(cudaSetDevice(impl_->device));
+    RND_CUDA(cudaMemset(d_film_, 0, film_doubles() * sizeof(double)));
+    stats_ = RenderStats{};
+    impl_->dump_count = 0;
+    return RRT_OK;
+}
+
+int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, std::string* err) {
+    if (!impl_) return RRT_ERR_INVALID;
+    Impl& I = *impl_;
+    if (tile_mod == 0 || tile_rank >= tile_mod) {
+        if (err) *err = "tile_rank must be < tile_mod";
+        return RRT_ERR_INVALID;
+    }
+    RND_CUDA(cudaSetDevice(I.device));
+    auto t_start = std::chrono::steady_clock::now();
+    const FilmParams& F = I.film;
+    const int64_t ntx = (F.sb[2] - F.sb[0] + kTile - 1) / kTile, nty = (F.sb[3] - F.sb[1] + kTile - 1) / kTile;
+    std::vector<uint32_t> tiles;
+    for (int64_t t = 0; t < ntx * nty; ++t) {
+        if ((uint64_t)t % tile_mod != tile_rank) continue;
+        if (crop) {
+            const int64_t x0 = F.sb[0] + (t % ntx) * kTile, y0 = F.sb[1] + (t / ntx) * kTile;
+            if (x0 + kTile <= crop[0] || x0 >= crop[2] || y0 + kTile <= crop[1] || y0 >= crop[3]) continue;
+        }
+        tiles.push_back((uint32_t)t);
+    }
+    if (tiles.empty() || I.ip.n_samples == 0) return RRT_OK;  // nsamp = 1 renders nothing (Q10)
+    if (tiles.size() > I.tiles_capacity) {
+        if (I.d_tiles) cudaFree(I.d_tiles);
+        I.d_tiles = nullptr;
+        RND_CUDA(cudaMalloc(&I.d_tiles, tiles.size() * sizeof(uint32_t)));
+        I.tiles_capacity = (uint32_t)tiles.size();
+    }
+    RND_CUDA(cudaMemcpyAsync(I.d_tiles, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, I.stream));
+    Frame fr{};
+    fr.tiles = I.d_tiles;
+    fr.n_tiles = (uint32_t)tiles.size();
+    fr.n_tiles_x = (uint32_t)ntx;
+    fr.use_crop = crop ? 1 : 0;
+    if (crop)
+        for (int k = 0; k < 4; ++k) fr.crop[k] = crop[k];
+    const uint64_t total = (uint64_t)tiles.size() * kTile * kTile * I.ip.n_samples;
+    if (I.dump_enabled) {
+        const uint64_t need = I.dump_count + total;
+        if (need > I.dump_capacity) {
+            double* nd = nullptr;
+            RND_CUDA(cudaMalloc(&nd, need * 6 * sizeof(double)));
+            if (I.d_dump) {
+                RND_CUDA(cudaMemcpy(nd, I.d_dump, I.dump_count * 6 * sizeof(double), cudaMemcpyDeviceToDevice));
+                cudaFree(I.d_dump);
+            }
+            I.d_dump = nd;
+            I.dump_capacity = need;
+        }
+        RND_CUDA(cudaMemsetAsync(I.d_dump + 6 * I.dump_count, 0xFF, total * 6 * sizeof(double), I.stream));  // NaN = empty slot
+    }
+    const uint32_t rounds = I.ip.kind == RRT_INTEGRATOR_PATH ? I.ip.max_depth + 1 : 1;
+    uint64_t launches = 0;
+    for (uint64_t base = 0; base < total; base += kChunk) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(kChunk, total - base);
+        RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
+        generate_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count,
+                                                                    I.d_paths, I.q);
+        launches += 1;
+        int cur = 0;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            int n = 0;
+            int rc = I.agg->closest_hit_indirect(count, I.q.counters + cur, I.q.ext_rays[cur], I.q.hits, I.stream, err, &n);
+            if (rc != RRT_OK) return rc;
+            launches += n;
+            shade_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
+            rc = I.agg->any_hit_indirect(count, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream, err, &n);
+            if (rc != RRT_OK) return rc;
+            launches += n;
+            resolve_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.d_paths, I.q);
+            advance_kernel<<<1, 1, 0, I.stream>>>(I.q, cur);
+            launches += 3;
+            cur ^= 1;
+        }
+        deposit_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.film, I.d_paths, count, static_cast<double*>(d_film_),
+                                                                   I.dump_enabled ? I.d_dump : nullptr, I.dump_count + base);
+        launches += 1;
+        stats_.chunks += 1;
+    }
+    RND_CUDA(cudaGetLastError());
+    uint32_t hc[16];
+    RND_CUDA(cudaMemcpyAsync(hc, I.q.counters, sizeof(hc), cudaMemcpyDeviceToHost, I.stream));
+    RND_CUDA(cudaStreamSynchronize(I.stream));
+    RND_CUDA(cudaMemsetAsync(I.q.counters + 4, 0, 12 * sizeof(uint32_t), I.stream));
+    if (I.dump_enabled) I.dump_count += total;
+    stats_.camera_rays += hc[4];
+    stats_.extension_rays += hc[5];
+    stats_.shadow_rays += hc[6];
+    stats_.bounces += hc[7];
+    stats_.zero_weight += hc[8];
+    stats_.samples += (uint64_t)hc[4] + hc[8];
+    stats_.launches += launches;
+    stats_.render_usec +=
+        (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
+    return RRT_OK;
+}
+
+int Renderer::read_film(double* rgb_out, double* raw, std::string* err) {
+    if (!impl_) return RRT_ERR_INVALID;
+    RND_CUDA(cudaSetDevice(impl_->device));
+    const size_t npix = (size_t)xres_ * (size_t)yres_;
+    std::vector<double> h(4 * npix);
+    RND_CUDA(cudaMemcpy(h.data(), d_film_, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npix; ++i) {
+        const double* c = &h[4 * i];
+        // merge_film_tile (film.rs:248-263): tile contribution -> XYZ; the weight sum is added
+        // once per colour channel (Q14)
+        double xyz[3] = {0.412453 * c[0] + 0.357580 * c[1] + 0.180423 * c[2],
+                         0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2],
+                         0.019334 * c[0] + 0.119193 * c[1] + 0.950227 * c[2]};
+        double fws = 0.0;
+        for (int k = 0; k < 3; ++k) fws += c[3];
+        if (raw) {
+            raw[4 * i] = xyz[0];
+            raw[4 * i + 1] = xyz[1];
+            raw[4 * i + 2] = xyz[2];
+            raw[4 * i + 3] = fws;
+        }
+        if (rgb_out) {
+            // Film::write_image (film.rs:323-366)
+            double rgbv[3] = {3.240479 * xyz[0] - 1.537150 * xyz[1] - 0.498535 * xyz[2],
+                              -0.969256 * xyz[0] + 1.875991 * xyz[1] + 0.041556 * xyz[2],
+                              0.055648 * xyz[0] - 0.204043 * xyz[1] + 1.057311 * xyz[2]};
+            if (fws != 0.0) {
+                const double inv = 1.0 / fws;
+                for (int k = 0; k < 3; ++k) rgbv[k] = std::fmax(0.0, rgbv[k] * inv);
+            }
+            for (int k = 0; k < 3; ++k) rgb_out[3 * i + k] = (rgbv[k] + 0.0) * impl_->film_scale;
+        }
+    }
+    return RRT_OK;
+}
+
+int Renderer::copy_film_device(void* dst, void* stream, std::string* err) {
+    if (!impl_ || !dst) return RRT_ERR_INVALID;
+    RND_CUDA(cudaMemcpyAsync(dst, d_film_, film_doubles() * sizeof(double), cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+    return RRT_OK;
+}
+
+int Renderer::hit_dump(int enable, double* out, uint64_t capacity, uint64_t* count, std::string* err) {
+    if (!impl_) return RRT_ERR_INVALID;
+    Impl& I = *impl_;
+    I.dump_enabled = enable != 0;
+    if (count) *count = I.dump_count;
+    if (out && I.dump_count) {
+        const uint64_t n = std::min<uint64_t>(capacity, I.dump_count);
+        RND_CUDA(cudaMemcpy(out, I.d_dump, n * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return RRT_OK;
+}
+
+}  // namespace rrt

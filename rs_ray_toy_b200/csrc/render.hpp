@@ -1,0 +1,50 @@
+// Host-visible interface of the wavefront renderer: the GPU stand-in for
+// `Box<dyn Integrator>` + `Arc<RealisticCamera>` + `Arc<Film>` + `Arc<dyn SamplerBuilder>`
+// (src/integrator/mod.rs:21-46, make_integrator in src/renderprocess.rs:1399-1499).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rrt.h"
+#include "aggregate.hpp"
+#include "host_scene.hpp"
+
+namespace rrt {
+
+struct RenderStats {
+    uint64_t camera_rays = 0, extension_rays = 0, shadow_rays = 0, bounces = 0, zero_weight = 0, samples = 0,
+             launches = 0, render_usec = 0, setup_usec = 0, chunks = 0;
+};
+
+class Renderer {
+  public:
+    Renderer() = default;
+    ~Renderer();
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+
+    // make_integrator: film, camera (thick-lens focus + exit-pupil bounds), sampler tables,
+    // light distribution; uploads the shading tables of `scene`.
+    int create(int device, const HostScene& scene, const DeviceAggregate* agg, const std::vector<rrt_material>& materials,
+               const std::vector<rrt_light>& lights, const double world_bound6[6], const rrt_render_desc& desc,
+               std::string* err);
+    // Integrator::render for this rank's tiles
+    int run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, std::string* err);
+    int clear(std::string* err);
+    int read_film(double* rgb, double* raw, std::string* err);
+    int copy_film_device(void* dst, void* stream, std::string* err);
+    void* film_device() const { return d_film_; }
+    uint64_t film_doubles() const { return 4ull * (uint64_t)xres_ * (uint64_t)yres_; }
+    int hit_dump(int enable, double* out, uint64_t capacity, uint64_t* count, std::string* err);
+    const RenderStats& stats() const { return stats_; }
+
+  private:
+    struct Impl;
+    Impl* impl_ = nullptr;
+    void* d_film_ = nullptr;
+    int64_t xres_ = 0, yres_ = 0;
+    RenderStats stats_;
+};
+
+}  // namespace rrt

@@ -1,0 +1,440 @@
+// scene.json + Wavefront .obj loading: the subset of src/renderprocess.rs (deploy_render,
+// make_scene, make_materials, make_triangle_mesh, make_all_lights, make_aggregate, make_film,
+// make_camera, make_sampler, make_integrator) and src/objparser.rs that the hot path consumes
+// (SURVEY.md Appendix C).  Keys, defaults and quirks follow the reference:
+//   * objs[].world_pos/rotation/scale are parsed but never applied to vertices (Q7);
+//   * a material parameter is a texture NAME; the only textures honoured here are BilerpTextures
+//     whose corners agree (the loader reads v10 and v11 from key "v01", renderprocess.rs:326-329),
+//     i.e. constants; everything else falls back to the documented default or is refused;
+//   * point lights ignore their transform (Q17); `Filter` must exist (may be {}).
+#include "scene_json.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+#include "json_min.hpp"
+
+namespace rrt {
+namespace {
+
+using json::Value;
+
+std::string read_file(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+// read_i64 / read_f64 / read_bool / read_string (renderprocess.rs:136-169)
+double read_f64(const Value& v, const char* key, double def) {
+    const Value* x = v.get(key);
+    return (x && x->is_number()) ? x->num : def;
+}
+int64_t read_i64(const Value& v, const char* key, int64_t def) {
+    const Value* x = v.get(key);
+    return (x && x->is_number()) ? (int64_t)x->num : def;
+}
+bool read_bool(const Value& v, const char* key, bool def) {
+    const Value* x = v.get(key);
+    return (x && x->kind == Value::Bool) ? x->b : def;
+}
+std::string read_string(const Value& v, const char* key, const char* def) {
+    const Value* x = v.get(key);
+    return (x && x->is_string()) ? x->str : std::string(def);
+}
+bool read_xyz(const Value& v, const char* key, double out[3], double dx, double dy, double dz) {
+    out[0] = dx;
+    out[1] = dy;
+    out[2] = dz;
+    const Value* x = v.get(key);
+    if (x && x->is_array() && x->arr.size() >= 3 && x->arr[0]->is_number() && x->arr[1]->is_number() && x->arr[2]->is_number()) {
+        for (int k = 0; k < 3; ++k) out[k] = x->arr[k]->num;
+        return true;
+    }
+    return false;
+}
+// make_spectrum (renderprocess.rs:1055-1076): { "values": [r, g, b] }
+void read_spectrum(const Value& v, const char* key, double out[3], double def) {
+    out[0] = out[1] = out[2] = def;
+    const Value* x = v.get(key);
+    if (!x) return;
+    const Value* vals = x->get("values");
+    if (!vals) return;
+    if (!vals->is_array() || vals->arr.size() < 3) throw std::runtime_error(std::string("Failed to parse Spectrum ") + key);
+    for (int k = 0; k < 3; ++k) out[k] = vals->arr[k]->num;
+}
+
+void mul44(const double a[4][4], const double b[4][4], double r[4][4]) {  // transform.rs:165-177
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j] + a[i][3] * b[3][j];
+}
+void normalize3(double v[3]) {  // Vector3f::normalize (geometry.rs:925-931)
+    double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (l == 0.0) return;
+    for (int k = 0; k < 3; ++k) v[k] /= l;
+}
+// make_to_world (renderprocess.rs:242-252): translate * rotate(angle, normalize(axis)) * scale
+Transform make_to_world(const Value& cfg) {
+    double pos[3], axis[3], sc[3];
+    read_xyz(cfg, "world_pos", pos, 0, 0, 0);
+    read_xyz(cfg, "rotation_axis", axis, 0, 0, 0);
+    read_xyz(cfg, "scale", sc, 1, 1, 1);
+    normalize3(axis);
+    const double angle = read_f64(cfg, "rotation_angle", 0.0);
+    double T[4][4] = {{1, 0, 0, pos[0]}, {0, 1, 0, pos[1]}, {0, 0, 1, pos[2]}, {0, 0, 0, 1}};
+    double Ti[4][4] = {{1, 0, 0, -pos[0]}, {0, 1, 0, -pos[1]}, {0, 0, 1, -pos[2]}, {0, 0, 0, 1}};
+    // Transform::rotate (transform.rs:327-351) normalises the axis again
+    double a[3] = {axis[0], axis[1], axis[2]};
+    normalize3(a);
+    const double rad = (3.14159265358979323846264338327950288 / 180.0) * angle;
+    const double s = std::sin(rad), c = std::cos(rad);
+    double R[4][4] = {{a[0] * a[0] + (1.0 - a[0] * a[0]) * c, a[0] * a[1] * (1.0 - c) - a[2] * s, a[0] * a[2] * (1.0 - c) + a[1] * s, 0},
+                      {a[0] * a[1] * (1.0 - c) + a[2] * s, a[1] * a[1] + (1.0 - a[1] * a[1]) * c, a[1] * a[2] * (1.0 - c) - a[0] * s, 0},
+                      {a[0] * a[2] * (1.0 - c) - a[1] * s, a[1] * a[2] * (1.0 - c) + a[0] * s, a[2] * a[2] + (1.0 - a[2] * a[2]) * c, 0},
+                      {0, 0, 0, 1}};
+    double Ri[4][4];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) Ri[i][j] = R[j][i];
+    double S[4][4] = {{sc[0], 0, 0, 0}, {0, sc[1], 0, 0}, {0, 0, sc[2], 0}, {0, 0, 0, 1}};
+    double Si[4][4] = {{1.0 / sc[0], 0, 0, 0}, {0, 1.0 / sc[1], 0, 0}, {0, 0, 1.0 / sc[2], 0}, {0, 0, 0, 1}};
+    Transform out;
+    double TR[4][4], RiTi[4][4];
+    mul44(T, R, TR);
+    mul44(TR, S, out.m.m);
+    // (T*R)*S inverse = S^-1 * (R^-1 * T^-1)  (Transform::mul, transform.rs:441-449)
+    mul44(Ri, Ti, RiTi);
+    mul44(Si, RiTi, out.inv.m);
+    return out;
+}
+
+// objparser.rs:83-247
+void parse_obj(const std::string& path, TriangleMesh* mesh) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::vector<uint32_t> vi, ni, uvi;
+    std::string line;
+    auto parse_index = [](const std::string& tok, int64_t out[3]) {
+        out[0] = out[1] = out[2] = -1;
+        size_t start = 0;
+        for (int k = 0; k < 3 && start <= tok.size(); ++k) {
+            size_t slash = tok.find('/', start);
+            std::string part = tok.substr(start, slash == std::string::npos ? std::string::npos : slash - start);
+            bool digits = !part.empty();
+            for (char c : part) digits &= (c >= '0' && c <= '9');
+            if (digits) {
+                int64_t v = std::strtoll(part.c_str(), nullptr, 10);
+                out[k] = v > 0 ? v - 1 : -1;  // usize::from_str(idx) - 1 (:219)
+            }
+            if (slash == std::string::npos) break;
+            start = slash + 1;
+        }
+    };
+    while (std::getline(f, line)) {
+        std::istringstream ss(line);
+        std::string tag;
+        if (!(ss >> tag)) continue;
+        if (tag == "v") {
+            double x, y, z;
+            if (!(ss >> x >> y >> z)) throw std::runtime_error("ParseObjError: bad vertex in " + path);
+            mesh->p.insert(mesh->p.end(), {x, y, z});
+        } else if (tag == "vt") {
+            double u, v = 0.0;
+            if (!(ss >> u)) throw std::runtime_error("ParseObjError: bad uv in " + path);
+            ss >> v;
+            mesh->uv.insert(mesh->uv.end(), {u, v});
+        } else if (tag == "vn") {
+            double x, y, z;
+            if (!(ss >> x >> y >> z)) throw std::runtime_error("ParseObjError: bad normal in " + path);
+            const double l = std::sqrt(x * x + y * y + z * z);  // Normal3f::normalize on read (:130)
+            mesh->n.insert(mesh->n.end(), {x / l, y / l, z / l});
+        } else if (tag == "f") {
+            std::string t[3];
+            if (!(ss >> t[0] >> t[1] >> t[2])) throw std::runtime_error("ParseObjError: Failed to get face element");
+            int64_t e[3][3];
+            for (int k = 0; k < 3; ++k) parse_index(t[k], e[k]);
+            if (e[0][0] >= 0 && e[1][0] >= 0 && e[2][0] >= 0) {
+                for (int k = 0; k < 3; ++k) vi.push_back((uint32_t)e[k][0]);
+                const int64_t nuv = (int64_t)mesh->uv.size() / 2, nn = (int64_t)mesh->n.size() / 3;
+                if (e[0][1] >= 0 && e[1][1] >= 0 && e[2][1] >= 0 && nuv > 0 && e[0][1] < nuv && e[1][1] < nuv && e[2][1] < nuv)
+                    for (int k = 0; k < 3; ++k) uvi.push_back((uint32_t)e[k][1]);
+                if (e[0][2] >= 0 && e[1][2] >= 0 && e[2][2] >= 0 && nn > 0 && e[0][2] < nn && e[1][2] < nn && e[2][2] < nn)
+                    for (int k = 0; k < 3; ++k) ni.push_back((uint32_t)e[k][2]);
+            }
+        }
+        // "#" and anything else: ignored (the reference logs unknown elements)
+    }
+    mesh->vi = vi;
+    // index arrays that do not cover every face cannot be addressed per triangle (triangle.rs:88-98)
+    if (ni.size() == vi.size()) mesh->ni = ni;
+    if (uvi.size() == vi.size()) mesh->uvi = uvi;
+    for (uint32_t x : mesh->vi)
+        if ((size_t)x >= mesh->p.size() / 3) throw std::runtime_error("ParseObjError: vertex index out of range in " + path);
+}
+
+struct ConstTextures {
+    std::map<std::string, double> f;
+    std::map<std::string, std::array<double, 3>> rgb;
+};
+ConstTextures collect_textures(const Value& root) {
+    ConstTextures t;
+    if (const Value* a = root.get("float_texture"); a && a->is_array())
+        for (const auto& tc : a->arr) {
+            if (read_string(*tc, "texture_type", "") != "BilerpTexture") continue;
+            const double v00 = read_f64(*tc, "v00", 0.0), v01 = read_f64(*tc, "v01", 1.0);
+            if (v00 == v01) t.f[read_string(*tc, "texture_name", "DefaultTextureName")] = v00;
+        }
+    if (const Value* a = root.get("rgb_texture"); a && a->is_array())
+        for (const auto& tc : a->arr) {
+            if (read_string(*tc, "texture_type", "") != "BilerpTexture") continue;
+            double v00[3], v01[3];
+            read_spectrum(*tc, "v00", v00, 0.0);
+            read_spectrum(*tc, "v01", v01, 1.0);
+            if (v00[0] == v01[0] && v00[1] == v01[1] && v00[2] == v01[2])
+                t.rgb[read_string(*tc, "texture_name", "DefaultTextureName")] = {v00[0], v00[1], v00[2]};
+        }
+    return t;
+}
+double tex_f(const Value& m, const ConstTextures& t, const char* key, double def) {
+    const Value* x = m.get(key);
+    if (x && x->is_string()) {
+        auto it = t.f.find(x->str);
+        if (it == t.f.end()) throw std::runtime_error("float texture '" + x->str + "' is outside the hot-path scope (constants only)");
+        return it->second;
+    }
+    return def;
+}
+void tex_rgb(const Value& m, const ConstTextures& t, const char* key, double out[3], const double def[3]) {
+    const Value* x = m.get(key);
+    if (x && x->is_string()) {
+        auto it = t.rgb.find(x->str);
+        if (it != t.rgb.end()) {  // fetch_rgb_texture falls through to the default when the name is unknown
+            for (int k = 0; k < 3; ++k) out[k] = it->second[k];
+            return;
+        }
+    }
+    for (int k = 0; k < 3; ++k) out[k] = def[k];
+}
+
+// RGB of the reference's default copper spectra: material/metal.rs COPPER_N / COPPER_K pushed
+// through RGBSpectrum::from_sampled (spectrum.rs:2701-2727); derivation in tests/golden/make_copper_rgb.py
+const double kCopperN[3] = {0.19998972096819712, 0.922085788777433, 1.0998762520488314};
+const double kCopperK[3] = {3.9046381767086675, 2.4476332238684626, 2.1376510366555137};
+
+bool make_material(const Value& m, const ConstTextures& t, rrt_material* out) {
+    const std::string type = read_string(m, "material_type", "");
+    rrt_material r;
+    std::memset(&r, 0, sizeof(r));
+    r.u_roughness = r.v_roughness = -1.0;
+    r.remap_roughness = read_bool(m, "remap_roughness", false) ? 1 : 0;
+    const double c5[3] = {0.5, 0.5, 0.5}, c25[3] = {0.25, 0.25, 0.25}, c9[3] = {0.9, 0.9, 0.9}, c1[3] = {1.0, 1.0, 1.0};
+    if (type == "MatteMaterial") {
+        r.kind = RRT_MAT_MATTE;
+        tex_rgb(m, t, "kd", r.kd, c5);
+        r.sigma = tex_f(m, t, "sigma", 0.0);
+    } else if (type == "PlasticMaterial") {
+        r.kind = RRT_MAT_PLASTIC;
+        tex_rgb(m, t, "kd", r.kd, c25);
+        tex_rgb(m, t, "ks", r.ks, c25);
+        r.roughness = tex_f(m, t, "roughness", 0.1);
+    } else if (type == "MetalMaterial") {
+        r.kind = RRT_MAT_METAL;
+        tex_rgb(m, t, "eta", r.metal_eta, kCopperN);
+        tex_rgb(m, t, "k", r.metal_k, kCopperK);
+        r.roughness = tex_f(m, t, "roughness", 0.01);
+        r.u_roughness = tex_f(m, t, "u_roughness", -1.0);
+        r.v_roughness = tex_f(m, t, "v_roughness", -1.0);
+    } else if (type == "MirrorMaterial") {
+        r.kind = RRT_MAT_MIRROR;
+        tex_rgb(m, t, "kr", r.kr, c9);
+    } else if (type == "GlassMaterial") {
+        r.kind = RRT_MAT_GLASS;
+        tex_rgb(m, t, "kr", r.kr, c1);
+        tex_rgb(m, t, "kt", r.kt, c1);
+        r.eta = tex_f(m, t, "eta", 1.5);
+        r.u_roughness = tex_f(m, t, "u_roughness", 0.0);
+        r.v_roughness = tex_f(m, t, "v_roughness", 0.0);
+    } else {
+        return false;  // Disney / Translucent / Mix / Debug: outside the hot path
+    }
+    if (m.get("bump_map") && m.get("bump_map")->is_string()) throw std::runtime_error("bump maps are outside the hot-path scope");
+    *out = r;
+    return true;
+}
+
+}  // namespace
+
+void load_scene_json(const std::string& path, const std::string& overrides_json, uint64_t seed, LoadedScene* out) {
+    json::ValuePtr root = json::parse(read_file(path));
+    if (!root->is_object()) throw std::runtime_error("scene.json: top level must be an object");
+    if (!overrides_json.empty()) {
+        json::ValuePtr ov = json::parse(overrides_json);
+        if (!ov->is_object()) throw std::runtime_error("overrides must be a JSON object");
+        for (const auto& kv : ov->obj) root->set(kv.first, kv.second);
+    }
+    std::string dir = ".";
+    if (size_t slash = path.find_last_of('/'); slash != std::string::npos) dir = path.substr(0, slash);
+
+    const ConstTextures tex = collect_textures(*root);
+    // ---- make_materials ----
+    std::map<std::string, uint32_t> material_index;
+    if (const Value* a = root->get("materials"); a && a->is_array())
+        for (const auto& mc : a->arr) {
+            rrt_material m;
+            if (make_material(*mc, tex, &m)) {
+                material_index[read_string(*mc, "material_name", "DefaultMaterialName")] = (uint32_t)out->materials.size();
+                out->materials.push_back(m);
+            }
+        }
+    // ---- make_triangle_mesh ----
+    std::map<std::string, uint32_t> mesh_index;
+    if (const Value* a = root->get("objs"); a && a->is_array())
+        for (const auto& oc : a->arr) {
+            TriangleMesh mesh;
+            const std::string file = read_string(*oc, "filename", "DefaultObj");
+            parse_obj(file.size() && file[0] == '/' ? file : dir + "/" + file, &mesh);
+            mesh_index[read_string(*oc, "obj_name", "DefaultObjName")] = (uint32_t)out->scene.meshes.size();
+            out->scene.meshes.push_back(std::move(mesh));
+        }
+    // ---- make_aggregate ----
+    const Value* agg = root->get("Aggregate");
+    if (!agg) throw std::runtime_error("No Aggregate Config Defined");
+    out->max_prims_in_node = (uint32_t)read_i64(*agg, "max_prims_in_node", 4);
+    if (const Value* prims = agg->get("primitives"); prims && prims->is_array())
+        for (const auto& pc : prims->arr) {
+            const std::string type = read_string(*pc, "primitive_type", "");
+            auto mit = material_index.find(read_string(*pc, "material_name", "DefaultMaterialName"));
+            const Value* inst = pc->get("instances");
+            const bool instanced = inst && inst->is_array();
+            if (type == "sphere") {
+                if (mit == material_index.end()) continue;
+                Sphere s;
+                s.obj_to_world = make_to_world(*pc);
+                s.radius = read_f64(*pc, "radius", 1.0);
+                s.z_min = read_f64(*pc, "z_min", -s.radius);
+                s.z_max = read_f64(*pc, "z_max", s.radius);
+                s.phi_max_deg = read_f64(*pc, "phi_max", 360.0);
+                out->scene.spheres.push_back(s);
+                const uint32_t sid = (uint32_t)out->scene.spheres.size() - 1;
+                if (instanced) {
+                    for (const auto& ic : inst->arr) {
+                        out->scene.instances.push_back(make_to_world(*ic));
+                        out->scene.prims.push_back({SHAPE_SPHERE, sid, 0, (int32_t)out->scene.instances.size() - 1, mit->second});
+                    }
+                } else {
+                    out->scene.prims.push_back({SHAPE_SPHERE, sid, 0, -1, mit->second});
+                }
+            } else if (type == "triangle") {
+                auto oit = mesh_index.find(read_string(*pc, "obj_name", "DefaultObjName"));
+                if (oit == mesh_index.end() || mit == material_index.end()) continue;
+                const uint32_t nt = out->scene.meshes[oit->second].n_triangles();
+                if (instanced) {
+                    for (const auto& ic : inst->arr) {
+                        out->scene.instances.push_back(make_to_world(*ic));
+                        const int32_t xi = (int32_t)out->scene.instances.size() - 1;
+                        for (uint32_t t = 0; t < nt; ++t) out->scene.prims.push_back({SHAPE_TRIANGLE, oit->second, t, xi, mit->second});
+                    }
+                } else {
+                    for (uint32_t t = 0; t < nt; ++t) out->scene.prims.push_back({SHAPE_TRIANGLE, oit->second, t, -1, mit->second});
+                }
+            }
+        }
+    // ---- make_all_lights ----
+    if (const Value* a = root->get("lights"); a && a->is_array())
+        for (const auto& lc : a->arr) {
+            rrt_light l;
+            std::memset(&l, 0, sizeof(l));
+            const std::string type = read_string(*lc, "light_type", "");
+            const Transform xf = make_to_world(*lc);
+            std::memcpy(l.to_world, xf.m.m, sizeof(l.to_world));
+            if (type == "point") {
+                l.kind = RRT_LIGHT_POINT;
+                read_spectrum(*lc, "spectrum", l.intensity, 1.0);
+            } else if (type == "distant") {
+                l.kind = RRT_LIGHT_DISTANT;
+                double li[3], sc[3], from[3], to[3];
+                read_spectrum(*lc, "l", li, 1.0);
+                read_spectrum(*lc, "scale", sc, 1.0);
+                read_xyz(*lc, "from", from, 0, 0, 0);
+                read_xyz(*lc, "to", to, 0, 0, 1);
+                for (int k = 0; k < 3; ++k) {
+                    l.intensity[k] = li[k] * sc[k];
+                    l.dir[k] = from[k] - to[k];
+                }
+            } else {
+                throw std::runtime_error("light type '" + type + "' is outside the hot-path scope (point, distant)");
+            }
+            out->lights.push_back(l);
+        }
+    if (const Value* a = root->get("infinite_lights"); a && a->is_array() && !a->arr.empty())
+        throw std::runtime_error("infinite lights are outside the hot-path scope");
+
+    // ---- make_integrator: film, camera, sampler, integrator ----
+    const Value *ic = root->get("Integrator"), *sc = root->get("Sampler"), *fc = root->get("Film"), *cc = root->get("Camera");
+    if (!ic || !sc || !fc || !cc) throw std::runtime_error("Failed to create Integrator: Integrator / Sampler / Film / Camera missing");
+    rrt_render_desc& d = out->desc;
+    std::memset(&d, 0, sizeof(d));
+    d.xres = read_i64(*fc, "xres", 1280);
+    d.yres = read_i64(*fc, "yres", 720);
+    d.scale = read_f64(*fc, "scale", 1.0);
+    d.diagonal_mm = read_f64(*fc, "diagonal", 35.0);
+    d.max_sample_luminance = read_f64(*fc, "max_sample_luminance", INFINITY);
+    const Value* flt = fc->get("Filter");
+    if (!flt) throw std::runtime_error("Failed to create Film: filter_config not found");
+    {
+        const std::string ft = read_string(*flt, "filter_type", "BoxFilter");
+        double def = 0.5;
+        d.filter_kind = RRT_FILTER_BOX;
+        if (ft == "TriangleFilter") {
+            d.filter_kind = RRT_FILTER_TRIANGLE;
+            def = 2.0;
+        } else if (ft == "GaussianFilter") {
+            d.filter_kind = RRT_FILTER_GAUSSIAN;
+            def = 2.0;
+        }
+        d.filter_radius[0] = d.filter_radius[1] = def;
+        if (const Value* r = flt->get("radius"); r && r->is_array() && r->arr.size() >= 2) {
+            d.filter_radius[0] = r->arr[0]->num;
+            d.filter_radius[1] = r->arr[1]->num;
+        }
+        d.filter_alpha = read_f64(*flt, "alpha", 2.0);
+    }
+    read_xyz(*cc, "world_pos", d.cam_pos, 0, 0, 0);
+    read_xyz(*cc, "look", d.cam_look, 1, 1, 1);
+    read_xyz(*cc, "up", d.cam_up, 0, 0, 1);
+    d.shutter_open = read_f64(*cc, "shutter_open", 0.0);
+    d.shutter_close = read_f64(*cc, "shutter_close", 1.0);
+    d.aperture_diameter = read_f64(*cc, "aperture_diameter", 1.0);
+    d.focus_distance = read_f64(*cc, "focus_distance", 10.0);
+    d.simple_weighting = read_bool(*cc, "simple_weighting", true) ? 1 : 0;
+    const Value* lens = cc->get("lens_data");
+    if (!lens || !lens->is_array()) throw std::runtime_error("Camera.lens_data is required (renderprocess.rs:1379)");
+    for (const auto& x : lens->arr) out->lens_data.push_back(x->num);
+    d.lens_data = out->lens_data.data();
+    d.n_lens_values = (uint32_t)out->lens_data.size();
+    const std::string st = read_string(*sc, "sampler_type", "");
+    if (st != "HaltonSampler")
+        throw std::runtime_error("Sampler '" + st + "': only HaltonSampler is reproducible; StratifiedSampler draws from an unseeded RNG");
+    d.nsamp = (uint64_t)read_i64(*sc, "nsamp", 16);
+    d.sample_at_center = read_bool(*sc, "sample_at_center", false) ? 1 : 0;
+    d.seed = seed;
+    const std::string it = read_string(*ic, "integrator_type", "AO");
+    if (it == "Path") {
+        d.integrator_kind = RRT_INTEGRATOR_PATH;
+        d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
+        d.rr_threshold = read_f64(*ic, "rr_threshold", 1.0);
+    } else if (it == "DirectLighting") {
+        if (read_string(*ic, "light_strategy", "one") == "all")
+            throw std::runtime_error("DirectLighting light_strategy 'all' is outside the hot-path scope");
+        d.integrator_kind = RRT_INTEGRATOR_DIRECT;
+        d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
+        d.rr_threshold = 1.0;
+    } else {
+        throw std::runtime_error("integrator '" + it + "' is outside the hot-path scope (Path, DirectLighting)");
+    }
+}
+
+}  // namespace rrt

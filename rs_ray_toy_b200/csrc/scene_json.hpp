@@ -1,0 +1,26 @@
+// deploy_render's loader (src/renderprocess.rs:92-105) for the hot-path subset of the schema.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rrt.h"
+#include "host_scene.hpp"
+
+namespace rrt {
+
+struct LoadedScene {
+    HostScene scene;
+    std::vector<rrt_material> materials;
+    std::vector<rrt_light> lights;
+    std::vector<double> lens_data;  // desc.lens_data points here
+    rrt_render_desc desc;
+    uint32_t max_prims_in_node = 4;
+};
+
+// Throws std::runtime_error with the reason on unreadable / unsupported input.
+void load_scene_json(const std::string& path, const std::string& overrides_json, uint64_t seed, LoadedScene* out);
+
+}  // namespace rrt

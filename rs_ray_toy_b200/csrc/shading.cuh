@@ -1,0 +1,628 @@
+// Device-side shading for the wavefront path tracer: hit record -> surface frame
+// (src/shape/triangle.rs:266-388, src/shape/sphere.rs:157-258, src/transform.rs:618-656),
+// material -> lobes (src/material/{matte,plastic,metal,mirror,glass}.rs), and the Bsdf
+// f / pdf / sample_f logic over those lobes (src/reflection.rs:216-404 with the BxDFs at
+// :622-1026 and the Trowbridge–Reitz distribution of src/microfacet.rs:253-425).
+//
+// A material kind fixes its lobe list, so there is no per-hit allocation (the reference builds a
+// Vec<Arc<dyn BxDF>> per hit): at most two lobes live in registers.  Quirks kept (Appendix A):
+// Q15 (Bsdf::sample_f: other lobes' pdfs added only when the chosen lobe is not reflective, the
+// recomputed multi-lobe f discarded), Q16 (Plastic's specular lobe gated on kd), Q5a (sphere hit
+// point taken on the instance-space ray), FresnelSpecular's type = SPECULAR | ALL.
+#pragma once
+#include "rmath.cuh"
+
+namespace rrt {
+
+// ---- scene tables in HBM ---------------------------------------------------------------------------
+struct PrimInfo {       // one per entry of the primitive list (prim_id order)
+    uint32_t kind;      // 0 triangle, 1 sphere
+    uint32_t material;
+    int32_t instance;   // -1 = bare GeometricPrimitive
+    uint32_t shape;     // triangle: mesh id; sphere: sphere id
+    uint32_t tri;       // triangle number inside the mesh
+    uint32_t pad[3];
+};
+struct MeshInfo {
+    uint64_t p_off, vi_off, n_off, ni_off, uv_off, uvi_off;  // element offsets into the pooled arrays
+    uint32_t has_n, has_ni, has_uv, has_uvi;
+};
+struct SphereInfo {
+    M34 o2w, w2o;
+    double radius, theta_min, theta_max, phi_max;
+};
+struct InstanceXf {
+    M34 m, inv;
+    uint32_t is_identity, pad;
+};
+struct MaterialRec {  // rrt_material, flattened
+    uint32_t kind, remap_roughness;
+    Rgb kd, ks, kr, kt, metal_eta, metal_k;
+    double sigma, roughness, u_roughness, v_roughness, eta;
+};
+struct LightRec {
+    uint32_t kind, pad;
+    Rgb intensity;
+    V3 p_light;       // point
+    V3 w_light;       // distant (normalised, world space)
+    double world_radius;
+};
+struct ShadeScene {
+    const PrimInfo* prims;
+    const MeshInfo* meshes;
+    const double* mesh_p;     // xyz per vertex (object space; the obj transform is never applied, Q7)
+    const uint32_t* mesh_vi;
+    const double* mesh_n;
+    const uint32_t* mesh_ni;
+    const double* mesh_uv;
+    const uint32_t* mesh_uvi;
+    const SphereInfo* spheres;
+    const InstanceXf* instances;
+    const MaterialRec* materials;
+    const LightRec* lights;
+    uint32_t n_lights, pad;
+};
+
+// What the integrator reads of a SurfaceInteraction (interaction.rs:95-113)
+struct Surface {
+    V3 p, n, wo;       // BaseInteraction: point, geometric normal, outgoing direction
+    V3 shn, shdpdu;    // shading.n, shading.dpdu
+    uint32_t material;
+};
+
+__device__ __forceinline__ V3 ld3(const double* a, uint64_t i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+
+// transform.rs:618-656
+__device__ __forceinline__ void xf_surface(const M34& m, const M34& inv, Surface* s) {
+    s->p = xf_point(m, s->p);
+    s->wo = xf_vector(m, s->wo);
+    s->n = xf_normal_inv(inv, s->n);
+    s->shn = normalize_n(xf_normal_inv(inv, s->shn));
+    s->shdpdu = xf_vector(m, s->shdpdu);
+    s->shn = faceforward(s->shn, s->n);
+}
+
+// Rebuilds the surface frame of hit (prim_id, t, u, v) for the world ray (o, d).
+__device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
+                                          Surface* out) {
+    const PrimInfo pi = sc.prims[prim_id];
+    V3 lo = o, ld = d;
+    if (pi.instance >= 0) {  // TransformedPrimitive::intersect (primitives.rs:126-139), Q6 fixed: d keeps its length
+        const InstanceXf& x = sc.instances[pi.instance];
+        lo = xf_point(x.inv, o);
+        ld = xf_vector(x.inv, d);
+    }
+    Surface s;
+    s.material = pi.material;
+    if (pi.kind == 0) {
+        const MeshInfo mi = sc.meshes[pi.shape];
+        const uint32_t* vi = sc.mesh_vi + mi.vi_off + 3ull * pi.tri;
+        const uint32_t v0 = vi[0], v1 = vi[1], v2 = vi[2];
+        const V3 p0 = ld3(sc.mesh_p + 3 * mi.p_off, v0), p1 = ld3(sc.mesh_p + 3 * mi.p_off, v1), p2 = ld3(sc.mesh_p + 3 * mi.p_off, v2);
+        // triangle.rs:113-129 get_uvs
+        P2 uv0 = {0.0, 0.0}, uv1 = {1.0, 0.0}, uv2 = {1.0, 1.0};
+        if (mi.has_uv) {
+            const double* uvb = sc.mesh_uv + 2 * mi.uv_off;
+            uint32_t i0 = 0, i1 = 0, i2 = 0;
+            if (mi.has_uvi) {
+                const uint32_t* ui = sc.mesh_uvi + mi.uvi_off + 3ull * pi.tri;
+                i0 = ui[0]; i1 = ui[1]; i2 = ui[2];
+            }
+            uv0 = P2{uvb[2 * i0], uvb[2 * i0 + 1]};
+            uv1 = P2{uvb[2 * i1], uvb[2 * i1 + 1]};
+            uv2 = P2{uvb[2 * i2], uvb[2 * i2 + 1]};
+        }
+        const double du02 = uv0.x - uv2.x, dv02 = uv0.y - uv2.y, du12 = uv1.x - uv2.x, dv12 = uv1.y - uv2.y;
+        const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+        const double determinant = du02 * dv12 - dv02 * du12;
+        const bool degenerate_uv = fabs(determinant) < 1e-8;
+        V3 dpdu = v3(0, 0, 0), dpdv = v3(0, 0, 0);
+        if (!degenerate_uv) {
+            const double i_det = 1.0 / determinant;
+            dpdu = (dp02 * dv12 - dp12 * dv02) * i_det;
+            dpdv = (dp02 * -du12 + dp12 * du02) * i_det;
+        }
+        if (degenerate_uv || length_sq(cross(dpdu, dpdv)) == 0.0) {
+            V3 ng = cross(p2 - p0, p1 - p0);
+            coordinate_system(normalize(ng), &dpdu, &dpdv);
+        }
+        s.p = lo + ld * t;
+        s.wo = -ld;
+        const V3 ist_n = normalize(cross(dp02, dp12));
+        s.n = ist_n;
+        s.shn = ist_n;
+        s.shdpdu = dpdu;
+        if (mi.has_n && mi.has_ni) {
+            const uint32_t* ni = sc.mesh_ni + mi.ni_off + 3ull * pi.tri;
+            const double* nb = sc.mesh_n + 3 * mi.n_off;
+            const V3 n0 = ld3(nb, ni[0]), n1 = ld3(nb, ni[1]), n2 = ld3(nb, ni[2]);
+            V3 ns = n0 * (1.0 - bu - bv) + n1 * bu + n2 * bv;
+            ns = length_sq(ns) > 0.0 ? normalize_n(ns) : ist_n;
+            V3 ss = normalize(dpdu);
+            V3 ts = cross(ss, ns);
+            if (length_sq(ts) > 0.0) {
+                ts = normalize(ts);
+                ss = cross(ts, ns);
+            } else {
+                coordinate_system(ns, &ss, &ts);
+            }
+            // set_shading_geometry(ss, ts, .., orientation_is_authoritative = true): the shading
+            // normal is the GEOMETRIC normal flipped towards ss x ts (interaction.rs:186-202)
+            V3 nn = normalize(cross(ss, ts));
+            s.shn = faceforward(s.n, nn);
+            s.shdpdu = ss;
+        }
+    } else {
+        const SphereInfo& sp = sc.spheres[pi.shape];
+        // sphere.rs:127-128: the shape works on the object-space ray, but the first hit point is
+        // taken on the ray it was handed (Q5a)
+        const V3 od = xf_vector(sp.w2o, ld);
+        V3 p = lo + ld * t;
+        if (p.x == 0.0 && p.y == 0.0) p.x = 1e-5 * sp.radius;
+        double phi = atan2(p.y, p.x);
+        if (phi < 0.0) phi += 2.0 * kPi;
+        const double theta = acos(clampd(p.z / sp.radius, -1.0, 1.0));
+        const double z_radius = sqrt(p.x * p.x + p.y * p.y);
+        const double inv_z_radius = 1.0 / z_radius;
+        const double cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
+        const V3 dpdu = v3(-sp.phi_max * p.y, sp.phi_max * p.x, 0.0);
+        const V3 dpdv = v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * sin(theta)) * (sp.theta_max - sp.theta_min);
+        s.p = p;
+        s.wo = -od;
+        s.n = normalize(cross(dpdu, dpdv));
+        s.shn = s.n;
+        s.shdpdu = dpdu;
+        xf_surface(sp.o2w, sp.w2o, &s);  // sphere.rs:245-255: always applied
+    }
+    if (pi.instance >= 0) {
+        const InstanceXf& x = sc.instances[pi.instance];
+        if (!x.is_identity) xf_surface(x.m, x.inv, &s);  // primitives.rs:135-137
+    }
+    *out = s;
+}
+
+// ---- reflection.rs helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ double cos2_theta(V3 w) { return w.z * w.z; }
+__device__ __forceinline__ double abs_cos_theta(V3 w) { return fabs(w.z); }
+__device__ __forceinline__ double sin2_theta(V3 w) { return rmax(0.0, 1.0 - cos2_theta(w)); }
+__device__ __forceinline__ double sin_theta(V3 w) { return sqrt(sin2_theta(w)); }
+__device__ __forceinline__ double tan_theta(V3 w) { return sin_theta(w) / w.z; }
+__device__ __forceinline__ double tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+__device__ __forceinline__ double cos_phi(V3 w) {
+    double s = sin_theta(w);
+    return s == 0.0 ? 1.0 : clampd(w.x / s, -1.0, 1.0);
+}
+__device__ __forceinline__ double sin_phi(V3 w) {
+    double s = sin_theta(w);
+    return s == 0.0 ? 0.0 : clampd(w.y / s, -1.0, 1.0);
+}
+__device__ __forceinline__ bool same_hemisphere(V3 a, V3 b) { return a.z * b.z > 0.0; }
+__device__ __forceinline__ V3 reflect_about(V3 wo, V3 n) { return -wo + n * 2.0 * dot(wo, n); }
+__device__ __forceinline__ bool refract_dir(V3 wi, V3 n, double eta, V3* wt) {
+    double cos_i = dot(n, wi);
+    double sin2_i = rmax(0.0, 1.0 - cos_i * cos_i);
+    double sin2_t = eta * eta * sin2_i;
+    if (sin2_t >= 1.0) return false;
+    double cos_t = sqrt(1.0 - sin2_t);
+    *wt = -wi * eta + n * (eta * cos_i - cos_t);
+    return true;
+}
+// reflection.rs:145-168
+__device__ double fr_dielectric(double cos_i, double eta_i, double eta_t) {
+    cos_i = clampd(cos_i, -1.0, 1.0);
+    if (!(cos_i > 0.0)) {
+        double s = eta_i;
+        eta_i = eta_t;
+        eta_t = s;
+        cos_i = fabs(cos_i);
+    }
+    double sin_i = sqrt(rmax(0.0, 1.0 - cos_i * cos_i));
+    double sin_t = eta_i / eta_t * sin_i;
+    if (sin_t >= 1.0) return 1.0;
+    double cos_t = sqrt(rmax(0.0, 1.0 - sin_t * sin_t));
+    double r_parl = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
+    double r_perp = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
+    return (r_parl * r_parl + r_perp * r_perp) / 2.0;
+}
+// reflection.rs:170-195
+__device__ Rgb fr_conductor(double cos_i, Rgb eta_i, Rgb eta_t, Rgb k) {
+    cos_i = clampd(cos_i, -1.0, 1.0);
+    Rgb eta = eta_t / eta_i, eta_k = k / eta_i;
+    double cos2 = cos_i * cos_i, sin2 = 1.0 - cos2;
+    Rgb eta_2 = eta * eta, eta_k2 = eta_k * eta_k;
+    Rgb t0 = eta_2 - eta_k2 - rgb(sin2);
+    Rgb a2_plus_b2 = sqrt_rgb(t0 * t0 + eta_2 * eta_k2 * rgb(4.0));
+    Rgb t1 = a2_plus_b2 + rgb(cos2);
+    Rgb a = sqrt_rgb((a2_plus_b2 + t0) * 0.5);
+    Rgb t2 = a * 2.0 * cos_i;
+    Rgb rs = (t1 - t2) / (t1 + t2);
+    Rgb t3 = a2_plus_b2 * cos2 + rgb(sin2 * sin2);
+    Rgb t4 = t2 * sin2;
+    Rgb rp = rs * (t3 - t4) / (t3 + t4);
+    return (rp + rs) * rgb(0.5);
+}
+// microfacet.rs:12-20
+__device__ double roughness_to_alpha(double roughness) {
+    roughness = rmax(roughness, 1e-3);
+    double x = log(roughness);
+    return 1.62142 + 0.819955 * x + 0.1734 * x * x + 0.0171201 * x * x * x + 0.000640711 * x * x * x * x;
+}
+
+// ---- lobes -----------------------------------------------------------------------------------------------
+enum : uint32_t { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY = 8, BXDF_SPECULAR = 16, BXDF_ALL = 31 };
+enum : uint32_t { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR, LOBE_MICROFACET, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC };
+enum : uint32_t { FRESNEL_NOOP = 0, FRESNEL_DIELECTRIC = 1, FRESNEL_CONDUCTOR = 2 };
+
+struct Lobe {
+    uint32_t kind, fresnel;
+    Rgb r, t;           // reflectance / transmittance
+    Rgb cond_eta, cond_k;  // FresnelConductor eta_t, k (eta_i = 1)
+    double a, b;        // FresnelDielectric eta_i, eta_t of the lobe's Fresnel term
+    double eta_a, eta_b;   // specular transmission / FresnelSpecular indices; Oren–Nayar A, B
+    double alpha_x, alpha_y;
+};
+__device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
+    switch (l.kind) {
+        case LOBE_LAMBERT:
+        case LOBE_OREN_NAYAR: return BXDF_DIFFUSE | BXDF_REFLECTION;
+        case LOBE_MICROFACET: return BXDF_GLOSSY | BXDF_REFLECTION;
+        case LOBE_SPEC_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
+        case LOBE_SPEC_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
+        default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
+    }
+}
+__device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type(l) & flags) == lobe_type(l); }
+__device__ Rgb lobe_fresnel(const Lobe& l, double cos_i) {  // reflection.rs:603-619
+    if (l.fresnel == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
+    if (l.fresnel == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
+    return rgb(1.0);
+}
+// TrowbridgeReitzDistribution (microfacet.rs:364-390)
+__device__ double tr_d(const Lobe& l, V3 wh) {
+    double tan2 = tan2_theta(wh);
+    if (isinf(tan2)) return 0.0;
+    double cos4 = cos2_theta(wh) * cos2_theta(wh);
+    double cp = cos_phi(wh), spv = sin_phi(wh);
+    double e = ((cp * cp) / (l.alpha_x * l.alpha_x) + (spv * spv) / (l.alpha_y * l.alpha_y)) * tan2;
+    return 1.0 / (kPi * l.alpha_x * l.alpha_y * cos4 * (1.0 + e) * (1.0 + e));
+}
+__device__ double tr_lambda(const Lobe& l, V3 w) {
+    double abs_tan = fabs(tan_theta(w));
+    if (isinf(abs_tan)) return 0.0;
+    double cp = cos_phi(w), spv = sin_phi(w);
+    double alpha = sqrt((cp * cp) * (l.alpha_x * l.alpha_x) + (spv * spv) * (l.alpha_y * l.alpha_y));
+    double a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
+    return (-1.0 + sqrt(1.0 + a2t2)) / 2.0;
+}
+__device__ double tr_pdf(const Lobe& l, V3 wo, V3 wh) {  // microfacet.rs:30-36, sample_visible_area
+    return tr_d(l, wh) * (1.0 / (1.0 + tr_lambda(l, wo))) * absdot(wo, wh) / abs_cos_theta(wo);
+}
+// microfacet.rs:270-362
+__device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, double u2) {
+    V3 ws = normalize(v3(ax * wi.x, ay * wi.y, wi.z));
+    double slope_x, slope_y;
+    const double cos_t = ws.z;
+    if (cos_t > 0.9999) {
+        double r = sqrt(u1 / (1.0 - u1));
+        double phi = 6.28318530718 * u2;
+        slope_x = r * cos(phi);
+        slope_y = r * sin(phi);
+    } else {
+        double sin_t = sqrt(rmax(0.0, 1.0 - cos_t * cos_t));
+        double tan_t = sin_t / cos_t;
+        double a = 1.0 / tan_t;
+        double g1 = 2.0 / (1.0 + sqrt(1.0 + 1.0 / (a * a)));
+        a = 2.0 * u1 / g1 - 1.0;
+        double tmp = 1.0 / (a * a - 1.0);
+        if (tmp > 1e10) tmp = 1e10;
+        double b = tan_t;
+        double dd = sqrt(rmax(b * b * tmp * tmp - (a * a - b * b) * tmp, 0.0));
+        double sx1 = b * tmp - dd, sx2 = b * tmp + dd;
+        slope_x = (a < 0.0 || sx2 > 1.0 / tan_t) ? sx1 : sx2;
+        double s, nu2;
+        if (u2 > 0.5) {
+            s = 1.0;
+            nu2 = 2.0 * (u2 - 0.5);
+        } else {
+            s = -1.0;
+            nu2 = 2.0 * (0.5 - u2);
+        }
+        double z = (nu2 * (nu2 * (nu2 * 0.27385 - 0.73369) + 0.46341)) /
+                   (nu2 * (nu2 * (nu2 * 0.093073 + 0.309420) - 1.0) + 0.597999);
+        slope_y = s * z * sqrt(1.0 + slope_x * slope_x);
+    }
+    double tmp = cos_phi(ws) * slope_x - sin_phi(ws) * slope_y;
+    slope_y = sin_phi(ws) * slope_x + cos_phi(ws) * slope_y;
+    slope_x = tmp;
+    slope_x *= ax;
+    slope_y *= ay;
+    return normalize(v3(-slope_x, -slope_y, 1.0));
+}
+
+__device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+    switch (l.kind) {
+        case LOBE_LAMBERT: return l.r / kPi;
+        case LOBE_OREN_NAYAR: {  // reflection.rs:916-941
+            double sin_i = sin_theta(wi), sin_o = sin_theta(wo), max_cos = 0.0;
+            if (sin_i > 1e-4 && sin_o > 1e-4) {
+                double d_cos = cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo);
+                max_cos = rmax(d_cos, 0.0);
+            }
+            double sin_alpha, tan_beta;
+            if (abs_cos_theta(wi) > abs_cos_theta(wo)) {
+                sin_alpha = sin_o;
+                tan_beta = sin_i / abs_cos_theta(wi);
+            } else {
+                sin_alpha = sin_i;
+                tan_beta = sin_o / abs_cos_theta(wo);
+            }
+            return l.r / kPi * (l.eta_a + l.eta_b * max_cos * sin_alpha * tan_beta);
+        }
+        case LOBE_MICROFACET: {  // reflection.rs:970-990
+            double cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
+            V3 wh = wi + wo;
+            if (cos_i == 0.0 || cos_o == 0.0) return rgb(0.0);
+            if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return rgb(0.0);
+            wh = normalize(wh);
+            Rgb fr = lobe_fresnel(l, dot(wi, faceforward(wh, v3(0.0, 0.0, 1.0))));
+            double g = 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
+            return l.r * tr_d(l, wh) * g * fr / (4.0 * cos_i * cos_o);
+        }
+        default: return rgb(0.0);
+    }
+}
+__device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+    switch (l.kind) {
+        case LOBE_LAMBERT:
+        case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
+        case LOBE_MICROFACET: {
+            if (!same_hemisphere(wo, wi)) return 0.0;
+            V3 wh = normalize(wo + wi);
+            return tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
+        }
+        default: return 0.0;
+    }
+}
+// BxDF::sample_f of each lobe; *pdf is left untouched on the early-outs (the caller zeroed it)
+__device__ Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+    switch (l.kind) {
+        case LOBE_LAMBERT:
+        case LOBE_OREN_NAYAR: {  // reflection.rs:428-443
+            *wi = cosine_sample_hemisphere(u);
+            if (wo.z < 0.0) wi->z *= -1.0;
+            *pdf = lobe_pdf(l, wo, *wi);
+            return lobe_f(l, wo, *wi);
+        }
+        case LOBE_MICROFACET: {  // reflection.rs:991-1015
+            if (wo.z == 0.0) return rgb(0.0);
+            V3 wh = wo.z < 0.0 ? -tr_sample_visible(-wo, l.alpha_x, l.alpha_y, u.x, u.y)
+                               : tr_sample_visible(wo, l.alpha_x, l.alpha_y, u.x, u.y);
+            if (dot(wo, wh) < 0.0) return rgb(0.0);
+            *wi = reflect_about(wo, wh);
+            if (!same_hemisphere(wo, *wi)) return rgb(0.0);
+            *pdf = tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
+            return lobe_f(l, wo, *wi);
+        }
+        case LOBE_SPEC_REFL: {  // reflection.rs:638-649
+            *wi = v3(-wo.x, -wo.y, wo.z);
+            *pdf = 1.0;
+            return lobe_fresnel(l, wi->z) * l.r / abs_cos_theta(*wi);
+        }
+        case LOBE_SPEC_TRANS: {  // reflection.rs:686-714, TransportMode::Radiance
+            bool entering = wo.z > 0.0;
+            double ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
+            if (!refract_dir(wo, faceforward(v3(0.0, 0.0, 1.0), wo), ei / et, wi)) return rgb(0.0);
+            *pdf = 1.0;
+            Rgb ft = l.t * (rgb(1.0) - rgb(fr_dielectric(wi->z, l.eta_a, l.eta_b)));
+            ft = ft * ((ei * ei) / (et * et));
+            return ft / abs_cos_theta(*wi);
+        }
+        default: {  // FresnelSpecular, reflection.rs:751-797
+            double fr = fr_dielectric(wo.z, l.eta_a, l.eta_b);
+            if (u.x < fr) {
+                *wi = v3(-wo.x, -wo.y, wo.z);
+                *sampled_type = BXDF_SPECULAR | BXDF_REFLECTION;
+                *pdf = fr;
+                return l.r * fr / abs_cos_theta(*wi);
+            }
+            bool entering = wo.z > 0.0;
+            double ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
+            if (!refract_dir(wo, faceforward(v3(0.0, 0.0, 1.0), wo), ei / et, wi)) return rgb(0.0);
+            Rgb ft = l.t * (1.0 - fr);
+            ft = ft * ((ei * ei) / (et * et));
+            *sampled_type = BXDF_SPECULAR | BXDF_TRANSMISSION;
+            *pdf = 1.0 - fr;
+            return ft / abs_cos_theta(*wi);
+        }
+    }
+}
+
+// ---- Bsdf over at most two lobes (reflection.rs:205-404) --------------------------------------------------
+struct Bsdf {
+    V3 ns, ng, ss, ts;
+    double eta;
+    int n_lobes;
+    bool present;
+    Lobe lobes[2];
+};
+__device__ __forceinline__ V3 to_local(const Bsdf& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+__device__ __forceinline__ V3 to_world(const Bsdf& b, V3 v) {
+    return v3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
+              b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+__device__ int bsdf_num_components(const Bsdf& b, uint32_t flags) {
+    int n = 0;
+    for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches(b.lobes[i], flags) ? 1 : 0;
+    return n;
+}
+__device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    V3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
+    if (wo.z == 0.0) return rgb(0.0);
+    bool reflect = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0;
+    Rgb f = rgb(0.0);
+    for (int i = 0; i < b.n_lobes; ++i) {
+        const Lobe& l = b.lobes[i];
+        const uint32_t ty = lobe_type(l);
+        if (lobe_matches(l, flags) && ((reflect && (ty & BXDF_REFLECTION)) || (!reflect && (ty & BXDF_TRANSMISSION))))
+            f = f + lobe_f(l, wo, wi);
+    }
+    return f;
+}
+__device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+    const int matching = bsdf_num_components(b, flags);
+    if (matching == 0) {
+        *pdf = 0.0;
+        *sampled_type = 0;
+        return rgb(0.0);
+    }
+    uint64_t c64 = as_u64(floor(u.x * (double)matching));
+    int comp = c64 > (uint64_t)matching ? matching : (int)c64;
+    int count = comp, chosen = 0;
+    for (int i = 0; i < b.n_lobes; ++i)
+        if (lobe_matches(b.lobes[i], flags)) {
+            if (count == 0) {
+                chosen = i;
+                break;
+            }
+            count -= 1;
+        }
+    const Lobe& l = b.lobes[chosen];
+    P2 ur = {rmin(u.x * (double)matching - (double)comp, kOneMinusEps), u.y};
+    V3 wi = v3(0, 0, 0), wo = to_local(b, wo_w);
+    if (wo.z == 0.0) return rgb(0.0);  // NB: *pdf is not touched here either (reflection.rs:343-345)
+    *pdf = 0.0;
+    *sampled_type = lobe_type(l);
+    Rgb f = lobe_sample_f(l, wo, &wi, ur, pdf, sampled_type);
+    if (*pdf == 0.0) {
+        *sampled_type = 0;
+        return rgb(0.0);
+    }
+    *wi_w = to_world(b, wi);
+    if (!(lobe_type(l) & BXDF_REFLECTION) && matching > 1) {
+        for (int i = 0; i < b.n_lobes; ++i)
+            if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+    }
+    if (matching > 1) *pdf /= (double)matching;
+    return f;  // Q15: the multi-lobe re-evaluation is computed into a shadowed variable and dropped
+}
+
+// Material::compute_scattering_functions for constant-valued parameters
+__device__ void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
+    b->ns = s.shn;
+    b->ss = normalize(s.shdpdu);
+    b->ng = s.n;
+    b->ts = cross(b->ns, b->ss);
+    b->eta = 1.0;
+    b->n_lobes = 0;
+    b->present = true;
+    Lobe l;
+    l.fresnel = FRESNEL_NOOP;
+    l.r = rgb(0.0);
+    l.t = rgb(0.0);
+    l.cond_eta = rgb(0.0);
+    l.cond_k = rgb(0.0);
+    l.a = l.b = 1.0;
+    l.eta_a = l.eta_b = 1.0;
+    l.alpha_x = l.alpha_y = 0.0;
+    switch (m.kind) {
+        case 0: {  // MatteMaterial (matte.rs:36-61)
+            Rgb r = clamp_rgb(m.kd, 0.0, kInfD);
+            double sig = clampd(m.sigma, 0.0, 90.0);
+            if (!is_black(r)) {
+                l.r = r;
+                if (sig == 0.0) {
+                    l.kind = LOBE_LAMBERT;
+                } else {
+                    l.kind = LOBE_OREN_NAYAR;  // reflection.rs:906-912: A, B kept in eta_a / eta_b
+                    double sr = (kPi / 180.0) * sig;
+                    double sigma2 = sr * sr;
+                    l.eta_a = 1.0 - (sigma2 / (2.0 * (sigma2 + 0.33)));
+                    l.eta_b = 0.45 * sigma2 / (sigma2 + 0.09);
+                }
+                b->lobes[b->n_lobes++] = l;
+            }
+            return;
+        }
+        case 1: {  // PlasticMaterial (plastic.rs:42-73), Q16
+            Rgb kd = clamp_rgb(m.kd, 0.0, kInfD), ks = clamp_rgb(m.ks, 0.0, kInfD);
+            if (!is_black(kd)) {
+                l.kind = LOBE_LAMBERT;
+                l.r = kd;
+                b->lobes[b->n_lobes++] = l;
+                double rough = m.roughness;
+                if (m.remap_roughness) rough = roughness_to_alpha(rough);
+                l.kind = LOBE_MICROFACET;
+                l.r = ks;
+                l.alpha_x = l.alpha_y = rough;
+                l.fresnel = FRESNEL_DIELECTRIC;
+                l.a = 1.5;
+                l.b = 1.0;
+                b->lobes[b->n_lobes++] = l;
+            }
+            return;
+        }
+        case 2: {  // MetalMaterial (metal.rs:48-90)
+            double ur = m.u_roughness >= 0.0 ? m.u_roughness : m.roughness;
+            double vr = m.v_roughness >= 0.0 ? m.v_roughness : m.roughness;
+            if (m.remap_roughness) {
+                ur = roughness_to_alpha(ur);
+                vr = roughness_to_alpha(vr);
+            }
+            l.kind = LOBE_MICROFACET;
+            l.r = rgb(1.0);
+            l.alpha_x = ur;
+            l.alpha_y = vr;
+            l.fresnel = FRESNEL_CONDUCTOR;
+            l.cond_eta = m.metal_eta;
+            l.cond_k = m.metal_k;
+            b->lobes[b->n_lobes++] = l;
+            return;
+        }
+        case 3: {  // MirrorMaterial (mirror.rs:28-48)
+            Rgb r = clamp_rgb(m.kr, 0.0, kInfD);
+            if (!is_black(r)) {
+                l.kind = LOBE_SPEC_REFL;
+                l.r = r;
+                b->lobes[b->n_lobes++] = l;
+            }
+            return;
+        }
+        default: {  // GlassMaterial (glass.rs:52-113), smooth only
+            Rgb r = clamp_rgb(m.kr, 0.0, kInfD), t = clamp_rgb(m.kt, 0.0, kInfD);
+            b->eta = m.eta;
+            if (is_black(r) && is_black(t)) {
+                b->present = false;
+                return;
+            }
+            if (allow_multiple_lobes) {
+                l.kind = LOBE_FRESNEL_SPEC;
+                l.r = r;
+                l.t = t;
+                l.eta_a = 1.0;
+                l.eta_b = m.eta;
+                b->lobes[b->n_lobes++] = l;
+                return;
+            }
+            if (!is_black(r)) {
+                l.kind = LOBE_SPEC_REFL;
+                l.r = r;
+                l.fresnel = FRESNEL_DIELECTRIC;
+                l.a = 1.0;
+                l.b = m.eta;
+                b->lobes[b->n_lobes++] = l;
+            }
+            if (!is_black(t)) {
+                l.kind = LOBE_SPEC_TRANS;
+                l.fresnel = FRESNEL_NOOP;
+                l.r = rgb(0.0);
+                l.t = t;
+                l.eta_a = 1.0;
+                l.eta_b = m.eta;
+                b->lobes[b->n_lobes++] = l;
+            }
+            return;
+        }
+    }
+}
+
+}  // namespace rrt

@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference's render entry points over the C ABI.
+
+`Render.load(ctx, "scene.json")` is `deploy_render` (src/renderprocess.rs:92-105) up to the
+`Box<dyn Integrator>`; `.run()` is `Integrator::render` (src/integrator/mod.rs:21-23,48-139) for
+all tiles or for one rank's share; `.film()` is `Film::write_image` (src/film.rs:323-366) up to
+the float image.  Everything is computed by librrt_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import capi
+from .aggregate import Context, GpuAggregate
+
+
+class RenderDesc(C.Structure):
+    """rrt_render_desc (include/rrt.h)."""
+    _fields_ = [
+        ("xres", C.c_int64), ("yres", C.c_int64),
+        ("diagonal_mm", C.c_double), ("scale", C.c_double), ("max_sample_luminance", C.c_double),
+        ("filter_kind", C.c_uint32), ("pad0", C.c_uint32),
+        ("filter_radius", C.c_double * 2), ("filter_alpha", C.c_double),
+        ("cam_pos", C.c_double * 3), ("cam_look", C.c_double * 3), ("cam_up", C.c_double * 3),
+        ("shutter_open", C.c_double), ("shutter_close", C.c_double), ("aperture_diameter", C.c_double),
+        ("focus_distance", C.c_double),
+        ("simple_weighting", C.c_uint32), ("n_lens_values", C.c_uint32),
+        ("lens_data", C.POINTER(C.c_double)),
+        ("nsamp", C.c_uint64),
+        ("sample_at_center", C.c_uint32), ("pad1", C.c_uint32),
+        ("seed", C.c_uint64),
+        ("integrator_kind", C.c_uint32), ("max_depth", C.c_uint32),
+        ("rr_threshold", C.c_double),
+    ]
+
+
+class Material(C.Structure):
+    """rrt_material."""
+    _fields_ = [("kind", C.c_uint32), ("remap_roughness", C.c_uint32),
+                ("kd", C.c_double * 3), ("ks", C.c_double * 3), ("kr", C.c_double * 3), ("kt", C.c_double * 3),
+                ("metal_eta", C.c_double * 3), ("metal_k", C.c_double * 3),
+                ("sigma", C.c_double), ("roughness", C.c_double), ("u_roughness", C.c_double),
+                ("v_roughness", C.c_double), ("eta", C.c_double)]
+
+
+class Light(C.Structure):
+    """rrt_light."""
+    _fields_ = [("kind", C.c_uint32), ("pad", C.c_uint32), ("intensity", C.c_double * 3), ("dir", C.c_double * 3),
+                ("to_world", C.c_double * 16)]
+
+
+COPPER_N = (0.19998972096819712, 0.922085788777433, 1.0998762520488314)
+COPPER_K = (3.9046381767086675, 2.4476332238684626, 2.1376510366555137)
+
+
+def matte(kd=(0.5, 0.5, 0.5), sigma=0.0) -> Material:
+    return Material(kind=0, kd=tuple(kd), sigma=sigma, u_roughness=-1, v_roughness=-1)
+
+
+def plastic(kd=(0.25,) * 3, ks=(0.25,) * 3, roughness=0.1, remap=False) -> Material:
+    return Material(kind=1, remap_roughness=int(remap), kd=tuple(kd), ks=tuple(ks), roughness=roughness, u_roughness=-1,
+                    v_roughness=-1)
+
+
+def metal(eta=COPPER_N, k=COPPER_K, roughness=0.01, u_roughness=-1.0, v_roughness=-1.0, remap=False) -> Material:
+    return Material(kind=2, remap_roughness=int(remap), metal_eta=tuple(eta), metal_k=tuple(k), roughness=roughness,
+                    u_roughness=u_roughness, v_roughness=v_roughness)
+
+
+def mirror(kr=(0.9,) * 3) -> Material:
+    return Material(kind=3, kr=tuple(kr), u_roughness=-1, v_roughness=-1)
+
+
+def glass(kr=(1.0,) * 3, kt=(1.0,) * 3, eta=1.5) -> Material:
+    return Material(kind=4, kr=tuple(kr), kt=tuple(kt), eta=eta, u_roughness=0.0, v_roughness=0.0)
+
+
+def point_light(intensity=(1.0, 1.0, 1.0)) -> Light:
+    l = Light(kind=0, intensity=tuple(intensity))
+    l.to_world[:] = np.eye(4).reshape(16).tolist()
+    return l
+
+
+def distant_light(l=(1.0, 1.0, 1.0), frm=(0.0, 0.0, 0.0), to=(0.0, 0.0, 1.0), to_world=None) -> Light:
+    lt = Light(kind=1, intensity=tuple(l), dir=tuple(np.subtract(frm, to).tolist()))
+    lt.to_world[:] = (np.eye(4) if to_world is None else np.asarray(to_world)).reshape(16).tolist()
+    return lt
+
+
+def _bind(L):
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    pvp = C.POINTER(C.c_void_p)
+    L.rrt_scene_set_materials.restype = i32
+    L.rrt_scene_set_materials.argtypes = [vp, u32, vp]
+    L.rrt_scene_set_lights.restype = i32
+    L.rrt_scene_set_lights.argtypes = [vp, u32, vp]
+    L.rrt_scene_load_json.restype = i32
+    L.rrt_scene_load_json.argtypes = [vp, C.c_char_p, C.c_char_p, u64, pvp, pvp]
+    L.rrt_scene_json_probe.restype = i32
+    L.rrt_scene_json_probe.argtypes = [C.c_char_p, C.c_char_p, vp, C.POINTER(RenderDesc)]
+    L.rrt_render_create.restype = i32
+    L.rrt_render_create.argtypes = [vp, C.POINTER(RenderDesc), pvp]
+    L.rrt_render_destroy.restype = None
+    L.rrt_render_destroy.argtypes = [vp]
+    L.rrt_render_run.restype = i32
+    L.rrt_render_run.argtypes = [vp, u32, u32, vp]
+    L.rrt_render_clear.restype = i32
+    L.rrt_render_clear.argtypes = [vp]
+    L.rrt_render_read_film.restype = i32
+    L.rrt_render_read_film.argtypes = [vp, vp, vp]
+    L.rrt_render_film_device.restype = i32
+    L.rrt_render_film_device.argtypes = [vp, pvp, C.POINTER(u64)]
+    L.rrt_render_stats.restype = i32
+    L.rrt_render_stats.argtypes = [vp, vp]
+    L.rrt_render_hit_dump.restype = i32
+    L.rrt_render_hit_dump.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
+    return L
+
+
+def lib():
+    L = capi.lib()
+    if not getattr(L, "_render_bound", False):
+        _bind(L)
+        L._render_bound = True
+    return L
+
+
+def json_probe(path, overrides=None):
+    """What the C++ loader reads from a scene file (host only; no GPU needed)."""
+    L = lib()
+    out = np.zeros(8, dtype=np.uint64)
+    desc = RenderDesc()
+    ov = json.dumps(overrides).encode() if overrides else None
+    capi.check(L.rrt_scene_json_probe(str(path).encode(), ov, out.ctypes.data, C.byref(desc)))
+    keys = ["prims", "meshes", "spheres", "instances", "materials", "lights", "max_prims_in_node", "lens_values"]
+    return {k: int(v) for k, v in zip(keys, out)}, desc
+
+
+class Render:
+    """The GPU stand-in for `Box<dyn Integrator>` (+ its camera, film and sampler)."""
+
+    def __init__(self, ctx: Context, scene_handle, render_handle, owns_scene: bool, xres: int, yres: int, keep=None):
+        self.ctx, self.L = ctx, lib()
+        self.scene_h, self.h, self.owns_scene = scene_handle, render_handle, owns_scene
+        self.xres, self.yres = xres, yres
+        self._keep = keep
+
+    @classmethod
+    def load(cls, ctx: Context, path, overrides=None, seed: int = 1) -> "Render":
+        """`deploy_render(filepath, ..)` up to the integrator: make_scene + make_integrator."""
+        L = lib()
+        sh, rh = C.c_void_p(), C.c_void_p()
+        ov = json.dumps(overrides).encode() if overrides else None
+        capi.check(L.rrt_scene_load_json(ctx.h, str(path).encode(), ov, seed, C.byref(sh), C.byref(rh)))
+        _, desc = json_probe(path, overrides)
+        return cls(ctx, sh, rh, True, int(desc.xres), int(desc.yres))
+
+    @classmethod
+    def create(cls, agg: GpuAggregate, materials, lights, desc: RenderDesc, lens_data) -> "Render":
+        """make_integrator for an aggregate assembled through GpuAggregate."""
+        L = lib()
+        mats = (Material * len(materials))(*materials)
+        lts = (Light * max(1, len(lights)))(*lights)
+        capi.check(L.rrt_scene_set_materials(agg.h, len(materials), C.cast(mats, C.c_void_p)))
+        capi.check(L.rrt_scene_set_lights(agg.h, len(lights), C.cast(lts, C.c_void_p)))
+        lens = np.ascontiguousarray(lens_data, dtype=np.float64).reshape(-1)
+        desc.lens_data = lens.ctypes.data_as(C.POINTER(C.c_double))
+        desc.n_lens_values = lens.shape[0]
+        rh = C.c_void_p()
+        capi.check(L.rrt_render_create(agg.h, C.byref(desc), C.byref(rh)))
+        return cls(agg.ctx, agg.h, rh, False, int(desc.xres), int(desc.yres), keep=(agg, lens))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rrt_render_destroy(self.h)
+            self.h = None
+            if self.owns_scene and self.scene_h:
+                self.L.rrt_scene_destroy(self.scene_h)
+                self.scene_h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, tile_mod: int = 1, tile_rank: int = 0, crop=None):
+        """`Integrator::render` for the tiles t with t % tile_mod == tile_rank."""
+        c = None
+        if crop is not None:
+            c = (C.c_int64 * 4)(*[int(x) for x in crop])
+        capi.check(self.L.rrt_render_run(self.h, tile_mod, tile_rank, C.cast(c, C.c_void_p) if c is not None else None))
+
+    def clear(self):
+        capi.check(self.L.rrt_render_clear(self.h))
+
+    def film(self, want_raw: bool = False):
+        """`Film::write_image` up to the float RGB image [yres, xres, 3] (+ raw xyz/weight)."""
+        rgb = np.zeros((self.yres, self.xres, 3))
+        raw = np.zeros((self.yres, self.xres, 4)) if want_raw else None
+        capi.check(self.L.rrt_render_read_film(self.h, rgb.ctypes.data, raw.ctypes.data if want_raw else None))
+        return (rgb, raw) if want_raw else rgb
+
+    def film_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        capi.check(self.L.rrt_render_film_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def stats(self) -> dict:
+        out = np.zeros(16, dtype=np.uint64)
+        capi.check(self.L.rrt_render_stats(self.h, out.ctypes.data))
+        keys = ["camera_rays", "extension_rays", "shadow_rays", "bounces", "zero_weight", "samples", "launches",
+                "render_usec", "setup_usec", "chunks"]
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def enable_hit_dump(self, on: bool = True):
+        capi.check(self.L.rrt_render_hit_dump(self.h, int(on), None, 0, None))
+
+    def hit_dump(self) -> np.ndarray:
+        """(pixel x, pixel y, sample, prim id | -1 miss | -2 zero weight, t, weight) per camera sample."""
+        n = C.c_uint64()
+        capi.check(self.L.rrt_render_hit_dump(self.h, 1, None, 0, C.byref(n)))
+        out = np.zeros((max(1, n.value), 6))
+        capi.check(self.L.rrt_render_hit_dump(self.h, 1, out.ctypes.data, n.value, C.byref(n)))
+        out = out[: n.value]
+        out = out[~np.isnan(out[:, 0])]
+        order = np.lexsort((out[:, 2], out[:, 0], out[:, 1]))
+        return out[order]

@@ -158,3 +158,159 @@ CUBE_VI = np.array(
 )
 CUBE_N = np.array([[0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [1, 0, 0], [0, 0, -1]], dtype=np.float64)
 CUBE_NI = np.repeat(np.array([0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5], dtype=np.uint32)[:, None], 3, axis=1)
+
+
+# ---- scene.json writers (reference-compatible files for configs 1, 2 and 4) ------------------------
+# Lens prescription used by the reference's sample scene (a 13-interface double-Gauss design in
+# millimetres: curvature radius, thickness, index of refraction, aperture diameter per interface).
+DGAUSS_LENS = [
+    71.97476, 2.43276, 1.54, 47.432, 23.39436, 19.9914, 1, 35.992, 26.17428, 10.25244, 1.772, 24.728,
+    -45.26588, 3.53848, 1.617, 19.624, 142.11604, 1.6368, 1, 18.304, 0, 4.55532, 0, 17.512,
+    -19.17168, 4.86508, 1.617, 16.368, -22.57728, 0.23012, 1, 18.304, -333.553, 6.19212, 1.713, 21.296,
+    -15.1822, 2.65364, 1.805, 22.88, -33.5324, 7.96136, 1, 24.552, -15.40572, 2.43276, 1.617, 26.84,
+    -23.94656, 0, 1, 35.992,
+]
+
+
+def write_cube_obj(path):
+    """An 8-vertex, 12-triangle cube with per-face normals in the .obj dialect objparser.rs reads
+    (`v`, `vn`, `f v//vn`), matching CUBE_P / CUBE_VI / CUBE_N above."""
+    lines = ["o Cube"]
+    lines += ["v %.6f %.6f %.6f" % tuple(p) for p in CUBE_P]
+    lines += ["vn %.4f %.4f %.4f" % tuple(n) for n in CUBE_N]
+    for t in range(12):
+        lines.append("f " + " ".join("%d//%d" % (CUBE_VI[t, k] + 1, CUBE_NI[t, k] + 1) for k in range(3)))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def _const_rgb_texture(name, rgb):
+    """The reference-loadable way to give a material a constant colour: a BilerpTexture whose corners
+    agree (renderprocess.rs:437-447 reads v10 and v11 from key "v01" as well)."""
+    v = {"values": [float(rgb[0]), float(rgb[1]), float(rgb[2])]}
+    return {"texture_name": name, "texture_type": "BilerpTexture", "v00": v, "v01": v}
+
+
+def _const_float_texture(name, value):
+    return {"texture_name": name, "texture_type": "BilerpTexture", "v00": float(value), "v01": float(value)}
+
+
+def _camera(world_pos, look, up=(0.0, 1.0, 0.0), focus_distance=30.0, aperture_diameter=50.0):
+    return {"lens_data": DGAUSS_LENS, "focus_distance": focus_distance, "aperture_diameter": aperture_diameter,
+            "world_pos": list(world_pos), "look": list(look), "up": list(up)}
+
+
+def scene_c1(directory, xres=640, yres=360, nsamp=17, integrator="Path", max_depth=5):
+    """Config 1: the reference's sample scene (three instanced cubes, three point lights, the
+    double-Gauss camera at (0,15,-25) looking at (35,0,0), 20 mm film) with the reproducible
+    Halton sampler and the Path integrator.  Returns the scene.json path."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    write_cube_obj(os.path.join(directory, "cube.obj"))
+    cfg = {
+        "float_texture": [], "rgb_texture": [],
+        "materials": [{"material_type": "MetalMaterial", "material_name": "mat_metal"},
+                      {"material_type": "PlasticMaterial", "material_name": "mat_plastic"},
+                      {"material_type": "MatteMaterial", "material_name": "mat_matte"}],
+        "objs": [{"filename": "cube.obj", "obj_name": "cube_01"}],
+        "lights": [
+            {"light_type": "point", "world_pos": [25.66, 8.69, 4.0], "spectrum": {"values": [800, 800, 800]}},
+            {"light_type": "point", "world_pos": [25.66, 6.69, -4.0], "spectrum": {"values": [800, 0, 0]}},
+            {"light_type": "point", "world_pos": [30, -3.69, -6.0], "spectrum": {"values": [0, 1000, 1000]}}],
+        "infinite_lights": [],
+        "Aggregate": {"max_prims_in_node": 4, "primitives": [{
+            "primitive_type": "triangle", "material_name": "mat_matte", "obj_name": "cube_01",
+            "instances": [
+                {"world_pos": [35.2, 1.0, 2.8], "scale": [1, 1, 1], "rotation_axis": [1.0, 0.0, 0.0], "rotation_angle": 15},
+                {"world_pos": [35.2, -0.3, -2.4], "scale": [1, 1, 1], "rotation_axis": [0.0, 0.0, 1.0], "rotation_angle": 35},
+                {"world_pos": [35.2, -1.3, 0.4], "scale": [1, 1, 1], "rotation_axis": [0.0, 0.0, 1.0], "rotation_angle": 78}]}]},
+        "Integrator": {"integrator_type": integrator, "max_depth": max_depth, "rr_threshold": 1.0},
+        "Sampler": {"sampler_type": "HaltonSampler", "nsamp": nsamp},
+        "Film": {"xres": xres, "yres": yres, "diagonal": 20, "Filter": {}},
+        "Camera": _camera((0.0, 15, -25.0), (35, 0, 0)),
+    }
+    path = os.path.join(directory, "scene.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
+def scene_c2(directory, n_instances=10000, xres=1920, yres=1080, nsamp=2, extent=50.0, seed=SEED_C2_INSTANCES):
+    """Config 2: the cube instanced `n_instances` times (random position / axis / angle, unit scale),
+    Matte, one point light (which sits at the origin whatever its world_pos, Q17), DirectLighting
+    with max_depth 1, Halton nsamp 2 (= 1 rendered sample), camera at (0,0,-4*extent)."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    write_cube_obj(os.path.join(directory, "cube.obj"))
+    prm = instance_params(n_instances, extent, seed)
+    inst = [{"world_pos": prm["world_pos"][i].tolist(), "rotation_axis": prm["axis"][i].tolist(),
+             "rotation_angle": float(prm["angle"][i]), "scale": [1, 1, 1]} for i in range(n_instances)]
+    cfg = {
+        "materials": [{"material_type": "MatteMaterial", "material_name": "mat_matte"}],
+        "objs": [{"filename": "cube.obj", "obj_name": "cube_01"}],
+        "lights": [{"light_type": "point", "spectrum": {"values": [20000, 20000, 20000]}}],
+        "infinite_lights": [],
+        "Aggregate": {"max_prims_in_node": 4, "primitives": [
+            {"primitive_type": "triangle", "material_name": "mat_matte", "obj_name": "cube_01", "instances": inst}]},
+        "Integrator": {"integrator_type": "DirectLighting", "max_depth": 1, "light_strategy": "one"},
+        "Sampler": {"sampler_type": "HaltonSampler", "nsamp": nsamp},
+        "Film": {"xres": xres, "yres": yres, "diagonal": 35, "Filter": {}},
+        "Camera": _camera((0.0, 0.0, -4.0 * extent), (0.0, 0.0, 0.0), focus_distance=4.0 * extent),
+    }
+    path = os.path.join(directory, "scene.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f)
+    return path
+
+
+def scene_c4(directory, n_spheres=100000, xres=1920, yres=1080, nsamp=65, extent=50.0, seed=SEED_C4_SPHERES,
+             max_depth=5, extra_materials=False):
+    """Config 4: `n_spheres` unit-instanced spheres of radius 0.5 as 16 sphere entries (8 Plastic
+    presets, roughness 0.05-0.5; 8 Metal presets, copper, roughness 0.01-0.3) x instances[], one
+    distant and one point light, Path integrator.  `extra_materials` swaps two presets for Mirror and
+    Glass (test coverage of the specular lobes)."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    prm = instance_params(n_spheres, extent, seed, rotate=False)
+    ftex, rtex, mats = [], [], []
+    for k in range(8):
+        rough = 0.05 + (0.5 - 0.05) * k / 7.0
+        kd = [0.15 + 0.08 * k, 0.6 - 0.05 * k, 0.25 + 0.03 * k]
+        ftex.append(_const_float_texture(f"rough_p{k}", rough))
+        rtex.append(_const_rgb_texture(f"kd_p{k}", kd))
+        mats.append({"material_type": "PlasticMaterial", "material_name": f"plastic_{k}", "kd": f"kd_p{k}",
+                     "roughness": f"rough_p{k}"})
+    for k in range(8):
+        rough = 0.01 + (0.3 - 0.01) * k / 7.0
+        ftex.append(_const_float_texture(f"rough_m{k}", rough))
+        mats.append({"material_type": "MetalMaterial", "material_name": f"metal_{k}", "roughness": f"rough_m{k}"})
+    if extra_materials:
+        mats[7] = {"material_type": "MirrorMaterial", "material_name": "plastic_7"}
+        mats[15] = {"material_type": "GlassMaterial", "material_name": "metal_7"}
+        mats[3] = {"material_type": "MatteMaterial", "material_name": "plastic_3", "sigma": "rough_m7"}
+    names = [m["material_name"] for m in mats]
+    prims = []
+    per = (n_spheres + 15) // 16
+    for k in range(16):
+        sl = slice(k * per, min(n_spheres, (k + 1) * per))
+        inst = [{"world_pos": p.tolist()} for p in prm["world_pos"][sl]]
+        if inst:
+            prims.append({"primitive_type": "sphere", "radius": 0.5, "material_name": names[k], "instances": inst})
+    cfg = {
+        "float_texture": ftex, "rgb_texture": rtex, "materials": mats, "objs": [],
+        "lights": [{"light_type": "distant", "l": {"values": [3.0, 3.0, 3.0]}, "from": [0.3, 1.0, -0.5], "to": [0, 0, 0]},
+                   {"light_type": "point", "spectrum": {"values": [30000, 30000, 30000]}}],
+        "infinite_lights": [],
+        "Aggregate": {"max_prims_in_node": 4, "primitives": prims},
+        "Integrator": {"integrator_type": "Path", "max_depth": max_depth, "rr_threshold": 1.0},
+        "Sampler": {"sampler_type": "HaltonSampler", "nsamp": nsamp},
+        "Film": {"xres": xres, "yres": yres, "diagonal": 35, "Filter": {"filter_type": "BoxFilter", "radius": [0.5, 0.5]}},
+        "Camera": _camera((0.0, 0.0, -4.0 * extent), (0.0, 0.0, 0.0), focus_distance=4.0 * extent),
+    }
+    path = os.path.join(directory, "scene.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f)
+    return path

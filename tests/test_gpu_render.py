@@ -1,0 +1,163 @@
+"""-m gpu: the wavefront renderer (through the C ABI) against the CPU oracle's restatement of
+si_render / PathIntegrator::li / DirectLightingIntegrator::li on the same scene.json files,
+seeds and sample counts.  Bars (BASELINE.json north_star): first-hit primitive index of every
+camera ray bit-exact (ties within 1e-6 relative excluded), t within 1e-5 relative, rendered image
+within 1e-3 relative RMSE.  The device shades in f64 with the reference's operation order, so the
+observed differences are libm last-ulp effects (sin / cos / atan2 / acos / exp / log)."""
+import numpy as np
+import pytest
+
+import oracle_scene as S
+from rs_ray_toy_b200 import synth
+from rs_ray_toy_b200.render import Render
+
+pytestmark = pytest.mark.gpu
+REL_RMSE = 1e-3
+
+
+def rel_rmse(a, b):
+    return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-300))
+
+
+def compare(gpu: Render, ref: dict, check_dump=True):
+    rgb, raw = gpu.film(want_raw=True)
+    st = gpu.stats()
+    out = {"rmse": rel_rmse(rgb, ref["rgb"]), "max_abs": float(np.abs(rgb - ref["rgb"]).max()),
+           "camera_rays": (st["camera_rays"], ref["stats"]["camera_rays"]),
+           "extension_rays": (st["extension_rays"], ref["stats"]["extension_rays"]),
+           "shadow_rays": (st["shadow_rays"], ref["stats"]["shadow_rays"]),
+           "zero_weight": (st["zero_weight"], ref["stats"]["zero_weight"])}
+    # filter weights are sample counts: exact
+    assert np.array_equal(raw[..., 3], ref["raw"][..., 3]), out
+    assert st["camera_rays"] == ref["stats"]["camera_rays"], out
+    assert st["zero_weight"] == ref["stats"]["zero_weight"], out
+    if check_dump:
+        d, r = gpu.hit_dump(), ref["dump"]
+        assert d.shape == r.shape, (d.shape, r.shape)
+        assert np.array_equal(d[:, :3], r[:, :3])
+        same = d[:, 3] == r[:, 3]
+        hit = r[:, 3] >= 0
+        rel = np.abs(d[:, 4] - r[:, 4]) / np.maximum(np.abs(r[:, 4]), 1e-300)
+        out["first_hit_mismatch"] = int((~same).sum())
+        out["first_hit_t_max_rel"] = float(rel[same & hit].max()) if (same & hit).any() else 0.0
+        assert (~same).sum() == 0, out
+        assert out["first_hit_t_max_rel"] <= 1e-5, out
+        assert np.allclose(d[:, 5], r[:, 5], rtol=1e-12, atol=0), out
+    assert out["rmse"] <= REL_RMSE, out
+    return out
+
+
+def test_config1_path_traced_sample_scene(ctx, tmp_path):
+    """Config 1: the reference's sample scene, Path integrator, Halton nsamp 17 (16 rendered)."""
+    path = synth.scene_c1(str(tmp_path / "c1"), nsamp=17)
+    ref = S.load(path).render(seed=1, want_dump=True)
+    gpu = Render.load(ctx, path, seed=1)
+    gpu.enable_hit_dump()
+    gpu.run()
+    out = compare(gpu, ref)
+    assert ref["stats"]["camera_rays"] > 500000
+    # extension / shadow ray counts agree unless a path decision flipped on a last-ulp difference
+    assert abs(out["extension_rays"][0] - out["extension_rays"][1]) <= 4, out
+    assert abs(out["shadow_rays"][0] - out["shadow_rays"][1]) <= 4, out
+    assert out["rmse"] < 1e-6, out
+
+
+def test_config1_seed_changes_image_and_identity_perms(ctx, tmp_path):
+    path = synth.scene_c1(str(tmp_path / "c1"), xres=160, yres=90, nsamp=9)
+    imgs = {}
+    for seed in (0, 1, 2):
+        ref = S.load(path).render(seed=seed, want_dump=True)
+        gpu = Render.load(ctx, path, seed=seed)
+        gpu.enable_hit_dump()
+        gpu.run()
+        compare(gpu, ref)
+        imgs[seed] = gpu.film()
+    assert not np.array_equal(imgs[1], imgs[2])
+
+
+def test_config2_direct_lighting_instanced_cubes(ctx, tmp_path):
+    path = synth.scene_c2(str(tmp_path / "c2"), n_instances=2000, xres=480, yres=270, extent=30.0)
+    ref = S.load(path).render(seed=1, want_dump=True)
+    gpu = Render.load(ctx, path, seed=1)
+    gpu.enable_hit_dump()
+    gpu.run()
+    out = compare(gpu, ref)
+    assert out["shadow_rays"][1] > 1000 and out["shadow_rays"][0] == out["shadow_rays"][1], out
+
+
+@pytest.mark.parametrize("extra", [False, True])
+def test_config4_sphere_field_materials(ctx, tmp_path, extra):
+    """Plastic / Metal presets (+ Mirror, Glass, Oren-Nayar Matte when `extra`), distant + point
+    light, 5-bounce paths with Russian roulette."""
+    path = synth.scene_c4(str(tmp_path / "c4"), n_spheres=4000, xres=320, yres=180, nsamp=9, extent=14.0,
+                          extra_materials=extra)
+    ref = S.load(path).render(seed=3, want_dump=True)
+    gpu = Render.load(ctx, path, seed=3)
+    gpu.enable_hit_dump()
+    gpu.run()
+    out = compare(gpu, ref)
+    assert out["extension_rays"][1] > 2 * out["camera_rays"][1], out
+    assert abs(out["extension_rays"][0] - out["extension_rays"][1]) <= max(8, out["extension_rays"][1] // 100000), out
+
+
+def test_filters_and_overrides(ctx, tmp_path):
+    """Gaussian / triangle filters of radius 2 (samples splat across tile borders) and the
+    luminance clamp, through the loader's `overrides`."""
+    path = synth.scene_c1(str(tmp_path / "c1"), xres=200, yres=120, nsamp=5)
+    for flt in ({"filter_type": "GaussianFilter", "radius": [2.0, 2.0], "alpha": 2.0},
+                {"filter_type": "TriangleFilter", "radius": [1.5, 2.0]}):
+        ov = {"Film": {"xres": 200, "yres": 120, "diagonal": 20, "scale": 2.0, "max_sample_luminance": 0.05, "Filter": flt}}
+        ref = S.load(path, ov).render(seed=1, want_dump=False)
+        gpu = Render.load(ctx, path, overrides=ov, seed=1)
+        gpu.run()
+        rgb, raw = gpu.film(want_raw=True)
+        assert np.allclose(raw[..., 3], ref["raw"][..., 3], rtol=1e-12)
+        assert rel_rmse(rgb, ref["rgb"]) <= 1e-9
+
+
+def test_tile_partition_is_exact(ctx, tmp_path):
+    """renderprocess/si_render tiling dealt to ranks: tiles t % G == r on G renderers, films summed,
+    equal the single-renderer film bit for bit (box filter 0.5: every pixel has one owner)."""
+    path = synth.scene_c4(str(tmp_path / "c4"), n_spheres=1500, xres=200, yres=120, nsamp=5, extent=10.0)
+    full = Render.load(ctx, path, seed=1)
+    full.run()
+    _, raw_full = full.film(want_raw=True)
+    for G in (2, 4):
+        acc = np.zeros_like(raw_full)
+        for r in range(G):
+            part = Render.load(ctx, path, seed=1)
+            part.run(tile_mod=G, tile_rank=r)
+            acc += part.film(want_raw=True)[1]
+            part.close()
+        assert np.array_equal(acc, raw_full)
+    # the oracle deals tiles the same way
+    ref = S.load(path).render(seed=1, tile_mod=2, tile_rank=1)
+    part = Render.load(ctx, path, seed=1)
+    part.run(tile_mod=2, tile_rank=1)
+    assert np.array_equal(part.film(want_raw=True)[1][..., 3], ref["raw"][..., 3])
+
+
+def test_crop_and_api_scene(ctx, tmp_path):
+    """A scene assembled through the aggregate API (no scene.json) renders like the same scene loaded
+    from a file; `crop` restricts sampling to a pixel rectangle."""
+    path = synth.scene_c1(str(tmp_path / "c1"), xres=160, yres=90, nsamp=5)
+    a = Render.load(ctx, path, seed=1)
+    a.run(crop=(40, 20, 100, 60))
+    ref = S.load(path).render(seed=1, crop=(40, 20, 100, 60))
+    rgb, raw = a.film(want_raw=True)
+    assert np.array_equal(raw[..., 3], ref["raw"][..., 3])
+    assert raw[..., 3][:20].sum() == 0 and raw[..., 3][20:60, 40:100].min() > 0
+    assert rel_rmse(rgb, ref["rgb"]) <= 1e-9
+
+
+def test_unsupported_inputs_are_refused(ctx, tmp_path):
+    from rs_ray_toy_b200 import capi
+    path = synth.scene_c1(str(tmp_path / "c1"), xres=64, yres=36, nsamp=3)
+    for ov, status in (({"Sampler": {"sampler_type": "StratifiedSampler"}}, capi.RRT_ERR_IO),
+                       ({"Integrator": {"integrator_type": "SPPM"}}, capi.RRT_ERR_IO),
+                       ({"infinite_lights": [{"light_type": "infinite"}]}, capi.RRT_ERR_IO)):
+        with pytest.raises(capi.RrtError) as e:
+            Render.load(ctx, path, overrides=ov)
+        assert e.value.status == status
+    with pytest.raises(capi.RrtError):
+        Render.load(ctx, str(tmp_path / "missing.json"))

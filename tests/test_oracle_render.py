@@ -1,0 +1,136 @@
+"""CPU-only checks of the oracle's renderer restatement and of the product's host-side loader."""
+import numpy as np
+
+import oracle_lib as O
+import oracle_scene as S
+from rs_ray_toy_b200 import render, synth
+
+
+def test_radical_inverse_known_answers():
+    L = O.lib()
+    import ctypes as C
+    L.orc_radical_inverse.restype = C.c_double
+    L.orc_radical_inverse.argtypes = [C.c_int32, C.c_uint64]
+    # base 2: bit reversal; base 3: digit reversal (lowdiscrepancy.rs:188-236)
+    assert L.orc_radical_inverse(0, 1) == 0.5 and L.orc_radical_inverse(0, 2) == 0.25 and L.orc_radical_inverse(0, 3) == 0.75
+    assert abs(L.orc_radical_inverse(1, 1) - 1 / 3) < 1e-15 and abs(L.orc_radical_inverse(1, 5) - (2 / 3 + 1 / 9)) < 1e-15
+    assert abs(L.orc_radical_inverse(2, 7) - (2 / 5 + 1 / 25)) < 1e-15
+    L.orc_scrambled_radical_inverse.restype = C.c_double
+    L.orc_scrambled_radical_inverse.argtypes = [C.c_int32, C.c_uint64, C.c_uint64]
+    # identity permutations (seed 0): scrambled == plain for digits with perm[0] = 0
+    for a in (1, 17, 123456):
+        assert abs(L.orc_scrambled_radical_inverse(3, a, 0) - L.orc_radical_inverse(3, a)) < 1e-15
+
+
+def test_halton_pixel_index_quirks():
+    """halton.rs:23-105 at 640x360: scales 128 = 2^7 and 243 = 3^5, stride 31104; the pixel offset
+    of the base-2 term is reversed over base_exponents[1] = 5 digits (Q13), so two pixels that
+    differ only above bit 4 of x share their Halton indices."""
+    import ctypes as C
+    L = O.lib()
+    L.orc_halton_index.restype = C.c_uint64
+    L.orc_halton_index.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]
+    stride = C.c_uint64()
+    i0 = L.orc_halton_index(640, 360, 0, 0, 1, C.byref(stride))
+    assert stride.value == 128 * 243 and i0 == stride.value
+    a = L.orc_halton_index(640, 360, 3, 7, 2, None)
+    b = L.orc_halton_index(640, 360, 3 + 32, 7, 2, None)
+    assert a == b            # Q13
+    assert L.orc_halton_index(640, 360, 3 + 128, 7, 2, None) == a   # kMaxResolution wrap (halton.rs:82-85)
+    assert L.orc_halton_index(640, 360, 4, 7, 2, None) != a
+
+
+def test_seeded_permutations_are_permutations():
+    import ctypes as C
+    L = O.lib()
+    L.orc_halton_perms.argtypes = [C.c_uint64, C.c_void_p, C.c_uint32]
+    primes = [2, 3, 5, 7, 11, 13]
+    n = sum(primes)
+    for seed in (0, 1, 99):
+        buf = np.zeros(n, dtype=np.uint16)
+        L.orc_halton_perms(seed, buf.ctypes.data, n)
+        off = 0
+        for p in primes:
+            assert sorted(buf[off:off + p].tolist()) == list(range(p))
+            if seed == 0:
+                assert buf[off:off + p].tolist() == list(range(p))
+            off += p
+
+
+def _probe(mat_row, wo, wi, u, allow=True):
+    import ctypes as C
+    L = O.lib()
+    pd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    L.orc_bsdf_probe.argtypes = [pd, pd, pd, pd, C.c_int32, pd]
+    out = np.zeros(12)
+    L.orc_bsdf_probe(np.ascontiguousarray(mat_row, dtype=np.float64), np.array(wo, dtype=np.float64),
+                     np.array(wi, dtype=np.float64), np.array(u, dtype=np.float64), int(allow), out)
+    return out
+
+
+def test_bsdf_known_answers():
+    tex = S.Textures({})
+    wo = np.array([0.3, 0.2, np.sqrt(1 - 0.13)])
+    wi = np.array([-0.5, 0.1, np.sqrt(1 - 0.26)])
+    # Matte kd=0.5: f = kd / pi, pdf = cos / pi (reflection.rs:807-840, :480-486)
+    out = _probe(S.material_row({"material_type": "MatteMaterial"}, tex), wo, wi, (0.3, 0.6))
+    assert np.allclose(out[:3], 0.5 / np.pi) and np.isclose(out[3], wi[2] / np.pi)
+    assert np.isclose(out[10], out[9] / np.pi) and out[11] == 5       # sampled: DIFFUSE | REFLECTION
+    # Mirror: specular reflection of wo about +z, f = kr / |cos|, pdf 1 (reflection.rs:638-649)
+    out = _probe(S.material_row({"material_type": "MirrorMaterial"}, tex), wo, wi, (0.3, 0.6))
+    assert np.allclose(out[:4], 0.0) and np.allclose(out[7:10], [-wo[0], -wo[1], wo[2]]) and out[10] == 1.0
+    assert np.allclose(out[4:7], 0.9 / wo[2]) and out[11] == 17
+    # Plastic (Q15): two reflective lobes -> pdf of the chosen lobe / 2; u0 < 0.5 picks the Lambertian
+    out = _probe(S.material_row({"material_type": "PlasticMaterial"}, tex), wo, wi, (0.25, 0.6))
+    assert np.isclose(out[10], out[9] / np.pi / 2.0) and np.allclose(out[4:7], 0.25 / np.pi)
+    out2 = _probe(S.material_row({"material_type": "PlasticMaterial"}, tex), wo, wi, (0.75, 0.6))
+    assert out2[11] == 9 and out2[10] > 0                             # GLOSSY | REFLECTION
+    # Glass with multiple lobes allowed: FresnelSpecular, type SPECULAR|ALL; f(wo,wi) == 0
+    out = _probe(S.material_row({"material_type": "GlassMaterial"}, tex), wo, wi, (0.9, 0.6))
+    assert np.allclose(out[:4], 0.0) and out[11] == 18 and out[9] < 0  # transmitted below the surface
+    # energy: Lambert sample weight f * cos / pdf == kd
+    out = _probe(S.material_row({"material_type": "MatteMaterial"}, tex), wo, wi, (0.11, 0.83))
+    assert np.allclose(out[4:7] * out[9] / out[10], 0.5)
+
+
+def test_film_weights_and_q10_q14(tmp_path):
+    """nsamp = N renders N-1 samples (Q10); every sample, vignetted or not, adds its filter weight
+    three times (Q14); a box filter of radius 0.5 puts each sample in its own pixel."""
+    path = synth.scene_c1(str(tmp_path / "c1"), xres=64, yres=36, nsamp=4)
+    r = S.load(path).render(seed=1, want_dump=True)
+    assert r["dump"].shape[0] == 64 * 36 * 3
+    assert np.array_equal(r["raw"][..., 3], np.full((36, 64), 9.0))
+    assert r["stats"]["camera_rays"] + r["stats"]["zero_weight"] == 64 * 36 * 3
+    r1 = S.load(path, {"Sampler": {"sampler_type": "HaltonSampler", "nsamp": 1}}).render(seed=1)
+    assert r1["raw"].sum() == 0.0                                       # nsamp = 1 renders nothing
+
+
+def test_oracle_render_is_deterministic_and_thread_independent(tmp_path):
+    path = synth.scene_c4(str(tmp_path / "c4"), n_spheres=300, xres=64, yres=36, nsamp=5, extent=6.0)
+    a = S.load(path).render(seed=5, nthreads=1)
+    b = S.load(path).render(seed=5, nthreads=4)
+    assert np.array_equal(a["rgb"], b["rgb"]) and a["stats"] == b["stats"]
+    halves = [S.load(path).render(seed=5, tile_mod=2, tile_rank=r)["raw"] for r in (0, 1)]
+    assert np.array_equal(halves[0] + halves[1], a["raw"])
+
+
+def test_product_loader_matches_oracle_loader(tmp_path):
+    """The C++ loader (rrt_scene_json_probe, host only) and the Python restatement read the same
+    counts and the same render description from the same files."""
+    for path in (synth.scene_c1(str(tmp_path / "c1"), nsamp=7),
+                 synth.scene_c2(str(tmp_path / "c2"), n_instances=50, xres=80, yres=60),
+                 synth.scene_c4(str(tmp_path / "c4"), n_spheres=200, xres=80, yres=60, nsamp=3, extra_materials=True)):
+        info, d = render.json_probe(path)
+        ls = S.load(path)
+        prm, lens = S.render_params(ls.cfg)
+        assert info["prims"] == ls.scene.num_prims
+        assert info["materials"] == ls.materials.shape[0] and info["lights"] == ls.lights.shape[0]
+        assert info["lens_values"] == lens.shape[0]
+        assert (d.xres, d.yres, d.diagonal_mm, d.filter_kind) == (prm[0], prm[1], prm[2], prm[3])
+        assert list(d.filter_radius) == [prm[4], prm[5]] and d.scale == prm[7]
+        assert list(d.cam_pos) == list(prm[9:12]) and list(d.cam_look) == list(prm[12:15]) and list(d.cam_up) == list(prm[15:18])
+        assert (d.aperture_diameter, d.focus_distance, d.nsamp) == (prm[20], prm[21], prm[23])
+        assert (d.integrator_kind, d.max_depth, d.rr_threshold) == (prm[26], prm[27], prm[28])
+    ov = {"Integrator": {"integrator_type": "Path", "max_depth": 3, "rr_threshold": 0.5}}
+    _, d = render.json_probe(synth.scene_c2(str(tmp_path / "c2b"), n_instances=10, xres=32, yres=32), ov)
+    assert (d.integrator_kind, d.max_depth, d.rr_threshold) == (0, 3, 0.5)
