@@ -206,6 +206,10 @@ int rrt_render_read_film(rrt_render* render, double* rgb, double* raw);
 /* Device pointer to the accumulation film (4 f64 per pixel: RGB contribution sum, filter weight sum)
  * for a multi-GPU gather/reduce; *n_doubles = 4 * xres * yres.                                   */
 int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_doubles);
+/* Copies the accumulation film to (to_render = 0) or from (to_render = 1) a caller-owned DEVICE
+ * buffer of n_doubles f64 on `cuda_stream` — the hand-off to a collective that sums ranks' films
+ * (merge_film_tile across ranks, film.rs:248-263).                                              */
+int rrt_render_film_copy(rrt_render* render, void* d_buffer, int to_render, void* cuda_stream);
 /* out16: camera rays, extension rays, shadow rays, bounces, zero-weight samples, samples, kernels
  * launched, render microseconds, ...                                                            */
 int rrt_render_stats(const rrt_render* render, uint64_t out16[16]);

@@ -483,6 +483,12 @@ int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_double
     *n_doubles = render->renderer.film_doubles();
     return RRT_OK;
 }
+int rrt_render_film_copy(rrt_render* render, void* d_buffer, int to_render, void* cuda_stream) {
+    if (!render || !d_buffer) return fail(RRT_ERR_INVALID, "rrt_render_film_copy: null argument");
+    std::string err;
+    int rc = render->renderer.copy_film_device(d_buffer, to_render != 0, cuda_stream, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
 int rrt_render_stats(const rrt_render* render, uint64_t out16[16]) {
     if (!render || !out16) return fail(RRT_ERR_INVALID, "rrt_render_stats: null argument");
     const rrt::RenderStats& s = render->renderer.stats();

@@ -1024,10 +1024,11 @@ int Renderer::read_film(double* rgb_out, double* raw, std::string* err) {
     return RRT_OK;
 }
 
-int Renderer::copy_film_device(void* dst, void* stream, std::string* err) {
-    if (!impl_ || !dst) return RRT_ERR_INVALID;
-    RND_CUDA(cudaMemcpyAsync(dst, d_film_, film_doubles() * sizeof(double), cudaMemcpyDeviceToDevice,
-                             static_cast<cudaStream_t>(stream)));
+int Renderer::copy_film_device(void* buffer, bool to_render, void* stream, std::string* err) {
+    if (!impl_ || !buffer) return RRT_ERR_INVALID;
+    RND_CUDA(cudaSetDevice(impl_->device));
+    RND_CUDA(cudaMemcpyAsync(to_render ? d_film_ : buffer, to_render ? buffer : d_film_, film_doubles() * sizeof(double),
+                             cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return RRT_OK;
 }
 

@@ -33,7 +33,7 @@ class Renderer {
     int run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, std::string* err);
     int clear(std::string* err);
     int read_film(double* rgb, double* raw, std::string* err);
-    int copy_film_device(void* dst, void* stream, std::string* err);
+    int copy_film_device(void* buffer, bool to_render, void* stream, std::string* err);
     void* film_device() const { return d_film_; }
     uint64_t film_doubles() const { return 4ull * (uint64_t)xres_ * (uint64_t)yres_; }
     int hit_dump(int enable, double* out, uint64_t capacity, uint64_t* count, std::string* err);

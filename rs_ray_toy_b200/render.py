@@ -112,6 +112,8 @@ def _bind(L):
     L.rrt_render_read_film.argtypes = [vp, vp, vp]
     L.rrt_render_film_device.restype = i32
     L.rrt_render_film_device.argtypes = [vp, pvp, C.POINTER(u64)]
+    L.rrt_render_film_copy.restype = i32
+    L.rrt_render_film_copy.argtypes = [vp, vp, i32, vp]
     L.rrt_render_stats.restype = i32
     L.rrt_render_stats.argtypes = [vp, vp]
     L.rrt_render_hit_dump.restype = i32
@@ -207,6 +209,10 @@ class Render:
         p, n = C.c_void_p(), C.c_uint64()
         capi.check(self.L.rrt_render_film_device(self.h, C.byref(p), C.byref(n)))
         return p.value, int(n.value)
+
+    def film_copy(self, d_buffer: int, to_render: bool, stream: int = 0):
+        """Accumulation film -> device buffer (to_render False) or back (True); 4*xres*yres f64."""
+        capi.check(self.L.rrt_render_film_copy(self.h, C.c_void_p(d_buffer), int(to_render), C.c_void_p(stream)))
 
     def stats(self) -> dict:
         out = np.zeros(16, dtype=np.uint64)

@@ -314,3 +314,49 @@ def scene_c4(directory, n_spheres=100000, xres=1920, yres=1080, nsamp=65, extent
     with open(path, "w") as f:
         json.dump(cfg, f)
     return path
+
+
+def default_render_desc(xres, yres, nsamp, cam_pos, cam_look, cam_up=(0.0, 1.0, 0.0), focus_distance=30.0,
+                        aperture_diameter=50.0, diagonal_mm=35.0, integrator="Path", max_depth=5, seed=1):
+    """An rrt_render_desc with the loader's defaults (renderprocess.rs:1306-1499) for scenes that are
+    assembled through the aggregate API instead of a scene.json (configs 3 and 5: millions of
+    triangles do not belong in a text file)."""
+    from .render import RenderDesc
+    d = RenderDesc()
+    d.xres, d.yres = xres, yres
+    d.diagonal_mm, d.scale, d.max_sample_luminance = diagonal_mm, 1.0, float("inf")
+    d.filter_kind = 0
+    d.filter_radius[:] = [0.5, 0.5]
+    d.filter_alpha = 2.0
+    d.cam_pos[:] = list(cam_pos)
+    d.cam_look[:] = list(cam_look)
+    d.cam_up[:] = list(cam_up)
+    d.shutter_open, d.shutter_close = 0.0, 1.0
+    d.aperture_diameter, d.focus_distance = aperture_diameter, focus_distance
+    d.simple_weighting = 1
+    d.nsamp, d.sample_at_center, d.seed = nsamp, 0, seed
+    d.integrator_kind = 0 if integrator == "Path" else 1
+    d.max_depth, d.rr_threshold = max_depth, 1.0
+    return d
+
+
+def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=257, seed=SEED_C5_SOUP, max_depth=5):
+    """Config 5: a `n_tris` random-soup mesh (half Matte, half Plastic), one point light at the origin
+    (Q17) and one distant light, camera outside the unit cube looking at its centre.  Returns
+    (aggregate, Render)."""
+    from .aggregate import GpuAggregate
+    from .render import Render, distant_light, matte, plastic, point_light
+    p, idx = soup_triangles(n_tris, edge, seed)
+    half = n_tris // 2
+    agg = GpuAggregate(ctx)
+    m0 = agg.add_mesh(p[: 3 * half], idx[:half])
+    m1 = agg.add_mesh(p[3 * half:], idx[half:] - 3 * half)
+    agg.add_triangles(m0, 0)
+    agg.add_triangles(m1, 1)
+    agg.commit(4)
+    desc = default_render_desc(xres, yres, nsamp, cam_pos=(0.5, 0.5, -2.5), cam_look=(0.5, 0.5, 0.5), focus_distance=3.0,
+                               max_depth=max_depth, seed=1)
+    r = Render.create(agg, [matte((0.6, 0.55, 0.5)), plastic((0.3, 0.4, 0.6), (0.3, 0.3, 0.3), 0.15)],
+                      [point_light((4.0, 4.0, 4.0)), distant_light((2.0, 2.0, 2.0), frm=(0.3, 1.0, -0.6), to=(0, 0, 0))],
+                      desc, DGAUSS_LENS)
+    return agg, r
