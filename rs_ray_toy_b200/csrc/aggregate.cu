@@ -164,7 +164,7 @@ __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a
 
 // Brings a ray whose origin lies far outside the world box close to it (in f64), so that the
 // fp32 traversal copy keeps |o| comparable to the scene and the host-side box widening holds.
-__device__ __forceinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_max, float* t_shift, RayF* rf) {
+__device__ __noinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_max, float* t_shift, RayF* rf) {
     double ts = 0.0;
     bool outside = o.x < A.world_lo[0] || o.x > A.world_hi[0] || o.y < A.world_lo[1] || o.y > A.world_hi[1] ||
                    o.z < A.world_lo[2] || o.z > A.world_hi[2];
@@ -268,10 +268,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_MINBLOCKS 7
 #endif
 constexpr int kRefill = RRT_REFILL;
-#ifndef RRT_SSTACK
-#define RRT_SSTACK 16
-#endif
-constexpr int kSmemStack = RRT_SSTACK;
+
 
 template <bool ANY, bool WIDE>
 __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
@@ -286,28 +283,13 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
     const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
     const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
 
-    // Traversal stack: the first kSmemStack levels live in shared memory, laid out [level][thread]
-    // so that 32 lanes at 32 different depths still hit 32 different banks (one wavefront per
-    // push/pop); deeper levels spill to a per-thread local array.
-    __shared__ int32_t sstack[kSmemStack * kBlock];
-    int32_t lstack[kStack - kSmemStack];
+    // Traversal stack: entirely in shared memory, laid out [level][thread] so that 32 lanes at 32
+    // different depths still hit 32 different banks (one wavefront per push / pop).  Level 0 holds
+    // the "stack empty" marker, so a pop never needs an underflow test.  The launch sizes it from
+    // the tree depth (stack_levels * kBlock * 4 bytes of dynamic shared memory).
+    extern __shared__ int32_t sstack[];
     int32_t* const my_stack = sstack + threadIdx.x;
-#define RRT_PUSH(v)                                            \
-    do {                                                       \
-        if (sp < kSmemStack) my_stack[sp * kBlock] = (v);      \
-        else lstack[sp - kSmemStack] = (v);                    \
-        ++sp;                                                  \
-    } while (0)
-#define RRT_POP(dst)                                                                     \
-    do {                                                                                 \
-        if (sp > 0) {                                                                    \
-            --sp;                                                                        \
-            (dst) = sp < kSmemStack ? my_stack[sp * kBlock] : lstack[sp - kSmemStack];   \
-        } else {                                                                         \
-            (dst) = kDone;                                                               \
-        }                                                                                \
-    } while (0)
-    int sp = 0;
+    int sp = 1;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
     int32_t leaf = kNoLeaf;   // parked leaf reference
     bool have_ray = false;
@@ -360,7 +342,8 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                     best_id = RRT_NO_HIT;
                     found = false;
                     have_ray = true;
-                    sp = 0;
+                    sp = 1;
+                    my_stack[0] = kDone;
                     leaf = kNoLeaf;
                     const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
                     node = live ? A.root : kDone;
@@ -384,21 +367,23 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                 float tn0, tn1;
                 const bool h0 = slab(rf, lo.a, lo.b, lo.c, lo.d, hi.a, hi.b, tcull, &tn0);
                 const bool h1 = slab(rf, lo.e, lo.f, lo.g, lo.h, hi.c, hi.d, tcull, &tn1);
-                if (h0 && h1) {
-                    const bool swap = !ANY && (tn1 < tn0);
-                    RRT_PUSH(swap ? ch_x : ch_y);
-                    node = swap ? ch_y : ch_x;
-                } else if (h0) {
-                    node = ch_x;
-                } else if (h1) {
-                    node = ch_y;
-                } else {
-                    RRT_POP(node);
+                // branch-free step: both hit -> push the far child, go near; one hit -> go there;
+                // none -> pop
+                const bool both = h0 && h1;
+                const bool swap = !ANY && (tn1 < tn0);
+                const int32_t near_c = swap ? ch_y : ch_x, far_c = swap ? ch_x : ch_y;
+                if (both) my_stack[sp * kBlock] = far_c;
+                sp += both ? 1 : 0;
+                node = both ? near_c : (h0 ? ch_x : ch_y);
+                if (!(h0 || h1)) {
+                    --sp;
+                    node = my_stack[sp * kBlock];
                 }
             }
             if (node < 0 && leaf == kNoLeaf) {  // park the first leaf, keep walking
                 leaf = node;
-                RRT_POP(node);
+                --sp;
+                node = my_stack[sp * kBlock];
             }
             // leave when no lane is still looking for its first leaf
             if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
@@ -437,10 +422,10 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                 leaf = kNoLeaf;
                 if (ANY && found) {
                     node = kDone;
-                    sp = 0;
                 } else if (node < 0) {  // the walk had already reached another leaf
                     leaf = node;
-                    RRT_POP(node);
+                    --sp;
+                    node = my_stack[sp * kBlock];
                 }
             }
         }
@@ -468,7 +453,7 @@ __device__ __forceinline__ uint32_t spread3(uint32_t x) {  // 10 bits -> every t
     return x;
 }
 
-__device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r) {
+__device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r, int bits) {
     const double2* rp = reinterpret_cast<const double2*>(r);
     const double2 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
     const double o[3] = {q0.x, q0.y, q1.x};
@@ -480,24 +465,24 @@ __device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r) 
         double f = ext > 0.0 ? (o[k] - A.world_lo[k]) / ext : 0.0;
         f = f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f);
         if (!(f == f)) f = 0.0;
-        uint32_t q = (uint32_t)(f * (double)(1u << kSortBits));
-        c[k] = q >= (1u << kSortBits) ? (1u << kSortBits) - 1u : q;
+        uint32_t q = (uint32_t)(f * (double)(1u << bits));
+        c[k] = q >= (1u << bits) ? (1u << bits) - 1u : q;
     }
     const uint32_t cell = spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2);
     const uint32_t oct = (dd[0] < 0.0 ? 1u : 0u) | (dd[1] < 0.0 ? 2u : 0u) | (dd[2] < 0.0 ? 4u : 0u);
     if (A.sort_mode == 0) return cell;
-    if (A.sort_mode == 2) return (oct << (3 * kSortBits)) | cell;
+    if (A.sort_mode == 2) return (oct << (3 * bits)) | cell;
     return (cell << 3) | oct;
 }
 
 __global__ void __launch_bounds__(256) sort_count_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
                                                           uint32_t* __restrict__ bins, uint32_t* __restrict__ key_out,
                                                           uint32_t* __restrict__ rank_out,
-                                                          const uint32_t* __restrict__ n_dev) {
+                                                          const uint32_t* __restrict__ n_dev, int bits) {
     if (n_dev) n = *n_dev;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
-    const uint32_t key = valid ? ray_key(A, rays + i) : 0xFFFFFFFFu;
+    const uint32_t key = valid ? ray_key(A, rays + i, bits) : 0xFFFFFFFFu;
     // one atomic per distinct key per warp
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const unsigned lane = threadIdx.x & 31u;
@@ -719,7 +704,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
     build_sah(boxes, sp, &tree);
     if (tree.max_depth + 2 > (uint32_t)kStack) {
-        if (err) *err = "tree deeper than the traversal stack (" + std::to_string(tree.max_depth) + ")";
+        if (err) *err = "tree deeper than the traversal stack (" + std::to_string(tree.max_depth) + " levels)";
         return RRT_ERR_UNSUPPORTED;
     }
     const Aabb world_box = tree.nodes[tree.root].box;
@@ -886,13 +871,17 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     stats_.build_usec =
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
     // L1-heavy kernels: no shared memory is used, give the whole carve-out to L1.
-    // the only shared memory is the short stack; everything else of the 256 KB stays L1
-    int carve = (int)((RRT_MINBLOCKS * kSmemStack * kBlock * 4 * 100 + 227 * 1024 - 1) / (227 * 1024)) + 4;
+    // the only shared memory is the traversal stack (one entry per tree level + the marker);
+    // everything else of the 256 KB stays L1
+    stack_levels_ = (int)tree.max_depth + 2;
+    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t);
+    int carve = (int)((RRT_MINBLOCKS * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
-    cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(trace_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(trace_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    for (auto fn : {(const void*)trace_kernel<false, false>, (const void*)trace_kernel<false, true>,
+                    (const void*)trace_kernel<true, false>, (const void*)trace_kernel<true, true>}) {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     return RRT_OK;
 }
 
@@ -942,23 +931,28 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     const bool sorting = sort_rays_ && n >= 4096;
     int count = 0;
     if (sorting) {
-        RRT_CUDA(cudaMemsetAsync(w.d_bins, 0, (size_t)kSortBins * sizeof(uint32_t), s));
+        // about one ray per cell: 7 bits per axis for >= 1 Mi rays, fewer for short queues
+        int bits = kSortBits;
+        while (bits > 4 && (1ull << (3 * bits)) > 2 * n) --bits;
+        const uint32_t nbins = (1u << (3 * bits)) * (view_.sort_mode == 0 ? 1u : 8u);
+        RRT_CUDA(cudaMemsetAsync(w.d_bins, 0, (size_t)nbins * sizeof(uint32_t), s));
         const unsigned sb = (unsigned)((n + 255) / 256);
-        sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank, n_dev);
-        scan_block_kernel<<<kSortBins / kScanBlock, kScanBlock, 0, s>>>(w.d_bins, kSortBins, w.d_block_sums, small + 2);
-        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, kSortBins / kScanBlock, small + 2, n, small + 3, n_dev);
+        sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank, n_dev, bits);
+        scan_block_kernel<<<nbins / kScanBlock, kScanBlock, 0, s>>>(w.d_bins, nbins, w.d_block_sums, small + 2);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, nbins / kScanBlock, small + 2, n, small + 3, n_dev);
         sort_scatter_kernel<<<sb, 256, 0, s>>>(n, w.d_bins, w.d_block_sums, w.d_key, w.d_rank, small + 3, w.d_perm,
                                                n_dev);
         count += 4;
     }
     auto kernel = view_.wide ? trace_kernel<ANY, true> : trace_kernel<ANY, false>;
+    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t);
     int per_sm = 0;
-    RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+    RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t blocks = (uint64_t)w.n_sms * (uint64_t)per_sm;
     const uint64_t needed = (n + kBlock - 1) / kBlock;
     if (blocks > needed) blocks = needed;
-    kernel<<<(unsigned)blocks, kBlock, 0, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
+    kernel<<<(unsigned)blocks, kBlock, smem, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
                                                sorting ? small + 3 : nullptr,
                                                reinterpret_cast<unsigned long long*>(small), n_dev);
     count += 1;

@@ -75,6 +75,7 @@ class DeviceAggregate {
     mutable Workspace ws_;
     mutable std::mutex ws_mutex_;
     bool sort_rays_ = true;
+    int stack_levels_ = 2;
     AggView view_{};
     AggregateStats stats_{};
     void* d_nodes_ = nullptr;

@@ -245,6 +245,12 @@ def scene_c2(directory, n_instances=10000, xres=1920, yres=1080, nsamp=2, extent
     os.makedirs(directory, exist_ok=True)
     write_cube_obj(os.path.join(directory, "cube.obj"))
     prm = instance_params(n_instances, extent, seed)
+    # the point light sits at the origin (Q17): keep it out of the cubes (half-diagonal 1.74) by
+    # moving any instance centre closer than 3 units radially out to 3
+    pos = prm["world_pos"]
+    r = np.linalg.norm(pos, axis=1)
+    near = r < 3.0
+    pos[near] = (pos[near] / np.maximum(r[near], 1e-9)[:, None] * 3.0).astype(np.float32).astype(np.float64)
     inst = [{"world_pos": prm["world_pos"][i].tolist(), "rotation_axis": prm["axis"][i].tolist(),
              "rotation_angle": float(prm["angle"][i]), "scale": [1, 1, 1]} for i in range(n_instances)]
     cfg = {
