@@ -184,6 +184,112 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+PT_CONFIGS = {
+    "c4": "config 4: 100,000 spheres r=0.5 (16 sphere entries: 8 Plastic rough 0.05-0.5, 8 Metal copper rough 0.01-0.3, "
+          "x 6,250 instances, centres U[-50,50]^3 seed 5), 1 distant + 1 point light, Path max_depth 5 rr_threshold 1, "
+          "Halton nsamp 65 (64 rendered, Q10), 1920x1080, box filter 0.5, double-Gauss lens camera",
+    "c5": "config 5: 4,194,304-triangle random soup (edge 0.006, seed 6; half Matte, half Plastic), 1 point + 1 distant "
+          "light, Path max_depth 5, Halton nsamp 257 (256 rendered), 3840x2160, box filter 0.5, double-Gauss lens camera",
+}
+
+
+def path_traced(args, ctx, rank, world, local_rank, barrier):
+    """Second half of BASELINE.json's metric: one path-traced frame, its 16x16 sample tiles dealt
+    t % world == rank over the ranks (scene replicated), films summed onto rank 0 over NCCL.
+    Strong scaling: the frame is fixed, value = camera samples of the whole frame / max-over-ranks time."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from rs_ray_toy_b200 import parallel, synth
+    from rs_ray_toy_b200.render import Render
+    t_setup = time.perf_counter()
+    if args.path_config == "c4":
+        d = tempfile.mkdtemp(prefix=f"rrt_c4_{rank}_")
+        path = synth.scene_c4(d)
+        r = Render.load(ctx, path, seed=1)
+        keep = None
+    else:
+        keep, r = synth.scene_c5_api(ctx)
+    setup_s = time.perf_counter() - t_setup
+    frames = max(1, min(args.steps, 3))
+    launches0 = ctx.launch_count
+
+    def frame():
+        r.clear()
+        r.run(tile_mod=world, tile_rank=rank)
+        if world > 1:
+            parallel.reduce_film(r, dst=0)
+
+    frame()  # warm-up frame
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(frames):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0   # rrt_render_run returns when the device finished: host clock = device time
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    st = r.stats()
+    counts = torch.tensor([st["samples"], st["camera_rays"], st["extension_rays"], st["shadow_rays"], st["bounces"]],
+                          dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    dt = float(t.item())
+    samples, cam, ext, sh, bnc = [float(x) for x in counts.tolist()]
+    out = None
+    if rank == 0:
+        img = r.film()
+        out = {
+            "metric": "Msamples/s path-traced", "unit": "Msamples/s", "value": samples / (dt / frames) / 1e6,
+            "ms_per_frame": dt / frames * 1e3, "frames": frames, "n_gpus": world, "scaling": "strong",
+            "config": {"workload": PT_CONFIGS[args.path_config], "parallelism": f"16x16 sample tiles dealt t % {world} == rank, "
+                       "scene replicated, one NCCL reduce(sum) of the 4-f64-per-pixel film per frame"},
+            "samples_per_frame": samples, "camera_rays": cam, "extension_rays": ext, "shadow_rays": sh,
+            "rays_per_sample": (ext + sh) / max(samples, 1.0), "mean_bounces": bnc / max(cam, 1.0),
+            "Mrays_per_s": (ext + sh) / (dt / frames) / 1e6, "setup_s": setup_s,
+            "gpu_launches": int(ctx.launch_count - launches0),
+            "image_mean_rgb": [float(x) for x in img.mean(axis=(0, 1))],
+            "dtype": "f64 shading and film, fp32 box culling",
+        }
+        if world == 1 and not args.no_cpu_baseline and args.path_config == "c4":
+            sys.path.insert(0, str(ROOT / "tests"))
+            import oracle_lib as O
+            import oracle_scene as S
+            crop = (880, 460, 1040, 620)   # centred 160x160 pixels, full spp
+            ls = S.load(path)
+            t0 = time.perf_counter()
+            ref = ls.render(seed=1, crop=crop)
+            cdt = time.perf_counter() - t0   # includes the camera's exit-pupil set-up (a few seconds)
+            rs = ref["stats"]
+            n_s = rs["camera_rays"] + rs["zero_weight"]
+            gpu_crop = img[crop[1]:crop[3], crop[0]:crop[2]]
+            ref_crop = ref["rgb"][crop[1]:crop[3], crop[0]:crop[2]]
+            rmse = float(np.sqrt(np.mean((gpu_crop - ref_crop) ** 2)) / max(np.sqrt(np.mean(ref_crop ** 2)), 1e-300))
+            nv = (rs["closest_nodes"] + rs["any_nodes"]) / max(n_s, 1)
+            nt = (rs["closest_prims"] + rs["any_prims"]) / max(n_s, 1)
+            rays_ps = (rs["extension_rays"] + rs["shadow_rays"]) / max(n_s, 1)
+            bbar = rs["bounces"] / max(n_s, 1)
+            # SURVEY.md §8d: sum over a sample's rays of (32 + 16|1 + 32 Nv + 16 Nt[sphere]) + film 16 + 2*96*B
+            bytes_ps = (32 + 16) * rs["extension_rays"] / max(n_s, 1) + (32 + 1) * rs["shadow_rays"] / max(n_s, 1) + \
+                32 * nv + 16 * nt + 16 + 2 * 96 * bbar
+            peak, _ = measured_peak()
+            out["cpu_baseline"] = {"value": n_s / cdt / 1e6, "unit": "Msamples/s", "cores": O.hardware_threads(), "kind": "port",
+                                   "sample": f"centred 160x160-pixel crop of the frame at full spp ({n_s} camera samples), oracle "
+                                             "Tier F, one thread per tile; includes the camera's exit-pupil set-up",
+                                   "crop_rel_rmse_gpu_vs_oracle": rmse}
+            out["roofline"] = {"bound": "hbm", "unit": "GB/s", "algorithmic_bytes_per_sample": bytes_ps,
+                               "nodes_visited_per_sample_oracle": nv, "prims_tested_per_sample_oracle": nt,
+                               "rays_per_sample_oracle": rays_ps, "bounces_per_sample_oracle": bbar,
+                               "achieved": out["value"] * 1e6 * bytes_ps / 1e9, "peak": peak,
+                               "frac": out["value"] * 1e6 * bytes_ps / 1e9 / peak}
+    r.close()
+    del keep
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +298,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=N_RAYS, help=argparse.SUPPRESS)
+    ap.add_argument("--path-config", default="c4", choices=["c4", "c5", "none"],
+                    help="second half of the metric: path-traced Msamples/s on config 4 (default) or config 5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -276,6 +384,11 @@ def main():
     if e2e_hit != n_hit:
         raise SystemExit(f"bench.py: host path and device path disagree ({e2e_hit} vs {n_hit} hits)")
 
+    # free the ray batch before the frame renders
+    del d_rays, d_hits
+    torch.cuda.empty_cache()
+    pt = path_traced(args, ctx, rank, world, local_rank, barrier) if args.path_config != "none" else None
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kernel_ms = float(np.mean(per_launch_ms))
@@ -298,6 +411,7 @@ def main():
             "hit_fraction": n_hit / n_rays,
             "scene": stats,
         }
+        line["path_traced"] = pt
         if not args.no_cpu_baseline and world == 1:
             n_sample = 1 << 22
             sample = synth.bounce_rays(p, idx, n_sample, seed=synth.SEED_C3_RAYS)

@@ -47,11 +47,20 @@ RRT_HD double radical_inverse(const HaltonTables& h, int base_index, uint64_t a)
     const double inv_base = 1.0 / (double)base;
     double inv_base_n = 1.0;
     uint64_t reversed = 0;
-    while (a != 0) {
+    while (a > 0xFFFFFFFFull) {
         uint64_t next = a / base, digit = a - next * base;
         reversed = reversed * base + digit;
         inv_base_n *= inv_base;
         a = next;
+    }
+    // same digits with 32-bit divisions once the index fits (a 64-bit divide is ~10x the instructions)
+    uint32_t a32 = (uint32_t)a;
+    const uint32_t b32 = (uint32_t)base;
+    while (a32 != 0) {
+        uint32_t next = a32 / b32, digit = a32 - next * b32;
+        reversed = reversed * base + digit;
+        inv_base_n *= inv_base;
+        a32 = next;
     }
     return rmin((double)reversed * inv_base_n, kOneMinusEps);
 }
@@ -61,11 +70,19 @@ RRT_HD double scrambled_radical_inverse(const HaltonTables& h, int base_index, u
     const double inv_base = 1.0 / (double)base;
     double inv_base_n = 1.0;
     uint64_t reversed = 0;
-    while (a > 0) {
+    while (a > 0xFFFFFFFFull) {
         uint64_t next = a / base, digit = a - next * base;
         reversed = reversed * base + perm[digit];
         inv_base_n *= inv_base;
         a = next;
+    }
+    uint32_t a32 = (uint32_t)a;
+    const uint32_t b32 = (uint32_t)base;
+    while (a32 != 0) {
+        uint32_t next = a32 / b32, digit = a32 - next * b32;
+        reversed = reversed * base + perm[digit];
+        inv_base_n *= inv_base;
+        a32 = next;
     }
     return rmin(inv_base_n * ((double)reversed + inv_base * (double)perm[0] / (1.0 - inv_base)), kOneMinusEps);
 }
