@@ -264,6 +264,9 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_REFILL
 #define RRT_REFILL 8
 #endif
+#ifndef RRT_STALE_SKIP
+#define RRT_STALE_SKIP 1
+#endif
 #ifndef RRT_MINBLOCKS
 #define RRT_MINBLOCKS 7
 #endif
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                                                         const uint32_t* __restrict__ perm,
                                                         const uint32_t* __restrict__ use_perm,
                                                         unsigned long long* __restrict__ cursor,
-                                                        const uint32_t* __restrict__ n_dev) {
+                                                        const uint32_t* __restrict__ n_dev, int stack_levels) {
     const unsigned FULL = 0xffffffffu;
     if (n_dev) n = *n_dev;  // wavefront queues: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
@@ -289,6 +292,22 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
     // the tree depth (stack_levels * kBlock * 4 bytes of dynamic shared memory).
     extern __shared__ int32_t sstack[];
     int32_t* const my_stack = sstack + threadIdx.x;
+#if RRT_STALE_SKIP
+    // closest hit only: every pushed subtree remembers its entry distance, so that a pop can drop
+    // subtrees that a hit found meanwhile has put out of reach without fetching their node
+    float* const my_tstack = reinterpret_cast<float*>(sstack + stack_levels * kBlock) + threadIdx.x;
+#define RRT_POP()                                                      \
+    do {                                                               \
+        --sp;                                                          \
+        node = my_stack[sp * kBlock];                                  \
+    } while (!ANY && my_tstack[sp * kBlock] > tcull)
+#else
+#define RRT_POP()                     \
+    do {                              \
+        --sp;                         \
+        node = my_stack[sp * kBlock]; \
+    } while (0)
+#endif
     int sp = 1;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
     int32_t leaf = kNoLeaf;   // parked leaf reference
@@ -344,6 +363,9 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                     have_ray = true;
                     sp = 1;
                     my_stack[0] = kDone;
+#if RRT_STALE_SKIP
+                    my_tstack[0] = -1.0f;  // the marker is never stale
+#endif
                     leaf = kNoLeaf;
                     const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
                     node = live ? A.root : kDone;
@@ -372,18 +394,19 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                 const bool both = h0 && h1;
                 const bool swap = !ANY && (tn1 < tn0);
                 const int32_t near_c = swap ? ch_y : ch_x, far_c = swap ? ch_x : ch_y;
-                if (both) my_stack[sp * kBlock] = far_c;
+                if (both) {
+                    my_stack[sp * kBlock] = far_c;
+#if RRT_STALE_SKIP
+                    if (!ANY) my_tstack[sp * kBlock] = swap ? tn0 : tn1;
+#endif
+                }
                 sp += both ? 1 : 0;
                 node = both ? near_c : (h0 ? ch_x : ch_y);
-                if (!(h0 || h1)) {
-                    --sp;
-                    node = my_stack[sp * kBlock];
-                }
+                if (!(h0 || h1)) RRT_POP();
             }
             if (node < 0 && leaf == kNoLeaf) {  // park the first leaf, keep walking
                 leaf = node;
-                --sp;
-                node = my_stack[sp * kBlock];
+                RRT_POP();
             }
             // leave when no lane is still looking for its first leaf
             if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
@@ -424,8 +447,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                     node = kDone;
                 } else if (node < 0) {  // the walk had already reached another leaf
                     leaf = node;
-                    --sp;
-                    node = my_stack[sp * kBlock];
+                    RRT_POP();
                 }
             }
         }
@@ -874,7 +896,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     // the only shared memory is the traversal stack (one entry per tree level + the marker);
     // everything else of the 256 KB stays L1
     stack_levels_ = (int)tree.max_depth + 2;
-    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t);
+    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
     int carve = (int)((RRT_MINBLOCKS * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
     for (auto fn : {(const void*)trace_kernel<false, false>, (const void*)trace_kernel<false, true>,
@@ -945,7 +967,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
         count += 4;
     }
     auto kernel = view_.wide ? trace_kernel<ANY, true> : trace_kernel<ANY, false>;
-    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t);
+    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
     int per_sm = 0;
     RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
     if (per_sm < 1) per_sm = 1;
@@ -954,7 +976,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     if (blocks > needed) blocks = needed;
     kernel<<<(unsigned)blocks, kBlock, smem, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
                                                sorting ? small + 3 : nullptr,
-                                               reinterpret_cast<unsigned long long*>(small), n_dev);
+                                               reinterpret_cast<unsigned long long*>(small), n_dev, stack_levels_);
     count += 1;
     RRT_CUDA(cudaGetLastError());
     RRT_CUDA(cudaEventRecord(w.last_use, s));
