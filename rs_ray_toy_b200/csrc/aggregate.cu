@@ -265,7 +265,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_REFILL 8
 #endif
 #ifndef RRT_STALE_SKIP
-#define RRT_STALE_SKIP 1
+#define RRT_STALE_SKIP 0
 #endif
 #ifndef RRT_MINBLOCKS
 #define RRT_MINBLOCKS 7

@@ -89,3 +89,56 @@ def compare_closest(hits, ref_prim, ref_t, rel_tie=1e-6, rel_t=1e-5):
         "hits": int(hit.sum()),
         "max_rel_dt": float(dt[both & same].max()) if (both & same).any() else 0.0,
     }
+
+
+def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthreads=None, crop=None, want_dump=False):
+    """The oracle-side twin of synth.scene_c5_api: same soup, materials, lights and camera, fed
+    through the oracle's C API (no scene.json for million-triangle meshes)."""
+    import ctypes as C
+    import oracle_scene as S
+    p, idx = synth.soup_triangles(n_tris, edge, synth.SEED_C5_SOUP)
+    half = n_tris // 2
+    s = O.OracleScene(O.TIER_F)
+    m0 = s.add_mesh(p[: 3 * half], idx[:half])
+    m1 = s.add_mesh(p[3 * half:], idx[half:] - 3 * half)
+    g0 = s.add_geo_triangles(m0, 0)
+    s.add_prims(g0, half, -1)
+    g1 = s.add_geo_triangles(m1, 1)
+    s.add_prims(g1, n_tris - half, -1)
+    s.build(4)
+    mats = np.zeros((2, 26))
+    mats[0, 0] = 0
+    mats[0, 1:4] = (0.6, 0.55, 0.5)
+    mats[1, 0] = 1
+    mats[1, 1:4] = (0.3, 0.4, 0.6)
+    mats[1, 4:7] = (0.3, 0.3, 0.3)
+    mats[1, 20] = 0.15
+    mats[:, 21:23] = -1.0
+    lights = np.zeros((2, 24))
+    lights[0, 0] = 0
+    lights[0, 1:4] = (4.0, 4.0, 4.0)
+    lights[0, 7:23] = np.eye(4).reshape(16)
+    lights[1, 0] = 1
+    lights[1, 1:4] = (2.0, 2.0, 2.0)
+    lights[1, 4:7] = np.subtract((0.3, 1.0, -0.6), (0, 0, 0))
+    lights[1, 7:23] = np.eye(4).reshape(16)
+    L = O.lib()
+    L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.orc_set_materials(s.h, 2, mats.ctypes.data)
+    L.orc_set_lights(s.h, 2, lights.ctypes.data)
+    prm = np.zeros(40)
+    prm[0], prm[1], prm[2] = xres, yres, 35.0
+    prm[3], prm[4], prm[5], prm[6], prm[7], prm[8] = 0, 0.5, 0.5, 2.0, 1.0, np.inf
+    prm[9:12] = (0.5, 0.5, -2.5)
+    prm[12:15] = (0.5, 0.5, 0.5)
+    prm[15:18] = (0.0, 1.0, 0.0)
+    prm[18], prm[19], prm[20], prm[21], prm[22] = 0.0, 1.0, 50.0, 3.0, 1.0
+    prm[23], prm[24], prm[25] = nsamp, 0, seed_render
+    prm[26], prm[27], prm[28] = 0, max_depth, 1.0
+    prm[29], prm[30] = 1, 0
+    if crop is not None:
+        prm[31] = 1.0
+        prm[32:36] = crop
+    prm[36] = 1.0 if want_dump else 0.0
+    return S.oracle_render(s, prm, np.array(synth.DGAUSS_LENS, dtype=np.float64), nthreads, want_dump)

@@ -100,6 +100,18 @@ def test_config4_sphere_field_materials(ctx, tmp_path, extra):
     assert abs(out["extension_rays"][0] - out["extension_rays"][1]) <= max(8, out["extension_rays"][1] // 100000), out
 
 
+def test_config5_soup_through_the_api(ctx):
+    """Config 5's shape at a small size: two bare (non-instanced) meshes, Matte + Plastic, point +
+    distant light, assembled through rrt_scene_add_* and rrt_render_create (no scene.json)."""
+    import scenes
+    agg, gpu = synth.scene_c5_api(ctx, n_tris=60000, edge=0.02, xres=256, yres=144, nsamp=5)
+    gpu.enable_hit_dump()
+    gpu.run()
+    ref = scenes.oracle_c5(60000, 0.02, 256, 144, 5, want_dump=True)
+    out = compare(gpu, ref)
+    assert out["extension_rays"][1] > out["camera_rays"][1], out
+
+
 def test_filters_and_overrides(ctx, tmp_path):
     """Gaussian / triangle filters of radius 2 (samples splat across tile borders) and the
     luminance clamp, through the loader's `overrides`."""
