@@ -130,6 +130,15 @@ __device__ __forceinline__ bool slab(const RayF& r, float lox, float hix, float 
     return tmin <= tmax;
 }
 
+// The same test on plane distances that were computed by the caller (quantised nodes).
+__device__ __forceinline__ bool slab_t(float tx0, float tx1, float ty0, float ty1, float tz0, float tz1, float tcull,
+                                       float* tnear) {
+    float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcull));
+    *tnear = tmin;
+    return tmin <= tmax;
+}
+
 template <bool WIDE>
 __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a, D3* b, D3* c, uint32_t* prim_id,
                                           uint32_t* kind) {
@@ -264,6 +273,9 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_REFILL
 #define RRT_REFILL 8
 #endif
+#ifndef RRT_NODE32
+#define RRT_NODE32 1
+#endif
 #ifndef RRT_STALE_SKIP
 #define RRT_STALE_SKIP 0
 #endif
@@ -283,7 +295,9 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
     const unsigned FULL = 0xffffffffu;
     if (n_dev) n = *n_dev;  // wavefront queues: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
+#if !RRT_NODE32
     const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
+#endif
     const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
 
     // Traversal stack: entirely in shared memory, laid out [level][thread] so that 32 lanes at 32
@@ -382,6 +396,27 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
         for (;;) {
             const bool walking = node >= 0 && node != kDone;
             if (walking) {
+#if RRT_NODE32
+                // one 256-bit load: frame origin, 12 quantised planes, cell exponent, two references
+                const F8 v = ldg256(reinterpret_cast<const char*>(A.nodes) + (size_t)node * sizeof(Node32));
+                const uint32_t q0 = __float_as_uint(v.d), q1 = __float_as_uint(v.e), q2 = __float_as_uint(v.f);
+                const uint32_t w0 = __float_as_uint(v.g), w1 = __float_as_uint(v.h);
+                const float cell = __uint_as_float((w0 & 0xffu) << 23);
+                // plane distance = (origin + q * cell - o) / d = q * (cell / d) + (origin / d - o / d)
+                const float ax = cell * rf.idx, ay = cell * rf.idy, az = cell * rf.idz;
+                const float bx = fmaf(v.a, rf.idx, -rf.oidx), by = fmaf(v.b, rf.idy, -rf.oidy), bz = fmaf(v.c, rf.idz, -rf.oidz);
+                const uint32_t r0 = (w0 >> 8) | ((w1 & 0xfu) << 24), r1 = w1 >> 4;
+                const int32_t ch_x = (r0 & 0x8000000u) ? ~(int32_t)(((r0 & 0x1FFFFFFu) << 3) | ((r0 >> 25) & 3u)) : (int32_t)r0;
+                const int32_t ch_y = (r1 & 0x8000000u) ? ~(int32_t)(((r1 & 0x1FFFFFFu) << 3) | ((r1 >> 25) & 3u)) : (int32_t)r1;
+                float tn0, tn1;
+                const bool h0 = slab_t(fmaf((float)(q0 & 0xffu), ax, bx), fmaf((float)(q0 >> 24), ax, bx),
+                                       fmaf((float)((q0 >> 8) & 0xffu), ay, by), fmaf((float)(q1 & 0xffu), ay, by),
+                                       fmaf((float)((q0 >> 16) & 0xffu), az, bz), fmaf((float)((q1 >> 8) & 0xffu), az, bz),
+                                       tcull, &tn0);
+                const bool h1 = slab_t(fmaf((float)((q1 >> 16) & 0xffu), ax, bx), fmaf((float)((q2 >> 8) & 0xffu), ax, bx),
+                                       fmaf((float)(q1 >> 24), ay, by), fmaf((float)((q2 >> 16) & 0xffu), ay, by),
+                                       fmaf((float)(q2 & 0xffu), az, bz), fmaf((float)(q2 >> 24), az, bz), tcull, &tn1);
+#else
                 const char* np = reinterpret_cast<const char*>(nodes + node);
                 const F8 lo = ldg256(np);        // c0 x/y slabs, c1 x/y slabs
                 const F8 hi = ldg256(np + 32);   // z slabs of both, child references
@@ -389,6 +424,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                 float tn0, tn1;
                 const bool h0 = slab(rf, lo.a, lo.b, lo.c, lo.d, hi.a, hi.b, tcull, &tn0);
                 const bool h1 = slab(rf, lo.e, lo.f, lo.g, lo.h, hi.c, hi.d, tcull, &tn1);
+#endif
                 // branch-free step: both hit -> push the far child, go near; one hit -> go there;
                 // none -> pop
                 const bool both = h0 && h1;
@@ -723,6 +759,9 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     Bvh2 tree;
     SahParams sp;
     sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
+#if RRT_NODE32
+    if (sp.max_leaf > 4) sp.max_leaf = 4;  // the 32-byte node's leaf reference holds a 2-bit count
+#endif
     if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
     build_sah(boxes, sp, &tree);
     if (tree.max_depth + 2 > (uint32_t)kStack) {
@@ -850,13 +889,89 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         }
     }
 
+#if RRT_NODE32
+    // ---- quantise: Node64 (fp32 planes) -> Node32 (8-bit planes on a per-node power-of-two grid) ----
+    std::vector<Node32> nodes32(nodes.size());
+    if (nodes.size() >= (1u << 27) || n >= (1u << 25)) {
+        if (err) *err = "scene too large for the 28-bit child references of the 32-byte node";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const Node64& s = nodes[i];
+        const double lo[2][3] = {{s.c0_lox, s.c0_loy, s.c0_loz}, {s.c1_lox, s.c1_loy, s.c1_loz}};
+        const double hi[2][3] = {{s.c0_hix, s.c0_hiy, s.c0_hiz}, {s.c1_hix, s.c1_hiy, s.c1_hiz}};
+        double ext = 0.0, maxabs = 0.0, mn[3];
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = std::fmin(lo[0][k], lo[1][k]);
+            const double mx = std::fmax(hi[0][k], hi[1][k]);
+            ext = std::fmax(ext, mx - mn[k]);
+            maxabs = std::fmax(maxabs, std::fmax(std::fabs(mn[k]), std::fabs(mx)));
+        }
+        // cell = 2^e: 254 cells span the node (one is lost to flooring the origin), and the grid is
+        // never finer than what fp32 can hold at these coordinates, so origin + q * cell is exact
+        double need = std::fmax(ext / 254.0, maxabs / 16776000.0);
+        need = std::fmax(need, std::ldexp(1.0, -100));
+        int e = 0;
+        std::frexp(need, &e);  // need = f * 2^e, f in [0.5, 1)  =>  2^e >= need
+        const double cell = std::ldexp(1.0, e);
+        Node32 o;
+        uint8_t qb[12];
+        double org[3];
+        bool ok = e + 127 >= 1 && e + 127 <= 254;
+        for (int k = 0; k < 3; ++k) {
+            org[k] = std::floor(mn[k] / cell) * cell;
+            ok = ok && (double)(float)org[k] == org[k];
+        }
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 3; ++k) {
+                const double ql = std::floor((lo[c][k] - org[k]) / cell), qh = std::ceil((hi[c][k] - org[k]) / cell);
+                ok = ok && ql >= 0.0 && qh <= 255.0 && ql <= qh;
+                // the decoded planes must enclose the box they replace, as exact fp32 values
+                const double dl = org[k] + ql * cell, dh = org[k] + qh * cell;
+                ok = ok && dl <= lo[c][k] && dh >= hi[c][k] && (double)(float)dl == dl && (double)(float)dh == dh;
+                // plane order inside the 12 bytes: c0 lo xyz, c0 hi xyz, c1 lo xyz, c1 hi xyz
+                qb[6 * c + k] = (uint8_t)ql;
+                qb[6 * c + 3 + k] = (uint8_t)qh;
+            }
+        if (!ok) {
+            if (err) *err = "node quantisation failed (box not representable on an fp32 grid)";
+            return RRT_ERR_UNSUPPORTED;
+        }
+        o.ox = (float)org[0];
+        o.oy = (float)org[1];
+        o.oz = (float)org[2];
+        for (int w = 0; w < 3; ++w)
+            o.q[w] = (uint32_t)qb[4 * w] | ((uint32_t)qb[4 * w + 1] << 8) | ((uint32_t)qb[4 * w + 2] << 16) | ((uint32_t)qb[4 * w + 3] << 24);
+        auto ref28 = [&](int32_t child, bool* good) -> uint32_t {
+            if (child >= 0) return (uint32_t)child;
+            const uint32_t r = ~(uint32_t)child, first = r >> 3, cnt1 = r & 7u;
+            if (cnt1 > 3u || first >= (1u << 25)) *good = false;
+            return 0x8000000u | (cnt1 << 25) | first;
+        };
+        bool good = true;
+        const uint32_t r0 = ref28(s.child0, &good), r1 = ref28(s.child1, &good);
+        if (!good) {
+            if (err) *err = "leaf does not fit the 32-byte node's reference (more than 4 primitives per leaf)";
+            return RRT_ERR_UNSUPPORTED;
+        }
+        o.w0 = (uint32_t)(e + 127) | ((r0 & 0xFFFFFFu) << 8);
+        o.w1 = (r0 >> 24) | (r1 << 4);
+        nodes32[i] = o;
+    }
+#endif
     // ---- upload ----
     RRT_CUDA(cudaSetDevice(device));
+#if RRT_NODE32
+    size_t node_bytes = nodes32.size() * sizeof(Node32);
+    const void* node_src = nodes32.data();
+#else
     size_t node_bytes = nodes.size() * sizeof(Node64);
+    const void* node_src = nodes.data();
+#endif
     size_t prim_bytes = wide ? rec96.size() * sizeof(PrimRec96) : rec48.size() * sizeof(PrimRec48);
     RRT_CUDA(cudaMalloc(&d_nodes_, node_bytes));
     RRT_CUDA(cudaMalloc(&d_prims_, prim_bytes));
-    RRT_CUDA(cudaMemcpy(d_nodes_, nodes.data(), node_bytes, cudaMemcpyHostToDevice));
+    RRT_CUDA(cudaMemcpy(d_nodes_, node_src, node_bytes, cudaMemcpyHostToDevice));
     RRT_CUDA(cudaMemcpy(d_prims_, wide ? (const void*)rec96.data() : (const void*)rec48.data(), prim_bytes,
                         cudaMemcpyHostToDevice));
     bool has_spheres = false;
