@@ -27,7 +27,13 @@ namespace rrt {
 namespace {
 
 constexpr int kStack = 64;
-constexpr int kBlock = 128;
+#ifndef RRT_BLOCK
+#define RRT_BLOCK 128
+#endif
+#ifndef RRT_UNROLL
+#define RRT_UNROLL 1
+#endif
+constexpr int kBlock = RRT_BLOCK;
 
 struct D3 {
     double x, y, z;
@@ -274,7 +280,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_REFILL 8
 #endif
 #ifndef RRT_NODE32
-#define RRT_NODE32 1
+#define RRT_NODE32 0
 #endif
 #ifndef RRT_STALE_SKIP
 #define RRT_STALE_SKIP 0
@@ -394,6 +400,8 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
 
         // ---- interior phase ----
         for (;;) {
+#pragma unroll
+          for (int step = 0; step < RRT_UNROLL; ++step) {
             const bool walking = node >= 0 && node != kDone;
             if (walking) {
 #if RRT_NODE32
@@ -444,6 +452,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
                 leaf = node;
                 RRT_POP();
             }
+          }
             // leave when no lane is still looking for its first leaf
             if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
         }
