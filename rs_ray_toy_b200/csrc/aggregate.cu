@@ -31,7 +31,7 @@ constexpr int kStack = 64;
 #define RRT_BLOCK 128
 #endif
 #ifndef RRT_UNROLL
-#define RRT_UNROLL 1
+#define RRT_UNROLL 2
 #endif
 constexpr int kBlock = RRT_BLOCK;
 

@@ -185,3 +185,83 @@ def test_full_size_properties_c3(ctx):
     h3 = agg.intersect(short)
     got = h3["prim_id"] != 0xFFFFFFFF
     assert not got.any(), int(got.sum())   # nothing lies in front of the closest hit
+
+
+def test_call_order_and_argument_errors(ctx):
+    """No panic / exception crosses the ABI: misuse comes back as a status with a message
+    (the reference asserts: bvh.rs:319, scene.rs:70,77)."""
+    import ctypes as C
+    from rs_ray_toy_b200 import capi
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    a = GpuAggregate(ctx)
+    with pytest.raises(capi.RrtError) as e:     # intersect before commit
+        a.intersect(np.zeros((4, 7)))
+    assert e.value.status == capi.RRT_ERR_INVALID
+    with pytest.raises(capi.RrtError):          # bad mesh id
+        a.add_triangles(7, 0)
+    with pytest.raises(capi.RrtError):          # vertex index out of range
+        a.add_mesh(np.zeros((3, 3)), np.array([[0, 1, 5]], dtype=np.uint32))
+    p, idx = scenes.soup(100)
+    m = a.add_mesh(p, idx)
+    a.add_triangles(m, 0)
+    a.commit()
+    with pytest.raises(capi.RrtError):          # committed scenes are immutable
+        a.add_triangles(m, 0)
+    with pytest.raises(capi.RrtError):
+        a.commit()
+    L = capi.lib()
+    assert L.rrt_intersect(a.h, 4, None, None) == capi.RRT_ERR_INVALID
+    assert L.rrt_last_error()
+    with pytest.raises(capi.RrtError) as e:     # the literal tier lives in the oracle only
+        b = GpuAggregate(ctx)
+        mb = b.add_mesh(p, idx)
+        b.add_triangles(mb, 0)
+        b.commit(4, capi.RRT_BUILD_LITERAL)
+    assert e.value.status == capi.RRT_ERR_UNSUPPORTED
+
+
+def test_concurrent_host_threads_share_one_aggregate(ctx):
+    """`Primitive: Send + Sync` (primitives.rs:14): several host threads query one committed
+    aggregate at once (the reference's rayon workers do)."""
+    import threading
+    p, idx = scenes.soup(20000)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    batches = [synth.bounce_rays(p, idx, 30000, seed=200 + k) for k in range(4)]
+    expect = [agg.intersect(b) for b in batches]
+    got = [None] * 4
+    occ = [None] * 4
+
+    def work(k):
+        for _ in range(3):
+            got[k] = agg.intersect(batches[k])
+            occ[k] = agg.intersect_p(batches[k])
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(4):
+        assert np.array_equal(got[k], expect[k])
+        assert np.array_equal(occ[k].astype(bool), expect[k]["prim_id"] != 0xFFFFFFFF)
+
+
+def test_device_pointer_entry_points(ctx):
+    """rrt_intersect_device / rrt_intersect_p_device on caller-owned device buffers and stream."""
+    import torch
+    from rs_ray_toy_b200.aggregate import HIT_DTYPE, pack_rays
+    p, idx = scenes.soup(30000)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    rays = synth.bounce_rays(p, idx, 50000, seed=9)
+    ref = agg.intersect(rays)
+    d_rays = torch.from_numpy(pack_rays(rays).view(np.float64).copy()).cuda()
+    d_hits = torch.zeros(50000 * 4, dtype=torch.float64, device="cuda")
+    d_occ = torch.zeros(50000, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        agg.intersect_device(50000, d_rays.data_ptr(), d_hits.data_ptr(), s.cuda_stream)
+        agg.intersect_p_device(50000, d_rays.data_ptr(), d_occ.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    hits = d_hits.cpu().numpy().view(HIT_DTYPE).reshape(-1)
+    assert np.array_equal(hits, ref)
+    assert np.array_equal(d_occ.cpu().numpy().astype(bool), ref["prim_id"] != 0xFFFFFFFF)
