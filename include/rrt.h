@@ -203,6 +203,12 @@ int rrt_render_clear(rrt_render* render);
 /* Film::write_image up to the float image (film.rs:323-366): rgb[yres*xres*3]; raw (may be NULL)
  * [yres*xres*4] = pixel xyz + filter_weight_sum as the reference's Film would hold them.        */
 int rrt_render_read_film(rrt_render* render, double* rgb, double* raw);
+/* write_image (renderprocess.rs:1501-1530): sRGB gamma + `clamp(255 g + 0.5) as u8`, alpha 255.
+ * rgba8[yres*xres*4]; rrt_render_write_png also writes the file (`save_to` of deploy_render).   */
+int rrt_render_read_rgba8(rrt_render* render, uint8_t* rgba8);
+int rrt_render_write_png(rrt_render* render, const char* path);
+/* The same quantisation for a caller-held float image (host only; no device is touched).        */
+int rrt_rgb_to_png(const double* rgb, uint32_t xres, uint32_t yres, const char* path, uint8_t* rgba8_or_null);
 /* Device pointer to the accumulation film (4 f64 per pixel: RGB contribution sum, filter weight sum)
  * for a multi-GPU gather/reduce; *n_doubles = 4 * xres * yres.                                   */
 int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_doubles);

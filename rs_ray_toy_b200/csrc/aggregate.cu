@@ -137,7 +137,7 @@ __device__ __forceinline__ bool slab(const RayF& r, float lox, float hix, float 
 }
 
 // The same test on plane distances that were computed by the caller (quantised nodes).
-__device__ __forceinline__ bool slab_t(float tx0, float tx1, float ty0, float ty1, float tz0, float tz1, float tcull,
+__device__ __forceinline__ bool __attribute__((unused)) slab_t(float tx0, float tx1, float ty0, float ty1, float tz0, float tz1, float tcull,
                                        float* tnear) {
     float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
     float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcull));
@@ -180,6 +180,12 @@ __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a
 // Brings a ray whose origin lies far outside the world box close to it (in f64), so that the
 // fp32 traversal copy keeps |o| comparable to the scene and the host-side box widening holds.
 __device__ __noinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_max, float* t_shift, RayF* rf) {
+    // Scene::intersect asserts d != 0 (scene.rs:70); here a ray without a direction, or with a
+    // non-finite component, simply hits nothing
+    const double len2 = d.x * d.x + d.y * d.y + d.z * d.z;
+    if (!(len2 > 0.0) || !(len2 < 1e300) || !(o.x == o.x) || !(o.y == o.y) || !(o.z == o.z) ||
+        fabs(o.x) > 1e300 || fabs(o.y) > 1e300 || fabs(o.z) > 1e300)
+        return false;
     double ts = 0.0;
     bool outside = o.x < A.world_lo[0] || o.x > A.world_hi[0] || o.y < A.world_lo[1] || o.y > A.world_hi[1] ||
                    o.z < A.world_lo[2] || o.z > A.world_hi[2];

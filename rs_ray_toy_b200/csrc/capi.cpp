@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aggregate.hpp"
+#include "png_min.hpp"
 #include "render.hpp"
 #include "scene_json.hpp"
 
@@ -476,6 +477,46 @@ int rrt_render_read_film(rrt_render* render, double* rgb, double* raw) {
     std::string err;
     int rc = render->renderer.read_film(rgb, raw, &err);
     return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_render_read_rgba8(rrt_render* render, uint8_t* rgba8) {
+    if (!render || !rgba8) return fail(RRT_ERR_INVALID, "rrt_render_read_rgba8: null argument");
+    try {
+        const size_t npix = (size_t)(render->renderer.film_doubles() / 4);
+        std::vector<double> rgb(3 * npix);
+        std::string err;
+        int rc = render->renderer.read_film(rgb.data(), nullptr, &err);
+        if (rc != RRT_OK) return fail(rc, err);
+        rrt::rgb_to_rgba8(rgb.data(), npix, rgba8);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_render_write_png(rrt_render* render, const char* path) {
+    if (!render || !path) return fail(RRT_ERR_INVALID, "rrt_render_write_png: null argument");
+    try {
+        const size_t npix = (size_t)(render->renderer.film_doubles() / 4);
+        std::vector<uint8_t> px(4 * npix);
+        int rc = rrt_render_read_rgba8(render, px.data());
+        if (rc != RRT_OK) return rc;
+        if (!rrt::write_png_rgba8(path, px.data(), (uint32_t)render->renderer.xres(), (uint32_t)render->renderer.yres()))
+            return fail(RRT_ERR_IO, std::string("cannot write ") + path);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_rgb_to_png(const double* rgb, uint32_t xres, uint32_t yres, const char* path, uint8_t* rgba8_or_null) {
+    if (!rgb || !xres || !yres) return fail(RRT_ERR_INVALID, "rrt_rgb_to_png: null argument");
+    try {
+        std::vector<uint8_t> px(4 * (size_t)xres * yres);
+        rrt::rgb_to_rgba8(rgb, (size_t)xres * yres, px.data());
+        if (rgba8_or_null) std::memcpy(rgba8_or_null, px.data(), px.size());
+        if (path && !rrt::write_png_rgba8(path, px.data(), xres, yres)) return fail(RRT_ERR_IO, std::string("cannot write ") + path);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
 }
 int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_doubles) {
     if (!render || !d_film || !n_doubles) return fail(RRT_ERR_INVALID, "rrt_render_film_device: null argument");

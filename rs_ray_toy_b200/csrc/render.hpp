@@ -35,6 +35,8 @@ class Renderer {
     int read_film(double* rgb, double* raw, std::string* err);
     int copy_film_device(void* buffer, bool to_render, void* stream, std::string* err);
     void* film_device() const { return d_film_; }
+    int64_t xres() const { return xres_; }
+    int64_t yres() const { return yres_; }
     uint64_t film_doubles() const { return 4ull * (uint64_t)xres_ * (uint64_t)yres_; }
     int hit_dump(int enable, double* out, uint64_t capacity, uint64_t* count, std::string* err);
     const RenderStats& stats() const { return stats_; }

@@ -112,6 +112,12 @@ def _bind(L):
     L.rrt_render_read_film.argtypes = [vp, vp, vp]
     L.rrt_render_film_device.restype = i32
     L.rrt_render_film_device.argtypes = [vp, pvp, C.POINTER(u64)]
+    L.rrt_render_read_rgba8.restype = i32
+    L.rrt_render_read_rgba8.argtypes = [vp, vp]
+    L.rrt_render_write_png.restype = i32
+    L.rrt_render_write_png.argtypes = [vp, C.c_char_p]
+    L.rrt_rgb_to_png.restype = i32
+    L.rrt_rgb_to_png.argtypes = [vp, u32, u32, C.c_char_p, vp]
     L.rrt_render_film_copy.restype = i32
     L.rrt_render_film_copy.argtypes = [vp, vp, i32, vp]
     L.rrt_render_stats.restype = i32
@@ -127,6 +133,15 @@ def lib():
         _bind(L)
         L._render_bound = True
     return L
+
+
+def rgb_to_png(rgb, path=None) -> np.ndarray:
+    """write_image's quantisation (+ optional PNG file) for a float image [h, w, 3]; host only."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.float64)
+    out = np.zeros(rgb.shape[:2] + (4,), dtype=np.uint8)
+    capi.check(lib().rrt_rgb_to_png(rgb.ctypes.data, rgb.shape[1], rgb.shape[0], str(path).encode() if path else None,
+                                    out.ctypes.data))
+    return out
 
 
 def json_probe(path, overrides=None):
@@ -204,6 +219,15 @@ class Render:
         raw = np.zeros((self.yres, self.xres, 4)) if want_raw else None
         capi.check(self.L.rrt_render_read_film(self.h, rgb.ctypes.data, raw.ctypes.data if want_raw else None))
         return (rgb, raw) if want_raw else rgb
+
+    def rgba8(self) -> np.ndarray:
+        """`write_image`'s 8-bit pixels (renderprocess.rs:1501-1530): [yres, xres, 4] uint8."""
+        out = np.zeros((self.yres, self.xres, 4), dtype=np.uint8)
+        capi.check(self.L.rrt_render_read_rgba8(self.h, out.ctypes.data))
+        return out
+
+    def write_png(self, path):
+        capi.check(self.L.rrt_render_write_png(self.h, str(path).encode()))
 
     def film_device(self):
         p, n = C.c_void_p(), C.c_uint64()

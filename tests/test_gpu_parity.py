@@ -187,6 +187,27 @@ def test_full_size_properties_c3(ctx):
     assert not got.any(), int(got.sum())   # nothing lies in front of the closest hit
 
 
+def test_degenerate_rays_hit_nothing(ctx):
+    """Rays the reference would refuse (scene.rs:70 asserts d != 0) or that carry NaN / inf: the
+    device reports a miss for them and is not disturbed for their neighbours in the batch."""
+    p, idx = scenes.soup(5000)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    rays = synth.bounce_rays(p, idx, 4096 + 64, seed=31)
+    good = agg.intersect(rays)
+    bad = rays.copy()
+    bad[0, 3:6] = 0.0
+    bad[1, 3] = np.nan
+    bad[2, 0] = np.nan
+    bad[3, 1] = np.inf
+    bad[4, 3:6] = (np.inf, 0.0, 0.0)
+    bad[5, 6] = -1.0          # negative t_max
+    bad[6, 6] = 0.0
+    h = agg.intersect(bad)
+    assert (h["prim_id"][:7] == 0xFFFFFFFF).all()
+    assert np.array_equal(h[7:], good[7:])
+    assert (agg.intersect_p(bad)[:7] == 0).all()
+
+
 def test_call_order_and_argument_errors(ctx):
     """No panic / exception crosses the ABI: misuse comes back as a status with a message
     (the reference asserts: bvh.rs:319, scene.rs:70,77)."""

@@ -134,3 +134,35 @@ def test_product_loader_matches_oracle_loader(tmp_path):
     ov = {"Integrator": {"integrator_type": "Path", "max_depth": 3, "rr_threshold": 0.5}}
     _, d = render.json_probe(synth.scene_c2(str(tmp_path / "c2b"), n_instances=10, xres=32, yres=32), ov)
     assert (d.integrator_kind, d.max_depth, d.rr_threshold) == (0, 3, 0.5)
+
+
+def test_write_image_quantisation_and_png(tmp_path):
+    """renderprocess.rs:1501-1530: sRGB gamma (misc.rs:46-52), clamp(255 g + 0.5) as u8, alpha 255 —
+    the host code of the product against a numpy restatement, and the PNG it writes decoded back."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(4)
+    img = rng.uniform(-0.1, 1.3, (37, 53, 3))
+    img[0, 0] = (0.0031308, 0.0, 1.0)
+    img[0, 1] = (np.nan, 0.5, 2.0)
+    g = np.where(img <= 0.0031308, 12.92 * img, 1.055 * np.power(np.maximum(img, 0), 1.0 / 2.4) - 0.055)
+    ref = np.clip(255.0 * g + 0.5, 0.0, 255.0)
+    ref = np.where(np.isnan(ref), 0.0, ref).astype(np.uint8)
+    path = tmp_path / "out.png"
+    got = render.rgb_to_png(img, path)
+    assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 255).all()
+    data = path.read_bytes()
+    assert data[:8] == bytes([0x89, 0x50, 0x4E, 0x47, 0x0D, 0x0A, 0x1A, 0x0A])
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == (zlib.crc32(typ + body) & 0xFFFFFFFF)
+        if typ == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", body)
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    assert ihdr == (53, 37, 8, 6, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(37, 1 + 53 * 4)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(37, 53, 4), got)
