@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -34,8 +35,17 @@ int cuda_fail(const char* what, cudaError_t e) {
         if (e_ != cudaSuccess) return cuda_fail(#call, e_); \
     } while (0)
 
-constexpr int kSlots = 3;                  // pipeline depth of the host-buffer calls
-constexpr uint64_t kChunkRays = 1u << 20;  // 64 MiB of rays per slot
+constexpr int kSlots = 3;  // pipeline depth of the host-buffer calls
+// rays per pipeline slot (64 B each); RRT_HOST_CHUNK overrides for experiments
+uint64_t chunk_rays() {
+    static const uint64_t v = [] {
+        const char* e = std::getenv("RRT_HOST_CHUNK");
+        uint64_t c = e ? std::strtoull(e, nullptr, 10) : (1ull << 20);
+        return c < 4096 ? 4096 : c;
+    }();
+    return v;
+}
+#define kChunkRays (chunk_rays())
 
 struct Slot {
     cudaStream_t stream = nullptr;
