@@ -60,7 +60,9 @@ typedef struct rrt_hit {
 /* BVHSplitMethod (bvh.rs:111-114) plus the parity tier.                         */
 typedef enum rrt_build_flags {
     RRT_BUILD_FAST = 0,    /* Tier F: own SAH tree, true closest hit, ties -> lowest prim id     */
-    RRT_BUILD_LITERAL = 1  /* Tier L: the reference's HLBVH topology and accept rules, quirks kept */
+    RRT_BUILD_LITERAL = 1  /* Tier L: the reference's HLBVH topology, visiting order and accept rules
+                              with every quirk kept (last accepted hit wins, ...): bit-for-bit what
+                              BVHAccel returns; one thread per ray, meant for parity not throughput */
 } rrt_build_flags;
 
 /* ---- context ----------------------------------------------------------------------------- */
@@ -106,6 +108,13 @@ int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out);
 int rrt_world_bound(const rrt_scene* scene, double out6[6]);
 /* Build statistics: nodes, leaves, max depth, bytes uploaded, host build seconds (x1e6).        */
 int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]);
+
+/* Host-only probe of the literal tier's tree builder (BVHAccel::new with HLBVH, bvh.rs:307-751) on a
+ * list of primitive world bounds (6 doubles each: p_min, p_max).  Returns the flattened
+ * LinearBVHNode array: node_bounds6[6 * i], node_meta3[3 * i] = (offset, n_primitives, axis), and the
+ * reordered primitive list.  *n_nodes receives the node count (also when capacity is too small).   */
+int rrt_hlbvh_literal_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
+                            uint32_t* n_nodes, double* node_bounds6, uint32_t* node_meta3, uint32_t* ordered);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* Scene::intersect -> BVHAccel::intersect (scene.rs:69-72, bvh.rs:183-236) over a batch.
@@ -187,6 +196,10 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
  * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */
 int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
                         rrt_render** render);
+/* The same with the parity tier chosen (RRT_BUILD_FAST / RRT_BUILD_LITERAL): in the literal tier the
+ * integrator also keeps the reference's shadow-ray construction (Q9) and instance-ray rule (Q6). */
+int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed,
+                             uint32_t build_flags, rrt_scene** scene, rrt_render** render);
 /* Host-only view of what the loader reads (no device is touched): out8 = primitives, meshes,
  * spheres, instances, materials, lights, max_prims_in_node, lens values; desc = the render
  * description (lens_data pointer left NULL).  Used by the CPU test-suite and by tooling.          */

@@ -31,7 +31,24 @@ struct AggView {
     int32_t sort_mode;   // ray-queue key: 0 cell, 1 cell|octant, 2 octant|cell
 };
 
-class DeviceAggregate {
+// What the C ABI and the renderer need from an aggregate: batches of closest-hit / any-hit
+// queries, with the batch size on the host or in device memory.
+class RayTracer {
+  public:
+    virtual ~RayTracer() = default;
+    virtual int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,
+                            int* launches = nullptr) const = 0;
+    virtual int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
+                        int* launches = nullptr) const = 0;
+    virtual int closest_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, rrt_hit* d_hits,
+                                     void* stream, std::string* err, int* launches = nullptr) const = 0;
+    virtual int any_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, uint8_t* d_occluded,
+                                 void* stream, std::string* err, int* launches = nullptr) const = 0;
+    virtual const AggregateStats& stats() const = 0;
+    virtual bool literal() const { return false; }
+};
+
+class DeviceAggregate : public RayTracer {
   public:
     DeviceAggregate() = default;
     ~DeviceAggregate();
@@ -44,19 +61,19 @@ class DeviceAggregate {
 
     // Asynchronous on `stream`; *launches (optional) receives the number of kernels launched.
     int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,
-                    int* launches = nullptr) const;
+                    int* launches = nullptr) const override;
     int any_hit(uint64_t n, const rrt_ray* d_rays, uint8_t* d_occluded, void* stream, std::string* err,
-                int* launches = nullptr) const;
+                int* launches = nullptr) const override;
 
     // Wavefront queues: the number of rays is read from device memory (*d_count <= capacity), so a
     // whole bounce loop can be enqueued without a host round trip.
     int closest_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, rrt_hit* d_hits,
-                             void* stream, std::string* err, int* launches = nullptr) const;
+                             void* stream, std::string* err, int* launches = nullptr) const override;
     int any_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, uint8_t* d_occluded,
-                         void* stream, std::string* err, int* launches = nullptr) const;
+                         void* stream, std::string* err, int* launches = nullptr) const override;
 
     const AggView& view() const { return view_; }
-    const AggregateStats& stats() const { return stats_; }
+    const AggregateStats& stats() const override { return stats_; }
 
   private:
     // Scratch for the ray sort + the persistent kernel's cursor, shared by all calls (stream-ordered).

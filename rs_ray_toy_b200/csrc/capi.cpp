@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "aggregate.hpp"
+#include "bvh_hlbvh.hpp"
+#include "literal.hpp"
 #include "png_min.hpp"
 #include "render.hpp"
 #include "scene_json.hpp"
@@ -88,7 +90,7 @@ struct rrt_scene {
     rrt::HostScene host;
     std::vector<rrt_material> materials;
     std::vector<rrt_light> lights;
-    std::unique_ptr<rrt::DeviceAggregate> agg;
+    std::unique_ptr<rrt::RayTracer> agg;  // DeviceAggregate (Tier F) or LiteralAggregate (Tier L)
     bool committed = false;
     uint32_t build_flags = 0;
 };
@@ -288,14 +290,20 @@ int rrt_scene_add_sphere(rrt_scene* scene, const double* obj_to_world_m, const d
 int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t build_flags) {
     if (!scene) return fail(RRT_ERR_INVALID, "rrt_scene_commit: null scene");
     if (scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_commit: already committed");
-    if (build_flags != RRT_BUILD_FAST)
-        return fail(RRT_ERR_UNSUPPORTED,
-                    "rrt_scene_commit: only RRT_BUILD_FAST (Tier F) runs on the device; the literal tier lives in the "
-                    "test oracle (DESIGN.md)");
+    if (build_flags != RRT_BUILD_FAST && build_flags != RRT_BUILD_LITERAL)
+        return fail(RRT_ERR_INVALID, "rrt_scene_commit: unknown build flags");
     try {
         std::string err;
-        scene->agg.reset(new rrt::DeviceAggregate());
-        int rc = scene->agg->build(scene->ctx->device, scene->host, max_prims_in_node, &err);
+        int rc;
+        if (build_flags == RRT_BUILD_LITERAL) {
+            auto* lit = new rrt::LiteralAggregate();
+            scene->agg.reset(lit);
+            rc = lit->build(scene->ctx->device, scene->host, max_prims_in_node, &err);
+        } else {
+            auto* fast = new rrt::DeviceAggregate();
+            scene->agg.reset(fast);
+            rc = fast->build(scene->ctx->device, scene->host, max_prims_in_node, &err);
+        }
         if (rc != RRT_OK) {
             scene->agg.reset();
             return fail(rc, err);
@@ -318,12 +326,54 @@ int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out) {
 int rrt_world_bound(const rrt_scene* scene, double out6[6]) {
     if (!scene || !out6) return fail(RRT_ERR_INVALID, "rrt_world_bound: null argument");
     if (scene->host.prims.empty()) return fail(RRT_ERR_EMPTY, "rrt_world_bound: no primitives");
-    // BVHAccel::world_bound = root bounds = union of every Primitive::world_bound (bvh.rs:177-182)
+    // BVHAccel::world_bound = root bounds (bvh.rs:177-182).  In the literal tier that is the root of
+    // the reference's own tree, which may have lost primitives (Q1); otherwise the union of every
+    // Primitive::world_bound.
+    if (scene->committed && scene->build_flags == RRT_BUILD_LITERAL) {
+        static_cast<const rrt::LiteralAggregate*>(scene->agg.get())->root_bounds(out6);
+        return RRT_OK;
+    }
     rrt::Aabb b;
     for (size_t i = 0; i < scene->host.prims.size(); ++i) b.grow(scene->host.reference_world_bound(i));
     for (int k = 0; k < 3; ++k) {
         out6[k] = b.lo[k];
         out6[3 + k] = b.hi[k];
+    }
+    return RRT_OK;
+}
+
+int rrt_hlbvh_literal_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
+                            uint32_t* n_nodes, double* node_bounds6, uint32_t* node_meta3, uint32_t* ordered) {
+    if (!bounds6 || !n_nodes) return fail(RRT_ERR_INVALID, "rrt_hlbvh_literal_probe: null argument");
+    if (n == 0) return fail(RRT_ERR_EMPTY, "BVHAccel::new needs at least one primitive (bvh.rs:319)");
+    try {
+        std::vector<rrt::Aabb> b(n);
+        for (uint32_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                b[i].lo[k] = bounds6[6 * (size_t)i + k];
+                b[i].hi[k] = bounds6[6 * (size_t)i + 3 + k];
+            }
+        rrt::LiteralBvh tree;
+        rrt::build_hlbvh_literal(b, max_prims_in_node, &tree);
+        *n_nodes = (uint32_t)tree.nodes.size();
+        if (tree.nodes.size() <= capacity_nodes) {
+            for (size_t i = 0; i < tree.nodes.size(); ++i) {
+                const rrt::LinearNode& nd = tree.nodes[i];
+                if (node_bounds6)
+                    for (int k = 0; k < 3; ++k) {
+                        node_bounds6[6 * i + k] = nd.lo[k];
+                        node_bounds6[6 * i + 3 + k] = nd.hi[k];
+                    }
+                if (node_meta3) {
+                    node_meta3[3 * i] = nd.offset;
+                    node_meta3[3 * i + 1] = nd.n_primitives;
+                    node_meta3[3 * i + 2] = nd.axis;
+                }
+            }
+            if (ordered) std::memcpy(ordered, tree.ordered.data(), tree.ordered.size() * sizeof(uint32_t));
+        }
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
     }
     return RRT_OK;
 }
@@ -412,6 +462,11 @@ void rrt_render_destroy(rrt_render* render) { delete render; }
 
 int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
                         rrt_render** render) {
+    return rrt_scene_load_json_tier(ctx, path, overrides_json, seed, RRT_BUILD_FAST, scene, render);
+}
+
+int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, uint32_t build_flags,
+                             rrt_scene** scene, rrt_render** render) {
     if (!ctx || !path || !scene) return fail(RRT_ERR_INVALID, "rrt_scene_load_json: null argument");
     *scene = nullptr;
     if (render) *render = nullptr;
@@ -427,7 +482,7 @@ int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_js
     s->host = std::move(loaded.scene);
     s->materials = loaded.materials;
     s->lights = loaded.lights;
-    rc = rrt_scene_commit(s, loaded.max_prims_in_node, RRT_BUILD_FAST);
+    rc = rrt_scene_commit(s, loaded.max_prims_in_node, build_flags);
     if (rc != RRT_OK) {
         rrt_scene_destroy(s);
         return rc;

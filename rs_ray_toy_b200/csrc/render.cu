@@ -24,6 +24,7 @@
 
 #include "camera.cuh"
 #include "render.hpp"
+#include "scene_tables.cuh"
 #include "shading.cuh"
 
 namespace rrt {
@@ -256,7 +257,10 @@ __global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables 
                             contrib = ip.kind == RRT_INTEGRATOR_PATH ? p.beta * ld : ld;
                             emit_sh = true;
                             so = s.p;
-                            sd = p1 - s.p;  // Q9 fixed: t runs over the segment, t_max = 1 - eps
+                            // Tier F (Q9 fixed): t runs over the segment, t_max = 1 - eps stops just short
+                            // of the light.  Tier L: Ray::new normalises d and keeps t_max = 1 - eps
+                            // (interaction.rs:66-77), so only boxes within one unit are ever entered.
+                            sd = sc.literal ? normalize(p1 - s.p) : p1 - s.p;
                         }
                     }
                 }
@@ -450,18 +454,7 @@ __global__ void __launch_bounds__(256) exit_pupil_kernel(CameraData cam, HaltonT
 
 template <class T>
 int upload(const std::vector<T>& v, void** d, std::string* err) {
-    *d = nullptr;
-    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    RND_CUDA(cudaMalloc(d, bytes));
-    if (!v.empty()) RND_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return RRT_OK;
-}
-
-M34 m34_of(const Mat4& m) {
-    M34 r;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 4; ++j) r.m[4 * i + j] = m.m[i][j];
-    return r;
+    return upload_vector(v, d, err);
 }
 Rgb rgb_of(const double* c) { return Rgb{c[0], c[1], c[2]}; }
 
@@ -471,7 +464,7 @@ bool look_at_inverse(const double pos[3], const double look[3], const double up[
 }  // namespace
 
 struct Renderer::Impl {
-    const DeviceAggregate* agg = nullptr;
+    const RayTracer* agg = nullptr;
     int device = 0;
     CameraData cam{};
     HaltonTables ht{};
@@ -536,7 +529,7 @@ bool look_at_inverse(const double pos[3], const double look[3], const double up[
 }
 }  // namespace
 
-int Renderer::create(int device, const HostScene& scene, const DeviceAggregate* agg, const std::vector<rrt_material>& materials,
+int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
                      const std::vector<rrt_light>& lights, const double wb[6], const rrt_render_desc& d, std::string* err) {
     auto t_start = std::chrono::steady_clock::now();
     if (d.xres <= 0 || d.yres <= 0 || d.xres > 32768 || d.yres > 32768) {
@@ -746,60 +739,8 @@ int Renderer::create(int device, const HostScene& scene, const DeviceAggregate* 
 
     // ---- shading tables ----
     {
-        std::vector<PrimInfo> prims(scene.prims.size());
-        for (size_t i = 0; i < scene.prims.size(); ++i) {
-            const Primitive& p = scene.prims[i];
-            PrimInfo pi{};
-            pi.kind = p.kind == SHAPE_TRIANGLE ? 0u : 1u;
-            pi.material = p.material;
-            pi.instance = p.instance;
-            pi.shape = p.shape;
-            pi.tri = p.tri;
-            prims[i] = pi;
-        }
-        std::vector<MeshInfo> meshes(scene.meshes.size());
-        std::vector<double> mp, mn, muv;
-        std::vector<uint32_t> mvi, mni, muvi;
-        for (size_t i = 0; i < scene.meshes.size(); ++i) {
-            const TriangleMesh& m = scene.meshes[i];
-            MeshInfo mi{};
-            mi.p_off = mp.size() / 3;
-            mi.vi_off = mvi.size();
-            mi.n_off = mn.size() / 3;
-            mi.ni_off = mni.size();
-            mi.uv_off = muv.size() / 2;
-            mi.uvi_off = muvi.size();
-            mi.has_n = m.n.empty() ? 0 : 1;
-            mi.has_ni = m.ni.empty() ? 0 : 1;
-            mi.has_uv = m.uv.empty() ? 0 : 1;
-            mi.has_uvi = m.uvi.empty() ? 0 : 1;
-            mp.insert(mp.end(), m.p.begin(), m.p.end());
-            mvi.insert(mvi.end(), m.vi.begin(), m.vi.end());
-            mn.insert(mn.end(), m.n.begin(), m.n.end());
-            mni.insert(mni.end(), m.ni.begin(), m.ni.end());
-            muv.insert(muv.end(), m.uv.begin(), m.uv.end());
-            muvi.insert(muvi.end(), m.uvi.begin(), m.uvi.end());
-            meshes[i] = mi;
-        }
-        std::vector<SphereInfo> spheres(scene.spheres.size());
-        for (size_t i = 0; i < scene.spheres.size(); ++i) {
-            const Sphere& s = scene.spheres[i];
-            SphereInfo si{};
-            si.o2w = m34_of(s.obj_to_world.m);
-            si.w2o = m34_of(s.obj_to_world.inv);
-            si.radius = s.radius;
-            // Sphere::new (sphere.rs:28-47)
-            si.theta_min = std::acos(clampd(std::fmin(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
-            si.theta_max = std::acos(clampd(std::fmax(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
-            si.phi_max = clampd(s.phi_max_deg, 0.0, 360.0) * (kPi / 180.0);
-            spheres[i] = si;
-        }
-        std::vector<InstanceXf> inst(scene.instances.size());
-        for (size_t i = 0; i < scene.instances.size(); ++i) {
-            inst[i].m = m34_of(scene.instances[i].m);
-            inst[i].inv = m34_of(scene.instances[i].inv);
-            inst[i].is_identity = scene.instances[i].is_identity() ? 1 : 0;
-        }
+        int grc = upload_geometry_tables(scene, &I.sc, &I.allocations, err);
+        if (grc != RRT_OK) return grc;
         std::vector<MaterialRec> mats(materials.size());
         for (size_t i = 0; i < materials.size(); ++i) {
             const rrt_material& m = materials[i];
@@ -844,19 +785,10 @@ int Renderer::create(int device, const HostScene& scene, const DeviceAggregate* 
         }
         ShadeScene& S = I.sc;
         int rc;
-        if ((rc = I.up(prims, &S.prims, err)) != RRT_OK) return rc;
-        if ((rc = I.up(meshes, &S.meshes, err)) != RRT_OK) return rc;
-        if ((rc = I.up(mp, &S.mesh_p, err)) != RRT_OK) return rc;
-        if ((rc = I.up(mvi, &S.mesh_vi, err)) != RRT_OK) return rc;
-        if ((rc = I.up(mn, &S.mesh_n, err)) != RRT_OK) return rc;
-        if ((rc = I.up(mni, &S.mesh_ni, err)) != RRT_OK) return rc;
-        if ((rc = I.up(muv, &S.mesh_uv, err)) != RRT_OK) return rc;
-        if ((rc = I.up(muvi, &S.mesh_uvi, err)) != RRT_OK) return rc;
-        if ((rc = I.up(spheres, &S.spheres, err)) != RRT_OK) return rc;
-        if ((rc = I.up(inst, &S.instances, err)) != RRT_OK) return rc;
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
         if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
         S.n_lights = (uint32_t)lts.size();
+        S.literal = agg->literal() ? 1u : 0u;
     }
 
     // ---- path state + queues ----

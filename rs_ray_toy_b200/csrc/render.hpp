@@ -26,7 +26,7 @@ class Renderer {
 
     // make_integrator: film, camera (thick-lens focus + exit-pupil bounds), sampler tables,
     // light distribution; uploads the shading tables of `scene`.
-    int create(int device, const HostScene& scene, const DeviceAggregate* agg, const std::vector<rrt_material>& materials,
+    int create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
                const std::vector<rrt_light>& lights, const double world_bound6[6], const rrt_render_desc& desc,
                std::string* err);
     // Integrator::render for this rank's tiles

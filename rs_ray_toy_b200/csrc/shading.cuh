@@ -60,7 +60,8 @@ struct ShadeScene {
     const InstanceXf* instances;
     const MaterialRec* materials;
     const LightRec* lights;
-    uint32_t n_lights, pad;
+    uint32_t n_lights;
+    uint32_t literal;  // Tier L: instance / sphere rays are renormalised like the reference (Q6)
 };
 
 // What the integrator reads of a SurfaceInteraction (interaction.rs:95-113)
@@ -83,7 +84,7 @@ __device__ __forceinline__ void xf_surface(const M34& m, const M34& inv, Surface
 }
 
 // Rebuilds the surface frame of hit (prim_id, t, u, v) for the world ray (o, d).
-__device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
+static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
                                           Surface* out) {
     const PrimInfo pi = sc.prims[prim_id];
     V3 lo = o, ld = d;
@@ -91,6 +92,7 @@ __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id
         const InstanceXf& x = sc.instances[pi.instance];
         lo = xf_point(x.inv, o);
         ld = xf_vector(x.inv, d);
+        if (sc.literal) ld = normalize(normalize(ld));  // transform.rs:525-537 + Ray::new
     }
     Surface s;
     s.material = pi.material;
@@ -156,7 +158,8 @@ __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id
         const SphereInfo& sp = sc.spheres[pi.shape];
         // sphere.rs:127-128: the shape works on the object-space ray, but the first hit point is
         // taken on the ray it was handed (Q5a)
-        const V3 od = xf_vector(sp.w2o, ld);
+        V3 od = xf_vector(sp.w2o, ld);
+        if (sc.literal) od = normalize(normalize(od));
         V3 p = lo + ld * t;
         if (p.x == 0.0 && p.y == 0.0) p.x = 1e-5 * sp.radius;
         double phi = atan2(p.y, p.x);
@@ -208,7 +211,7 @@ __device__ __forceinline__ bool refract_dir(V3 wi, V3 n, double eta, V3* wt) {
     return true;
 }
 // reflection.rs:145-168
-__device__ double fr_dielectric(double cos_i, double eta_i, double eta_t) {
+static __device__ double fr_dielectric(double cos_i, double eta_i, double eta_t) {
     cos_i = clampd(cos_i, -1.0, 1.0);
     if (!(cos_i > 0.0)) {
         double s = eta_i;
@@ -225,7 +228,7 @@ __device__ double fr_dielectric(double cos_i, double eta_i, double eta_t) {
     return (r_parl * r_parl + r_perp * r_perp) / 2.0;
 }
 // reflection.rs:170-195
-__device__ Rgb fr_conductor(double cos_i, Rgb eta_i, Rgb eta_t, Rgb k) {
+static __device__ Rgb fr_conductor(double cos_i, Rgb eta_i, Rgb eta_t, Rgb k) {
     cos_i = clampd(cos_i, -1.0, 1.0);
     Rgb eta = eta_t / eta_i, eta_k = k / eta_i;
     double cos2 = cos_i * cos_i, sin2 = 1.0 - cos2;
@@ -242,7 +245,7 @@ __device__ Rgb fr_conductor(double cos_i, Rgb eta_i, Rgb eta_t, Rgb k) {
     return (rp + rs) * rgb(0.5);
 }
 // microfacet.rs:12-20
-__device__ double roughness_to_alpha(double roughness) {
+static __device__ double roughness_to_alpha(double roughness) {
     roughness = rmax(roughness, 1e-3);
     double x = log(roughness);
     return 1.62142 + 0.819955 * x + 0.1734 * x * x + 0.0171201 * x * x * x + 0.000640711 * x * x * x * x;
@@ -272,13 +275,13 @@ __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
     }
 }
 __device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type(l) & flags) == lobe_type(l); }
-__device__ Rgb lobe_fresnel(const Lobe& l, double cos_i) {  // reflection.rs:603-619
+static __device__ Rgb lobe_fresnel(const Lobe& l, double cos_i) {  // reflection.rs:603-619
     if (l.fresnel == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
     if (l.fresnel == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
     return rgb(1.0);
 }
 // TrowbridgeReitzDistribution (microfacet.rs:364-390)
-__device__ double tr_d(const Lobe& l, V3 wh) {
+static __device__ double tr_d(const Lobe& l, V3 wh) {
     double tan2 = tan2_theta(wh);
     if (isinf(tan2)) return 0.0;
     double cos4 = cos2_theta(wh) * cos2_theta(wh);
@@ -286,7 +289,7 @@ __device__ double tr_d(const Lobe& l, V3 wh) {
     double e = ((cp * cp) / (l.alpha_x * l.alpha_x) + (spv * spv) / (l.alpha_y * l.alpha_y)) * tan2;
     return 1.0 / (kPi * l.alpha_x * l.alpha_y * cos4 * (1.0 + e) * (1.0 + e));
 }
-__device__ double tr_lambda(const Lobe& l, V3 w) {
+static __device__ double tr_lambda(const Lobe& l, V3 w) {
     double abs_tan = fabs(tan_theta(w));
     if (isinf(abs_tan)) return 0.0;
     double cp = cos_phi(w), spv = sin_phi(w);
@@ -294,11 +297,11 @@ __device__ double tr_lambda(const Lobe& l, V3 w) {
     double a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
     return (-1.0 + sqrt(1.0 + a2t2)) / 2.0;
 }
-__device__ double tr_pdf(const Lobe& l, V3 wo, V3 wh) {  // microfacet.rs:30-36, sample_visible_area
+static __device__ double tr_pdf(const Lobe& l, V3 wo, V3 wh) {  // microfacet.rs:30-36, sample_visible_area
     return tr_d(l, wh) * (1.0 / (1.0 + tr_lambda(l, wo))) * absdot(wo, wh) / abs_cos_theta(wo);
 }
 // microfacet.rs:270-362
-__device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, double u2) {
+static __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, double u2) {
     V3 ws = normalize(v3(ax * wi.x, ay * wi.y, wi.z));
     double slope_x, slope_y;
     const double cos_t = ws.z;
@@ -339,7 +342,7 @@ __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, double u
     return normalize(v3(-slope_x, -slope_y, 1.0));
 }
 
-__device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+static __device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT: return l.r / kPi;
         case LOBE_OREN_NAYAR: {  // reflection.rs:916-941
@@ -371,7 +374,7 @@ __device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
         default: return rgb(0.0);
     }
 }
-__device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+static __device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
@@ -384,7 +387,7 @@ __device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     }
 }
 // BxDF::sample_f of each lobe; *pdf is left untouched on the early-outs (the caller zeroed it)
-__device__ Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+static __device__ Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: {  // reflection.rs:428-443
@@ -450,12 +453,12 @@ __device__ __forceinline__ V3 to_world(const Bsdf& b, V3 v) {
     return v3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
               b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-__device__ int bsdf_num_components(const Bsdf& b, uint32_t flags) {
+static __device__ int bsdf_num_components(const Bsdf& b, uint32_t flags) {
     int n = 0;
     for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches(b.lobes[i], flags) ? 1 : 0;
     return n;
 }
-__device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+static __device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     V3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);
     bool reflect = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0;
@@ -468,7 +471,7 @@ __device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     }
     return f;
 }
-__device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+static __device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
     const int matching = bsdf_num_components(b, flags);
     if (matching == 0) {
         *pdf = 0.0;
@@ -507,7 +510,7 @@ __device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf
 }
 
 // Material::compute_scattering_functions for constant-valued parameters
-__device__ void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
+static __device__ void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
     b->ns = s.shn;
     b->ss = normalize(s.shdpdu);
     b->ng = s.n;

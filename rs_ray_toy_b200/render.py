@@ -98,6 +98,8 @@ def _bind(L):
     L.rrt_scene_set_lights.argtypes = [vp, u32, vp]
     L.rrt_scene_load_json.restype = i32
     L.rrt_scene_load_json.argtypes = [vp, C.c_char_p, C.c_char_p, u64, pvp, pvp]
+    L.rrt_scene_load_json_tier.restype = i32
+    L.rrt_scene_load_json_tier.argtypes = [vp, C.c_char_p, C.c_char_p, u64, u32, pvp, pvp]
     L.rrt_scene_json_probe.restype = i32
     L.rrt_scene_json_probe.argtypes = [C.c_char_p, C.c_char_p, vp, C.POINTER(RenderDesc)]
     L.rrt_render_create.restype = i32
@@ -165,12 +167,15 @@ class Render:
         self._keep = keep
 
     @classmethod
-    def load(cls, ctx: Context, path, overrides=None, seed: int = 1) -> "Render":
-        """`deploy_render(filepath, ..)` up to the integrator: make_scene + make_integrator."""
+    def load(cls, ctx: Context, path, overrides=None, seed: int = 1, literal: bool = False) -> "Render":
+        """`deploy_render(filepath, ..)` up to the integrator: make_scene + make_integrator.
+        `literal` selects the Tier-L aggregate and integrator rules (every reference quirk kept)."""
         L = lib()
         sh, rh = C.c_void_p(), C.c_void_p()
         ov = json.dumps(overrides).encode() if overrides else None
-        capi.check(L.rrt_scene_load_json(ctx.h, str(path).encode(), ov, seed, C.byref(sh), C.byref(rh)))
+        capi.check(L.rrt_scene_load_json_tier(ctx.h, str(path).encode(), ov, seed,
+                                              capi.RRT_BUILD_LITERAL if literal else capi.RRT_BUILD_FAST,
+                                              C.byref(sh), C.byref(rh)))
         _, desc = json_probe(path, overrides)
         return cls(ctx, sh, rh, True, int(desc.xres), int(desc.yres))
 

@@ -233,12 +233,12 @@ def test_call_order_and_argument_errors(ctx):
     L = capi.lib()
     assert L.rrt_intersect(a.h, 4, None, None) == capi.RRT_ERR_INVALID
     assert L.rrt_last_error()
-    with pytest.raises(capi.RrtError) as e:     # the literal tier lives in the oracle only
+    with pytest.raises(capi.RrtError) as e:     # unknown build flags
         b = GpuAggregate(ctx)
         mb = b.add_mesh(p, idx)
         b.add_triangles(mb, 0)
-        b.commit(4, capi.RRT_BUILD_LITERAL)
-    assert e.value.status == capi.RRT_ERR_UNSUPPORTED
+        b.commit(4, 7)
+    assert e.value.status == capi.RRT_ERR_INVALID
 
 
 def test_concurrent_host_threads_share_one_aggregate(ctx):
@@ -286,3 +286,66 @@ def test_device_pointer_entry_points(ctx):
     hits = d_hits.cpu().numpy().view(HIT_DTYPE).reshape(-1)
     assert np.array_equal(hits, ref)
     assert np.array_equal(d_occ.cpu().numpy().astype(bool), ref["prim_id"] != 0xFFFFFFFF)
+
+
+# ---- Tier L: the reference's own tree, order and accept rules, every quirk kept ------------------------
+def _literal_pair(ctx, kind, n, **kw):
+    import oracle_lib as O
+    from rs_ray_toy_b200 import capi
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    if kind == "soup":
+        p, idx = scenes.soup(n, edge=kw.get("edge", 0.02))
+        ref = scenes.oracle_soup(p, idx, tier=O.TIER_L)
+        a = GpuAggregate(ctx)
+        m = a.add_mesh(p, idx)
+        a.add_triangles(m, 0)
+        rays = synth.bounce_rays(p, idx, kw.get("rays", 20000), seed=17)
+    elif kind == "cubes":
+        m_, inv = scenes.cube_instances(n, extent=kw.get("extent", 20.0))
+        ref = scenes.oracle_cubes(m_, inv, tier=O.TIER_L)
+        a = GpuAggregate(ctx)
+        mesh = a.add_mesh(synth.CUBE_P, synth.CUBE_VI, synth.CUBE_N, synth.CUBE_NI)
+        a.add_triangles(mesh, 0, instances=(m_, inv))
+        rays = synth.camera_like_rays(kw.get("rays", 20000), (0.0, 0.0, -60.0), kw.get("extent", 20.0))
+    else:
+        m_, inv = scenes.sphere_instances(n, extent=kw.get("extent", 12.0))
+        ref = scenes.oracle_spheres(m_, inv, 0.5, tier=O.TIER_L)
+        a = GpuAggregate(ctx)
+        a.add_sphere(radius=0.5, instances=(m_, inv))
+        rays = synth.camera_like_rays(kw.get("rays", 20000), (0.0, 0.0, -40.0), kw.get("extent", 12.0))
+    a.commit(4, capi.RRT_BUILD_LITERAL)
+    return a, ref, rays
+
+
+@pytest.mark.parametrize("kind,n", [("soup", 3000), ("cubes", 300), ("spheres", 1500)])
+def test_literal_tier_is_bit_exact(ctx, kind, n):
+    """RRT_BUILD_LITERAL: same HLBVH (Q1/Q2 included), same visiting order, "last accepted hit wins"
+    (Q3), instance rays renormalised (Q6), intersect_p with E2 = p2 - p1 (Q4): the primitive index, t
+    and the any-hit flags equal the oracle's literal tier bit for bit (f64, same operation order)."""
+    agg, ref, rays = _literal_pair(ctx, kind, n)
+    assert np.array_equal(agg.world_bound(), ref.world_bound())
+    r = ref.intersect(rays)
+    h = agg.intersect(rays)
+    gp = h["prim_id"].astype(np.int64)
+    gp[gp == 0xFFFFFFFF] = -1
+    assert np.array_equal(gp, r["prim"])
+    hit = r["prim"] >= 0
+    assert hit.sum() > 500
+    assert np.array_equal(h["t"][hit], r["t"][hit])
+    occ_ref, _ = ref.intersect_p(rays)
+    assert np.array_equal(agg.intersect_p(rays), occ_ref)
+    sh = synth.shadow_rays_from(rays if kind == "soup" else np.concatenate([rays[:, :3] + rays[:, 3:6] * 30.0, rays[:, 3:]], axis=1),
+                                (0.5, 0.5, 1.5) if kind == "soup" else (0.0, 30.0, 0.0))
+    occ_ref, _ = ref.intersect_p(sh)
+    assert np.array_equal(agg.intersect_p(sh), occ_ref)
+
+
+def test_literal_and_fixed_tiers_differ_where_the_survey_says(ctx):
+    """Q1 drops primitives inside treelets that split: on instanced cubes the literal aggregate misses
+    geometry the fixed tier finds."""
+    import oracle_lib as O
+    agg_l, ref_l, rays = _literal_pair(ctx, "cubes", 300)
+    m_, inv = scenes.cube_instances(300, extent=20.0)
+    agg_f = scenes.gpu_cubes(ctx, m_, inv)
+    hl, hf = agg_l.intersect(rays), agg_f.intersect(rays)
+    assert (hl["prim_id"] != hf["prim_id"]).sum() > 0

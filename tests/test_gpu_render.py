@@ -62,6 +62,23 @@ def test_config1_path_traced_sample_scene(ctx, tmp_path):
     assert out["rmse"] < 1e-6, out
 
 
+def test_config1_literal_tier(ctx, tmp_path):
+    """Config 1 in the LITERAL tier: the reference's own tree and accept rules, Q9 shadow rays, Q6
+    instance rays — against the oracle with every quirk flag at its reference setting."""
+    import oracle_lib as O
+    path = synth.scene_c1(str(tmp_path / "c1"), nsamp=9)
+    ref = S.load(path, tier=O.TIER_L).render(seed=1, want_dump=True)
+    gpu = Render.load(ctx, path, seed=1, literal=True)
+    gpu.enable_hit_dump()
+    gpu.run()
+    out = compare(gpu, ref)
+    assert out["rmse"] < 1e-6, out
+    # and it is a different image from the fixed tier (shadows: Q4 / Q9)
+    fixed = Render.load(ctx, path, seed=1)
+    fixed.run()
+    assert rel_rmse(fixed.film(), ref["rgb"]) > 1e-3
+
+
 def test_config1_seed_changes_image_and_identity_perms(ctx, tmp_path):
     path = synth.scene_c1(str(tmp_path / "c1"), xres=160, yres=90, nsamp=9)
     imgs = {}

@@ -119,3 +119,32 @@ def test_golden_vectors(name):
     assert (r["t"] == g["t"]).all()
     assert (r["uv"] == g["uv"]).all()
     assert (occ == g["occluded"]).all()
+
+
+def test_product_literal_hlbvh_builder_matches_the_oracle():
+    """The product's own restatement of BVHAccel::new / HLBVH (csrc/bvh_hlbvh.cpp, host only) against the
+    oracle's literal tier: same flattened nodes (bounds, offsets, axes) and same reordered primitive
+    list, Q1 duplicates and the Q2-skewed upper tree included."""
+    import ctypes as C
+    from rs_ray_toy_b200 import capi
+    L = capi.lib()
+    L.rrt_hlbvh_literal_probe.restype = C.c_int
+    L.rrt_hlbvh_literal_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    for n, edge, max_prims in ((37, 0.2, 4), (5000, 0.02, 4), (20000, 0.01, 4), (3000, 0.05, 2), (3000, 0.05, 7)):
+        p, idx = scenes.soup(n, edge=edge, seed=11 + n)
+        ref = scenes.oracle_soup(p, idx, tier=O.TIER_L, max_prims=max_prims)
+        rb, rm, ro = ref.nodes()
+        tri = p[idx]                                   # [n, 3, 3]
+        bounds = np.concatenate([tri.min(axis=1), tri.max(axis=1)], axis=1).copy()
+        cap = 2 * n + 8
+        nb, nm, no = np.zeros((cap, 6)), np.zeros((cap, 3), dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        cnt = C.c_uint32()
+        capi.check(L.rrt_hlbvh_literal_probe(n, bounds.ctypes.data, max_prims, cap, C.byref(cnt), nb.ctypes.data,
+                                             nm.ctypes.data, no.ctypes.data))
+        assert cnt.value == len(rm)
+        assert np.array_equal(nm[: cnt.value], rm)
+        assert np.array_equal(nb[: cnt.value], rb)
+        assert np.array_equal(no, ro)
+        if n >= 3000 and max_prims == 4:
+            assert len(set(ro.tolist())) < n           # Q1 really dropped primitives here
