@@ -114,8 +114,14 @@ __device__ bool prim_intersect_literal(const ShadeScene& sc, uint32_t prim, V3 o
 // Shape::intersect_p: Triangle uses E2 = p2 - p1 (Q4, triangle.rs:175) and ignores t_max
 __device__ bool prim_intersect_p_literal(const ShadeScene& sc, uint32_t prim, V3 o, V3 d) {
     const PrimInfo pi = sc.prims[prim];
+    if (pi.kind != 0) {
+        // sphere.rs:50-109: for a full sphere the any-hit accept rule is the closest-hit one (the clip
+        // test runs on an uninitialised p_hit = 0, phi = 0 and never fires, Q5c)
+        double t, u, v;
+        return prim_intersect_literal(sc, prim, o, d, &t, &u, &v);
+    }
     if (pi.instance >= 0) xf_ray_literal(sc.instances[pi.instance].inv, &o, &d);
-    if (pi.kind == 0) {
+    {
         const MeshInfo mi = sc.meshes[pi.shape];
         const uint32_t* vi = sc.mesh_vi + mi.vi_off + 3ull * pi.tri;
         const double* pb = sc.mesh_p + 3 * mi.p_off;
@@ -134,8 +140,6 @@ __device__ bool prim_intersect_p_literal(const ShadeScene& sc, uint32_t prim, V3
         const double tt = f * dot(E2, Q);
         return !(tt < 0.0000001);
     }
-    double t, u, v;
-    return prim_intersect_literal(sc, prim, o, d, &t, &u, &v);  // sphere.rs:50-109: same accept rule for full spheres
 }
 
 template <bool ANY>
