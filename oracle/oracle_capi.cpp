@@ -389,6 +389,21 @@ RenderSetup& setup_of(void* s) {
 
 extern "C" {
 
+// Debug ray log (rt_render.hpp raylog()): begin, render single-threaded, then take the records.
+void orc_raylog_begin() {
+    static std::vector<double> store;
+    store.clear();
+    raylog() = &store;
+}
+uint64_t orc_raylog_take(double* out, uint64_t cap_records) {
+    std::vector<double>* v = raylog();
+    raylog() = nullptr;
+    if (!v) return 0;
+    uint64_t n = v->size() / 10;
+    if (out) std::memcpy(out, v->data(), sizeof(double) * 10 * std::min(n, cap_records));
+    return n;
+}
+
 // Material table.  26 doubles per material:
 //  0 kind (MaterialKind) | 1-3 kd | 4-6 ks | 7-9 kr | 10-12 kt | 13-15 metal eta | 16-18 metal k |
 //  19 sigma | 20 roughness | 21 u_roughness (<0 = None) | 22 v_roughness | 23 glass eta | 24 remap | 25 pad

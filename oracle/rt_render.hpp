@@ -30,6 +30,14 @@ struct HitDump {
     double t, weight;
 };
 
+// Optional ray log for debugging a parity failure (tools/debug_render_rays.py): every Scene::intersect /
+// unoccluded call appends 10 doubles {kind 0 closest / 1 shadow, o, d, t_max, result prim or occluded, t}.
+// Single-threaded use only.
+inline std::vector<double>*& raylog() {
+    static std::vector<double>* g = nullptr;
+    return g;
+}
+
 struct RenderScene {
     const Geometry* geom = nullptr;
     const BVH* bvh = nullptr;
@@ -40,10 +48,17 @@ struct RenderScene {
     // Scene::intersect (scene.rs:69-72)
     bool intersect(Ray& r, SI* si, RenderStats* st) const {
         HitRecord h;
-        return bvh->intersect(r, &h, si, st ? &st->closest : nullptr);
+        return intersect_with_record(r, si, &h, st);
     }
     bool intersect_with_record(Ray& r, SI* si, HitRecord* h, RenderStats* st) const {
-        return bvh->intersect(r, h, si, st ? &st->closest : nullptr);
+        const Ray in = r;
+        const bool hit = bvh->intersect(r, h, si, st ? &st->closest : nullptr);
+        if (raylog()) {
+            const double rec[10] = {0.0, in.o.x, in.o.y, in.o.z, in.d.x, in.d.y, in.d.z, in.t_max,
+                                    hit ? (double)h->prim : -1.0, hit ? r.t_max : 0.0};
+            raylog()->insert(raylog()->end(), rec, rec + 10);
+        }
+        return hit;
     }
     // VisibilityTester::unoccluded (lights/mod.rs:64-66) over spawn_ray_to_si (interaction.rs:66-77):
     // p_error is always zero, so both offset origins are the points themselves (geometry.rs:721-749).
@@ -58,7 +73,12 @@ struct RenderScene {
             r = ray_new(p0, d, 1.0 - SHADOW_EPSILON, 0.0);  // Q9: d normalised, t_max left at 1 - eps
         }
         if (st) st->shadow_rays += 1;
-        return !bvh->intersect_p(r, st ? &st->any : nullptr);
+        const bool occ = bvh->intersect_p(r, st ? &st->any : nullptr);
+        if (raylog()) {
+            const double rec[10] = {1.0, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.t_max, occ ? 1.0 : 0.0, 0.0};
+            raylog()->insert(raylog()->end(), rec, rec + 10);
+        }
+        return !occ;
     }
     // Light::sample_li (point.rs:55-77, distant.rs:69-93)
     Rgb sample_li(const Light& l, V3 p, V3* wi, double* pdf, V3* p1) const {

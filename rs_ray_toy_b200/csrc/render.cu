@@ -202,6 +202,11 @@ __global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables 
             p.first_prim = found ? (int32_t)h.prim_id : -1;
             p.first_t = found ? h.t : 0.0;
         }
+#ifdef RRT_DEBUG_PIXEL_X  // diagnostic build only (tools/debug_render_rays.py --gpu-log): every extension ray of one pixel
+        if (p.px == RRT_DEBUG_PIXEL_X && p.py == RRT_DEBUG_PIXEL_Y)
+            printf("GPURAY s %u b %u o %a %a %a d %a %a %a prim %d t %a\n", p.sample, p.bounces, p.o.x, p.o.y, p.o.z, p.d.x,
+                   p.d.y, p.d.z, found ? (int)h.prim_id : -1, found ? h.t : 0.0);
+#endif
         // path.rs:79-93: no emitted radiance in scope (Q22, no infinite lights); stop on escape / depth
         bool alive = found && !(ip.kind == RRT_INTEGRATOR_PATH && p.bounces >= ip.max_depth);
         if (alive) {
