@@ -73,33 +73,41 @@ RRT_HD bool intersect_spherical_element(double radius, double z_center, const Ra
     *n = faceforward(normalize_n(*n), -ray.d);
     return true;
 }
+// One interface of trace_lenses_from_film's loop (camera.rs:163-214).  `eta_t` is the index on the far side:
+// el[i-1].eta when i > 0 and that is non-zero, else 1.  The wavefront generate kernel calls this directly so
+// that the 32 lanes of a warp can sit at 32 different interfaces.
+RRT_HD bool lens_step_from_film(const LensElement& e, double eta_t, double* element_z, RayD* rp) {
+    RayD& r = *rp;
+    *element_z -= e.thickness;
+    double t = 0.0;
+    V3 n = v3(0, 0, 0);
+    const bool is_stop = e.curvature_radius == 0.0;
+    if (is_stop) {
+        if (r.d.z >= 0.0) return false;
+        t = (*element_z - r.o.z) / r.d.z;
+    } else {
+        if (!intersect_spherical_element(e.curvature_radius, *element_z + e.curvature_radius, r, &t, &n)) return false;
+    }
+    V3 p = r.o + r.d * t;
+    double r2 = p.x * p.x + p.y * p.y;
+    if (r2 >= e.aperture_radius * e.aperture_radius) return false;
+    r.o = p;
+    if (!is_stop) {
+        V3 w;
+        double eta_i = e.eta;
+        if (!refract(normalize(-r.d), n, eta_i / eta_t, &w)) return false;
+        r.d = w;
+    }
+    return true;
+}
 // camera.rs:156-219
 RRT_HD bool trace_lenses_from_film(const CameraData& c, const RayD& r_camera, RayD* r_out) {
     double element_z = 0.0;
     RayD r = flip_z(r_camera);
     for (int i = c.n_elements - 1; i >= 0; --i) {
         const LensElement e = c.el[i];
-        element_z -= e.thickness;
-        double t = 0.0;
-        V3 n = v3(0, 0, 0);
-        const bool is_stop = e.curvature_radius == 0.0;
-        if (is_stop) {
-            if (r.d.z >= 0.0) return false;
-            t = (element_z - r.o.z) / r.d.z;
-        } else {
-            if (!intersect_spherical_element(e.curvature_radius, element_z + e.curvature_radius, r, &t, &n)) return false;
-        }
-        V3 p = r.o + r.d * t;
-        double r2 = p.x * p.x + p.y * p.y;
-        if (r2 >= e.aperture_radius * e.aperture_radius) return false;
-        r.o = p;
-        if (!is_stop) {
-            V3 w;
-            double eta_i = e.eta;
-            double eta_t = (i > 0 && c.el[i - 1].eta != 0.0) ? c.el[i - 1].eta : 1.0;
-            if (!refract(normalize(-r.d), n, eta_i / eta_t, &w)) return false;
-            r.d = w;
-        }
+        const double eta_t = (i > 0 && c.el[i - 1].eta != 0.0) ? c.el[i - 1].eta : 1.0;
+        if (!lens_step_from_film(e, eta_t, &element_z, &r)) return false;
     }
     *r_out = flip_z(r);
     return true;
@@ -146,27 +154,37 @@ RRT_HD void sample_exit_pupil(const CameraData& c, double fx, double fy, P2 lens
     *p_rear = v3(cos_t * lx - sin_t * ly, sin_t * lx + cos_t * ly, lens_rear_z(c));
     *area = (pb.x1 - pb.x0) * (pb.y1 - pb.y0);
 }
-// RealisticCamera::generate_ray (camera.rs:534-580): world-space ray + weight
-RRT_HD double generate_ray(const CameraData& c, P2 p_film_raster, P2 p_lens, RayD* ray) {
+// RealisticCamera::generate_ray (camera.rs:534-580) in three pieces, so that the generate kernel can run the
+// lens trace between them one interface at a time: the film-side ray, the weight, the world-space ray.
+RRT_HD void begin_film_ray(const CameraData& c, P2 p_film_raster, P2 p_lens, RayD* r_film, double* area) {
     P2 s = {p_film_raster.x / (double)c.xres, p_film_raster.y / (double)c.yres};
     double px = lerpd(s.x, c.physical_extent.x0, c.physical_extent.x1);
     double py = lerpd(s.y, c.physical_extent.y0, c.physical_extent.y1);
     V3 p_film = v3(-px, py, 0.0);
     V3 p_rear;
-    double area;
-    sample_exit_pupil(c, p_film.x, p_film.y, p_lens, &p_rear, &area);
-    RayD r_film;
-    r_film.o = p_film;
-    r_film.d = normalize(p_rear - p_film);
-    RayD r;
-    if (!trace_lenses_from_film(c, r_film, &r)) return 0.0;
-    // camera_to_world.t(ray) normalises d twice; generate_ray normalises it once more
-    ray->o = xf_point(c.camera_to_world, r.o);
-    ray->d = normalize(normalize(normalize(xf_vector(c.camera_to_world, r.d))));
-    double cos_t = normalize(r_film.d).z;
+    sample_exit_pupil(c, p_film.x, p_film.y, p_lens, &p_rear, area);
+    r_film->o = p_film;
+    r_film->d = normalize(p_rear - p_film);
+}
+RRT_HD double film_ray_weight(const CameraData& c, double r_film_dz_normalized, double area) {
+    double cos_t = r_film_dz_normalized;
     double cos4 = (cos_t * cos_t) * (cos_t * cos_t);
     if (c.simple_weighting) return cos4 * area / ((c.exit_pupil[0].x1 - c.exit_pupil[0].x0) * (c.exit_pupil[0].y1 - c.exit_pupil[0].y0));
     return (c.shutter_close - c.shutter_open) * (cos4 * area) / lens_rear_z(c) * lens_rear_z(c);
+}
+RRT_HD void camera_ray_to_world(const CameraData& c, const RayD& r, RayD* ray) {
+    // camera_to_world.t(ray) normalises d twice; generate_ray normalises it once more
+    ray->o = xf_point(c.camera_to_world, r.o);
+    ray->d = normalize(normalize(normalize(xf_vector(c.camera_to_world, r.d))));
+}
+RRT_HD double generate_ray(const CameraData& c, P2 p_film_raster, P2 p_lens, RayD* ray) {
+    RayD r_film;
+    double area;
+    begin_film_ray(c, p_film_raster, p_lens, &r_film, &area);
+    RayD r;
+    if (!trace_lenses_from_film(c, r_film, &r)) return 0.0;
+    camera_ray_to_world(c, r, ray);
+    return film_ray_weight(c, normalize(r_film.d).z, area);
 }
 // RealisticCamera::generate_ray_differential (camera.rs:582-628).  The differentials themselves
 // feed only texture filtering (out of scope: constant textures); what survives is the weight,

@@ -110,82 +110,216 @@ __device__ __forceinline__ uint32_t queue_slot(uint32_t* counter, bool want) {
 }
 
 // ---- generate ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) generate_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms,
-                                                        FilmParams film, IntegratorParams ip, Frame fr, uint64_t base,
-                                                        uint32_t count, Path* __restrict__ paths, Queues q) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool emit = false;
-    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 0);
-    if (i < count) {
-        const uint64_t s = base + i;
-        const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
-        const uint32_t tslot = (uint32_t)(s / per_tile);
-        const uint32_t within = (uint32_t)(s % per_tile);
-        const uint32_t pix = within / ip.n_samples, sn = within % ip.n_samples + 1u;  // sample numbers 1..nsamp-1 (Q10)
-        const uint32_t tile = fr.tiles[tslot];
-        const int64_t px = film.sb[0] + (int64_t)(tile % fr.n_tiles_x) * kTile + (pix % kTile);
-        const int64_t py = film.sb[1] + (int64_t)(tile / fr.n_tiles_x) * kTile + (pix / kTile);
-        Path p;
-        p.state = 0;
-        bool valid = px < film.sb[2] && py < film.sb[3] && px >= 0 && px < film.xres && py >= 0 && py < film.yres;
-        if (valid && fr.use_crop) valid = px >= fr.crop[0] && px < fr.crop[2] && py >= fr.crop[1] && py < fr.crop[3];
-        if (valid) {
-            const uint64_t hidx = halton_index(ht, px, py, sn);
-            // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
-            const P2 pf = {(double)px + halton_sample(ht, perms, hidx, 0), (double)py + halton_sample(ht, perms, hidx, 1)};
-            const P2 pl = {halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
-            RayD ray;
-            ray.o = v3(0, 0, 0);
-            ray.d = v3(0, 0, 0);
-            const double w = generate_ray_weighted(cam, pf, pl, &ray);
-            p.o = ray.o;
-            p.d = ray.d;
-            p.beta = rgb(1.0);
-            p.L = rgb(0.0);
-            p.eta_scale = 1.0;
-            p.pfx = pf.x;
-            p.pfy = pf.y;
-            p.weight = w;
-            p.hidx = hidx;
-            p.dim = 5;
-            p.bounces = 0;
-            p.px = (int32_t)px;
-            p.py = (int32_t)py;
-            p.sample = sn;
-            p.first_prim = w > 0.0 ? -1 : -2;
-            p.first_t = 0.0;
-            p.pad = 0;
-            if (w > 0.0) {
-                p.state = 1;
-                emit = true;
-                ro = ray.o;
-                rd = ray.d;
-                atomicAdd(q.counters + 4, 1u);  // camera rays
-            } else {
-                p.state = 2;
-                atomicAdd(q.counters + 8, 1u);  // zero-weight samples
+// get_camerasample + RealisticCamera::generate_ray_differential for a chunk of camera samples.  Two thirds of
+// the samples of the sample scenes are vignetted somewhere inside the 13-interface lens, and a surviving sample
+// traces three to five rays through it (camera.rs:582-628), so one-thread-per-sample leaves most lanes idle
+// (measured: 13.5 of 32 active in the lens loop).  Here a lane is a small state machine — (sample, which of the
+// five rays, interface index) — every trip of the loop advances every lane by ONE interface, and lanes whose
+// sample is finished take the next sample from a chunk-wide cursor.  Per-sample arithmetic is unchanged.
+#ifndef RRT_GEN_MINBLOCKS
+#define RRT_GEN_MINBLOCKS 5
+#endif
+#ifndef RRT_GEN_REFILL
+#define RRT_GEN_REFILL 24
+#endif
+enum GenStage : int { GEN_MAIN = 0, GEN_XP = 1, GEN_XM = 2, GEN_YP = 3, GEN_YM = 4 };
+
+__global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
+    generate_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film, IntegratorParams ip,
+                    Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    // lens table in shared memory: lanes index it at different interfaces (a constant-bank read would serialise)
+    __shared__ LensElement s_el[kMaxLensElements];
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_el[k] = cam.el[k];
+    __syncthreads();
+    uint32_t* const cursor = q.counters + 3;
+
+    bool have = false, exhausted = false;
+    uint32_t slot = 0, sn = 0, n_camera = 0, n_zero = 0;
+    int32_t px = 0, py = 0;
+    int stage = GEN_MAIN, ei = 0;
+    uint64_t hidx = 0;
+    P2 pf = {0, 0}, pl = {0, 0};
+    RayD r = {v3(0, 0, 0), v3(0, 0, 0)};
+    double element_z = 0.0, area = 0.0, film_dz = 0.0, wt = 0.0;
+
+    bool need_begin = false;
+
+    for (;;) {
+        // ---- gate: lanes without a sample and lanes between two lens traces wait until enough of them have
+        // gathered (or nobody is left to step), so that the set-up code below runs with a well-filled warp ----
+        const unsigned waiting = __ballot_sync(FULL, !have || need_begin);
+        if (__popc(waiting) >= RRT_GEN_REFILL || waiting == FULL) {
+            const unsigned idle = __ballot_sync(FULL, !have);
+            if (idle != 0u && !exhausted) {
+                const int want = __popc(idle);
+                uint32_t first = 0;
+                if (lane == 0) first = atomicAdd(cursor, (uint32_t)want);
+                first = __shfl_sync(FULL, first, 0);
+                if ((uint64_t)first + (uint64_t)want >= count) exhausted = true;
+                const uint64_t mine = (uint64_t)first + (uint64_t)__popc(idle & ((1u << lane) - 1u));
+                if (!have && mine < count) {
+                    slot = (uint32_t)mine;
+                    const uint64_t s = base + slot;
+                    const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
+                    const uint32_t tslot = (uint32_t)(s / per_tile);
+                    const uint32_t within = (uint32_t)(s % per_tile);
+                    const uint32_t pix = within / ip.n_samples;
+                    sn = within % ip.n_samples + 1u;  // sample numbers 1..nsamp-1 (Q10)
+                    const uint32_t tile = fr.tiles[tslot];
+                    const int64_t x = film.sb[0] + (int64_t)(tile % fr.n_tiles_x) * kTile + (pix % kTile);
+                    const int64_t y = film.sb[1] + (int64_t)(tile / fr.n_tiles_x) * kTile + (pix / kTile);
+                    bool valid = x < film.sb[2] && y < film.sb[3] && x >= 0 && x < film.xres && y >= 0 && y < film.yres;
+                    if (valid && fr.use_crop) valid = x >= fr.crop[0] && x < fr.crop[2] && y >= fr.crop[1] && y < fr.crop[3];
+                    if (!valid) {
+                        paths[slot].state = 0;  // no sample in this slot
+                    } else {
+                        px = (int32_t)x;
+                        py = (int32_t)y;
+                        hidx = halton_index(ht, x, y, sn);
+                        // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
+                        pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
+                        pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                        have = true;
+                        stage = GEN_MAIN;
+                        need_begin = true;
+                    }
+                }
+            }
+            // start one of the five lens traces of the sample (generate_ray up to trace_lenses_from_film)
+            if (have && need_begin) {
+                const P2 pfr = stage == GEN_MAIN ? pf
+                             : stage == GEN_XP ? P2{pf.x + 0.05, pf.y}
+                             : stage == GEN_XM ? P2{pf.x + -0.05, pf.y}
+                             : stage == GEN_YP ? P2{pf.x, pf.y + 0.05} : P2{pf.x, pf.y + -0.05};
+                RayD r_film;
+                begin_film_ray(cam, pfr, pl, &r_film, &area);
+                film_dz = normalize(r_film.d).z;
+                r = flip_z(r_film);  // trace_lenses_from_film's first statement
+                element_z = 0.0;
+                ei = cam.n_elements - 1;
+                need_begin = false;
             }
         }
-        paths[i] = p;
+        if (__ballot_sync(FULL, have) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- one interface for every lane that holds a sample ----
+        bool emit = false;
+        if (have && !need_begin) {
+            bool blocked = false, through = false;
+            {
+                const LensElement e = s_el[ei];
+                const double eta_prev = ei > 0 ? s_el[ei - 1].eta : 0.0;
+                const double eta_t = (ei > 0 && eta_prev != 0.0) ? eta_prev : 1.0;
+                if (!lens_step_from_film(e, eta_t, &element_z, &r)) blocked = true;
+                else if (--ei < 0) through = true;
+            }
+            if (blocked || through) {
+                // generate_ray returns 0 for a blocked ray, the weight otherwise; generate_ray_differential
+                // (camera.rs:582-628) tests each of those returns against 0.0
+                const double w = through ? film_ray_weight(cam, film_dz, area) : 0.0;
+                const bool ok = w != 0.0;
+                bool done = false;
+                double final_w = 0.0;
+                if (stage == GEN_MAIN) {
+                    RayD world = {v3(0, 0, 0), v3(0, 0, 0)};
+                    if (ok) camera_ray_to_world(cam, flip_z(r), &world);
+                    paths[slot].o = world.o;
+                    paths[slot].d = world.d;
+                    wt = w;
+                    done = !ok;
+                    stage = GEN_XP;
+                } else if (stage == GEN_XP) {
+                    stage = ok ? GEN_YP : GEN_XM;
+                } else if (stage == GEN_XM) {
+                    done = !ok;
+                    stage = GEN_YP;
+                } else if (stage == GEN_YP) {
+                    done = ok;
+                    final_w = wt;
+                    stage = GEN_YM;
+                } else {
+                    done = true;
+                    final_w = ok ? wt : 0.0;
+                }
+                need_begin = !done;
+                if (done) {
+                    Path* P = paths + slot;
+                    P->beta = rgb(1.0);
+                    P->L = rgb(0.0);
+                    P->eta_scale = 1.0;
+                    P->pfx = pf.x;
+                    P->pfy = pf.y;
+                    P->weight = final_w;
+                    P->hidx = hidx;
+                    P->dim = 5;
+                    P->bounces = 0;
+                    P->px = px;
+                    P->py = py;
+                    P->sample = sn;
+                    P->first_prim = final_w > 0.0 ? -1 : -2;
+                    P->first_t = 0.0;
+                    P->pad = 0;
+                    if (final_w > 0.0) {
+                        P->state = 1;
+                        emit = true;
+                        n_camera += 1;
+                    } else {
+                        P->state = 2;
+                        n_zero += 1;
+                    }
+                    have = false;
+                }
+            }
+        }
+        // ---- camera rays of the samples that finished in this trip (warp-uniform point) ----
+        const uint32_t es = queue_slot(q.counters + 0, emit);
+        if (emit) {
+            write_ray(q.ext_rays[0] + es, paths[slot].o, paths[slot].d, kInfD);
+            q.ext_path[0][es] = slot;
+        }
     }
-    const uint32_t slot = queue_slot(q.counters + 0, emit);
-    if (emit) {
-        write_ray(q.ext_rays[0] + slot, ro, rd, kInfD);
-        q.ext_path[0][slot] = i;
+    // statistics: one atomic per warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_camera += __shfl_xor_sync(FULL, n_camera, off);
+        n_zero += __shfl_xor_sync(FULL, n_zero, off);
+    }
+    if (lane == 0) {
+        if (n_camera) atomicAdd(q.counters + 4, n_camera);
+        if (n_zero) atomicAdd(q.counters + 8, n_zero);
     }
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double next_1d(const HaltonTables& ht, const uint16_t* perms, Path& p) {
+// The part of a Path the shade kernel works on: it reads and writes these fields only, the rest of the 200-byte
+// record (film position, weight, radiance, pixel) stays in memory.
+struct PathCore {
+    V3 o, d;
+    Rgb beta;
+    double eta_scale;
+    uint64_t hidx;
+    uint32_t dim, bounces;
+};
+template <class S>
+__device__ __forceinline__ double next_1d(const HaltonTables& ht, const uint16_t* perms, S& p) {
     return halton_sample(ht, perms, p.hidx, p.dim++);
 }
-__device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* perms, Path& p) {
+template <class S>
+__device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* perms, S& p) {
     P2 u = {halton_sample(ht, perms, p.hidx, p.dim), halton_sample(ht, perms, p.hidx, p.dim + 1)};
     p.dim += 2;
     return u;
 }
 
-__global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
+#ifndef RRT_SHADE_MINBLOCKS
+#define RRT_SHADE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
                                                      IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
     const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = q.counters[cur];
@@ -195,16 +329,24 @@ __global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables 
     uint32_t pid = 0;
     if (qi < n) {
         pid = q.ext_path[cur][qi];
-        Path p = paths[pid];
+        Path* const P = paths + pid;
+        PathCore p;
+        p.o = P->o;
+        p.d = P->d;
+        p.beta = P->beta;
+        p.eta_scale = P->eta_scale;
+        p.hidx = P->hidx;
+        p.dim = P->dim;
+        p.bounces = P->bounces;
         const rrt_hit h = q.hits[qi];
         const bool found = h.prim_id != RRT_NO_HIT;
         if (p.bounces == 0) {
-            p.first_prim = found ? (int32_t)h.prim_id : -1;
-            p.first_t = found ? h.t : 0.0;
+            P->first_prim = found ? (int32_t)h.prim_id : -1;
+            P->first_t = found ? h.t : 0.0;
         }
 #ifdef RRT_DEBUG_PIXEL_X  // diagnostic build only (tools/debug_render_rays.py --gpu-log): every extension ray of one pixel
-        if (p.px == RRT_DEBUG_PIXEL_X && p.py == RRT_DEBUG_PIXEL_Y)
-            printf("GPURAY s %u b %u o %a %a %a d %a %a %a prim %d t %a\n", p.sample, p.bounces, p.o.x, p.o.y, p.o.z, p.d.x,
+        if (P->px == RRT_DEBUG_PIXEL_X && P->py == RRT_DEBUG_PIXEL_Y)
+            printf("GPURAY s %u b %u o %a %a %a d %a %a %a prim %d t %a\n", P->sample, p.bounces, p.o.x, p.o.y, p.o.z, p.d.x,
                    p.d.y, p.d.z, found ? (int)h.prim_id : -1, found ? h.t : 0.0);
 #endif
         // path.rs:79-93: no emitted radiance in scope (Q22, no infinite lights); stop on escape / depth
@@ -312,8 +454,16 @@ __global__ void __launch_bounds__(128) shade_kernel(ShadeScene sc, HaltonTables 
                 }
             }
         }
-        if (!alive) p.state = 2;
-        paths[pid] = p;
+        if (alive) {
+            P->o = p.o;
+            P->d = p.d;
+            P->beta = p.beta;
+            P->eta_scale = p.eta_scale;
+            P->bounces = p.bounces;
+        } else {
+            P->state = 2;
+        }
+        P->dim = p.dim;
     }
     const uint32_t es = queue_slot(q.counters + (cur ^ 1), emit_ext);
     if (emit_ext) {
@@ -471,6 +621,7 @@ bool look_at_inverse(const double pos[3], const double look[3], const double up[
 struct Renderer::Impl {
     const RayTracer* agg = nullptr;
     int device = 0;
+    int sm_count = 148;
     CameraData cam{};
     HaltonTables ht{};
     FilmParams film{};
@@ -587,6 +738,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     Impl& I = *impl_;
     I.agg = agg;
     I.device = device;
+    cudaDeviceGetAttribute(&I.sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (I.sm_count <= 0) I.sm_count = 148;
     xres_ = d.xres;
     yres_ = d.yres;
     RND_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
@@ -884,8 +1037,9 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
     for (uint64_t base = 0; base < total; base += kChunk) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(kChunk, total - base);
         RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
-        generate_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count,
-                                                                    I.d_paths, I.q);
+        // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
+        const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
+        generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q);
         launches += 1;
         int cur = 0;
         for (uint32_t r = 0; r < rounds; ++r) {
