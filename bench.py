@@ -193,7 +193,7 @@ PT_CONFIGS = {
 }
 
 
-def path_traced(args, ctx, rank, world, local_rank, barrier):
+def path_traced(args, ctx, rank, world, local_rank, barrier, config):
     """Second half of BASELINE.json's metric: one path-traced frame, its 16x16 sample tiles dealt
     t % world == rank over the ranks (scene replicated), films summed onto rank 0 over NCCL.
     Strong scaling: the frame is fixed, value = camera samples of the whole frame / max-over-ranks time."""
@@ -203,7 +203,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier):
     from rs_ray_toy_b200 import parallel, synth
     from rs_ray_toy_b200.render import Render
     t_setup = time.perf_counter()
-    if args.path_config == "c4":
+    if config == "c4":
         d = tempfile.mkdtemp(prefix=f"rrt_c4_{rank}_")
         path = synth.scene_c4(d)
         r = Render.load(ctx, path, seed=1)
@@ -211,8 +211,8 @@ def path_traced(args, ctx, rank, world, local_rank, barrier):
     else:
         keep, r = synth.scene_c5_api(ctx)
     setup_s = time.perf_counter() - t_setup
-    frames = max(1, min(args.steps, 3))
-    launches0 = ctx.launch_count
+    # config 5 is 2.1 G camera samples (about 7 s on one B200): one timed frame after a warm-up on a 1/64 crop
+    frames = max(1, min(args.steps, 3)) if config == "c4" else 1
 
     def frame():
         r.clear()
@@ -220,7 +220,15 @@ def path_traced(args, ctx, rank, world, local_rank, barrier):
         if world > 1:
             parallel.reduce_film(r, dst=0)
 
-    frame()  # warm-up frame
+    if config == "c4":
+        frame()  # warm-up frame
+    else:
+        r.clear()
+        r.run(tile_mod=world, tile_rank=rank, crop=(1680, 945, 2160, 1215))
+        if world > 1:
+            parallel.reduce_film(r, dst=0)
+        r.clear()
+    launches0 = ctx.launch_count
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -245,7 +253,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier):
         out = {
             "metric": "Msamples/s path-traced", "unit": "Msamples/s", "value": samples / (dt / frames) / 1e6,
             "ms_per_frame": dt / frames * 1e3, "frames": frames, "n_gpus": world, "scaling": "strong",
-            "config": {"workload": PT_CONFIGS[args.path_config], "parallelism": f"16x16 sample tiles dealt t % {world} == rank, "
+            "config": {"workload": PT_CONFIGS[config], "parallelism": f"16x16 sample tiles dealt t % {world} == rank, "
                        "scene replicated, one NCCL reduce(sum) of the 4-f64-per-pixel film per frame"},
             "samples_per_frame": samples, "camera_rays": cam, "extension_rays": ext, "shadow_rays": sh,
             "rays_per_sample": (ext + sh) / max(samples, 1.0), "mean_bounces": bnc / max(cam, 1.0),
@@ -254,7 +262,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier):
             "image_mean_rgb": [float(x) for x in img.mean(axis=(0, 1))],
             "dtype": "f64 shading and film, fp32 box culling",
         }
-        if world == 1 and not args.no_cpu_baseline and args.path_config == "c4":
+        if world == 1 and not args.no_cpu_baseline and config == "c4":
             sys.path.insert(0, str(ROOT / "tests"))
             import oracle_lib as O
             import oracle_scene as S
@@ -298,8 +306,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=N_RAYS, help=argparse.SUPPRESS)
-    ap.add_argument("--path-config", default="c4", choices=["c4", "c5", "none"],
-                    help="second half of the metric: path-traced Msamples/s on config 4 (default) or config 5")
+    ap.add_argument("--path-config", default="both", choices=["both", "c4", "c5", "none"],
+                    help="second half of the metric: path-traced Msamples/s on config 4 (1080p, 64 spp) and config 5 "
+                         "(4K, 256 spp, the multi-GPU configuration)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -387,7 +396,12 @@ def main():
     # free the ray batch before the frame renders
     del d_rays, d_hits
     torch.cuda.empty_cache()
-    pt = path_traced(args, ctx, rank, world, local_rank, barrier) if args.path_config != "none" else None
+    del agg
+    pt = pt5 = None
+    if args.path_config in ("both", "c4"):
+        pt = path_traced(args, ctx, rank, world, local_rank, barrier, "c4")
+    if args.path_config in ("both", "c5"):
+        pt5 = path_traced(args, ctx, rank, world, local_rank, barrier, "c5")
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -412,6 +426,7 @@ def main():
             "scene": stats,
         }
         line["path_traced"] = pt
+        line["path_traced_4k"] = pt5
         if not args.no_cpu_baseline and world == 1:
             n_sample = 1 << 22
             sample = synth.bounce_rays(p, idx, n_sample, seed=synth.SEED_C3_RAYS)

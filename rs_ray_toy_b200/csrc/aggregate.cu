@@ -136,15 +136,6 @@ __device__ __forceinline__ bool slab(const RayF& r, float lox, float hix, float 
     return tmin <= tmax;
 }
 
-// The same test on plane distances that were computed by the caller (quantised nodes).
-__device__ __forceinline__ bool __attribute__((unused)) slab_t(float tx0, float tx1, float ty0, float ty1, float tz0, float tz1, float tcull,
-                                       float* tnear) {
-    float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-    float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcull));
-    *tnear = tmin;
-    return tmin <= tmax;
-}
-
 template <bool WIDE>
 __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a, D3* b, D3* c, uint32_t* prim_id,
                                           uint32_t* kind) {
@@ -214,12 +205,23 @@ __device__ __noinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_
     ts = (double)tsf;
     *t_shift = tsf;
     double sx = o.x + d.x * ts, sy = o.y + d.y * ts, sz = o.z + d.z * ts;
-    rf->idx = safe_inv(d.x);
-    rf->idy = safe_inv(d.y);
-    rf->idz = safe_inv(d.z);
-    rf->oidx = (float)sx * rf->idx;
-    rf->oidy = (float)sy * rf->idy;
-    rf->oidz = (float)sz * rf->idz;
+    const float ix = safe_inv(d.x), iy = safe_inv(d.y), iz = safe_inv(d.z);
+    if (A.quantised) {
+        // Node32 planes: distance = f * (extent / d) - (o - (lo - extent)) / d, f in [1, 2) straight from the node
+        rf->idx = A.grid_ext[0] * ix;
+        rf->idy = A.grid_ext[1] * iy;
+        rf->idz = A.grid_ext[2] * iz;
+        rf->oidx = (float)(sx - A.grid_c[0]) * ix;
+        rf->oidy = (float)(sy - A.grid_c[1]) * iy;
+        rf->oidz = (float)(sz - A.grid_c[2]) * iz;
+    } else {
+        rf->idx = ix;
+        rf->idy = iy;
+        rf->idz = iz;
+        rf->oidx = (float)sx * ix;
+        rf->oidy = (float)sy * iy;
+        rf->oidz = (float)sz * iz;
+    }
     return true;
 }
 
@@ -286,19 +288,22 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_REFILL 8
 #endif
 #ifndef RRT_NODE32
-#define RRT_NODE32 0
+#define RRT_NODE32 1  // 0: never quantise, 1: per scene (quantise when the grid is fine enough), 2: always
 #endif
 #ifndef RRT_STALE_SKIP
 #define RRT_STALE_SKIP 0
 #endif
 #ifndef RRT_MINBLOCKS
-#define RRT_MINBLOCKS 7
+#define RRT_MINBLOCKS 7  // Node64 kernels: 72 registers
+#endif
+#ifndef RRT_MINBLOCKS_Q
+#define RRT_MINBLOCKS_Q 8  // Node32 kernels: 64 registers (measured best, profiles/r1_sweep8.txt)
 #endif
 constexpr int kRefill = RRT_REFILL;
 
 
-template <bool ANY, bool WIDE>
-__global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
+template <bool ANY, bool WIDE, bool QUANT>
+__global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
                                                         rrt_hit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                         const uint32_t* __restrict__ perm,
                                                         const uint32_t* __restrict__ use_perm,
@@ -307,9 +312,7 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
     const unsigned FULL = 0xffffffffu;
     if (n_dev) n = *n_dev;  // wavefront queues: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
-#if !RRT_NODE32
     const Node64* __restrict__ nodes = static_cast<const Node64*>(A.nodes);
-#endif
     const bool permuted = perm != nullptr && (use_perm == nullptr || *use_perm != 0u);
 
     // Traversal stack: entirely in shared memory, laid out [level][thread] so that 32 lanes at 32
@@ -410,35 +413,30 @@ __global__ void __launch_bounds__(kBlock, RRT_MINBLOCKS) trace_kernel(AggView A,
           for (int step = 0; step < RRT_UNROLL; ++step) {
             const bool walking = node >= 0 && node != kDone;
             if (walking) {
-#if RRT_NODE32
-                // one 256-bit load: frame origin, 12 quantised planes, cell exponent, two references
-                const F8 v = ldg256(reinterpret_cast<const char*>(A.nodes) + (size_t)node * sizeof(Node32));
-                const uint32_t q0 = __float_as_uint(v.d), q1 = __float_as_uint(v.e), q2 = __float_as_uint(v.f);
-                const uint32_t w0 = __float_as_uint(v.g), w1 = __float_as_uint(v.h);
-                const float cell = __uint_as_float((w0 & 0xffu) << 23);
-                // plane distance = (origin + q * cell - o) / d = q * (cell / d) + (origin / d - o / d)
-                const float ax = cell * rf.idx, ay = cell * rf.idy, az = cell * rf.idz;
-                const float bx = fmaf(v.a, rf.idx, -rf.oidx), by = fmaf(v.b, rf.idy, -rf.oidy), bz = fmaf(v.c, rf.idz, -rf.oidz);
-                const uint32_t r0 = (w0 >> 8) | ((w1 & 0xfu) << 24), r1 = w1 >> 4;
-                const int32_t ch_x = (r0 & 0x8000000u) ? ~(int32_t)(((r0 & 0x1FFFFFFu) << 3) | ((r0 >> 25) & 3u)) : (int32_t)r0;
-                const int32_t ch_y = (r1 & 0x8000000u) ? ~(int32_t)(((r1 & 0x1FFFFFFu) << 3) | ((r1 >> 25) & 3u)) : (int32_t)r1;
+                int32_t ch_x, ch_y;
                 float tn0, tn1;
-                const bool h0 = slab_t(fmaf((float)(q0 & 0xffu), ax, bx), fmaf((float)(q0 >> 24), ax, bx),
-                                       fmaf((float)((q0 >> 8) & 0xffu), ay, by), fmaf((float)(q1 & 0xffu), ay, by),
-                                       fmaf((float)((q0 >> 16) & 0xffu), az, bz), fmaf((float)((q1 >> 8) & 0xffu), az, bz),
-                                       tcull, &tn0);
-                const bool h1 = slab_t(fmaf((float)((q1 >> 16) & 0xffu), ax, bx), fmaf((float)((q2 >> 8) & 0xffu), ax, bx),
-                                       fmaf((float)(q1 >> 24), ay, by), fmaf((float)((q2 >> 16) & 0xffu), ay, by),
-                                       fmaf((float)(q2 & 0xffu), az, bz), fmaf((float)(q2 >> 24), az, bz), tcull, &tn1);
-#else
-                const char* np = reinterpret_cast<const char*>(nodes + node);
-                const F8 lo = ldg256(np);        // c0 x/y slabs, c1 x/y slabs
-                const F8 hi = ldg256(np + 32);   // z slabs of both, child references
-                const int32_t ch_x = __float_as_int(hi.e), ch_y = __float_as_int(hi.f);
-                float tn0, tn1;
-                const bool h0 = slab(rf, lo.a, lo.b, lo.c, lo.d, hi.a, hi.b, tcull, &tn0);
-                const bool h1 = slab(rf, lo.e, lo.f, lo.g, lo.h, hi.c, hi.d, tcull, &tn1);
-#endif
+                bool h0, h1;
+                if (QUANT) {
+                    // one 256-bit load: 12 quantised planes + two child references; a plane becomes the float
+                    // 1 + q / 32768 with one byte permute (device_layout.h)
+                    const F8 v = ldg256(reinterpret_cast<const char*>(A.nodes) + (size_t)node * sizeof(Node32));
+                    const uint32_t w0 = __float_as_uint(v.a), w1 = __float_as_uint(v.b), w2 = __float_as_uint(v.c);
+                    const uint32_t w3 = __float_as_uint(v.d), w4 = __float_as_uint(v.e), w5 = __float_as_uint(v.f);
+                    ch_x = __float_as_int(v.g);
+                    ch_y = __float_as_int(v.h);
+#define RRT_QLO(w) __uint_as_float(__byte_perm((w), 0x3Fu, 0x4105))
+#define RRT_QHI(w) __uint_as_float(__byte_perm((w), 0x3Fu, 0x4325))
+                    h0 = slab(rf, RRT_QLO(w0), RRT_QHI(w0), RRT_QLO(w1), RRT_QHI(w1), RRT_QLO(w2), RRT_QHI(w2), tcull, &tn0);
+                    h1 = slab(rf, RRT_QLO(w3), RRT_QHI(w3), RRT_QLO(w4), RRT_QHI(w4), RRT_QLO(w5), RRT_QHI(w5), tcull, &tn1);
+                } else {
+                    const char* np = reinterpret_cast<const char*>(nodes + node);
+                    const F8 lo = ldg256(np);        // c0 x/y slabs, c1 x/y slabs
+                    const F8 hi = ldg256(np + 32);   // z slabs of both, child references
+                    ch_x = __float_as_int(hi.e);
+                    ch_y = __float_as_int(hi.f);
+                    h0 = slab(rf, lo.a, lo.b, lo.c, lo.d, hi.a, hi.b, tcull, &tn0);
+                    h1 = slab(rf, lo.e, lo.f, lo.g, lo.h, hi.c, hi.d, tcull, &tn1);
+                }
                 // branch-free step: both hit -> push the far child, go near; one hit -> go there;
                 // none -> pop
                 const bool both = h0 && h1;
@@ -774,9 +772,6 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     Bvh2 tree;
     SahParams sp;
     sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
-#if RRT_NODE32
-    if (sp.max_leaf > 4) sp.max_leaf = 4;  // the 32-byte node's leaf reference holds a 2-bit count
-#endif
     if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
     build_sah(boxes, sp, &tree);
     if (tree.max_depth + 2 > (uint32_t)kStack) {
@@ -904,85 +899,72 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         }
     }
 
-#if RRT_NODE32
-    // ---- quantise: Node64 (fp32 planes) -> Node32 (8-bit planes on a per-node power-of-two grid) ----
-    std::vector<Node32> nodes32(nodes.size());
-    if (nodes.size() >= (1u << 27) || n >= (1u << 25)) {
-        if (err) *err = "scene too large for the 28-bit child references of the 32-byte node";
-        return RRT_ERR_UNSUPPORTED;
+    // ---- quantise: Node64 (fp32 planes) -> Node32 (15-bit planes on one grid over the widened world box) ----
+    double grid_lo[3], grid_c[3];
+    float grid_ext[3];
+    for (int k = 0; k < 3; ++k) {
+        // fp32-rounding margins around the root's (already widened) children, and an extent that is an fp32 value
+        grid_lo[k] = world_box.lo[k] - 4.0 * delta;
+        double ext = (world_box.hi[k] + 4.0 * delta) - grid_lo[k];
+        ext = std::fmax(ext, scale * std::ldexp(1.0, -10));
+        grid_ext[k] = round_up(ext * (1.0 + std::ldexp(1.0, -20)));
+        grid_c[k] = grid_lo[k] - (double)grid_ext[k];
     }
-    for (size_t i = 0; i < nodes.size(); ++i) {
-        const Node64& s = nodes[i];
-        const double lo[2][3] = {{s.c0_lox, s.c0_loy, s.c0_loz}, {s.c1_lox, s.c1_loy, s.c1_loz}};
-        const double hi[2][3] = {{s.c0_hix, s.c0_hiy, s.c0_hiz}, {s.c1_hix, s.c1_hiy, s.c1_hiz}};
-        double ext = 0.0, maxabs = 0.0, mn[3];
-        for (int k = 0; k < 3; ++k) {
-            mn[k] = std::fmin(lo[0][k], lo[1][k]);
-            const double mx = std::fmax(hi[0][k], hi[1][k]);
-            ext = std::fmax(ext, mx - mn[k]);
-            maxabs = std::fmax(maxabs, std::fmax(std::fabs(mn[k]), std::fabs(mx)));
-        }
-        // cell = 2^e: 254 cells span the node (one is lost to flooring the origin), and the grid is
-        // never finer than what fp32 can hold at these coordinates, so origin + q * cell is exact
-        double need = std::fmax(ext / 254.0, maxabs / 16776000.0);
-        need = std::fmax(need, std::ldexp(1.0, -100));
-        int e = 0;
-        std::frexp(need, &e);  // need = f * 2^e, f in [0.5, 1)  =>  2^e >= need
-        const double cell = std::ldexp(1.0, e);
-        Node32 o;
-        uint8_t qb[12];
-        double org[3];
-        bool ok = e + 127 >= 1 && e + 127 <= 254;
-        for (int k = 0; k < 3; ++k) {
-            org[k] = std::floor(mn[k] / cell) * cell;
-            ok = ok && (double)(float)org[k] == org[k];
-        }
-        for (int c = 0; c < 2; ++c)
-            for (int k = 0; k < 3; ++k) {
-                const double ql = std::floor((lo[c][k] - org[k]) / cell), qh = std::ceil((hi[c][k] - org[k]) / cell);
-                ok = ok && ql >= 0.0 && qh <= 255.0 && ql <= qh;
-                // the decoded planes must enclose the box they replace, as exact fp32 values
-                const double dl = org[k] + ql * cell, dh = org[k] + qh * cell;
-                ok = ok && dl <= lo[c][k] && dh >= hi[c][k] && (double)(float)dl == dl && (double)(float)dh == dh;
-                // plane order inside the 12 bytes: c0 lo xyz, c0 hi xyz, c1 lo xyz, c1 hi xyz
-                qb[6 * c + k] = (uint8_t)ql;
-                qb[6 * c + 3 + k] = (uint8_t)qh;
+    // The grid costs every box up to one cell per side.  That is nothing for a scene whose primitives are much
+    // larger than extent / 32768 (configs 1-5: 0.3% of a leaf's edge), and it would ruin the culling of a scene
+    // with small details in a huge box; such scenes keep the fp32 node.  Measure: mean over the leaf boxes of the
+    // relative growth of their half-perimeter.
+    bool quantise = RRT_NODE32 == 2;
+    if (RRT_NODE32 == 1) {
+        double growth = 0.0;
+        size_t n_boxes = 0;
+        for (const Node64& s : nodes) {
+            const float* b[2] = {&s.c0_lox, &s.c1_lox};
+            const float* z[2] = {&s.c0_loz, &s.c1_loz};
+            const int32_t ch[2] = {s.child0, s.child1};
+            for (int c = 0; c < 2; ++c) {
+                if (ch[c] >= 0) continue;
+                const double ex = (double)b[c][1] - (double)b[c][0], ey = (double)b[c][3] - (double)b[c][2],
+                             ez = (double)z[c][1] - (double)z[c][0];
+                const double cells = 2.0 * ((double)grid_ext[0] + (double)grid_ext[1] + (double)grid_ext[2]) / 32768.0;
+                growth += cells / std::fmax(ex + ey + ez, 1e-300);
+                n_boxes += 1;
             }
-        if (!ok) {
-            if (err) *err = "node quantisation failed (box not representable on an fp32 grid)";
-            return RRT_ERR_UNSUPPORTED;
         }
-        o.ox = (float)org[0];
-        o.oy = (float)org[1];
-        o.oz = (float)org[2];
-        for (int w = 0; w < 3; ++w)
-            o.q[w] = (uint32_t)qb[4 * w] | ((uint32_t)qb[4 * w + 1] << 8) | ((uint32_t)qb[4 * w + 2] << 16) | ((uint32_t)qb[4 * w + 3] << 24);
-        auto ref28 = [&](int32_t child, bool* good) -> uint32_t {
-            if (child >= 0) return (uint32_t)child;
-            const uint32_t r = ~(uint32_t)child, first = r >> 3, cnt1 = r & 7u;
-            if (cnt1 > 3u || first >= (1u << 25)) *good = false;
-            return 0x8000000u | (cnt1 << 25) | first;
-        };
-        bool good = true;
-        const uint32_t r0 = ref28(s.child0, &good), r1 = ref28(s.child1, &good);
-        if (!good) {
-            if (err) *err = "leaf does not fit the 32-byte node's reference (more than 4 primitives per leaf)";
-            return RRT_ERR_UNSUPPORTED;
-        }
-        o.w0 = (uint32_t)(e + 127) | ((r0 & 0xFFFFFFu) << 8);
-        o.w1 = (r0 >> 24) | (r1 << 4);
-        nodes32[i] = o;
+        quantise = n_boxes > 0 && growth / (double)n_boxes < 0.05;
     }
-#endif
+    if (const char* e = std::getenv("RRT_QUANTISE")) quantise = atoi(e) != 0;
+    std::vector<Node32> nodes32;
+    if (quantise) {
+        nodes32.resize(nodes.size());
+        // the device evaluates fmaf(f, ext / d, -(o - c) / d) in fp32: 11 roundings of magnitude <= 2 ext / |d|
+        // (DESIGN.md §3), i.e. less than ext * 2^-20 in position; the planes move outward by twice that
+        auto quant = [&](double plane, int k, bool upper) -> uint32_t {
+            const double cell = (double)grid_ext[k] / 32768.0;
+            const double margin = (double)grid_ext[k] * std::ldexp(1.0, -19);
+            double q = upper ? std::ceil((plane + margin - grid_lo[k]) / cell) : std::floor((plane - margin - grid_lo[k]) / cell);
+            if (q < 0.0) q = 0.0;
+            if (q > 32767.0) q = 32767.0;
+            return 0x8000u | (uint32_t)q;
+        };
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const Node64& s = nodes[i];
+            Node32 o;
+            o.p[0] = quant(s.c0_lox, 0, false) | (quant(s.c0_hix, 0, true) << 16);
+            o.p[1] = quant(s.c0_loy, 1, false) | (quant(s.c0_hiy, 1, true) << 16);
+            o.p[2] = quant(s.c0_loz, 2, false) | (quant(s.c0_hiz, 2, true) << 16);
+            o.p[3] = quant(s.c1_lox, 0, false) | (quant(s.c1_hix, 0, true) << 16);
+            o.p[4] = quant(s.c1_loy, 1, false) | (quant(s.c1_hiy, 1, true) << 16);
+            o.p[5] = quant(s.c1_loz, 2, false) | (quant(s.c1_hiz, 2, true) << 16);
+            o.child0 = s.child0;
+            o.child1 = s.child1;
+            nodes32[i] = o;
+        }
+    }
     // ---- upload ----
     RRT_CUDA(cudaSetDevice(device));
-#if RRT_NODE32
-    size_t node_bytes = nodes32.size() * sizeof(Node32);
-    const void* node_src = nodes32.data();
-#else
-    size_t node_bytes = nodes.size() * sizeof(Node64);
-    const void* node_src = nodes.data();
-#endif
+    const size_t node_bytes = quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64);
+    const void* node_src = quantise ? (const void*)nodes32.data() : (const void*)nodes.data();
     size_t prim_bytes = wide ? rec96.size() * sizeof(PrimRec96) : rec48.size() * sizeof(PrimRec48);
     RRT_CUDA(cudaMalloc(&d_nodes_, node_bytes));
     RRT_CUDA(cudaMalloc(&d_prims_, prim_bytes));
@@ -1008,6 +990,11 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         view_.world_hi[k] = world_box.hi[k] + delta;
     }
     view_.scene_scale = scale;
+    for (int k = 0; k < 3; ++k) {
+        view_.grid_c[k] = grid_c[k];
+        view_.grid_ext[k] = grid_ext[k];
+    }
+    view_.quantised = quantise ? 1 : 0;
     view_.root = 0;
     view_.wide = wide ? 1 : 0;
     view_.sort_mode = 0;
@@ -1027,10 +1014,12 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     // everything else of the 256 KB stays L1
     stack_levels_ = (int)tree.max_depth + 2;
     const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
-    int carve = (int)((RRT_MINBLOCKS * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
+    int carve = (int)(((quantise ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
-    for (auto fn : {(const void*)trace_kernel<false, false>, (const void*)trace_kernel<false, true>,
-                    (const void*)trace_kernel<true, false>, (const void*)trace_kernel<true, true>}) {
+    for (auto fn : {(const void*)trace_kernel<false, false, false>, (const void*)trace_kernel<false, true, false>,
+                    (const void*)trace_kernel<true, false, false>, (const void*)trace_kernel<true, true, false>,
+                    (const void*)trace_kernel<false, false, true>, (const void*)trace_kernel<false, true, true>,
+                    (const void*)trace_kernel<true, false, true>, (const void*)trace_kernel<true, true, true>}) {
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
@@ -1096,7 +1085,8 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
                                                n_dev);
         count += 4;
     }
-    auto kernel = view_.wide ? trace_kernel<ANY, true> : trace_kernel<ANY, false>;
+    auto kernel = view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true> : trace_kernel<ANY, false, true>)
+                                  : (view_.wide ? trace_kernel<ANY, true, false> : trace_kernel<ANY, false, false>);
     const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
     int per_sm = 0;
     RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));

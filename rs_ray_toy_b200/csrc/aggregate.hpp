@@ -25,6 +25,9 @@ struct AggView {
     double world_lo[3];  // tight world box of the tree, used to pull far-away origins close
     double world_hi[3];
     double scene_scale;  // max |coordinate| of the world box
+    double grid_c[3];    // Node32: quantisation grid, lo - extent per axis (plane = grid_c + f * grid_ext)
+    float grid_ext[3];   //             extent per axis (an fp32 value)
+    int32_t quantised;   // 1 => nodes is Node32[] (15-bit planes on the grid), 0 => Node64[]
     int32_t root;        // interior node index of the root (always 0)
     int32_t wide;        // 1 => PrimRec96
     int32_t has_spheres;

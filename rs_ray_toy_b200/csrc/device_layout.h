@@ -26,20 +26,20 @@ struct RRT_ALIGN(16) Node64 {
 };
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
-// 32 B interior node (RRT_NODE32 builds): the same two child boxes quantised to 8 bits per plane
-// on a per-node grid, so that one 256-bit load fetches a whole node.
-//   origin (3 x fp32, a multiple of the cell size) ; 12 plane bytes ; cell exponent ; two 28-bit
-//   child references.  A decoded plane origin + q * 2^e is an exact fp32 value that lies outside
-//   the (already widened) box it replaces, so culling stays conservative.
-//   q bytes:  q[0] = c0.lo.x c0.lo.y c0.lo.z c0.hi.x | q[1] = c0.hi.y c0.hi.z c1.lo.x c1.lo.y |
-//             q[2] = c1.lo.z c1.hi.x c1.hi.y c1.hi.z          (little-endian bytes of each word)
-//   w0 = cell exponent byte | (ref0 & 0xFFFFFF) << 8 ;  w1 = (ref0 >> 24) | ref1 << 4
-//   ref (28 bits): bit 27 clear -> interior node index; set -> leaf: bits 0-24 first record,
-//   bits 25-26 count - 1 (at most 4 primitives per leaf).
+// 32 B interior node (RRT_NODE32 builds): the same two child boxes with every plane quantised to 15 bits on ONE
+// grid that spans the (widened) world box, so that a single 256-bit load fetches a whole node and decoding a
+// plane is one byte permute:
+//   a stored plane is the 16-bit value 0x8000 | q (q in 0..32767); PRMT drops it into a float's bits 8..23 under
+//   the exponent byte 0x3F, giving f = 1 + q / 32768 in [1, 2) exactly, and the plane's distance along the ray is
+//   fmaf(f, A, B) with the per-ray constants A = extent / d and B = (lo - extent - o) / d — the same one FFMA
+//   per plane as the fp32 node.  Lower planes are rounded down and upper planes up to the grid (after the
+//   fp32-rounding margin), so culling stays conservative; the price is boxes up to one cell
+//   (extent / 32768 per axis) larger per side.
+//   p[0] = c0.lo.x | c0.hi.x << 16   p[1] = c0.lo.y | c0.hi.y << 16   p[2] = c0.lo.z | c0.hi.z << 16
+//   p[3..5] the same for child 1; child references as in Node64.
 struct RRT_ALIGN(32) Node32 {
-    float ox, oy, oz;
-    uint32_t q[3];
-    uint32_t w0, w1;
+    uint32_t p[6];
+    int32_t child0, child1;
 };
 static_assert(sizeof(Node32) == 32, "Node32 must be 32 bytes");
 

@@ -349,3 +349,48 @@ def test_literal_and_fixed_tiers_differ_where_the_survey_says(ctx):
     agg_f = scenes.gpu_cubes(ctx, m_, inv)
     hl, hf = agg_l.intersect(rays), agg_f.intersect(rays)
     assert (hl["prim_id"] != hf["prim_id"]).sum() > 0
+
+
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_both_node_formats_agree_with_the_oracle(ctx, force, monkeypatch):
+    """The fp32 Node64 and the 15-bit-grid Node32 (device_layout.h) are two encodings of the same conservative
+    boxes: forced either way (RRT_QUANTISE is read at commit) the hits are the oracle's, on triangles, rotated
+    instances and spheres."""
+    monkeypatch.setenv("RRT_QUANTISE", force)
+    p, idx = scenes.soup(60000)
+    rays = synth.bounce_rays(p, idx, 120000, seed=77)
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    st = agg.stats()
+    assert (st["device_bytes"] - 48 * st["n_records"]) // st["n_nodes"] == (32 if force == "1" else 64), st
+    c = _assert_closest(agg.intersect(rays), ref["prim"], ref["t"], ref["uv"])
+    assert c["t_exact"] == c["hits"], c
+    sh = synth.shadow_rays_from(rays, (0.5, 0.5, 1.5))
+    occ_ref, _ = scenes.oracle_soup(p, idx).intersect_p(sh)
+    assert (agg.intersect_p(sh) == occ_ref).all()
+    m, inv = scenes.cube_instances(300, extent=8.0)
+    rng = np.random.default_rng(5)
+    rays = np.concatenate([rng.uniform(-12, 12, (60000, 3)), synth.random_unit_vectors(60000, rng), np.full((60000, 1), np.inf)], axis=1)
+    ref = scenes.oracle_cubes(m, inv).intersect(rays)
+    _assert_closest(scenes.gpu_cubes(ctx, m, inv).intersect(rays), ref["prim"], ref["t"])
+    m, inv = scenes.sphere_instances(2000, extent=10.0)
+    ref = scenes.oracle_spheres(m, inv).intersect(rays)
+    _assert_closest(scenes.gpu_spheres(ctx, m, inv).intersect(rays), ref["prim"], ref["t"])
+
+
+def test_small_details_in_a_huge_box_keep_fp32_nodes(ctx):
+    """A grid cell of extent / 32768 would swallow 1e-4-sized triangles scattered over a 1000-unit box: such a scene
+    must stay on Node64 (chosen per scene at commit), and either way the answers are the oracle's."""
+    p, idx = scenes.soup(20000, edge=1e-4)
+    p = p * 1000.0
+    p = p.astype(np.float32).astype(np.float64)
+    rays = synth.bounce_rays(p, idx, 50000, seed=9)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    st = agg.stats()
+    assert (st["device_bytes"] - 48 * st["n_records"]) // st["n_nodes"] == 64, st
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    _assert_closest(agg.intersect(rays), ref["prim"], ref["t"], ref["uv"])
+    # config-3 shape: the grid is 0.3% of a leaf's edge -> quantised
+    p, idx = scenes.soup(20000)
+    st = scenes.gpu_soup(ctx, p, idx).stats()
+    assert (st["device_bytes"] - 48 * st["n_records"]) // st["n_nodes"] == 32, st
