@@ -293,6 +293,18 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_STALE_SKIP
 #define RRT_STALE_SKIP 0
 #endif
+#ifndef RRT_STATS
+#define RRT_STATS 0
+#endif
+#ifndef RRT_WALK_MIN
+#define RRT_WALK_MIN 12
+#endif
+#ifndef RRT_LEAF_TRIPS
+#define RRT_LEAF_TRIPS 0  // 0: the leaf phase empties every queue; k: at most k leaves per lane and phase
+#endif
+#ifndef RRT_LEAFQ
+#define RRT_LEAFQ 3  // postponed leaves per lane (measured: with one, 10 of 32 lanes stand at their second leaf)
+#endif
 #ifndef RRT_MINBLOCKS
 #define RRT_MINBLOCKS 7  // Node64 kernels: 72 registers
 #endif
@@ -339,7 +351,27 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
 #endif
     int sp = 1;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
-    int32_t leaf = kNoLeaf;   // parked leaf reference
+    int32_t leaf = kNoLeaf;   // parked leaf reference (head of the queue)
+#if RRT_LEAFQ > 1
+    int32_t lq[RRT_LEAFQ - 1];  // further parked leaves: the walk goes on past RRT_LEAFQ untested leaves
+#pragma unroll
+    for (int k = 0; k < RRT_LEAFQ - 1; ++k) lq[k] = kNoLeaf;
+    // filled front to back, so the queue is full exactly when its last slot is taken
+#define RRT_PARK()                                         \
+    do {                                                   \
+        bool placed_ = false;                              \
+        if (leaf == kNoLeaf) {                             \
+            leaf = node;                                   \
+            placed_ = true;                                \
+        }                                                  \
+        _Pragma("unroll") for (int k_ = 0; k_ < RRT_LEAFQ - 1; ++k_) { \
+            if (!placed_ && lq[k_] == kNoLeaf) {           \
+                lq[k_] = node;                             \
+                placed_ = true;                            \
+            }                                              \
+        }                                                  \
+    } while (0)
+#endif
     bool have_ray = false;
     bool exhausted = false;   // the global queue is empty (warp-uniform)
     uint64_t ray_index = 0;
@@ -349,6 +381,9 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
     float t_shift = 0.0f, tcull = 0.0f;
     uint32_t best_id = RRT_NO_HIT, best_rec = 0;
     bool found = false;
+#if RRT_STATS  // diagnostic build: where do the lanes of an interior / leaf trip stand? (tools/sweep.py "STATS=1")
+    unsigned long long st_trips = 0, st_walk = 0, st_noray = 0, st_drained = 0, st_second = 0, st_ltrips = 0, st_lact = 0;
+#endif
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes ----
@@ -396,6 +431,10 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                     my_tstack[0] = -1.0f;  // the marker is never stale
 #endif
                     leaf = kNoLeaf;
+#if RRT_LEAFQ > 1
+#pragma unroll
+                    for (int k = 0; k < RRT_LEAFQ - 1; ++k) lq[k] = kNoLeaf;
+#endif
                     const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
                     node = live ? A.root : kDone;
                     tcull = __double2float_ru(best_t - (double)t_shift);
@@ -412,6 +451,13 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
 #pragma unroll
           for (int step = 0; step < RRT_UNROLL; ++step) {
             const bool walking = node >= 0 && node != kDone;
+#if RRT_STATS
+            st_trips += 1;
+            st_walk += __popc(__ballot_sync(FULL, walking));
+            st_noray += __popc(__ballot_sync(FULL, !have_ray));
+            st_drained += __popc(__ballot_sync(FULL, have_ray && node == kDone));
+            st_second += __popc(__ballot_sync(FULL, have_ray && node < 0));
+#endif
             if (walking) {
                 int32_t ch_x, ch_y;
                 float tn0, tn1;
@@ -452,17 +498,38 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                 node = both ? near_c : (h0 ? ch_x : ch_y);
                 if (!(h0 || h1)) RRT_POP();
             }
+#if RRT_LEAFQ > 1
+            if (node < 0 && lq[RRT_LEAFQ - 2] == kNoLeaf) {  // park the leaf, keep walking
+                RRT_PARK();
+                RRT_POP();
+            }
+#else
             if (node < 0 && leaf == kNoLeaf) {  // park the first leaf, keep walking
                 leaf = node;
                 RRT_POP();
             }
+#endif
           }
             // leave when no lane is still looking for its first leaf
             if (!__any_sync(FULL, leaf == kNoLeaf && node != kDone)) break;
+#if RRT_WALK_MIN > 0
+            // ... or when too few lanes are left walking to fill the warp (the rest stand at a full leaf queue or
+            // have emptied their stack): the searching lanes resume after the leaf phase
+            if (__popc(__ballot_sync(FULL, node >= 0 && node != kDone)) < RRT_WALK_MIN) break;
+#endif
         }
 
         // ---- leaf phase ----
+#if RRT_LEAF_TRIPS > 0
+#pragma unroll 1
+        for (int trip = 0; trip < RRT_LEAF_TRIPS && __any_sync(FULL, leaf != kNoLeaf); ++trip) {
+#else
         while (__any_sync(FULL, leaf != kNoLeaf)) {
+#endif
+#if RRT_STATS
+            st_ltrips += 1;
+            st_lact += __popc(__ballot_sync(FULL, leaf != kNoLeaf));
+#endif
             if (leaf != kNoLeaf) {
                 const uint32_t ref = ~(uint32_t)leaf;
                 const uint32_t first = ref >> 3, cnt = (ref & 7u) + 1u;
@@ -491,6 +558,21 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                         }
                     }
                 }
+#if RRT_LEAFQ > 1
+                leaf = lq[0];
+#pragma unroll
+                for (int k = 0; k < RRT_LEAFQ - 2; ++k) lq[k] = lq[k + 1];
+                lq[RRT_LEAFQ - 2] = kNoLeaf;
+                if (ANY && found) {
+                    node = kDone;
+                    leaf = kNoLeaf;
+#pragma unroll
+                    for (int k = 0; k < RRT_LEAFQ - 1; ++k) lq[k] = kNoLeaf;
+                } else if (node < 0) {  // the walk stands at one more leaf: it takes the slot that came free
+                    RRT_PARK();
+                    RRT_POP();
+                }
+#else
                 leaf = kNoLeaf;
                 if (ANY && found) {
                     node = kDone;
@@ -498,9 +580,21 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                     leaf = node;
                     RRT_POP();
                 }
+#endif
             }
         }
     }
+#if RRT_STATS
+    if (lane == 0) {
+        atomicAdd(cursor + 2, st_trips);
+        atomicAdd(cursor + 3, st_walk);
+        atomicAdd(cursor + 4, st_noray);
+        atomicAdd(cursor + 5, st_drained);
+        atomicAdd(cursor + 6, st_second);
+        atomicAdd(cursor + 7, st_ltrips);
+        atomicAdd(cursor + 8, st_lact);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1031,7 +1125,7 @@ int DeviceAggregate::ensure_workspace(uint64_t n, std::string* err) const {
     if (!w.d_small) {
         RRT_CUDA(cudaMalloc(&w.d_bins, (size_t)kSortBins * sizeof(uint32_t)));
         RRT_CUDA(cudaMalloc(&w.d_block_sums, (size_t)(kSortBins / kScanBlock) * sizeof(uint32_t)));
-        RRT_CUDA(cudaMalloc(&w.d_small, 64));
+        RRT_CUDA(cudaMalloc(&w.d_small, 128));
         RRT_CUDA(cudaEventCreateWithFlags(&w.last_use, cudaEventDisableTiming));
         int dev = 0, sms = 0;
         RRT_CUDA(cudaGetDevice(&dev));
@@ -1068,7 +1162,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     // the scratch buffers are shared by every call on this aggregate: order this call after the last one
     if (w.used) RRT_CUDA(cudaStreamWaitEvent(s, w.last_use, 0));
     uint32_t* small = static_cast<uint32_t*>(w.d_small);  // [0..1] cursor, [2] max_bin, [3] use_perm
-    RRT_CUDA(cudaMemsetAsync(small, 0, 64, s));
+    RRT_CUDA(cudaMemsetAsync(small, 0, 128, s));
     const bool sorting = sort_rays_ && n >= 4096;
     int count = 0;
     if (sorting) {
@@ -1099,6 +1193,17 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
                                                reinterpret_cast<unsigned long long*>(small), n_dev, stack_levels_);
     count += 1;
     RRT_CUDA(cudaGetLastError());
+#if RRT_STATS
+    {
+        unsigned long long h[16];
+        RRT_CUDA(cudaStreamSynchronize(s));
+        RRT_CUDA(cudaMemcpy(h, small, 128, cudaMemcpyDeviceToHost));
+        if (n >= (1u << 20))
+            fprintf(stderr, "RRT_STATS any=%d n=%llu interior trips %llu: walking %.2f no-ray %.2f drained %.2f at-2nd-leaf %.2f | leaf trips %llu: active %.2f\n",
+                    (int)ANY, (unsigned long long)n, h[2], (double)h[3] / h[2], (double)h[4] / h[2], (double)h[5] / h[2],
+                    (double)h[6] / h[2], h[7], (double)h[8] / (h[7] ? h[7] : 1));
+    }
+#endif
     RRT_CUDA(cudaEventRecord(w.last_use, s));
     w.used = true;
     if (launches) *launches = count;
