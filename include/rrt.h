@@ -60,9 +60,13 @@ typedef struct rrt_hit {
 /* BVHSplitMethod (bvh.rs:111-114) plus the parity tier.                         */
 typedef enum rrt_build_flags {
     RRT_BUILD_FAST = 0,    /* Tier F: own SAH tree, true closest hit, ties -> lowest prim id     */
-    RRT_BUILD_LITERAL = 1  /* Tier L: the reference's HLBVH topology, visiting order and accept rules
+    RRT_BUILD_LITERAL = 1, /* Tier L: the reference's HLBVH topology, visiting order and accept rules
                               with every quirk kept (last accepted hit wins, ...): bit-for-bit what
                               BVHAccel returns; one thread per ray, meant for parity not throughput */
+    RRT_BUILD_DEVICE_LBVH = 2 /* Tier F with the tree built ON the GPU: Morton keys, radix sort, binary radix
+                              tree, bottom-up boxes (the device counterpart of hlbvh_build's Morton half,
+                              bvh.rs:365-612).  Milliseconds instead of a host SAH build; same answers (Tier-F
+                              results do not depend on topology), a somewhat slower tree to walk            */
 } rrt_build_flags;
 
 /* ---- context ----------------------------------------------------------------------------- */
@@ -108,6 +112,17 @@ int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out);
 int rrt_world_bound(const rrt_scene* scene, double out6[6]);
 /* Build statistics: nodes, leaves, max depth, bytes uploaded, host build seconds (x1e6).        */
 int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]);
+
+/* How the tree was built: out4 = { microseconds the GPU spent building it (0 for a host build), bytes per
+ * interior node (32 or 64), 1 if built on the device, reserved }.                                            */
+int rrt_scene_build_info(const rrt_scene* scene, uint64_t out4[4]);
+
+/* Host-only probe of the device LBVH builder's per-element code (lbvh_core.h runs unchanged on the host; this
+ * is a checker for the CPU tests, not a product path): world bounds in (6 doubles each), out: the emitted
+ * Node64 array (16 x 4-byte words per node: 12 fp32 planes as laid out in device_layout.h, child0, child1, pad),
+ * the primitive order, and info3 = { nodes, max depth, leaves }.  *n_nodes is set also when capacity is short. */
+int rrt_lbvh_host_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
+                        uint32_t* n_nodes, uint32_t* node_words16, uint32_t* order, uint32_t info3[3]);
 
 /* Host-only probe of the literal tier's tree builder (BVHAccel::new with HLBVH, bvh.rs:307-751) on a
  * list of primitive world bounds (6 doubles each: p_min, p_max).  Returns the flattened

@@ -164,6 +164,12 @@ class GpuAggregate:
         keys = ["n_nodes", "n_leaves", "max_depth", "device_bytes", "build_usec", "n_records", "wide_records", "n_prims"]
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def build_info(self) -> dict:
+        """How the tree was built (rrt_scene_build_info)."""
+        out = np.zeros(4, dtype=np.uint64)
+        capi.check(self.L.rrt_scene_build_info(self.h, _ptr(out)))
+        return {"tree_device_usec": int(out[0]), "node_bytes": int(out[1]), "device_lbvh": bool(out[2])}
+
     # ---- Primitive / IntersectP over batches, HOST buffers ----------------------------------
     def intersect(self, rays, out=None) -> np.ndarray:
         """`Scene::intersect` (scene.rs:69-72) for a batch: returns rrt_hit records."""
@@ -188,9 +194,23 @@ class GpuAggregate:
                                                  C.c_void_p(stream)))
 
 
-def soup_aggregate(ctx: Context, p, idx, max_prims_in_node: int = 4) -> GpuAggregate:
+def lbvh_host_probe(bounds6: np.ndarray, max_prims_in_node: int = 4):
+    """rrt_lbvh_host_probe: the device LBVH builder's per-element code run on the host (CPU tests).
+    Returns (nodes as [n_nodes, 16] uint32 words of Node64, order, info {nodes, max_depth, leaves})."""
+    L = capi.lib()
+    b = np.ascontiguousarray(bounds6, dtype=np.float64).reshape(-1, 6)
+    n = b.shape[0]
+    words = np.zeros((max(n, 1), 16), dtype=np.uint32)
+    order = np.zeros(n, dtype=np.uint32)
+    info = np.zeros(3, dtype=np.uint32)
+    cnt = C.c_uint32()
+    capi.check(L.rrt_lbvh_host_probe(n, _ptr(b), max_prims_in_node, words.shape[0], C.byref(cnt), _ptr(words), _ptr(order), _ptr(info)))
+    return words[: cnt.value], order, {"nodes": int(info[0]), "max_depth": int(info[1]), "leaves": int(info[2])}
+
+
+def soup_aggregate(ctx: Context, p, idx, max_prims_in_node: int = 4, build_flags: int = capi.RRT_BUILD_FAST) -> GpuAggregate:
     """A bare (non-instanced) triangle mesh as one aggregate — configs 3 and 5."""
     agg = GpuAggregate(ctx)
     mesh = agg.add_mesh(p, idx)
     agg.add_triangles(mesh, 0)
-    return agg.commit(max_prims_in_node)
+    return agg.commit(max_prims_in_node, build_flags)

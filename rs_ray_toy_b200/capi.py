@@ -24,6 +24,7 @@ RRT_ERR_IO = -5
 RRT_NO_HIT = 0xFFFFFFFF
 RRT_BUILD_FAST = 0
 RRT_BUILD_LITERAL = 1
+RRT_BUILD_DEVICE_LBVH = 2
 
 
 class RrtError(RuntimeError):
@@ -69,6 +70,8 @@ def lib() -> C.CDLL:
         "rrt_scene_num_prims": (i32, [vp, C.POINTER(u32)]),
         "rrt_world_bound": (i32, [vp, vp]),
         "rrt_scene_stats": (i32, [vp, vp]),
+        "rrt_scene_build_info": (i32, [vp, vp]),
+        "rrt_lbvh_host_probe": (i32, [u32, vp, u32, u32, C.POINTER(u32), vp, vp, vp]),
         "rrt_intersect_device": (i32, [vp, u64, vp, vp, vp]),
         "rrt_intersect_p_device": (i32, [vp, u64, vp, vp, vp]),
         "rrt_intersect": (i32, [vp, u64, vp, vp]),

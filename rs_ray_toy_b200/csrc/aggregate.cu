@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "aggregate.hpp"
+#include "bvh_lbvh.hpp"
 #include "device_layout.h"
 
 namespace rrt {
@@ -797,7 +798,7 @@ DeviceAggregate::~DeviceAggregate() {
     if (w.last_use) cudaEventDestroy(w.last_use);
 }
 
-int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err) {
+int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err, bool device_lbvh) {
     auto t_start = std::chrono::steady_clock::now();
     device_ = device;
     const size_t n = scene.prims.size();
@@ -862,23 +863,50 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             boxes[i].grow(hi);
         }
     }
+    // ---- frame: world box, fp32 margin, Node32 grid, node format ----
+    Aabb world_box;
+    for (size_t i = 0; i < n; ++i) world_box.grow(boxes[i]);
+    const NodeFrame frame = make_node_frame(world_box);
+    const double scale = frame.scale, delta = frame.delta;
+    const double* grid_lo = frame.grid_lo;
+    const double* grid_c = frame.grid_c;
+    const float* grid_ext = frame.grid_ext;
+    // The grid costs every box up to one cell per side.  That is nothing for a scene whose primitives are much
+    // larger than extent / 32768 (configs 1-5: under 1% of a primitive box's half-perimeter), and it would ruin
+    // the culling of a scene with small details in a huge box; such scenes keep the fp32 node.
+    bool quantise = RRT_NODE32 == 2;
+    if (RRT_NODE32 == 1) {
+        const double cells = 2.0 * ((double)grid_ext[0] + (double)grid_ext[1] + (double)grid_ext[2]) / 32768.0;
+        double growth = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            const double hp = (boxes[i].hi[0] - boxes[i].lo[0]) + (boxes[i].hi[1] - boxes[i].lo[1]) + (boxes[i].hi[2] - boxes[i].lo[2]);
+            growth += std::fmin(1.0, cells / std::fmax(hp, 1e-300));
+        }
+        quantise = growth / (double)n < 0.05;
+    }
+    if (const char* e = std::getenv("RRT_QUANTISE")) quantise = atoi(e) != 0;
+    const uint32_t max_leaf = max_prims_in_node == 0 ? 4 : (max_prims_in_node > 8 ? 8 : max_prims_in_node);
+    const bool on_device = device_lbvh && n > 16 && n > max_leaf;
+
     // ---- tree ----
     Bvh2 tree;
-    SahParams sp;
-    sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
-    if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
-    build_sah(boxes, sp, &tree);
+    LbvhResult lb;
+    if (on_device) {
+        int rc = build_lbvh_device(device, boxes, max_leaf, delta, quantise, grid_lo, grid_ext, &lb, err);
+        if (rc != RRT_OK) return rc;
+        tree.max_depth = lb.max_depth + 1;
+        tree.n_leaves = lb.n_leaves;
+    } else {
+        SahParams sp;
+        sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
+        if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
+        build_sah(boxes, sp, &tree);
+    }
     if (tree.max_depth + 2 > (uint32_t)kStack) {
+        if (on_device) cudaFree(lb.d_nodes);
         if (err) *err = "tree deeper than the traversal stack (" + std::to_string(tree.max_depth) + " levels)";
         return RRT_ERR_UNSUPPORTED;
     }
-    const Aabb world_box = tree.nodes[tree.root].box;
-    double scale = 0.0;
-    for (int k = 0; k < 3; ++k) scale = std::fmax(scale, std::fmax(std::fabs(world_box.lo[k]), std::fabs(world_box.hi[k])));
-    if (!(scale > 0.0)) scale = 1.0;
-    // Widening that absorbs every fp32 rounding of the slab test: the fp32 copy
-    // of the origin (<= scale * 2^-24 after prepare_ray), of 1/d and of the products.
-    const double delta = scale * std::ldexp(1.0, -19);
 
     // ---- pack: interior nodes in DFS order, leaves become references ----
     std::vector<Node64> nodes;
@@ -890,10 +918,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         rec96.reserve(n);
     else
         rec48.reserve(n);
-    auto emit_leaf = [&](const Bvh2Node& nd) -> int32_t {
-        uint32_t first = (uint32_t)(wide ? rec96.size() : rec48.size());
-        for (uint32_t k = 0; k < nd.count; ++k) {
-            uint32_t pi = tree.order[nd.first + k];
+    auto push_record = [&](uint32_t pi) {
+        {
             const Primitive& pr = scene.prims[pi];
             if (wide) {
                 PrimRec96 r;
@@ -924,6 +950,10 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                 rec48.push_back(r);
             }
         }
+    };
+    auto emit_leaf = [&](const Bvh2Node& nd) -> int32_t {
+        uint32_t first = (uint32_t)(wide ? rec96.size() : rec48.size());
+        for (uint32_t k = 0; k < nd.count; ++k) push_record(tree.order[nd.first + k]);
         return make_leaf_ref(first, nd.count);
     };
     auto set_child = [&](Node64& out, int which, const Aabb& b) {
@@ -940,7 +970,10 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             out.c1_loz = lo[2]; out.c1_hiz = hi[2];
         }
     };
-    {
+    if (on_device) {
+        // the device tree's leaves are runs of the sorted order: records simply follow it
+        for (size_t r = 0; r < n; ++r) push_record(lb.order[r]);
+    } else {
         const Bvh2Node& root = tree.nodes[tree.root];
         if (root.count > 0) {
             // the whole scene fits one leaf: the root's two children both reference that leaf
@@ -993,43 +1026,9 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         }
     }
 
-    // ---- quantise: Node64 (fp32 planes) -> Node32 (15-bit planes on one grid over the widened world box) ----
-    double grid_lo[3], grid_c[3];
-    float grid_ext[3];
-    for (int k = 0; k < 3; ++k) {
-        // fp32-rounding margins around the root's (already widened) children, and an extent that is an fp32 value
-        grid_lo[k] = world_box.lo[k] - 4.0 * delta;
-        double ext = (world_box.hi[k] + 4.0 * delta) - grid_lo[k];
-        ext = std::fmax(ext, scale * std::ldexp(1.0, -10));
-        grid_ext[k] = round_up(ext * (1.0 + std::ldexp(1.0, -20)));
-        grid_c[k] = grid_lo[k] - (double)grid_ext[k];
-    }
-    // The grid costs every box up to one cell per side.  That is nothing for a scene whose primitives are much
-    // larger than extent / 32768 (configs 1-5: 0.3% of a leaf's edge), and it would ruin the culling of a scene
-    // with small details in a huge box; such scenes keep the fp32 node.  Measure: mean over the leaf boxes of the
-    // relative growth of their half-perimeter.
-    bool quantise = RRT_NODE32 == 2;
-    if (RRT_NODE32 == 1) {
-        double growth = 0.0;
-        size_t n_boxes = 0;
-        for (const Node64& s : nodes) {
-            const float* b[2] = {&s.c0_lox, &s.c1_lox};
-            const float* z[2] = {&s.c0_loz, &s.c1_loz};
-            const int32_t ch[2] = {s.child0, s.child1};
-            for (int c = 0; c < 2; ++c) {
-                if (ch[c] >= 0) continue;
-                const double ex = (double)b[c][1] - (double)b[c][0], ey = (double)b[c][3] - (double)b[c][2],
-                             ez = (double)z[c][1] - (double)z[c][0];
-                const double cells = 2.0 * ((double)grid_ext[0] + (double)grid_ext[1] + (double)grid_ext[2]) / 32768.0;
-                growth += cells / std::fmax(ex + ey + ez, 1e-300);
-                n_boxes += 1;
-            }
-        }
-        quantise = n_boxes > 0 && growth / (double)n_boxes < 0.05;
-    }
-    if (const char* e = std::getenv("RRT_QUANTISE")) quantise = atoi(e) != 0;
+    // ---- quantise the host tree: Node64 (fp32 planes) -> Node32 (15-bit planes on the grid) ----
     std::vector<Node32> nodes32;
-    if (quantise) {
+    if (quantise && !on_device) {
         nodes32.resize(nodes.size());
         // the device evaluates fmaf(f, ext / d, -(o - c) / d) in fp32: 11 roundings of magnitude <= 2 ext / |d|
         // (DESIGN.md §3), i.e. less than ext * 2^-20 in position; the planes move outward by twice that
@@ -1057,12 +1056,16 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     }
     // ---- upload ----
     RRT_CUDA(cudaSetDevice(device));
-    const size_t node_bytes = quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64);
+    const size_t node_bytes = on_device ? lb.node_bytes : (quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64));
     const void* node_src = quantise ? (const void*)nodes32.data() : (const void*)nodes.data();
     size_t prim_bytes = wide ? rec96.size() * sizeof(PrimRec96) : rec48.size() * sizeof(PrimRec48);
-    RRT_CUDA(cudaMalloc(&d_nodes_, node_bytes));
+    if (on_device) {
+        d_nodes_ = lb.d_nodes;
+    } else {
+        RRT_CUDA(cudaMalloc(&d_nodes_, node_bytes));
+        RRT_CUDA(cudaMemcpy(d_nodes_, node_src, node_bytes, cudaMemcpyHostToDevice));
+    }
     RRT_CUDA(cudaMalloc(&d_prims_, prim_bytes));
-    RRT_CUDA(cudaMemcpy(d_nodes_, node_src, node_bytes, cudaMemcpyHostToDevice));
     RRT_CUDA(cudaMemcpy(d_prims_, wide ? (const void*)rec96.data() : (const void*)rec48.data(), prim_bytes,
                         cudaMemcpyHostToDevice));
     bool has_spheres = false;
@@ -1094,7 +1097,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     view_.sort_mode = 0;
     if (const char* e = std::getenv("RRT_SORT_MODE")) view_.sort_mode = atoi(e);
     if (const char* e = std::getenv("RRT_SORT")) sort_rays_ = atoi(e) != 0;
-    stats_.n_nodes = nodes.size();
+    stats_.n_nodes = on_device ? lb.n_nodes : nodes.size();
+    stats_.tree_device_usec = on_device ? (uint64_t)(lb.device_ms * 1000.0f) : 0;
     stats_.n_leaves = tree.n_leaves;
     stats_.max_depth = tree.max_depth;
     stats_.device_bytes = node_bytes + prim_bytes;

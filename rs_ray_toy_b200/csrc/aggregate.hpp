@@ -15,6 +15,7 @@ namespace rrt {
 struct AggregateStats {
     uint64_t n_nodes = 0, n_leaves = 0, max_depth = 0, device_bytes = 0, build_usec = 0, n_records = 0,
              wide_records = 0, n_prims = 0;
+    uint64_t tree_device_usec = 0;  // RRT_BUILD_DEVICE_LBVH: keys -> emitted nodes on the GPU (CUDA events)
 };
 
 // Kernel-side view, passed by value to every launch.
@@ -60,7 +61,8 @@ class DeviceAggregate : public RayTracer {
 
     // Bake primitives to world space, build the SAH tree, pack Node64 / PrimRec and upload.
     // Returns an rrt_status; on failure *err holds the reason.
-    int build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err);
+    // `device_lbvh`: build the tree on the GPU (bvh_lbvh.cu) instead of the host SAH builder.
+    int build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err, bool device_lbvh = false);
 
     // Asynchronous on `stream`; *launches (optional) receives the number of kernels launched.
     int closest_hit(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* stream, std::string* err,

@@ -1,0 +1,356 @@
+// Device LBVH builder (RRT_BUILD_DEVICE_LBVH): Morton keys -> radix sort -> binary radix tree -> bottom-up
+// boxes -> collapse small subtrees into leaves -> Node32 / Node64 written in place, all on the GPU; the host
+// only receives the primitive order (to lay the primitive records out leaf by leaf).  See lbvh_core.h for what
+// it replaces in the reference and for the per-element code (shared with the host probe).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <vector>
+
+#include "bvh_lbvh.hpp"
+#include "lbvh_core.h"
+
+namespace rrt {
+
+using namespace lbvh;
+
+namespace {
+
+#define LB_CUDA(call)                                                           \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            return RRT_ERR_CUDA;                                                \
+        }                                                                       \
+    } while (0)
+
+struct CentroidFrame {
+    float lo[3], inv_ext[3];
+};
+
+__global__ void __launch_bounds__(256) keys_kernel(uint32_t n, const BoxF* __restrict__ boxes, CentroidFrame f,
+                                                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = morton63(boxes[i], f.lo, f.inv_ext);
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) hierarchy_kernel(uint32_t n, const uint64_t* __restrict__ keys,
+                                                         RadixNode* __restrict__ nodes, int32_t* __restrict__ parent_of_node,
+                                                         int32_t* __restrict__ parent_of_leaf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const RadixNode r = radix_node(keys, (int64_t)n, (int64_t)i);
+    nodes[i] = r;
+    if (r.left < 0) parent_of_leaf[~r.left] = (int32_t)i; else parent_of_node[r.left] = (int32_t)i;
+    if (r.right < 0) parent_of_leaf[~r.right] = (int32_t)i; else parent_of_node[r.right] = (int32_t)i;
+    if (i == 0) parent_of_node[0] = -1;
+}
+
+// One thread per primitive (sorted position): gathers its box, then climbs; the second thread to reach a
+// node owns it (its sibling's box is complete and visible after the fence).
+__global__ void __launch_bounds__(256) refit_kernel(uint32_t n, const BoxF* __restrict__ boxes, const uint32_t* __restrict__ order,
+                                                     const RadixNode* __restrict__ nodes, const int32_t* __restrict__ parent_of_node,
+                                                     const int32_t* __restrict__ parent_of_leaf, BoxF* __restrict__ leaf_box,
+                                                     BoxF* __restrict__ node_box, uint32_t* __restrict__ visits) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    leaf_box[p] = boxes[order[p]];
+    __threadfence();
+    int32_t node = parent_of_leaf[p];
+    while (node >= 0) {
+        if (atomicAdd(visits + node, 1u) == 0u) return;  // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        const RadixNode r = nodes[node];
+        const volatile BoxF* lb = r.left < 0 ? leaf_box + ~r.left : node_box + r.left;
+        const volatile BoxF* rb = r.right < 0 ? leaf_box + ~r.right : node_box + r.right;
+        BoxF a, b;
+        for (int k = 0; k < 3; ++k) {
+            a.lo[k] = lb->lo[k]; a.hi[k] = lb->hi[k];
+            b.lo[k] = rb->lo[k]; b.hi[k] = rb->hi[k];
+        }
+        node_box[node] = box_union(a, b);
+        __threadfence();
+        node = parent_of_node[node];
+    }
+}
+
+__global__ void __launch_bounds__(256) flag_kernel(uint32_t n_internal, const RadixNode* __restrict__ nodes, uint32_t max_leaf,
+                                                    uint32_t* __restrict__ keep) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    keep[i] = (nodes[i].last - nodes[i].first + 1u > max_leaf) ? 1u : 0u;
+}
+
+template <bool QUANT>
+__global__ void __launch_bounds__(256) emit_kernel(uint32_t n_internal, const RadixNode* __restrict__ nodes,
+                                                    const uint32_t* __restrict__ keep, const uint32_t* __restrict__ new_index,
+                                                    const BoxF* __restrict__ leaf_box, const BoxF* __restrict__ node_box, EmitParams P,
+                                                    void* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal || keep[i] == 0u) return;
+    const RadixNode r = nodes[i];
+    const BoxF b0 = r.left < 0 ? leaf_box[~r.left] : node_box[r.left];
+    const BoxF b1 = r.right < 0 ? leaf_box[~r.right] : node_box[r.right];
+    const int32_t r0 = child_ref(r.left, nodes, new_index, P.max_leaf), r1 = child_ref(r.right, nodes, new_index, P.max_leaf);
+    if (QUANT) emit32(b0, b1, r0, r1, P, static_cast<Node32*>(out) + new_index[i]);
+    else emit64(b0, b1, r0, r1, P, static_cast<Node64*>(out) + new_index[i]);
+}
+
+// Depth of the emitted tree (kept ancestors of a primitive) and the number of leaf references.
+__global__ void __launch_bounds__(256) depth_kernel(uint32_t n, const RadixNode* __restrict__ nodes, const uint32_t* __restrict__ keep,
+                                                     const int32_t* __restrict__ parent_of_node, const int32_t* __restrict__ parent_of_leaf,
+                                                     uint32_t* __restrict__ out2) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t depth = 0;
+    int32_t node = parent_of_leaf[p];
+    bool leaf_head = true;  // p opens a leaf iff it is the first position of the topmost collapsed subtree above it
+    while (node >= 0) {
+        if (keep[node]) depth += 1;
+        else if (nodes[node].first != p) leaf_head = false;
+        node = parent_of_node[node];
+    }
+    atomicMax(out2, depth);
+    if (leaf_head) atomicAdd(out2 + 1, 1u);
+}
+
+}  // namespace
+
+int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_leaf, double delta, bool quantise,
+                      const double grid_lo[3], const float grid_ext[3], LbvhResult* out, std::string* err) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint32_t n = (uint32_t)boxes.size();
+    if (n < 2 || n <= max_leaf) {
+        if (err) *err = "device LBVH needs more primitives than one leaf holds";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    LB_CUDA(cudaSetDevice(device));
+    // fp32 boxes rounded outward + the centroid frame
+    std::vector<BoxF> hb(n);
+    double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            hb[i].lo[k] = down_f(boxes[i].lo[k]);
+            hb[i].hi[k] = up_f(boxes[i].hi[k]);
+            const double c = 0.5 * (double)hb[i].lo[k] + 0.5 * (double)hb[i].hi[k];
+            clo[k] = std::fmin(clo[k], c);
+            chi[k] = std::fmax(chi[k], c);
+        }
+    }
+    CentroidFrame fr;
+    for (int k = 0; k < 3; ++k) {
+        fr.lo[k] = down_f(clo[k]);
+        const double ext = chi[k] - (double)fr.lo[k];
+        fr.inv_ext[k] = ext > 0.0 ? (float)(1.0 / ext) : 0.0f;
+    }
+    EmitParams P;
+    P.max_leaf = max_leaf;
+    P.quantise = quantise ? 1 : 0;
+    P.delta = delta;
+    for (int k = 0; k < 3; ++k) {
+        P.grid_lo[k] = grid_lo[k];
+        P.grid_ext[k] = (double)grid_ext[k];
+    }
+
+    BoxF *d_boxes = nullptr, *d_leaf_box = nullptr, *d_node_box = nullptr;
+    uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+    uint32_t *d_vals = nullptr, *d_order = nullptr, *d_visits = nullptr, *d_keep = nullptr, *d_new = nullptr, *d_out2 = nullptr;
+    RadixNode* d_nodes = nullptr;
+    int32_t *d_pnode = nullptr, *d_pleaf = nullptr;
+    void *d_tmp = nullptr, *d_emit = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : {(void*)d_boxes, (void*)d_leaf_box, (void*)d_node_box, (void*)d_keys, (void*)d_keys_sorted, (void*)d_vals,
+                        (void*)d_order, (void*)d_visits, (void*)d_keep, (void*)d_new, (void*)d_out2, (void*)d_nodes, (void*)d_pnode,
+                        (void*)d_pleaf, d_tmp})
+            if (p) cudaFree(p);
+    };
+#define LB_TRY(call)                                                            \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            cleanup();                                                          \
+            if (d_emit) cudaFree(d_emit);                                       \
+            return RRT_ERR_CUDA;                                                \
+        }                                                                       \
+    } while (0)
+    const uint32_t ni = n - 1;
+    LB_TRY(cudaMalloc(&d_boxes, (size_t)n * sizeof(BoxF)));
+    LB_TRY(cudaMalloc(&d_leaf_box, (size_t)n * sizeof(BoxF)));
+    LB_TRY(cudaMalloc(&d_node_box, (size_t)ni * sizeof(BoxF)));
+    LB_TRY(cudaMalloc(&d_keys, (size_t)n * sizeof(uint64_t)));
+    LB_TRY(cudaMalloc(&d_keys_sorted, (size_t)n * sizeof(uint64_t)));
+    LB_TRY(cudaMalloc(&d_vals, (size_t)n * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_order, (size_t)n * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_visits, (size_t)ni * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_keep, (size_t)ni * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_new, (size_t)ni * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_out2, 2 * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&d_nodes, (size_t)ni * sizeof(RadixNode)));
+    LB_TRY(cudaMalloc(&d_pnode, (size_t)ni * sizeof(int32_t)));
+    LB_TRY(cudaMalloc(&d_pleaf, (size_t)n * sizeof(int32_t)));
+    LB_TRY(cudaMemcpy(d_boxes, hb.data(), (size_t)n * sizeof(BoxF), cudaMemcpyHostToDevice));
+    LB_TRY(cudaMemset(d_visits, 0, (size_t)ni * sizeof(uint32_t)));
+    LB_TRY(cudaMemset(d_out2, 0, 2 * sizeof(uint32_t)));
+
+    cudaEvent_t e0, e1;
+    LB_TRY(cudaEventCreate(&e0));
+    LB_TRY(cudaEventCreate(&e1));
+    LB_TRY(cudaEventRecord(e0, 0));
+    const unsigned gb = (n + 255) / 256, gi = (ni + 255) / 256;
+    keys_kernel<<<gb, 256>>>(n, d_boxes, fr, d_keys, d_vals);
+    size_t tmp_sort = 0, tmp_scan = 0;
+    LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, 63));
+    LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_keep, d_new, (int)ni));
+    const size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
+    LB_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+    size_t tb = tmp_bytes;
+    LB_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, 63));
+    hierarchy_kernel<<<gi, 256>>>(n, d_keys_sorted, d_nodes, d_pnode, d_pleaf);
+    refit_kernel<<<gb, 256>>>(n, d_boxes, d_order, d_nodes, d_pnode, d_pleaf, d_leaf_box, d_node_box, d_visits);
+    flag_kernel<<<gi, 256>>>(ni, d_nodes, max_leaf, d_keep);
+    tb = tmp_bytes;
+    LB_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_keep, d_new, (int)ni));
+    uint32_t last_keep = 0, last_new = 0;
+    LB_TRY(cudaMemcpy(&last_keep, d_keep + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    LB_TRY(cudaMemcpy(&last_new, d_new + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const uint32_t n_kept = last_new + last_keep;
+    const size_t node_size = quantise ? sizeof(Node32) : sizeof(Node64);
+    LB_TRY(cudaMalloc(&d_emit, (size_t)n_kept * node_size));
+    if (quantise) emit_kernel<true><<<gi, 256>>>(ni, d_nodes, d_keep, d_new, d_leaf_box, d_node_box, P, d_emit);
+    else emit_kernel<false><<<gi, 256>>>(ni, d_nodes, d_keep, d_new, d_leaf_box, d_node_box, P, d_emit);
+    depth_kernel<<<gb, 256>>>(n, d_nodes, d_keep, d_pnode, d_pleaf, d_out2);
+    LB_TRY(cudaEventRecord(e1, 0));
+    LB_TRY(cudaGetLastError());
+    LB_TRY(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    uint32_t out2[2] = {0, 0};
+    LB_TRY(cudaMemcpy(out2, d_out2, sizeof(out2), cudaMemcpyDeviceToHost));
+    out->order.resize(n);
+    LB_TRY(cudaMemcpy(out->order.data(), d_order, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // the root's box (for the caller's world bound): node 0 of the radix tree
+    BoxF root;
+    LB_TRY(cudaMemcpy(&root, d_node_box, sizeof(BoxF), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) {
+        out->root_lo[k] = root.lo[k];
+        out->root_hi[k] = root.hi[k];
+    }
+    cleanup();
+    out->d_nodes = d_emit;
+    out->node_bytes = (size_t)n_kept * node_size;
+    out->n_nodes = n_kept;
+    out->max_depth = out2[0];
+    out->n_leaves = out2[1];
+    out->device_ms = ms;
+    out->total_usec = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return RRT_OK;
+#undef LB_TRY
+}
+
+// Host run of the same per-element code, for the CPU tests (a checker, not a product path): returns the emitted
+// Node64 array, the primitive order and (max depth, leaves).
+int lbvh_host_probe(const std::vector<Aabb>& boxes, uint32_t max_leaf, double delta, bool quantise, const double grid_lo[3],
+                    const float grid_ext[3], std::vector<uint8_t>* nodes_out, std::vector<uint32_t>* order_out, uint32_t* depth_out,
+                    uint32_t* leaves_out) {
+    const uint32_t n = (uint32_t)boxes.size();
+    if (n < 2 || n <= max_leaf) return RRT_ERR_UNSUPPORTED;
+    std::vector<BoxF> hb(n);
+    double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            hb[i].lo[k] = down_f(boxes[i].lo[k]);
+            hb[i].hi[k] = up_f(boxes[i].hi[k]);
+            const double c = 0.5 * (double)hb[i].lo[k] + 0.5 * (double)hb[i].hi[k];
+            clo[k] = std::fmin(clo[k], c);
+            chi[k] = std::fmax(chi[k], c);
+        }
+    float flo[3], finv[3];
+    for (int k = 0; k < 3; ++k) {
+        flo[k] = down_f(clo[k]);
+        const double ext = chi[k] - (double)flo[k];
+        finv[k] = ext > 0.0 ? (float)(1.0 / ext) : 0.0f;
+    }
+    std::vector<std::pair<uint64_t, uint32_t>> kv(n);
+    for (uint32_t i = 0; i < n; ++i) kv[i] = {morton63(hb[i], flo, finv), i};
+    std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t>& order = *order_out;
+    order.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        keys[i] = kv[i].first;
+        order[i] = kv[i].second;
+    }
+    const uint32_t ni = n - 1;
+    std::vector<RadixNode> nodes(ni);
+    std::vector<int32_t> pnode(ni, -1), pleaf(n, -1);
+    for (uint32_t i = 0; i < ni; ++i) {
+        const RadixNode r = radix_node(keys.data(), n, i);
+        nodes[i] = r;
+        if (r.left < 0) pleaf[~r.left] = (int32_t)i; else pnode[r.left] = (int32_t)i;
+        if (r.right < 0) pleaf[~r.right] = (int32_t)i; else pnode[r.right] = (int32_t)i;
+    }
+    std::vector<BoxF> leaf_box(n), node_box(ni);
+    std::vector<uint32_t> visits(ni, 0);
+    for (uint32_t p = 0; p < n; ++p) leaf_box[p] = hb[order[p]];
+    for (uint32_t p = 0; p < n; ++p) {
+        int32_t node = pleaf[p];
+        while (node >= 0) {
+            if (visits[node]++ == 0) break;
+            const RadixNode& r = nodes[node];
+            node_box[node] = box_union(r.left < 0 ? leaf_box[~r.left] : node_box[r.left], r.right < 0 ? leaf_box[~r.right] : node_box[r.right]);
+            node = pnode[node];
+        }
+    }
+    std::vector<uint32_t> keep(ni), new_index(ni);
+    uint32_t n_kept = 0;
+    for (uint32_t i = 0; i < ni; ++i) {
+        keep[i] = nodes[i].last - nodes[i].first + 1u > max_leaf ? 1u : 0u;
+        new_index[i] = n_kept;
+        n_kept += keep[i];
+    }
+    EmitParams P;
+    P.max_leaf = max_leaf;
+    P.quantise = quantise ? 1 : 0;
+    P.delta = delta;
+    for (int k = 0; k < 3; ++k) {
+        P.grid_lo[k] = grid_lo[k];
+        P.grid_ext[k] = (double)grid_ext[k];
+    }
+    const size_t node_size = quantise ? sizeof(Node32) : sizeof(Node64);
+    nodes_out->assign((size_t)n_kept * node_size, 0);
+    for (uint32_t i = 0; i < ni; ++i) {
+        if (!keep[i]) continue;
+        const RadixNode& r = nodes[i];
+        const BoxF b0 = r.left < 0 ? leaf_box[~r.left] : node_box[r.left], b1 = r.right < 0 ? leaf_box[~r.right] : node_box[r.right];
+        const int32_t r0 = child_ref(r.left, nodes.data(), new_index.data(), max_leaf), r1 = child_ref(r.right, nodes.data(), new_index.data(), max_leaf);
+        if (quantise) emit32(b0, b1, r0, r1, P, reinterpret_cast<Node32*>(nodes_out->data()) + new_index[i]);
+        else emit64(b0, b1, r0, r1, P, reinterpret_cast<Node64*>(nodes_out->data()) + new_index[i]);
+    }
+    uint32_t depth = 0, leaves = 0;
+    for (uint32_t p = 0; p < n; ++p) {
+        uint32_t d = 0;
+        bool head = true;
+        for (int32_t node = pleaf[p]; node >= 0; node = pnode[node]) {
+            if (keep[node]) d += 1;
+            else if (nodes[node].first != p) head = false;
+        }
+        depth = std::max(depth, d);
+        leaves += head ? 1 : 0;
+    }
+    *depth_out = depth;
+    *leaves_out = leaves;
+    return RRT_OK;
+}
+
+}  // namespace rrt

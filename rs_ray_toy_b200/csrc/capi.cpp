@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "aggregate.hpp"
+#include "bvh_lbvh.hpp"
 #include "bvh_hlbvh.hpp"
 #include "literal.hpp"
 #include "png_min.hpp"
@@ -290,7 +291,7 @@ int rrt_scene_add_sphere(rrt_scene* scene, const double* obj_to_world_m, const d
 int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t build_flags) {
     if (!scene) return fail(RRT_ERR_INVALID, "rrt_scene_commit: null scene");
     if (scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_commit: already committed");
-    if (build_flags != RRT_BUILD_FAST && build_flags != RRT_BUILD_LITERAL)
+    if (build_flags != RRT_BUILD_FAST && build_flags != RRT_BUILD_LITERAL && build_flags != RRT_BUILD_DEVICE_LBVH)
         return fail(RRT_ERR_INVALID, "rrt_scene_commit: unknown build flags");
     try {
         std::string err;
@@ -302,7 +303,7 @@ int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t buil
         } else {
             auto* fast = new rrt::DeviceAggregate();
             scene->agg.reset(fast);
-            rc = fast->build(scene->ctx->device, scene->host, max_prims_in_node, &err);
+            rc = fast->build(scene->ctx->device, scene->host, max_prims_in_node, &err, build_flags == RRT_BUILD_DEVICE_LBVH);
         }
         if (rc != RRT_OK) {
             scene->agg.reset();
@@ -371,6 +372,52 @@ int rrt_hlbvh_literal_probe(uint32_t n, const double* bounds6, uint32_t max_prim
                 }
             }
             if (ordered) std::memcpy(ordered, tree.ordered.data(), tree.ordered.size() * sizeof(uint32_t));
+        }
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
+int rrt_scene_build_info(const rrt_scene* scene, uint64_t out4[4]) {
+    if (!scene || !out4 || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_build_info: scene not committed");
+    const rrt::AggregateStats& s = scene->agg->stats();
+    out4[0] = s.tree_device_usec;
+    out4[1] = s.n_nodes ? (s.device_bytes - s.n_records * (s.wide_records ? 96u : 48u)) / s.n_nodes : 0;
+    out4[2] = scene->build_flags == RRT_BUILD_DEVICE_LBVH ? 1 : 0;
+    out4[3] = 0;
+    return RRT_OK;
+}
+
+int rrt_lbvh_host_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
+                        uint32_t* n_nodes, uint32_t* node_words16, uint32_t* order, uint32_t info3[3]) {
+    if (!bounds6 || !n_nodes) return fail(RRT_ERR_INVALID, "rrt_lbvh_host_probe: null argument");
+    try {
+        std::vector<rrt::Aabb> b(n);
+        rrt::Aabb world;
+        for (uint32_t i = 0; i < n; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                b[i].lo[k] = bounds6[6 * (size_t)i + k];
+                b[i].hi[k] = bounds6[6 * (size_t)i + 3 + k];
+            }
+            world.grow(b[i]);
+        }
+        const rrt::NodeFrame f = rrt::make_node_frame(world);
+        std::vector<uint8_t> nodes;
+        std::vector<uint32_t> ord;
+        uint32_t depth = 0, leaves = 0;
+        const uint32_t max_leaf = max_prims_in_node == 0 ? 4 : (max_prims_in_node > 8 ? 8 : max_prims_in_node);
+        int rc = rrt::lbvh_host_probe(b, max_leaf, f.delta, false, f.grid_lo, f.grid_ext, &nodes, &ord, &depth, &leaves);
+        if (rc != RRT_OK) return fail(rc, "device LBVH needs more primitives than one leaf holds");
+        *n_nodes = (uint32_t)(nodes.size() / 64);
+        if (info3) {
+            info3[0] = *n_nodes;
+            info3[1] = depth;
+            info3[2] = leaves;
+        }
+        if (*n_nodes <= capacity_nodes) {
+            if (node_words16) std::memcpy(node_words16, nodes.data(), nodes.size());
+            if (order) std::memcpy(order, ord.data(), ord.size() * sizeof(uint32_t));
         }
     } catch (const std::exception& e) {
         return fail(RRT_ERR_INVALID, e.what());

@@ -14,9 +14,9 @@ def oracle_soup(p, idx, tier=O.TIER_F, max_prims=4):
     return O.soup_scene(p, idx, tier, max_prims)
 
 
-def gpu_soup(ctx, p, idx, max_prims=4):
+def gpu_soup(ctx, p, idx, max_prims=4, build_flags=0):
     from rs_ray_toy_b200.aggregate import soup_aggregate
-    return soup_aggregate(ctx, p, idx, max_prims)
+    return soup_aggregate(ctx, p, idx, max_prims, build_flags)
 
 
 def cube_instances(n, extent=50.0, seed=synth.SEED_C2_INSTANCES):
@@ -35,12 +35,12 @@ def oracle_cubes(m, inv, tier=O.TIER_F, max_prims=4):
     return s
 
 
-def gpu_cubes(ctx, m, inv, max_prims=4):
+def gpu_cubes(ctx, m, inv, max_prims=4, build_flags=0):
     from rs_ray_toy_b200.aggregate import GpuAggregate
     a = GpuAggregate(ctx)
     mesh = a.add_mesh(synth.CUBE_P, synth.CUBE_VI, synth.CUBE_N, synth.CUBE_NI)
     a.add_triangles(mesh, 0, instances=(m, inv))
-    return a.commit(max_prims)
+    return a.commit(max_prims, build_flags)
 
 
 def sphere_instances(n, extent=50.0, seed=synth.SEED_C4_SPHERES):
@@ -59,11 +59,11 @@ def oracle_spheres(m, inv, radius=0.5, tier=O.TIER_F, max_prims=4):
     return s
 
 
-def gpu_spheres(ctx, m, inv, radius=0.5, max_prims=4):
+def gpu_spheres(ctx, m, inv, radius=0.5, max_prims=4, build_flags=0):
     from rs_ray_toy_b200.aggregate import GpuAggregate
     a = GpuAggregate(ctx)
     a.add_sphere(radius=radius, instances=(m, inv))
-    return a.commit(max_prims)
+    return a.commit(max_prims, build_flags)
 
 
 def compare_closest(hits, ref_prim, ref_t, rel_tie=1e-6, rel_t=1e-5):

@@ -394,3 +394,46 @@ def test_small_details_in_a_huge_box_keep_fp32_nodes(ctx):
     p, idx = scenes.soup(20000)
     st = scenes.gpu_soup(ctx, p, idx).stats()
     assert (st["device_bytes"] - 48 * st["n_records"]) // st["n_nodes"] == 32, st
+
+
+@pytest.mark.parametrize("quantise", ["0", "1"])
+def test_device_lbvh_build_gives_the_oracles_answers(ctx, quantise, monkeypatch):
+    """RRT_BUILD_DEVICE_LBVH: the tree is built on the GPU (Morton keys, radix sort, binary radix tree).  Tier-F
+    answers do not depend on the tree, so every check of the host-built aggregate must hold unchanged — triangles
+    (fp32 records), rotated instances (f64 records), spheres, both node formats, leaf sizes 1 / 4 / 8."""
+    from rs_ray_toy_b200 import capi
+    monkeypatch.setenv("RRT_QUANTISE", quantise)
+    p, idx = scenes.soup(200000)
+    rays = synth.bounce_rays(p, idx, 200000, seed=43)
+    oracle = scenes.oracle_soup(p, idx)
+    ref = oracle.intersect(rays)
+    sh = synth.shadow_rays_from(rays, (0.5, 0.5, 1.5))
+    occ_ref, _ = oracle.intersect_p(sh)
+    for max_prims in (4, 1, 8):
+        agg = scenes.gpu_soup(ctx, p, idx, max_prims, capi.RRT_BUILD_DEVICE_LBVH)
+        info = agg.build_info()
+        assert info["device_lbvh"] and info["node_bytes"] == (32 if quantise == "1" else 64), info
+        assert 0 < info["tree_device_usec"] < 2_000_000
+        st = agg.stats()
+        assert st["n_leaves"] == st["n_nodes"] + 1 and st["n_records"] == 200000
+        c = _assert_closest(agg.intersect(rays), ref["prim"], ref["t"], ref["uv"])
+        assert c["t_exact"] == c["hits"], c
+        assert (agg.intersect_p(sh) == occ_ref).all()
+    rng = np.random.default_rng(6)
+    rays = np.concatenate([rng.uniform(-12, 12, (60000, 3)), synth.random_unit_vectors(60000, rng), np.full((60000, 1), np.inf)], axis=1)
+    m, inv = scenes.cube_instances(300, extent=8.0)
+    ref = scenes.oracle_cubes(m, inv).intersect(rays)
+    _assert_closest(scenes.gpu_cubes(ctx, m, inv, build_flags=capi.RRT_BUILD_DEVICE_LBVH).intersect(rays), ref["prim"], ref["t"])
+    m, inv = scenes.sphere_instances(2000, extent=10.0)
+    ref = scenes.oracle_spheres(m, inv).intersect(rays)
+    _assert_closest(scenes.gpu_spheres(ctx, m, inv, build_flags=capi.RRT_BUILD_DEVICE_LBVH).intersect(rays), ref["prim"], ref["t"])
+
+
+def test_device_lbvh_small_scenes_fall_back_to_the_host_builder(ctx):
+    from rs_ray_toy_b200 import capi
+    p, idx = scenes.soup(12)
+    rays = synth.bounce_rays(p, idx, 2000, seed=3)
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    agg = scenes.gpu_soup(ctx, p, idx, 4, capi.RRT_BUILD_DEVICE_LBVH)
+    assert agg.build_info()["tree_device_usec"] == 0
+    _assert_closest(agg.intersect(rays), ref["prim"], ref["t"])
