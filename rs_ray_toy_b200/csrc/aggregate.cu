@@ -16,7 +16,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "aggregate.hpp"
@@ -767,6 +770,26 @@ inline float round_up(double v) {
     return f;
 }
 
+// Splits [0, n) over the host threads (per-primitive loops of the commit: baking, record packing).
+template <class F>
+void parallel_ranges(size_t n, F f) {
+    unsigned t = std::thread::hardware_concurrency();
+    if (t == 0) t = 1;
+    if (t > 32) t = 32;
+    if (n < 65536 || t == 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t step = (n + t - 1) / t;
+    for (unsigned k = 0; k < t; ++k) {
+        const size_t a = (size_t)k * step, b = std::min(n, a + step);
+        if (a >= b) break;
+        pool.emplace_back([=]() { f(a, b); });
+    }
+    for (auto& th : pool) th.join();
+}
+
 bool fp32_exact(const double* v, int n) {
     for (int i = 0; i < n; ++i)
         if ((double)(float)v[i] != v[i]) return false;
@@ -800,6 +823,13 @@ DeviceAggregate::~DeviceAggregate() {
 
 int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err, bool device_lbvh) {
     auto t_start = std::chrono::steady_clock::now();
+    const bool timing = std::getenv("RRT_BUILD_TIMING") != nullptr;
+    auto lap = [&, t_last = t_start](const char* what) mutable {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "RRT_BUILD_TIMING %-22s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     device_ = device;
     const size_t n = scene.prims.size();
     if (n == 0) {
@@ -816,8 +846,10 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     };
     std::vector<World> world(n);
     std::vector<Aabb> boxes(n);
+    std::atomic<int> not_fp32{0}, bad_partial{0}, bad_scaled{0};
+    parallel_ranges(n, [&](size_t i0, size_t i1) {
     bool all_fp32 = true;
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = i0; i < i1; ++i) {
         const Primitive& pr = scene.prims[i];
         if (pr.kind == SHAPE_TRIANGLE) {
             scene.world_triangle(i, world[i].v);
@@ -826,8 +858,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         } else {
             const Sphere& s = scene.spheres[pr.shape];
             if (!s.is_full()) {
-                if (err) *err = "partial spheres (z_min/z_max/phi_max) are not on the Tier-F device path yet";
-                return RRT_ERR_UNSUPPORTED;
+                bad_partial = 1;
+                continue;
             }
             // world centre; the instance / object transforms must be rigid (unit scale)
             Vec3d c = s.obj_to_world.point(Vec3d{0, 0, 0});
@@ -845,8 +877,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             double tol = 1e-9;
             if (std::fabs(len(ex) - 1) > tol || std::fabs(len(ey) - 1) > tol || std::fabs(len(ez) - 1) > tol ||
                 std::fabs(dt(ex, ey)) > tol || std::fabs(dt(ex, ez)) > tol || std::fabs(dt(ey, ez)) > tol) {
-                if (err) *err = "scaled / sheared sphere instances are not on the Tier-F device path yet";
-                return RRT_ERR_UNSUPPORTED;
+                bad_scaled = 1;
+                continue;
             }
             world[i].v[0] = c.x;
             world[i].v[1] = c.y;
@@ -863,6 +895,18 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             boxes[i].grow(hi);
         }
     }
+    if (!all_fp32) not_fp32 = 1;
+    });
+    if (bad_partial) {
+        if (err) *err = "partial spheres (z_min/z_max/phi_max) are not on the Tier-F device path yet";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    if (bad_scaled) {
+        if (err) *err = "scaled / sheared sphere instances are not on the Tier-F device path yet";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    const bool all_fp32 = not_fp32 == 0;
+    lap("bake to world space");
     // ---- frame: world box, fp32 margin, Node32 grid, node format ----
     Aabb world_box;
     for (size_t i = 0; i < n; ++i) world_box.grow(boxes[i]);
@@ -888,6 +932,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     const uint32_t max_leaf = max_prims_in_node == 0 ? 4 : (max_prims_in_node > 8 ? 8 : max_prims_in_node);
     const bool on_device = device_lbvh && n > 16 && n > max_leaf;
 
+    lap("frame + node format");
     // ---- tree ----
     Bvh2 tree;
     LbvhResult lb;
@@ -908,6 +953,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         return RRT_ERR_UNSUPPORTED;
     }
 
+    lap(on_device ? "device LBVH (total)" : "host SAH tree");
     // ---- pack: interior nodes in DFS order, leaves become references ----
     std::vector<Node64> nodes;
     nodes.reserve(tree.nodes.size() / 2 + 2);
@@ -915,10 +961,11 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     std::vector<PrimRec48> rec48;
     std::vector<PrimRec96> rec96;
     if (wide)
-        rec96.reserve(n);
+        rec96.resize(n);
     else
-        rec48.reserve(n);
-    auto push_record = [&](uint32_t pi) {
+        rec48.resize(n);
+    size_t n_rec = 0;  // host tree: records are appended leaf by leaf
+    auto make_record = [&](uint32_t pi, size_t slot) {
         {
             const Primitive& pr = scene.prims[pi];
             if (wide) {
@@ -928,7 +975,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                 r.prim_id = pi;
                 r.kind = pr.kind == SHAPE_TRIANGLE ? PRIM_TRIANGLE : PRIM_SPHERE;
                 r.pad[0] = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
-                rec96.push_back(r);
+                rec96[slot] = r;
             } else {
                 PrimRec48 r;
                 std::memset(&r, 0, sizeof(r));
@@ -947,13 +994,13 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                     r.sph.kind = PRIM_SPHERE;
                     r.sph.instance = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
                 }
-                rec48.push_back(r);
+                rec48[slot] = r;
             }
         }
     };
     auto emit_leaf = [&](const Bvh2Node& nd) -> int32_t {
-        uint32_t first = (uint32_t)(wide ? rec96.size() : rec48.size());
-        for (uint32_t k = 0; k < nd.count; ++k) push_record(tree.order[nd.first + k]);
+        uint32_t first = (uint32_t)n_rec;
+        for (uint32_t k = 0; k < nd.count; ++k) make_record(tree.order[nd.first + k], n_rec++);
         return make_leaf_ref(first, nd.count);
     };
     auto set_child = [&](Node64& out, int which, const Aabb& b) {
@@ -972,7 +1019,9 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     };
     if (on_device) {
         // the device tree's leaves are runs of the sorted order: records simply follow it
-        for (size_t r = 0; r < n; ++r) push_record(lb.order[r]);
+        parallel_ranges(n, [&](size_t r0, size_t r1) {
+            for (size_t r = r0; r < r1; ++r) make_record(lb.order[r], r);
+        });
     } else {
         const Bvh2Node& root = tree.nodes[tree.root];
         if (root.count > 0) {
@@ -1054,6 +1103,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             nodes32[i] = o;
         }
     }
+    lap("pack nodes + records");
     // ---- upload ----
     RRT_CUDA(cudaSetDevice(device));
     const size_t node_bytes = on_device ? lb.node_bytes : (quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64));
@@ -1078,6 +1128,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         RRT_CUDA(cudaMalloc(&d_inst_, w2p.size() * sizeof(double)));
         RRT_CUDA(cudaMemcpy(d_inst_, w2p.data(), w2p.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    lap("upload");
     view_.inst_w2p = static_cast<const double*>(d_inst_);
     view_.has_spheres = has_spheres ? 1 : 0;
     view_.nodes = d_nodes_;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -136,14 +138,32 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     // fp32 boxes rounded outward + the centroid frame
     std::vector<BoxF> hb(n);
     double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t i = 0; i < n; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            hb[i].lo[k] = down_f(boxes[i].lo[k]);
-            hb[i].hi[k] = up_f(boxes[i].hi[k]);
-            const double c = 0.5 * (double)hb[i].lo[k] + 0.5 * (double)hb[i].hi[k];
-            clo[k] = std::fmin(clo[k], c);
-            chi[k] = std::fmax(chi[k], c);
-        }
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt == 0 ? 1 : (nt > 32 ? 32 : nt);
+        if (n < 65536) nt = 1;
+        std::vector<std::array<double, 6>> part(nt, {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY});
+        std::vector<std::thread> pool;
+        const size_t step = ((size_t)n + nt - 1) / nt;
+        auto work = [&](unsigned t) {
+            const size_t a = (size_t)t * step, b = std::min<size_t>(n, a + step);
+            for (size_t i = a; i < b; ++i)
+                for (int k = 0; k < 3; ++k) {
+                    hb[i].lo[k] = down_f(boxes[i].lo[k]);
+                    hb[i].hi[k] = up_f(boxes[i].hi[k]);
+                    const double c = 0.5 * (double)hb[i].lo[k] + 0.5 * (double)hb[i].hi[k];
+                    part[t][k] = std::fmin(part[t][k], c);
+                    part[t][3 + k] = std::fmax(part[t][3 + k], c);
+                }
+        };
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        for (unsigned t = 0; t < nt; ++t)
+            for (int k = 0; k < 3; ++k) {
+                clo[k] = std::fmin(clo[k], part[t][k]);
+                chi[k] = std::fmax(chi[k], part[t][3 + k]);
+            }
     }
     CentroidFrame fr;
     for (int k = 0; k < 3; ++k) {
