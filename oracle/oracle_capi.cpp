@@ -431,12 +431,13 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
 }
 // Lights.  24 doubles per light: 0 kind | 1-3 I or L | 4-6 point: p_light, distant: from - to |
 // 7-22 light_to_world m (row-major) | 23 pad.  (The inverse is not needed: vectors use m.)
+// Light table, 80 doubles per light (tests/oracle_scene.py light_row).
 void orc_set_lights(void* sp, uint32_t n, const double* l) {
     RenderSetup& rs = setup_of(sp);
     rs.light_specs.clear();
     rs.light_xf.clear();
     for (uint32_t i = 0; i < n; ++i) {
-        const double* a = l + 24 * (size_t)i;
+        const double* a = l + 80 * (size_t)i;
         Light lt;
         lt.kind = (uint32_t)a[0];
         lt.intensity = Rgb(a[1], a[2], a[3]);
@@ -445,9 +446,41 @@ void orc_set_lights(void* sp, uint32_t n, const double* l) {
         Xform x;
         std::memcpy(x.m.m, a + 7, 16 * sizeof(double));
         x.inv = x.m;  // unused
+        if (lt.kind == LIGHT_DIFFUSE_AREA) {
+            lt.shape_kind = (uint32_t)a[23];
+            Xform o2w, w2o;
+            std::memcpy(o2w.m.m, a + 24, 16 * sizeof(double));
+            std::memcpy(o2w.inv.m, a + 40, 16 * sizeof(double));
+            w2o = xf_inverse(o2w);
+            lt.sphere = sphere_new(o2w, w2o, a[56], a[57], a[58], a[59]);
+            for (int k = 0; k < 3; ++k) {
+                lt.tp[k] = V3(a[60 + 3 * k], a[61 + 3 * k], a[62 + 3 * k]);
+                lt.tn[k] = V3(a[69 + 3 * k], a[70 + 3 * k], a[71 + 3 * k]);
+            }
+            lt.tri_has_n = a[78] != 0.0;
+        }
         rs.light_specs.push_back(lt);
         rs.light_xf.push_back(x);
     }
+}
+
+// DiffuseAreaLight::sample_li probe for one light row (80 doubles): out10 = wi[3], pdf, p_shape[3], L[3].
+void orc_area_light_probe(const double* row80, const double* ref_p3, const double* u2, double* out10) {
+    void* tmp = orc_scene_new(0);
+    orc_set_lights(tmp, 1, row80);
+    RenderSetup& rs = setup_of(tmp);
+    RenderScene sc;
+    V3 wi, p1;
+    double pdf = 0.0;
+    Rgb L = sc.area_sample_li(rs.light_specs[0], V3(ref_p3[0], ref_p3[1], ref_p3[2]), P2(u2[0], u2[1]), &wi, &pdf, &p1);
+    const double o[10] = {wi.x, wi.y, wi.z, pdf, p1.x, p1.y, p1.z, L.c[0], L.c[1], L.c[2]};
+    std::memcpy(out10, o, sizeof(o));
+    for (size_t i = 0; i < g_setups.size(); ++i)
+        if (g_setups[i].first == tmp) {
+            g_setups.erase(g_setups.begin() + i);
+            break;
+        }
+    orc_scene_free(tmp);
 }
 
 // params (doubles):
@@ -479,6 +512,32 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
             Light lt = rs.light_specs[i];
             if (lt.kind == LIGHT_POINT) {
                 lt.p_light = V3(0.0, 0.0, 0.0);  // Q17: PointLight::new(.., Point3f::default(), ..), light_to_world unused
+            } else if (lt.kind == LIGHT_DIFFUSE_AREA) {
+                // the light's own shape, kept apart from the aggregate (Shape::pdf_ref intersects it)
+                Geometry& lg = job.scene.light_shapes;
+                lg.q = s->geom.q;
+                GeoPrim g;
+                g.material = -1;
+                if (lt.shape_kind == 0) {
+                    lg.spheres.push_back(lt.sphere);
+                    g.kind = SHAPE_SPHERE;
+                    g.a = (int32_t)lg.spheres.size() - 1;
+                    g.b = 0;
+                } else {
+                    TriMesh m;
+                    m.p = {lt.tp[0], lt.tp[1], lt.tp[2]};
+                    m.vi = {0, 1, 2};
+                    if (lt.tri_has_n) {
+                        m.n = {lt.tn[0], lt.tn[1], lt.tn[2]};
+                        m.ni = {0, 1, 2};
+                    }
+                    lg.meshes.push_back(m);
+                    g.kind = SHAPE_TRIANGLE;
+                    g.a = (int32_t)lg.meshes.size() - 1;
+                    g.b = 0;
+                }
+                lg.geos.push_back(g);
+                lt.probe_geo = (int)lg.geos.size() - 1;
             } else {
                 lt.w_light = normalize_vec(xf_vector(rs.light_xf[i], lt.w_light));  // distant.rs:30
                 b3_bounding_sphere(wb, &lt.world_center, &lt.world_radius);
@@ -519,7 +578,7 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
             uint64_t v[16] = {st.camera_rays, st.extension_rays, st.shadow_rays, st.bounces, st.zero_weight, st.asserts,
                               st.closest.rays, st.closest.nodes_visited, st.closest.prims_tested, st.closest.max_stack,
                               st.any.rays, st.any.nodes_visited, st.any.prims_tested, st.any.max_stack,
-                              st.closest.stack_overflow + st.any.stack_overflow, 0};
+                              st.closest.stack_overflow + st.any.stack_overflow, st.mis_probe_rays};
             std::memcpy(stats16, v, sizeof(v));
         }
         if (dump_count) *dump_count = job.dump.size();

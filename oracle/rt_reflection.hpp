@@ -572,15 +572,27 @@ inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_l
     }
 }
 
-// ---- lights (lights/{point,distant}.rs) -------------------------------------------------------------
-enum LightKind : uint32_t { LIGHT_POINT = 0, LIGHT_DISTANT = 1 };
+// ---- lights (lights/{point,distant,diffuse}.rs) -----------------------------------------------------
+enum LightKind : uint32_t { LIGHT_POINT = 0, LIGHT_DISTANT = 1, LIGHT_DIFFUSE_AREA = 2 };
 struct Light {
     uint32_t kind = LIGHT_POINT;
-    Rgb intensity;        // point: I ; distant: L (already l * scale)
+    Rgb intensity;        // point: I ; distant: L (already l * scale) ; diffuse area: lemit
     V3 p_light;           // point: always (0,0,0) in the reference (Q17, renderprocess.rs:996)
     V3 w_light;           // distant: normalised light_to_world(from - to)
     V3 world_center;      // distant
     double world_radius = 0;
+    // DiffuseAreaLight (lights/diffuse.rs): the shape it samples — make_light_shape (renderprocess.rs:1078-1095)
+    // gives a Sphere with its own transform, or triangle `tri_num` of a loaded mesh (vertices untransformed, Q7).
+    // The shape is NOT part of the aggregate and no primitive carries an area light (Q22): the emitter is invisible.
+    uint32_t shape_kind = 0;  // 0 sphere, 1 triangle
+    Sphere sphere;
+    V3 tp[3], tn[3];
+    bool tri_has_n = false;
+    int probe_geo = -1;       // index of the shape in RenderScene::light_shapes (Shape::pdf_ref's intersect)
+    double area() const {
+        if (shape_kind == 0) return sphere.phi_max * sphere.radius * (sphere.z_max - sphere.z_min);  // sphere.rs:261-263
+        return 0.5 * length(cross(tp[1] - tp[0], tp[2] - tp[0]));                                     // triangle.rs:419-424
+    }
 };
 
 }  // namespace orc

@@ -21,6 +21,7 @@ enum IntegratorKind : uint32_t { INTEGRATOR_PATH = 0, INTEGRATOR_DIRECT = 1 };
 
 struct RenderStats {
     uint64_t camera_rays = 0, extension_rays = 0, shadow_rays = 0, bounces = 0, zero_weight = 0, asserts = 0;
+    uint64_t mis_probe_rays = 0;  // estimate_direct's BSDF-sampled rays towards an area light (they cannot add radiance, Q22)
     TraversalStats closest, any;
 };
 
@@ -43,6 +44,7 @@ struct RenderScene {
     const BVH* bvh = nullptr;
     std::vector<Material> materials;
     std::vector<Light> lights;
+    Geometry light_shapes;  // the area lights' shapes, for Shape::pdf_ref (they are not in the aggregate)
     bool fix_q9 = false;
 
     // Scene::intersect (scene.rs:69-72)
@@ -93,20 +95,107 @@ struct RenderScene {
         *p1 = p + l.w_light * (2.0 * l.world_radius);
         return l.intensity;
     }
-    // estimate_direct (integrator/mod.rs:403-558) — both in-scope lights are delta lights, so the
-    // BSDF-sampling half (:484-556) never runs.
-    Rgb estimate_direct(const SI& si, const Bsdf& bsdf, const Light& light, RenderStats* st) const {
+    // Shape::sample (sphere.rs:265-284: uniform over the WHOLE sphere whatever z_min / z_max / phi_max say;
+    // triangle.rs:393-417: "barycentrics" drawn with uniform_sample_sphere, Q20) — point and normal only.
+    static void shape_sample(const Light& l, P2 u, V3* p, V3* n) {
+        if (l.shape_kind == 0) {
+            const Sphere& s = l.sphere;
+            V3 p_obj = V3(0.0, 0.0, 0.0) + uniform_sample_sphere(u) * s.radius;
+            *n = normalize_vec(xf_normal(s.o2w, p_obj));
+            p_obj = p_obj * (s.radius / distance(p_obj, V3(0.0, 0.0, 0.0)));
+            *p = xf_point(s.o2w, p_obj);
+            return;
+        }
+        V3 b = uniform_sample_sphere(u);
+        *p = l.tp[0] * b.x + l.tp[1] * b.y + l.tp[2] * b.z;
+        *n = normalize_vec(cross(l.tp[1] - l.tp[0], l.tp[2] - l.tp[0]));
+        if (l.tri_has_n) {
+            V3 ns = l.tn[0] * b.x + l.tn[1] * b.y + l.tn[2] * b.z;
+            *n = faceforward(*n, ns);
+        }
+    }
+    // DiffuseAreaLight::sample_li (diffuse.rs:62-79) over Shape::sample_ref (shape/mod.rs:33-48).  NB sample_ref
+    // ASSIGNS the solid-angle conversion factor to *pdf instead of multiplying the 1 / area from Shape::sample
+    // by it (Q28): light_pdf = distance^2 / |cos| with no area in it.
+    Rgb area_sample_li(const Light& l, V3 ref_p, P2 u, V3* wi, double* pdf, V3* p1) const {
+        V3 ps, ns;
+        shape_sample(l, u, &ps, &ns);
+        V3 w = ps - ref_p;
+        double len_sq = length_sq(w);
+        if (len_sq == 0.0) {
+            *pdf = 0.0;
+        } else {
+            w = normalize_vec(w);
+            *pdf = len_sq / absdot(-w, ns);
+            if (std::isinf(*pdf)) *pdf = 0.0;
+        }
+        if (*pdf == 0.0 || length_sq(ps - ref_p) == 0.0) {
+            *pdf = 0.0;
+            return Rgb();
+        }
+        *wi = normalize_vec(ps - ref_p);
+        *p1 = ps;
+        return dot(ns, -*wi) > 0.0 ? l.intensity : Rgb();  // AreaLight::l (diffuse.rs:134-140)
+    }
+    // Light::pdf_li -> Shape::pdf_ref (shape/mod.rs:49-66): intersect the light's own shape
+    double area_pdf_li(const Light& l, V3 ref_p, V3 wi) const {
+        Ray r = ray_new_od(ref_p, wi);
+        double thit = 0.0, a = 0.0, b = 0.0;
+        SI ist;
+        const GeoPrim& g = light_shapes.geos[l.probe_geo];
+        bool hit = g.kind == SHAPE_TRIANGLE ? light_shapes.tri_intersect(g, r, &thit, &a, &b, &ist, true)
+                                            : light_shapes.sph_intersect(g, r, &thit, &a, &b, &ist, true);
+        if (!hit) return 0.0;
+        double pdf = length_sq(ref_p - ist.p) / (absdot(-wi, ist.n) * l.area());
+        if (std::isinf(pdf)) pdf = 0.0;
+        return pdf;
+    }
+    // estimate_direct (integrator/mod.rs:403-558), specular = false, no media
+    Rgb estimate_direct(const SI& si, const Bsdf& bsdf, const Light& light, P2 u_light, P2 u_scattering, RenderStats* st) const {
         const uint8_t flags = BXDF_ALL & ~BXDF_SPECULAR;
+        const bool delta = light.kind != LIGHT_DIFFUSE_AREA;
         Rgb ld;
         V3 wi, p1;
-        double light_pdf = 0.0;
-        Rgb li = sample_li(light, si.p, &wi, &light_pdf, &p1);
+        double light_pdf = 0.0, scattering_pdf = 0.0;
+        Rgb li = delta ? sample_li(light, si.p, &wi, &light_pdf, &p1) : area_sample_li(light, si.p, u_light, &wi, &light_pdf, &p1);
         if (light_pdf > 0.0 && !li.is_black()) {
             Rgb f;
-            if (bsdf.present) f = bsdf.f(si.wo, wi, flags) * absdot(wi, si.sh.n);
+            if (bsdf.present) {
+                f = bsdf.f(si.wo, wi, flags) * absdot(wi, si.sh.n);
+                scattering_pdf = bsdf.pdf(si.wo, wi, flags);
+            }
             if (!f.is_black()) {
                 if (!unoccluded(si.p, p1, st)) li = Rgb();
-                if (!li.is_black()) ld += f * li / light_pdf;
+                if (!li.is_black()) {
+                    if (delta) {
+                        ld += f * li / light_pdf;
+                    } else {
+                        double weight = power_heuristic(1, light_pdf, 1, scattering_pdf);
+                        ld += li * f * weight / light_pdf;
+                    }
+                }
+            }
+        }
+        // Sample BSDF with multiple importance sampling (:484-556).  For an area light the ray found this way can
+        // only add radiance through `light_isect.primitive.get_arealight()`, which is None for every primitive the
+        // loader creates (Q22), or through Light::le, which is zero for everything but an infinite light: the whole
+        // half is traced and then contributes nothing.  Restated (and counted) for completeness.
+        if (!delta && bsdf.present) {
+            uint8_t sampled = 0;
+            Rgb f = bsdf.sample_f(si.wo, &wi, u_scattering, &scattering_pdf, flags, &sampled);
+            f = f * absdot(wi, si.sh.n);
+            bool sampled_specular = (sampled & BXDF_SPECULAR) != 0;
+            if (!f.is_black() && scattering_pdf > 0.0) {
+                if (!sampled_specular) {
+                    light_pdf = area_pdf_li(light, si.p, wi);
+                    if (light_pdf == 0.0) return ld;
+                }
+                Ray ray = ray_new_od(si.p, wi);
+                SI light_isect;
+                HitRecord h;
+                if (st) st->mis_probe_rays += 1;
+                bvh->intersect(ray, &h, &light_isect, nullptr);
+                // found: get_arealight() is None -> li = 0; not found: Light::le = 0 (lights/mod.rs:37-39)
             }
         }
         return ld;
@@ -125,9 +214,9 @@ struct RenderScene {
             light_num = std::min<size_t>((size_t)rust_as_u64(sampler.get_1d() * (double)n_lights), n_lights - 1);
             light_pdf = 1.0 / (double)n_lights;
         }
-        sampler.get_2d();  // u_light (delta lights ignore it)
-        sampler.get_2d();  // u_scattering
-        return estimate_direct(si, bsdf, lights[light_num], st) / light_pdf;
+        P2 u_light = sampler.get_2d();       // delta lights ignore it
+        P2 u_scattering = sampler.get_2d();
+        return estimate_direct(si, bsdf, lights[light_num], u_light, u_scattering, st) / light_pdf;
     }
 };
 
@@ -314,6 +403,7 @@ struct RenderJob {
             stats.bounces += s.bounces;
             stats.zero_weight += s.zero_weight;
             stats.asserts += s.asserts;
+            stats.mis_probe_rays += s.mis_probe_rays;
             for (TraversalStats* pair : {&stats.closest, &stats.any}) {
                 TraversalStats& src = (pair == &stats.closest) ? s.closest : s.any;
                 pair->rays += src.rays;

@@ -59,6 +59,13 @@ inline V3 cosine_sample_hemisphere(P2 u) {
     double z = std::sqrt(rmax(0.0, 1.0 - d.x * d.x - d.y * d.y));
     return V3(d.x, d.y, z);
 }
+// sampling.rs:233-242
+inline V3 uniform_sample_sphere(P2 u) {
+    double z = 1.0 - 2.0 * u.x;
+    double r = std::sqrt(rmax(0.0, 1.0 - z * z));
+    double phi = 2.0 * PI * u.y;
+    return V3(r * std::cos(phi), r * std::sin(phi), z);
+}
 // sampling.rs:324-328
 inline double power_heuristic(int nf, double f_pdf, int ng, double g_pdf) {
     double f = nf * f_pdf, g = ng * g_pdf;

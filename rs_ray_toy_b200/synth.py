@@ -236,6 +236,34 @@ def scene_c1(directory, xres=640, yres=360, nsamp=17, integrator="Path", max_dep
     return path
 
 
+def scene_area_lights(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
+    """Config 1's cubes lit by two DiffuseAreaLights: a sphere emitter above the cubes and
+    triangle 4 of cube.obj (the light shape is the raw mesh triangle, Q7), plus one point light.  The emitters
+    are sampled for next-event estimation only — the loader attaches no area light to any primitive (Q22)."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    write_cube_obj(os.path.join(directory, "cube.obj"))
+    cfg = json.loads(open(scene_c1(directory, xres=xres, yres=yres, nsamp=nsamp, integrator=integrator, max_depth=max_depth)).read())
+    cfg["materials"] = [{"material_type": "MatteMaterial", "material_name": "mat_matte"},
+                        {"material_type": "PlasticMaterial", "material_name": "mat_plastic"}]
+    cfg["lights"] = [
+        {"light_type": "diffuse", "spectrum": {"values": [40, 36, 30]}, "n_samples": 1,
+         "light_shape": {"shape_type": "sphere", "radius": 1.5, "world_pos": [33.0, 6.0, -1.0]}},
+        {"light_type": "diffuse", "spectrum": {"values": [5, 30, 60]},
+         "light_shape": {"shape_type": "triangle", "obj_name": "cube_01", "tri_num": 4}},
+        {"light_type": "point", "spectrum": {"values": [300, 300, 300]}}]
+    prim = cfg["Aggregate"]["primitives"][0]
+    second = dict(prim)
+    second["material_name"] = "mat_plastic"
+    second["instances"] = [{"world_pos": [36.5, 2.2, -0.6], "scale": [1, 1, 1], "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 20}]
+    cfg["Aggregate"]["primitives"] = [prim, second]
+    path = os.path.join(directory, "scene_area.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_c2(directory, n_instances=10000, xres=1920, yres=1080, nsamp=2, extent=50.0, seed=SEED_C2_INSTANCES):
     """Config 2: the cube instanced `n_instances` times (random position / axis / angle, unit scale),
     Matte, one point light (which sits at the origin whatever its world_pos, Q17), DirectLighting

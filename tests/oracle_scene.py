@@ -154,9 +154,15 @@ def material_row(cfg, tex: Textures):
     return r
 
 
-def light_row(cfg):
-    """make_light (renderprocess.rs:967-1053): point and distant."""
-    r = np.zeros(24)
+LIGHT_ROW = 80
+
+
+def light_row(cfg, meshes=None):
+    """make_light (renderprocess.rs:967-1053): point, distant and diffuse (area) lights.
+    Row: 0 kind | 1-3 intensity / lemit | 4-6 dir | 7-22 light_to_world | 23 shape kind (0 sphere, 1 triangle) |
+    24-39 sphere obj_to_world | 40-55 its inverse | 56 radius 57 z_min 58 z_max 59 phi_max (deg) |
+    60-68 triangle p0 p1 p2 | 69-77 its vertex normals | 78 has normals."""
+    r = np.zeros(LIGHT_ROW)
     m, _ = to_world(cfg)
     r[7:23] = m.reshape(16)
     t = cfg.get("light_type")
@@ -168,6 +174,27 @@ def light_row(cfg):
         l, sc = np.array(_spectrum(cfg, "l", 1.0)), np.array(_spectrum(cfg, "scale", 1.0))
         r[1:4] = l * sc
         r[4:7] = np.array(_xyz(cfg, "from", (0, 0, 0))) - np.array(_xyz(cfg, "to", (0, 0, 1)))
+    elif t == "diffuse":
+        r[0] = 2
+        r[1:4] = _spectrum(cfg, "spectrum", 1.0)
+        shp = cfg["light_shape"]           # "Shape Required for a DiffuseLight!" (renderprocess.rs:1015)
+        if shp.get("shape_type") == "sphere":   # make_sphere (renderprocess.rs:1097-1106)
+            sm, sinv = to_world(shp)
+            radius = float(shp.get("radius", 1.0))
+            r[23] = 0
+            r[24:40] = sm.reshape(16)
+            r[40:56] = sinv.reshape(16)
+            r[56:60] = [radius, float(shp.get("z_min", -radius)), float(shp.get("z_max", radius)), float(shp.get("phi_max", 360.0))]
+        elif shp.get("shape_type") == "triangle":  # mesh[tri_num] of a loaded obj, vertices untransformed (Q7)
+            mesh = meshes[shp.get("obj_name", "")]
+            k = int(shp.get("tri_num", 0))
+            r[23] = 1
+            r[60:69] = mesh["p"][mesh["vi"][k]].reshape(9)
+            if mesh["n"] is not None and len(mesh["n"]) and mesh["ni"] is not None and len(mesh["ni"]):
+                r[69:78] = mesh["n"][mesh["ni"][k]].reshape(9)
+                r[78] = 1
+        else:
+            raise ValueError("Failed to parse a Shape (renderprocess.rs:1094)")
     else:
         raise ValueError(f"light type {t!r} is outside the restated subset")
     return r
@@ -265,7 +292,7 @@ class LoadedScene:
                 else:
                     s.add_prims(g0, nt, -1)
         s.build(int(agg.get("max_prims_in_node", 4)))
-        self.lights = np.array([light_row(l) for l in (cfg.get("lights", []) or [])]).reshape(-1, 24)
+        self.lights = np.array([light_row(l, meshes) for l in (cfg.get("lights", []) or [])]).reshape(-1, LIGHT_ROW)
         L = O.lib()
         L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -297,7 +324,7 @@ def oracle_render(scene, prm, lens, nthreads=None, want_dump=False):
         raise RuntimeError(L.orc_last_error().decode())
     names = ["camera_rays", "extension_rays", "shadow_rays", "bounces", "zero_weight", "asserts", "closest_rays",
              "closest_nodes", "closest_prims", "closest_max_stack", "any_rays", "any_nodes", "any_prims", "any_max_stack",
-             "stack_overflow", "_"]
+             "stack_overflow", "mis_probe_rays"]
     out = {"rgb": rgb, "raw": raw, "stats": {k: int(v) for k, v in zip(names, stats)}}
     if want_dump:
         out["dump"] = dump[: min(cap, cnt.value)]
