@@ -168,14 +168,24 @@ typedef struct rrt_material {
     double eta;                       /* Glass index                                            */
 } rrt_material;
 
-/* lights/point.rs, lights/distant.rs (make_light, renderprocess.rs:967-1053).                   */
-typedef enum rrt_light_kind { RRT_LIGHT_POINT = 0, RRT_LIGHT_DISTANT = 1 } rrt_light_kind;
+/* lights/point.rs, lights/distant.rs, lights/diffuse.rs (make_light, renderprocess.rs:967-1053).
+ * A DiffuseAreaLight samples a shape of its own — make_light_shape (renderprocess.rs:1078-1095): a Sphere with its
+ * own transform, or one triangle of a loaded mesh (untransformed vertices, Q7).  That shape is not in the aggregate
+ * and the loader attaches no area light to any primitive (Q22): the emitter is sampled by next-event estimation only. */
+typedef enum rrt_light_kind { RRT_LIGHT_POINT = 0, RRT_LIGHT_DISTANT = 1, RRT_LIGHT_DIFFUSE_AREA = 2 } rrt_light_kind;
+typedef enum rrt_light_shape_kind { RRT_LIGHT_SHAPE_SPHERE = 0, RRT_LIGHT_SHAPE_TRIANGLE = 1 } rrt_light_shape_kind;
 typedef struct rrt_light {
     uint32_t kind;
-    uint32_t pad;
-    double intensity[3];  /* point: I ("spectrum"); distant: l * scale                          */
+    uint32_t shape_kind;  /* area: rrt_light_shape_kind                                          */
+    double intensity[3];  /* point: I ("spectrum"); distant: l * scale; area: lemit ("spectrum") */
     double dir[3];        /* distant: from - to                                                 */
     double to_world[16];  /* light_to_world matrix, row-major (unused by point lights: Q17)     */
+    /* area light shape */
+    double shape_to_world[16], shape_to_world_inv[16]; /* sphere: make_sphere's transform and inverse */
+    double radius, z_min, z_max, phi_max_deg;          /* sphere (sampling ignores the clipping; area() does not) */
+    double tri_p[9];      /* triangle: p0 p1 p2                                                 */
+    double tri_n[9];      /* triangle: vertex normals (when tri_has_n)                          */
+    uint32_t tri_has_n, pad;
 } rrt_light;
 
 typedef enum rrt_filter_kind { RRT_FILTER_BOX = 0, RRT_FILTER_GAUSSIAN = 1, RRT_FILTER_TRIANGLE = 2 } rrt_filter_kind;

@@ -382,12 +382,16 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                         uint64_t k = as_u64(ul * (double)ip.n_lights);
                         light_num = k > ip.n_lights - 1 ? ip.n_lights - 1 : (uint32_t)k;
                     }
-                    p.dim += 4;  // u_light, u_scattering: drawn, unused by delta lights
-                    // ---- estimate_direct (integrator/mod.rs:403-481), delta lights only ----
-                    const LightRec lt = sc.lights[light_num];
-                    V3 wi, p1;
+                    // ---- estimate_direct (integrator/mod.rs:403-481) ----
+                    const LightRec& lt = sc.lights[light_num];
+                    V3 wi = v3(0, 0, 0), p1 = v3(0, 0, 0);
                     Rgb li;
-                    if (lt.kind == RRT_LIGHT_POINT) {  // point.rs:55-77
+                    double light_pdf = 1.0;
+                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA;
+                    if (area) {  // diffuse.rs:62-79; u_light is dimensions dim, dim + 1 of this sample
+                        const P2 u_light = {halton_sample(ht, perms, p.hidx, p.dim), halton_sample(ht, perms, p.hidx, p.dim + 1)};
+                        li = area_sample_li(lt, s.p, u_light, &wi, &light_pdf, &p1);
+                    } else if (lt.kind == RRT_LIGHT_POINT) {  // point.rs:55-77
                         wi = normalize(lt.p_light - s.p);
                         p1 = lt.p_light;
                         li = lt.intensity / length_sq(lt.p_light - s.p);
@@ -396,11 +400,22 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                         p1 = s.p + lt.w_light * (2.0 * lt.world_radius);
                         li = lt.intensity;
                     }
-                    if (!is_black(li)) {
+                    p.dim += 4;  // u_light, u_scattering: always drawn (integrator/mod.rs:385-386)
+                    if (light_pdf > 0.0 && !is_black(li)) {
                         const Rgb f = bsdf_f(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR) * absdot(wi, s.shn);
                         if (!is_black(f)) {
-                            // ld = f * li / light_pdf(=1), then / the light-choice pdf, then * beta
-                            Rgb ld = (f * li / 1.0) / ip.light_pdf;
+                            // delta light: ld = f * li / light_pdf(=1); area light: li * f * w / light_pdf with
+                            // w = power_heuristic(light_pdf, bsdf pdf).  Then / the light-choice pdf, then * beta.
+                            // estimate_direct's second, BSDF-sampling half (:484-556) is not run: the ray it traces
+                            // can only add radiance through get_arealight(), None for every primitive (Q22), or
+                            // through Light::le, zero for these lights — the oracle traces and counts those rays.
+                            Rgb ld;
+                            if (area) {
+                                const double weight = power_heuristic(1, light_pdf, 1, bsdf_pdf(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR));
+                                ld = (li * f * weight / light_pdf) / ip.light_pdf;
+                            } else {
+                                ld = (f * li / 1.0) / ip.light_pdf;
+                            }
                             contrib = ip.kind == RRT_INTEGRATOR_PATH ? p.beta * ld : ld;
                             emit_sh = true;
                             so = s.p;
@@ -935,6 +950,25 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
                 std::memcpy(m.m, l.to_world, sizeof(m.m));
                 r.w_light = normalize(xf_vector(m34_of(m), v3(l.dir[0], l.dir[1], l.dir[2])));  // distant.rs:30
                 r.world_radius = radius;
+            } else if (l.kind == RRT_LIGHT_DIFFUSE_AREA) {
+                r.shape_kind = l.shape_kind;
+                if (l.shape_kind == RRT_LIGHT_SHAPE_SPHERE) {
+                    Mat4 m, mi;
+                    std::memcpy(m.m, l.shape_to_world, sizeof(m.m));
+                    std::memcpy(mi.m, l.shape_to_world_inv, sizeof(mi.m));
+                    r.o2w = m34_of(m);
+                    r.w2o = m34_of(mi);
+                    r.radius = l.radius;
+                } else if (l.shape_kind == RRT_LIGHT_SHAPE_TRIANGLE) {
+                    for (int k = 0; k < 3; ++k) {
+                        r.tp[k] = v3(l.tri_p[3 * k], l.tri_p[3 * k + 1], l.tri_p[3 * k + 2]);
+                        r.tn[k] = v3(l.tri_n[3 * k], l.tri_n[3 * k + 1], l.tri_n[3 * k + 2]);
+                    }
+                    r.tri_has_n = l.tri_has_n;
+                } else {
+                    if (err) *err = "area light shape must be a sphere or a triangle (renderprocess.rs:1078-1095)";
+                    return RRT_ERR_INVALID;
+                }
             } else if (l.kind != RRT_LIGHT_POINT) {
                 if (err) *err = "light kind outside the hot-path scope";
                 return RRT_ERR_UNSUPPORTED;

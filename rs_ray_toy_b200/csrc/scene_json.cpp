@@ -364,8 +364,40 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
                     l.intensity[k] = li[k] * sc[k];
                     l.dir[k] = from[k] - to[k];
                 }
+            } else if (type == "diffuse") {  // renderprocess.rs:999-1017
+                l.kind = RRT_LIGHT_DIFFUSE_AREA;
+                read_spectrum(*lc, "spectrum", l.intensity, 1.0);
+                const Value* sc = lc->get("light_shape");
+                if (!sc) throw std::runtime_error("Shape Required for a DiffuseLight! (renderprocess.rs:1015)");
+                const std::string st = read_string(*sc, "shape_type", "");
+                if (st == "sphere") {  // make_sphere (renderprocess.rs:1097-1106)
+                    l.shape_kind = RRT_LIGHT_SHAPE_SPHERE;
+                    const Transform sx = make_to_world(*sc);
+                    std::memcpy(l.shape_to_world, sx.m.m, sizeof(l.shape_to_world));
+                    std::memcpy(l.shape_to_world_inv, sx.inv.m, sizeof(l.shape_to_world_inv));
+                    l.radius = read_f64(*sc, "radius", 1.0);
+                    l.z_min = read_f64(*sc, "z_min", -l.radius);
+                    l.z_max = read_f64(*sc, "z_max", l.radius);
+                    l.phi_max_deg = read_f64(*sc, "phi_max", 360.0);
+                } else if (st == "triangle") {  // mesh[tri_num] of a loaded obj (renderprocess.rs:1084-1090)
+                    l.shape_kind = RRT_LIGHT_SHAPE_TRIANGLE;
+                    auto oit = mesh_index.find(read_string(*sc, "obj_name", ""));
+                    if (oit == mesh_index.end()) throw std::runtime_error("area light: unknown obj_name");
+                    const TriangleMesh& m = out->scene.meshes[oit->second];
+                    const uint32_t k = (uint32_t)read_f64(*sc, "tri_num", 0.0);
+                    if (k >= m.n_triangles()) throw std::runtime_error("area light: tri_num out of range");
+                    for (int v = 0; v < 3; ++v)
+                        for (int c = 0; c < 3; ++c) l.tri_p[3 * v + c] = m.p[3 * (size_t)m.vi[3 * k + v] + c];
+                    if (!m.n.empty() && !m.ni.empty()) {
+                        l.tri_has_n = 1;
+                        for (int v = 0; v < 3; ++v)
+                            for (int c = 0; c < 3; ++c) l.tri_n[3 * v + c] = m.n[3 * (size_t)m.ni[3 * k + v] + c];
+                    }
+                } else {
+                    throw std::runtime_error("Failed to parse a Shape (renderprocess.rs:1094)");
+                }
             } else {
-                throw std::runtime_error("light type '" + type + "' is outside the hot-path scope (point, distant)");
+                throw std::runtime_error("light type '" + type + "' is outside the hot-path scope (point, distant, diffuse)");
             }
             out->lights.push_back(l);
         }

@@ -41,11 +41,16 @@ struct MaterialRec {  // rrt_material, flattened
     double sigma, roughness, u_roughness, v_roughness, eta;
 };
 struct LightRec {
-    uint32_t kind, pad;
-    Rgb intensity;
+    uint32_t kind, shape_kind;
+    Rgb intensity;    // point: I; distant: L; diffuse area: lemit
     V3 p_light;       // point
     V3 w_light;       // distant (normalised, world space)
     double world_radius;
+    // DiffuseAreaLight's shape (lights/diffuse.rs; renderprocess.rs:1078-1106)
+    M34 o2w, w2o;     // sphere
+    double radius;
+    V3 tp[3], tn[3];  // triangle vertices and vertex normals
+    uint32_t tri_has_n, pad;
 };
 struct ShadeScene {
     const PrimInfo* prims;
@@ -471,6 +476,66 @@ static __device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     }
     return f;
 }
+// Bsdf::pdf (reflection.rs:382-404)
+static __device__ double bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    if (b.n_lobes == 0) return 0.0;
+    V3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
+    if (wo.z == 0.0) return 0.0;
+    double pdf = 0.0;
+    int matching = 0;
+    for (int i = 0; i < b.n_lobes; ++i)
+        if (lobe_matches(b.lobes[i], flags)) {
+            matching += 1;
+            pdf += lobe_pdf(b.lobes[i], wo, wi);
+        }
+    return matching > 0 ? pdf / (double)matching : 0.0;
+}
+// sampling.rs:233-242
+__device__ __forceinline__ V3 uniform_sample_sphere(P2 u) {
+    double z = 1.0 - 2.0 * u.x;
+    double r = sqrt(rmax(0.0, 1.0 - z * z));
+    double phi = 2.0 * kPi * u.y;
+    return v3(r * cos(phi), r * sin(phi), z);
+}
+// sampling.rs:324-328
+__device__ __forceinline__ double power_heuristic(int nf, double f_pdf, int ng, double g_pdf) {
+    double f = (double)nf * f_pdf, g = (double)ng * g_pdf;
+    return (f * f) / (f * f + g * g);
+}
+// DiffuseAreaLight::sample_li (diffuse.rs:62-79) over Shape::sample_ref (shape/mod.rs:33-48) over Shape::sample
+// (sphere.rs:265-284: uniform over the whole sphere; triangle.rs:393-417: "barycentrics" from uniform_sample_sphere,
+// Q20).  sample_ref ASSIGNS distance^2 / |cos| to the pdf, dropping Shape::sample's 1 / area (Q28).
+static __device__ Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, double* pdf, V3* p1) {
+    V3 ps, ns;
+    if (l.shape_kind == 0) {
+        V3 p_obj = v3(0.0, 0.0, 0.0) + uniform_sample_sphere(u) * l.radius;
+        ns = normalize_n(xf_normal_inv(l.w2o, p_obj));
+        p_obj = p_obj * (l.radius / length(p_obj - v3(0.0, 0.0, 0.0)));
+        ps = xf_point(l.o2w, p_obj);
+    } else {
+        V3 b = uniform_sample_sphere(u);
+        ps = l.tp[0] * b.x + l.tp[1] * b.y + l.tp[2] * b.z;
+        ns = normalize(cross(l.tp[1] - l.tp[0], l.tp[2] - l.tp[0]));
+        if (l.tri_has_n) ns = faceforward(ns, l.tn[0] * b.x + l.tn[1] * b.y + l.tn[2] * b.z);
+    }
+    V3 w = ps - ref_p;
+    const double len_sq = length_sq(w);
+    if (len_sq == 0.0) {
+        *pdf = 0.0;
+    } else {
+        w = normalize(w);
+        *pdf = len_sq / absdot(-w, ns);
+        if (isinf(*pdf)) *pdf = 0.0;
+    }
+    if (*pdf == 0.0 || length_sq(ps - ref_p) == 0.0) {
+        *pdf = 0.0;
+        return rgb(0.0);
+    }
+    *wi = normalize(ps - ref_p);
+    *p1 = ps;
+    return dot(ns, -*wi) > 0.0 ? l.intensity : rgb(0.0);  // AreaLight::l (diffuse.rs:134-140)
+}
+
 static __device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
     const int matching = bsdf_num_components(b, flags);
     if (matching == 0) {

@@ -47,8 +47,10 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     """rrt_light."""
-    _fields_ = [("kind", C.c_uint32), ("pad", C.c_uint32), ("intensity", C.c_double * 3), ("dir", C.c_double * 3),
-                ("to_world", C.c_double * 16)]
+    _fields_ = [("kind", C.c_uint32), ("shape_kind", C.c_uint32), ("intensity", C.c_double * 3), ("dir", C.c_double * 3),
+                ("to_world", C.c_double * 16), ("shape_to_world", C.c_double * 16), ("shape_to_world_inv", C.c_double * 16),
+                ("radius", C.c_double), ("z_min", C.c_double), ("z_max", C.c_double), ("phi_max_deg", C.c_double),
+                ("tri_p", C.c_double * 9), ("tri_n", C.c_double * 9), ("tri_has_n", C.c_uint32), ("pad", C.c_uint32)]
 
 
 COPPER_N = (0.19998972096819712, 0.922085788777433, 1.0998762520488314)
@@ -87,6 +89,32 @@ def distant_light(l=(1.0, 1.0, 1.0), frm=(0.0, 0.0, 0.0), to=(0.0, 0.0, 1.0), to
     lt = Light(kind=1, intensity=tuple(l), dir=tuple(np.subtract(frm, to).tolist()))
     lt.to_world[:] = (np.eye(4) if to_world is None else np.asarray(to_world)).reshape(16).tolist()
     return lt
+
+
+def area_light_sphere(lemit=(1.0, 1.0, 1.0), radius=1.0, obj_to_world=None) -> Light:
+    """DiffuseAreaLight over make_sphere's Sphere (renderprocess.rs:999-1017, 1097-1106)."""
+    l = Light()
+    l.kind, l.shape_kind = 2, 0
+    l.intensity[:] = lemit
+    m, inv = obj_to_world if obj_to_world is not None else (np.eye(4), np.eye(4))
+    l.to_world[:] = np.eye(4).reshape(16).tolist()
+    l.shape_to_world[:] = np.asarray(m, dtype=np.float64).reshape(16).tolist()
+    l.shape_to_world_inv[:] = np.asarray(inv, dtype=np.float64).reshape(16).tolist()
+    l.radius, l.z_min, l.z_max, l.phi_max_deg = radius, -radius, radius, 360.0
+    return l
+
+
+def area_light_triangle(lemit, p3x3, n3x3=None) -> Light:
+    """DiffuseAreaLight over one mesh triangle (renderprocess.rs:1084-1090)."""
+    l = Light()
+    l.kind, l.shape_kind = 2, 1
+    l.intensity[:] = lemit
+    l.to_world[:] = np.eye(4).reshape(16).tolist()
+    l.tri_p[:] = np.asarray(p3x3, dtype=np.float64).reshape(9).tolist()
+    if n3x3 is not None:
+        l.tri_n[:] = np.asarray(n3x3, dtype=np.float64).reshape(9).tolist()
+        l.tri_has_n = 1
+    return l
 
 
 def _bind(L):

@@ -114,7 +114,7 @@ def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthre
     mats[1, 4:7] = (0.3, 0.3, 0.3)
     mats[1, 20] = 0.15
     mats[:, 21:23] = -1.0
-    lights = np.zeros((2, 24))
+    lights = np.zeros((2, S.LIGHT_ROW))
     lights[0, 0] = 0
     lights[0, 1:4] = (4.0, 4.0, 4.0)
     lights[0, 7:23] = np.eye(4).reshape(16)
