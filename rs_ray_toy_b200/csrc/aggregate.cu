@@ -140,6 +140,25 @@ __device__ __forceinline__ bool slab(const RayF& r, float lox, float hix, float 
     return tmin <= tmax;
 }
 
+// Node32 variant: the ray's direction signs pick the near / far plane of every axis when the plane is decoded
+// (the PRMT selector), so no min / max pair per axis is needed.  w* hold lo | hi << 16 (device_layout.h).
+#ifndef RRT_SIGN_SELECT
+#define RRT_SIGN_SELECT 0  // measured slower: three more live registers -> spills at 64, fewer CTAs at 72 (profiles/r1_sweep13)
+#endif
+__device__ __forceinline__ bool slab_q(const RayF& r, uint32_t wx, uint32_t wy, uint32_t wz, uint32_t selx, uint32_t sely,
+                                       uint32_t selz, float tcull, float* tnear) {
+    const float nx = fmaf(__uint_as_float(__byte_perm(wx, 0x3Fu, selx)), r.idx, -r.oidx);
+    const float ny = fmaf(__uint_as_float(__byte_perm(wy, 0x3Fu, sely)), r.idy, -r.oidy);
+    const float nz = fmaf(__uint_as_float(__byte_perm(wz, 0x3Fu, selz)), r.idz, -r.oidz);
+    const float fx = fmaf(__uint_as_float(__byte_perm(wx, 0x3Fu, selx ^ 0x0220u)), r.idx, -r.oidx);
+    const float fy = fmaf(__uint_as_float(__byte_perm(wy, 0x3Fu, sely ^ 0x0220u)), r.idy, -r.oidy);
+    const float fz = fmaf(__uint_as_float(__byte_perm(wz, 0x3Fu, selz ^ 0x0220u)), r.idz, -r.oidz);
+    const float tmin = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+    const float tmax = fminf(fminf(fx, fy), fminf(fz, tcull));
+    *tnear = tmin;
+    return tmin <= tmax;
+}
+
 template <bool WIDE>
 __device__ __forceinline__ void load_prim(const void* prims, uint32_t idx, D3* a, D3* b, D3* c, uint32_t* prim_id,
                                           uint32_t* kind) {
@@ -303,6 +322,9 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_WALK_MIN
 #define RRT_WALK_MIN 12
 #endif
+#ifndef RRT_LEAF_MIN
+#define RRT_LEAF_MIN 8
+#endif
 #ifndef RRT_LEAF_TRIPS
 #define RRT_LEAF_TRIPS 0  // 0: the leaf phase empties every queue; k: at most k leaves per lane and phase
 #endif
@@ -381,6 +403,7 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
     uint64_t ray_index = 0;
     D3 o = {0, 0, 0}, d = {0, 0, 0};
     RayF rf = {0, 0, 0, 0, 0, 0};
+    uint32_t selx = 0x4105u, sely = 0x4105u, selz = 0x4105u;  // Node32: PRMT selectors of the near planes
     double best_t = 0.0;
     float t_shift = 0.0f, tcull = 0.0f;
     uint32_t best_id = RRT_NO_HIT, best_rec = 0;
@@ -442,6 +465,11 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                     const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
                     node = live ? A.root : kDone;
                     tcull = __double2float_ru(best_t - (double)t_shift);
+                    if (QUANT && RRT_SIGN_SELECT) {  // a negative direction meets the upper plane first
+                        selx = rf.idx < 0.0f ? 0x4325u : 0x4105u;
+                        sely = rf.idy < 0.0f ? 0x4325u : 0x4105u;
+                        selz = rf.idz < 0.0f ? 0x4325u : 0x4105u;
+                    }
                 }
             }
         }
@@ -476,8 +504,13 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                     ch_y = __float_as_int(v.h);
 #define RRT_QLO(w) __uint_as_float(__byte_perm((w), 0x3Fu, 0x4105))
 #define RRT_QHI(w) __uint_as_float(__byte_perm((w), 0x3Fu, 0x4325))
+#if RRT_SIGN_SELECT
+                    h0 = slab_q(rf, w0, w1, w2, selx, sely, selz, tcull, &tn0);
+                    h1 = slab_q(rf, w3, w4, w5, selx, sely, selz, tcull, &tn1);
+#else
                     h0 = slab(rf, RRT_QLO(w0), RRT_QHI(w0), RRT_QLO(w1), RRT_QHI(w1), RRT_QLO(w2), RRT_QHI(w2), tcull, &tn0);
                     h1 = slab(rf, RRT_QLO(w3), RRT_QHI(w3), RRT_QLO(w4), RRT_QHI(w4), RRT_QLO(w5), RRT_QHI(w5), tcull, &tn1);
+#endif
                 } else {
                     const char* np = reinterpret_cast<const char*>(nodes + node);
                     const F8 lo = ldg256(np);        // c0 x/y slabs, c1 x/y slabs
@@ -527,6 +560,13 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
 #if RRT_LEAF_TRIPS > 0
 #pragma unroll 1
         for (int trip = 0; trip < RRT_LEAF_TRIPS && __any_sync(FULL, leaf != kNoLeaf); ++trip) {
+#elif RRT_LEAF_MIN > 0
+        // a leaf trip is worth its ~150 f64 instructions only with enough lanes in it: below RRT_LEAF_MIN the
+        // remaining leaves stay queued while the others walk on — unless nobody is left to walk
+        for (;;) {
+            const unsigned with_leaf = __ballot_sync(FULL, leaf != kNoLeaf);
+            if (with_leaf == 0u) break;
+            if (__popc(with_leaf) < RRT_LEAF_MIN && __any_sync(FULL, node >= 0 && node != kDone)) break;
 #else
         while (__any_sync(FULL, leaf != kNoLeaf)) {
 #endif
