@@ -30,7 +30,10 @@
 namespace rrt {
 namespace {
 
-constexpr uint32_t kChunk = 1u << 21;  // camera samples in flight
+#ifndef RRT_CHUNK_LOG2
+#define RRT_CHUNK_LOG2 23
+#endif
+constexpr uint32_t kChunk = 1u << RRT_CHUNK_LOG2;  // camera samples in flight
 constexpr int kTile = 16;              // integrator/mod.rs:55
 
 #define RND_CUDA(call)                                                          \
@@ -637,6 +640,7 @@ struct Renderer::Impl {
     const RayTracer* agg = nullptr;
     int device = 0;
     int sm_count = 148;
+    uint32_t chunk = kChunk;  // camera samples in flight: min(kChunk, the frame)
     CameraData cam{};
     HaltonTables ht{};
     FilmParams film{};
@@ -990,16 +994,24 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         return RRT_OK;
     };
     int rc;
-    if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kChunk * sizeof(Path))) != RRT_OK) return rc;
-    for (int k = 0; k < 2; ++k) {
-        if ((rc = dev_alloc((void**)&I.q.ext_rays[k], (size_t)kChunk * sizeof(rrt_ray))) != RRT_OK) return rc;
-        if ((rc = dev_alloc((void**)&I.q.ext_path[k], (size_t)kChunk * sizeof(uint32_t))) != RRT_OK) return rc;
+    {
+        // a frame smaller than kChunk does not need kChunk slots (461 bytes each)
+        const FilmParams& F = I.film;
+        const uint64_t ntx = (uint64_t)(F.sb[2] - F.sb[0] + kTile - 1) / kTile, nty = (uint64_t)(F.sb[3] - F.sb[1] + kTile - 1) / kTile;
+        const uint64_t frame = ntx * nty * kTile * kTile * std::max<uint64_t>(1, I.ip.n_samples);
+        I.chunk = (uint32_t)std::min<uint64_t>(kChunk, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
     }
-    if ((rc = dev_alloc((void**)&I.q.hits, (size_t)kChunk * sizeof(rrt_hit))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_rays, (size_t)kChunk * sizeof(rrt_ray))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_path, (size_t)kChunk * sizeof(uint32_t))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_contrib, (size_t)kChunk * sizeof(Rgb))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_occluded, (size_t)kChunk)) != RRT_OK) return rc;
+    const size_t kSlots = I.chunk;
+    if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = dev_alloc((void**)&I.q.ext_rays[k], kSlots * sizeof(rrt_ray))) != RRT_OK) return rc;
+        if ((rc = dev_alloc((void**)&I.q.ext_path[k], kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
+    }
+    if ((rc = dev_alloc((void**)&I.q.hits, kSlots * sizeof(rrt_hit))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_rays, kSlots * sizeof(rrt_ray))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_path, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_contrib, kSlots * sizeof(Rgb))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_occluded, kSlots)) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.counters, 64 * sizeof(uint32_t))) != RRT_OK) return rc;
     RND_CUDA(cudaMemset(I.q.counters, 0, 64 * sizeof(uint32_t)));
     stats_.setup_usec =
@@ -1068,8 +1080,8 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
     }
     const uint32_t rounds = I.ip.kind == RRT_INTEGRATOR_PATH ? I.ip.max_depth + 1 : 1;
     uint64_t launches = 0;
-    for (uint64_t base = 0; base < total; base += kChunk) {
-        const uint32_t count = (uint32_t)std::min<uint64_t>(kChunk, total - base);
+    for (uint64_t base = 0; base < total; base += I.chunk) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(I.chunk, total - base);
         RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
