@@ -83,8 +83,15 @@ struct Queues {
     uint32_t* sh_path;
     Rgb* sh_contrib;
     uint8_t* sh_occluded;
-    uint32_t* counters;  // [0] ext cur, [1] ext next, [2] shadow, [4..] statistics
+    uint32_t* counters;  // [0] ext cur, [1] ext next, [2] shadow, [3] generate cursor, [4..15] statistics,
+                         // [16..23] shade bins, [24..31] shade bin cursors
+    uint8_t* shade_key;   // per extension-queue entry: 0 = miss, 1 + material kind otherwise
+    uint32_t* shade_perm; // extension-queue entries grouped by shade_key
 };
+constexpr int kShadeBins = 8;
+#ifndef RRT_SHADE_SORT
+#define RRT_SHADE_SORT 1  // group the hits of a round by material kind before shading (fewer divergent warps)
+#endif
 
 struct Frame {
     const uint32_t* tiles;  // tile ids of this rank
@@ -319,13 +326,61 @@ __device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* pe
     return u;
 }
 
+// ---- shade order: a counting sort of the round's hits by (miss | material kind) -----------------------------
+__global__ void __launch_bounds__(256) shade_bin_kernel(ShadeScene sc, Queues q, int cur) {
+    const uint32_t n = q.counters[cur];
+    if (blockIdx.x * 256u >= n) return;
+    __shared__ uint32_t h[kShadeBins];
+    if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    uint32_t key = 0xFFu;
+    if (i < n) {
+        const uint32_t prim = q.hits[i].prim_id;
+        key = 0;
+        if (prim != RRT_NO_HIT) {
+            const uint32_t kind = sc.materials[sc.prims[prim].material].kind;
+            key = 1u + (kind < (uint32_t)kShadeBins - 2u ? kind : (uint32_t)kShadeBins - 2u);
+        }
+        q.shade_key[i] = (uint8_t)key;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key != 0xFFu && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[key], (uint32_t)__popc(peers));
+    __syncthreads();
+    if (threadIdx.x < kShadeBins && h[threadIdx.x]) atomicAdd(q.counters + 16 + threadIdx.x, h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
+    const uint32_t n = q.counters[cur];
+    if (blockIdx.x * 256u >= n) return;
+    __shared__ uint32_t h[kShadeBins], base[kShadeBins];
+    if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t key = i < n ? (uint32_t)q.shade_key[i] : 0xFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t rank = 0;
+    if (key != 0xFFu && (int)lane == leader) rank = atomicAdd(&h[key], (uint32_t)__popc(peers));
+    rank = __shfl_sync(0xffffffffu, rank, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x < kShadeBins) {
+        uint32_t before = 0;
+        for (int b = 0; b < (int)threadIdx.x; ++b) before += q.counters[16 + b];
+        base[threadIdx.x] = before + (h[threadIdx.x] ? atomicAdd(q.counters + 24 + threadIdx.x, h[threadIdx.x]) : 0u);
+    }
+    __syncthreads();
+    if (key != 0xFFu) q.shade_perm[base[key] + rank] = i;
+}
+
 #ifndef RRT_SHADE_MINBLOCKS
 #define RRT_SHADE_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
                                                      IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
-    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = q.counters[cur];
+    if (RRT_SHADE_SORT && qi < n) qi = q.shade_perm[qi];
     bool emit_ext = false, emit_sh = false;
     V3 eo = v3(0, 0, 0), ed = v3(0, 0, 0), so = v3(0, 0, 0), sd = v3(0, 0, 0);
     Rgb contrib = rgb(0.0);
@@ -512,6 +567,7 @@ __global__ void advance_kernel(Queues q, int cur) {
     q.counters[7] += q.counters[cur ^ 1];  // bounces
     q.counters[cur] = 0;
     q.counters[2] = 0;
+    for (int b = 0; b < 2 * kShadeBins; ++b) q.counters[16 + b] = 0;
 }
 
 // FilmTile::add_sample (film.rs:77-130) straight into the frame's film: radiance guards of
@@ -1012,6 +1068,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     if ((rc = dev_alloc((void**)&I.q.sh_path, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.sh_contrib, kSlots * sizeof(Rgb))) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.sh_occluded, kSlots)) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.shade_key, kSlots)) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.shade_perm, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.counters, 64 * sizeof(uint32_t))) != RRT_OK) return rc;
     RND_CUDA(cudaMemset(I.q.counters, 0, 64 * sizeof(uint32_t)));
     stats_.setup_usec =
@@ -1093,6 +1151,11 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             int rc = I.agg->closest_hit_indirect(count, I.q.counters + cur, I.q.ext_rays[cur], I.q.hits, I.stream, err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;
+#if RRT_SHADE_SORT
+            shade_bin_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.sc, I.q, cur);
+            shade_scatter_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.q, cur);
+            launches += 2;
+#endif
             shade_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
             rc = I.agg->any_hit_indirect(count, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream, err, &n);
             if (rc != RRT_OK) return rc;
