@@ -322,6 +322,9 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_WALK_MIN
 #define RRT_WALK_MIN 12
 #endif
+#ifndef RRT_PREFETCH_FAR
+#define RRT_PREFETCH_FAR 0  // 1: prefetch.global.L2, 2: prefetch.global.L1 of the pushed child
+#endif
 #ifndef RRT_LEAF_MIN
 #define RRT_LEAF_MIN 8
 #endif
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
             if (!have_ray) {
                 const unsigned long long q = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
                 if (q < n) {
-                    ray_index = permuted ? (uint64_t)__ldg(perm + q) : (uint64_t)q;
+                    ray_index = permuted ? (uint64_t)__ldcs(perm + q) : (uint64_t)q;  // read once: streaming
                     const double2* rp = reinterpret_cast<const double2*>(rays + ray_index);
                     const double2 q0 = __ldcs(rp), q1 = __ldcs(rp + 1), q2 = __ldcs(rp + 2), q3 = __ldcs(rp + 3);
                     o = {q0.x, q0.y, q1.x};
@@ -527,6 +530,17 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                 const int32_t near_c = swap ? ch_y : ch_x, far_c = swap ? ch_x : ch_y;
                 if (both) {
                     my_stack[sp * kBlock] = far_c;
+#if RRT_PREFETCH_FAR
+                    // the far child is popped later: start moving its node towards L1 / L2 now
+                    if (far_c >= 0) {
+                        const char* fp = reinterpret_cast<const char*>(A.nodes) + (size_t)far_c * (QUANT ? sizeof(Node32) : sizeof(Node64));
+#if RRT_PREFETCH_FAR == 1
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(fp));
+#else
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
+#endif
+                    }
+#endif
 #if RRT_STALE_SKIP
                     if (!ANY) my_tstack[sp * kBlock] = swap ? tn0 : tn1;
 #endif
@@ -1169,6 +1183,22 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         RRT_CUDA(cudaMemcpy(d_inst_, w2p.data(), w2p.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     lap("upload");
+    // Optional (RRT_L2_PERSIST=1): a persisting L2 access-policy window over the nodes, against the ray / hit
+    // streams that pass through L2 (1.5 GB per 16 Mi-ray batch).  Measured: no gain (1443 vs 1466 Mrays/s,
+    // profiles/r1_sweep14) — the streams already use evict-first loads / stores — so it is off by default.
+    l2_window_bytes_ = 0;
+    {
+        const char* e = std::getenv("RRT_L2_PERSIST");
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (e && atoi(e) != 0 && max_persist > 0 && max_window > 0) {
+            const size_t want = std::min<size_t>(node_bytes, (size_t)max_window);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)max_persist, want));
+            l2_window_bytes_ = want;
+            l2_hit_ratio_ = (float)std::min(1.0, (double)std::min<size_t>((size_t)max_persist, want) / (double)want);
+        }
+    }
     view_.inst_w2p = static_cast<const double*>(d_inst_);
     view_.has_spheres = has_spheres ? 1 : 0;
     view_.nodes = d_nodes_;
@@ -1283,6 +1313,16 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     uint64_t blocks = (uint64_t)w.n_sms * (uint64_t)per_sm;
     const uint64_t needed = (n + kBlock - 1) / kBlock;
     if (blocks > needed) blocks = needed;
+    if (l2_window_bytes_ && w.window_stream != s) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = d_nodes_;
+        attr.accessPolicyWindow.num_bytes = l2_window_bytes_;
+        attr.accessPolicyWindow.hitRatio = l2_hit_ratio_;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        w.window_stream = s;
+    }
     kernel<<<(unsigned)blocks, kBlock, smem, s>>>(view_, n, d_rays, d_hits, d_occ, sorting ? w.d_perm : nullptr,
                                                sorting ? small + 3 : nullptr,
                                                reinterpret_cast<unsigned long long*>(small), n_dev, stack_levels_);

@@ -89,6 +89,7 @@ class DeviceAggregate : public RayTracer {
         struct CUevent_st* last_use = nullptr;
         bool used = false;
         int n_sms = 0;
+        void* window_stream = (void*)-1;  // the stream that last received the L2 access-policy window
     };
     int ensure_workspace(uint64_t n, std::string* err) const;
     template <bool ANY>
@@ -98,6 +99,8 @@ class DeviceAggregate : public RayTracer {
     mutable std::mutex ws_mutex_;
     bool sort_rays_ = true;
     int stack_levels_ = 2;
+    size_t l2_window_bytes_ = 0;  // persisting L2 window over the nodes (0 = off)
+    float l2_hit_ratio_ = 1.0f;
     AggView view_{};
     AggregateStats stats_{};
     void* d_nodes_ = nullptr;
