@@ -21,9 +21,10 @@ for n_tris, edge, seed in ((1 << 20, 0.01, synth.SEED_C3_SOUP), (1 << 22, 0.006,
     d_rays = torch.from_numpy(rays.view(np.float64)).cuda()
     d_hits = torch.empty(n_rays * 4, dtype=torch.float64, device="cuda")
     prims = {}
-    for name, flags in (("host SAH", capi.RRT_BUILD_FAST), ("device LBVH", capi.RRT_BUILD_DEVICE_LBVH)):
+    for name, flags, leaf in (("host SAH", capi.RRT_BUILD_FAST, 4), ("device LBVH", capi.RRT_BUILD_DEVICE_LBVH, 4),
+                              ("device LBVH leaf 2", capi.RRT_BUILD_DEVICE_LBVH, 2), ("device LBVH leaf 1", capi.RRT_BUILD_DEVICE_LBVH, 1)):
         t0 = time.perf_counter()
-        agg = soup_aggregate(ctx, p, idx, 4, flags)
+        agg = soup_aggregate(ctx, p, idx, leaf, flags)
         commit_s = time.perf_counter() - t0
         st, info = agg.stats(), agg.build_info()
         s = torch.cuda.current_stream()
@@ -41,4 +42,4 @@ for n_tris, edge, seed in ((1 << 20, 0.01, synth.SEED_C3_SOUP), (1 << 22, 0.006,
                           "tree_device_ms": info["tree_device_usec"] / 1e3, "n_nodes": st["n_nodes"], "max_depth": st["max_depth"],
                           "node_bytes": info["node_bytes"], "Mrays_per_s": round(n_rays / ms / 1e3, 1)}), flush=True)
         del agg
-    print("same primitive on every ray:", bool((prims["host SAH"] == prims["device LBVH"]).all()))
+    print("same primitive on every ray:", all(bool((prims["host SAH"] == v).all()) for v in prims.values()))
