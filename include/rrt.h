@@ -66,7 +66,7 @@ typedef enum rrt_build_flags {
     RRT_BUILD_DEVICE_LBVH = 2 /* Tier F with the tree built ON the GPU: Morton keys, radix sort, binary radix
                               tree, bottom-up boxes (the device counterpart of hlbvh_build's Morton half,
                               bvh.rs:365-612).  Milliseconds instead of a host SAH build; same answers (Tier-F
-                              results do not depend on topology), a somewhat slower tree to walk            */
+                              results do not depend on topology), a tree 2-5% slower to walk              */
 } rrt_build_flags;
 
 /* ---- context ----------------------------------------------------------------------------- */

@@ -985,13 +985,18 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     if (const char* e = std::getenv("RRT_QUANTISE")) quantise = atoi(e) != 0;
     const uint32_t max_leaf = max_prims_in_node == 0 ? 4 : (max_prims_in_node > 8 ? 8 : max_prims_in_node);
     const bool on_device = device_lbvh && n > 16 && n > max_leaf;
+    // The device builder makes ONE-primitive leaves whatever max_prims_in_node says (Tier-F answers do not depend on
+    // it): without SAH the collapsed 2-4 primitive leaves cost more f64 tests than they save nodes — measured 1364
+    // (1) / 1261 (2) / 1076 (4) Mrays/s on config 3 (profiles/r1_bench_build_lbvh.txt).  RRT_LBVH_LEAF overrides.
+    uint32_t lbvh_leaf = 1;
+    if (const char* e = std::getenv("RRT_LBVH_LEAF")) lbvh_leaf = (uint32_t)std::max(1, std::min(8, atoi(e)));
 
     lap("frame + node format");
     // ---- tree ----
     Bvh2 tree;
     LbvhResult lb;
     if (on_device) {
-        int rc = build_lbvh_device(device, boxes, max_leaf, delta, quantise, grid_lo, grid_ext, &lb, err);
+        int rc = build_lbvh_device(device, boxes, std::min(max_leaf, lbvh_leaf), delta, quantise, grid_lo, grid_ext, &lb, err);
         if (rc != RRT_OK) return rc;
         tree.max_depth = lb.max_depth + 1;
         tree.n_leaves = lb.n_leaves;
