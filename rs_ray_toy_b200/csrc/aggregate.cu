@@ -995,24 +995,33 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     // ---- tree ----
     Bvh2 tree;
     LbvhResult lb;
+    bool on_device_ok = on_device;
     if (on_device) {
         int rc = build_lbvh_device(device, boxes, std::min(max_leaf, lbvh_leaf), delta, quantise, grid_lo, grid_ext, &lb, err);
         if (rc != RRT_OK) return rc;
         tree.max_depth = lb.max_depth + 1;
         tree.n_leaves = lb.n_leaves;
-    } else {
+        if (tree.max_depth + 2 > (uint32_t)kStack) {
+            // thousands of primitives with one centroid make a radix tree deeper than the traversal stack:
+            // such scenes get the SAH tree (which splits equal centroids by count)
+            cudaFree(lb.d_nodes);
+            lb = LbvhResult();
+            on_device_ok = false;
+        }
+    }
+    if (!on_device_ok) {
         SahParams sp;
         sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
         if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
         build_sah(boxes, sp, &tree);
     }
     if (tree.max_depth + 2 > (uint32_t)kStack) {
-        if (on_device) cudaFree(lb.d_nodes);
+        if (on_device_ok) cudaFree(lb.d_nodes);
         if (err) *err = "tree deeper than the traversal stack (" + std::to_string(tree.max_depth) + " levels)";
         return RRT_ERR_UNSUPPORTED;
     }
 
-    lap(on_device ? "device LBVH (total)" : "host SAH tree");
+    lap(on_device_ok ? "device LBVH (total)" : "host SAH tree");
     // ---- pack: interior nodes in DFS order, leaves become references ----
     std::vector<Node64> nodes;
     nodes.reserve(tree.nodes.size() / 2 + 2);
@@ -1076,7 +1085,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             out.c1_loz = lo[2]; out.c1_hiz = hi[2];
         }
     };
-    if (on_device) {
+    if (on_device_ok) {
         // the device tree's leaves are runs of the sorted order: records simply follow it
         parallel_ranges(n, [&](size_t r0, size_t r1) {
             for (size_t r = r0; r < r1; ++r) make_record(lb.order[r], r);
@@ -1136,7 +1145,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
 
     // ---- quantise the host tree: Node64 (fp32 planes) -> Node32 (15-bit planes on the grid) ----
     std::vector<Node32> nodes32;
-    if (quantise && !on_device) {
+    if (quantise && !on_device_ok) {
         nodes32.resize(nodes.size());
         // the device evaluates fmaf(f, ext / d, -(o - c) / d) in fp32: 11 roundings of magnitude <= 2 ext / |d|
         // (DESIGN.md §3), i.e. less than ext * 2^-20 in position; the planes move outward by twice that
@@ -1165,10 +1174,10 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     lap("pack nodes + records");
     // ---- upload ----
     RRT_CUDA(cudaSetDevice(device));
-    const size_t node_bytes = on_device ? lb.node_bytes : (quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64));
+    const size_t node_bytes = on_device_ok ? lb.node_bytes : (quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64));
     const void* node_src = quantise ? (const void*)nodes32.data() : (const void*)nodes.data();
     size_t prim_bytes = wide ? rec96.size() * sizeof(PrimRec96) : rec48.size() * sizeof(PrimRec48);
-    if (on_device) {
+    if (on_device_ok) {
         d_nodes_ = lb.d_nodes;
     } else {
         RRT_CUDA(cudaMalloc(&d_nodes_, node_bytes));
@@ -1223,8 +1232,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     view_.sort_mode = 0;
     if (const char* e = std::getenv("RRT_SORT_MODE")) view_.sort_mode = atoi(e);
     if (const char* e = std::getenv("RRT_SORT")) sort_rays_ = atoi(e) != 0;
-    stats_.n_nodes = on_device ? lb.n_nodes : nodes.size();
-    stats_.tree_device_usec = on_device ? (uint64_t)(lb.device_ms * 1000.0f) : 0;
+    stats_.n_nodes = on_device_ok ? lb.n_nodes : nodes.size();
+    stats_.tree_device_usec = on_device_ok ? (uint64_t)(lb.device_ms * 1000.0f) : 0;
     stats_.n_leaves = tree.n_leaves;
     stats_.max_depth = tree.max_depth;
     stats_.device_bytes = node_bytes + prim_bytes;

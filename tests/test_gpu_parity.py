@@ -437,3 +437,42 @@ def test_device_lbvh_small_scenes_fall_back_to_the_host_builder(ctx):
     agg = scenes.gpu_soup(ctx, p, idx, 4, capi.RRT_BUILD_DEVICE_LBVH)
     assert agg.build_info()["tree_device_usec"] == 0
     _assert_closest(agg.intersect(rays), ref["prim"], ref["t"])
+
+
+def test_device_lbvh_duplicates_and_a_tree_too_deep_for_the_stack(ctx):
+    """Equal centroids are split by position on the device too; and a scene whose Morton keys are 1, 2, 4, ... 2^62
+    plus thousands of copies at key 0 makes a radix tree deeper than the 64-entry traversal stack — the commit
+    then falls back to the SAH builder instead of failing.  Answers are the oracle's in both cases."""
+    from rs_ray_toy_b200 import capi
+    rng = np.random.default_rng(12)
+    tri = np.array([[0.0, 0.0, 0.0], [1e-3, 0.0, 0.0], [0.0, 1e-3, 0.0]])
+    # 6000 identical triangles + 2000 random ones
+    p_rand, idx_rand = scenes.soup(2000)
+    p = np.concatenate([np.tile(tri + 0.25, (6000, 1)), p_rand])
+    idx = np.arange(len(p), dtype=np.uint32).reshape(-1, 3)
+    rays = synth.bounce_rays(p_rand, idx_rand, 20000, seed=2)
+    rays[:5000, 0:3] = (0.2503, 0.2503, 1.0)
+    rays[:5000, 3:6] = (0.0, 0.0, -1.0)
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    agg = scenes.gpu_soup(ctx, p, idx, 4, capi.RRT_BUILD_DEVICE_LBVH)
+    assert agg.build_info()["tree_device_usec"] > 0
+    c = _assert_closest(agg.intersect(rays), ref["prim"], ref["t"])
+    assert c["hits"] >= 5000
+    # one tiny triangle per Morton bit + 5000 copies at the origin corner
+    pts = [np.zeros(3)]
+    for j in range(21):
+        for axis in range(3):
+            q = np.zeros(3)
+            q[axis] = 2.0 ** j / 2.0 ** 21
+            pts.append(q)
+    pts = np.array(pts) * 0.5
+    small = tri * 1e-9
+    p = np.concatenate([np.tile(small, (5000, 1))] + [small + q for q in pts])
+    idx = np.arange(len(p), dtype=np.uint32).reshape(-1, 3)
+    o = np.concatenate([rng.uniform(-0.1, 0.6, (4000, 2)), np.full((4000, 1), 1.0)], axis=1)
+    rays = np.concatenate([o, np.tile([0.0, 0.0, -1.0], (4000, 1)), np.full((4000, 1), np.inf)], axis=1)
+    rays[:500, 0:2] = 2e-13
+    ref = scenes.oracle_soup(p, idx).intersect(rays)
+    agg = scenes.gpu_soup(ctx, p, idx, 4, capi.RRT_BUILD_DEVICE_LBVH)
+    _assert_closest(agg.intersect(rays), ref["prim"], ref["t"])
+    assert agg.stats()["max_depth"] + 2 <= 64
