@@ -10,6 +10,14 @@
 // recomputed multi-lobe f discarded), Q16 (Plastic's specular lobe gated on kd), Q5a (sphere hit
 // point taken on the instance-space ray), FresnelSpecular's type = SPECULAR | ALL.
 #pragma once
+#ifndef RRT_SHADE_NOINLINE
+#define RRT_SHADE_NOINLINE 1  // measured: 160 registers without spills, +3% (profiles/r1_sweep_shade_noinline.txt)
+#endif
+#if RRT_SHADE_NOINLINE
+#define RRT_SHADE_FN static __device__ __noinline__
+#else
+#define RRT_SHADE_FN static __device__
+#endif
 #include "rmath.cuh"
 
 namespace rrt {
@@ -347,7 +355,7 @@ static __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, d
     return normalize(v3(-slope_x, -slope_y, 1.0));
 }
 
-static __device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT: return l.r / kPi;
         case LOBE_OREN_NAYAR: {  // reflection.rs:916-941
@@ -379,7 +387,7 @@ static __device__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
         default: return rgb(0.0);
     }
 }
-static __device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
@@ -392,7 +400,7 @@ static __device__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     }
 }
 // BxDF::sample_f of each lobe; *pdf is left untouched on the early-outs (the caller zeroed it)
-static __device__ Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: {  // reflection.rs:428-443
@@ -463,7 +471,7 @@ static __device__ int bsdf_num_components(const Bsdf& b, uint32_t flags) {
     for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches(b.lobes[i], flags) ? 1 : 0;
     return n;
 }
-static __device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+RRT_SHADE_FN Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     V3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);
     bool reflect = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0;
@@ -477,7 +485,7 @@ static __device__ Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     return f;
 }
 // Bsdf::pdf (reflection.rs:382-404)
-static __device__ double bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+RRT_SHADE_FN double bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     if (b.n_lobes == 0) return 0.0;
     V3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
     if (wo.z == 0.0) return 0.0;
@@ -505,7 +513,7 @@ __device__ __forceinline__ double power_heuristic(int nf, double f_pdf, int ng, 
 // DiffuseAreaLight::sample_li (diffuse.rs:62-79) over Shape::sample_ref (shape/mod.rs:33-48) over Shape::sample
 // (sphere.rs:265-284: uniform over the whole sphere; triangle.rs:393-417: "barycentrics" from uniform_sample_sphere,
 // Q20).  sample_ref ASSIGNS distance^2 / |cos| to the pdf, dropping Shape::sample's 1 / area (Q28).
-static __device__ Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, double* pdf, V3* p1) {
+RRT_SHADE_FN Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, double* pdf, V3* p1) {
     V3 ps, ns;
     if (l.shape_kind == 0) {
         V3 p_obj = v3(0.0, 0.0, 0.0) + uniform_sample_sphere(u) * l.radius;
@@ -536,7 +544,7 @@ static __device__ Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, 
     return dot(ns, -*wi) > 0.0 ? l.intensity : rgb(0.0);  // AreaLight::l (diffuse.rs:134-140)
 }
 
-static __device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
     const int matching = bsdf_num_components(b, flags);
     if (matching == 0) {
         *pdf = 0.0;
@@ -575,7 +583,7 @@ static __device__ Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, doub
 }
 
 // Material::compute_scattering_functions for constant-valued parameters
-static __device__ void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
+RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
     b->ns = s.shn;
     b->ss = normalize(s.shdpdu);
     b->ng = s.n;
