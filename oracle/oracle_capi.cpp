@@ -374,6 +374,7 @@ int32_t orc_hardware_threads() { return (int32_t)std::thread::hardware_concurren
 
 namespace {
 struct RenderSetup {
+    std::vector<Texture> textures;
     std::vector<Material> materials;
     std::vector<Light> light_specs;  // distant: w_light holds the raw (from - to) until render time
     std::vector<Xform> light_xf;
@@ -411,7 +412,7 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
     RenderSetup& rs = setup_of(sp);
     rs.materials.clear();
     for (uint32_t i = 0; i < n; ++i) {
-        const double* a = m + 26 * (size_t)i;
+        const double* a = m + 40 * (size_t)i;
         Material mat;
         mat.kind = (uint32_t)a[0];
         mat.kd = Rgb(a[1], a[2], a[3]);
@@ -426,11 +427,52 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
         mat.v_roughness = a[22];
         mat.eta = a[23];
         mat.remap_roughness = a[24] != 0.0;
+        for (int k = 0; k < 11; ++k) mat.tex[k] = (int32_t)a[26 + k];
         rs.materials.push_back(mat);
     }
 }
 // Lights.  24 doubles per light: 0 kind | 1-3 I or L | 4-6 point: p_light, distant: from - to |
 // 7-22 light_to_world m (row-major) | 23 pad.  (The inverse is not needed: vectors use m.)
+// Texture table, 48 doubles per texture (tests/oracle_scene.py texture_rows): 0 kind | 1 is_rgb | 2 mapping | 3 aa |
+// 4 t1 | 5 t2 | 6 amount | 8-19 v[4][3] | 20-27 map[8] | 28-43 IdentityMapping3D matrix (row-major).
+void orc_set_textures(void* sp, uint32_t n, const double* t) {
+    RenderSetup& rs = setup_of(sp);
+    rs.textures.clear();
+    if (n > (uint32_t)kMaxTextures) {
+        g_err = "more textures than the restated evaluator holds";
+        return;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const double* a = t + 48 * (size_t)i;
+        Texture x;
+        x.kind = (uint32_t)a[0];
+        x.mapping = (uint32_t)a[2];
+        x.t1 = (int32_t)a[4];
+        x.t2 = (int32_t)a[5];
+        x.amount = (int32_t)a[6];
+        for (int k = 0; k < 4; ++k) x.v[k] = Rgb(a[8 + 3 * k], a[9 + 3 * k], a[10 + 3 * k]);
+        for (int k = 0; k < 8; ++k) x.map[k] = a[20 + k];
+        std::memcpy(x.w2t.m.m, a + 28, 16 * sizeof(double));
+        x.w2t.inv = x.w2t.m;  // unused
+        rs.textures.push_back(x);
+    }
+}
+// Texture probe: evaluates the table at (uv, p) and returns every texture's value (3 doubles each).
+void orc_texture_probe(uint32_t n, const double* table, const double* uv2, const double* p3, double* out) {
+    void* tmp = orc_scene_new(0);
+    orc_set_textures(tmp, n, table);
+    RenderSetup& rs = setup_of(tmp);
+    Rgb vals[kMaxTextures];
+    tex_eval_all(rs.textures, P2(uv2[0], uv2[1]), V3(p3[0], p3[1], p3[2]), vals);
+    for (uint32_t i = 0; i < n && i < (uint32_t)kMaxTextures; ++i)
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = vals[i].c[c];
+    for (size_t i = 0; i < g_setups.size(); ++i)
+        if (g_setups[i].first == tmp) {
+            g_setups.erase(g_setups.begin() + i);
+            break;
+        }
+    orc_scene_free(tmp);
+}
 // Light table, 80 doubles per light (tests/oracle_scene.py light_row).
 void orc_set_lights(void* sp, uint32_t n, const double* l) {
     RenderSetup& rs = setup_of(sp);
@@ -504,6 +546,7 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
         job.scene.geom = &s->geom;
         job.scene.bvh = &s->bvh;
         job.scene.materials = rs.materials;
+        job.scene.textures = rs.textures;
         job.scene.fix_q9 = s->geom.q.fix_q9;
         for (const GeoPrim& g : s->geom.geos)
             if (g.material < 0 || (size_t)g.material >= rs.materials.size()) throw std::runtime_error("material index out of range");

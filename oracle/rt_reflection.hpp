@@ -438,6 +438,68 @@ struct Bsdf {
 
 // ---- materials (material/*.rs) with constant-valued parameters -------------------------------------
 enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4, MAT_NONE = 5 };
+// ---- textures (texture/{bilerp,mix,scale,checkerboard}.rs, texture/mod.rs mappings) ------------------------------
+// A material parameter is a texture.  The loader flattens the float and rgb textures of a scene file into one
+// table in definition order (a texture can only name textures defined before it: make_textures looks names up
+// in the maps it is filling, renderprocess.rs:298-515; an unknown name falls back to a constant, :282-296), so
+// evaluating the table front to back evaluates every child before its parent.  Float textures use component 0.
+// In scope: Constant, Bilerp, Scale, Mix, Checkerboard 2D (aamode none) and 3D; UV and planar 2D mappings,
+// IdentityMapping3D.  Closed-form checkerboard filtering needs ray differentials and is refused by the loaders.
+enum TexKind : uint32_t { TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5 };
+enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1 };
+struct Texture {
+    uint32_t kind = TEX_CONST, mapping = MAP_UV;
+    int32_t t1 = -1, t2 = -1, amount = -1;
+    Rgb v[4];
+    double map[8] = {1, 1, 0, 0, 0, 0, 0, 0};  // uv: su sv du dv; planar: vs[3] vt[3] ds dt
+    Xform w2t;                                  // checkerboard 3D: IdentityMapping3D's transform
+};
+constexpr int kMaxTextures = 32;
+// TextureMapping2D::map without the differentials (texture/mod.rs:218-229 uv, :338-347 planar)
+inline P2 tex_map2d(const Texture& t, P2 uv, V3 p) {
+    if (t.mapping == MAP_UV) return P2(t.map[0] * uv.x + t.map[2], t.map[1] * uv.y + t.map[3]);
+    V3 vs(t.map[0], t.map[1], t.map[2]), vt(t.map[3], t.map[4], t.map[5]);
+    return P2(t.map[6] + dot(p, vs), t.map[7] + dot(p, vt));
+}
+inline int32_t rust_f64_as_i32(double v) {  // `as i32`: saturating, NaN -> 0
+    if (!(v == v)) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (int32_t)-2147483647 - 1;
+    return (int32_t)v;
+}
+inline void tex_eval_all(const std::vector<Texture>& table, P2 uv, V3 p, Rgb* vals) {
+    for (size_t i = 0; i < table.size(); ++i) {
+        const Texture& t = table[i];
+        switch (t.kind) {
+            case TEX_CONST: vals[i] = t.v[0]; break;
+            case TEX_BILERP: {  // bilerp.rs:31-44
+                P2 st = tex_map2d(t, uv, p);
+                vals[i] = t.v[0] * (1.0 - st.x) * (1.0 - st.y) + t.v[1] * (1.0 - st.x) * st.y + t.v[2] * st.x * (1.0 - st.y) +
+                          t.v[3] * st.x * st.y;
+                break;
+            }
+            case TEX_SCALE: vals[i] = vals[t.t1] * vals[t.t2]; break;  // scale.rs:27-32
+            case TEX_MIX: {                                            // mix.rs:33-38
+                double amt = vals[t.amount].c[0];
+                vals[i] = vals[t.t1] * (1.0 - amt) + vals[t.t2] * amt;
+                break;
+            }
+            case TEX_CHECKER2D: {  // checkerboard.rs:57-64 (AANone)
+                P2 st = tex_map2d(t, uv, p);
+                int32_t sum = (int32_t)((uint32_t)rust_f64_as_i32(std::floor(st.x)) + (uint32_t)rust_f64_as_i32(std::floor(st.y)));
+                vals[i] = (sum % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                break;
+            }
+            default: {  // checkerboard.rs:121-131
+                V3 q = xf_point(t.w2t, p);
+                int32_t k = rust_f64_as_i32(std::floor(q.x) + std::floor(q.y) + std::floor(q.z));
+                vals[i] = (k % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                break;
+            }
+        }
+    }
+}
+
 struct Material {
     uint32_t kind = MAT_MATTE;
     Rgb kd = Rgb(0.5), ks = Rgb(0.25), kr = Rgb(0.9), kt = Rgb(1.0);
@@ -447,7 +509,29 @@ struct Material {
     double u_roughness = -1.0, v_roughness = -1.0;  // metal: < 0 = None; glass: value
     double eta = 1.5;        // glass index
     bool remap_roughness = false;
+    // texture ids of kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta (-1: the constant above)
+    int32_t tex[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    bool textured() const {
+        for (int k = 0; k < 11; ++k)
+            if (tex[k] >= 0) return true;
+        return false;
+    }
 };
+// The material with every textured parameter evaluated at the hit (Texture::evaluate(si) in each
+// compute_scattering_functions, material/*.rs).
+inline Material material_at(const Material& m, const std::vector<Texture>& table, const SI& si) {
+    if (!m.textured()) return m;
+    Rgb vals[kMaxTextures];
+    tex_eval_all(table, si.uv, si.p, vals);
+    Material r = m;
+    Rgb* rgbs[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.eta_rgb, &r.k_rgb};
+    for (int k = 0; k < 6; ++k)
+        if (m.tex[k] >= 0) *rgbs[k] = vals[m.tex[k]];
+    double* fs[5] = {&r.sigma, &r.roughness, &r.u_roughness, &r.v_roughness, &r.eta};
+    for (int k = 0; k < 5; ++k)
+        if (m.tex[6 + k] >= 0) *fs[k] = vals[m.tex[6 + k]].c[0];
+    return r;
+}
 // Fills si-dependent Bsdf exactly as the material's compute_scattering_functions would
 // (bump maps are out of scope).  `allow_multiple_lobes` as passed by the integrator.
 inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_lobes, Bsdf* bsdf) {

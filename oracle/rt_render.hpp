@@ -43,6 +43,7 @@ struct RenderScene {
     const Geometry* geom = nullptr;
     const BVH* bvh = nullptr;
     std::vector<Material> materials;
+    std::vector<Texture> textures;  // the scene file's float and rgb textures, definition order
     std::vector<Light> lights;
     Geometry light_shapes;  // the area lights' shapes, for Shape::pdf_ref (they are not in the aggregate)
     bool fix_q9 = false;
@@ -241,7 +242,7 @@ struct Integrator {
             (void)specular_bounce;  // isect.le() == 0 (Q22) and there are no infinite lights in scope
             if (!found || bounces >= max_depth) break;
             Bsdf bsdf;
-            material_bsdf(sc.materials[sc.geom->geos[isect.geo].material], isect, true, &bsdf);
+            material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect), isect, true, &bsdf);
             if (!bsdf.present) {
                 // path.rs:101-106: `bounces -= 1` on usize — wraps in release, panics in debug (Q21)
                 if (st) st->asserts += 1;
@@ -290,7 +291,7 @@ struct Integrator {
         if (first_hit) *first_hit = rec;
         if (!found) return l;  // Light::le of point / distant lights is zero
         Bsdf bsdf;
-        material_bsdf(sc.materials[sc.geom->geos[isect.geo].material], isect, false, &bsdf);
+        material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect), isect, false, &bsdf);
         if (!bsdf.present) return li_direct(sc, ray_new_od(isect.p, ray.d), sampler, depth, st, nullptr);
         if (!sc.lights.empty()) l += sc.uniform_sample_one_light(isect, bsdf, sampler, nullptr, st);
         if (depth + 1 < max_depth) {

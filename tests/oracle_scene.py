@@ -88,68 +88,182 @@ def _spectrum(cfg, key, default):
     return [float(default)] * 3 if not isinstance(default, (list, tuple)) else list(default)
 
 
+TEX_ROW = 48
+TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D = range(6)
+
+
 class Textures:
-    """Only what the in-scope materials can reach: a BilerpTexture whose corners agree is a
-    constant (the loader reads v10 and v11 from key "v01", renderprocess.rs:326-329,439-442)."""
+    """make_textures (renderprocess.rs:298-515) flattened into one table in definition order: float textures first,
+    then rgb textures; a texture can only name textures defined before it, an unknown name falls back to a constant
+    (get_text_fallback, :282-296).  Row layout: oracle_capi.cpp orc_set_textures.
+    A BilerpTexture whose corners agree is stored as the constant it is (the loader reads v10 and v11 from key
+    "v01", :326-329,439-442) — the device loader does the same, so both sides drop the 1-ulp sum-of-weights factor."""
 
     def __init__(self, cfg):
-        self.f, self.rgb = {}, {}
+        self.rows, self.f, self.rgb = [], {}, {}
         for t in cfg.get("float_texture", []) or []:
-            if t.get("texture_type") == "BilerpTexture":
-                v00, v01 = float(t.get("v00", 0.0)), float(t.get("v01", 1.0))
-                if v00 == v01:
-                    self.f[t.get("texture_name", "DefaultTextureName")] = v00
+            self._add(t, False)
         for t in cfg.get("rgb_texture", []) or []:
-            if t.get("texture_type") == "BilerpTexture":
-                v00, v01 = _spectrum(t, "v00", 0.0), _spectrum(t, "v01", 1.0)
-                if v00 == v01:
-                    self.rgb[t.get("texture_name", "DefaultTextureName")] = v00
+            self._add(t, True)
+        if len(self.rows) > 32:
+            raise ValueError("more than 32 textures")
+
+    def table(self):
+        return np.array(self.rows).reshape(-1, TEX_ROW)
+
+    def _row(self, kind, is_rgb):
+        r = np.zeros(TEX_ROW)
+        r[0], r[1] = kind, 1.0 if is_rgb else 0.0
+        r[4:7] = -1
+        r[20:24] = (1, 1, 0, 0)
+        r[28:44] = np.eye(4).reshape(16)
+        self.rows.append(r)
+        return r, len(self.rows) - 1
+
+    def const(self, value, is_rgb):
+        r, i = self._row(TEX_CONST, is_rgb)
+        r[8:11] = value if is_rgb else [value, 0.0, 0.0]
+        return i
+
+    def _value(self, t, key, default, is_rgb):
+        return _spectrum(t, key, default) if is_rgb else float(t.get(key, default))
+
+    def _child(self, names, name, default, is_rgb):
+        return names[name] if name in names else self.const([default] * 3 if is_rgb else default, is_rgb)
+
+    def _mapping(self, r, t):
+        mp = t.get("mapping")
+        if mp is None:
+            return
+        kind = mp.get("mapping", "uv")
+        if kind == "uv":     # NB du / dv default to 1 when a mapping block is given (renderprocess.rs:582-583)
+            r[2] = 0
+            r[20:24] = [float(mp.get("su", 1.0)), float(mp.get("sv", 1.0)), float(mp.get("du", 1.0)), float(mp.get("dv", 1.0))]
+        elif kind == "planar":
+            r[2] = 1
+            r[20:23] = _xyz(mp, "v1", (1, 0, 0))
+            r[23:26] = _xyz(mp, "v2", (0, 1, 0))
+            r[26], r[27] = float(mp.get("udelta", 0.0)), float(mp.get("vdelta", 0.0))
+        else:
+            raise ValueError(f"texture mapping {kind!r} is outside the restated subset")
+
+    def _add(self, t, is_rgb):
+        names = self.rgb if is_rgb else self.f
+        ty, name = t.get("texture_type", ""), t.get("texture_name", "DefaultTextureName")
+        one, zero = (1.0, 0.0)
+        if ty == "BilerpTexture":
+            v00, v01 = self._value(t, "v00", 0.0, is_rgb), self._value(t, "v01", 1.0, is_rgb)
+            v10, v11 = self._value(t, "v01", 0.0, is_rgb), self._value(t, "v01", 1.0, is_rgb)
+            if v00 == v01 == v10 == v11:
+                names[name] = self.const(v00, is_rgb)
+                return
+            r, i = self._row(TEX_BILERP, is_rgb)
+            for k, v in enumerate((v00, v01, v10, v11)):
+                r[8 + 3 * k: 11 + 3 * k] = v if is_rgb else [v, 0.0, 0.0]
+            self._mapping(r, t)
+        elif ty == "ScaleTexture":
+            c1 = self._child(names, t.get("t1", "ErrorTextureName"), one, is_rgb)
+            c2 = self._child(names, t.get("t2", "ErrorTextureName"), one, is_rgb)
+            r, i = self._row(TEX_SCALE, is_rgb)
+            r[4], r[5] = c1, c2
+        elif ty == "MixTexture":   # the amount texture is looked up under the key "t2" as well (:319,411)
+            c1 = self._child(names, t.get("t1", "ErrorTextureName"), zero, is_rgb)
+            c2 = self._child(names, t.get("t2", "ErrorTextureName"), one, is_rgb)
+            amt = self._child(self.f, t.get("t2", "ErrorTextureName"), 0.5, False)
+            r, i = self._row(TEX_MIX, is_rgb)
+            r[4], r[5], r[6] = c1, c2, amt
+        elif ty == "CheckerBoardTexture":
+            dim = int(t.get("dimension", 2))
+            if dim not in (2, 3):
+                return
+            c1 = self._child(names, t.get("t1", "ErrorTextureName"), one, is_rgb)
+            c2 = self._child(names, t.get("t2", "ErrorTextureName"), zero, is_rgb)
+            if dim == 2:
+                if t.get("aamode", "closedform") != "none":
+                    raise ValueError("closed-form checkerboard filtering needs ray differentials: outside the restated subset")
+                r, i = self._row(TEX_CHECKER2D, is_rgb)
+                self._mapping(r, t)
+            else:
+                r, i = self._row(TEX_CHECKER3D, is_rgb)
+                m, _ = to_world(t)   # IdentityMapping3D::new(to_world): the matrix is used as world_to_texture
+                r[28:44] = m.reshape(16)
+            r[4], r[5] = c1, c2
+        else:
+            names[name] = -2   # known name, type outside the subset: an error only if a material uses it
+            return
+        names[name] = i
+
+    def _resolve(self, names, name, is_rgb):
+        i = names[name]
+        if i == -2:
+            raise ValueError(f"texture {name!r} has a type outside the restated subset")
+        if self.rows[i][0] == TEX_CONST:   # constants stay constants in the material record
+            v = self.rows[i][8:11]
+            return (list(v) if is_rgb else float(v[0])), -1
+        return None, i
 
     def fval(self, cfg, key, default):
+        """-> (constant, texture id or -1)"""
         name = cfg.get(key)
         if isinstance(name, str):
             if name not in self.f:
-                raise ValueError(f"float texture {name!r} is outside the restated subset")
-            return self.f[name]
-        return default
+                raise ValueError(f"float texture {name!r} does not exist (the reference panics: renderprocess.rs:621)")
+            v, i = self._resolve(self.f, name, False)
+            return (default if v is None else v), i
+        return default, -1
 
     def rgbval(self, cfg, key, default):
         name = cfg.get(key)
+        d = [default] * 3 if not isinstance(default, (list, tuple)) else list(default)
         if isinstance(name, str) and name in self.rgb:
-            return self.rgb[name]
-        return [default] * 3 if not isinstance(default, (list, tuple)) else list(default)
+            v, i = self._resolve(self.rgb, name, True)
+            return (d if v is None else v), i
+        return d, -1
+
+
+MAT_ROW = 40
+# texture-id slots of a material row (26 + k): kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta
+T_KD, T_KS, T_KR, T_KT, T_ETA_RGB, T_K_RGB, T_SIGMA, T_ROUGH, T_UR, T_VR, T_ETA = range(11)
 
 
 def material_row(cfg, tex: Textures):
-    """make_materials (renderprocess.rs:664-871) -> the oracle's 26-double material record."""
+    """make_materials (renderprocess.rs:664-871) -> the oracle's 40-double material record."""
     kind = MAT_KIND.get(cfg.get("material_type", ""))
     if kind is None:
         return None
-    r = np.zeros(26)
+    r = np.zeros(MAT_ROW)
     r[0] = kind
     r[21] = r[22] = -1.0
+    r[26:37] = -1
+
+    def rgb(lo, slot, key, default):
+        r[lo:lo + 3], r[26 + slot] = tex.rgbval(cfg, key, default)
+
+    def flt(at, slot, key, default):
+        r[at], r[26 + slot] = tex.fval(cfg, key, default)
+
     cu_n, cu_k = copper_rgb()
     if kind == 0:
-        r[1:4] = tex.rgbval(cfg, "kd", 0.5)
-        r[19] = tex.fval(cfg, "sigma", 0.0)
+        rgb(1, T_KD, "kd", 0.5)
+        flt(19, T_SIGMA, "sigma", 0.0)
     elif kind == 1:
-        r[1:4] = tex.rgbval(cfg, "kd", 0.25)
-        r[4:7] = tex.rgbval(cfg, "ks", 0.25)
-        r[20] = tex.fval(cfg, "roughness", 0.1)
+        rgb(1, T_KD, "kd", 0.25)
+        rgb(4, T_KS, "ks", 0.25)
+        flt(20, T_ROUGH, "roughness", 0.1)
     elif kind == 2:
-        r[13:16] = tex.rgbval(cfg, "eta", cu_n)
-        r[16:19] = tex.rgbval(cfg, "k", cu_k)
-        r[20] = tex.fval(cfg, "roughness", 0.01)
-        r[21] = tex.fval(cfg, "u_roughness", -1.0)
-        r[22] = tex.fval(cfg, "v_roughness", -1.0)
+        rgb(13, T_ETA_RGB, "eta", cu_n)
+        rgb(16, T_K_RGB, "k", cu_k)
+        flt(20, T_ROUGH, "roughness", 0.01)
+        flt(21, T_UR, "u_roughness", -1.0)
+        flt(22, T_VR, "v_roughness", -1.0)
     elif kind == 3:
-        r[7:10] = tex.rgbval(cfg, "kr", 0.9)
+        rgb(7, T_KR, "kr", 0.9)
     elif kind == 4:
-        r[7:10] = tex.rgbval(cfg, "kr", 1.0)
-        r[10:13] = tex.rgbval(cfg, "kt", 1.0)
-        r[23] = tex.fval(cfg, "eta", 1.5)
-        r[21] = tex.fval(cfg, "u_roughness", 0.0)
-        r[22] = tex.fval(cfg, "v_roughness", 0.0)
+        rgb(7, T_KR, "kr", 1.0)
+        rgb(10, T_KT, "kt", 1.0)
+        flt(23, T_ETA, "eta", 1.5)
+        flt(21, T_UR, "u_roughness", 0.0)
+        flt(22, T_VR, "v_roughness", 0.0)
     r[24] = 1.0 if cfg.get("remap_roughness", False) else 0.0
     return r
 
@@ -255,7 +369,8 @@ class LoadedScene:
             if row is not None:
                 self.mat_index[m.get("material_name", "DefaultMaterialName")] = len(rows)
                 rows.append(row)
-        self.materials = np.array(rows).reshape(-1, 26)
+        self.materials = np.array(rows).reshape(-1, MAT_ROW)
+        self.textures = tex.table()
         meshes = {}
         for o in cfg.get("objs", []) or []:
             meshes[o.get("obj_name", "DefaultObjName")] = parse_obj(root / o.get("filename", "DefaultObj"))
@@ -296,6 +411,8 @@ class LoadedScene:
         L = O.lib()
         L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_set_textures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_set_textures(s.h, self.textures.shape[0], self.textures.ctypes.data)
         L.orc_set_materials(s.h, self.materials.shape[0], self.materials.ctypes.data)
         L.orc_set_lights(s.h, self.lights.shape[0], self.lights.ctypes.data)
 
