@@ -168,6 +168,35 @@ typedef struct rrt_material {
     double eta;                       /* Glass index                                            */
 } rrt_material;
 
+/* Textures a material parameter can name (make_textures, renderprocess.rs:298-515): the scene's float and rgb
+ * textures flattened into ONE table in definition order (float textures first).  A texture can only name textures
+ * defined before it (the loader looks names up in the maps it is filling; an unknown name becomes a constant,
+ * get_text_fallback :282-296), so children always have smaller indices.  Float textures use v[.][0].
+ * texture/{bilerp,mix,scale,checkerboard,uv}.rs; mappings texture/mod.rs:206-347.  Point-sampled only: the
+ * closed-form checkerboard filter is evaluated with zero texture-space differentials (what every non-camera ray
+ * sees in the reference: interaction.rs:223-284 leaves du/dv at 0 without ray differentials).             */
+typedef enum rrt_texture_kind {
+    RRT_TEX_CONSTANT = 0, RRT_TEX_BILERP = 1, RRT_TEX_SCALE = 2, RRT_TEX_MIX = 3, RRT_TEX_CHECKER2D = 4,
+    RRT_TEX_CHECKER3D = 5, RRT_TEX_UV = 6
+} rrt_texture_kind;
+typedef enum rrt_texture_mapping {
+    RRT_TEXMAP_UV = 0, RRT_TEXMAP_PLANAR = 1, RRT_TEXMAP_SPHERICAL = 2, RRT_TEXMAP_CYLINDRICAL = 3
+} rrt_texture_mapping;
+#define RRT_MAX_TEXTURES 32
+typedef struct rrt_texture {
+    uint32_t kind, mapping;
+    int32_t t1, t2, amount;       /* child texture indices (< own index); amount: a float texture (Mix)        */
+    uint32_t pad;
+    double v[4][3];               /* Constant: v[0]; Bilerp: v00 v01 v10 v11                                   */
+    double map[8];                /* uv: su sv du dv; planar: vs[3] vt[3] ds dt                                */
+    double world_to_texture[16];  /* Checkerboard 3D (IdentityMapping3D), spherical / cylindrical: row-major   */
+} rrt_texture;
+/* Which texture drives each parameter of a material; -1 = the constant held in rrt_material.               */
+typedef enum rrt_material_slot {
+    RRT_SLOT_KD = 0, RRT_SLOT_KS, RRT_SLOT_KR, RRT_SLOT_KT, RRT_SLOT_METAL_ETA, RRT_SLOT_METAL_K, RRT_SLOT_SIGMA,
+    RRT_SLOT_ROUGHNESS, RRT_SLOT_U_ROUGHNESS, RRT_SLOT_V_ROUGHNESS, RRT_SLOT_ETA, RRT_MATERIAL_SLOTS
+} rrt_material_slot;
+
 /* lights/point.rs, lights/distant.rs, lights/diffuse.rs (make_light, renderprocess.rs:967-1053).
  * A DiffuseAreaLight samples a shape of its own — make_light_shape (renderprocess.rs:1078-1095): a Sphere with its
  * own transform, or one triangle of a loaded mesh (untransformed vertices, Q7).  That shape is not in the aggregate
@@ -216,6 +245,14 @@ typedef struct rrt_render rrt_render; /* Box<dyn Integrator> + its film, camera 
 
 int rrt_scene_set_materials(rrt_scene* scene, uint32_t n, const rrt_material* materials);
 int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
+/* The texture table (n <= RRT_MAX_TEXTURES) and, per material set with rrt_scene_set_materials, the
+ * RRT_MATERIAL_SLOTS texture indices of its parameters (slots[material * RRT_MATERIAL_SLOTS + slot], -1 = constant).
+ * Optional: a scene without these calls has constant-valued materials.                                        */
+int rrt_scene_set_textures(rrt_scene* scene, uint32_t n, const rrt_texture* textures);
+int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, const int32_t* slots);
+/* Host-only evaluation of a texture table at (uv, p) with the product's own evaluator (csrc/texture_core.h, the
+ * code the shade kernel runs): out[3 * i + c] for every texture i.  For the CPU test-suite.                  */
+int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3], double* out);
 /* deploy_render's loader: parses scene.json (+ the .obj files it names, relative to it) into a
  * committed scene and the integrator that renders it.  `overrides_json` (may be NULL) replaces
  * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */
@@ -229,6 +266,10 @@ int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrid
  * spheres, instances, materials, lights, max_prims_in_node, lens values; desc = the render
  * description (lens_data pointer left NULL).  Used by the CPU test-suite and by tooling.          */
 int rrt_scene_json_probe(const char* path, const char* overrides_json, uint64_t out8[8], rrt_render_desc* desc);
+/* Host-only view of the loader's texture table and materials: textures (room for RRT_MAX_TEXTURES, may be NULL),
+ * the first max_materials materials and their RRT_MATERIAL_SLOTS texture indices each (may be NULL).          */
+int rrt_scene_json_texture_probe(const char* path, const char* overrides_json, uint32_t* n_textures, rrt_texture* textures,
+                                 uint32_t max_materials, uint32_t* n_materials, rrt_material* materials, int32_t* slots);
 /* make_integrator for an assembled scene.                                                       */
 int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out);
 void rrt_render_destroy(rrt_render* render);

@@ -443,21 +443,31 @@ enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MA
 // table in definition order (a texture can only name textures defined before it: make_textures looks names up
 // in the maps it is filling, renderprocess.rs:298-515; an unknown name falls back to a constant, :282-296), so
 // evaluating the table front to back evaluates every child before its parent.  Float textures use component 0.
-// In scope: Constant, Bilerp, Scale, Mix, Checkerboard 2D (aamode none) and 3D; UV and planar 2D mappings,
-// IdentityMapping3D.  Closed-form checkerboard filtering needs ray differentials and is refused by the loaders.
-enum TexKind : uint32_t { TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5 };
-enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1 };
+// In scope: Constant, Bilerp, Scale, Mix, UV, Checkerboard 2D (aamode none) and 3D; UV, planar, spherical and
+// cylindrical 2D mappings, IdentityMapping3D.  Closed-form checkerboard filtering needs ray differentials and is
+// refused by the loaders.
+enum TexKind : uint32_t { TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5, TEX_UV = 6 };
+enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1, MAP_SPHERICAL = 2, MAP_CYLINDRICAL = 3 };
 struct Texture {
     uint32_t kind = TEX_CONST, mapping = MAP_UV;
     int32_t t1 = -1, t2 = -1, amount = -1;
     Rgb v[4];
     double map[8] = {1, 1, 0, 0, 0, 0, 0, 0};  // uv: su sv du dv; planar: vs[3] vt[3] ds dt
-    Xform w2t;                                  // checkerboard 3D: IdentityMapping3D's transform
+    Xform w2t;                                  // checkerboard 3D: IdentityMapping3D's transform; spherical / cylindrical
 };
 constexpr int kMaxTextures = 32;
-// TextureMapping2D::map without the differentials (texture/mod.rs:218-229 uv, :338-347 planar)
+// TextureMapping2D::map without the differentials (texture/mod.rs:235-243 uv, :254-260 spherical, :295-298
+// cylindrical, :338-347 planar)
 inline P2 tex_map2d(const Texture& t, P2 uv, V3 p) {
     if (t.mapping == MAP_UV) return P2(t.map[0] * uv.x + t.map[2], t.map[1] * uv.y + t.map[3]);
+    if (t.mapping == MAP_SPHERICAL || t.mapping == MAP_CYLINDRICAL) {
+        V3 v = normalize_vec(xf_point(t.w2t, p) - V3());
+        if (t.mapping == MAP_CYLINDRICAL) return P2((PI + std::atan2(v.y, v.x)) / (2.0 * PI), v.z);
+        double theta = std::acos(clamp_t(v.z, -1.0, 1.0));  // geometry.rs:1189-1201
+        double phi = std::atan2(v.y, v.x);
+        if (phi < 0.0) phi = phi + 2.0 * PI;
+        return P2(theta / PI, phi / (PI * 2.0));
+    }
     V3 vs(t.map[0], t.map[1], t.map[2]), vt(t.map[3], t.map[4], t.map[5]);
     return P2(t.map[6] + dot(p, vs), t.map[7] + dot(p, vt));
 }
@@ -488,6 +498,11 @@ inline void tex_eval_all(const std::vector<Texture>& table, P2 uv, V3 p, Rgb* va
                 P2 st = tex_map2d(t, uv, p);
                 int32_t sum = (int32_t)((uint32_t)rust_f64_as_i32(std::floor(st.x)) + (uint32_t)rust_f64_as_i32(std::floor(st.y)));
                 vals[i] = (sum % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                break;
+            }
+            case TEX_UV: {  // uv.rs:20-27 (Spectrum<3>::from_rgb copies, spectrum.rs:2740-2742)
+                P2 st = tex_map2d(t, uv, p);
+                vals[i] = Rgb(st.x - std::floor(st.x), st.y - std::floor(st.y), 0.0);
                 break;
             }
             default: {  // checkerboard.rs:121-131

@@ -3,6 +3,7 @@
 // (src/scene.rs:69-80) stand in the reference.  No exception leaves this file.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -91,6 +92,8 @@ struct rrt_scene {
     rrt::HostScene host;
     std::vector<rrt_material> materials;
     std::vector<rrt_light> lights;
+    std::vector<rrt_texture> textures;
+    std::vector<int32_t> material_slots;  // RRT_MATERIAL_SLOTS per material, or empty
     std::unique_ptr<rrt::RayTracer> agg;  // DeviceAggregate (Tier F) or LiteralAggregate (Tier L)
     bool committed = false;
     uint32_t build_flags = 0;
@@ -484,6 +487,36 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights) 
     return RRT_OK;
 }
 
+int rrt_scene_set_textures(rrt_scene* scene, uint32_t n, const rrt_texture* textures) {
+    if (!scene || (n && !textures)) return fail(RRT_ERR_INVALID, "rrt_scene_set_textures: null argument");
+    if (n > RRT_MAX_TEXTURES) return fail(RRT_ERR_UNSUPPORTED, "rrt_scene_set_textures: more than RRT_MAX_TEXTURES textures");
+    try {
+        std::string err;
+        if (!rrt::validate_textures(textures, n, &err)) return fail(RRT_ERR_INVALID, "rrt_scene_set_textures: " + err);
+        scene->textures.assign(textures, textures + n);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, const int32_t* slots) {
+    if (!scene || (n_materials && !slots)) return fail(RRT_ERR_INVALID, "rrt_scene_set_material_textures: null argument");
+    try {
+        scene->material_slots.assign(slots, slots + (size_t)n_materials * RRT_MATERIAL_SLOTS);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3], double* out) {
+    if ((n && !textures) || !uv || !p || !out) return fail(RRT_ERR_INVALID, "rrt_texture_host_probe: null argument");
+    if (n > RRT_MAX_TEXTURES) return fail(RRT_ERR_UNSUPPORTED, "rrt_texture_host_probe: more than RRT_MAX_TEXTURES textures");
+    std::string err;
+    if (!rrt::validate_textures(textures, n, &err)) return fail(RRT_ERR_INVALID, "rrt_texture_host_probe: " + err);
+    rrt::texture_host_eval(textures, n, uv, p, out);
+    return RRT_OK;
+}
+
 int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out) {
     if (!scene || !desc || !out) return fail(RRT_ERR_INVALID, "rrt_render_create: null argument");
     *out = nullptr;
@@ -495,8 +528,8 @@ int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render*
         std::unique_ptr<rrt_render> r(new rrt_render());
         r->scene = scene;
         std::string err;
-        rc = r->renderer.create(scene->ctx->device, scene->host, scene->agg.get(), scene->materials, scene->lights, wb, *desc,
-                                &err);
+        rc = r->renderer.create(scene->ctx->device, scene->host, scene->agg.get(), scene->materials, scene->lights,
+                                scene->textures, scene->material_slots, wb, *desc, &err);
         if (rc != RRT_OK) return fail(rc, err);
         scene->ctx->launches.fetch_add(r->renderer.stats().launches, std::memory_order_relaxed);
         *out = r.release();
@@ -529,6 +562,8 @@ int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrid
     s->host = std::move(loaded.scene);
     s->materials = loaded.materials;
     s->lights = loaded.lights;
+    s->textures = loaded.textures;
+    s->material_slots = loaded.material_slots;
     rc = rrt_scene_commit(s, loaded.max_prims_in_node, build_flags);
     if (rc != RRT_OK) {
         rrt_scene_destroy(s);
@@ -543,6 +578,24 @@ int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrid
         }
     }
     *scene = s;
+    return RRT_OK;
+}
+
+int rrt_scene_json_texture_probe(const char* path, const char* overrides_json, uint32_t* n_textures, rrt_texture* textures,
+                                 uint32_t max_materials, uint32_t* n_materials, rrt_material* materials, int32_t* slots) {
+    if (!path || !n_textures || !n_materials) return fail(RRT_ERR_INVALID, "rrt_scene_json_texture_probe: null argument");
+    try {
+        rrt::LoadedScene l;
+        rrt::load_scene_json(path, overrides_json ? overrides_json : "", 0, &l);
+        *n_textures = (uint32_t)l.textures.size();
+        *n_materials = (uint32_t)l.materials.size();
+        if (textures) std::copy(l.textures.begin(), l.textures.end(), textures);
+        const size_t nm = std::min<size_t>(max_materials, l.materials.size());
+        if (materials) std::copy(l.materials.begin(), l.materials.begin() + nm, materials);
+        if (slots) std::copy(l.material_slots.begin(), l.material_slots.begin() + nm * RRT_MATERIAL_SLOTS, slots);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_IO, e.what());
+    }
     return RRT_OK;
 }
 

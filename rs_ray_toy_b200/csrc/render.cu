@@ -413,7 +413,15 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
             Surface s;
             make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
             Bsdf bsdf;
-            make_bsdf(sc.materials[s.material], s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
+            {
+                const MaterialRec* m = sc.materials + s.material;
+                MaterialRec textured;
+                if (m->needed) {
+                    material_at(sc, *m, s, &textured);
+                    m = &textured;
+                }
+                make_bsdf(*m, s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
+            }
             if (!bsdf.present) {
                 alive = false;  // path.rs:101-106 (usize underflow in the reference, Q21): the path ends here
             } else {
@@ -760,8 +768,58 @@ bool look_at_inverse(const double pos[3], const double look[3], const double up[
 }
 }  // namespace
 
+namespace {
+TextureRec texture_rec_of(const rrt_texture& t) {
+    TextureRec r{};
+    r.kind = t.kind;
+    r.mapping = t.mapping;
+    r.t1 = t.t1;
+    r.t2 = t.t2;
+    r.amount = t.amount;
+    for (int k = 0; k < 4; ++k) r.v[k] = Rgb{t.v[k][0], t.v[k][1], t.v[k][2]};
+    for (int k = 0; k < 8; ++k) r.map[k] = t.map[k];
+    for (int k = 0; k < 12; ++k) r.w2t.m[k] = t.world_to_texture[k];
+    return r;
+}
+}  // namespace
+
+bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err) {
+    auto bad = [&](uint32_t i, const char* what) {
+        if (err) *err = "texture " + std::to_string(i) + ": " + what;
+        return false;
+    };
+    if (n > (uint32_t)kMaxTextures) return bad(n, "more than RRT_MAX_TEXTURES textures");
+    for (uint32_t i = 0; i < n; ++i) {
+        const rrt_texture& x = t[i];
+        if (x.kind > RRT_TEX_UV) return bad(i, "kind outside the hot-path scope");
+        if (x.mapping > RRT_TEXMAP_CYLINDRICAL) return bad(i, "mapping outside the hot-path scope");
+        const bool pair = x.kind == RRT_TEX_SCALE || x.kind == RRT_TEX_MIX || x.kind == RRT_TEX_CHECKER2D || x.kind == RRT_TEX_CHECKER3D;
+        auto child_ok = [&](int32_t c) { return c >= 0 && (uint32_t)c < i; };
+        if (pair && (!child_ok(x.t1) || !child_ok(x.t2))) return bad(i, "t1 / t2 must name textures defined earlier");
+        if (x.kind == RRT_TEX_MIX && !child_ok(x.amount)) return bad(i, "amount must name a texture defined earlier");
+        const double* last = x.world_to_texture + 12;
+        const bool uses_matrix = x.kind == RRT_TEX_CHECKER3D || x.mapping >= RRT_TEXMAP_SPHERICAL;
+        if (uses_matrix && !(last[0] == 0.0 && last[1] == 0.0 && last[2] == 0.0 && last[3] == 1.0))
+            return bad(i, "world_to_texture must be affine");
+    }
+    return true;
+}
+
+void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], double* out) {
+    TextureRec table[kMaxTextures];
+    Rgb vals[kMaxTextures];
+    for (uint32_t i = 0; i < n; ++i) table[i] = texture_rec_of(t[i]);
+    texture_eval_table(table, n, n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u), P2{uv[0], uv[1]}, v3(p[0], p[1], p[2]), vals);
+    for (uint32_t i = 0; i < n; ++i) {
+        out[3 * i] = vals[i].r;
+        out[3 * i + 1] = vals[i].g;
+        out[3 * i + 2] = vals[i].b;
+    }
+}
+
 int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
-                     const std::vector<rrt_light>& lights, const double wb[6], const rrt_render_desc& d, std::string* err) {
+                     const std::vector<rrt_light>& lights, const std::vector<rrt_texture>& textures,
+                     const std::vector<int32_t>& material_slots, const double wb[6], const rrt_render_desc& d, std::string* err) {
     auto t_start = std::chrono::steady_clock::now();
     if (d.xres <= 0 || d.yres <= 0 || d.xres > 32768 || d.yres > 32768) {
         if (err) *err = "Film resolution out of range";
@@ -788,6 +846,27 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
             if (err) *err = "primitive refers to a material that was not set";
             return RRT_ERR_INVALID;
         }
+    if (!validate_textures(textures.data(), (uint32_t)textures.size(), err)) return RRT_ERR_INVALID;
+    if (!material_slots.empty()) {
+        if (material_slots.size() != materials.size() * RRT_MATERIAL_SLOTS) {
+            if (err) *err = "rrt_scene_set_material_textures must cover the materials that were set";
+            return RRT_ERR_INVALID;
+        }
+        for (size_t i = 0; i < material_slots.size(); ++i) {
+            const int32_t t = material_slots[i];
+            if (t < -1 || t >= (int32_t)textures.size()) {
+                if (err) *err = "material names a texture that was not set";
+                return RRT_ERR_INVALID;
+            }
+            // a textured glass roughness could turn the material into rough glass at some hits
+            const size_t slot = i % RRT_MATERIAL_SLOTS;
+            if (t >= 0 && materials[i / RRT_MATERIAL_SLOTS].kind == RRT_MAT_GLASS &&
+                (slot == RRT_SLOT_U_ROUGHNESS || slot == RRT_SLOT_V_ROUGHNESS)) {
+                if (err) *err = "textured glass roughness (MicrofacetTransmission) is outside the hot-path scope";
+                return RRT_ERR_UNSUPPORTED;
+            }
+        }
+    }
     bool specular_material = false;
     for (const rrt_material& m : materials) {
         if (m.kind > RRT_MAT_GLASS) {
@@ -974,6 +1053,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     {
         int grc = upload_geometry_tables(scene, &I.sc, &I.allocations, err);
         if (grc != RRT_OK) return grc;
+        std::vector<TextureRec> texs(textures.size());
+        for (size_t i = 0; i < textures.size(); ++i) texs[i] = texture_rec_of(textures[i]);
         std::vector<MaterialRec> mats(materials.size());
         for (size_t i = 0; i < materials.size(); ++i) {
             const rrt_material& m = materials[i];
@@ -991,6 +1072,10 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
             r.u_roughness = m.u_roughness;
             r.v_roughness = m.v_roughness;
             r.eta = m.eta;
+            for (int k = 0; k < RRT_MATERIAL_SLOTS; ++k) {
+                r.tex[k] = material_slots.empty() ? -1 : material_slots[i * RRT_MATERIAL_SLOTS + k];
+                r.needed |= texture_closure(texs.data(), r.tex[k]);
+            }
             mats[i] = r;
         }
         std::vector<LightRec> lts(lights.size());
@@ -1038,6 +1123,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         ShadeScene& S = I.sc;
         int rc;
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
+        if ((rc = I.up(texs, &S.textures, err)) != RRT_OK) return rc;
+        S.n_textures = (uint32_t)texs.size();
         if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
         S.n_lights = (uint32_t)lts.size();
         S.literal = agg->literal() ? 1u : 0u;

@@ -17,6 +17,11 @@ struct RenderStats {
              launches = 0, render_usec = 0, setup_usec = 0, chunks = 0;
 };
 
+// rrt_texture table checks shared by the ABI setters: kinds / mappings known, children defined earlier.
+bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err);
+// texture_core.h on the host: out[3 * i + c] for every texture (rrt_texture_host_probe)
+void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], double* out);
+
 class Renderer {
   public:
     Renderer() = default;
@@ -27,7 +32,8 @@ class Renderer {
     // make_integrator: film, camera (thick-lens focus + exit-pupil bounds), sampler tables,
     // light distribution; uploads the shading tables of `scene`.
     int create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
-               const std::vector<rrt_light>& lights, const double world_bound6[6], const rrt_render_desc& desc,
+               const std::vector<rrt_light>& lights, const std::vector<rrt_texture>& textures,
+               const std::vector<int32_t>& material_slots, const double world_bound6[6], const rrt_render_desc& desc,
                std::string* err);
     // Integrator::render for this rank's tiles
     int run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, std::string* err);

@@ -175,48 +175,172 @@ void parse_obj(const std::string& path, TriangleMesh* mesh) {
         if ((size_t)x >= mesh->p.size() / 3) throw std::runtime_error("ParseObjError: vertex index out of range in " + path);
 }
 
-struct ConstTextures {
-    std::map<std::string, double> f;
-    std::map<std::string, std::array<double, 3>> rgb;
+// make_textures (renderprocess.rs:298-515) flattened into the rrt_texture table: float textures first, then rgb
+// textures, each in definition order.  Names are looked up in the map being filled, so a texture only sees the
+// ones defined before it; an unknown child name becomes a constant (get_text_fallback, :282-296); a redefined name
+// replaces the earlier entry for later lookups (HashMap::insert).
+struct TextureTable {
+    std::vector<rrt_texture> rows;
+    std::map<std::string, int32_t> f, rgb;  // name -> row; -2 = defined, but of a type outside the hot-path scope
+
+    int32_t push(uint32_t kind) {
+        rrt_texture t;
+        std::memset(&t, 0, sizeof(t));
+        t.kind = kind;
+        t.mapping = RRT_TEXMAP_UV;
+        t.t1 = t.t2 = t.amount = -1;
+        t.map[0] = t.map[1] = 1.0;  // UVMapping2D::new(1, 1, 0, 0) when no mapping block is given (:607-609)
+        for (int k = 0; k < 4; ++k) t.world_to_texture[5 * k] = 1.0;
+        if (rows.size() >= RRT_MAX_TEXTURES) throw std::runtime_error("more than RRT_MAX_TEXTURES textures (constants included)");
+        rows.push_back(t);
+        return (int32_t)rows.size() - 1;
+    }
+    int32_t constant(const double v[3]) {
+        const int32_t i = push(RRT_TEX_CONSTANT);
+        for (int k = 0; k < 3; ++k) rows[i].v[0][k] = v[k];
+        return i;
+    }
+    int32_t child(const std::map<std::string, int32_t>& names, const std::string& name, double def, bool is_rgb) {
+        auto it = names.find(name);
+        if (it != names.end()) {
+            if (it->second == -2) throw std::runtime_error("texture '" + name + "' has a type outside the hot-path scope");
+            return it->second;
+        }
+        const double v[3] = {def, is_rgb ? def : 0.0, is_rgb ? def : 0.0};
+        return constant(v);
+    }
+    // make_texture_mapping_2d (:571-612)
+    void mapping(int32_t i, const Value& tc, const Transform& to_world) {
+        const Value* mc = tc.get("mapping");
+        if (!mc) return;
+        rrt_texture& t = rows[i];
+        const std::string kind = read_string(*mc, "mapping", "uv");
+        if (kind == "uv") {  // du / dv default to 1 once a mapping block is given (:582-583)
+            t.mapping = RRT_TEXMAP_UV;
+            t.map[0] = read_f64(*mc, "su", 1.0);
+            t.map[1] = read_f64(*mc, "sv", 1.0);
+            t.map[2] = read_f64(*mc, "du", 1.0);
+            t.map[3] = read_f64(*mc, "dv", 1.0);
+        } else if (kind == "planar") {
+            t.mapping = RRT_TEXMAP_PLANAR;
+            read_xyz(*mc, "v1", t.map, 1, 0, 0);
+            read_xyz(*mc, "v2", t.map + 3, 0, 1, 0);
+            t.map[6] = read_f64(*mc, "udelta", 0.0);
+            t.map[7] = read_f64(*mc, "vdelta", 0.0);
+        } else if (kind == "spherical" || kind == "cylindrical") {  // Transform::inverse(to_world)
+            t.mapping = kind == "spherical" ? RRT_TEXMAP_SPHERICAL : RRT_TEXMAP_CYLINDRICAL;
+            std::memcpy(t.world_to_texture, to_world.inv.m, sizeof(t.world_to_texture));
+        } else {
+            throw std::runtime_error("Unsupported Mapping Type " + kind);  // the reference panics (:601-606)
+        }
+    }
+    void add(const Value& tc, bool is_rgb) {
+        std::map<std::string, int32_t>& names = is_rgb ? rgb : f;
+        const Transform to_world = make_to_world(tc);
+        const std::string type = read_string(tc, "texture_type", "");
+        const std::string name = read_string(tc, "texture_name", "DefaultTextureName");
+        auto value = [&](const char* key, double def, double out[3]) {
+            if (is_rgb) {
+                read_spectrum(tc, key, out, def);
+            } else {
+                out[0] = read_f64(tc, key, def);
+                out[1] = out[2] = 0.0;
+            }
+        };
+        const std::string t1 = read_string(tc, "t1", "ErrorTextureName"), t2 = read_string(tc, "t2", "ErrorTextureName");
+        int32_t i;
+        if (type == "BilerpTexture") {
+            double v[4][3];  // v10 and v11 are read from the key "v01" (:326-329, :439-442)
+            value("v00", 0.0, v[0]);
+            value("v01", 1.0, v[1]);
+            value("v01", 0.0, v[2]);
+            value("v01", 1.0, v[3]);
+            bool same = true;
+            for (int k = 1; k < 4; ++k)
+                for (int c = 0; c < 3; ++c) same &= v[k][c] == v[0][c];
+            if (same) {  // a constant in all but the 1-ulp sum of the four weights
+                names[name] = constant(v[0]);
+                return;
+            }
+            i = push(RRT_TEX_BILERP);
+            std::memcpy(rows[i].v, v, sizeof(v));
+            mapping(i, tc, to_world);
+        } else if (type == "UVTexture" && is_rgb) {
+            i = push(RRT_TEX_UV);
+            mapping(i, tc, to_world);
+        } else if (type == "ScaleTexture") {
+            const int32_t c1 = child(names, t1, 1.0, is_rgb), c2 = child(names, t2, 1.0, is_rgb);
+            i = push(RRT_TEX_SCALE);
+            rows[i].t1 = c1;
+            rows[i].t2 = c2;
+        } else if (type == "MixTexture") {  // the amount is looked up under the key "t2" too (:319, :411)
+            const int32_t c1 = child(names, t1, 0.0, is_rgb), c2 = child(names, t2, 1.0, is_rgb), amt = child(f, t2, 0.5, false);
+            i = push(RRT_TEX_MIX);
+            rows[i].t1 = c1;
+            rows[i].t2 = c2;
+            rows[i].amount = amt;
+        } else if (type == "CheckerBoardTexture") {
+            const int64_t dim = read_i64(tc, "dimension", 2);
+            if (dim != 2 && dim != 3) return;  // logged and skipped (:341-344)
+            const int32_t c1 = child(names, t1, 1.0, is_rgb), c2 = child(names, t2, 0.0, is_rgb);
+            if (dim == 2) {
+                if (read_string(tc, "aamode", "closedform") != "none")
+                    throw std::runtime_error("closed-form checkerboard filtering needs ray differentials: set \"aamode\": \"none\"");
+                i = push(RRT_TEX_CHECKER2D);
+                mapping(i, tc, to_world);
+            } else {  // IdentityMapping3D::new(to_world): the matrix is used as world_to_texture as it stands
+                i = push(RRT_TEX_CHECKER3D);
+                std::memcpy(rows[i].world_to_texture, to_world.m.m, sizeof(rows[i].world_to_texture));
+            }
+            rows[i].t1 = c1;
+            rows[i].t2 = c2;
+        } else if (type == "ImageTexture" || type == "WindyTexture" || type == "WrinkledTexture" || (type == "UVTexture" && !is_rgb)) {
+            if (type == "UVTexture") return;  // not a float texture type: "Unsupported Texture Type", nothing inserted
+            names[name] = -2;                  // an error only if something uses it
+            return;
+        } else {
+            return;  // "Unsupported Texture Type": nothing inserted
+        }
+        names[name] = i;
+    }
+    // -> texture index, or -1 with the constant written to `out`
+    int32_t resolve(int32_t i, const std::string& name, double out[3]) const {
+        if (i == -2) throw std::runtime_error("texture '" + name + "' has a type outside the hot-path scope");
+        if (rows[i].kind != RRT_TEX_CONSTANT) return i;
+        for (int k = 0; k < 3; ++k) out[k] = rows[i].v[0][k];
+        return -1;
+    }
 };
-ConstTextures collect_textures(const Value& root) {
-    ConstTextures t;
+TextureTable collect_textures(const Value& root) {
+    TextureTable t;
     if (const Value* a = root.get("float_texture"); a && a->is_array())
-        for (const auto& tc : a->arr) {
-            if (read_string(*tc, "texture_type", "") != "BilerpTexture") continue;
-            const double v00 = read_f64(*tc, "v00", 0.0), v01 = read_f64(*tc, "v01", 1.0);
-            if (v00 == v01) t.f[read_string(*tc, "texture_name", "DefaultTextureName")] = v00;
-        }
+        for (const auto& tc : a->arr) t.add(*tc, false);
     if (const Value* a = root.get("rgb_texture"); a && a->is_array())
-        for (const auto& tc : a->arr) {
-            if (read_string(*tc, "texture_type", "") != "BilerpTexture") continue;
-            double v00[3], v01[3];
-            read_spectrum(*tc, "v00", v00, 0.0);
-            read_spectrum(*tc, "v01", v01, 1.0);
-            if (v00[0] == v01[0] && v00[1] == v01[1] && v00[2] == v01[2])
-                t.rgb[read_string(*tc, "texture_name", "DefaultTextureName")] = {v00[0], v00[1], v00[2]};
-        }
+        for (const auto& tc : a->arr) t.add(*tc, true);
     return t;
 }
-double tex_f(const Value& m, const ConstTextures& t, const char* key, double def) {
+// fetch_float_texture (:614-626): a name that is not a float texture panics in the reference
+double tex_f(const Value& m, const TextureTable& t, const char* key, double def, int32_t* slot) {
+    *slot = -1;
     const Value* x = m.get(key);
     if (x && x->is_string()) {
         auto it = t.f.find(x->str);
-        if (it == t.f.end()) throw std::runtime_error("float texture '" + x->str + "' is outside the hot-path scope (constants only)");
-        return it->second;
+        if (it == t.f.end()) throw std::runtime_error("float texture '" + x->str + "' does not exist");
+        double v[3] = {def, 0.0, 0.0};
+        *slot = t.resolve(it->second, x->str, v);
+        return v[0];
     }
     return def;
 }
-void tex_rgb(const Value& m, const ConstTextures& t, const char* key, double out[3], const double def[3]) {
+// fetch_rgb_texture (:643-661) falls through to the default when the name is unknown
+void tex_rgb(const Value& m, const TextureTable& t, const char* key, double out[3], const double def[3], int32_t* slot) {
+    *slot = -1;
+    for (int k = 0; k < 3; ++k) out[k] = def[k];
     const Value* x = m.get(key);
     if (x && x->is_string()) {
         auto it = t.rgb.find(x->str);
-        if (it != t.rgb.end()) {  // fetch_rgb_texture falls through to the default when the name is unknown
-            for (int k = 0; k < 3; ++k) out[k] = it->second[k];
-            return;
-        }
+        if (it != t.rgb.end()) *slot = t.resolve(it->second, x->str, out);
     }
-    for (int k = 0; k < 3; ++k) out[k] = def[k];
 }
 
 // RGB of the reference's default copper spectra: material/metal.rs COPPER_N / COPPER_K pushed
@@ -224,39 +348,40 @@ void tex_rgb(const Value& m, const ConstTextures& t, const char* key, double out
 const double kCopperN[3] = {0.19998972096819712, 0.922085788777433, 1.0998762520488314};
 const double kCopperK[3] = {3.9046381767086675, 2.4476332238684626, 2.1376510366555137};
 
-bool make_material(const Value& m, const ConstTextures& t, rrt_material* out) {
+bool make_material(const Value& m, const TextureTable& t, rrt_material* out, int32_t slots[RRT_MATERIAL_SLOTS]) {
     const std::string type = read_string(m, "material_type", "");
     rrt_material r;
     std::memset(&r, 0, sizeof(r));
+    for (int k = 0; k < RRT_MATERIAL_SLOTS; ++k) slots[k] = -1;
     r.u_roughness = r.v_roughness = -1.0;
     r.remap_roughness = read_bool(m, "remap_roughness", false) ? 1 : 0;
     const double c5[3] = {0.5, 0.5, 0.5}, c25[3] = {0.25, 0.25, 0.25}, c9[3] = {0.9, 0.9, 0.9}, c1[3] = {1.0, 1.0, 1.0};
     if (type == "MatteMaterial") {
         r.kind = RRT_MAT_MATTE;
-        tex_rgb(m, t, "kd", r.kd, c5);
-        r.sigma = tex_f(m, t, "sigma", 0.0);
+        tex_rgb(m, t, "kd", r.kd, c5, &slots[RRT_SLOT_KD]);
+        r.sigma = tex_f(m, t, "sigma", 0.0, &slots[RRT_SLOT_SIGMA]);
     } else if (type == "PlasticMaterial") {
         r.kind = RRT_MAT_PLASTIC;
-        tex_rgb(m, t, "kd", r.kd, c25);
-        tex_rgb(m, t, "ks", r.ks, c25);
-        r.roughness = tex_f(m, t, "roughness", 0.1);
+        tex_rgb(m, t, "kd", r.kd, c25, &slots[RRT_SLOT_KD]);
+        tex_rgb(m, t, "ks", r.ks, c25, &slots[RRT_SLOT_KS]);
+        r.roughness = tex_f(m, t, "roughness", 0.1, &slots[RRT_SLOT_ROUGHNESS]);
     } else if (type == "MetalMaterial") {
         r.kind = RRT_MAT_METAL;
-        tex_rgb(m, t, "eta", r.metal_eta, kCopperN);
-        tex_rgb(m, t, "k", r.metal_k, kCopperK);
-        r.roughness = tex_f(m, t, "roughness", 0.01);
-        r.u_roughness = tex_f(m, t, "u_roughness", -1.0);
-        r.v_roughness = tex_f(m, t, "v_roughness", -1.0);
+        tex_rgb(m, t, "eta", r.metal_eta, kCopperN, &slots[RRT_SLOT_METAL_ETA]);
+        tex_rgb(m, t, "k", r.metal_k, kCopperK, &slots[RRT_SLOT_METAL_K]);
+        r.roughness = tex_f(m, t, "roughness", 0.01, &slots[RRT_SLOT_ROUGHNESS]);
+        r.u_roughness = tex_f(m, t, "u_roughness", -1.0, &slots[RRT_SLOT_U_ROUGHNESS]);
+        r.v_roughness = tex_f(m, t, "v_roughness", -1.0, &slots[RRT_SLOT_V_ROUGHNESS]);
     } else if (type == "MirrorMaterial") {
         r.kind = RRT_MAT_MIRROR;
-        tex_rgb(m, t, "kr", r.kr, c9);
+        tex_rgb(m, t, "kr", r.kr, c9, &slots[RRT_SLOT_KR]);
     } else if (type == "GlassMaterial") {
         r.kind = RRT_MAT_GLASS;
-        tex_rgb(m, t, "kr", r.kr, c1);
-        tex_rgb(m, t, "kt", r.kt, c1);
-        r.eta = tex_f(m, t, "eta", 1.5);
-        r.u_roughness = tex_f(m, t, "u_roughness", 0.0);
-        r.v_roughness = tex_f(m, t, "v_roughness", 0.0);
+        tex_rgb(m, t, "kr", r.kr, c1, &slots[RRT_SLOT_KR]);
+        tex_rgb(m, t, "kt", r.kt, c1, &slots[RRT_SLOT_KT]);
+        r.eta = tex_f(m, t, "eta", 1.5, &slots[RRT_SLOT_ETA]);
+        r.u_roughness = tex_f(m, t, "u_roughness", 0.0, &slots[RRT_SLOT_U_ROUGHNESS]);
+        r.v_roughness = tex_f(m, t, "v_roughness", 0.0, &slots[RRT_SLOT_V_ROUGHNESS]);
     } else {
         return false;  // Disney / Translucent / Mix / Debug: outside the hot path
     }
@@ -278,15 +403,18 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
     std::string dir = ".";
     if (size_t slash = path.find_last_of('/'); slash != std::string::npos) dir = path.substr(0, slash);
 
-    const ConstTextures tex = collect_textures(*root);
+    const TextureTable tex = collect_textures(*root);
+    out->textures = tex.rows;
     // ---- make_materials ----
     std::map<std::string, uint32_t> material_index;
     if (const Value* a = root->get("materials"); a && a->is_array())
         for (const auto& mc : a->arr) {
             rrt_material m;
-            if (make_material(*mc, tex, &m)) {
+            int32_t slots[RRT_MATERIAL_SLOTS];
+            if (make_material(*mc, tex, &m, slots)) {
                 material_index[read_string(*mc, "material_name", "DefaultMaterialName")] = (uint32_t)out->materials.size();
                 out->materials.push_back(m);
+                out->material_slots.insert(out->material_slots.end(), slots, slots + RRT_MATERIAL_SLOTS);
             }
         }
     // ---- make_triangle_mesh ----

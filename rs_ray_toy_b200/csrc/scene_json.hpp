@@ -15,6 +15,8 @@ struct LoadedScene {
     HostScene scene;
     std::vector<rrt_material> materials;
     std::vector<rrt_light> lights;
+    std::vector<rrt_texture> textures;      // make_textures: float textures, then rgb textures, definition order
+    std::vector<int32_t> material_slots;    // RRT_MATERIAL_SLOTS per material
     std::vector<double> lens_data;  // desc.lens_data points here
     rrt_render_desc desc;
     uint32_t max_prims_in_node = 4;

@@ -19,6 +19,7 @@
 #define RRT_SHADE_FN static __device__
 #endif
 #include "rmath.cuh"
+#include "texture_core.h"
 
 namespace rrt {
 
@@ -47,6 +48,10 @@ struct MaterialRec {  // rrt_material, flattened
     uint32_t kind, remap_roughness;
     Rgb kd, ks, kr, kt, metal_eta, metal_k;
     double sigma, roughness, u_roughness, v_roughness, eta;
+    // texture index per parameter (rrt_material_slot order; -1 = the constant above) and the bits of every
+    // texture those reach; 0 = a constant-valued material, which is never copied
+    int32_t tex[11];
+    uint32_t needed;
 };
 struct LightRec {
     uint32_t kind, shape_kind;
@@ -72,6 +77,8 @@ struct ShadeScene {
     const SphereInfo* spheres;
     const InstanceXf* instances;
     const MaterialRec* materials;
+    const TextureRec* textures;
+    uint32_t n_textures;
     const LightRec* lights;
     uint32_t n_lights;
     uint32_t literal;  // Tier L: instance / sphere rays are renormalised like the reference (Q6)
@@ -81,6 +88,7 @@ struct ShadeScene {
 struct Surface {
     V3 p, n, wo;       // BaseInteraction: point, geometric normal, outgoing direction
     V3 shn, shdpdu;    // shading.n, shading.dpdu
+    P2 uv;             // SurfaceInteraction::uv (textures only)
     uint32_t material;
 };
 
@@ -143,6 +151,10 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         }
         s.p = lo + ld * t;
         s.wo = -ld;
+        {   // triangle.rs:289: uv[0] * (1 - u - v) + uv[1] * u + uv[2] * v
+            const double b0 = sub(sub(1.0, bu), bv);
+            s.uv = P2{add(add(mul(uv0.x, b0), mul(uv1.x, bu)), mul(uv2.x, bv)), add(add(mul(uv0.y, b0), mul(uv1.y, bu)), mul(uv2.y, bv))};
+        }
         const V3 ist_n = normalize(cross(dp02, dp12));
         s.n = ist_n;
         s.shn = ist_n;
@@ -185,6 +197,7 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         const V3 dpdv = v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * sin(theta)) * (sp.theta_max - sp.theta_min);
         s.p = p;
         s.wo = -od;
+        s.uv = P2{phi / sp.phi_max, sub(theta, sp.theta_min) / sub(sp.theta_max, sp.theta_min)};  // sphere.rs:157-160
         s.n = normalize(cross(dpdu, dpdv));
         s.shn = s.n;
         s.shdpdu = dpdu;
@@ -582,7 +595,24 @@ RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* p
     return f;  // Q15: the multi-lobe re-evaluation is computed into a shadowed variable and dropped
 }
 
-// Material::compute_scattering_functions for constant-valued parameters
+// The material with every textured parameter evaluated at the hit (each compute_scattering_functions starts with
+// Texture::evaluate(si), material/*.rs).  Only called for materials with `needed != 0`.
+static __device__ __noinline__ void material_at(const ShadeScene& sc, const MaterialRec& m, const Surface& s, MaterialRec* out) {
+    Rgb vals[kMaxTextures];
+    texture_eval_table(sc.textures, sc.n_textures, m.needed, s.uv, s.p, vals);
+    MaterialRec r = m;
+    Rgb* const colours[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.metal_eta, &r.metal_k};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (m.tex[k] >= 0) *colours[k] = vals[m.tex[k]];
+    double* const scalars[5] = {&r.sigma, &r.roughness, &r.u_roughness, &r.v_roughness, &r.eta};
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (m.tex[6 + k] >= 0) *scalars[k] = vals[m.tex[6 + k]].r;
+    *out = r;
+}
+
+// Material::compute_scattering_functions once the parameters are values
 RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
     b->ns = s.shn;
     b->ss = normalize(s.shdpdu);

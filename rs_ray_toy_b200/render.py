@@ -45,6 +45,55 @@ class Material(C.Structure):
                 ("v_roughness", C.c_double), ("eta", C.c_double)]
 
 
+class Texture(C.Structure):
+    """rrt_texture."""
+    _fields_ = [("kind", C.c_uint32), ("mapping", C.c_uint32), ("t1", C.c_int32), ("t2", C.c_int32), ("amount", C.c_int32),
+                ("pad", C.c_uint32), ("v", (C.c_double * 3) * 4), ("map", C.c_double * 8), ("world_to_texture", C.c_double * 16)]
+
+
+MAX_TEXTURES = 32
+MATERIAL_SLOTS = 11
+(SLOT_KD, SLOT_KS, SLOT_KR, SLOT_KT, SLOT_METAL_ETA, SLOT_METAL_K, SLOT_SIGMA, SLOT_ROUGHNESS, SLOT_U_ROUGHNESS,
+ SLOT_V_ROUGHNESS, SLOT_ETA) = range(11)
+TEX_CONSTANT, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV = range(7)
+TEXMAP_UV, TEXMAP_PLANAR, TEXMAP_SPHERICAL, TEXMAP_CYLINDRICAL = range(4)
+
+
+def texture(kind, v=(), mapping=TEXMAP_UV, map8=(1, 1, 0, 0, 0, 0, 0, 0), t1=-1, t2=-1, amount=-1, world_to_texture=None) -> Texture:
+    """One row of the texture table; `v` = up to four values (floats or RGB triples)."""
+    t = Texture(kind=kind, mapping=mapping, t1=t1, t2=t2, amount=amount)
+    for k, val in enumerate(v):
+        t.v[k][:] = [float(val), 0.0, 0.0] if np.isscalar(val) else [float(x) for x in val]
+    t.map[:] = [float(x) for x in map8]
+    t.world_to_texture[:] = (np.eye(4) if world_to_texture is None else np.asarray(world_to_texture, dtype=np.float64)).reshape(16).tolist()
+    return t
+
+
+def texture_host_probe(textures, uv, p) -> np.ndarray:
+    """rrt_texture_host_probe: every texture of the table evaluated at (uv, p) by the product's evaluator on the host."""
+    L = lib()
+    arr = (Texture * max(1, len(textures)))(*textures)
+    out = np.zeros((len(textures), 3))
+    uv2 = (C.c_double * 2)(*[float(x) for x in uv])
+    p3 = (C.c_double * 3)(*[float(x) for x in p])
+    capi.check(L.rrt_texture_host_probe(len(textures), C.cast(arr, C.c_void_p), uv2, p3, out.ctypes.data))
+    return out
+
+
+def json_texture_probe(path, overrides=None, max_materials=256):
+    """rrt_scene_json_texture_probe -> (list of Texture, list of Material, slots[n_materials, 11])."""
+    L = lib()
+    tex = (Texture * MAX_TEXTURES)()
+    mats = (Material * max_materials)()
+    slots = np.full((max_materials, MATERIAL_SLOTS), -1, dtype=np.int32)
+    nt, nm = C.c_uint32(), C.c_uint32()
+    ov = json.dumps(overrides).encode() if overrides else None
+    capi.check(L.rrt_scene_json_texture_probe(str(path).encode(), ov, C.byref(nt), C.cast(tex, C.c_void_p), max_materials,
+                                              C.byref(nm), C.cast(mats, C.c_void_p), slots.ctypes.data))
+    n = min(nm.value, max_materials)
+    return [tex[i] for i in range(nt.value)], [mats[i] for i in range(n)], slots[:n].copy()
+
+
 class Light(C.Structure):
     """rrt_light."""
     _fields_ = [("kind", C.c_uint32), ("shape_kind", C.c_uint32), ("intensity", C.c_double * 3), ("dir", C.c_double * 3),
@@ -124,6 +173,14 @@ def _bind(L):
     L.rrt_scene_set_materials.argtypes = [vp, u32, vp]
     L.rrt_scene_set_lights.restype = i32
     L.rrt_scene_set_lights.argtypes = [vp, u32, vp]
+    L.rrt_scene_set_textures.restype = i32
+    L.rrt_scene_set_textures.argtypes = [vp, u32, vp]
+    L.rrt_scene_set_material_textures.restype = i32
+    L.rrt_scene_set_material_textures.argtypes = [vp, u32, vp]
+    L.rrt_texture_host_probe.restype = i32
+    L.rrt_texture_host_probe.argtypes = [u32, vp, vp, vp, vp]
+    L.rrt_scene_json_texture_probe.restype = i32
+    L.rrt_scene_json_texture_probe.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(u32), vp, u32, C.POINTER(u32), vp, vp]
     L.rrt_scene_load_json.restype = i32
     L.rrt_scene_load_json.argtypes = [vp, C.c_char_p, C.c_char_p, u64, pvp, pvp]
     L.rrt_scene_load_json_tier.restype = i32
@@ -208,13 +265,21 @@ class Render:
         return cls(ctx, sh, rh, True, int(desc.xres), int(desc.yres))
 
     @classmethod
-    def create(cls, agg: GpuAggregate, materials, lights, desc: RenderDesc, lens_data) -> "Render":
-        """make_integrator for an aggregate assembled through GpuAggregate."""
+    def create(cls, agg: GpuAggregate, materials, lights, desc: RenderDesc, lens_data, textures=None,
+               material_slots=None) -> "Render":
+        """make_integrator for an aggregate assembled through GpuAggregate.  `textures` = rows of the texture table,
+        `material_slots[n_materials, 11]` = which texture drives each material parameter (-1: the constant)."""
         L = lib()
         mats = (Material * len(materials))(*materials)
         lts = (Light * max(1, len(lights)))(*lights)
         capi.check(L.rrt_scene_set_materials(agg.h, len(materials), C.cast(mats, C.c_void_p)))
         capi.check(L.rrt_scene_set_lights(agg.h, len(lights), C.cast(lts, C.c_void_p)))
+        if textures is not None:
+            tex = (Texture * max(1, len(textures)))(*textures)
+            capi.check(L.rrt_scene_set_textures(agg.h, len(textures), C.cast(tex, C.c_void_p)))
+        if material_slots is not None:
+            sl = np.ascontiguousarray(material_slots, dtype=np.int32).reshape(len(materials), MATERIAL_SLOTS)
+            capi.check(L.rrt_scene_set_material_textures(agg.h, len(materials), sl.ctypes.data))
         lens = np.ascontiguousarray(lens_data, dtype=np.float64).reshape(-1)
         desc.lens_data = lens.ctypes.data_as(C.POINTER(C.c_double))
         desc.n_lens_values = lens.shape[0]

@@ -264,6 +264,89 @@ def scene_area_lights(directory, xres=192, yres=108, nsamp=9, integrator="Path",
     return path
 
 
+def write_floor_obj(path, half=6.0, y=-2.4, cx=35.2, cz=0.0, uv_scale=8.0):
+    """A two-triangle floor with texture coordinates (`v`, `vt`, `vn`, `f v/vt/vn`)."""
+    xs, zs = (cx - half, cx + half), (cz - half, cz + half)
+    lines = ["o Floor"]
+    for (x, z) in ((xs[0], zs[0]), (xs[1], zs[0]), (xs[1], zs[1]), (xs[0], zs[1])):
+        lines.append("v %.6f %.6f %.6f" % (x, y, z))
+    for (u, v) in ((0, 0), (uv_scale, 0), (uv_scale, uv_scale), (0, uv_scale)):
+        lines.append("vt %.4f %.4f" % (u, v))
+    lines.append("vn 0 1 0")
+    lines += ["f 1/1/1 3/3/1 2/2/1", "f 1/1/1 4/4/1 3/3/1"]
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
+    """SURVEY.md §8f row 3 (procedural part): config 1's cubes on a floor, plus three spheres, with every in-scope texture
+    type driving a material parameter — Checkerboard 2D (point-sampled) over mesh uvs and over a planar mapping,
+    Checkerboard 3D with a texture transform, Bilerp (float and rgb), Scale, Mix (whose amount is looked up under
+    "t2", renderprocess.rs:319), UV, spherical and cylindrical mappings — on Matte / Plastic / Metal / Mirror."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    cfg = json.loads(open(scene_c1(directory, xres=xres, yres=yres, nsamp=nsamp, integrator=integrator, max_depth=max_depth)).read())
+    write_floor_obj(os.path.join(directory, "floor.obj"))
+
+    def rgbv(r, g, b):
+        return {"values": [r, g, b]}
+
+    cfg["float_texture"] = [
+        _const_float_texture("f_lo", 0.05),
+        _const_float_texture("f_hi", 0.6),
+        {"texture_name": "f_ramp", "texture_type": "BilerpTexture", "v00": 0.02},            # v01 absent: corners 0.02 1 0 1
+        {"texture_name": "f_rough_check", "texture_type": "CheckerBoardTexture", "dimension": 3, "t1": "f_lo", "t2": "f_hi",
+         "scale": [2.0, 2.0, 2.0]},
+        {"texture_name": "f_sigma", "texture_type": "ScaleTexture", "t1": "f_ramp", "t2": "f_sixty"},  # f_sixty unknown: 1.0
+        {"texture_name": "dark", "texture_type": "BilerpTexture", "v00": 0.3, "v01": 0.3},   # float amount for the rgb Mix below
+    ]
+    cfg["rgb_texture"] = [
+        _const_rgb_texture("white", (0.85, 0.85, 0.8)),
+        _const_rgb_texture("dark", (0.1, 0.12, 0.3)),
+        _const_rgb_texture("red", (0.7, 0.15, 0.1)),
+        {"texture_name": "floor_check", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "white", "t2": "dark"},
+        {"texture_name": "planar_check", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "red", "t2": "white",
+         "mapping": {"mapping": "planar", "v1": [1.3, 0.0, 0.2], "v2": [0.0, 1.7, 0.0], "udelta": 0.25, "vdelta": -0.5}},
+        {"texture_name": "solid_check", "texture_type": "CheckerBoardTexture", "dimension": 3, "t1": "white", "t2": "red",
+         "world_pos": [0.3, 0.1, 0.2], "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 30, "scale": [1.5, 1.5, 1.5]},
+        {"texture_name": "uvcol", "texture_type": "UVTexture", "mapping": {"mapping": "uv", "su": 3.0, "sv": 2.0, "du": 0.0, "dv": 0.0}},
+        {"texture_name": "grad", "texture_type": "BilerpTexture", "v00": rgbv(0.9, 0.2, 0.1), "v01": rgbv(0.1, 0.3, 0.9),
+         "mapping": {"mapping": "spherical"}, "world_pos": [33.0, -1.0, 3.0]},
+        {"texture_name": "cyl", "texture_type": "UVTexture", "mapping": {"mapping": "cylindrical"}, "world_pos": [37.0, 0.0, -3.0]},
+        {"texture_name": "mixed", "texture_type": "MixTexture", "t1": "uvcol", "t2": "dark"},          # amount: float "dark" = 0.3
+        {"texture_name": "tinted", "texture_type": "ScaleTexture", "t1": "floor_check", "t2": "grad"},
+    ]
+    cfg["materials"] = [
+        {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_check"},
+        {"material_type": "MatteMaterial", "material_name": "m_planar", "kd": "planar_check", "sigma": "f_sigma"},
+        {"material_type": "PlasticMaterial", "material_name": "m_solid", "kd": "solid_check", "ks": "white", "roughness": "f_rough_check"},
+        {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "roughness": "f_lo"},
+        {"material_type": "MatteMaterial", "material_name": "m_grad", "kd": "grad"},
+        {"material_type": "MetalMaterial", "material_name": "m_metal", "roughness": "f_rough_check", "k": "tinted"},
+        {"material_type": "MirrorMaterial", "material_name": "m_mirror", "kr": "cyl"},
+    ]
+    cfg["objs"].append({"filename": "floor.obj", "obj_name": "floor_01"})
+    inst = cfg["Aggregate"]["primitives"][0]["instances"]
+    cube = {"primitive_type": "triangle", "obj_name": "cube_01"}
+    cfg["Aggregate"]["primitives"] = [
+        {"primitive_type": "triangle", "obj_name": "floor_01", "material_name": "m_floor", "instances": [{"world_pos": [0, 0, 0]}]},
+        dict(cube, material_name="m_planar", instances=[inst[0]]),
+        dict(cube, material_name="m_solid", instances=[inst[1]]),
+        dict(cube, material_name="m_mixed", instances=[inst[2]]),
+        {"primitive_type": "sphere", "radius": 1.0, "material_name": "m_grad", "instances": [{"world_pos": [33.0, -1.0, 3.0]}]},
+        {"primitive_type": "sphere", "radius": 0.9, "material_name": "m_metal", "instances": [{"world_pos": [33.5, -1.2, -4.0]}]},
+        {"primitive_type": "sphere", "radius": 1.1, "material_name": "m_mirror", "instances": [{"world_pos": [37.5, -0.8, -3.0]}]},
+    ]
+    cfg["lights"] = [
+        {"light_type": "distant", "l": {"values": [2.5, 2.4, 2.2]}, "from": [-0.4, 1.0, -0.6], "to": [0, 0, 0]},
+        {"light_type": "point", "spectrum": {"values": [900, 900, 900]}}]
+    path = os.path.join(directory, "scene_textured.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_c2(directory, n_instances=10000, xres=1920, yres=1080, nsamp=2, extent=50.0, seed=SEED_C2_INSTANCES):
     """Config 2: the cube instanced `n_instances` times (random position / axis / angle, unit scale),
     Matte, one point light (which sits at the origin whatever its world_pos, Q17), DirectLighting
@@ -374,10 +457,25 @@ def default_render_desc(xres, yres, nsamp, cam_pos, cam_look, cam_up=(0.0, 1.0, 
     return d
 
 
-def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=257, seed=SEED_C5_SOUP, max_depth=5):
+def c5_texture_rows():
+    """The optional textures of scene_c5_api(textured=True) as plain tuples (kind, values, mapping, map8, t1, t2,
+    world_to_texture) — shared with the oracle-side twin in tests/scenes.py: a 3D checkerboard of 1/8-unit cells for
+    the Matte kd and a planar-mapped float ramp for the Plastic roughness."""
+    w2t = np.diag([8.0, 8.0, 8.0, 1.0])
+    return [
+        (0, [(0.75, 0.7, 0.6)], 0, (1, 1, 0, 0, 0, 0, 0, 0), -1, -1, np.eye(4)),
+        (0, [(0.15, 0.2, 0.5)], 0, (1, 1, 0, 0, 0, 0, 0, 0), -1, -1, np.eye(4)),
+        (5, [], 0, (1, 1, 0, 0, 0, 0, 0, 0), 0, 1, w2t),
+        (1, [0.05, 0.4, 0.1, 0.6], 1, (1, 0, 0, 0, 1, 0, 0.0, 0.0), -1, -1, np.eye(4)),
+    ]
+
+
+def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=257, seed=SEED_C5_SOUP, max_depth=5,
+                 textured=False):
     """Config 5: a `n_tris` random-soup mesh (half Matte, half Plastic), one point light at the origin
     (Q17) and one distant light, camera outside the unit cube looking at its centre.  Returns
-    (aggregate, Render)."""
+    (aggregate, Render).  `textured` drives the Matte kd and the Plastic roughness by c5_texture_rows()
+    (rrt_scene_set_textures / rrt_scene_set_material_textures)."""
     from .aggregate import GpuAggregate
     from .render import Render, distant_light, matte, plastic, point_light
     p, idx = soup_triangles(n_tris, edge, seed)
@@ -390,7 +488,14 @@ def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=25
     agg.commit(4)
     desc = default_render_desc(xres, yres, nsamp, cam_pos=(0.5, 0.5, -2.5), cam_look=(0.5, 0.5, 0.5), focus_distance=3.0,
                                max_depth=max_depth, seed=1)
+    textures = slots = None
+    if textured:
+        from . import render as R
+        textures = [R.texture(k, v, mapping=mp, map8=m8, t1=t1, t2=t2, world_to_texture=w) for (k, v, mp, m8, t1, t2, w) in c5_texture_rows()]
+        slots = np.full((2, R.MATERIAL_SLOTS), -1, dtype=np.int32)
+        slots[0, R.SLOT_KD] = 2
+        slots[1, R.SLOT_ROUGHNESS] = 3
     r = Render.create(agg, [matte((0.6, 0.55, 0.5)), plastic((0.3, 0.4, 0.6), (0.3, 0.3, 0.3), 0.15)],
                       [point_light((4.0, 4.0, 4.0)), distant_light((2.0, 2.0, 2.0), frm=(0.3, 1.0, -0.6), to=(0, 0, 0))],
-                      desc, DGAUSS_LENS)
+                      desc, DGAUSS_LENS, textures=textures, material_slots=slots)
     return agg, r

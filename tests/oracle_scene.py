@@ -89,7 +89,7 @@ def _spectrum(cfg, key, default):
 
 
 TEX_ROW = 48
-TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D = range(6)
+TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV = range(7)
 
 
 class Textures:
@@ -144,6 +144,10 @@ class Textures:
             r[20:23] = _xyz(mp, "v1", (1, 0, 0))
             r[23:26] = _xyz(mp, "v2", (0, 1, 0))
             r[26], r[27] = float(mp.get("udelta", 0.0)), float(mp.get("vdelta", 0.0))
+        elif kind in ("spherical", "cylindrical"):   # Transform::inverse(to_world) of the TEXTURE's block (:594-599)
+            r[2] = 2 if kind == "spherical" else 3
+            _, inv = to_world(t)
+            r[28:44] = inv.reshape(16)
         else:
             raise ValueError(f"texture mapping {kind!r} is outside the restated subset")
 
@@ -160,6 +164,9 @@ class Textures:
             r, i = self._row(TEX_BILERP, is_rgb)
             for k, v in enumerate((v00, v01, v10, v11)):
                 r[8 + 3 * k: 11 + 3 * k] = v if is_rgb else [v, 0.0, 0.0]
+            self._mapping(r, t)
+        elif ty == "UVTexture" and is_rgb:
+            r, i = self._row(TEX_UV, True)
             self._mapping(r, t)
         elif ty == "ScaleTexture":
             c1 = self._child(names, t.get("t1", "ErrorTextureName"), one, is_rgb)

@@ -91,7 +91,8 @@ def compare_closest(hits, ref_prim, ref_t, rel_tie=1e-6, rel_t=1e-5):
     }
 
 
-def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthreads=None, crop=None, want_dump=False):
+def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthreads=None, crop=None, want_dump=False,
+              textured=False):
     """The oracle-side twin of synth.scene_c5_api: same soup, materials, lights and camera, fed
     through the oracle's C API (no scene.json for million-triangle meshes)."""
     import ctypes as C
@@ -126,6 +127,18 @@ def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthre
     L = O.lib()
     L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    if textured:
+        rows = np.zeros((4, S.TEX_ROW))
+        for r, (kind, vals, mp, m8, t1, t2, w2t) in zip(rows, synth.c5_texture_rows()):
+            r[0], r[2], r[4], r[5], r[6] = kind, mp, t1, t2, -1
+            for k, v in enumerate(vals):
+                r[8 + 3 * k: 11 + 3 * k] = [v, 0.0, 0.0] if np.isscalar(v) else v
+            r[20:28] = m8
+            r[28:44] = np.asarray(w2t, dtype=np.float64).reshape(16)
+        mats[0, 26 + S.T_KD] = 2
+        mats[1, 26 + S.T_ROUGH] = 3
+        L.orc_set_textures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_set_textures(s.h, 4, rows.ctypes.data)
     L.orc_set_materials(s.h, 2, mats.ctypes.data)
     L.orc_set_lights(s.h, 2, lights.ctypes.data)
     prm = np.zeros(40)

@@ -1,0 +1,149 @@
+"""SURVEY.md §8f row 3, procedural textures (texture/{bilerp,mix,scale,checkerboard,uv}.rs + mappings of
+texture/mod.rs:206-347, make_textures renderprocess.rs:298-515).  CPU part: the oracle's evaluator against
+hand-computed answers, the product's evaluator (csrc/texture_core.h run on the host through
+rrt_texture_host_probe — the code the shade kernel runs) against the oracle bit for bit, and the two scene.json
+loaders against each other.  The GPU render comparison is tests/test_gpu_render.py::test_textured_scene."""
+import ctypes as C
+import json
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import oracle_scene as S
+from rs_ray_toy_b200 import render as R
+from rs_ray_toy_b200 import capi, synth
+
+
+def oracle_probe(table, uv, p):
+    L = O.lib()
+    L.orc_texture_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_texture_probe.restype = None
+    table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, S.TEX_ROW)
+    uv = np.ascontiguousarray(uv, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.zeros((table.shape[0], 3))
+    L.orc_texture_probe(table.shape[0], table.ctypes.data, uv.ctypes.data, p.ctypes.data, out.ctypes.data)
+    return out
+
+
+def product_rows(table):
+    """Oracle table rows (tests/oracle_scene.py layout) -> rrt_texture rows."""
+    rows = []
+    for r in np.asarray(table).reshape(-1, S.TEX_ROW):
+        rows.append(R.texture(int(r[0]), [r[8 + 3 * k: 11 + 3 * k] for k in range(4)], mapping=int(r[2]), map8=r[20:28],
+                              t1=int(r[4]), t2=int(r[5]), amount=int(r[6]), world_to_texture=r[28:44].reshape(4, 4)))
+    return rows
+
+
+def _tex(cfg_float=(), cfg_rgb=()):
+    return S.Textures({"float_texture": list(cfg_float), "rgb_texture": list(cfg_rgb)})
+
+
+def test_known_answers():
+    v = lambda r, g, b: {"values": [r, g, b]}
+    t = _tex(
+        cfg_float=[{"texture_name": "ramp", "texture_type": "BilerpTexture", "v00": 0.0},      # corners 0 1 0 1 (v10, v11 read "v01")
+                   {"texture_name": "amt", "texture_type": "BilerpTexture", "v00": 0.25, "v01": 0.25}],
+        cfg_rgb=[{"texture_name": "a", "texture_type": "BilerpTexture", "v00": v(1, 2, 3), "v01": v(1, 2, 3)},
+                 {"texture_name": "b", "texture_type": "BilerpTexture", "v00": v(5, 6, 7), "v01": v(5, 6, 7)},
+                 {"texture_name": "chk", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "a", "t2": "b",
+                  "mapping": {"mapping": "uv", "su": 4.0, "sv": 4.0, "du": 0.0, "dv": 0.0}},
+                 {"texture_name": "chk3", "texture_type": "CheckerBoardTexture", "dimension": 3, "t1": "a", "t2": "b"},
+                 {"texture_name": "amt", "texture_type": "MixTexture", "t1": "a", "t2": "amt"},   # t2 unknown as rgb -> 1; amount = float "amt"
+                 {"texture_name": "sc", "texture_type": "ScaleTexture", "t1": "a", "t2": "b"},
+                 {"texture_name": "uv", "texture_type": "UVTexture", "mapping": {"mapping": "uv", "su": 2.0, "sv": 3.0}},
+                 {"texture_name": "pl", "texture_type": "UVTexture",
+                  "mapping": {"mapping": "planar", "v1": [1, 0, 0], "v2": [0, 0, 2], "udelta": 0.5, "vdelta": 0.25}}])
+    uv, p = (0.3, 0.6), (1.25, -2.5, 3.125)
+    vals = oracle_probe(t.table(), uv, p)
+    f, g = t.f, t.rgb
+    # bilerp.rs:31-44 with corners (0, 1, 0, 1): (1-s)(1-t)*0 + (1-s)t + s(1-t)*0 + s t = t
+    assert vals[f["ramp"]][0] == pytest.approx(0.6, abs=1e-15)
+    # checkerboard.rs:57-64: floor(1.2) + floor(2.4) = 3, odd -> tex2
+    assert vals[g["chk"]].tolist() == [5, 6, 7]
+    # checkerboard.rs:121-131: floor(1.25) + floor(-2.5) + floor(3.125) = 1 - 3 + 3 = 1, odd -> tex2
+    assert vals[g["chk3"]].tolist() == [5, 6, 7]
+    # mix.rs:33-38: a * 0.75 + 1 * 0.25
+    assert vals[g["amt"]].tolist() == [1 * 0.75 + 0.25, 2 * 0.75 + 0.25, 3 * 0.75 + 0.25]
+    assert vals[g["sc"]].tolist() == [5, 12, 21]
+    # uv.rs:20-27 with su 2, sv 3 and du = dv = 1 (the defaults once a mapping block exists, renderprocess.rs:582-583)
+    assert vals[g["uv"]].tolist() == [2 * 0.3 + 1 - 1, 3 * 0.6 + 1 - 2, 0.0]
+    # planar (texture/mod.rs:338-347): s = 0.5 + p.x, t = 0.25 + 2 p.z = 6.5
+    assert vals[g["pl"]].tolist() == [0.75, 0.5, 0.0]
+    # negative coordinates: floor(-0.2) = -1 -> (-1 + 0) % 2 = -1 != 0 in Rust and C alike -> tex2
+    vals = oracle_probe(t.table(), (-0.05, 0.1), p)
+    assert vals[g["chk"]].tolist() == [5, 6, 7]
+
+
+def test_spherical_and_cylindrical_mappings():
+    t = _tex(cfg_rgb=[{"texture_name": "s", "texture_type": "UVTexture", "mapping": {"mapping": "spherical"}, "world_pos": [1.0, 2.0, 3.0]},
+                      {"texture_name": "c", "texture_type": "UVTexture", "mapping": {"mapping": "cylindrical"}, "world_pos": [1.0, 2.0, 3.0],
+                       "scale": [2.0, 2.0, 2.0]}])
+    p = np.array([1.0, 2.0, 3.0]) + np.array([0.0, 1.0, 1.0])
+    vals = oracle_probe(t.table(), (0, 0), p)
+    # v = normalize(0, 1, 1): theta = acos(1/sqrt 2) = pi/4 -> s = 1/4; phi = atan2(1, 0) = pi/2 -> t = 1/4
+    assert vals[t.rgb["s"]][:2] == pytest.approx([0.25, 0.25], abs=1e-15)
+    # cylinder: s = (pi + atan2(v.y, v.x)) / 2 pi = 3/4, t = v.z = 1/sqrt 2 (the scale drops out in the normalisation)
+    assert vals[t.rgb["c"]][:2] == pytest.approx([0.75, 1 / math.sqrt(2)], abs=1e-15)
+
+
+def test_host_evaluator_is_the_oracles_bit_for_bit(tmp_path):
+    sc = S.load(synth.scene_textured(str(tmp_path)))
+    table = sc.textures
+    rows = product_rows(table)
+    rng = np.random.default_rng(11)
+    kinds = set(int(k) for k in table[:, 0])
+    assert kinds == set(range(7)), kinds          # the scene covers every in-scope texture kind
+    assert set(int(k) for k in table[:, 2]) == {0, 1, 2, 3}
+    for _ in range(400):
+        uv = rng.uniform(-2.0, 9.0, 2)
+        p = rng.uniform(-8.0, 40.0, 3)
+        a, b = oracle_probe(table, uv, p), R.texture_host_probe(rows, uv, p)
+        assert np.array_equal(a, b), (uv, p, a, b)
+
+
+def test_loaders_agree(tmp_path):
+    path = synth.scene_textured(str(tmp_path))
+    sc = S.load(path)
+    tex, mats, slots = R.json_texture_probe(path)
+    assert len(tex) == sc.textures.shape[0] and len(mats) == sc.materials.shape[0]
+    for row, t in zip(sc.textures, tex):
+        assert (int(row[0]), int(row[2]), int(row[4]), int(row[5]), int(row[6])) == (t.kind, t.mapping, t.t1, t.t2, t.amount)
+        assert np.array_equal(row[8:20], np.array([list(t.v[k]) for k in range(4)]).reshape(12))
+        assert np.array_equal(row[20:28], np.array(list(t.map)))
+        if t.kind == R.TEX_CHECKER3D or t.mapping >= R.TEXMAP_SPHERICAL:
+            assert np.array_equal(row[28:44], np.array(list(t.world_to_texture)))
+    assert np.array_equal(sc.materials[:, 26:37].astype(np.int32), slots)
+    for row, m in zip(sc.materials, mats):
+        assert int(row[0]) == m.kind
+        assert np.array_equal(row[1:4], list(m.kd)) and np.array_equal(row[4:7], list(m.ks))
+        assert row[19] == m.sigma and row[20] == m.roughness
+
+
+def test_out_of_scope_textures_are_refused(tmp_path):
+    path = synth.scene_textured(str(tmp_path))
+    cfg = json.loads(open(path).read())
+    closed = dict(cfg)
+    closed["rgb_texture"] = [dict(t) for t in cfg["rgb_texture"]]
+    del closed["rgb_texture"][3]["aamode"]          # the default is the closed-form filter (renderprocess.rs:357)
+    p2 = tmp_path / "closed.json"
+    p2.write_text(json.dumps(closed))
+    with pytest.raises(ValueError):
+        S.load(str(p2))
+    with pytest.raises(capi.RrtError):
+        R.json_texture_probe(str(p2))
+    # a child that is not defined earlier is not a table the evaluator accepts
+    bad = [R.texture(R.TEX_SCALE, t1=0, t2=1), R.texture(R.TEX_CONSTANT, [1.0])]
+    with pytest.raises(capi.RrtError):
+        R.texture_host_probe(bad, (0, 0), (0, 0, 0))
+    # a float parameter naming a texture that does not exist panics in the reference (renderprocess.rs:621)
+    missing = dict(cfg)
+    missing["materials"] = [dict(cfg["materials"][1], sigma="no_such_texture")]
+    p3 = tmp_path / "missing.json"
+    p3.write_text(json.dumps(missing))
+    with pytest.raises(ValueError):
+        S.load(str(p3))
+    with pytest.raises(capi.RrtError):
+        R.json_texture_probe(str(p3))
