@@ -172,9 +172,11 @@ typedef struct rrt_material {
  * textures flattened into ONE table in definition order (float textures first).  A texture can only name textures
  * defined before it (the loader looks names up in the maps it is filling; an unknown name becomes a constant,
  * get_text_fallback :282-296), so children always have smaller indices.  Float textures use v[.][0].
- * texture/{bilerp,mix,scale,checkerboard,uv}.rs; mappings texture/mod.rs:206-347.  Point-sampled only: the
- * closed-form checkerboard filter is evaluated with zero texture-space differentials (what every non-camera ray
- * sees in the reference: interaction.rs:223-284 leaves du/dv at 0 without ray differentials).             */
+ * texture/{bilerp,mix,scale,checkerboard,uv}.rs; mappings texture/mod.rs:206-347 with their screen-space
+ * differentials: the renderer carries the camera ray's differentials (RealisticCamera::generate_ray_differential,
+ * camera.rs:582-628, scaled by 1/sqrt(spp), integrator/mod.rs:92-94) to the first hit and runs
+ * SurfaceInteraction::compute_differentials (interaction.rs:223-284) there when a texture asks for them (a
+ * closed-form checkerboard); every later hit has none, like the reference's spawned rays.               */
 typedef enum rrt_texture_kind {
     RRT_TEX_CONSTANT = 0, RRT_TEX_BILERP = 1, RRT_TEX_SCALE = 2, RRT_TEX_MIX = 3, RRT_TEX_CHECKER2D = 4,
     RRT_TEX_CHECKER3D = 5, RRT_TEX_UV = 6
@@ -186,7 +188,7 @@ typedef enum rrt_texture_mapping {
 typedef struct rrt_texture {
     uint32_t kind, mapping;
     int32_t t1, t2, amount;       /* child texture indices (< own index); amount: a float texture (Mix)        */
-    uint32_t pad;
+    uint32_t aa;                  /* Checkerboard 2D: 0 = AAMethod::AANone, 1 = ClosedForm (the loader's default) */
     double v[4][3];               /* Constant: v[0]; Bilerp: v00 v01 v10 v11                                   */
     double map[8];                /* uv: su sv du dv; planar: vs[3] vt[3] ds dt                                */
     double world_to_texture[16];  /* Checkerboard 3D (IdentityMapping3D), spherical / cylindrical: row-major   */
@@ -251,8 +253,13 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
 int rrt_scene_set_textures(rrt_scene* scene, uint32_t n, const rrt_texture* textures);
 int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, const int32_t* slots);
 /* Host-only evaluation of a texture table at (uv, p) with the product's own evaluator (csrc/texture_core.h, the
- * code the shade kernel runs): out[3 * i + c] for every texture i.  For the CPU test-suite.                  */
-int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3], double* out);
+ * code the shade kernel runs): out[3 * i + c] for every texture i.  `diff` (may be NULL = none) holds the
+ * screen-space differentials dpdx[3] dpdy[3] dudx dvdx dudy dvdy.  For the CPU test-suite.                    */
+int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3],
+                           const double* diff, double* out);
+/* Host-only SurfaceInteraction::compute_differentials with the product's code (csrc/texture_core.h): in = p[3] n[3]
+ * dpdu[3] dpdv[3] rx_origin[3] rx_direction[3] ry_origin[3] ry_direction[3]; out = dpdx[3] dpdy[3] dudx dvdx dudy dvdy. */
+int rrt_differentials_host_probe(const double in24[24], double out10[10]);
 /* deploy_render's loader: parses scene.json (+ the .obj files it names, relative to it) into a
  * committed scene and the integrator that renders it.  `overrides_json` (may be NULL) replaces
  * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */

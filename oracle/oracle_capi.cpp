@@ -447,6 +447,7 @@ void orc_set_textures(void* sp, uint32_t n, const double* t) {
         Texture x;
         x.kind = (uint32_t)a[0];
         x.mapping = (uint32_t)a[2];
+        x.aa = (uint32_t)a[3];
         x.t1 = (int32_t)a[4];
         x.t2 = (int32_t)a[5];
         x.amount = (int32_t)a[6];
@@ -457,13 +458,25 @@ void orc_set_textures(void* sp, uint32_t n, const double* t) {
         rs.textures.push_back(x);
     }
 }
-// Texture probe: evaluates the table at (uv, p) and returns every texture's value (3 doubles each).
-void orc_texture_probe(uint32_t n, const double* table, const double* uv2, const double* p3, double* out) {
+// Texture probe: evaluates the table at (uv, p) and returns every texture's value (3 doubles each).  `diff` (may be
+// null) = dpdx[3] dpdy[3] dudx dvdx dudy dvdy as compute_differentials would leave them.
+void orc_texture_probe(uint32_t n, const double* table, const double* uv2, const double* p3, const double* diff, double* out) {
     void* tmp = orc_scene_new(0);
     orc_set_textures(tmp, n, table);
     RenderSetup& rs = setup_of(tmp);
     Rgb vals[kMaxTextures];
-    tex_eval_all(rs.textures, P2(uv2[0], uv2[1]), V3(p3[0], p3[1], p3[2]), vals);
+    TexPoint q;
+    q.uv = P2(uv2[0], uv2[1]);
+    q.p = V3(p3[0], p3[1], p3[2]);
+    if (diff) {
+        q.dpdx = V3(diff[0], diff[1], diff[2]);
+        q.dpdy = V3(diff[3], diff[4], diff[5]);
+        q.dudx = diff[6];
+        q.dvdx = diff[7];
+        q.dudy = diff[8];
+        q.dvdy = diff[9];
+    }
+    tex_eval_all(rs.textures, q, vals);
     for (uint32_t i = 0; i < n && i < (uint32_t)kMaxTextures; ++i)
         for (int c = 0; c < 3; ++c) out[3 * i + c] = vals[i].c[c];
     for (size_t i = 0; i < g_setups.size(); ++i)
@@ -472,6 +485,24 @@ void orc_texture_probe(uint32_t n, const double* table, const double* uv2, const
             break;
         }
     orc_scene_free(tmp);
+}
+// compute_differentials probe: in = p n dpdu dpdv rx_o rx_d ry_o ry_d (3 doubles each); out = dpdx dpdy dudx dvdx dudy dvdy
+void orc_differentials_probe(const double* in24, double* out10) {
+    auto v = [&](int k) { return V3(in24[3 * k], in24[3 * k + 1], in24[3 * k + 2]); };
+    SI si;
+    si.p = v(0);
+    si.n = v(1);
+    si.dpdu = v(2);
+    si.dpdv = v(3);
+    RayDiff rd;
+    rd.has_differentials = true;
+    rd.rx_o = v(4);
+    rd.rx_d = v(5);
+    rd.ry_o = v(6);
+    rd.ry_d = v(7);
+    TexPoint q = compute_differentials(si, &rd);
+    const double o[10] = {q.dpdx.x, q.dpdx.y, q.dpdx.z, q.dpdy.x, q.dpdy.y, q.dpdy.z, q.dudx, q.dvdx, q.dudy, q.dvdy};
+    for (int k = 0; k < 10; ++k) out10[k] = o[k];
 }
 // Light table, 80 doubles per light (tests/oracle_scene.py light_row).
 void orc_set_lights(void* sp, uint32_t n, const double* l) {

@@ -438,38 +438,112 @@ struct Bsdf {
 
 // ---- materials (material/*.rs) with constant-valued parameters -------------------------------------
 enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4, MAT_NONE = 5 };
-// ---- textures (texture/{bilerp,mix,scale,checkerboard}.rs, texture/mod.rs mappings) ------------------------------
+// ---- textures (texture/{bilerp,mix,scale,checkerboard,uv}.rs, texture/mod.rs mappings) --------------------------
 // A material parameter is a texture.  The loader flattens the float and rgb textures of a scene file into one
 // table in definition order (a texture can only name textures defined before it: make_textures looks names up
 // in the maps it is filling, renderprocess.rs:298-515; an unknown name falls back to a constant, :282-296), so
 // evaluating the table front to back evaluates every child before its parent.  Float textures use component 0.
-// In scope: Constant, Bilerp, Scale, Mix, UV, Checkerboard 2D (aamode none) and 3D; UV, planar, spherical and
-// cylindrical 2D mappings, IdentityMapping3D.  Closed-form checkerboard filtering needs ray differentials and is
-// refused by the loaders.
+// In scope: Constant, Bilerp, Scale, Mix, UV, Checkerboard 2D (point-sampled and closed-form box filter) and 3D;
+// UV, planar, spherical and cylindrical 2D mappings with their screen-space differentials, IdentityMapping3D.
 enum TexKind : uint32_t { TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5, TEX_UV = 6 };
 enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1, MAP_SPHERICAL = 2, MAP_CYLINDRICAL = 3 };
 struct Texture {
     uint32_t kind = TEX_CONST, mapping = MAP_UV;
+    uint32_t aa = 0;  // checkerboard 2D: 0 = AAMethod::AANone, 1 = ClosedForm
     int32_t t1 = -1, t2 = -1, amount = -1;
     Rgb v[4];
     double map[8] = {1, 1, 0, 0, 0, 0, 0, 0};  // uv: su sv du dv; planar: vs[3] vt[3] ds dt
     Xform w2t;                                  // checkerboard 3D: IdentityMapping3D's transform; spherical / cylindrical
 };
 constexpr int kMaxTextures = 32;
-// TextureMapping2D::map without the differentials (texture/mod.rs:235-243 uv, :254-260 spherical, :295-298
-// cylindrical, :338-347 planar)
-inline P2 tex_map2d(const Texture& t, P2 uv, V3 p) {
-    if (t.mapping == MAP_UV) return P2(t.map[0] * uv.x + t.map[2], t.map[1] * uv.y + t.map[3]);
+
+// What Texture::evaluate reads of a SurfaceInteraction: uv, p and the screen-space differentials that
+// SurfaceInteraction::compute_differentials (interaction.rs:223-284) leaves behind.
+struct TexPoint {
+    P2 uv;
+    V3 p;
+    V3 dpdx, dpdy;
+    double dudx = 0.0, dvdx = 0.0, dudy = 0.0, dvdy = 0.0;
+};
+// transform.rs:153-164
+inline bool solve_linear_system_2x2(const double a[2][2], const double b[2], double* x0, double* x1) {
+    double det = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+    if (std::fabs(det) < 1e-10) return false;
+    *x0 = (a[1][1] * b[0] - a[0][1] * b[1]) / det;
+    *x1 = (a[0][0] * b[1] - a[1][0] * b[0]) / det;
+    if (*x0 != *x0 || *x1 != *x1) return false;
+    return true;
+}
+// interaction.rs:223-284.  Q29: the y plane intersection uses dot(n, ry_direction) where dot(n, ry_origin) was
+// meant (:237-238) — kept literally: deterministic and order-independent.
+inline TexPoint compute_differentials(const SI& si, const RayDiff* ray) {
+    TexPoint tp;
+    tp.uv = si.uv;
+    tp.p = si.p;
+    if (!ray || !ray->has_differentials) return tp;
+    const V3 n = si.n;
+    double d = dot(n, si.p);
+    double tx = -(dot(n, ray->rx_o) - d) / dot(n, ray->rx_d);
+    if (std::isinf(tx) || tx != tx) return tp;
+    V3 px = ray->rx_o + ray->rx_d * tx;
+    double ty = -(dot(n, ray->ry_d) - d) / dot(n, ray->ry_d);
+    if (std::isinf(ty) || ty != ty) return tp;
+    V3 py = ray->ry_o + ray->ry_d * ty;
+    tp.dpdx = px - si.p;
+    tp.dpdy = py - si.p;
+    int dim[2];
+    if (std::fabs(n.x) > std::fabs(n.y) && std::fabs(n.x) > std::fabs(n.z)) {
+        dim[0] = 1;
+        dim[1] = 2;
+    } else if (std::fabs(n.y) > std::fabs(n.z)) {
+        dim[0] = 0;
+        dim[1] = 2;
+    } else {
+        dim[0] = 0;
+        dim[1] = 1;
+    }
+    const double a[2][2] = {{si.dpdu[dim[0]], si.dpdv[dim[0]]}, {si.dpdu[dim[1]], si.dpdv[dim[1]]}};
+    const double bx[2] = {px[dim[0]] - si.p[dim[0]], px[dim[1]] - si.p[dim[1]]};
+    const double by[2] = {py[dim[0]] - si.p[dim[0]], py[dim[1]] - si.p[dim[1]]};
+    if (!solve_linear_system_2x2(a, bx, &tp.dudx, &tp.dvdx)) tp.dudx = tp.dvdx = 0.0;
+    if (!solve_linear_system_2x2(a, by, &tp.dudy, &tp.dvdy)) tp.dudy = tp.dvdy = 0.0;
+    return tp;
+}
+
+// SphericalMapping2D::sphere / CylindricalMapping2D::cylinder (texture/mod.rs:254-260, :295-298)
+inline P2 tex_sphere_or_cylinder(const Texture& t, V3 p) {
+    V3 v = normalize_vec(xf_point(t.w2t, p) - V3());
+    if (t.mapping == MAP_CYLINDRICAL) return P2((PI + std::atan2(v.y, v.x)) / (2.0 * PI), v.z);
+    double theta = std::acos(clamp_t(v.z, -1.0, 1.0));  // geometry.rs:1189-1201
+    double phi = std::atan2(v.y, v.x);
+    if (phi < 0.0) phi = phi + 2.0 * PI;
+    return P2(theta / PI, phi / (PI * 2.0));
+}
+// TextureMapping2D::map (texture/mod.rs:235-243 uv, :262-289 spherical, :301-325 cylindrical, :338-347 planar):
+// (s, t) and its screen-space differentials
+inline P2 tex_map2d(const Texture& t, const TexPoint& q, P2* dstdx, P2* dstdy) {
+    if (t.mapping == MAP_UV) {
+        *dstdx = P2(t.map[0] * q.dudx, t.map[1] * q.dvdx);
+        *dstdy = P2(t.map[0] * q.dudy, t.map[1] * q.dvdy);
+        return P2(t.map[0] * q.uv.x + t.map[2], t.map[1] * q.uv.y + t.map[3]);
+    }
     if (t.mapping == MAP_SPHERICAL || t.mapping == MAP_CYLINDRICAL) {
-        V3 v = normalize_vec(xf_point(t.w2t, p) - V3());
-        if (t.mapping == MAP_CYLINDRICAL) return P2((PI + std::atan2(v.y, v.x)) / (2.0 * PI), v.z);
-        double theta = std::acos(clamp_t(v.z, -1.0, 1.0));  // geometry.rs:1189-1201
-        double phi = std::atan2(v.y, v.x);
-        if (phi < 0.0) phi = phi + 2.0 * PI;
-        return P2(theta / PI, phi / (PI * 2.0));
+        P2 st = tex_sphere_or_cylinder(t, q.p);
+        const double delta = 0.1;
+        P2 sx = tex_sphere_or_cylinder(t, q.p + q.dpdx * delta);
+        *dstdx = P2((sx.x - st.x) / delta, (sx.y - st.y) / delta);
+        P2 sy = tex_sphere_or_cylinder(t, q.p + q.dpdy * delta);
+        *dstdy = P2((sy.x - st.x) / delta, (sy.y - st.y) / delta);
+        if (dstdx->y > 0.5) dstdx->y = 1.0 - dstdx->y;
+        else if (dstdx->y < -0.5) dstdx->y = -(dstdx->y + 1.0);
+        if (dstdy->y > 0.5) dstdy->y = 1.0 - dstdy->y;
+        else if (dstdy->y < -0.5) dstdy->y = -(dstdy->y + 1.0);
+        return st;
     }
     V3 vs(t.map[0], t.map[1], t.map[2]), vt(t.map[3], t.map[4], t.map[5]);
-    return P2(t.map[6] + dot(p, vs), t.map[7] + dot(p, vt));
+    *dstdx = P2(dot(q.dpdx, vs), dot(q.dpdx, vt));
+    *dstdy = P2(dot(q.dpdy, vs), dot(q.dpdy, vt));
+    return P2(t.map[6] + dot(q.p, vs), t.map[7] + dot(q.p, vt));
 }
 inline int32_t rust_f64_as_i32(double v) {  // `as i32`: saturating, NaN -> 0
     if (!(v == v)) return 0;
@@ -477,13 +551,18 @@ inline int32_t rust_f64_as_i32(double v) {  // `as i32`: saturating, NaN -> 0
     if (v <= -2147483648.0) return (int32_t)-2147483647 - 1;
     return (int32_t)v;
 }
-inline void tex_eval_all(const std::vector<Texture>& table, P2 uv, V3 p, Rgb* vals) {
+// checkerboard.rs:45-47
+inline double bump_int(double x) {
+    return std::floor(x / 2.0) + 2.0 * std::fmax(x / 2.0 - std::floor(x / 2.0) - 0.5, 0.0);
+}
+inline void tex_eval_all(const std::vector<Texture>& table, const TexPoint& q, Rgb* vals) {
     for (size_t i = 0; i < table.size(); ++i) {
         const Texture& t = table[i];
+        P2 dstdx, dstdy;
         switch (t.kind) {
             case TEX_CONST: vals[i] = t.v[0]; break;
             case TEX_BILERP: {  // bilerp.rs:31-44
-                P2 st = tex_map2d(t, uv, p);
+                P2 st = tex_map2d(t, q, &dstdx, &dstdy);
                 vals[i] = t.v[0] * (1.0 - st.x) * (1.0 - st.y) + t.v[1] * (1.0 - st.x) * st.y + t.v[2] * st.x * (1.0 - st.y) +
                           t.v[3] * st.x * st.y;
                 break;
@@ -494,20 +573,37 @@ inline void tex_eval_all(const std::vector<Texture>& table, P2 uv, V3 p, Rgb* va
                 vals[i] = vals[t.t1] * (1.0 - amt) + vals[t.t2] * amt;
                 break;
             }
-            case TEX_CHECKER2D: {  // checkerboard.rs:57-64 (AANone)
-                P2 st = tex_map2d(t, uv, p);
+            case TEX_CHECKER2D: {  // checkerboard.rs:53-100
+                P2 st = tex_map2d(t, q, &dstdx, &dstdy);
                 int32_t sum = (int32_t)((uint32_t)rust_f64_as_i32(std::floor(st.x)) + (uint32_t)rust_f64_as_i32(std::floor(st.y)));
-                vals[i] = (sum % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                Rgb point = (sum % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                if (t.aa == 0) {
+                    vals[i] = point;
+                    break;
+                }
+                // Vector2::abs().max_comp() (geometry.rs:762-775)
+                double ax = std::fabs(dstdx.x), ay = std::fabs(dstdx.y), bx = std::fabs(dstdy.x), by = std::fabs(dstdy.y);
+                double ds = ax > ay ? ax : ay, dt = bx > by ? bx : by;
+                double s0 = st.x - ds, s1 = st.x + ds, t0 = st.y - dt, t1 = st.y + dt;
+                if (std::floor(s0) == std::floor(s1) && std::floor(t0) == std::floor(t1)) {
+                    vals[i] = point;
+                    break;
+                }
+                double sint = (bump_int(s1) - bump_int(s0)) / (2.0 * ds);
+                double tint = (bump_int(t1) - bump_int(t0)) / (2.0 * dt);
+                double area2 = sint + tint - 2.0 * sint * tint;
+                if (ds > 1.0 || dt > 1.0) area2 = 0.5;
+                vals[i] = vals[t.t1] * (1.0 - area2) + vals[t.t2] * area2;
                 break;
             }
             case TEX_UV: {  // uv.rs:20-27 (Spectrum<3>::from_rgb copies, spectrum.rs:2740-2742)
-                P2 st = tex_map2d(t, uv, p);
+                P2 st = tex_map2d(t, q, &dstdx, &dstdy);
                 vals[i] = Rgb(st.x - std::floor(st.x), st.y - std::floor(st.y), 0.0);
                 break;
             }
             default: {  // checkerboard.rs:121-131
-                V3 q = xf_point(t.w2t, p);
-                int32_t k = rust_f64_as_i32(std::floor(q.x) + std::floor(q.y) + std::floor(q.z));
+                V3 w = xf_point(t.w2t, q.p);
+                int32_t k = rust_f64_as_i32(std::floor(w.x) + std::floor(w.y) + std::floor(w.z));
                 vals[i] = (k % 2 == 0) ? vals[t.t1] : vals[t.t2];
                 break;
             }
@@ -534,10 +630,10 @@ struct Material {
 };
 // The material with every textured parameter evaluated at the hit (Texture::evaluate(si) in each
 // compute_scattering_functions, material/*.rs).
-inline Material material_at(const Material& m, const std::vector<Texture>& table, const SI& si) {
+inline Material material_at(const Material& m, const std::vector<Texture>& table, const SI& si, const RayDiff* ray) {
     if (!m.textured()) return m;
     Rgb vals[kMaxTextures];
-    tex_eval_all(table, si.uv, si.p, vals);
+    tex_eval_all(table, compute_differentials(si, ray), vals);
     Material r = m;
     Rgb* rgbs[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.eta_rgb, &r.k_rgb};
     for (int k = 0; k < 6; ++k)

@@ -228,7 +228,9 @@ struct Integrator {
     Distribution1D light_distrib;  // path.rs:47-49: uniform over the lights
 
     // PathIntegrator::li (path.rs:51-226)
-    Rgb li_path(const RenderScene& sc, Ray ray, HaltonSampler& sampler, RenderStats* st, HitRecord* first_hit) const {
+    // `camera` carries the differentials of the camera ray; every later ray is spawn_ray(..).into(): none
+    Rgb li_path(const RenderScene& sc, const RayDiff& camera, HaltonSampler& sampler, RenderStats* st, HitRecord* first_hit) const {
+        Ray ray = camera.ray;
         Rgb l, beta(1.0);
         bool specular_bounce = false;
         uint64_t bounces = 0;
@@ -242,7 +244,8 @@ struct Integrator {
             (void)specular_bounce;  // isect.le() == 0 (Q22) and there are no infinite lights in scope
             if (!found || bounces >= max_depth) break;
             Bsdf bsdf;
-            material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect), isect, true, &bsdf);
+            material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, bounces == 0 ? &camera : nullptr),
+                          isect, true, &bsdf);
             if (!bsdf.present) {
                 // path.rs:101-106: `bounces -= 1` on usize — wraps in release, panics in debug (Q21)
                 if (st) st->asserts += 1;
@@ -282,7 +285,7 @@ struct Integrator {
     // DirectLightingIntegrator::li with UniformSampleOne (directlighting.rs:72-132).  The specular
     // recursion (integrator/mod.rs:150-301) is followed without ray differentials.
     Rgb li_direct(const RenderScene& sc, Ray ray, HaltonSampler& sampler, uint32_t depth, RenderStats* st,
-                  HitRecord* first_hit) const {
+                  HitRecord* first_hit, const RayDiff* camera = nullptr) const {
         Rgb l;
         SI isect;
         HitRecord rec;
@@ -291,7 +294,7 @@ struct Integrator {
         if (first_hit) *first_hit = rec;
         if (!found) return l;  // Light::le of point / distant lights is zero
         Bsdf bsdf;
-        material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect), isect, false, &bsdf);
+        material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, camera), isect, false, &bsdf);
         if (!bsdf.present) return li_direct(sc, ray_new_od(isect.p, ray.d), sampler, depth, st, nullptr);
         if (!sc.lights.empty()) l += sc.uniform_sample_one_light(isect, bsdf, sampler, nullptr, st);
         if (depth + 1 < max_depth) {
@@ -367,14 +370,16 @@ struct RenderJob {
                             cs.time = sampler.get_1d() + 0.5;
                             RayDiff rd;
                             double w = camera.generate_ray_differential(cs, &rd);
+                            // integrator/mod.rs:92-94
+                            rd.scale_differentials(1.0 / std::sqrt((double)sampler.samples_per_pixel));
                             Rgb l;
                             HitRecord first;
                             if (w > 0.0) {
                                 st.camera_rays += 1;
                                 if (integrator.kind == INTEGRATOR_PATH)
-                                    l = integrator.li_path(scene, rd.ray, sampler, &st, &first);
+                                    l = integrator.li_path(scene, rd, sampler, &st, &first);
                                 else
-                                    l = integrator.li_direct(scene, rd.ray, sampler, 1, &st, &first);
+                                    l = integrator.li_direct(scene, rd.ray, sampler, 1, &st, &first, &rd);
                             } else {
                                 st.zero_weight += 1;
                             }

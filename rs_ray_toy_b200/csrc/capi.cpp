@@ -508,12 +508,18 @@ int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, cons
     }
     return RRT_OK;
 }
-int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3], double* out) {
+int rrt_differentials_host_probe(const double in24[24], double out10[10]) {
+    if (!in24 || !out10) return fail(RRT_ERR_INVALID, "rrt_differentials_host_probe: null argument");
+    rrt::differentials_host_eval(in24, out10);
+    return RRT_OK;
+}
+int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3], const double* diff,
+                           double* out) {
     if ((n && !textures) || !uv || !p || !out) return fail(RRT_ERR_INVALID, "rrt_texture_host_probe: null argument");
     if (n > RRT_MAX_TEXTURES) return fail(RRT_ERR_UNSUPPORTED, "rrt_texture_host_probe: more than RRT_MAX_TEXTURES textures");
     std::string err;
     if (!rrt::validate_textures(textures, n, &err)) return fail(RRT_ERR_INVALID, "rrt_texture_host_probe: " + err);
-    rrt::texture_host_eval(textures, n, uv, p, out);
+    rrt::texture_host_eval(textures, n, uv, p, diff, out);
     return RRT_OK;
 }
 

@@ -136,7 +136,8 @@ enum GenStage : int { GEN_MAIN = 0, GEN_XP = 1, GEN_XM = 2, GEN_YP = 3, GEN_YM =
 
 __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     generate_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film, IntegratorParams ip,
-                    Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q) {
+                    Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q, RayDiffRec* __restrict__ diffs,
+                    double diff_scale) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     // lens table in shared memory: lanes index it at different interfaces (a constant-bank read would serialise)
@@ -243,18 +244,37 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     wt = w;
                     done = !ok;
                     stage = GEN_XP;
-                } else if (stage == GEN_XP) {
-                    stage = ok ? GEN_YP : GEN_XM;
-                } else if (stage == GEN_XM) {
-                    done = !ok;
-                    stage = GEN_YP;
-                } else if (stage == GEN_YP) {
-                    done = ok;
-                    final_w = wt;
-                    stage = GEN_YM;
                 } else {
-                    done = true;
-                    final_w = ok ? wt : 0.0;
+                    if (diffs != nullptr && ok) {
+                        // camera.rs:595-599 / :612-616: the neighbour ray by a forward (or backward) difference over
+                        // eps = +-0.05 px, then RayDifferential::scale_differentials(1 / sqrt(spp)) (integrator/mod.rs:92-94)
+                        RayD world;
+                        camera_ray_to_world(cam, flip_z(r), &world);
+                        const double eps = (stage == GEN_XP || stage == GEN_YP) ? 0.05 : -0.05;
+                        const V3 o = paths[slot].o, d = paths[slot].d;
+                        const V3 no = o + ((o + (world.o - o) / eps) - o) * diff_scale;
+                        const V3 nd = d + ((d + (world.d - d) / eps) - d) * diff_scale;
+                        if (stage == GEN_XP || stage == GEN_XM) {
+                            diffs[slot].rx_o = no;
+                            diffs[slot].rx_d = nd;
+                        } else {
+                            diffs[slot].ry_o = no;
+                            diffs[slot].ry_d = nd;
+                        }
+                    }
+                    if (stage == GEN_XP) {
+                        stage = ok ? GEN_YP : GEN_XM;
+                    } else if (stage == GEN_XM) {
+                        done = !ok;
+                        stage = GEN_YP;
+                    } else if (stage == GEN_YP) {
+                        done = ok;
+                        final_w = wt;
+                        stage = GEN_YM;
+                    } else {
+                        done = true;
+                        final_w = ok ? wt : 0.0;
+                    }
                 }
                 need_begin = !done;
                 if (done) {
@@ -376,6 +396,8 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
 #ifndef RRT_SHADE_MINBLOCKS
 #define RRT_SHADE_MINBLOCKS 3
 #endif
+// TEXTURED = some material parameter is driven by a texture: the kernel for constant-valued scenes carries none of it.
+template <bool TEXTURED>
 __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
                                                      IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
     uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,14 +435,17 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
             Surface s;
             make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
             Bsdf bsdf;
-            {
+            if (TEXTURED) {
                 const MaterialRec* m = sc.materials + s.material;
                 MaterialRec textured;
                 if (m->needed) {
-                    material_at(sc, *m, s, &textured);
+                    // the camera ray is the only one with differentials (path.rs:163, directlighting.rs:91-94)
+                    material_at(sc, *m, s, (sc.ray_diffs != nullptr && p.bounces == 0) ? sc.ray_diffs + pid : nullptr, &textured);
                     m = &textured;
                 }
                 make_bsdf(*m, s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
+            } else {
+                make_bsdf(sc.materials[s.material], s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
             }
             if (!bsdf.present) {
                 alive = false;  // path.rs:101-106 (usize underflow in the reference, Q21): the path ends here
@@ -714,6 +739,9 @@ struct Renderer::Impl {
     std::vector<void*> allocations;
     uint16_t* d_perms = nullptr;
     Path* d_paths = nullptr;
+    RayDiffRec* d_diffs = nullptr;  // camera-ray differentials per slot, when a texture filters with them
+    double diff_scale = 1.0;        // 1 / sqrt(samples_per_pixel) (integrator/mod.rs:92-94)
+    bool textured = false, want_diffs = false;
     Queues q{};
     uint32_t* d_tiles = nullptr;
     uint32_t tiles_capacity = 0;
@@ -776,6 +804,7 @@ TextureRec texture_rec_of(const rrt_texture& t) {
     r.t1 = t.t1;
     r.t2 = t.t2;
     r.amount = t.amount;
+    r.aa = t.aa;
     for (int k = 0; k < 4; ++k) r.v[k] = Rgb{t.v[k][0], t.v[k][1], t.v[k][2]};
     for (int k = 0; k < 8; ++k) r.map[k] = t.map[k];
     for (int k = 0; k < 12; ++k) r.w2t.m[k] = t.world_to_texture[k];
@@ -805,16 +834,33 @@ bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err) {
     return true;
 }
 
-void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], double* out) {
+void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], const double* diff, double* out) {
     TextureRec table[kMaxTextures];
     Rgb vals[kMaxTextures];
     for (uint32_t i = 0; i < n; ++i) table[i] = texture_rec_of(t[i]);
-    texture_eval_table(table, n, n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u), P2{uv[0], uv[1]}, v3(p[0], p[1], p[2]), vals);
+    TexPoint q = tex_point(P2{uv[0], uv[1]}, v3(p[0], p[1], p[2]));
+    if (diff) {
+        q.dpdx = v3(diff[0], diff[1], diff[2]);
+        q.dpdy = v3(diff[3], diff[4], diff[5]);
+        q.dudx = diff[6];
+        q.dvdx = diff[7];
+        q.dudy = diff[8];
+        q.dvdy = diff[9];
+    }
+    texture_eval_table(table, n, n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u), q, vals);
     for (uint32_t i = 0; i < n; ++i) {
         out[3 * i] = vals[i].r;
         out[3 * i + 1] = vals[i].g;
         out[3 * i + 2] = vals[i].b;
     }
+}
+void differentials_host_eval(const double in24[24], double out10[10]) {
+    auto v = [&](int k) { return v3(in24[3 * k], in24[3 * k + 1], in24[3 * k + 2]); };
+    TexPoint q = tex_point(P2{0.0, 0.0}, v(0));
+    const RayDiffRec rd{v(4), v(5), v(6), v(7)};
+    compute_differentials(v(1), v(2), v(3), rd, &q);
+    const double o[10] = {q.dpdx.x, q.dpdx.y, q.dpdx.z, q.dpdy.x, q.dpdy.y, q.dpdy.z, q.dudx, q.dvdx, q.dudy, q.dvdy};
+    for (int k = 0; k < 10; ++k) out10[k] = o[k];
 }
 
 int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
@@ -1124,7 +1170,13 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         int rc;
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
         if ((rc = I.up(texs, &S.textures, err)) != RRT_OK) return rc;
-        S.n_textures = (uint32_t)texs.size();
+        uint32_t reached = 0;
+        for (const MaterialRec& m : mats) reached |= m.needed;
+        I.textured = reached != 0;
+        // make_surface fills uv / dpdu / dpdv only when someone reads them
+        S.n_textures = I.textured ? (uint32_t)texs.size() : 0u;
+        for (size_t i = 0; i < texs.size(); ++i)
+            I.want_diffs |= ((reached >> i) & 1u) && texs[i].kind == TEXK_CHECKER2D && texs[i].aa != 0;
         if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
         S.n_lights = (uint32_t)lts.size();
         S.literal = agg->literal() ? 1u : 0u;
@@ -1146,6 +1198,11 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     }
     const size_t kSlots = I.chunk;
     if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
+    if (I.want_diffs) {
+        if ((rc = dev_alloc((void**)&I.d_diffs, (size_t)kSlots * sizeof(RayDiffRec))) != RRT_OK) return rc;
+        I.sc.ray_diffs = I.d_diffs;
+        I.diff_scale = 1.0 / std::sqrt((double)d.nsamp);
+    }
     for (int k = 0; k < 2; ++k) {
         if ((rc = dev_alloc((void**)&I.q.ext_rays[k], kSlots * sizeof(rrt_ray))) != RRT_OK) return rc;
         if ((rc = dev_alloc((void**)&I.q.ext_path[k], kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
@@ -1230,7 +1287,8 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
         RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
-        generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q);
+        generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q,
+                                                          I.d_diffs, I.diff_scale);
         launches += 1;
         int cur = 0;
         for (uint32_t r = 0; r < rounds; ++r) {
@@ -1243,7 +1301,10 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             shade_scatter_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.q, cur);
             launches += 2;
 #endif
-            shade_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
+            if (I.textured)
+                shade_kernel<true><<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
+            else
+                shade_kernel<false><<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
             rc = I.agg->any_hit_indirect(count, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream, err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;

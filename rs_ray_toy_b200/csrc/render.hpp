@@ -20,7 +20,9 @@ struct RenderStats {
 // rrt_texture table checks shared by the ABI setters: kinds / mappings known, children defined earlier.
 bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err);
 // texture_core.h on the host: out[3 * i + c] for every texture (rrt_texture_host_probe)
-void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], double* out);
+void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], const double p[3], const double* diff, double* out);
+// compute_differentials of texture_core.h on the host (rrt_differentials_host_probe)
+void differentials_host_eval(const double in24[24], double out10[10]);
 
 class Renderer {
   public:

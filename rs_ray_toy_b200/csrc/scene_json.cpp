@@ -284,9 +284,8 @@ struct TextureTable {
             if (dim != 2 && dim != 3) return;  // logged and skipped (:341-344)
             const int32_t c1 = child(names, t1, 1.0, is_rgb), c2 = child(names, t2, 0.0, is_rgb);
             if (dim == 2) {
-                if (read_string(tc, "aamode", "closedform") != "none")
-                    throw std::runtime_error("closed-form checkerboard filtering needs ray differentials: set \"aamode\": \"none\"");
                 i = push(RRT_TEX_CHECKER2D);
+                rows[i].aa = read_string(tc, "aamode", "closedform") == "none" ? 0u : 1u;  // AAMethod (:357-366)
                 mapping(i, tc, to_world);
             } else {  // IdentityMapping3D::new(to_world): the matrix is used as world_to_texture as it stands
                 i = push(RRT_TEX_CHECKER3D);

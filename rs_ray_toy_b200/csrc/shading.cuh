@@ -79,6 +79,8 @@ struct ShadeScene {
     const MaterialRec* materials;
     const TextureRec* textures;
     uint32_t n_textures;
+    // camera-ray differentials per path slot (null unless a texture filters with them: a closed-form checkerboard)
+    const RayDiffRec* ray_diffs;
     const LightRec* lights;
     uint32_t n_lights;
     uint32_t literal;  // Tier L: instance / sphere rays are renormalised like the reference (Q6)
@@ -88,7 +90,9 @@ struct ShadeScene {
 struct Surface {
     V3 p, n, wo;       // BaseInteraction: point, geometric normal, outgoing direction
     V3 shn, shdpdu;    // shading.n, shading.dpdu
-    P2 uv;             // SurfaceInteraction::uv (textures only)
+    // what textures read (filled only for scenes that have textures): SurfaceInteraction::uv, dpdu, dpdv
+    P2 uv;
+    V3 dpdu, dpdv;
     uint32_t material;
 };
 
@@ -102,6 +106,10 @@ __device__ __forceinline__ void xf_surface(const M34& m, const M34& inv, Surface
     s->shn = normalize_n(xf_normal_inv(inv, s->shn));
     s->shdpdu = xf_vector(m, s->shdpdu);
     s->shn = faceforward(s->shn, s->n);
+}
+__device__ __forceinline__ void xf_surface_partials(const M34& m, Surface* s) {
+    s->dpdu = xf_vector(m, s->dpdu);
+    s->dpdv = xf_vector(m, s->dpdv);
 }
 
 // Rebuilds the surface frame of hit (prim_id, t, u, v) for the world ray (o, d).
@@ -117,6 +125,7 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
     }
     Surface s;
     s.material = pi.material;
+    const bool textured = sc.n_textures != 0;
     if (pi.kind == 0) {
         const MeshInfo mi = sc.meshes[pi.shape];
         const uint32_t* vi = sc.mesh_vi + mi.vi_off + 3ull * pi.tri;
@@ -151,9 +160,11 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         }
         s.p = lo + ld * t;
         s.wo = -ld;
-        {   // triangle.rs:289: uv[0] * (1 - u - v) + uv[1] * u + uv[2] * v
+        if (textured) {  // triangle.rs:289: uv[0] * (1 - u - v) + uv[1] * u + uv[2] * v
             const double b0 = sub(sub(1.0, bu), bv);
             s.uv = P2{add(add(mul(uv0.x, b0), mul(uv1.x, bu)), mul(uv2.x, bv)), add(add(mul(uv0.y, b0), mul(uv1.y, bu)), mul(uv2.y, bv))};
+            s.dpdu = dpdu;
+            s.dpdv = dpdv;
         }
         const V3 ist_n = normalize(cross(dp02, dp12));
         s.n = ist_n;
@@ -197,15 +208,23 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         const V3 dpdv = v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * sin(theta)) * (sp.theta_max - sp.theta_min);
         s.p = p;
         s.wo = -od;
-        s.uv = P2{phi / sp.phi_max, sub(theta, sp.theta_min) / sub(sp.theta_max, sp.theta_min)};  // sphere.rs:157-160
         s.n = normalize(cross(dpdu, dpdv));
         s.shn = s.n;
         s.shdpdu = dpdu;
         xf_surface(sp.o2w, sp.w2o, &s);  // sphere.rs:245-255: always applied
+        if (textured) {
+            s.uv = P2{phi / sp.phi_max, sub(theta, sp.theta_min) / sub(sp.theta_max, sp.theta_min)};  // sphere.rs:157-160
+            s.dpdu = dpdu;
+            s.dpdv = dpdv;
+            xf_surface_partials(sp.o2w, &s);
+        }
     }
     if (pi.instance >= 0) {
         const InstanceXf& x = sc.instances[pi.instance];
-        if (!x.is_identity) xf_surface(x.m, x.inv, &s);  // primitives.rs:135-137
+        if (!x.is_identity) {
+            xf_surface(x.m, x.inv, &s);  // primitives.rs:135-137
+            if (textured) xf_surface_partials(x.m, &s);
+        }
     }
     *out = s;
 }
@@ -596,10 +615,14 @@ RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* p
 }
 
 // The material with every textured parameter evaluated at the hit (each compute_scattering_functions starts with
-// Texture::evaluate(si), material/*.rs).  Only called for materials with `needed != 0`.
-static __device__ __noinline__ void material_at(const ShadeScene& sc, const MaterialRec& m, const Surface& s, MaterialRec* out) {
+// Texture::evaluate(si), material/*.rs; si.compute_differentials ran just before, interaction.rs:203-214).  Only
+// called for materials with `needed != 0`.  `diff` = the camera ray's differentials at a path's first hit, or null.
+static __device__ __noinline__ void material_at(const ShadeScene& sc, const MaterialRec& m, const Surface& s, const RayDiffRec* diff,
+                                                MaterialRec* out) {
     Rgb vals[kMaxTextures];
-    texture_eval_table(sc.textures, sc.n_textures, m.needed, s.uv, s.p, vals);
+    TexPoint q = tex_point(s.uv, s.p);
+    if (diff) compute_differentials(s.n, s.dpdu, s.dpdv, *diff, &q);
+    texture_eval_table(sc.textures, sc.n_textures, m.needed, q, vals);
     MaterialRec r = m;
     Rgb* const colours[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.metal_eta, &r.metal_k};
 #pragma unroll

@@ -48,7 +48,7 @@ class Material(C.Structure):
 class Texture(C.Structure):
     """rrt_texture."""
     _fields_ = [("kind", C.c_uint32), ("mapping", C.c_uint32), ("t1", C.c_int32), ("t2", C.c_int32), ("amount", C.c_int32),
-                ("pad", C.c_uint32), ("v", (C.c_double * 3) * 4), ("map", C.c_double * 8), ("world_to_texture", C.c_double * 16)]
+                ("aa", C.c_uint32), ("v", (C.c_double * 3) * 4), ("map", C.c_double * 8), ("world_to_texture", C.c_double * 16)]
 
 
 MAX_TEXTURES = 32
@@ -59,9 +59,11 @@ TEX_CONSTANT, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_
 TEXMAP_UV, TEXMAP_PLANAR, TEXMAP_SPHERICAL, TEXMAP_CYLINDRICAL = range(4)
 
 
-def texture(kind, v=(), mapping=TEXMAP_UV, map8=(1, 1, 0, 0, 0, 0, 0, 0), t1=-1, t2=-1, amount=-1, world_to_texture=None) -> Texture:
-    """One row of the texture table; `v` = up to four values (floats or RGB triples)."""
-    t = Texture(kind=kind, mapping=mapping, t1=t1, t2=t2, amount=amount)
+def texture(kind, v=(), mapping=TEXMAP_UV, map8=(1, 1, 0, 0, 0, 0, 0, 0), t1=-1, t2=-1, amount=-1, world_to_texture=None,
+            aa=0) -> Texture:
+    """One row of the texture table; `v` = up to four values (floats or RGB triples); `aa` = 1 for a closed-form
+    checkerboard."""
+    t = Texture(kind=kind, mapping=mapping, t1=t1, t2=t2, amount=amount, aa=aa)
     for k, val in enumerate(v):
         t.v[k][:] = [float(val), 0.0, 0.0] if np.isscalar(val) else [float(x) for x in val]
     t.map[:] = [float(x) for x in map8]
@@ -69,14 +71,26 @@ def texture(kind, v=(), mapping=TEXMAP_UV, map8=(1, 1, 0, 0, 0, 0, 0, 0), t1=-1,
     return t
 
 
-def texture_host_probe(textures, uv, p) -> np.ndarray:
-    """rrt_texture_host_probe: every texture of the table evaluated at (uv, p) by the product's evaluator on the host."""
+def texture_host_probe(textures, uv, p, diff=None) -> np.ndarray:
+    """rrt_texture_host_probe: every texture of the table evaluated at (uv, p) by the product's evaluator on the host.
+    `diff` = dpdx[3] dpdy[3] dudx dvdx dudy dvdy (None: no differentials)."""
     L = lib()
     arr = (Texture * max(1, len(textures)))(*textures)
     out = np.zeros((len(textures), 3))
     uv2 = (C.c_double * 2)(*[float(x) for x in uv])
     p3 = (C.c_double * 3)(*[float(x) for x in p])
-    capi.check(L.rrt_texture_host_probe(len(textures), C.cast(arr, C.c_void_p), uv2, p3, out.ctypes.data))
+    d = None if diff is None else (C.c_double * 10)(*[float(x) for x in diff])
+    capi.check(L.rrt_texture_host_probe(len(textures), C.cast(arr, C.c_void_p), uv2, p3, d, out.ctypes.data))
+    return out
+
+
+def differentials_host_probe(p, n, dpdu, dpdv, rx_o, rx_d, ry_o, ry_d) -> np.ndarray:
+    """rrt_differentials_host_probe: SurfaceInteraction::compute_differentials with the product's code on the host
+    -> dpdx[3] dpdy[3] dudx dvdx dudy dvdy."""
+    L = lib()
+    a = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(3) for x in (p, n, dpdu, dpdv, rx_o, rx_d, ry_o, ry_d)]))
+    out = np.zeros(10)
+    capi.check(L.rrt_differentials_host_probe(a.ctypes.data, out.ctypes.data))
     return out
 
 
@@ -178,7 +192,9 @@ def _bind(L):
     L.rrt_scene_set_material_textures.restype = i32
     L.rrt_scene_set_material_textures.argtypes = [vp, u32, vp]
     L.rrt_texture_host_probe.restype = i32
-    L.rrt_texture_host_probe.argtypes = [u32, vp, vp, vp, vp]
+    L.rrt_texture_host_probe.argtypes = [u32, vp, vp, vp, vp, vp]
+    L.rrt_differentials_host_probe.restype = i32
+    L.rrt_differentials_host_probe.argtypes = [vp, vp]
     L.rrt_scene_json_texture_probe.restype = i32
     L.rrt_scene_json_texture_probe.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(u32), vp, u32, C.POINTER(u32), vp, vp]
     L.rrt_scene_load_json.restype = i32

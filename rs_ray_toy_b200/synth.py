@@ -280,7 +280,8 @@ def write_floor_obj(path, half=6.0, y=-2.4, cx=35.2, cz=0.0, uv_scale=8.0):
 
 def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
     """SURVEY.md §8f row 3 (procedural part): config 1's cubes on a floor, plus three spheres, with every in-scope texture
-    type driving a material parameter — Checkerboard 2D (point-sampled) over mesh uvs and over a planar mapping,
+    type driving a material parameter — Checkerboard 2D over mesh uvs (closed-form filter: the loader's default, fed by
+    the camera ray's differentials) and over a planar mapping (point-sampled),
     Checkerboard 3D with a texture transform, Bilerp (float and rgb), Scale, Mix (whose amount is looked up under
     "t2", renderprocess.rs:319), UV, spherical and cylindrical mappings — on Matte / Plastic / Metal / Mirror."""
     import json
@@ -305,7 +306,7 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         _const_rgb_texture("white", (0.85, 0.85, 0.8)),
         _const_rgb_texture("dark", (0.1, 0.12, 0.3)),
         _const_rgb_texture("red", (0.7, 0.15, 0.1)),
-        {"texture_name": "floor_check", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "white", "t2": "dark"},
+        {"texture_name": "floor_check", "texture_type": "CheckerBoardTexture", "t1": "white", "t2": "dark"},   # closed-form filter
         {"texture_name": "planar_check", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "red", "t2": "white",
          "mapping": {"mapping": "planar", "v1": [1.3, 0.0, 0.2], "v2": [0.0, 1.7, 0.0], "udelta": 0.25, "vdelta": -0.5}},
         {"texture_name": "solid_check", "texture_type": "CheckerBoardTexture", "dimension": 3, "t1": "white", "t2": "red",
@@ -316,9 +317,16 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         {"texture_name": "cyl", "texture_type": "UVTexture", "mapping": {"mapping": "cylindrical"}, "world_pos": [37.0, 0.0, -3.0]},
         {"texture_name": "mixed", "texture_type": "MixTexture", "t1": "uvcol", "t2": "dark"},          # amount: float "dark" = 0.3
         {"texture_name": "tinted", "texture_type": "ScaleTexture", "t1": "floor_check", "t2": "grad"},
+        # 50-unit checks over the floor (edges at x = 35 and z = 0), closed-form: interaction.rs:237-238 computes the y
+        # neighbour's plane distance from the wrong dot product (Q29), so dpdy is tens of units long at a first hit —
+        # an 8-checks-per-floor board filters to flat grey there, while this one gets wide but partial footprints
+        # whose value depends on every component of the camera ray's differentials
+        {"texture_name": "big_check", "texture_type": "CheckerBoardTexture", "t1": "white", "t2": "red",
+         "mapping": {"mapping": "planar", "v1": [0.02, 0.0, 0.0], "v2": [0.0, 0.0, 0.02], "udelta": 0.3, "vdelta": 0.0}},
+        {"texture_name": "floor_kd", "texture_type": "ScaleTexture", "t1": "floor_check", "t2": "big_check"},
     ]
     cfg["materials"] = [
-        {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_check"},
+        {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_kd"},
         {"material_type": "MatteMaterial", "material_name": "m_planar", "kd": "planar_check", "sigma": "f_sigma"},
         {"material_type": "PlasticMaterial", "material_name": "m_solid", "kd": "solid_check", "ks": "white", "roughness": "f_rough_check"},
         {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "roughness": "f_lo"},

@@ -186,9 +186,8 @@ class Textures:
             c1 = self._child(names, t.get("t1", "ErrorTextureName"), one, is_rgb)
             c2 = self._child(names, t.get("t2", "ErrorTextureName"), zero, is_rgb)
             if dim == 2:
-                if t.get("aamode", "closedform") != "none":
-                    raise ValueError("closed-form checkerboard filtering needs ray differentials: outside the restated subset")
                 r, i = self._row(TEX_CHECKER2D, is_rgb)
+                r[3] = 0.0 if t.get("aamode", "closedform") == "none" else 1.0   # AAMethod (renderprocess.rs:357-366)
                 self._mapping(r, t)
             else:
                 r, i = self._row(TEX_CHECKER3D, is_rgb)

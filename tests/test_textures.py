@@ -16,15 +16,27 @@ from rs_ray_toy_b200 import render as R
 from rs_ray_toy_b200 import capi, synth
 
 
-def oracle_probe(table, uv, p):
+def oracle_probe(table, uv, p, diff=None):
     L = O.lib()
-    L.orc_texture_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_texture_probe.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_texture_probe.restype = None
     table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, S.TEX_ROW)
     uv = np.ascontiguousarray(uv, dtype=np.float64)
     p = np.ascontiguousarray(p, dtype=np.float64)
+    d = None if diff is None else np.ascontiguousarray(diff, dtype=np.float64)
     out = np.zeros((table.shape[0], 3))
-    L.orc_texture_probe(table.shape[0], table.ctypes.data, uv.ctypes.data, p.ctypes.data, out.ctypes.data)
+    L.orc_texture_probe(table.shape[0], table.ctypes.data, uv.ctypes.data, p.ctypes.data, None if d is None else d.ctypes.data,
+                        out.ctypes.data)
+    return out
+
+
+def oracle_differentials(*vecs):
+    L = O.lib()
+    L.orc_differentials_probe.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_differentials_probe.restype = None
+    a = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64).reshape(3) for v in vecs]))
+    out = np.zeros(10)
+    L.orc_differentials_probe(a.ctypes.data, out.ctypes.data)
     return out
 
 
@@ -33,7 +45,7 @@ def product_rows(table):
     rows = []
     for r in np.asarray(table).reshape(-1, S.TEX_ROW):
         rows.append(R.texture(int(r[0]), [r[8 + 3 * k: 11 + 3 * k] for k in range(4)], mapping=int(r[2]), map8=r[20:28],
-                              t1=int(r[4]), t2=int(r[5]), amount=int(r[6]), world_to_texture=r[28:44].reshape(4, 4)))
+                              t1=int(r[4]), t2=int(r[5]), amount=int(r[6]), world_to_texture=r[28:44].reshape(4, 4), aa=int(r[3])))
     return rows
 
 
@@ -97,11 +109,75 @@ def test_host_evaluator_is_the_oracles_bit_for_bit(tmp_path):
     kinds = set(int(k) for k in table[:, 0])
     assert kinds == set(range(7)), kinds          # the scene covers every in-scope texture kind
     assert set(int(k) for k in table[:, 2]) == {0, 1, 2, 3}
+    assert set(int(k) for k in table[table[:, 0] == S.TEX_CHECKER2D][:, 3]) == {0, 1}   # point-sampled and closed-form
+    filtered = 0
     for _ in range(400):
         uv = rng.uniform(-2.0, 9.0, 2)
         p = rng.uniform(-8.0, 40.0, 3)
         a, b = oracle_probe(table, uv, p), R.texture_host_probe(rows, uv, p)
         assert np.array_equal(a, b), (uv, p, a, b)
+        # with screen-space differentials (footprints from a hundredth of a check to several checks)
+        diff = np.concatenate([rng.normal(0, 1, 6) * 10 ** rng.uniform(-3, 0.5), rng.normal(0, 1, 4) * 10 ** rng.uniform(-3, 0.5)])
+        c, d = oracle_probe(table, uv, p, diff), R.texture_host_probe(rows, uv, p, diff)
+        assert np.array_equal(c, d), (uv, p, diff, c, d)
+        filtered += int(not np.array_equal(a, c))
+    assert filtered > 100   # the closed-form filter did something
+
+
+def test_closed_form_checkerboard_known_answers():
+    v = lambda r, g, b: {"values": [r, g, b]}
+    t = _tex(cfg_rgb=[{"texture_name": "a", "texture_type": "BilerpTexture", "v00": v(1, 1, 1), "v01": v(1, 1, 1)},
+                      {"texture_name": "b", "texture_type": "BilerpTexture", "v00": v(0, 0, 0), "v01": v(0, 0, 0)},
+                      {"texture_name": "chk", "texture_type": "CheckerBoardTexture", "t1": "a", "t2": "b",     # aamode: closedform
+                       "mapping": {"mapping": "uv", "su": 1.0, "sv": 1.0, "du": 0.0, "dv": 0.0}}])
+    i = t.rgb["chk"]
+    assert t.table()[i][3] == 1.0
+    z3 = [0.0] * 3
+
+    def at(uv, dudx=0.0, dvdx=0.0, dudy=0.0, dvdy=0.0):
+        return oracle_probe(t.table(), uv, (0, 0, 0), z3 + z3 + [dudx, dvdx, dudy, dvdy])[i][0]
+
+    # a footprint inside one check: the point sample (checkerboard.rs:76-83)
+    assert at((0.5, 0.5), 0.1, 0, 0, 0.1) == 1.0 and at((1.5, 0.5), 0.1, 0, 0, 0.1) == 0.0
+    # footprint [0.75, 1.25] x [0.4, 0.6]: half in check (0, 0), half in check (1, 0).  bump_int(1.25) - bump_int(0.75)
+    # = 0.25 - 0 -> sint = 0.25 / 0.5 = 0.5, tint = 0 -> area2 = 0.5 -> 0.5 * tex1 + 0.5 * tex2
+    assert at((1.0, 0.5), 0.25, 0, 0, 0.1) == pytest.approx(0.5, abs=1e-15)
+    # a quarter of the s-extent past the edge: [0.85, 1.05]: bump_int(1.05) = 0 + 2 * 0.025 -> sint = 0.05 / 0.2 = 0.25
+    assert at((0.95, 0.5), 0.1, 0, 0, 0.1) == pytest.approx(0.75, abs=1e-12)
+    # wider than a check in s: 50 % grey (:88-90)
+    assert at((0.3, 0.5), 1.5, 0, 0, 0.1) == 0.5
+    # ds = max(|dstdx|) is taken over BOTH components of dstdx (s and t derivatives along x), dt likewise (:70-71)
+    assert at((0.95, 0.5), 0.0, 0.1, 0.0, 0.1) == pytest.approx(0.75, abs=1e-12)
+    # a footprint that crosses an edge in s with NO extent in t divides 0 by 0 (:85-86), in the reference as here
+    assert math.isnan(at((0.95, 0.5), 0.1, 0.0, 0.0, 0.0))
+
+
+def test_compute_differentials():
+    """interaction.rs:223-284, with the reference's y-plane slip (Q29: dot(n, ry_direction) in the numerator)."""
+    rng = np.random.default_rng(5)
+    p, n = np.array([0.0, 0.0, 5.0]), np.array([0.0, 0.0, -1.0])
+    dpdu, dpdv = np.array([2.0, 0.0, 0.0]), np.array([0.0, 4.0, 0.0])
+    o = np.zeros(3)
+    rx_o, rx_d = o, np.array([0.1, 0.0, 1.0])
+    ry_o, ry_d = o, np.array([0.0, 0.2, 1.0])
+    out = oracle_differentials(p, n, dpdu, dpdv, rx_o, rx_d, ry_o, ry_d)
+    # x: tx = -(n.rx_o - n.p) / n.rx_d = -(0 + 5) / -1 = 5 -> px = (0.5, 0, 5): dpdx = (0.5, 0, 0), dudx = 0.25
+    assert out[:3].tolist() == [0.5, 0.0, 0.0] and out[6] == 0.25 and out[7] == 0.0
+    # y as the reference computes it: ty = -(n.ry_d - n.p) / n.ry_d = -(-1 + 5) / -1 = 4 (5 was meant) -> py = (0, 0.8, 4)
+    assert out[3:6].tolist() == [0.0, 0.8, -1.0] and out[8] == 0.0 and out[9] == pytest.approx(0.2, abs=1e-15)
+    # a ray parallel to the surface: no differentials at all (:230-232)
+    flat = oracle_differentials(p, n, dpdu, dpdv, rx_o, np.array([1.0, 0.0, 0.0]), ry_o, ry_d)
+    assert not flat.any()
+    # degenerate dpdu / dpdv: the solve fails, du / dv are zero but dpdx / dpdy stay (:276-283)
+    deg = oracle_differentials(p, n, dpdu, dpdu, rx_o, rx_d, ry_o, ry_d)
+    assert deg[:3].tolist() == [0.5, 0.0, 0.0] and not deg[6:].any()
+    # the product's code is the oracle's, bit for bit
+    for _ in range(500):
+        vecs = [rng.normal(0, 3, 3) for _ in range(8)]
+        if rng.uniform() < 0.2:
+            vecs[1] = np.eye(3)[rng.integers(3)] * rng.choice([-1.0, 1.0])
+        a, b = oracle_differentials(*vecs), R.differentials_host_probe(*vecs)
+        assert np.array_equal(a, b), (vecs, a, b)
 
 
 def test_loaders_agree(tmp_path):
@@ -125,11 +201,11 @@ def test_loaders_agree(tmp_path):
 def test_out_of_scope_textures_are_refused(tmp_path):
     path = synth.scene_textured(str(tmp_path))
     cfg = json.loads(open(path).read())
-    closed = dict(cfg)
-    closed["rgb_texture"] = [dict(t) for t in cfg["rgb_texture"]]
-    del closed["rgb_texture"][3]["aamode"]          # the default is the closed-form filter (renderprocess.rs:357)
-    p2 = tmp_path / "closed.json"
-    p2.write_text(json.dumps(closed))
+    mapped = dict(cfg)
+    mapped["rgb_texture"] = [dict(t) for t in cfg["rgb_texture"]]
+    mapped["rgb_texture"][3]["mapping"] = {"mapping": "conical"}      # the reference panics (renderprocess.rs:601-606)
+    p2 = tmp_path / "mapped.json"
+    p2.write_text(json.dumps(mapped))
     with pytest.raises(ValueError):
         S.load(str(p2))
     with pytest.raises(capi.RrtError):

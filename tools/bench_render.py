@@ -19,6 +19,7 @@ ap.add_argument("--scale", type=float, default=1.0, help="resolution scale")
 ap.add_argument("--nsamp", type=int, default=0)
 ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--textured", action="store_true", help="config 5 with a 3D checkerboard kd and a textured roughness")
 a = ap.parse_args()
 ctx = Context(0)
 d = tempfile.mkdtemp()
@@ -33,7 +34,8 @@ elif a.config == "c1":
     path = synth.scene_c1(d, nsamp=a.nsamp or 17)
     r = Render.load(ctx, path, seed=1)
 else:
-    agg, r = synth.scene_c5_api(ctx, n_tris=a.n or (1 << 22), xres=int(3840 * a.scale), yres=int(2160 * a.scale), nsamp=a.nsamp or 257)
+    agg, r = synth.scene_c5_api(ctx, n_tris=a.n or (1 << 22), xres=int(3840 * a.scale), yres=int(2160 * a.scale), nsamp=a.nsamp or 257,
+                                  textured=a.textured)
 setup = time.time() - t0
 for rep in range(a.reps):
     r.clear()
