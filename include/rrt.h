@@ -303,7 +303,8 @@ int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_double
  * (merge_film_tile across ranks, film.rs:248-263).                                              */
 int rrt_render_film_copy(rrt_render* render, void* d_buffer, int to_render, void* cuda_stream);
 /* out16: camera rays, extension rays, shadow rays, bounces, zero-weight samples, samples, kernels
- * launched, render microseconds, ...                                                            */
+ * launched, render microseconds, set-up microseconds, chunks, neighbour lens rays decided by the fp32
+ * walk, neighbour lens rays it handed to the f64 walk, ...                                       */
 int rrt_render_stats(const rrt_render* render, uint64_t out16[16]);
 /* First-hit record of every camera sample of the last run, in launch order: 6 doubles per sample
  * (pixel x, pixel y, sample number, prim id or -1 miss / -2 zero weight, t, ray weight).         */

@@ -221,7 +221,8 @@ enum BxdfKind : uint8_t {
     BX_MICROFACET_REFL,
     BX_SPECULAR_REFL,
     BX_SPECULAR_TRANS,
-    BX_FRESNEL_SPECULAR
+    BX_FRESNEL_SPECULAR,
+    BX_MICROFACET_TRANS
 };
 struct Bxdf {
     uint8_t kind = BX_LAMBERTIAN;
@@ -238,6 +239,7 @@ struct Bxdf {
             case BX_MICROFACET_REFL: return BXDF_GLOSSY | BXDF_REFLECTION;
             case BX_SPECULAR_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
             case BX_SPECULAR_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
+            case BX_MICROFACET_TRANS: return BXDF_GLOSSY | BXDF_TRANSMISSION;  // reflection.rs:1143-1145
             default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
         }
     }
@@ -274,6 +276,20 @@ struct Bxdf {
                 Rgb fr = fresnel.evaluate(dot(wi, faceforward(wh, V3(0.0, 0.0, 1.0))));
                 return r * distrib.d(wh) * distrib.g(wo, wi) * fr / (4.0 * cos_i * cos_o);
             }
+            case BX_MICROFACET_TRANS: {  // reflection.rs:1058-1099 (mode == Radiance)
+                if (same_hemisphere(wo, wi)) return Rgb();
+                double cos_o = cos_theta(wo), cos_i = cos_theta(wi);
+                if (cos_i == 0.0 || cos_o == 0.0) return Rgb();
+                double eta = cos_theta(wo) > 0.0 ? eta_b / eta_a : eta_a / eta_b;
+                V3 wh = normalize_vec(wo + wi * eta);
+                if (wh.z < 0.0) wh = -wh;
+                Rgb fr(fr_dielectric(dot(wo, wh), eta_a, eta_b));
+                double sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+                double factor = 1.0 / eta;
+                return (Rgb(1.0) - fr) * t *
+                       std::fabs(distrib.d(wh) * distrib.g(wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
+                                 (cos_i * cos_o * sqrt_denom * sqrt_denom));
+            }
             default: return Rgb();
         }
     }
@@ -285,6 +301,14 @@ struct Bxdf {
                 if (!same_hemisphere(wo, wi)) return 0.0;
                 V3 wh = normalize_vec(wo + wi);
                 return distrib.pdf(wo, wh) / (4.0 * dot(wo, wh));
+            }
+            case BX_MICROFACET_TRANS: {  // reflection.rs:1127-1142
+                if (same_hemisphere(wo, wi)) return 0.0;
+                double eta = cos_theta(wo) > 0.0 ? eta_b / eta_a : eta_a / eta_b;
+                V3 wh = normalize_vec(wo + wi * eta);
+                double sqrt_denom = dot(wo, wh) + dot(wi, wh) * eta;
+                double dwh_dwi = std::fabs((eta * eta * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+                return distrib.pdf(wo, wh) * dwh_dwi;
             }
             default: return 0.0;
         }
@@ -321,6 +345,15 @@ struct Bxdf {
                 Rgb ft = t * (Rgb(1.0) - Rgb(fr_dielectric(cos_theta(*wi), eta_a, eta_b)));
                 ft *= (ei * ei) / (et * et);
                 return ft / abs_cos_theta(*wi);
+            }
+            case BX_MICROFACET_TRANS: {  // reflection.rs:1100-1126
+                if (wo.z == 0.0) return Rgb();
+                V3 wh = distrib.sample_wh(wo, u);
+                if (dot(wo, wh) < 0.0) return Rgb();
+                double eta = cos_theta(wo) > 0.0 ? eta_a / eta_b : eta_b / eta_a;
+                if (!refract(wo, wh, eta, wi)) return Rgb();
+                *pdf = this->pdf(wo, *wi);
+                return f(wo, *wi);
             }
             default: {  // FresnelSpecular, reflection.rs:751-797
                 double fr = fr_dielectric(cos_theta(wo), eta_a, eta_b);
@@ -724,7 +757,7 @@ inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_l
             }
             return;
         }
-        case MAT_GLASS: {  // glass.rs:52-113; rough transmission (MicrofacetTransmission) is out of scope
+        case MAT_GLASS: {  // glass.rs:52-113
             double eta = m.eta, ur = rmax(m.u_roughness, 0.0), vr = rmax(m.v_roughness, 0.0);
             Rgb r = m.kr.clamp(0.0, kInf), t = m.kt.clamp(0.0, kInf);
             bsdf->init(si, eta);
@@ -743,22 +776,37 @@ inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_l
                 bsdf->add(b);
                 return;
             }
-            if (!is_specular) throw std::runtime_error("oracle: rough glass (MicrofacetTransmission) is out of scope");
+            if (m.remap_roughness) {  // glass.rs:80-83: the remap applies on this branch only
+                ur = roughness_to_alpha(ur);
+                vr = roughness_to_alpha(vr);
+            }
             if (!r.is_black()) {
                 Bxdf b;
-                b.kind = BX_SPECULAR_REFL;
                 b.r = r;
                 b.fresnel.kind = FR_DIELECTRIC;
                 b.fresnel.eta_i = 1.0;
                 b.fresnel.eta_t = eta;
+                if (is_specular) {
+                    b.kind = BX_SPECULAR_REFL;
+                } else {
+                    b.kind = BX_MICROFACET_REFL;
+                    b.distrib.alpha_x = ur;
+                    b.distrib.alpha_y = vr;
+                }
                 bsdf->add(b);
             }
             if (!t.is_black()) {
                 Bxdf b;
-                b.kind = BX_SPECULAR_TRANS;
                 b.t = t;
                 b.eta_a = 1.0;
                 b.eta_b = eta;
+                if (is_specular) {
+                    b.kind = BX_SPECULAR_TRANS;
+                } else {
+                    b.kind = BX_MICROFACET_TRANS;
+                    b.distrib.alpha_x = ur;
+                    b.distrib.alpha_y = vr;
+                }
                 bsdf->add(b);
             }
             return;

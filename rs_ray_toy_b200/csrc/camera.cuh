@@ -112,6 +112,75 @@ RRT_HD bool trace_lenses_from_film(const CameraData& c, const RayD& r_camera, Ra
     *r_out = flip_z(r);
     return true;
 }
+#if defined(__CUDACC__)
+// Does trace_lenses_from_film let this film-side ray through?  An fp32 walk that answers only when every test of
+// the f64 walk (discriminant, root choice, t >= 0, aperture, total internal reflection, stop direction) is decided
+// with a margin of kLensBand — three orders of magnitude above the fp32 error of the walk, whose sphere test is
+// written relative to the element's vertex (c = q.q - 2 R q.z) so that it does not cancel.  Anything closer to a
+// decision boundary than that returns LENS_UNSURE and the caller runs the f64 walk.  Used for the +-0.05 px
+// neighbour rays of generate_ray_differential, of which only "made it through or not" is needed when no texture
+// reads the differentials (tests/test_gpu_render.py::test_f32_neighbour_walk_changes_nothing).
+enum : int { LENS_BLOCKED = 0, LENS_THROUGH = 1, LENS_UNSURE = 2 };
+constexpr float kLensBand = 2e-3f;
+__device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, int n, const RayD& r0) {
+    float ox = (float)r0.o.x, oy = (float)r0.o.y, oz = (float)r0.o.z;
+    float dx = (float)r0.d.x, dy = (float)r0.d.y, dz = (float)r0.d.z;
+    float element_z = 0.0f;
+    for (int i = n - 1; i >= 0; --i) {
+        const float R = (float)el[i].curvature_radius, ap = (float)el[i].aperture_radius;
+        element_z -= (float)el[i].thickness;
+        if (!(fabsf(dz) > kLensBand)) return LENS_UNSURE;  // root choice and the stop's direction test hang on its sign
+        float t, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (R == 0.0f) {
+            if (dz > 0.0f) return LENS_BLOCKED;
+            t = (element_z - oz) / dz;
+        } else {
+            const float qz = oz - element_z;  // the ray origin relative to the element's vertex
+            const float a = dx * dx + dy * dy + dz * dz;
+            const float b = 2.0f * (dx * ox + dy * oy + dz * (qz - R));
+            const float c = ox * ox + oy * oy + qz * qz - 2.0f * R * qz;
+            const float disc = b * b - 4.0f * a * c;
+            const float scale = b * b + fabsf(4.0f * a * c);
+            if (disc < -kLensBand * scale) return LENS_BLOCKED;
+            if (!(disc > kLensBand * scale)) return LENS_UNSURE;
+            const float root = sqrtf(disc);
+            const float q = b < 0.0f ? -0.5f * (b - root) : -0.5f * (b + root);
+            const float ta = q / a, tb = c / q;
+            const float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+            t = ((dz > 0.0f) != (R < 0.0f)) ? t0 : t1;
+            if (t < -kLensBand * ap) return LENS_BLOCKED;  // lengths are judged against the element's aperture radius
+            if (!(t > kLensBand * ap)) return LENS_UNSURE;
+            nx = ox + dx * t;
+            ny = oy + dy * t;
+            nz = (qz - R) + dz * t;
+            const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+            nx *= inv; ny *= inv; nz *= inv;
+            if (nx * -dx + ny * -dy + nz * -dz < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // faceforward(n, -d)
+        }
+        const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+        const float r2 = px * px + py * py, ap2 = ap * ap;
+        if (r2 > ap2 * (1.0f + kLensBand)) return LENS_BLOCKED;
+        if (!(r2 < ap2 * (1.0f - kLensBand))) return LENS_UNSURE;
+        ox = px; oy = py; oz = pz;
+        if (R != 0.0f) {
+            const float eta_prev = i > 0 ? (float)el[i - 1].eta : 0.0f;
+            const float eta = (float)el[i].eta / ((i > 0 && eta_prev != 0.0f) ? eta_prev : 1.0f);
+            const float dinv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            const float wx = -dx * dinv, wy = -dy * dinv, wz = -dz * dinv;
+            const float cos_i = nx * wx + ny * wy + nz * wz;
+            const float sin2_t = eta * eta * fmaxf(0.0f, 1.0f - cos_i * cos_i);
+            if (sin2_t > 1.0f + kLensBand) return LENS_BLOCKED;
+            if (!(sin2_t < 1.0f - kLensBand)) return LENS_UNSURE;
+            const float k = eta * cos_i - sqrtf(1.0f - sin2_t);
+            dx = -wx * eta + nx * k;
+            dy = -wy * eta + ny * k;
+            dz = -wz * eta + nz * k;
+        }
+    }
+    return LENS_THROUGH;
+}
+#endif
+
 // camera.rs:254-308
 RRT_HD bool trace_lenses_from_scene(const CameraData& c, const RayD& r_camera, RayD* r_out) {
     double element_z = -lens_front_z(c);

@@ -705,7 +705,7 @@ int rrt_render_stats(const rrt_render* render, uint64_t out16[16]) {
     if (!render || !out16) return fail(RRT_ERR_INVALID, "rrt_render_stats: null argument");
     const rrt::RenderStats& s = render->renderer.stats();
     const uint64_t v[16] = {s.camera_rays, s.extension_rays, s.shadow_rays, s.bounces, s.zero_weight, s.samples,
-                            s.launches, s.render_usec, s.setup_usec, s.chunks, 0, 0, 0, 0, 0, 0};
+                            s.launches, s.render_usec, s.setup_usec, s.chunks, s.f32_neighbours, s.f32_unsure, 0, 0, 0, 0};
     std::memcpy(out16, v, sizeof(v));
     return RRT_OK;
 }

@@ -137,7 +137,7 @@ enum GenStage : int { GEN_MAIN = 0, GEN_XP = 1, GEN_XM = 2, GEN_YP = 3, GEN_YM =
 __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     generate_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film, IntegratorParams ip,
                     Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q, RayDiffRec* __restrict__ diffs,
-                    double diff_scale) {
+                    double diff_scale, int f32_neighbours) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     // lens table in shared memory: lanes index it at different interfaces (a constant-bank read would serialise)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     uint32_t* const cursor = q.counters + 3;
 
     bool have = false, exhausted = false;
-    uint32_t slot = 0, sn = 0, n_camera = 0, n_zero = 0;
+    uint32_t slot = 0, sn = 0, n_camera = 0, n_zero = 0, n_quick = 0, n_unsure = 0;
     int32_t px = 0, py = 0;
     int stage = GEN_MAIN, ei = 0;
     uint64_t hidx = 0;
@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     double element_z = 0.0, area = 0.0, film_dz = 0.0, wt = 0.0;
 
     bool need_begin = false;
+    // a sample whose neighbour rays were all decided by the fp32 walk finishes without another f64 lens trace
+    bool pre_done = false;
+    double pre_w = 0.0;
+    const bool quick = f32_neighbours != 0 && diffs == nullptr;
 
     for (;;) {
         // ---- gate: lanes without a sample and lanes between two lens traces wait until enough of them have
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                 }
             }
             // start one of the five lens traces of the sample (generate_ray up to trace_lenses_from_film)
-            if (have && need_begin) {
+            while (have && need_begin) {
                 const P2 pfr = stage == GEN_MAIN ? pf
                              : stage == GEN_XP ? P2{pf.x + 0.05, pf.y}
                              : stage == GEN_XM ? P2{pf.x + -0.05, pf.y}
@@ -211,6 +215,34 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                 element_z = 0.0;
                 ei = cam.n_elements - 1;
                 need_begin = false;
+                if (quick && stage != GEN_MAIN) {
+                    // only "through or not" is asked of a neighbour ray: the fp32 walk answers unless the ray passes
+                    // within its margin of a decision boundary, in which case the f64 state machine below takes it
+                    const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, r);
+                    n_quick += verdict != LENS_UNSURE;
+                    n_unsure += verdict == LENS_UNSURE;
+                    if (verdict != LENS_UNSURE) {
+                        const bool ok = verdict == LENS_THROUGH && film_ray_weight(cam, film_dz, area) != 0.0;
+                        bool done = false;
+                        double final_w = 0.0;
+                        if (stage == GEN_XP) {
+                            stage = ok ? GEN_YP : GEN_XM;
+                        } else if (stage == GEN_XM) {
+                            done = !ok;
+                            stage = GEN_YP;
+                        } else if (stage == GEN_YP) {
+                            done = ok;
+                            final_w = wt;
+                            stage = GEN_YM;
+                        } else {
+                            done = true;
+                            final_w = ok ? wt : 0.0;
+                        }
+                        need_begin = !done;
+                        pre_done = done;
+                        pre_w = final_w;
+                    }
+                }
             }
         }
         if (__ballot_sync(FULL, have) == 0u) {
@@ -219,8 +251,13 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
         }
 
         // ---- one interface for every lane that holds a sample ----
-        bool emit = false;
-        if (have && !need_begin) {
+        bool emit = false, finish = false;
+        double finish_w = 0.0;
+        if (have && pre_done) {
+            finish = true;
+            finish_w = pre_w;
+            pre_done = false;
+        } else if (have && !need_begin) {
             bool blocked = false, through = false;
             {
                 const LensElement e = s_el[ei];
@@ -277,34 +314,37 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     }
                 }
                 need_begin = !done;
-                if (done) {
-                    Path* P = paths + slot;
-                    P->beta = rgb(1.0);
-                    P->L = rgb(0.0);
-                    P->eta_scale = 1.0;
-                    P->pfx = pf.x;
-                    P->pfy = pf.y;
-                    P->weight = final_w;
-                    P->hidx = hidx;
-                    P->dim = 5;
-                    P->bounces = 0;
-                    P->px = px;
-                    P->py = py;
-                    P->sample = sn;
-                    P->first_prim = final_w > 0.0 ? -1 : -2;
-                    P->first_t = 0.0;
-                    P->pad = 0;
-                    if (final_w > 0.0) {
-                        P->state = 1;
-                        emit = true;
-                        n_camera += 1;
-                    } else {
-                        P->state = 2;
-                        n_zero += 1;
-                    }
-                    have = false;
-                }
+                finish = done;
+                finish_w = final_w;
             }
+        }
+        if (finish) {
+            const double final_w = finish_w;
+            Path* P = paths + slot;
+            P->beta = rgb(1.0);
+            P->L = rgb(0.0);
+            P->eta_scale = 1.0;
+            P->pfx = pf.x;
+            P->pfy = pf.y;
+            P->weight = final_w;
+            P->hidx = hidx;
+            P->dim = 5;
+            P->bounces = 0;
+            P->px = px;
+            P->py = py;
+            P->sample = sn;
+            P->first_prim = final_w > 0.0 ? -1 : -2;
+            P->first_t = 0.0;
+            P->pad = 0;
+            if (final_w > 0.0) {
+                P->state = 1;
+                emit = true;
+                n_camera += 1;
+            } else {
+                P->state = 2;
+                n_zero += 1;
+            }
+            have = false;
         }
         // ---- camera rays of the samples that finished in this trip (warp-uniform point) ----
         const uint32_t es = queue_slot(q.counters + 0, emit);
@@ -318,10 +358,14 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     for (int off = 16; off > 0; off >>= 1) {
         n_camera += __shfl_xor_sync(FULL, n_camera, off);
         n_zero += __shfl_xor_sync(FULL, n_zero, off);
+        n_quick += __shfl_xor_sync(FULL, n_quick, off);
+        n_unsure += __shfl_xor_sync(FULL, n_unsure, off);
     }
     if (lane == 0) {
         if (n_camera) atomicAdd(q.counters + 4, n_camera);
         if (n_zero) atomicAdd(q.counters + 8, n_zero);
+        if (n_quick) atomicAdd(q.counters + 9, n_quick);
+        if (n_unsure) atomicAdd(q.counters + 10, n_unsure);
     }
 }
 
@@ -742,6 +786,7 @@ struct Renderer::Impl {
     RayDiffRec* d_diffs = nullptr;  // camera-ray differentials per slot, when a texture filters with them
     double diff_scale = 1.0;        // 1 / sqrt(samples_per_pixel) (integrator/mod.rs:92-94)
     bool textured = false, want_diffs = false;
+    bool f32_neighbours = true;     // RRT_GEN_F32=0: every neighbour lens trace in f64 (the A/B switch of the parity test)
     Queues q{};
     uint32_t* d_tiles = nullptr;
     uint32_t tiles_capacity = 0;
@@ -904,23 +949,12 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
                 if (err) *err = "material names a texture that was not set";
                 return RRT_ERR_INVALID;
             }
-            // a textured glass roughness could turn the material into rough glass at some hits
-            const size_t slot = i % RRT_MATERIAL_SLOTS;
-            if (t >= 0 && materials[i / RRT_MATERIAL_SLOTS].kind == RRT_MAT_GLASS &&
-                (slot == RRT_SLOT_U_ROUGHNESS || slot == RRT_SLOT_V_ROUGHNESS)) {
-                if (err) *err = "textured glass roughness (MicrofacetTransmission) is outside the hot-path scope";
-                return RRT_ERR_UNSUPPORTED;
-            }
         }
     }
     bool specular_material = false;
     for (const rrt_material& m : materials) {
         if (m.kind > RRT_MAT_GLASS) {
             if (err) *err = "material kind outside the hot-path scope";
-            return RRT_ERR_UNSUPPORTED;
-        }
-        if (m.kind == RRT_MAT_GLASS && (m.u_roughness > 0.0 || m.v_roughness > 0.0)) {
-            if (err) *err = "rough glass (MicrofacetTransmission) is outside the hot-path scope";
             return RRT_ERR_UNSUPPORTED;
         }
         specular_material |= m.kind == RRT_MAT_MIRROR || m.kind == RRT_MAT_GLASS;
@@ -1198,6 +1232,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     }
     const size_t kSlots = I.chunk;
     if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
+    if (const char* e = std::getenv("RRT_GEN_F32")) I.f32_neighbours = std::atoi(e) != 0;
     if (I.want_diffs) {
         if ((rc = dev_alloc((void**)&I.d_diffs, (size_t)kSlots * sizeof(RayDiffRec))) != RRT_OK) return rc;
         I.sc.ray_diffs = I.d_diffs;
@@ -1288,7 +1323,7 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
         generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q,
-                                                          I.d_diffs, I.diff_scale);
+                                                          I.d_diffs, I.diff_scale, I.f32_neighbours ? 1 : 0);
         launches += 1;
         int cur = 0;
         for (uint32_t r = 0; r < rounds; ++r) {
@@ -1330,6 +1365,8 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
     stats_.bounces += hc[7];
     stats_.zero_weight += hc[8];
     stats_.samples += (uint64_t)hc[4] + hc[8];
+    stats_.f32_neighbours += hc[9];
+    stats_.f32_unsure += hc[10];
     stats_.launches += launches;
     stats_.render_usec +=
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();

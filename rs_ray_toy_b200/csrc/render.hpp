@@ -14,7 +14,8 @@ namespace rrt {
 
 struct RenderStats {
     uint64_t camera_rays = 0, extension_rays = 0, shadow_rays = 0, bounces = 0, zero_weight = 0, samples = 0,
-             launches = 0, render_usec = 0, setup_usec = 0, chunks = 0;
+             launches = 0, render_usec = 0, setup_usec = 0, chunks = 0,
+             f32_neighbours = 0, f32_unsure = 0;  // neighbour lens rays decided by the fp32 walk / handed to the f64 walk
 };
 
 // rrt_texture table checks shared by the ABI setters: kinds / mappings known, children defined earlier.

@@ -298,7 +298,8 @@ static __device__ double roughness_to_alpha(double roughness) {
 
 // ---- lobes -----------------------------------------------------------------------------------------------
 enum : uint32_t { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY = 8, BXDF_SPECULAR = 16, BXDF_ALL = 31 };
-enum : uint32_t { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR, LOBE_MICROFACET, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC };
+enum : uint32_t { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR, LOBE_MICROFACET, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC,
+                  LOBE_MICROFACET_TRANS };
 enum : uint32_t { FRESNEL_NOOP = 0, FRESNEL_DIELECTRIC = 1, FRESNEL_CONDUCTOR = 2 };
 
 struct Lobe {
@@ -316,6 +317,7 @@ __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
         case LOBE_MICROFACET: return BXDF_GLOSSY | BXDF_REFLECTION;
         case LOBE_SPEC_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
         case LOBE_SPEC_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
+        case LOBE_MICROFACET_TRANS: return BXDF_GLOSSY | BXDF_TRANSMISSION;  // reflection.rs:1143-1145
         default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
     }
 }
@@ -416,6 +418,21 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
             double g = 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
             return l.r * tr_d(l, wh) * g * fr / (4.0 * cos_i * cos_o);
         }
+        case LOBE_MICROFACET_TRANS: {  // MicrofacetTransmission::f (reflection.rs:1058-1099), TransportMode::Radiance
+            if (same_hemisphere(wo, wi)) return rgb(0.0);
+            const double cos_o = wo.z, cos_i = wi.z;
+            if (cos_i == 0.0 || cos_o == 0.0) return rgb(0.0);
+            const double eta = wo.z > 0.0 ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+            V3 wh = normalize(wo + wi * eta);
+            if (wh.z < 0.0) wh = -wh;
+            const Rgb fr = rgb(fr_dielectric(dot(wo, wh), l.eta_a, l.eta_b));
+            const double sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+            const double factor = 1.0 / eta;
+            const double g = 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
+            return (rgb(1.0) - fr) * l.t *
+                   fabs(tr_d(l, wh) * g * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
+                        (cos_i * cos_o * sqrt_denom * sqrt_denom));
+        }
         default: return rgb(0.0);
     }
 }
@@ -427,6 +444,14 @@ RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
             if (!same_hemisphere(wo, wi)) return 0.0;
             V3 wh = normalize(wo + wi);
             return tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
+        }
+        case LOBE_MICROFACET_TRANS: {  // reflection.rs:1127-1142
+            if (same_hemisphere(wo, wi)) return 0.0;
+            const double eta = wo.z > 0.0 ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+            const V3 wh = normalize(wo + wi * eta);
+            const double sqrt_denom = dot(wo, wh) + dot(wi, wh) * eta;
+            const double dwh_dwi = fabs((eta * eta * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+            return tr_pdf(l, wo, wh) * dwh_dwi;
         }
         default: return 0.0;
     }
@@ -464,6 +489,16 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             Rgb ft = l.t * (rgb(1.0) - rgb(fr_dielectric(wi->z, l.eta_a, l.eta_b)));
             ft = ft * ((ei * ei) / (et * et));
             return ft / abs_cos_theta(*wi);
+        }
+        case LOBE_MICROFACET_TRANS: {  // reflection.rs:1100-1126
+            if (wo.z == 0.0) return rgb(0.0);
+            const V3 wh = wo.z < 0.0 ? -tr_sample_visible(-wo, l.alpha_x, l.alpha_y, u.x, u.y)
+                                     : tr_sample_visible(wo, l.alpha_x, l.alpha_y, u.x, u.y);
+            if (dot(wo, wh) < 0.0) return rgb(0.0);
+            const double eta = wo.z > 0.0 ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
+            if (!refract_dir(wo, wh, eta, wi)) return rgb(0.0);
+            *pdf = lobe_pdf(l, wo, *wi);
+            return lobe_f(l, wo, *wi);
         }
         default: {  // FresnelSpecular, reflection.rs:751-797
             double fr = fr_dielectric(wo.z, l.eta_a, l.eta_b);
@@ -716,14 +751,16 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
             }
             return;
         }
-        default: {  // GlassMaterial (glass.rs:52-113), smooth only
+        default: {  // GlassMaterial (glass.rs:52-113)
             Rgb r = clamp_rgb(m.kr, 0.0, kInfD), t = clamp_rgb(m.kt, 0.0, kInfD);
+            double ur = rmax(m.u_roughness, 0.0), vr = rmax(m.v_roughness, 0.0);
             b->eta = m.eta;
             if (is_black(r) && is_black(t)) {
                 b->present = false;
                 return;
             }
-            if (allow_multiple_lobes) {
+            const bool is_specular = ur == 0.0 && vr == 0.0;
+            if (is_specular && allow_multiple_lobes) {
                 l.kind = LOBE_FRESNEL_SPEC;
                 l.r = r;
                 l.t = t;
@@ -732,8 +769,14 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
                 b->lobes[b->n_lobes++] = l;
                 return;
             }
+            if (m.remap_roughness) {
+                ur = roughness_to_alpha(ur);
+                vr = roughness_to_alpha(vr);
+            }
+            l.alpha_x = ur;  // TrowbridgeReitzDistribution::new(u_rough, v_rough, true) for both rough lobes
+            l.alpha_y = vr;
             if (!is_black(r)) {
-                l.kind = LOBE_SPEC_REFL;
+                l.kind = is_specular ? LOBE_SPEC_REFL : LOBE_MICROFACET;
                 l.r = r;
                 l.fresnel = FRESNEL_DIELECTRIC;
                 l.a = 1.0;
@@ -741,7 +784,7 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
                 b->lobes[b->n_lobes++] = l;
             }
             if (!is_black(t)) {
-                l.kind = LOBE_SPEC_TRANS;
+                l.kind = is_specular ? LOBE_SPEC_TRANS : LOBE_MICROFACET_TRANS;
                 l.fresnel = FRESNEL_NOOP;
                 l.r = rgb(0.0);
                 l.t = t;

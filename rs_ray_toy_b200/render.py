@@ -356,7 +356,7 @@ class Render:
         out = np.zeros(16, dtype=np.uint64)
         capi.check(self.L.rrt_render_stats(self.h, out.ctypes.data))
         keys = ["camera_rays", "extension_rays", "shadow_rays", "bounces", "zero_weight", "samples", "launches",
-                "render_usec", "setup_usec", "chunks"]
+                "render_usec", "setup_usec", "chunks", "f32_neighbours", "f32_unsure"]
         return {k: int(v) for k, v in zip(keys, out)}
 
     def enable_hit_dump(self, on: bool = True):

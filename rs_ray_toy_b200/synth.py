@@ -394,8 +394,8 @@ def scene_c4(directory, n_spheres=100000, xres=1920, yres=1080, nsamp=65, extent
              max_depth=5, extra_materials=False):
     """Config 4: `n_spheres` unit-instanced spheres of radius 0.5 as 16 sphere entries (8 Plastic
     presets, roughness 0.05-0.5; 8 Metal presets, copper, roughness 0.01-0.3) x instances[], one
-    distant and one point light, Path integrator.  `extra_materials` swaps two presets for Mirror and
-    Glass (test coverage of the specular lobes)."""
+    distant and one point light, Path integrator.  `extra_materials` swaps presets for Mirror, smooth
+    Glass, two rough Glasses and an Oren-Nayar Matte (test coverage of the other lobes)."""
     import json
     import os
     os.makedirs(directory, exist_ok=True)
@@ -416,6 +416,11 @@ def scene_c4(directory, n_spheres=100000, xres=1920, yres=1080, nsamp=65, extent
         mats[7] = {"material_type": "MirrorMaterial", "material_name": "plastic_7"}
         mats[15] = {"material_type": "GlassMaterial", "material_name": "metal_7"}
         mats[3] = {"material_type": "MatteMaterial", "material_name": "plastic_3", "sigma": "rough_m7"}
+        # rough glass (MicrofacetReflection + MicrofacetTransmission), anisotropic; and one with remapped roughness
+        mats[14] = {"material_type": "GlassMaterial", "material_name": "metal_6", "u_roughness": "rough_m6", "v_roughness": "rough_m3"}
+        mats[13] = {"material_type": "GlassMaterial", "material_name": "metal_5", "u_roughness": "rough_p4", "v_roughness": "rough_p4",
+                    "remap_roughness": True, "eta": "rough_eta"}
+        ftex.append(_const_float_texture("rough_eta", 1.33))
     names = [m["material_name"] for m in mats]
     prims = []
     per = (n_spheres + 15) // 16

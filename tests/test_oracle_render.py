@@ -93,6 +93,79 @@ def test_bsdf_known_answers():
     assert np.allclose(out[4:7] * out[9] / out[10], 0.5)
 
 
+def test_rough_glass_known_answers():
+    """GlassMaterial with non-zero roughness (glass.rs:77-108): MicrofacetReflection + MicrofacetTransmission
+    (reflection.rs:1028-1146) over an anisotropic Trowbridge-Reitz distribution, against the textbook formulas
+    written out independently in numpy."""
+    tex = S.Textures({"float_texture": [{"texture_name": "ur", "texture_type": "BilerpTexture", "v00": 0.2, "v01": 0.2},
+                                        {"texture_name": "vr", "texture_type": "BilerpTexture", "v00": 0.35, "v01": 0.35}],
+                      "rgb_texture": [{"texture_name": "black", "texture_type": "BilerpTexture", "v00": {"values": [0, 0, 0]},
+                                       "v01": {"values": [0, 0, 0]}},
+                                      {"texture_name": "kt", "texture_type": "BilerpTexture", "v00": {"values": [0.9, 0.8, 0.7]},
+                                       "v01": {"values": [0.9, 0.8, 0.7]}}]})
+    row = S.material_row({"material_type": "GlassMaterial", "kr": "black", "kt": "kt", "u_roughness": "ur", "v_roughness": "vr"}, tex)
+    ax, ay, eta_b = 0.2, 0.35, 1.5
+    wo = np.array([0.3, 0.2, np.sqrt(1 - 0.13)])
+    wi = np.array([-0.25, 0.1, -np.sqrt(1 - 0.0725)])
+
+    def D(wh):
+        c2 = wh[2] ** 2
+        t2 = (1 - c2) / c2
+        s2 = max(1 - c2, 0.0)
+        cp2, sp2 = (wh[0] ** 2 / s2, wh[1] ** 2 / s2) if s2 > 0 else (1.0, 0.0)
+        return 1.0 / (np.pi * ax * ay * c2 * c2 * (1 + t2 * (cp2 / ax ** 2 + sp2 / ay ** 2)) ** 2)
+
+    def lam(w):
+        c2 = w[2] ** 2
+        s2 = max(1 - c2, 0.0)
+        t = np.sqrt(s2 / c2)
+        cp2, sp2 = (w[0] ** 2 / s2, w[1] ** 2 / s2) if s2 > 0 else (1.0, 0.0)
+        a = np.sqrt(cp2 * ax ** 2 + sp2 * ay ** 2)
+        return (-1 + np.sqrt(1 + (a * t) ** 2)) / 2
+
+    def fresnel(c, ei, et):
+        c = np.clip(c, -1, 1)
+        if c <= 0:
+            ei, et, c = et, ei, abs(c)
+        st = ei / et * np.sqrt(max(0, 1 - c * c))
+        if st >= 1:
+            return 1.0
+        ct = np.sqrt(max(0, 1 - st * st))
+        rl = (et * c - ei * ct) / (et * c + ei * ct)
+        rp = (ei * c - et * ct) / (ei * c + et * ct)
+        return (rl * rl + rp * rp) / 2
+
+    eta = eta_b / 1.0                                   # wo above the surface
+    wh = wo + wi * eta
+    wh = wh / np.linalg.norm(wh)
+    if wh[2] < 0:
+        wh = -wh
+    F = fresnel(wo @ wh, 1.0, eta_b)
+    denom = wo @ wh + eta * (wi @ wh)
+    G = 1 / (1 + lam(wo) + lam(wi))
+    f_expect = (1 - F) * np.array([0.9, 0.8, 0.7]) * abs(D(wh) * G * eta * eta * abs(wi @ wh) * abs(wo @ wh) * (1 / eta) ** 2
+                                                         / (wi[2] * wo[2] * denom * denom))
+    whp = (wo + wi * eta) / np.linalg.norm(wo + wi * eta)   # pdf uses the unflipped half vector (reflection.rs:1138)
+    pdf_expect = D(whp) * (1 / (1 + lam(wo))) * abs(wo @ whp) / abs(wo[2]) * abs(eta * eta * (wi @ whp) / denom ** 2)
+    out = _probe(row, wo, wi, (0.37, 0.61), allow=False)
+    assert np.allclose(out[:3], f_expect, rtol=1e-12) and f_expect.min() > 0
+    assert np.isclose(out[3], pdf_expect, rtol=1e-12)
+    # the sampled direction is the refraction of wo about a visible normal: below the surface, and the generalised half
+    # vector of (wo, wi) is that normal again, so f / pdf are the values above evaluated at the sample
+    swi = out[7:10]
+    assert out[11] == 10 and swi[2] < 0 and np.isclose(np.linalg.norm(swi), 1.0)      # GLOSSY | TRANSMISSION
+    again = _probe(row, wo, swi, (0.37, 0.61), allow=False)
+    assert np.allclose(again[:3], out[4:7], rtol=1e-12) and np.isclose(again[3], out[10], rtol=1e-12)
+    # with kr too there are two lobes: the glossy reflection half is MicrofacetReflection with a dielectric Fresnel term
+    row2 = S.material_row({"material_type": "GlassMaterial", "u_roughness": "ur", "v_roughness": "vr"}, tex)
+    wr = np.array([-0.1, 0.25, np.sqrt(1 - 0.0725)])
+    o2 = _probe(row2, wo, wr, (0.2, 0.6), allow=True)                                 # allow_multiple_lobes is ignored when rough
+    h = (wo + wr) / np.linalg.norm(wo + wr)
+    fr = fresnel(wr @ h, 1.0, 1.5) * D(h) / (1 + lam(wo) + lam(wr)) / (4 * wr[2] * wo[2])
+    assert np.allclose(o2[:3], fr, rtol=1e-12)
+    assert o2[11] in (9, 10)
+
+
 def test_film_weights_and_q10_q14(tmp_path):
     """nsamp = N renders N-1 samples (Q10); every sample, vignetted or not, adds its filter weight
     three times (Q14); a box filter of radius 0.5 puts each sample in its own pixel."""
