@@ -164,7 +164,8 @@ typedef struct rrt_material {
     double metal_eta[3], metal_k[3];  /* FresnelConductor eta / k (default: copper)             */
     double sigma;                     /* Matte: Oren-Nayar sigma in degrees                     */
     double roughness;                 /* Plastic / Metal                                        */
-    double u_roughness, v_roughness;  /* Metal: < 0 = None (use roughness); Glass: values       */
+    double u_roughness, v_roughness;  /* Metal: < 0 = None (use roughness); Glass: values; non-zero = rough
+                                       * glass, MicrofacetReflection + MicrofacetTransmission (glass.rs:77-108) */
     double eta;                       /* Glass index                                            */
 } rrt_material;
 

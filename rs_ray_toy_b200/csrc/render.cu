@@ -369,6 +369,284 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     }
 }
 
+// ---- generate, screened ----------------------------------------------------------------------------------
+// The same camera samples with the work reordered.  generate_ray_differential gives a sample its weight only if the
+// main lens ray and one neighbour in x and in y make it through (camera.rs:582-628), and of the neighbours only that
+// yes / no is used when no texture reads the differentials.  Two thirds of the samples of the BASELINE cameras fail
+// that test.  So a warp alternates between two phases, each with all 32 lanes busy:
+//   screen — every lane walks ONE lens ray per trip in fp32 (lens_walk_from_film_f32: the main ray, then the
+//            neighbours), drops samples that are certainly blocked with their zero weight, and appends survivors to a
+//            per-warp queue in shared memory;
+//   trace  — 32 queued survivors run the f64 lens trace in lockstep: every one of them crosses all interfaces, so
+//            no lane waits for another.
+// A ray that passes within the walk's margin of any decision boundary is never decided in fp32: its sample goes to
+// the queue marked "undecided" and the trace phase runs the whole f64 procedure for it, neighbours included.
+struct GenSample {
+    uint32_t slot, sn;
+    int32_t px, py;
+    uint32_t nb_ok, pad;  // nb_ok: both neighbours are known to pass
+    uint64_t hidx;
+    P2 pf, pl;
+};
+constexpr uint32_t kGenQueue = 64;  // per warp; the screen phase stops at >= 32 entries and adds at most 32 per trip
+
+__device__ __forceinline__ P2 neighbour_film_point(P2 pf, int stage) {
+    return stage == GEN_MAIN ? pf
+         : stage == GEN_XP ? P2{pf.x + 0.05, pf.y}
+         : stage == GEN_XM ? P2{pf.x + -0.05, pf.y}
+         : stage == GEN_YP ? P2{pf.x, pf.y + 0.05} : P2{pf.x, pf.y + -0.05};
+}
+__device__ __forceinline__ void finish_camera_sample(Path* P, const GenSample& g, double final_w) {
+    P->beta = rgb(1.0);
+    P->L = rgb(0.0);
+    P->eta_scale = 1.0;
+    P->pfx = g.pf.x;
+    P->pfy = g.pf.y;
+    P->weight = final_w;
+    P->hidx = g.hidx;
+    P->dim = 5;
+    P->bounces = 0;
+    P->px = g.px;
+    P->py = g.py;
+    P->sample = g.sn;
+    P->first_prim = final_w > 0.0 ? -1 : -2;
+    P->first_t = 0.0;
+    P->pad = 0;
+    P->state = final_w > 0.0 ? 1u : 2u;
+}
+
+__global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
+    generate_screened_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film,
+                             IntegratorParams ip, Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    __shared__ LensElement s_el[kMaxLensElements];
+    __shared__ GenSample s_queue[4][kGenQueue];
+    __shared__ GenSample s_screen[128], s_trace[128];  // the sample a lane is screening / tracing
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_el[k] = cam.el[k];
+    __syncthreads();
+    GenSample* const wq = s_queue[threadIdx.x >> 5];
+    GenSample& fs = s_screen[threadIdx.x];
+    GenSample& cs = s_trace[threadIdx.x];
+    uint32_t* const cursor = q.counters + 3;
+
+    uint32_t qhead = 0, qcount = 0;  // warp-uniform
+    bool exhausted = false;          // warp-uniform: the chunk's cursor has run out
+    bool fhave = false;
+    int fstage = GEN_MAIN;
+    bool have = false, need_begin = false;
+    int stage = GEN_MAIN, ei = 0;
+    RayD r = {v3(0, 0, 0), v3(0, 0, 0)};
+    double element_z = 0.0, area = 0.0, film_dz = 0.0, wt = 0.0;
+    uint32_t n_camera = 0, n_zero = 0, n_quick = 0, n_unsure = 0;
+
+    for (;;) {
+        // ================= screen =================
+        for (;;) {
+            const unsigned pending = __ballot_sync(FULL, fhave);
+            if (qcount >= 32u || (exhausted && pending == 0u)) break;
+            const unsigned idle = ~pending;
+            if (idle != 0u && !exhausted) {
+                const int want = __popc(idle);
+                uint32_t first = 0;
+                if (lane == 0) first = atomicAdd(cursor, (uint32_t)want);
+                first = __shfl_sync(FULL, first, 0);
+                if ((uint64_t)first + (uint64_t)want >= count) exhausted = true;
+                const uint64_t mine = (uint64_t)first + (uint64_t)__popc(idle & lt);
+                if (!fhave && mine < count) {
+                    const uint32_t slot = (uint32_t)mine;
+                    const uint64_t sidx = base + slot;
+                    const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
+                    const uint32_t tslot = (uint32_t)(sidx / per_tile);
+                    const uint32_t within = (uint32_t)(sidx % per_tile);
+                    const uint32_t pix = within / ip.n_samples;
+                    const uint32_t sn = within % ip.n_samples + 1u;  // sample numbers 1..nsamp-1 (Q10)
+                    const uint32_t tile = fr.tiles[tslot];
+                    const int64_t x = film.sb[0] + (int64_t)(tile % fr.n_tiles_x) * kTile + (pix % kTile);
+                    const int64_t y = film.sb[1] + (int64_t)(tile / fr.n_tiles_x) * kTile + (pix / kTile);
+                    bool valid = x < film.sb[2] && y < film.sb[3] && x >= 0 && x < film.xres && y >= 0 && y < film.yres;
+                    if (valid && fr.use_crop) valid = x >= fr.crop[0] && x < fr.crop[2] && y >= fr.crop[1] && y < fr.crop[3];
+                    if (!valid) {
+                        paths[slot].state = 0;  // no sample in this slot
+                    } else {
+                        const uint64_t hidx = halton_index(ht, x, y, sn);
+                        fs.slot = slot;
+                        fs.sn = sn;
+                        fs.px = (int32_t)x;
+                        fs.py = (int32_t)y;
+                        fs.nb_ok = 0;
+                        fs.hidx = hidx;
+                        // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
+                        fs.pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
+                        fs.pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                        fhave = true;
+                        fstage = GEN_MAIN;
+                    }
+                }
+            }
+            // one fp32 walk per lane
+            bool push = false, zero = false;
+            uint32_t nb = 0;
+            if (fhave) {
+                RayD r_film;
+                double a;
+                begin_film_ray(cam, neighbour_film_point(fs.pf, fstage), fs.pl, &r_film, &a);
+                const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, flip_z(r_film));
+                if (verdict == LENS_UNSURE) {
+                    push = true;  // undecided: the f64 procedure takes the whole sample
+                    n_unsure += 1;
+                } else if (fstage == GEN_MAIN) {
+                    if (verdict == LENS_BLOCKED) zero = true;
+                    else fstage = GEN_XP;
+                } else {
+                    n_quick += 1;
+                    const bool ok = verdict == LENS_THROUGH && film_ray_weight(cam, normalize(r_film.d).z, a) != 0.0;
+                    if (fstage == GEN_XP) {
+                        fstage = ok ? GEN_YP : GEN_XM;
+                    } else if (fstage == GEN_XM) {
+                        if (ok) fstage = GEN_YP;
+                        else zero = true;
+                    } else if (fstage == GEN_YP) {
+                        if (ok) {
+                            push = true;
+                            nb = 1;
+                        } else {
+                            fstage = GEN_YM;
+                        }
+                    } else {
+                        if (ok) {
+                            push = true;
+                            nb = 1;
+                        } else {
+                            zero = true;
+                        }
+                    }
+                }
+            }
+            if (zero) {
+                Path* P = paths + fs.slot;
+                P->o = v3(0, 0, 0);
+                P->d = v3(0, 0, 0);
+                finish_camera_sample(P, fs, 0.0);
+                n_zero += 1;
+                fhave = false;
+            }
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (push) {
+                GenSample g = fs;
+                g.nb_ok = nb;
+                wq[(qhead + qcount + (uint32_t)__popc(pm & lt)) % kGenQueue] = g;
+                fhave = false;
+            }
+            qcount += (uint32_t)__popc(pm);
+            __syncwarp();
+        }
+        if (qcount == 0u) break;  // the chunk is exhausted and nothing is left to trace
+
+        // ================= trace =================
+        const bool last = exhausted && __ballot_sync(FULL, fhave) == 0u;
+        for (;;) {
+            const unsigned waiting = __ballot_sync(FULL, !have || need_begin);
+            if (__popc(waiting) >= RRT_GEN_REFILL || waiting == FULL) {
+                const unsigned idle = __ballot_sync(FULL, !have);
+                if (idle == FULL && qcount < 32u && !(last && qcount > 0u)) break;  // screen some more first
+                if (idle != 0u && qcount > 0u) {
+                    const uint32_t take = min((uint32_t)__popc(idle), qcount);
+                    const uint32_t k = (uint32_t)__popc(idle & lt);
+                    if (!have && k < take) {
+                        cs = wq[(qhead + k) % kGenQueue];
+                        have = true;
+                        stage = GEN_MAIN;
+                        need_begin = true;
+                    }
+                    qhead = (qhead + take) % kGenQueue;
+                    qcount -= take;
+                    __syncwarp();
+                }
+                if (have && need_begin) {
+                    RayD r_film;
+                    begin_film_ray(cam, neighbour_film_point(cs.pf, stage), cs.pl, &r_film, &area);
+                    film_dz = normalize(r_film.d).z;
+                    r = flip_z(r_film);  // trace_lenses_from_film's first statement
+                    element_z = 0.0;
+                    ei = cam.n_elements - 1;
+                    need_begin = false;
+                }
+            }
+            if (__ballot_sync(FULL, have) == 0u) break;
+            bool emit = false;
+            if (have && !need_begin) {
+                bool blocked = false, through = false;
+                {
+                    const LensElement e = s_el[ei];
+                    const double eta_prev = ei > 0 ? s_el[ei - 1].eta : 0.0;
+                    const double eta_t = (ei > 0 && eta_prev != 0.0) ? eta_prev : 1.0;
+                    if (!lens_step_from_film(e, eta_t, &element_z, &r)) blocked = true;
+                    else if (--ei < 0) through = true;
+                }
+                if (blocked || through) {
+                    const double w = through ? film_ray_weight(cam, film_dz, area) : 0.0;
+                    const bool ok = w != 0.0;
+                    bool done = false;
+                    double final_w = 0.0;
+                    if (stage == GEN_MAIN) {
+                        RayD world = {v3(0, 0, 0), v3(0, 0, 0)};
+                        if (ok) camera_ray_to_world(cam, flip_z(r), &world);
+                        paths[cs.slot].o = world.o;
+                        paths[cs.slot].d = world.d;
+                        wt = w;
+                        done = !ok || cs.nb_ok != 0u;  // the screen phase vouches for the neighbours
+                        final_w = ok ? wt : 0.0;
+                        stage = GEN_XP;
+                    } else if (stage == GEN_XP) {
+                        stage = ok ? GEN_YP : GEN_XM;
+                    } else if (stage == GEN_XM) {
+                        done = !ok;
+                        stage = GEN_YP;
+                    } else if (stage == GEN_YP) {
+                        done = ok;
+                        final_w = wt;
+                        stage = GEN_YM;
+                    } else {
+                        done = true;
+                        final_w = ok ? wt : 0.0;
+                    }
+                    need_begin = !done;
+                    if (done) {
+                        finish_camera_sample(paths + cs.slot, cs, final_w);
+                        if (final_w > 0.0) {
+                            emit = true;
+                            n_camera += 1;
+                        } else {
+                            n_zero += 1;
+                        }
+                        have = false;
+                    }
+                }
+            }
+            const uint32_t es = queue_slot(q.counters + 0, emit);
+            if (emit) {
+                write_ray(q.ext_rays[0] + es, paths[cs.slot].o, paths[cs.slot].d, kInfD);
+                q.ext_path[0][es] = cs.slot;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_camera += __shfl_xor_sync(FULL, n_camera, off);
+        n_zero += __shfl_xor_sync(FULL, n_zero, off);
+        n_quick += __shfl_xor_sync(FULL, n_quick, off);
+        n_unsure += __shfl_xor_sync(FULL, n_unsure, off);
+    }
+    if (lane == 0) {
+        if (n_camera) atomicAdd(q.counters + 4, n_camera);
+        if (n_zero) atomicAdd(q.counters + 8, n_zero);
+        if (n_quick) atomicAdd(q.counters + 9, n_quick);
+        if (n_unsure) atomicAdd(q.counters + 10, n_unsure);
+    }
+}
+
 // ---- shade ---------------------------------------------------------------------------------------------
 // The part of a Path the shade kernel works on: it reads and writes these fields only, the rest of the 200-byte
 // record (film position, weight, radiance, pixel) stays in memory.
@@ -786,7 +1064,9 @@ struct Renderer::Impl {
     RayDiffRec* d_diffs = nullptr;  // camera-ray differentials per slot, when a texture filters with them
     double diff_scale = 1.0;        // 1 / sqrt(samples_per_pixel) (integrator/mod.rs:92-94)
     bool textured = false, want_diffs = false;
-    bool f32_neighbours = true;     // RRT_GEN_F32=0: every neighbour lens trace in f64 (the A/B switch of the parity test)
+    // RRT_GEN_F32: 2 = screened generate kernel (fp32 walks decide blocked samples and neighbour rays; the default),
+    // 1 = the lane-state-machine kernel with fp32 neighbour walks, 0 = every lens trace in f64 (the parity tests' A/B switch)
+    int gen_mode = 2;
     Queues q{};
     uint32_t* d_tiles = nullptr;
     uint32_t tiles_capacity = 0;
@@ -1232,7 +1512,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     }
     const size_t kSlots = I.chunk;
     if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
-    if (const char* e = std::getenv("RRT_GEN_F32")) I.f32_neighbours = std::atoi(e) != 0;
+    if (const char* e = std::getenv("RRT_GEN_F32")) I.gen_mode = std::atoi(e);
     if (I.want_diffs) {
         if ((rc = dev_alloc((void**)&I.d_diffs, (size_t)kSlots * sizeof(RayDiffRec))) != RRT_OK) return rc;
         I.sc.ray_diffs = I.d_diffs;
@@ -1322,8 +1602,12 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
         RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
-        generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q,
-                                                          I.d_diffs, I.diff_scale, I.f32_neighbours ? 1 : 0);
+        if (I.gen_mode == 2 && I.d_diffs == nullptr)
+            generate_screened_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count,
+                                                                       I.d_paths, I.q);
+        else
+            generate_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q,
+                                                              I.d_diffs, I.diff_scale, I.gen_mode == 1 ? 1 : 0);
         launches += 1;
         int cur = 0;
         for (uint32_t r = 0; r < rounds; ++r) {

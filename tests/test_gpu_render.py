@@ -283,27 +283,31 @@ def test_textures_through_the_api(ctx):
                       textures=[R.texture(R.TEX_CONSTANT, [(0.5, 0.5, 0.5)])], material_slots=slots)
 
 
-def test_f32_neighbour_walk_changes_nothing(ctx, tmp_path, monkeypatch):
+def test_f32_lens_walks_change_nothing(ctx, tmp_path, monkeypatch):
     """generate_ray_differential's +-0.05 px neighbour rays only decide whether a sample keeps its weight
-    (camera.rs:582-628).  The generate kernel answers that with an fp32 lens walk that abstains near every decision
-    boundary (csrc/camera.cuh lens_walk_from_film_f32); RRT_GEN_F32=0 sends every neighbour through the f64 walk.
-    Both must give every camera sample the same weight, first hit and film, on the two camera set-ups of the
-    BASELINE configs — and the oracle's zero-weight count (checked by every other render test) stays exact."""
+    (camera.rs:582-628), and a main ray that is blocked in the lens only makes the weight zero.  The generate kernels
+    answer those yes / no questions with an fp32 lens walk that abstains near every decision boundary
+    (csrc/camera.cuh lens_walk_from_film_f32): RRT_GEN_F32=2 is the screened kernel (the default), 1 the lane state
+    machine with fp32 neighbour walks, 0 sends every ray through the f64 walk.  All three must give every camera sample
+    the same weight, first hit and film, on the two camera set-ups of the BASELINE configs — and the oracle's
+    zero-weight count (checked by every other render test) stays exact."""
     scenes_ = [synth.scene_c1(str(tmp_path / "c1"), xres=640, yres=360, nsamp=9),
                synth.scene_c4(str(tmp_path / "c4"), n_spheres=3000, xres=480, yres=270, nsamp=9, extent=12.0)]
     for path in scenes_:
-        runs = []
-        for flag in ("0", "1"):
+        runs = {}
+        for flag in ("0", "1", "2"):
             monkeypatch.setenv("RRT_GEN_F32", flag)
             gpu = Render.load(ctx, path, seed=1)
             gpu.enable_hit_dump()
             gpu.run()
-            runs.append((gpu.hit_dump(), gpu.film(), gpu.stats()))
-        (d0, f0, s0), (d1, f1, s1) = runs
-        assert s0["f32_neighbours"] == 0 and s1["f32_neighbours"] > 2 * s1["camera_rays"] * 0.9, (s0, s1)
-        assert s1["f32_unsure"] < 0.1 * s1["f32_neighbours"], s1
-        assert s0["camera_rays"] == s1["camera_rays"] and s0["zero_weight"] == s1["zero_weight"]
-        key = lambda d: np.lexsort((d[:, 2], d[:, 0], d[:, 1]))
-        a, b = d0[key(d0)], d1[key(d1)]
-        assert np.array_equal(a, b)   # pixel, sample, first primitive, t and weight of every camera sample: equal bits
-        assert np.allclose(f0, f1, rtol=1e-12, atol=0)
+            runs[flag] = (gpu.hit_dump(), gpu.film(), gpu.stats())
+        d0, f0, s0 = runs["0"]
+        assert s0["f32_neighbours"] == 0 and s0["f32_unsure"] == 0
+        for flag in ("1", "2"):
+            d1, f1, s1 = runs[flag]
+            assert s1["f32_neighbours"] > 2 * s1["camera_rays"] * 0.9, (flag, s1)
+            assert s1["f32_unsure"] < 0.05 * s1["f32_neighbours"], (flag, s1)
+            assert s0["camera_rays"] == s1["camera_rays"] and s0["zero_weight"] == s1["zero_weight"], (flag, s0, s1)
+            assert s0["extension_rays"] == s1["extension_rays"] and s0["shadow_rays"] == s1["shadow_rays"], (flag, s0, s1)
+            assert np.array_equal(d0, d1), flag   # pixel, sample, first primitive, t and weight of every camera sample
+            assert np.allclose(f0, f1, rtol=1e-12, atol=0), flag
