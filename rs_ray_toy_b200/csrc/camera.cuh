@@ -122,9 +122,14 @@ RRT_HD bool trace_lenses_from_film(const CameraData& c, const RayD& r_camera, Ra
 // reads the differentials (tests/test_gpu_render.py::test_f32_neighbour_walk_changes_nothing).
 enum : int { LENS_BLOCKED = 0, LENS_THROUGH = 1, LENS_UNSURE = 2 };
 constexpr float kLensBand = 2e-3f;
-__device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, int n, const RayD& r0) {
-    float ox = (float)r0.o.x, oy = (float)r0.o.y, oz = (float)r0.o.z;
-    float dx = (float)r0.d.x, dy = (float)r0.d.y, dz = (float)r0.d.z;
+struct RayF {
+    float ox, oy, oz, dx, dy, dz;
+};
+__device__ __forceinline__ RayF ray_f32(const RayD& r) {
+    return RayF{(float)r.o.x, (float)r.o.y, (float)r.o.z, (float)r.d.x, (float)r.d.y, (float)r.d.z};
+}
+__device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, int n, RayF ray) {
+    float ox = ray.ox, oy = ray.oy, oz = ray.oz, dx = ray.dx, dy = ray.dy, dz = ray.dz;
     float element_z = 0.0f;
     for (int i = n - 1; i >= 0; --i) {
         const float R = (float)el[i].curvature_radius, ap = (float)el[i].aperture_radius;
@@ -133,48 +138,51 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, in
         float t, nx = 0.0f, ny = 0.0f, nz = 0.0f;
         if (R == 0.0f) {
             if (dz > 0.0f) return LENS_BLOCKED;
-            t = (element_z - oz) / dz;
+            t = __fdividef(element_z - oz, dz);
         } else {
             const float qz = oz - element_z;  // the ray origin relative to the element's vertex
-            const float a = dx * dx + dy * dy + dz * dz;
-            const float b = 2.0f * (dx * ox + dy * oy + dz * (qz - R));
-            const float c = ox * ox + oy * oy + qz * qz - 2.0f * R * qz;
-            const float disc = b * b - 4.0f * a * c;
-            const float scale = b * b + fabsf(4.0f * a * c);
+            const float cz = qz - R;          // ... and relative to the sphere's centre
+            const float a = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float b = 2.0f * fmaf(dx, ox, fmaf(dy, oy, dz * cz));
+            const float c = fmaf(ox, ox, fmaf(oy, oy, fmaf(qz, qz, -2.0f * R * qz)));
+            const float bb = b * b, ac4 = 4.0f * a * c;
+            const float disc = bb - ac4;
+            const float scale = bb + fabsf(ac4);
             if (disc < -kLensBand * scale) return LENS_BLOCKED;
             if (!(disc > kLensBand * scale)) return LENS_UNSURE;
-            const float root = sqrtf(disc);
+            const float root = disc * rsqrtf(disc);
             const float q = b < 0.0f ? -0.5f * (b - root) : -0.5f * (b + root);
-            const float ta = q / a, tb = c / q;
+            const float ta = __fdividef(q, a), tb = __fdividef(c, q);
             const float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
             t = ((dz > 0.0f) != (R < 0.0f)) ? t0 : t1;
             if (t < -kLensBand * ap) return LENS_BLOCKED;  // lengths are judged against the element's aperture radius
             if (!(t > kLensBand * ap)) return LENS_UNSURE;
-            nx = ox + dx * t;
-            ny = oy + dy * t;
-            nz = (qz - R) + dz * t;
-            const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);
+            nx = fmaf(dx, t, ox);
+            ny = fmaf(dy, t, oy);
+            nz = fmaf(dz, t, cz);
+            const float inv = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
             nx *= inv; ny *= inv; nz *= inv;
-            if (nx * -dx + ny * -dy + nz * -dz < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // faceforward(n, -d)
+            if (fmaf(nx, dx, fmaf(ny, dy, nz * dz)) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // faceforward(n, -d)
         }
-        const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
-        const float r2 = px * px + py * py, ap2 = ap * ap;
+        const float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
+        const float r2 = fmaf(px, px, py * py), ap2 = ap * ap;
         if (r2 > ap2 * (1.0f + kLensBand)) return LENS_BLOCKED;
         if (!(r2 < ap2 * (1.0f - kLensBand))) return LENS_UNSURE;
         ox = px; oy = py; oz = pz;
         if (R != 0.0f) {
             const float eta_prev = i > 0 ? (float)el[i - 1].eta : 0.0f;
-            const float eta = (float)el[i].eta / ((i > 0 && eta_prev != 0.0f) ? eta_prev : 1.0f);
-            const float dinv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            const float eta = __fdividef((float)el[i].eta, (i > 0 && eta_prev != 0.0f) ? eta_prev : 1.0f);
+            const float dinv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             const float wx = -dx * dinv, wy = -dy * dinv, wz = -dz * dinv;
-            const float cos_i = nx * wx + ny * wy + nz * wz;
+            const float cos_i = fmaf(nx, wx, fmaf(ny, wy, nz * wz));
             const float sin2_t = eta * eta * fmaxf(0.0f, 1.0f - cos_i * cos_i);
             if (sin2_t > 1.0f + kLensBand) return LENS_BLOCKED;
             if (!(sin2_t < 1.0f - kLensBand)) return LENS_UNSURE;
-            const float k = eta * cos_i - sqrtf(1.0f - sin2_t);
-            dx = -wx * eta + nx * k;
-            dy = -wy * eta + ny * k;
-            dz = -wz * eta + nz * k;
+            const float ct2 = 1.0f - sin2_t;
+            const float k = eta * cos_i - ct2 * rsqrtf(ct2);
+            dx = fmaf(nx, k, -wx * eta);
+            dy = fmaf(ny, k, -wy * eta);
+            dz = fmaf(nz, k, -wz * eta);
         }
     }
     return LENS_THROUGH;
@@ -241,6 +249,30 @@ RRT_HD double film_ray_weight(const CameraData& c, double r_film_dz_normalized, 
     if (c.simple_weighting) return cos4 * area / ((c.exit_pupil[0].x1 - c.exit_pupil[0].x0) * (c.exit_pupil[0].y1 - c.exit_pupil[0].y0));
     return (c.shutter_close - c.shutter_open) * (cos4 * area) / lens_rear_z(c) * lens_rear_z(c);
 }
+#if defined(__CUDACC__)
+// begin_film_ray + flip_z for the fp32 walk.  The exit-pupil slab is chosen in f64 exactly as sample_exit_pupil does
+// (Q18: a discrete choice), the rest is fp32.  *weight_nonzero = whether film_ray_weight can be non-zero for this
+// slab (it is cos^4 times a per-slab factor, and cos is far from zero for any ray the walk lets through).
+__device__ __forceinline__ RayF begin_film_ray_f32(const CameraData& c, P2 p_film_raster, P2 p_lens, bool* weight_nonzero) {
+    const P2 s = {p_film_raster.x / (double)c.xres, p_film_raster.y / (double)c.yres};
+    const double fx = -lerpd(s.x, c.physical_extent.x0, c.physical_extent.x1);
+    const double fy = lerpd(s.y, c.physical_extent.y0, c.physical_extent.y1);
+    const double r_film = sqrt(fx * fx + fy * fy);
+    uint64_t r_index = as_u64(r_film / (c.film_diagonal / 2.0)) * (uint64_t)kExitPupilSlabs;
+    if (r_index > (uint64_t)kExitPupilSlabs - 1) r_index = kExitPupilSlabs - 1;
+    const Bounds2 pb = c.exit_pupil[r_index];
+    *weight_nonzero = film_ray_weight(c, 1.0, (pb.x1 - pb.x0) * (pb.y1 - pb.y0)) != 0.0;
+    const float u = (float)p_lens.x, v = (float)p_lens.y;
+    const float lx = fmaf((float)pb.x1, u, (float)pb.x0 * (1.0f - u)), ly = fmaf((float)pb.y1, v, (float)pb.y0 * (1.0f - v));
+    const float rf = (float)r_film, ffx = (float)fx, ffy = (float)fy;
+    const float sin_t = rf != 0.0f ? __fdividef(ffy, rf) : 0.0f, cos_t = rf != 0.0f ? __fdividef(ffx, rf) : 1.0f;
+    const float rx = cos_t * lx - sin_t * ly, ry = sin_t * lx + cos_t * ly, rz = (float)lens_rear_z(c);
+    float dx = rx - ffx, dy = ry - ffy, dz = rz;
+    const float inv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    dx *= inv; dy *= inv; dz *= inv;
+    return RayF{ffx, ffy, -0.0f, dx, dy, -dz};  // flip_z: Transform::scale(1, 1, -1)
+}
+#endif
 RRT_HD void camera_ray_to_world(const CameraData& c, const RayD& r, RayD* ray) {
     // camera_to_world.t(ray) normalises d twice; generate_ray normalises it once more
     ray->o = xf_point(c.camera_to_world, r.o);

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                 if (quick && stage != GEN_MAIN) {
                     // only "through or not" is asked of a neighbour ray: the fp32 walk answers unless the ray passes
                     // within its margin of a decision boundary, in which case the f64 state machine below takes it
-                    const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, r);
+                    const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, ray_f32(r));
                     n_quick += verdict != LENS_UNSURE;
                     n_unsure += verdict == LENS_UNSURE;
                     if (verdict != LENS_UNSURE) {
@@ -489,10 +489,9 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
             bool push = false, zero = false;
             uint32_t nb = 0;
             if (fhave) {
-                RayD r_film;
-                double a;
-                begin_film_ray(cam, neighbour_film_point(fs.pf, fstage), fs.pl, &r_film, &a);
-                const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, flip_z(r_film));
+                bool weight_nonzero;
+                const RayF rf = begin_film_ray_f32(cam, neighbour_film_point(fs.pf, fstage), fs.pl, &weight_nonzero);
+                const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, rf);
                 if (verdict == LENS_UNSURE) {
                     push = true;  // undecided: the f64 procedure takes the whole sample
                     n_unsure += 1;
@@ -501,7 +500,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     else fstage = GEN_XP;
                 } else {
                     n_quick += 1;
-                    const bool ok = verdict == LENS_THROUGH && film_ray_weight(cam, normalize(r_film.d).z, a) != 0.0;
+                    const bool ok = verdict == LENS_THROUGH && weight_nonzero;
                     if (fstage == GEN_XP) {
                         fstage = ok ? GEN_YP : GEN_XM;
                     } else if (fstage == GEN_XM) {
