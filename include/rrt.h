@@ -258,6 +258,13 @@ int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, cons
  * screen-space differentials dpdx[3] dpdy[3] dudx dvdx dudy dvdy.  For the CPU test-suite.                    */
 int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3],
                            const double* diff, double* out);
+/* Host-only HaltonSampler probe (csrc/halton.cuh, the code the kernels run): for each i the sample index of
+ * (px, py, sample) (Halton::get_index_for_sample, halton.rs:75-105) and its value in dimension dim
+ * (sample_dimension, :107-128) for a film of xres x yres and the given permutation seed.  use_tables = 1 takes the
+ * table-driven paths the device takes (per-dimension constants, exact multiply-shift division, per-pixel index
+ * terms), 0 the generic digit loops: both must give the same bits.                                            */
+int rrt_halton_host_probe(int64_t xres, int64_t yres, uint64_t seed, int use_tables, uint64_t n, const int64_t* px,
+                          const int64_t* py, const uint64_t* sample, const uint32_t* dim, uint64_t* index_out, double* value_out);
 /* Host-only SurfaceInteraction::compute_differentials with the product's code (csrc/texture_core.h): in = p[3] n[3]
  * dpdu[3] dpdv[3] rx_origin[3] rx_direction[3] ry_origin[3] ry_direction[3]; out = dpdx[3] dpdy[3] dudx dvdx dudy dvdy. */
 int rrt_differentials_host_probe(const double in24[24], double out10[10]);

@@ -128,12 +128,23 @@ struct RayF {
 __device__ __forceinline__ RayF ray_f32(const RayD& r) {
     return RayF{(float)r.o.x, (float)r.o.y, (float)r.o.z, (float)r.d.x, (float)r.d.y, (float)r.d.z};
 }
-__device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, int n, RayF ray) {
+// One interface as the walk reads it: the element in fp32 with the margins folded in
+struct LensF {
+    float R, thickness, t_band, ap2_hi, ap2_lo, eta;  // eta = eta_i / eta_t of lens_step_from_film
+};
+__device__ __forceinline__ LensF lens_f32(const LensElement* el, int i) {
+    const float ap = (float)el[i].aperture_radius;
+    const double eta_prev = i > 0 ? el[i - 1].eta : 0.0;
+    return LensF{(float)el[i].curvature_radius, (float)el[i].thickness, kLensBand * ap, ap * ap * (1.0f + kLensBand),
+                 ap * ap * (1.0f - kLensBand), (float)(el[i].eta / ((i > 0 && eta_prev != 0.0) ? eta_prev : 1.0))};
+}
+__device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, RayF ray) {
     float ox = ray.ox, oy = ray.oy, oz = ray.oz, dx = ray.dx, dy = ray.dy, dz = ray.dz;
     float element_z = 0.0f;
     for (int i = n - 1; i >= 0; --i) {
-        const float R = (float)el[i].curvature_radius, ap = (float)el[i].aperture_radius;
-        element_z -= (float)el[i].thickness;
+        const LensF e = el[i];
+        const float R = e.R;
+        element_z -= e.thickness;
         if (!(fabsf(dz) > kLensBand)) return LENS_UNSURE;  // root choice and the stop's direction test hang on its sign
         float t, nx = 0.0f, ny = 0.0f, nz = 0.0f;
         if (R == 0.0f) {
@@ -155,8 +166,8 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, in
             const float ta = __fdividef(q, a), tb = __fdividef(c, q);
             const float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
             t = ((dz > 0.0f) != (R < 0.0f)) ? t0 : t1;
-            if (t < -kLensBand * ap) return LENS_BLOCKED;  // lengths are judged against the element's aperture radius
-            if (!(t > kLensBand * ap)) return LENS_UNSURE;
+            if (t < -e.t_band) return LENS_BLOCKED;  // lengths are judged against the element's aperture radius
+            if (!(t > e.t_band)) return LENS_UNSURE;
             nx = fmaf(dx, t, ox);
             ny = fmaf(dy, t, oy);
             nz = fmaf(dz, t, cz);
@@ -165,13 +176,12 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensElement* el, in
             if (fmaf(nx, dx, fmaf(ny, dy, nz * dz)) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // faceforward(n, -d)
         }
         const float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
-        const float r2 = fmaf(px, px, py * py), ap2 = ap * ap;
-        if (r2 > ap2 * (1.0f + kLensBand)) return LENS_BLOCKED;
-        if (!(r2 < ap2 * (1.0f - kLensBand))) return LENS_UNSURE;
+        const float r2 = fmaf(px, px, py * py);
+        if (r2 > e.ap2_hi) return LENS_BLOCKED;
+        if (!(r2 < e.ap2_lo)) return LENS_UNSURE;
         ox = px; oy = py; oz = pz;
         if (R != 0.0f) {
-            const float eta_prev = i > 0 ? (float)el[i - 1].eta : 0.0f;
-            const float eta = __fdividef((float)el[i].eta, (i > 0 && eta_prev != 0.0f) ? eta_prev : 1.0f);
+            const float eta = e.eta;
             const float dinv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             const float wx = -dx * dinv, wy = -dy * dinv, wz = -dz * dinv;
             const float cos_i = fmaf(nx, wx, fmaf(ny, wy, nz * wz));

@@ -16,6 +16,7 @@
 #include "aggregate.hpp"
 #include "bvh_lbvh.hpp"
 #include "bvh_hlbvh.hpp"
+#include "halton.cuh"
 #include "literal.hpp"
 #include "png_min.hpp"
 #include "render.hpp"
@@ -503,6 +504,29 @@ int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, cons
     if (!scene || (n_materials && !slots)) return fail(RRT_ERR_INVALID, "rrt_scene_set_material_textures: null argument");
     try {
         scene->material_slots.assign(slots, slots + (size_t)n_materials * RRT_MATERIAL_SLOTS);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_halton_host_probe(int64_t xres, int64_t yres, uint64_t seed, int use_tables, uint64_t n, const int64_t* px,
+                          const int64_t* py, const uint64_t* sample, const uint32_t* dim, uint64_t* index_out, double* value_out) {
+    if (n && (!px || !py || !sample || !dim || !index_out || !value_out))
+        return fail(RRT_ERR_INVALID, "rrt_halton_host_probe: null argument");
+    try {
+        rrt::HaltonTables h = rrt::make_halton_tables(xres, yres, false);
+        const std::vector<uint16_t> perms = rrt::make_halton_permutations(h, seed);
+        const std::vector<rrt::HaltonDim> dims = rrt::make_halton_dims(h, perms);
+        const std::vector<uint64_t> offs = rrt::make_halton_pixel_offsets(h);
+        if (use_tables) {
+            if (dims.empty()) return fail(RRT_ERR_INVALID, "rrt_halton_host_probe: a divider failed its check");
+            h.dims = dims.data();
+            h.pixel_off = offs.data();
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            index_out[i] = rrt::halton_index(h, px[i], py[i], sample[i]);
+            value_out[i] = rrt::halton_sample(h, perms.data(), index_out[i], dim[i]);
+        }
     } catch (const std::exception& e) {
         return fail(RRT_ERR_INVALID, e.what());
     }

@@ -19,13 +19,33 @@ constexpr int kHaltonDims = 128;  // primes 2..719; a max_depth-5 path reads few
 constexpr int64_t kMaxResolution = 128;  // halton.rs:4
 constexpr double kPow2M64 = 0.00000000000000000005421010862427522;  // lowdiscrepancy.rs:7
 
+// Per-dimension constants that the digit loops would otherwise recompute per call: 1 / base, the scrambled
+// inverse's tail term inv_base * perm[0] / (1 - inv_base) (lowdiscrepancy.rs:224-226; evaluated once on the host with
+// the same expression), and a multiply-shift pair that divides any u32 by the base exactly (checked for every base
+// when the tables are made).  Values and rounding are the generic path's: same operations in the same order.
+struct HaltonDim {
+    double inv_base, tail;
+    uint32_t magic, shift;
+};
 struct HaltonTables {
     uint32_t primes[kHaltonDims];
     uint32_t prime_sums[kHaltonDims + 1];
     int64_t base_scales[2], base_exponents[2];
     uint64_t sample_stride, mult_inverse[2];
     uint32_t sample_at_pixel_center, pad;
+    // device-side accelerators (null where they were not built: the host and the oracle-facing probes)
+    const HaltonDim* dims;      // [kHaltonDims]
+    const uint64_t* pixel_off;  // [2][kMaxResolution]: get_index_for_sample's x / y terms, reduced mod sample_stride
 };
+// n / d for any u32 n with (magic, shift) from halton_divider (the round-up method with a 33-bit multiplier)
+RRT_HD uint32_t halton_fastdiv(uint32_t n, uint32_t magic, uint32_t shift) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t q = __umulhi(magic, n);
+#else
+    const uint32_t q = (uint32_t)(((uint64_t)magic * (uint64_t)n) >> 32);
+#endif
+    return (((n - q) >> 1) + q) >> shift;
+}
 
 // lowdiscrepancy.rs:170-186
 RRT_HD uint32_t reverse_bits_32(uint32_t n) {
@@ -44,7 +64,9 @@ RRT_HD uint64_t reverse_bits_64(uint64_t n) {
 RRT_HD double radical_inverse(const HaltonTables& h, int base_index, uint64_t a) {
     if (base_index == 0) return (double)reverse_bits_64(a) * kPow2M64;
     const uint64_t base = h.primes[base_index];
-    const double inv_base = 1.0 / (double)base;
+    const bool fast = h.dims != nullptr;
+    const double inv_base = fast ? h.dims[base_index].inv_base : 1.0 / (double)base;
+    const uint32_t magic = fast ? h.dims[base_index].magic : 0u, shift = fast ? h.dims[base_index].shift : 0u;
     double inv_base_n = 1.0;
     uint64_t reversed = 0;
     while (a > 0xFFFFFFFFull) {
@@ -57,7 +79,7 @@ RRT_HD double radical_inverse(const HaltonTables& h, int base_index, uint64_t a)
     uint32_t a32 = (uint32_t)a;
     const uint32_t b32 = (uint32_t)base;
     while (a32 != 0) {
-        uint32_t next = a32 / b32, digit = a32 - next * b32;
+        uint32_t next = fast ? halton_fastdiv(a32, magic, shift) : a32 / b32, digit = a32 - next * b32;
         reversed = reversed * base + digit;
         inv_base_n *= inv_base;
         a32 = next;
@@ -67,7 +89,9 @@ RRT_HD double radical_inverse(const HaltonTables& h, int base_index, uint64_t a)
 // lowdiscrepancy.rs:206-227
 RRT_HD double scrambled_radical_inverse(const HaltonTables& h, int base_index, uint64_t a, const uint16_t* perm) {
     const uint64_t base = h.primes[base_index];
-    const double inv_base = 1.0 / (double)base;
+    const bool fast = h.dims != nullptr;
+    const double inv_base = fast ? h.dims[base_index].inv_base : 1.0 / (double)base;
+    const uint32_t magic = fast ? h.dims[base_index].magic : 0u, shift = fast ? h.dims[base_index].shift : 0u;
     double inv_base_n = 1.0;
     uint64_t reversed = 0;
     while (a > 0xFFFFFFFFull) {
@@ -79,12 +103,13 @@ RRT_HD double scrambled_radical_inverse(const HaltonTables& h, int base_index, u
     uint32_t a32 = (uint32_t)a;
     const uint32_t b32 = (uint32_t)base;
     while (a32 != 0) {
-        uint32_t next = a32 / b32, digit = a32 - next * b32;
+        uint32_t next = fast ? halton_fastdiv(a32, magic, shift) : a32 / b32, digit = a32 - next * b32;
         reversed = reversed * base + perm[digit];
         inv_base_n *= inv_base;
         a32 = next;
     }
-    return rmin(inv_base_n * ((double)reversed + inv_base * (double)perm[0] / (1.0 - inv_base)), kOneMinusEps);
+    const double tail = fast ? h.dims[base_index].tail : inv_base * (double)perm[0] / (1.0 - inv_base);
+    return rmin(inv_base_n * ((double)reversed + tail), kOneMinusEps);
 }
 // lowdiscrepancy.rs:239-248
 RRT_HD uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, uint64_t n_digits) {
@@ -104,7 +129,11 @@ RRT_HD int64_t mod_i64(int64_t a, int64_t b) {
 // Halton::get_index_for_sample (halton.rs:75-105) for sample number `sample_num` of pixel (px, py)
 RRT_HD uint64_t halton_index(const HaltonTables& h, int64_t px, int64_t py, uint64_t sample_num) {
     uint64_t off = 0;
-    if (h.sample_stride > 1) {
+    if (h.sample_stride > 1 && h.pixel_off != nullptr) {
+        // (x term + y term) % stride from the two terms already reduced: one conditional subtraction
+        off = h.pixel_off[mod_i64(px, kMaxResolution)] + h.pixel_off[kMaxResolution + mod_i64(py, kMaxResolution)];
+        if (off >= h.sample_stride) off -= h.sample_stride;
+    } else if (h.sample_stride > 1) {
         const int64_t pm[2] = {mod_i64(px, kMaxResolution), mod_i64(py, kMaxResolution)};
         // Q13: the base-2 term is reversed over base_exponents[1] digits
         off += inverse_radical_inverse(2, (uint64_t)pm[0], (uint64_t)h.base_exponents[1]) *
@@ -191,6 +220,52 @@ inline HaltonTables make_halton_tables(int64_t res_x, int64_t res_y, bool at_cen
     h.mult_inverse[1] = halton_multiplicative_inverse((uint64_t)h.base_scales[0], (uint64_t)h.base_scales[1]);
     h.sample_at_pixel_center = at_center ? 1u : 0u;
     return h;
+}
+// The two terms of get_index_for_sample (halton.rs:84-99) for every pixel residue, each reduced mod sample_stride
+inline std::vector<uint64_t> make_halton_pixel_offsets(const HaltonTables& h) {
+    std::vector<uint64_t> t(2 * (size_t)kMaxResolution, 0);
+    if (h.sample_stride <= 1) return t;
+    for (int64_t v = 0; v < kMaxResolution; ++v) {
+        t[(size_t)v] = (inverse_radical_inverse(2, (uint64_t)v, (uint64_t)h.base_exponents[1]) *
+                        (h.sample_stride / (uint64_t)h.base_scales[0]) * h.mult_inverse[0]) % h.sample_stride;
+        t[(size_t)(kMaxResolution + v)] = (inverse_radical_inverse(3, (uint64_t)v, (uint64_t)h.base_exponents[1]) *
+                                           (h.sample_stride / (uint64_t)h.base_scales[1]) * h.mult_inverse[1]) % h.sample_stride;
+    }
+    return t;
+}
+// (magic, shift) with halton_fastdiv(n, magic, shift) == n / d for every u32 n (d > 1, not a power of two)
+inline bool halton_divider(uint32_t d, uint32_t* magic, uint32_t* shift) {
+    uint32_t l = 0;
+    while ((2u << l) <= d) ++l;  // floor(log2 d)
+    const uint64_t pw = 1ull << (32 + l);
+    uint64_t m = pw / d;
+    const uint64_t rem = pw - m * d;
+    m += m;
+    const uint64_t twice = rem + rem;
+    if (twice >= d) m += 1;
+    *magic = (uint32_t)(m + 1);
+    *shift = l;
+    // checked, not trusted: the ends of the range, every multiple boundary near them, and a pseudo-random sweep
+    uint64_t x = 88172645463325252ull;
+    for (int k = 0; k < 4096; ++k) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const uint32_t tests[4] = {(uint32_t)x, (uint32_t)(((uint32_t)x / d) * d), (uint32_t)(((uint32_t)x / d) * d - 1u), 0xFFFFFFFFu - (uint32_t)k};
+        for (uint32_t n : tests)
+            if (halton_fastdiv(n, *magic, *shift) != n / d) return false;
+    }
+    return true;
+}
+// The HaltonDim table for these permutations; an empty vector if any divider failed its check (generic path then)
+inline std::vector<HaltonDim> make_halton_dims(const HaltonTables& h, const std::vector<uint16_t>& perms) {
+    std::vector<HaltonDim> t(kHaltonDims);
+    for (int i = 0; i < kHaltonDims; ++i) {
+        const double inv_base = 1.0 / (double)h.primes[i];
+        t[i].inv_base = inv_base;
+        t[i].tail = inv_base * (double)perms[h.prime_sums[i]] / (1.0 - inv_base);
+        t[i].magic = t[i].shift = 0;
+        if (i > 0 && !halton_divider(h.primes[i], &t[i].magic, &t[i].shift)) return {};
+    }
+    return t;
 }
 // compute_radical_inverse_permutations (lowdiscrepancy.rs:250-270) with the seeded generator
 inline std::vector<uint16_t> make_halton_permutations(const HaltonTables& h, uint64_t seed) {

@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     const unsigned lane = threadIdx.x & 31u;
     // lens table in shared memory: lanes index it at different interfaces (a constant-bank read would serialise)
     __shared__ LensElement s_el[kMaxLensElements];
-    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_el[k] = cam.el[k];
+    __shared__ LensF s_lf[kMaxLensElements];
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) {
+        s_el[k] = cam.el[k];
+        s_lf[k] = lens_f32(cam.el, k);
+    }
     __syncthreads();
     uint32_t* const cursor = q.counters + 3;
 
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                 if (quick && stage != GEN_MAIN) {
                     // only "through or not" is asked of a neighbour ray: the fp32 walk answers unless the ray passes
                     // within its margin of a decision boundary, in which case the f64 state machine below takes it
-                    const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, ray_f32(r));
+                    const int verdict = lens_walk_from_film_f32(s_lf, cam.n_elements, ray_f32(r));
                     n_quick += verdict != LENS_UNSURE;
                     n_unsure += verdict == LENS_UNSURE;
                     if (verdict != LENS_UNSURE) {
@@ -424,7 +428,11 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
     __shared__ LensElement s_el[kMaxLensElements];
     __shared__ GenSample s_queue[4][kGenQueue];
     __shared__ GenSample s_screen[128], s_trace[128];  // the sample a lane is screening / tracing
-    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_el[k] = cam.el[k];
+    __shared__ LensF s_lf[kMaxLensElements];
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) {
+        s_el[k] = cam.el[k];
+        s_lf[k] = lens_f32(cam.el, k);
+    }
     __syncthreads();
     GenSample* const wq = s_queue[threadIdx.x >> 5];
     GenSample& fs = s_screen[threadIdx.x];
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
             if (fhave) {
                 bool weight_nonzero;
                 const RayF rf = begin_film_ray_f32(cam, neighbour_film_point(fs.pf, fstage), fs.pl, &weight_nonzero);
-                const int verdict = lens_walk_from_film_f32(s_el, cam.n_elements, rf);
+                const int verdict = lens_walk_from_film_f32(s_lf, cam.n_elements, rf);
                 if (verdict == LENS_UNSURE) {
                     push = true;  // undecided: the f64 procedure takes the whole sample
                     n_unsure += 1;
@@ -1299,6 +1307,17 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         int rc = I.up(perms, &dp, err);
         if (rc != RRT_OK) return rc;
         I.d_perms = const_cast<uint16_t*>(dp);
+        // per-dimension constants and per-pixel index terms (csrc/halton.cuh): same values, fewer instructions.
+        // RRT_HALTON_TABLES=0 keeps the generic digit loops (the A/B switch of the parity test)
+        const char* e = std::getenv("RRT_HALTON_TABLES");
+        if (!(e && std::atoi(e) == 0)) {
+            const std::vector<HaltonDim> dims = make_halton_dims(I.ht, perms);
+            const std::vector<uint64_t> offs = make_halton_pixel_offsets(I.ht);
+            if (!dims.empty()) {
+                if ((rc = I.up(dims, &I.ht.dims, err)) != RRT_OK) return rc;
+                if ((rc = I.up(offs, &I.ht.pixel_off, err)) != RRT_OK) return rc;
+            }
+        }
     }
 
     // ---- Camera (camera.rs:66-135) ----

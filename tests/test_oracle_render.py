@@ -289,3 +289,32 @@ def test_area_light_scene_renders_and_the_bsdf_half_is_dead(tmp_path):
     # Tier L renders too (Q9 shadow rays towards the sampled point)
     r3 = S.load(path, tier=O.TIER_L).render(seed=1)
     assert np.isfinite(r3["rgb"]).all()
+
+
+def test_halton_tables_are_the_digit_loops():
+    """The device draws Halton samples through per-dimension tables (1 / base, the scrambled tail term, an exact
+    multiply-shift division) and per-pixel index terms (csrc/halton.cuh).  On the host the same code must give the
+    generic digit loops' bits for every dimension, with 32- and 64-bit indices, on the films of configs 1, 4 and 5."""
+    import ctypes as C
+    from rs_ray_toy_b200 import capi
+    L = capi.lib()
+    L.rrt_halton_host_probe.restype = C.c_int
+    L.rrt_halton_host_probe.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_uint64] + [C.c_void_p] * 6
+    rng = np.random.default_rng(3)
+    for (xres, yres, spp) in ((640, 360, 17), (1920, 1080, 65), (3840, 2160, 257)):
+        n = 20000
+        px = rng.integers(-2, xres + 2, n).astype(np.int64)
+        py = rng.integers(-2, yres + 2, n).astype(np.int64)
+        sm = rng.integers(0, spp, n).astype(np.uint64)
+        sm[:50] = 1 << 40                       # indices beyond 32 bits take the 64-bit digit loop first
+        dim = rng.integers(0, 128, n).astype(np.uint32)
+        dim[:128] = np.arange(128)
+        outs = []
+        for tables in (0, 1):
+            idx, val = np.zeros(n, dtype=np.uint64), np.zeros(n)
+            capi.check(L.rrt_halton_host_probe(xres, yres, 7, tables, n, px.ctypes.data, py.ctypes.data, sm.ctypes.data,
+                                               dim.ctypes.data, idx.ctypes.data, val.ctypes.data))
+            outs.append((idx, val))
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1], outs[1][1])
+        assert 0.0 <= outs[1][1].min() and outs[1][1].max() < 1.0 and len(np.unique(outs[1][1])) > n // 2
