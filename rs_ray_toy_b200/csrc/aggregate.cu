@@ -25,6 +25,7 @@
 #include "aggregate.hpp"
 #include "bvh_lbvh.hpp"
 #include "device_layout.h"
+#include "sphere_core.cuh"
 
 namespace rrt {
 
@@ -248,6 +249,15 @@ __device__ __noinline__ bool prepare_ray(const AggView& A, D3 o, D3 d, double t_
     return true;
 }
 
+// Partial spheres and spheres under non-rigid transforms: the whole of Sphere::intersect in object space
+// (sphere_core.cuh).  Out of line: scenes without such spheres never pay for it.
+__device__ __noinline__ bool general_sphere_test(const AggView& A, double index, D3 o, D3 d, double t_far, double* t) {
+    const GenSphere& g = static_cast<const GenSphere*>(A.gspheres)[(uint32_t)index];
+    V3 p;
+    double phi;
+    return gen_sphere_hit(g, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), t_far, t, &p, &phi);
+}
+
 // Surface parameters of the winning record.  Sphere hit, sphere.rs:157-198 for a full sphere: the hit point is taken
 // on the ray the shape was handed (the instance-space ray, Q5a), phi = atan2(y, x) wrapped to
 // [0, 2pi), u = phi / phi_max, v = (theta - theta_min) / (theta_max - theta_min) with
@@ -262,6 +272,15 @@ __device__ __noinline__ void hit_params(const AggView& A, uint32_t rec, D3 o, D3
         // the same operations, hence the same bits (triangle.rs:245-256)
         double tt;
         tri_test(o, d, a, b, c, &tt, u, v);
+        return;
+    }
+    if (kind == PRIM_SPHERE_GENERAL) {
+        // replay the accepted hit (t_far = t reproduces the walk's root and clipping decisions) for its point
+        const GenSphere& g = static_cast<const GenSphere*>(A.gspheres)[(uint32_t)a.x];
+        V3 p;
+        double phi, tt;
+        *u = *v = 0.0;
+        if (gen_sphere_hit(g, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), t, &tt, &p, &phi)) gen_sphere_uv(g, p, phi, u, v);
         return;
     }
     if (!WIDE) inst = static_cast<const PrimRec48*>(A.prims)[rec].words[8];
@@ -343,7 +362,9 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 constexpr int kRefill = RRT_REFILL;
 
 
-template <bool ANY, bool WIDE, bool QUANT>
+// GEN: the scene holds spheres that need the object-space test (PRIM_SPHERE_GENERAL); every other scene runs the
+// instantiation without that branch, whose register allocation is the measured one.
+template <bool ANY, bool WIDE, bool QUANT, bool GEN>
 __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) trace_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
                                                         rrt_hit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                         const uint32_t* __restrict__ perm,
@@ -599,8 +620,10 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                     bool hit;
                     if (kind == PRIM_TRIANGLE) {
                         hit = tri_test(o, d, a, b, c, &t, &u, &v) && !(t > best_t);
-                    } else {
+                    } else if (!GEN || kind == PRIM_SPHERE) {
                         hit = sphere_test(o, d, a, b.x, best_t, &t);
+                    } else {
+                        hit = general_sphere_test(A, a.x, o, d, best_t, &t);
                     }
                     if (hit) {
                         if (ANY) {
@@ -865,6 +888,7 @@ DeviceAggregate::~DeviceAggregate() {
     if (d_nodes_) cudaFree(d_nodes_);
     if (d_prims_) cudaFree(d_prims_);
     if (d_inst_) cudaFree(d_inst_);
+    if (d_gspheres_) cudaFree(d_gspheres_);
     Workspace& w = ws_;
     if (w.d_bins) cudaFree(w.d_bins);
     if (w.d_block_sums) cudaFree(w.d_block_sums);
@@ -900,7 +924,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     };
     std::vector<World> world(n);
     std::vector<Aabb> boxes(n);
-    std::atomic<int> not_fp32{0}, bad_partial{0}, bad_scaled{0};
+    std::atomic<int> not_fp32{0};
+    std::vector<uint8_t> general(n, 0);  // spheres that need the object-space test (sphere_core.cuh)
     parallel_ranges(n, [&](size_t i0, size_t i1) {
     bool all_fp32 = true;
     for (size_t i = i0; i < i1; ++i) {
@@ -911,8 +936,22 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             if (all_fp32 && !fp32_exact(world[i].v, 9)) all_fp32 = false;
         } else {
             const Sphere& s = scene.spheres[pr.shape];
+            auto general_sphere = [&]() {
+                // box of the object-space extent [-r, r]^2 x [z_min, z_max] (Sphere::object_bound, sphere.rs:262-268)
+                // carried to world space corner by corner; the GenSphere entry itself is made after this loop
+                general[i] = 1;
+                const double zl = std::fmax(std::fmin(s.z_min, s.z_max), -s.radius), zh = std::fmin(std::fmax(s.z_min, s.z_max), s.radius);
+                for (int k = 0; k < 8; ++k) {
+                    Vec3d q = s.obj_to_world.point(Vec3d{(k & 1) ? s.radius : -s.radius, (k & 2) ? s.radius : -s.radius, (k & 4) ? zh : zl});
+                    if (pr.instance >= 0) q = scene.instances[pr.instance].point(q);
+                    const double pad = 1e-12 * (std::fabs(q.x) + std::fabs(q.y) + std::fabs(q.z) + s.radius);
+                    const double lo[3] = {q.x - pad, q.y - pad, q.z - pad}, hi[3] = {q.x + pad, q.y + pad, q.z + pad};
+                    boxes[i].grow(lo);
+                    boxes[i].grow(hi);
+                }
+            };
             if (!s.is_full()) {
-                bad_partial = 1;
+                general_sphere();
                 continue;
             }
             // world centre; the instance / object transforms must be rigid (unit scale)
@@ -931,7 +970,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             double tol = 1e-9;
             if (std::fabs(len(ex) - 1) > tol || std::fabs(len(ey) - 1) > tol || std::fabs(len(ez) - 1) > tol ||
                 std::fabs(dt(ex, ey)) > tol || std::fabs(dt(ex, ez)) > tol || std::fabs(dt(ey, ez)) > tol) {
-                bad_scaled = 1;
+                general_sphere();
                 continue;
             }
             world[i].v[0] = c.x;
@@ -951,13 +990,28 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     }
     if (!all_fp32) not_fp32 = 1;
     });
-    if (bad_partial) {
-        if (err) *err = "partial spheres (z_min/z_max/phi_max) are not on the Tier-F device path yet";
-        return RRT_ERR_UNSUPPORTED;
-    }
-    if (bad_scaled) {
-        if (err) *err = "scaled / sheared sphere instances are not on the Tier-F device path yet";
-        return RRT_ERR_UNSUPPORTED;
+    std::vector<GenSphere> gspheres;
+    for (size_t i = 0; i < n; ++i) {
+        if (!general[i]) continue;
+        const Primitive& pr = scene.prims[i];
+        const Sphere& s = scene.spheres[pr.shape];
+        GenSphere g{};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) {
+                g.inst_inv.m[4 * r + c] = pr.instance >= 0 ? scene.instances[pr.instance].inv.m[r][c] : (r == c ? 1.0 : 0.0);
+                g.w2o.m[4 * r + c] = s.obj_to_world.inv.m[r][c];
+            }
+        // Sphere::new (sphere.rs:28-47)
+        const double kPiD = 3.14159265358979323846264338327950288;
+        g.clip.radius = s.radius;
+        g.clip.z_min = s.z_min;
+        g.clip.z_max = s.z_max;
+        g.theta_min = std::acos(std::fmin(std::fmax(std::fmin(s.z_min, s.z_max) / s.radius, -1.0), 1.0));
+        g.theta_max = std::acos(std::fmin(std::fmax(std::fmax(s.z_min, s.z_max) / s.radius, -1.0), 1.0));
+        g.clip.phi_max = std::fmin(std::fmax(s.phi_max_deg, 0.0), 360.0) * (kPiD / 180.0);
+        world[i].v[0] = (double)gspheres.size();
+        world[i].v[3] = s.radius;
+        gspheres.push_back(g);
     }
     const bool all_fp32 = not_fp32 == 0;
     lap("bake to world space");
@@ -1041,7 +1095,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                 std::memset(&r, 0, sizeof(r));
                 std::memcpy(r.v, world[pi].v, sizeof(double) * 9);
                 r.prim_id = pi;
-                r.kind = pr.kind == SHAPE_TRIANGLE ? PRIM_TRIANGLE : PRIM_SPHERE;
+                r.kind = pr.kind == SHAPE_TRIANGLE ? PRIM_TRIANGLE : (general[pi] ? PRIM_SPHERE_GENERAL : PRIM_SPHERE);
                 r.pad[0] = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
                 rec96[slot] = r;
             } else {
@@ -1059,7 +1113,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                     for (int j = 0; j < 3; ++j) r.sph.c[j] = world[pi].v[j];
                     r.sph.radius = world[pi].v[3];
                     r.sph.prim_id = pi;
-                    r.sph.kind = PRIM_SPHERE;
+                    r.sph.kind = general[pi] ? PRIM_SPHERE_GENERAL : PRIM_SPHERE;
                     r.sph.instance = pr.instance >= 0 ? (uint32_t)pr.instance : 0xFFFFFFFFu;
                 }
                 rec48[slot] = r;
@@ -1196,6 +1250,11 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         RRT_CUDA(cudaMalloc(&d_inst_, w2p.size() * sizeof(double)));
         RRT_CUDA(cudaMemcpy(d_inst_, w2p.data(), w2p.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (!gspheres.empty()) {
+        RRT_CUDA(cudaMalloc(&d_gspheres_, gspheres.size() * sizeof(GenSphere)));
+        RRT_CUDA(cudaMemcpy(d_gspheres_, gspheres.data(), gspheres.size() * sizeof(GenSphere), cudaMemcpyHostToDevice));
+    }
+    view_.gspheres = d_gspheres_;
     lap("upload");
     // Optional (RRT_L2_PERSIST=1): a persisting L2 access-policy window over the nodes, against the ray / hit
     // streams that pass through L2 (1.5 GB per 16 Mi-ray batch).  Measured: no gain (1443 vs 1466 Mrays/s,
@@ -1249,10 +1308,14 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
     int carve = (int)(((quantise ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
-    for (auto fn : {(const void*)trace_kernel<false, false, false>, (const void*)trace_kernel<false, true, false>,
-                    (const void*)trace_kernel<true, false, false>, (const void*)trace_kernel<true, true, false>,
-                    (const void*)trace_kernel<false, false, true>, (const void*)trace_kernel<false, true, true>,
-                    (const void*)trace_kernel<true, false, true>, (const void*)trace_kernel<true, true, true>}) {
+    for (auto fn : {(const void*)trace_kernel<false, false, false, false>, (const void*)trace_kernel<false, true, false, false>,
+                    (const void*)trace_kernel<true, false, false, false>, (const void*)trace_kernel<true, true, false, false>,
+                    (const void*)trace_kernel<false, false, true, false>, (const void*)trace_kernel<false, true, true, false>,
+                    (const void*)trace_kernel<true, false, true, false>, (const void*)trace_kernel<true, true, true, false>,
+                    (const void*)trace_kernel<false, false, false, true>, (const void*)trace_kernel<false, true, false, true>,
+                    (const void*)trace_kernel<true, false, false, true>, (const void*)trace_kernel<true, true, false, true>,
+                    (const void*)trace_kernel<false, false, true, true>, (const void*)trace_kernel<false, true, true, true>,
+                    (const void*)trace_kernel<true, false, true, true>, (const void*)trace_kernel<true, true, true, true>}) {
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
@@ -1318,8 +1381,11 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
                                                n_dev);
         count += 4;
     }
-    auto kernel = view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true> : trace_kernel<ANY, false, true>)
-                                  : (view_.wide ? trace_kernel<ANY, true, false> : trace_kernel<ANY, false, false>);
+    auto kernel = view_.gspheres != nullptr
+                      ? (view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true, true> : trace_kernel<ANY, false, true, true>)
+                                         : (view_.wide ? trace_kernel<ANY, true, false, true> : trace_kernel<ANY, false, false, true>))
+                      : (view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true, false> : trace_kernel<ANY, false, true, false>)
+                                         : (view_.wide ? trace_kernel<ANY, true, false, false> : trace_kernel<ANY, false, false, false>));
     const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
     int per_sm = 0;
     RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));

@@ -23,6 +23,7 @@ struct AggView {
     const void* nodes;   // Node64[]
     const void* prims;   // PrimRec48[] or PrimRec96[]
     const double* inst_w2p;  // world->primitive 3x4 (row-major f64) per instance; sphere (u,v) only
+    const void* gspheres;    // GenSphere[] (sphere_core.cuh): partial spheres and spheres under non-rigid transforms
     double world_lo[3];  // tight world box of the tree, used to pull far-away origins close
     double world_hi[3];
     double scene_scale;  // max |coordinate| of the world box
@@ -106,6 +107,7 @@ class DeviceAggregate : public RayTracer {
     void* d_nodes_ = nullptr;
     void* d_prims_ = nullptr;
     void* d_inst_ = nullptr;
+    void* d_gspheres_ = nullptr;
     int device_ = 0;
 };
 

@@ -54,11 +54,13 @@ inline
 }
 
 // Primitive record kinds (first word of the last 16-byte lane).
-enum : uint32_t { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1 };
+// PRIM_SPHERE_GENERAL: c[0] holds the index of the sphere's GenSphere entry (sphere_core.cuh) instead of a centre.
+enum : uint32_t { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_SPHERE_GENERAL = 2 };
 
 // 48 B primitive record, stored in leaf order so that a leaf is one contiguous run.
 //   triangle : v0,v1,v2 as fp32 (bit-exact copies of f64 inputs that are fp32-representable)
-//   sphere   : centre (3 x f64) + radius (f64) — world space, rigid instances only
+//   sphere   : centre (3 x f64) + radius (f64) — world space, full spheres under rigid transforms;
+//              any other sphere: the index of its GenSphere entry in c[0]
 // Tail: prim_id (index in the caller's primitive list) and kind.
 struct RRT_ALIGN(16) PrimRec48 {
     union {

@@ -85,6 +85,9 @@ inline int upload_geometry_tables(const HostScene& scene, ShadeScene* S, std::ve
         si.theta_min = std::acos(clampd(std::fmin(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
         si.theta_max = std::acos(clampd(std::fmax(s.z_min, s.z_max) / s.radius, -1.0, 1.0));
         si.phi_max = clampd(s.phi_max_deg, 0.0, 360.0) * (kPi / 180.0);
+        si.z_min = s.z_min;
+        si.z_max = s.z_max;
+        si.partial = s.is_full() ? 0u : 1u;
         spheres[i] = si;
     }
     std::vector<InstanceXf> inst(scene.instances.size());

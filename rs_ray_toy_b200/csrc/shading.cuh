@@ -19,6 +19,7 @@
 #define RRT_SHADE_FN static __device__
 #endif
 #include "rmath.cuh"
+#include "sphere_core.cuh"
 #include "texture_core.h"
 
 namespace rrt {
@@ -39,6 +40,8 @@ struct MeshInfo {
 struct SphereInfo {
     M34 o2w, w2o;
     double radius, theta_min, theta_max, phi_max;
+    double z_min, z_max;
+    uint32_t partial, pad;  // z_min / z_max / phi_max clip the sphere: the hit point depends on which root was taken
 };
 struct InstanceXf {
     M34 m, inv;
@@ -200,6 +203,17 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         if (p.x == 0.0 && p.y == 0.0) p.x = 1e-5 * sp.radius;
         double phi = atan2(p.y, p.x);
         if (phi < 0.0) phi += 2.0 * kPi;
+        if (sp.partial && !sc.literal) {
+            // a clipped sphere may have been hit at its far root, whose point is taken on the object-space ray and
+            // re-projected (sphere.rs:171-186): replay the accepted hit (t_far = t reproduces the decisions)
+            const SphereClip clip = {sp.radius, sp.z_min, sp.z_max, sp.phi_max};
+            V3 q;
+            double tt, f;
+            if (sphere_hit_local(sp.w2o, clip, lo, ld, t, &tt, &q, &f)) {
+                p = q;
+                phi = f;
+            }
+        }
         const double theta = acos(clampd(p.z / sp.radius, -1.0, 1.0));
         const double z_radius = sqrt(p.x * p.x + p.y * p.y);
         const double inv_z_radius = 1.0 / z_radius;

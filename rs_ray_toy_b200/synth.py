@@ -355,6 +355,52 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
     return path
 
 
+def scene_clipped_spheres(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
+    """SURVEY.md §8a6 in the renderer: config 1's floor-less cubes swapped for spheres that are clipped in z and phi
+    (bowls and wedges whose inside is seen through the opening: hits at the far root), stretched by their own object
+    transform and by their instances, with uv-driven textures so that the hit point's (u, v) shows."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    cfg = json.loads(open(scene_c1(directory, xres=xres, yres=yres, nsamp=nsamp, integrator=integrator, max_depth=max_depth)).read())
+    cfg["rgb_texture"] = [
+        _const_rgb_texture("white", (0.85, 0.85, 0.8)),
+        _const_rgb_texture("blue", (0.1, 0.2, 0.6)),
+        {"texture_name": "check", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "white", "t2": "blue",
+         "mapping": {"mapping": "uv", "su": 8.0, "sv": 4.0, "du": 0.0, "dv": 0.0}},
+        {"texture_name": "uvcol", "texture_type": "UVTexture"},
+    ]
+    cfg["float_texture"] = []
+    cfg["materials"] = [
+        {"material_type": "MatteMaterial", "material_name": "m_check", "kd": "check"},
+        {"material_type": "PlasticMaterial", "material_name": "m_uv", "kd": "uvcol", "roughness": 0.2},
+        {"material_type": "MetalMaterial", "material_name": "m_metal"},
+    ]
+    cfg["Aggregate"]["primitives"] = [
+        # a bowl (lower part of a sphere), opening towards the camera side, stretched by its instance
+        {"primitive_type": "sphere", "radius": 1.6, "z_min": -1.6, "z_max": 0.3, "material_name": "m_check",
+         "instances": [{"world_pos": [35.0, 0.5, 2.6], "rotation_axis": [1.0, 0.2, 0.0], "rotation_angle": 70, "scale": [1.0, 1.0, 1.3]}]},
+        # a wedge: three quarters of a sphere in phi, the object transform of the sphere itself non-uniform
+        {"primitive_type": "sphere", "radius": 1.2, "phi_max": 250.0, "material_name": "m_uv",
+         "world_pos": [0.0, 0.0, 0.0], "scale": [1.0, 0.7, 1.0],
+         "instances": [{"world_pos": [35.4, -0.2, -0.6], "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 200},
+                       {"world_pos": [33.0, 2.4, -3.2], "rotation_axis": [0.3, 1.0, 0.2], "rotation_angle": 40, "scale": [0.8, 0.8, 0.8]}]},
+        # a band (both poles cut away), not instanced: its own transform carries it into the scene (Q5a applies)
+        {"primitive_type": "sphere", "radius": 1.0, "z_min": -0.5, "z_max": 0.5, "phi_max": 300.0, "material_name": "m_metal",
+         "world_pos": [36.5, -0.8, -3.4], "rotation_axis": [1.0, 0.0, 0.0], "rotation_angle": 90},
+        # and one ordinary full sphere
+        {"primitive_type": "sphere", "radius": 0.8, "material_name": "m_check", "instances": [{"world_pos": [33.5, -1.2, 1.0]}]},
+    ]
+    cfg["objs"] = []
+    cfg["lights"] = [
+        {"light_type": "distant", "l": {"values": [2.5, 2.4, 2.2]}, "from": [-0.4, 1.0, -0.6], "to": [0, 0, 0]},
+        {"light_type": "point", "spectrum": {"values": [900, 900, 900]}}]
+    path = os.path.join(directory, "scene_clipped.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_c2(directory, n_instances=10000, xres=1920, yres=1080, nsamp=2, extent=50.0, seed=SEED_C2_INSTANCES):
     """Config 2: the cube instanced `n_instances` times (random position / axis / angle, unit scale),
     Matte, one point light (which sits at the origin whatever its world_pos, Q17), DirectLighting

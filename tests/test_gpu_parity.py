@@ -9,8 +9,9 @@ import numpy as np
 import pytest
 
 import golden_cases
+import oracle_lib as O
 import scenes
-from rs_ray_toy_b200 import synth
+from rs_ray_toy_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
@@ -476,3 +477,84 @@ def test_device_lbvh_duplicates_and_a_tree_too_deep_for_the_stack(ctx):
     agg = scenes.gpu_soup(ctx, p, idx, 4, capi.RRT_BUILD_DEVICE_LBVH)
     _assert_closest(agg.intersect(rays), ref["prim"], ref["t"])
     assert agg.stats()["max_depth"] + 2 <= 64
+
+
+def _general_sphere_scene(ctx, tier_scene):
+    """Spheres that need Sphere::intersect in full (sphere.rs:124-259): clipped in z and in phi, under their own
+    translated / rotated / non-uniformly scaled object transform, bare and instanced (instances with scale too),
+    next to ordinary full spheres.  Built identically on both sides; prim ids follow insertion order."""
+    from rs_ray_toy_b200 import transform as T
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    rng = np.random.default_rng(21)
+    shapes = []
+    for k in range(40):
+        radius = float(rng.uniform(0.4, 1.2))
+        kind = k % 5
+        z_min, z_max, phi_max = -radius, radius, 360.0
+        if kind in (0, 1, 4):
+            z_min, z_max = sorted((float(rng.uniform(-radius, 0.2 * radius)), float(rng.uniform(0.3 * radius, radius))))
+        if kind in (1, 2, 4):
+            phi_max = float(rng.uniform(60.0, 330.0))
+        scale = (1.0, 1.0, 1.0) if kind in (0, 2) else tuple(rng.uniform(0.6, 1.8, 3))
+        o2w = T.make_to_world(rng.uniform(-6, 6, 3), rng.normal(0, 1, 3), float(rng.uniform(0, 360)), scale)
+        inst = None
+        if k % 2 == 0:
+            ms, invs = [], []
+            for _ in range(3):
+                m, inv = T.make_to_world(rng.uniform(-8, 8, 3), rng.normal(0, 1, 3), float(rng.uniform(0, 360)),
+                                         tuple(rng.uniform(0.7, 1.4, 3)) if kind != 0 else (1.0, 1.0, 1.0))
+                ms.append(m)
+                invs.append(inv)
+            inst = (np.array(ms), np.array(invs))
+        shapes.append((radius, z_min, z_max, phi_max, o2w, inst))
+    a = GpuAggregate(ctx)
+    s = O.OracleScene(tier_scene)
+    for (radius, z_min, z_max, phi_max, o2w, inst) in shapes:
+        a.add_sphere(radius=radius, z_min=z_min, z_max=z_max, phi_max=phi_max, obj_to_world=o2w, instances=inst)
+        g = s.add_geo_sphere(s.add_sphere(o2w[0], o2w[1], radius, z_min, z_max, phi_max))
+        if inst is None:
+            s.add_prims(g, 1, -1)
+        else:
+            for i in range(inst[0].shape[0]):
+                s.add_prims(g, 1, s.add_xform(inst[0][i], inst[1][i]))
+    # ordinary full spheres through rigid instances keep the world-space fast path in the same tree
+    m, inv = scenes.sphere_instances(200, extent=9.0)
+    a.add_sphere(radius=0.5, instances=(m, inv))
+    g = s.add_geo_sphere(s.add_sphere(None, None, 0.5))
+    for i in range(m.shape[0]):
+        s.add_prims(g, 1, s.add_xform(m[i], inv[i]))
+    return a, s
+
+
+@pytest.mark.parametrize("flags", [0, "lbvh"])
+def test_partial_and_scaled_spheres(ctx, flags):
+    """SURVEY §8a6 in full: z / phi clipping with the retry at the far root, any affine object and instance transform
+    (Tier F: one parameter t through all spaces), Q5a kept — closest hit, (u, v) and any-hit against the oracle."""
+    build = capi.RRT_BUILD_DEVICE_LBVH if flags == "lbvh" else capi.RRT_BUILD_FAST
+    a, s = _general_sphere_scene(ctx, O.TIER_F)
+    a.commit(4, build)
+    s.build(4)
+    rng = np.random.default_rng(8)
+    n = 200000
+    o = rng.uniform(-14, 14, (n, 3))
+    tgt = rng.uniform(-9, 9, (n, 3))
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    rays = np.concatenate([o, d, np.full((n, 1), np.inf)], axis=1)
+    rays[: n // 4, 6] = rng.uniform(2.0, 20.0, n // 4)       # finite t_max too
+    ref = s.intersect(rays)
+    hits = a.intersect(rays)
+    c = _assert_closest(hits, ref["prim"], ref["t"], ref["uv"])
+    assert c["hits"] > n // 10, c
+    # the clipped shapes are really clipped: a fair share of rays passes through a sphere's removed part
+    occ_ref, _ = s.intersect_p(rays)
+    assert (a.intersect_p(rays) == occ_ref).all()
+    # rays leaving the surfaces (inside and outside: the far root and the self-hit floor, Q8)
+    hit = ref["prim"] >= 0
+    p = rays[hit, 0:3] + rays[hit, 3:6] * ref["t"][hit, None]
+    d2 = synth.random_unit_vectors(p.shape[0], rng)
+    sec = np.concatenate([p, d2, np.full((p.shape[0], 1), np.inf)], axis=1)
+    r2 = s.intersect(sec)
+    _assert_closest(a.intersect(sec), r2["prim"], r2["t"], r2["uv"])
+    occ2, _ = s.intersect_p(sec)
+    assert (a.intersect_p(sec) == occ2).all()

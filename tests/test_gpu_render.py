@@ -311,3 +311,20 @@ def test_f32_lens_walks_change_nothing(ctx, tmp_path, monkeypatch):
             assert s0["extension_rays"] == s1["extension_rays"] and s0["shadow_rays"] == s1["shadow_rays"], (flag, s0, s1)
             assert np.array_equal(d0, d1), flag   # pixel, sample, first primitive, t and weight of every camera sample
             assert np.allclose(f0, f1, rtol=1e-12, atol=0), flag
+
+
+@pytest.mark.parametrize("integrator", ["Path", "DirectLighting"])
+def test_clipped_and_stretched_spheres(ctx, tmp_path, integrator):
+    """SURVEY §8a6 through the renderer: spheres clipped in z / phi (their inside seen through the opening: hits at the
+    far root, whose point comes from the object-space ray), under non-uniform object and instance transforms, with
+    uv-driven textures.  First hits bit-equal, film to rounding."""
+    path = synth.scene_clipped_spheres(str(tmp_path / "s"), xres=256, yres=144, nsamp=9, integrator=integrator,
+                                       max_depth=5 if integrator == "Path" else 1)
+    ref = S.load(path).render(seed=1, want_dump=True)
+    gpu = Render.load(ctx, path, seed=1)
+    gpu.enable_hit_dump()
+    gpu.run()
+    out = compare(gpu, ref)
+    assert out["rmse"] < 1e-4, out
+    hit = ref["dump"][:, 3] >= 0
+    assert hit.sum() > 0.05 * hit.shape[0]
