@@ -33,6 +33,7 @@ Quirks quirks_from_mask(uint32_t mask) {
     q.fix_q6 = mask & 32u;
     q.fix_q8 = mask & 64u;
     q.fix_q9 = mask & 128u;
+    q.fix_q5c = mask & 256u;
     return q;
 }
 struct Scene {
@@ -61,7 +62,7 @@ extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
 
-// quirk_mask: bit i set = fix Q(1,2,3,4,5b,6,8,9)[i]; 0 = literal reference, 0xFF = Tier F.
+// quirk_mask: bit i set = fix Q(1,2,3,4,5b,6,8,9,5c)[i]; 0 = literal reference, 0x1FF = Tier F.
 void* orc_scene_new(uint32_t quirk_mask) {
     Scene* s = new Scene();
     s->geom.q = quirks_from_mask(quirk_mask);

@@ -327,6 +327,12 @@ bool Geometry::sph_intersect_p(const GeoPrim& g, const Ray& r) const {
         ts = t1;
         if (ts > far) return false;
     }
+    if (q.fix_q5c) {  // what Sphere::intersect does at this point (sphere.rs:157-164)
+        p_hit = r.at(ts);
+        if (p_hit.x == 0.0 && p_hit.y == 0.0) p_hit.x = 1e-5 * s.radius;
+        phi = std::atan2(p_hit.y, p_hit.x);
+        if (phi < 0.0) phi += 2.0 * PI;
+    }
     if (sphere_clipped(s, p_hit, phi)) {
         if (ts == t1) return false;
         if (t1 > far) return false;

@@ -21,10 +21,15 @@ struct Quirks {
     bool fix_q6 = false;   // instance ray transform does not renormalise d (transform.rs:525-537)
     bool fix_q8 = false;   // sphere roots below 1e-7*max(1,radius) are rejected (self-hit policy)
     bool fix_q9 = false;   // shadow ray reaches the light: t_max = 1-1e-4 on the UNnormalised segment
+    // Sphere::intersect_p clips the first root against an UNINITIALISED hit point (p_hit = 0, phi = 0: sphere.rs:52-53,
+    // 78-81), so a clipped sphere shadows like a full one wherever z = 0 is inside its slab — at points outside the
+    // shape's bound, which the BVH reaches only when the ray happens to cross the leaf's box.  Fixed = the clip test of
+    // Sphere::intersect (the point on the ray the shape was handed, Q5a kept)
+    bool fix_q5c = false;
     static Quirks literal() { return Quirks{}; }
     static Quirks tier_f() {
         Quirks q;
-        q.fix_q1 = q.fix_q2 = q.fix_q3 = q.fix_q4 = q.fix_q5b = q.fix_q6 = q.fix_q8 = q.fix_q9 = true;
+        q.fix_q1 = q.fix_q2 = q.fix_q3 = q.fix_q4 = q.fix_q5b = q.fix_q6 = q.fix_q8 = q.fix_q9 = q.fix_q5c = true;
         return q;
     }
 };

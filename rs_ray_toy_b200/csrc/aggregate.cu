@@ -924,7 +924,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     };
     std::vector<World> world(n);
     std::vector<Aabb> boxes(n);
-    std::atomic<int> not_fp32{0};
+    std::atomic<int> not_fp32{0}, clipped_with_own_transform{0};
     std::vector<uint8_t> general(n, 0);  // spheres that need the object-space test (sphere_core.cuh)
     parallel_ranges(n, [&](size_t i0, size_t i1) {
     bool all_fp32 = true;
@@ -951,6 +951,15 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
                 }
             };
             if (!s.is_full()) {
+                // Q5a (sphere.rs:157): the first root is clipped by the z / phi of the INSTANCE-space point.  With a
+                // transform of the sphere's own that accepts points outside the shape's bound, which the reference
+                // finds only when the ray happens to cross the leaf's box: the answer depends on the tree.  A clipped
+                // sphere is therefore placed through instances[] (as config 4 places its spheres), where both spaces
+                // are one and the same.
+                if (!s.obj_to_world.is_identity()) {
+                    clipped_with_own_transform = 1;
+                    continue;
+                }
                 general_sphere();
                 continue;
             }
@@ -990,6 +999,12 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     }
     if (!all_fp32) not_fp32 = 1;
     });
+    if (clipped_with_own_transform) {
+        if (err)
+            *err = "a sphere clipped by z_min / z_max / phi_max must get its placement from instances[], not from a transform of "
+                   "its own: the reference clips the first root in instance space (Q5a) and its answer then depends on the tree";
+        return RRT_ERR_UNSUPPORTED;
+    }
     std::vector<GenSphere> gspheres;
     for (size_t i = 0; i < n; ++i) {
         if (!general[i]) continue;

@@ -382,12 +382,14 @@ def scene_clipped_spheres(directory, xres=192, yres=108, nsamp=9, integrator="Pa
          "instances": [{"world_pos": [35.0, 0.5, 2.6], "rotation_axis": [1.0, 0.2, 0.0], "rotation_angle": 70, "scale": [1.0, 1.0, 1.3]}]},
         # a wedge: three quarters of a sphere in phi, the object transform of the sphere itself non-uniform
         {"primitive_type": "sphere", "radius": 1.2, "phi_max": 250.0, "material_name": "m_uv",
-         "world_pos": [0.0, 0.0, 0.0], "scale": [1.0, 0.7, 1.0],
-         "instances": [{"world_pos": [35.4, -0.2, -0.6], "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 200},
+         "instances": [{"world_pos": [35.4, -0.2, -0.6], "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 200, "scale": [1.0, 0.7, 1.0]},
                        {"world_pos": [33.0, 2.4, -3.2], "rotation_axis": [0.3, 1.0, 0.2], "rotation_angle": 40, "scale": [0.8, 0.8, 0.8]}]},
-        # a band (both poles cut away), not instanced: its own transform carries it into the scene (Q5a applies)
+        # a band (both poles cut away and a slice in phi)
         {"primitive_type": "sphere", "radius": 1.0, "z_min": -0.5, "z_max": 0.5, "phi_max": 300.0, "material_name": "m_metal",
-         "world_pos": [36.5, -0.8, -3.4], "rotation_axis": [1.0, 0.0, 0.0], "rotation_angle": 90},
+         "instances": [{"world_pos": [36.5, -0.8, -3.4], "rotation_axis": [1.0, 0.0, 0.0], "rotation_angle": 90}]},
+        # a full sphere stretched by an object transform of its own, not instanced (Q5a: its (u, v) come from the world point)
+        {"primitive_type": "sphere", "radius": 0.8, "material_name": "m_uv",
+         "world_pos": [34.2, 1.6, 0.9], "rotation_axis": [0.0, 0.0, 1.0], "rotation_angle": 25, "scale": [1.4, 0.8, 1.0]},
         # and one ordinary full sphere
         {"primitive_type": "sphere", "radius": 0.8, "material_name": "m_check", "instances": [{"world_pos": [33.5, -1.2, 1.0]}]},
     ]

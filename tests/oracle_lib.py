@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 LIB_PATH = ROOT / "oracle" / "build" / "liboracle.so"
 
 TIER_L = 0x00  # literal reference behaviour, every Appendix-A quirk kept
-TIER_F = 0xFF  # Q1,Q2,Q3,Q4,Q5b,Q6,Q8,Q9 switched to the evident intent
+TIER_F = 0x1FF  # Q1,Q2,Q3,Q4,Q5b,Q5c,Q6,Q8,Q9 switched to the evident intent
 
 _lib = None
 

@@ -496,13 +496,16 @@ def _general_sphere_scene(ctx, tier_scene):
         if kind in (1, 2, 4):
             phi_max = float(rng.uniform(60.0, 330.0))
         scale = (1.0, 1.0, 1.0) if kind in (0, 2) else tuple(rng.uniform(0.6, 1.8, 3))
-        o2w = T.make_to_world(rng.uniform(-6, 6, 3), rng.normal(0, 1, 3), float(rng.uniform(0, 360)), scale)
+        clipped = kind != 3
+        # a clipped sphere is placed through instances (Q5a: see test_clipped_sphere_with_own_transform_is_refused)
+        o2w = T.make_to_world(rng.uniform(-6, 6, 3), rng.normal(0, 1, 3), float(rng.uniform(0, 360)), scale) if not clipped \
+            else T.make_to_world()
         inst = None
-        if k % 2 == 0:
+        if k % 2 == 0 or clipped:
             ms, invs = [], []
             for _ in range(3):
                 m, inv = T.make_to_world(rng.uniform(-8, 8, 3), rng.normal(0, 1, 3), float(rng.uniform(0, 360)),
-                                         tuple(rng.uniform(0.7, 1.4, 3)) if kind != 0 else (1.0, 1.0, 1.0))
+                                         tuple(rng.uniform(0.6, 1.6, 3)) if kind != 0 else (1.0, 1.0, 1.0))
                 ms.append(m)
                 invs.append(inv)
             inst = (np.array(ms), np.array(invs))
@@ -558,3 +561,22 @@ def test_partial_and_scaled_spheres(ctx, flags):
     _assert_closest(a.intersect(sec), r2["prim"], r2["t"], r2["uv"])
     occ2, _ = s.intersect_p(sec)
     assert (a.intersect_p(sec) == occ2).all()
+
+
+def test_clipped_sphere_with_own_transform_is_refused(ctx):
+    """The reference clips a sphere's first root by the z / phi of the point on the ray it was HANDED (Q5a, sphere.rs:157).
+    If the sphere has an object transform of its own, that accepts points outside the shape's bound, found only when the
+    ray happens to cross the BVH leaf's box: the reference's own answer depends on the tree.  Such a sphere gets its
+    placement from instances[] instead; the same sphere with the same placement as an instance commits."""
+    from rs_ray_toy_b200 import transform as T
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    xf = T.make_to_world((1.0, 2.0, 3.0), (0.0, 1.0, 0.0), 30.0)
+    a = GpuAggregate(ctx)
+    a.add_sphere(radius=1.0, z_min=-0.3, z_max=0.8, obj_to_world=xf)
+    with pytest.raises(capi.RrtError) as e:
+        a.commit(4)
+    assert e.value.status == capi.RRT_ERR_UNSUPPORTED
+    b = GpuAggregate(ctx)
+    b.add_sphere(radius=1.0, z_min=-0.3, z_max=0.8, instances=(xf[0][None], xf[1][None]))
+    b.commit(4)
+    assert b.num_prims == 1

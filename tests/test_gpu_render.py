@@ -326,5 +326,5 @@ def test_clipped_and_stretched_spheres(ctx, tmp_path, integrator):
     gpu.run()
     out = compare(gpu, ref)
     assert out["rmse"] < 1e-4, out
-    hit = ref["dump"][:, 3] >= 0
-    assert hit.sum() > 0.05 * hit.shape[0]
+    first = ref["dump"][:, 3]
+    assert all((first == k).sum() > 200 for k in range(6))   # every sphere of the scene is seen by camera rays
