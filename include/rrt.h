@@ -237,7 +237,9 @@ typedef struct rrt_render_desc {
     const double* lens_data;          /* 4 values per element interface, millimetres            */
     /* Sampler (HaltonSampler) */
     uint64_t nsamp;                   /* the reference renders nsamp - 1 samples per pixel (Q10) */
-    uint32_t sample_at_center, pad1;
+    uint32_t sample_at_center;
+    uint32_t light_strategy;          /* DirectLighting: 0 = UniformSampleOne, 1 = UniformSampleAll (one sample per
+                                       * light: the reference's sample arrays never reach its tile samplers, Q30) */
     uint64_t seed;                    /* digit-permutation seed (0 = identity); DESIGN.md §6    */
     /* Integrator */
     uint32_t integrator_kind, max_depth;

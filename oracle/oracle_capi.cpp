@@ -562,6 +562,7 @@ void orc_area_light_probe(const double* row80, const double* ref_p3, const doubl
 //  9-11 camera world_pos 12-14 look 15-17 up 18 shutter_open 19 shutter_close 20 aperture_diameter
 //  21 focus_distance 22 simple_weighting 23 nsamp 24 sample_at_center 25 seed 26 integrator kind
 //  27 max_depth 28 rr_threshold 29 tile_mod 30 tile_rank 31 crop flag 32-35 crop x0 y0 x1 y1 36 want_dump
+//  37 light strategy (DirectLighting: 0 one, 1 all)
 // outputs: rgb[3*npix] (Film::write_image values before the PNG quantisation), raw[4*npix]
 // (xyz + filter_weight_sum), stats[16], dump (6 doubles per camera sample, capacity dump_cap).
 int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_t n_lens_values, double* rgb,
@@ -635,6 +636,7 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
         job.integrator.kind = (uint32_t)prm[26];
         job.integrator.max_depth = (uint32_t)prm[27];
         job.integrator.rr_threshold = prm[28];
+        job.integrator.sample_all_lights = prm[37] != 0.0;
         job.want_dump = prm[36] != 0.0 && dump != nullptr;
         int64_t crop[4] = {(int64_t)prm[32], (int64_t)prm[33], (int64_t)prm[34], (int64_t)prm[35]};
         job.render(std::max(1, nthreads), std::max<uint32_t>(1, (uint32_t)prm[29]), (uint32_t)prm[30],

@@ -219,12 +219,26 @@ struct RenderScene {
         P2 u_scattering = sampler.get_2d();
         return estimate_direct(si, bsdf, lights[light_num], u_light, u_scattering, st) / light_pdf;
     }
+    // uniform_sample_all_lights (integrator/mod.rs:304-355) as it runs.  Q30: DirectLightingIntegrator::preprocess
+    // requests its 2D sample arrays on a throwaway sampler (`pre_sampler`, integrator/mod.rs:50-51) — the tile samplers
+    // are built afresh and hold none, get_2d_array returns an empty slice (samplers/mod.rs:108-111), and every light
+    // takes the single-sample branch (:321-335): two get_2d per light, one estimate, no division.
+    Rgb uniform_sample_all_lights(const SI& si, const Bsdf& bsdf, HaltonSampler& sampler, RenderStats* st) const {
+        Rgb l;
+        for (size_t j = 0; j < lights.size(); ++j) {
+            P2 u_light = sampler.get_2d();
+            P2 u_scattering = sampler.get_2d();
+            l += estimate_direct(si, bsdf, lights[j], u_light, u_scattering, st);
+        }
+        return l;
+    }
 };
 
 struct Integrator {
     uint32_t kind = INTEGRATOR_PATH;
     uint32_t max_depth = 5;
     double rr_threshold = 1.0;
+    bool sample_all_lights = false;  // DirectLighting: LightStrategy::UniformSampleAll (directlighting.rs:102-110)
     Distribution1D light_distrib;  // path.rs:47-49: uniform over the lights
 
     // PathIntegrator::li (path.rs:51-226)
@@ -296,7 +310,9 @@ struct Integrator {
         Bsdf bsdf;
         material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, camera), isect, false, &bsdf);
         if (!bsdf.present) return li_direct(sc, ray_new_od(isect.p, ray.d), sampler, depth, st, nullptr);
-        if (!sc.lights.empty()) l += sc.uniform_sample_one_light(isect, bsdf, sampler, nullptr, st);
+        if (!sc.lights.empty())
+            l += sample_all_lights ? sc.uniform_sample_all_lights(isect, bsdf, sampler, st)
+                                   : sc.uniform_sample_one_light(isect, bsdf, sampler, nullptr, st);
         if (depth + 1 < max_depth) {
             for (int pass = 0; pass < 2; ++pass) {
                 uint8_t ty = BXDF_SPECULAR | (pass == 0 ? BXDF_REFLECTION : BXDF_TRANSMISSION);

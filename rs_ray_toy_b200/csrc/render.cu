@@ -726,7 +726,8 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
 #define RRT_SHADE_MINBLOCKS 3
 #endif
 // TEXTURED = some material parameter is driven by a texture: the kernel for constant-valued scenes carries none of it.
-template <bool TEXTURED>
+// ALL_LIGHTS = DirectLighting with LightStrategy::UniformSampleAll: one light sample per light and hit (Q30).
+template <bool TEXTURED, bool ALL_LIGHTS>
 __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
                                                      IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
     uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -781,10 +782,14 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
             } else {
                 // ---- uniform_sample_one_light (integrator/mod.rs:359-401) ----
                 const bool do_nee = ip.kind == RRT_INTEGRATOR_DIRECT || bsdf_num_components(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0;
-                if (do_nee && ip.n_lights > 0) {
-                    const double ul = next_1d(ht, perms, p);
+                const uint32_t n_estimates = (do_nee && ip.n_lights > 0) ? (ALL_LIGHTS ? ip.n_lights : 1u) : 0u;
+                for (uint32_t estimate = 0; estimate < n_estimates; ++estimate) {
+                    // uniform_sample_all_lights (integrator/mod.rs:304-355) draws no light choice: light j, two get_2d
+                    const double ul = ALL_LIGHTS ? 0.0 : next_1d(ht, perms, p);
                     uint32_t light_num;
-                    if (ip.kind == RRT_INTEGRATOR_PATH) {
+                    if (ALL_LIGHTS) {
+                        light_num = estimate;
+                    } else if (ip.kind == RRT_INTEGRATOR_PATH) {
                         // Distribution1D::sample_discrete (sampling.rs:87-122): bisection over the CDF
                         uint32_t first = 0, len = ip.n_lights + 1;
                         while (len > 0) {
@@ -832,17 +837,27 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                             Rgb ld;
                             if (area) {
                                 const double weight = power_heuristic(1, light_pdf, 1, bsdf_pdf(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR));
-                                ld = (li * f * weight / light_pdf) / ip.light_pdf;
+                                ld = li * f * weight / light_pdf;
                             } else {
-                                ld = (f * li / 1.0) / ip.light_pdf;
+                                ld = f * li / 1.0;
                             }
+                            if (!ALL_LIGHTS) ld = ld / ip.light_pdf;
                             contrib = ip.kind == RRT_INTEGRATOR_PATH ? p.beta * ld : ld;
-                            emit_sh = true;
                             so = s.p;
                             // Tier F (Q9 fixed): t runs over the segment, t_max = 1 - eps stops just short
                             // of the light.  Tier L: Ray::new normalises d and keeps t_max = 1 - eps
                             // (interaction.rs:66-77), so only boxes within one unit are ever entered.
                             sd = sc.literal ? normalize(p1 - s.p) : p1 - s.p;
+                            if (ALL_LIGHTS) {
+                                // several shadow rays per hit: each takes its own slot (resolve_kernel adds them
+                                // to the path with atomics in this mode)
+                                const uint32_t slot_sh = atomicAdd(q.counters + 2, 1u);
+                                write_ray(q.sh_rays + slot_sh, so, sd, 1.0 - kShadowEps);
+                                q.sh_path[slot_sh] = pid;
+                                q.sh_contrib[slot_sh] = contrib;
+                            } else {
+                                emit_sh = true;
+                            }
                         }
                     }
                 }
@@ -914,12 +929,20 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
 }
 
 // Unoccluded light samples join their path's radiance (`l += ld`, path.rs:121 / directlighting.rs:113)
-__global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, Queues q) {
+// `shared_paths`: several light samples may belong to one path (UniformSampleAll): they are added with atomics.
+__global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, Queues q, int shared_paths) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.counters[2]) return;
     if (q.sh_occluded[i]) return;
     Path& p = paths[q.sh_path[i]];
-    p.L = p.L + q.sh_contrib[i];
+    const Rgb c = q.sh_contrib[i];
+    if (shared_paths) {
+        atomicAdd(&p.L.r, c.r);
+        atomicAdd(&p.L.g, c.g);
+        atomicAdd(&p.L.b, c.b);
+    } else {
+        p.L = p.L + c;
+    }
 }
 
 // Between rounds: statistics, then the next round's queue becomes current and the others empty.
@@ -1071,6 +1094,8 @@ struct Renderer::Impl {
     RayDiffRec* d_diffs = nullptr;  // camera-ray differentials per slot, when a texture filters with them
     double diff_scale = 1.0;        // 1 / sqrt(samples_per_pixel) (integrator/mod.rs:92-94)
     bool textured = false, want_diffs = false;
+    bool all_lights = false;        // DirectLighting, UniformSampleAll
+    uint32_t shadow_per_hit = 1;
     // RRT_GEN_F32: 2 = screened generate kernel (fp32 walks decide blocked samples and neighbour rays; the default),
     // 1 = the lane-state-machine kernel with fp32 neighbour walks, 0 = every lens trace in f64 (the parity tests' A/B switch)
     int gen_mode = 2;
@@ -1527,6 +1552,10 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         const uint64_t ntx = (uint64_t)(F.sb[2] - F.sb[0] + kTile - 1) / kTile, nty = (uint64_t)(F.sb[3] - F.sb[1] + kTile - 1) / kTile;
         const uint64_t frame = ntx * nty * kTile * kTile * std::max<uint64_t>(1, I.ip.n_samples);
         I.chunk = (uint32_t)std::min<uint64_t>(kChunk, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
+        // UniformSampleAll: up to n_lights shadow rays per hit — the chunk shrinks so that the shadow queue does not grow
+        I.all_lights = d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.light_strategy == 1 && !lights.empty();
+        I.shadow_per_hit = I.all_lights ? (uint32_t)lights.size() : 1u;
+        if (I.all_lights) I.chunk = std::max<uint32_t>(1u << 16, (I.chunk / I.shadow_per_hit) & ~65535u);
     }
     const size_t kSlots = I.chunk;
     if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
@@ -1541,10 +1570,11 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         if ((rc = dev_alloc((void**)&I.q.ext_path[k], kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
     }
     if ((rc = dev_alloc((void**)&I.q.hits, kSlots * sizeof(rrt_hit))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_rays, kSlots * sizeof(rrt_ray))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_path, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_contrib, kSlots * sizeof(Rgb))) != RRT_OK) return rc;
-    if ((rc = dev_alloc((void**)&I.q.sh_occluded, kSlots)) != RRT_OK) return rc;
+    const size_t kShadow = kSlots * I.shadow_per_hit;
+    if ((rc = dev_alloc((void**)&I.q.sh_rays, kShadow * sizeof(rrt_ray))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_path, kShadow * sizeof(uint32_t))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_contrib, kShadow * sizeof(Rgb))) != RRT_OK) return rc;
+    if ((rc = dev_alloc((void**)&I.q.sh_occluded, kShadow)) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.shade_key, kSlots)) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.shade_perm, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.counters, 64 * sizeof(uint32_t))) != RRT_OK) return rc;
@@ -1638,14 +1668,17 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             shade_scatter_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.q, cur);
             launches += 2;
 #endif
-            if (I.textured)
-                shade_kernel<true><<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
-            else
-                shade_kernel<false><<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
-            rc = I.agg->any_hit_indirect(count, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream, err, &n);
+            {
+                auto shade = I.all_lights ? (I.textured ? shade_kernel<true, true> : shade_kernel<false, true>)
+                                          : (I.textured ? shade_kernel<true, false> : shade_kernel<false, false>);
+                shade<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
+            }
+            rc = I.agg->any_hit_indirect((uint64_t)count * I.shadow_per_hit, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream,
+                                         err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;
-            resolve_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.d_paths, I.q);
+            resolve_kernel<<<(unsigned)(((uint64_t)count * I.shadow_per_hit + 255) / 256), 256, 0, I.stream>>>(I.d_paths, I.q,
+                                                                                                            I.all_lights ? 1 : 0);
             advance_kernel<<<1, 1, 0, I.stream>>>(I.q, cur);
             launches += 3;
             cur ^= 1;

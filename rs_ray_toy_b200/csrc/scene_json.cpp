@@ -586,8 +586,7 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
         d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
         d.rr_threshold = read_f64(*ic, "rr_threshold", 1.0);
     } else if (it == "DirectLighting") {
-        if (read_string(*ic, "light_strategy", "one") == "all")
-            throw std::runtime_error("DirectLighting light_strategy 'all' is outside the hot-path scope");
+        d.light_strategy = read_string(*ic, "light_strategy", "one") == "all" ? 1u : 0u;  // renderprocess.rs:1413-1417
         d.integrator_kind = RRT_INTEGRATOR_DIRECT;
         d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
         d.rr_threshold = 1.0;

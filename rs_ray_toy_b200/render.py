@@ -29,7 +29,7 @@ class RenderDesc(C.Structure):
         ("simple_weighting", C.c_uint32), ("n_lens_values", C.c_uint32),
         ("lens_data", C.POINTER(C.c_double)),
         ("nsamp", C.c_uint64),
-        ("sample_at_center", C.c_uint32), ("pad1", C.c_uint32),
+        ("sample_at_center", C.c_uint32), ("light_strategy", C.c_uint32),
         ("seed", C.c_uint64),
         ("integrator_kind", C.c_uint32), ("max_depth", C.c_uint32),
         ("rr_threshold", C.c_double),

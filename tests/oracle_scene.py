@@ -350,9 +350,8 @@ def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=Fal
     if it == "Path":
         p[26], p[27], p[28] = 0, int(integ.get("max_depth", 5)), float(integ.get("rr_threshold", 1.0))
     elif it == "DirectLighting":
-        if integ.get("light_strategy", "one") == "all":
-            raise ValueError("light_strategy 'all' is outside the restated subset")
         p[26], p[27], p[28] = 1, int(integ.get("max_depth", 5)), 1.0
+        p[37] = 1.0 if integ.get("light_strategy", "one") == "all" else 0.0   # renderprocess.rs:1413-1417
     else:
         raise ValueError(f"integrator {it!r} is outside the restated subset")
     p[29], p[30] = tile_mod, tile_rank

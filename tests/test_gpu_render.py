@@ -328,3 +328,20 @@ def test_clipped_and_stretched_spheres(ctx, tmp_path, integrator):
     assert out["rmse"] < 1e-4, out
     first = ref["dump"][:, 3]
     assert all((first == k).sum() > 200 for k in range(6))   # every sphere of the scene is seen by camera rays
+
+
+def test_direct_lighting_sample_all_lights(ctx, tmp_path):
+    """light_strategy "all": one estimate per light and hit (Q30), point lights (config 1's three) and area lights."""
+    every = {"Integrator": {"integrator_type": "DirectLighting", "max_depth": 1, "light_strategy": "all"}}
+    for path in (synth.scene_c1(str(tmp_path / "c1"), xres=256, yres=144, nsamp=9, integrator="DirectLighting", max_depth=1),
+                 synth.scene_area_lights(str(tmp_path / "a"), xres=192, yres=108, nsamp=9, integrator="DirectLighting", max_depth=1)):
+        ref = S.load(path, every).render(seed=1, want_dump=True)
+        gpu = Render.load(ctx, path, overrides=every, seed=1)
+        gpu.enable_hit_dump()
+        gpu.run()
+        out = compare(gpu, ref)
+        assert out["rmse"] < 1e-6, out
+        assert out["shadow_rays"][0] == out["shadow_rays"][1], out
+        one = Render.load(ctx, path, seed=1)
+        one.run()
+        assert one.stats()["shadow_rays"] < out["shadow_rays"][0]

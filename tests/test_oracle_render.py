@@ -318,3 +318,19 @@ def test_halton_tables_are_the_digit_loops():
         assert np.array_equal(outs[0][0], outs[1][0])
         assert np.array_equal(outs[0][1], outs[1][1])
         assert 0.0 <= outs[1][1].min() and outs[1][1].max() < 1.0 and len(np.unique(outs[1][1])) > n // 2
+
+
+def test_sample_all_lights_is_one_estimate_per_light(tmp_path):
+    """DirectLighting with light_strategy "all" (directlighting.rs:102-110, uniform_sample_all_lights
+    integrator/mod.rs:304-355).  The sample arrays are requested on a throwaway sampler (Q30), so every light gets one
+    estimate from two get_2d draws and the estimates are summed: the image is an unbiased estimate of the same
+    integral as strategy "one" (which picks one light and multiplies by their number), with one shadow ray per light
+    and lit hit instead of one per hit."""
+    path = synth.scene_c1(str(tmp_path), xres=160, yres=90, nsamp=17, integrator="DirectLighting", max_depth=1)
+    one = S.load(path).render(seed=1)
+    every = S.load(path, {"Integrator": {"integrator_type": "DirectLighting", "max_depth": 1, "light_strategy": "all"}}).render(seed=1)
+    assert every["stats"]["extension_rays"] == one["stats"]["extension_rays"]
+    assert every["stats"]["shadow_rays"] > 2 * one["stats"]["shadow_rays"]        # three lights
+    m1, m2 = one["rgb"].mean(axis=(0, 1)), every["rgb"].mean(axis=(0, 1))
+    assert np.allclose(m1, m2, rtol=0.05), (m1, m2)
+    assert not np.allclose(one["rgb"], every["rgb"])
