@@ -783,7 +783,9 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                 // ---- uniform_sample_one_light (integrator/mod.rs:359-401) ----
                 const bool do_nee = ip.kind == RRT_INTEGRATOR_DIRECT || bsdf_num_components(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0;
                 const uint32_t n_estimates = (do_nee && ip.n_lights > 0) ? (ALL_LIGHTS ? ip.n_lights : 1u) : 0u;
-                for (uint32_t estimate = 0; estimate < n_estimates; ++estimate) {
+                uint32_t estimate = 0;
+            next_estimate:  // a loop only when ALL_LIGHTS: the other instantiations keep the plain `if` they were tuned with
+                if (estimate < n_estimates) {
                     // uniform_sample_all_lights (integrator/mod.rs:304-355) draws no light choice: light j, two get_2d
                     const double ul = ALL_LIGHTS ? 0.0 : next_1d(ht, perms, p);
                     uint32_t light_num;
@@ -859,6 +861,10 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                                 emit_sh = true;
                             }
                         }
+                    }
+                    if (ALL_LIGHTS) {
+                        ++estimate;
+                        goto next_estimate;
                     }
                 }
                 if (ip.kind == RRT_INTEGRATOR_DIRECT) {
