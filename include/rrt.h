@@ -173,14 +173,16 @@ typedef struct rrt_material {
  * textures flattened into ONE table in definition order (float textures first).  A texture can only name textures
  * defined before it (the loader looks names up in the maps it is filling; an unknown name becomes a constant,
  * get_text_fallback :282-296), so children always have smaller indices.  Float textures use v[.][0].
- * texture/{bilerp,mix,scale,checkerboard,uv}.rs; mappings texture/mod.rs:206-347 with their screen-space
+ * texture/{bilerp,mix,scale,checkerboard,uv,windy,wrinkled}.rs; mappings texture/mod.rs:206-347 with their screen-space
  * differentials: the renderer carries the camera ray's differentials (RealisticCamera::generate_ray_differential,
  * camera.rs:582-628, scaled by 1/sqrt(spp), integrator/mod.rs:92-94) to the first hit and runs
  * SurfaceInteraction::compute_differentials (interaction.rs:223-284) there when a texture asks for them (a
- * closed-form checkerboard); every later hit has none, like the reference's spawned rays.               */
+ * closed-form checkerboard, a noise texture); every later hit has none, like the reference's spawned rays.               */
 typedef enum rrt_texture_kind {
     RRT_TEX_CONSTANT = 0, RRT_TEX_BILERP = 1, RRT_TEX_SCALE = 2, RRT_TEX_MIX = 3, RRT_TEX_CHECKER2D = 4,
-    RRT_TEX_CHECKER3D = 5, RRT_TEX_UV = 6
+    RRT_TEX_CHECKER3D = 5, RRT_TEX_UV = 6,
+    RRT_TEX_WINDY = 7,    /* windy.rs: |fbm(0.1 p, 3 octaves)| * fbm(p, 6 octaves) over Perlin noise (texture/mod.rs:75-155) */
+    RRT_TEX_WRINKLED = 8  /* wrinkled.rs: turbulence(p, omega = map[1], octaves = map[0]) (texture/mod.rs:157-188)     */
 } rrt_texture_kind;
 typedef enum rrt_texture_mapping {
     RRT_TEXMAP_UV = 0, RRT_TEXMAP_PLANAR = 1, RRT_TEXMAP_SPHERICAL = 2, RRT_TEXMAP_CYLINDRICAL = 3
@@ -192,7 +194,8 @@ typedef struct rrt_texture {
     uint32_t aa;                  /* Checkerboard 2D: 0 = AAMethod::AANone, 1 = ClosedForm (the loader's default) */
     double v[4][3];               /* Constant: v[0]; Bilerp: v00 v01 v10 v11                                   */
     double map[8];                /* uv: su sv du dv; planar: vs[3] vt[3] ds dt                                */
-    double world_to_texture[16];  /* Checkerboard 3D (IdentityMapping3D), spherical / cylindrical: row-major   */
+    double world_to_texture[16];  /* Checkerboard 3D / Windy / Wrinkled (IdentityMapping3D), spherical /
+                                   * cylindrical: row-major                                                   */
 } rrt_texture;
 /* Which texture drives each parameter of a material; -1 = the constant held in rrt_material.               */
 typedef enum rrt_material_slot {

@@ -478,7 +478,10 @@ enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MA
 // evaluating the table front to back evaluates every child before its parent.  Float textures use component 0.
 // In scope: Constant, Bilerp, Scale, Mix, UV, Checkerboard 2D (point-sampled and closed-form box filter) and 3D;
 // UV, planar, spherical and cylindrical 2D mappings with their screen-space differentials, IdentityMapping3D.
-enum TexKind : uint32_t { TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5, TEX_UV = 6 };
+enum TexKind : uint32_t {
+    TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5, TEX_UV = 6,
+    TEX_WINDY = 7, TEX_WRINKLED = 8  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D in w2t
+};
 enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1, MAP_SPHERICAL = 2, MAP_CYLINDRICAL = 3 };
 struct Texture {
     uint32_t kind = TEX_CONST, mapping = MAP_UV;
@@ -584,6 +587,79 @@ inline int32_t rust_f64_as_i32(double v) {  // `as i32`: saturating, NaN -> 0
     if (v <= -2147483648.0) return (int32_t)-2147483647 - 1;
     return (int32_t)v;
 }
+// ---- Perlin noise (texture/mod.rs:13-177) ----
+inline const uint8_t* noise_perm() {
+    static const uint8_t t[256] = {
+#include "noise_perm.h"
+        RRT_NOISE_PERM_256};
+    return t;
+}
+inline double noise_grad(int32_t x, int32_t y, int32_t z, double dx, double dy, double dz) {  // :113-130
+    const uint8_t* P = noise_perm();
+    uint8_t h = P[(P[(P[x & 255] + y) & 255] + z) & 255];  // the reference indexes a doubled table: same entries
+    h &= 15;
+    double u = (h < 8 || h == 12 || h == 13) ? dx : dy;
+    double v = (h < 4 || h == 12 || h == 13) ? dy : dz;
+    return ((h & 1) ? -u : u) + ((h & 2) ? -v : v);
+}
+inline double noise_weight(double t) {  // :132-136
+    double t3 = t * t * t, t4 = t3 * t;
+    return 6.0 * t4 * t - 15.0 * t4 + 10.0 * t3;
+}
+inline double lerp_f(double t, double a, double b) { return a * (1.0 - t) + b * t; }  // misc.rs:223-228
+inline double noise3(V3 p) {  // noise_flt, :75-107
+    int32_t ix = rust_f64_as_i32(std::floor(p.x)), iy = rust_f64_as_i32(std::floor(p.y)), iz = rust_f64_as_i32(std::floor(p.z));
+    double dx = p.x - (double)ix, dy = p.y - (double)iy, dz = p.z - (double)iz;
+    ix &= 255;
+    iy &= 255;
+    iz &= 255;
+    double w000 = noise_grad(ix, iy, iz, dx, dy, dz), w100 = noise_grad(ix + 1, iy, iz, dx - 1.0, dy, dz);
+    double w010 = noise_grad(ix, iy + 1, iz, dx, dy - 1.0, dz), w110 = noise_grad(ix + 1, iy + 1, iz, dx - 1.0, dy - 1.0, dz);
+    double w001 = noise_grad(ix, iy, iz + 1, dx, dy, dz - 1.0), w101 = noise_grad(ix + 1, iy, iz + 1, dx - 1.0, dy, dz - 1.0);
+    double w011 = noise_grad(ix, iy + 1, iz + 1, dx, dy - 1.0, dz - 1.0), w111 = noise_grad(ix + 1, iy + 1, iz + 1, dx - 1.0, dy - 1.0, dz - 1.0);
+    double wx = noise_weight(dx), wy = noise_weight(dy), wz = noise_weight(dz);
+    double x00 = lerp_f(wx, w000, w100), x10 = lerp_f(wx, w010, w110), x01 = lerp_f(wx, w001, w101), x11 = lerp_f(wx, w011, w111);
+    return lerp_f(wz, lerp_f(wy, x00, x10), lerp_f(wy, x01, x11));
+}
+inline double smooth_step(double lo, double hi, double v) {  // :70-73
+    double t = clamp_t((v - lo) / (hi - lo), 0.0, 1.0);
+    return t * t * (-2.0 * t + 3.0);
+}
+inline double noise_octaves(V3 dpdx, V3 dpdy, double max_octaves) {
+    double len2 = rmax(length_sq(dpdx), length_sq(dpdy));
+    return clamp_t(-1.0 - 0.5 * std::log2(len2), 0.0, max_octaves);
+}
+inline double fbm(V3 p, V3 dpdx, V3 dpdy, double omega, uint64_t max_octaves) {  // :138-155
+    double n = noise_octaves(dpdx, dpdy, (double)max_octaves);
+    int32_t n_int = rust_f64_as_i32(std::floor(n));
+    double sum = 0.0, lambda = 1.0, o = 1.0;
+    for (int32_t i = 0; i < n_int; ++i) {
+        sum += o * noise3(p * lambda);
+        lambda *= 1.99;
+        o *= omega;
+    }
+    double n_partial = n - (double)n_int;
+    sum += o * smooth_step(0.3, 0.7, n_partial) * noise3(p * lambda);
+    return sum;
+}
+inline double turbulence(V3 p, V3 dpdx, V3 dpdy, double omega, uint64_t max_octaves) {  // :157-188
+    double n = noise_octaves(dpdx, dpdy, (double)max_octaves);
+    uint64_t n_int = rust_as_u64(std::floor(n));
+    double sum = 0.0, lambda = 1.0, o = 1.0;
+    for (uint64_t i = 0; i < n_int; ++i) {
+        sum += o * std::fabs(noise3(p * lambda));
+        lambda *= 1.99;
+        o *= omega;
+    }
+    double n_partial = n - (double)n_int;
+    sum += o * lerp_f(smooth_step(0.3, 0.7, n_partial), 0.2, std::fabs(noise3(p * lambda)));
+    for (uint64_t i = n_int; i < max_octaves; ++i) {
+        sum += o * 0.2;
+        o *= omega;
+    }
+    return sum;
+}
+
 // checkerboard.rs:45-47
 inline double bump_int(double x) {
     return std::floor(x / 2.0) + 2.0 * std::fmax(x / 2.0 - std::floor(x / 2.0) - 0.5, 0.0);
@@ -627,6 +703,18 @@ inline void tex_eval_all(const std::vector<Texture>& table, const TexPoint& q, R
                 double area2 = sint + tint - 2.0 * sint * tint;
                 if (ds > 1.0 || dt > 1.0) area2 = 0.5;
                 vals[i] = vals[t.t1] * (1.0 - area2) + vals[t.t2] * area2;
+                break;
+            }
+            case TEX_WINDY: {  // windy.rs:13-22; IdentityMapping3D::map (texture/mod.rs:362-368)
+                V3 w = xf_point(t.w2t, q.p), dx = xf_vector(t.w2t, q.dpdx), dy = xf_vector(t.w2t, q.dpdy);
+                double wind_strength = fbm(w * 0.1, dx * 0.1, dy * 0.1, 0.5, 3);
+                double wave_height = fbm(w, dx, dy, 0.5, 6);
+                vals[i] = Rgb(std::fabs(wind_strength) * wave_height);
+                break;
+            }
+            case TEX_WRINKLED: {  // wrinkled.rs:22-28
+                V3 w = xf_point(t.w2t, q.p), dx = xf_vector(t.w2t, q.dpdx), dy = xf_vector(t.w2t, q.dpdy);
+                vals[i] = Rgb(turbulence(w, dx, dy, t.map[1], rust_as_u64(t.map[0])));
                 break;
             }
             case TEX_UV: {  // uv.rs:20-27 (Spectrum<3>::from_rgb copies, spectrum.rs:2740-2742)

@@ -1183,14 +1183,16 @@ bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err) {
     if (n > (uint32_t)kMaxTextures) return bad(n, "more than RRT_MAX_TEXTURES textures");
     for (uint32_t i = 0; i < n; ++i) {
         const rrt_texture& x = t[i];
-        if (x.kind > RRT_TEX_UV) return bad(i, "kind outside the hot-path scope");
+        if (x.kind > RRT_TEX_WRINKLED) return bad(i, "kind outside the hot-path scope");
+        if (x.kind == RRT_TEX_WRINKLED && !(x.map[0] >= 0.0 && x.map[0] <= 64.0)) return bad(i, "octaves must be in 0..64");
         if (x.mapping > RRT_TEXMAP_CYLINDRICAL) return bad(i, "mapping outside the hot-path scope");
         const bool pair = x.kind == RRT_TEX_SCALE || x.kind == RRT_TEX_MIX || x.kind == RRT_TEX_CHECKER2D || x.kind == RRT_TEX_CHECKER3D;
         auto child_ok = [&](int32_t c) { return c >= 0 && (uint32_t)c < i; };
         if (pair && (!child_ok(x.t1) || !child_ok(x.t2))) return bad(i, "t1 / t2 must name textures defined earlier");
         if (x.kind == RRT_TEX_MIX && !child_ok(x.amount)) return bad(i, "amount must name a texture defined earlier");
         const double* last = x.world_to_texture + 12;
-        const bool uses_matrix = x.kind == RRT_TEX_CHECKER3D || x.mapping >= RRT_TEXMAP_SPHERICAL;
+        const bool uses_matrix = x.kind == RRT_TEX_CHECKER3D || x.kind == RRT_TEX_WINDY || x.kind == RRT_TEX_WRINKLED ||
+                                 x.mapping >= RRT_TEXMAP_SPHERICAL;
         if (uses_matrix && !(last[0] == 0.0 && last[1] == 0.0 && last[2] == 0.0 && last[3] == 1.0))
             return bad(i, "world_to_texture must be affine");
     }
@@ -1539,7 +1541,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         // make_surface fills uv / dpdu / dpdv only when someone reads them
         S.n_textures = I.textured ? (uint32_t)texs.size() : 0u;
         for (size_t i = 0; i < texs.size(); ++i)
-            I.want_diffs |= ((reached >> i) & 1u) && texs[i].kind == TEXK_CHECKER2D && texs[i].aa != 0;
+            I.want_diffs |= ((reached >> i) & 1u) && ((texs[i].kind == TEXK_CHECKER2D && texs[i].aa != 0) ||
+                                                      texs[i].kind == TEXK_WINDY || texs[i].kind == TEXK_WRINKLED);
         if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
         S.n_lights = (uint32_t)lts.size();
         S.literal = agg->literal() ? 1u : 0u;

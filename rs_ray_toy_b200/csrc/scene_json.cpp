@@ -293,7 +293,14 @@ struct TextureTable {
             }
             rows[i].t1 = c1;
             rows[i].t2 = c2;
-        } else if (type == "ImageTexture" || type == "WindyTexture" || type == "WrinkledTexture" || (type == "UVTexture" && !is_rgb)) {
+        } else if (type == "WindyTexture" || type == "WrinkledTexture") {  // IdentityMapping3D::new(to_world) (:376-388, :485-497)
+            i = push(type == "WindyTexture" ? RRT_TEX_WINDY : RRT_TEX_WRINKLED);
+            std::memcpy(rows[i].world_to_texture, to_world.m.m, sizeof(rows[i].world_to_texture));
+            if (type == "WrinkledTexture") {
+                rows[i].map[0] = (double)(uint64_t)read_i64(tc, "octaves", 8);
+                rows[i].map[1] = read_f64(tc, "omega", 0.5);
+            }
+        } else if (type == "ImageTexture" || (type == "UVTexture" && !is_rgb)) {
             if (type == "UVTexture") return;  // not a float texture type: "Unsupported Texture Type", nothing inserted
             names[name] = -2;                  // an error only if something uses it
             return;

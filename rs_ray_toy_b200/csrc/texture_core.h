@@ -12,11 +12,15 @@
 // `spawn_ray(..).into()`, has_differentials = false) and only a closed-form checkerboard reads them; with zero
 // differentials that filter reduces to its point sample (checkerboard.rs:69-83).
 #pragma once
+#include "noise_perm.h"
 #include "rmath.cuh"
 
 namespace rrt {
 
-enum : uint32_t { TEXK_CONSTANT = 0, TEXK_BILERP = 1, TEXK_SCALE = 2, TEXK_MIX = 3, TEXK_CHECKER2D = 4, TEXK_CHECKER3D = 5, TEXK_UV = 6 };
+enum : uint32_t {
+    TEXK_CONSTANT = 0, TEXK_BILERP = 1, TEXK_SCALE = 2, TEXK_MIX = 3, TEXK_CHECKER2D = 4, TEXK_CHECKER3D = 5, TEXK_UV = 6,
+    TEXK_WINDY = 7, TEXK_WRINKLED = 8  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D's matrix in w2t
+};
 enum : uint32_t { TEXM_UV = 0, TEXM_PLANAR = 1, TEXM_SPHERICAL = 2, TEXM_CYLINDRICAL = 3 };
 constexpr int kMaxTextures = 32;
 
@@ -134,6 +138,81 @@ RRT_HD P2 texture_st(const TextureRec& t, const TexPoint& q, bool want, P2* dstd
     }
 }
 
+// ---- Perlin noise, fBm and turbulence (texture/mod.rs:13-188) ----
+#if defined(__CUDACC__)
+static __device__ const uint8_t kNoisePermDevice[256] = {RRT_NOISE_PERM_256};
+#endif
+static const uint8_t kNoisePermHost[256] = {RRT_NOISE_PERM_256};
+RRT_HD uint32_t noise_perm(uint32_t i) {  // the reference indexes a doubled copy of the table: same entries
+#if defined(__CUDA_ARCH__)
+    return kNoisePermDevice[i & 255u];
+#else
+    return kNoisePermHost[i & 255u];
+#endif
+}
+RRT_HD double noise_grad(int32_t x, int32_t y, int32_t z, double dx, double dy, double dz) {  // :113-130
+    const uint32_t h = noise_perm(noise_perm(noise_perm((uint32_t)x) + (uint32_t)y) + (uint32_t)z) & 15u;
+    const double u = (h < 8u || h == 12u || h == 13u) ? dx : dy;
+    const double v = (h < 4u || h == 12u || h == 13u) ? dy : dz;
+    return add((h & 1u) ? -u : u, (h & 2u) ? -v : v);
+}
+RRT_HD double noise_weight(double t) {  // :132-136
+    const double t3 = mul(mul(t, t), t), t4 = mul(t3, t);
+    return add(sub(mul(mul(6.0, t4), t), mul(15.0, t4)), mul(10.0, t3));
+}
+RRT_HD double noise3(V3 p) {  // noise_flt, :75-107
+    int32_t ix = as_i32(floor(p.x)), iy = as_i32(floor(p.y)), iz = as_i32(floor(p.z));
+    const double dx = sub(p.x, (double)ix), dy = sub(p.y, (double)iy), dz = sub(p.z, (double)iz);
+    ix &= 255;
+    iy &= 255;
+    iz &= 255;
+    const double dx1 = sub(dx, 1.0), dy1 = sub(dy, 1.0), dz1 = sub(dz, 1.0);
+    const double w000 = noise_grad(ix, iy, iz, dx, dy, dz), w100 = noise_grad(ix + 1, iy, iz, dx1, dy, dz);
+    const double w010 = noise_grad(ix, iy + 1, iz, dx, dy1, dz), w110 = noise_grad(ix + 1, iy + 1, iz, dx1, dy1, dz);
+    const double w001 = noise_grad(ix, iy, iz + 1, dx, dy, dz1), w101 = noise_grad(ix + 1, iy, iz + 1, dx1, dy, dz1);
+    const double w011 = noise_grad(ix, iy + 1, iz + 1, dx, dy1, dz1), w111 = noise_grad(ix + 1, iy + 1, iz + 1, dx1, dy1, dz1);
+    const double wx = noise_weight(dx), wy = noise_weight(dy), wz = noise_weight(dz);
+    const double x00 = lerpd(wx, w000, w100), x10 = lerpd(wx, w010, w110), x01 = lerpd(wx, w001, w101), x11 = lerpd(wx, w011, w111);
+    return lerpd(wz, lerpd(wy, x00, x10), lerpd(wy, x01, x11));
+}
+RRT_HD double smooth_step(double lo, double hi, double v) {  // :70-73
+    const double t = clampd(sub(v, lo) / sub(hi, lo), 0.0, 1.0);
+    return mul(mul(t, t), add(mul(-2.0, t), 3.0));
+}
+RRT_HD double noise_octaves(V3 dpdx, V3 dpdy, double max_octaves) {
+    const double len2 = rmax(length_sq(dpdx), length_sq(dpdy));
+    return clampd(sub(-1.0, mul(0.5, log2(len2))), 0.0, max_octaves);
+}
+RRT_HD double fbm(V3 p, V3 dpdx, V3 dpdy, double omega, uint64_t max_octaves) {  // :138-155
+    const double n = noise_octaves(dpdx, dpdy, (double)max_octaves);
+    const int32_t n_int = as_i32(floor(n));
+    double sum = 0.0, lambda = 1.0, o = 1.0;
+    for (int32_t i = 0; i < n_int; ++i) {
+        sum = add(sum, mul(o, noise3(p * lambda)));
+        lambda = mul(lambda, 1.99);
+        o = mul(o, omega);
+    }
+    const double n_partial = sub(n, (double)n_int);
+    return add(sum, mul(mul(o, smooth_step(0.3, 0.7, n_partial)), noise3(p * lambda)));
+}
+RRT_HD double turbulence(V3 p, V3 dpdx, V3 dpdy, double omega, uint64_t max_octaves) {  // :157-188
+    const double n = noise_octaves(dpdx, dpdy, (double)max_octaves);
+    const uint64_t n_int = as_u64(floor(n));
+    double sum = 0.0, lambda = 1.0, o = 1.0;
+    for (uint64_t i = 0; i < n_int; ++i) {
+        sum = add(sum, mul(o, fabs(noise3(p * lambda))));
+        lambda = mul(lambda, 1.99);
+        o = mul(o, omega);
+    }
+    const double n_partial = sub(n, (double)n_int);
+    sum = add(sum, mul(o, lerpd(smooth_step(0.3, 0.7, n_partial), 0.2, fabs(noise3(p * lambda)))));
+    for (uint64_t i = n_int; i < max_octaves; ++i) {
+        sum = add(sum, mul(o, 0.2));
+        o = mul(o, omega);
+    }
+    return sum;
+}
+
 // checkerboard.rs:45-47
 RRT_HD double bump_int(double x) {
     const double h = x / 2.0, f = floor(h);
@@ -188,6 +267,18 @@ RRT_HD void texture_eval_table(const TextureRec* table, uint32_t n, uint32_t nee
                 const V3 w = xf_point(t.w2t, q.p);
                 const int32_t k = as_i32(add(add(floor(w.x), floor(w.y)), floor(w.z)));
                 out = (k % 2 == 0) ? vals[t.t1] : vals[t.t2];
+                break;
+            }
+            case TEXK_WINDY: {  // windy.rs:13-22 through IdentityMapping3D::map (texture/mod.rs:362-368)
+                const V3 w = xf_point(t.w2t, q.p), dx = xf_vector(t.w2t, q.dpdx), dy = xf_vector(t.w2t, q.dpdy);
+                const double wind_strength = fbm(w * 0.1, dx * 0.1, dy * 0.1, 0.5, 3);
+                const double wave_height = fbm(w, dx, dy, 0.5, 6);
+                out = rgb(mul(fabs(wind_strength), wave_height));
+                break;
+            }
+            case TEXK_WRINKLED: {  // wrinkled.rs:22-28
+                const V3 w = xf_point(t.w2t, q.p), dx = xf_vector(t.w2t, q.dpdx), dy = xf_vector(t.w2t, q.dpdy);
+                out = rgb(turbulence(w, dx, dy, t.map[1], as_u64(t.map[0])));
                 break;
             }
             default: {  // UVTexture (uv.rs:20-27)

@@ -301,6 +301,7 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
          "scale": [2.0, 2.0, 2.0]},
         {"texture_name": "f_sigma", "texture_type": "ScaleTexture", "t1": "f_ramp", "t2": "f_sixty"},  # f_sixty unknown: 1.0
         {"texture_name": "dark", "texture_type": "BilerpTexture", "v00": 0.3, "v01": 0.3},   # float amount for the rgb Mix below
+        {"texture_name": "f_wrinkle", "texture_type": "WrinkledTexture", "octaves": 5, "omega": 0.6, "scale": [0.7, 0.7, 0.7]},
     ]
     cfg["rgb_texture"] = [
         _const_rgb_texture("white", (0.85, 0.85, 0.8)),
@@ -324,13 +325,18 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         {"texture_name": "big_check", "texture_type": "CheckerBoardTexture", "t1": "white", "t2": "red",
          "mapping": {"mapping": "planar", "v1": [0.02, 0.0, 0.0], "v2": [0.0, 0.0, 0.02], "udelta": 0.3, "vdelta": 0.0}},
         {"texture_name": "floor_kd", "texture_type": "ScaleTexture", "t1": "floor_check", "t2": "big_check"},
+        # Perlin-noise textures (fBm / turbulence; their octave count follows the screen-space footprint)
+        {"texture_name": "waves", "texture_type": "WindyTexture", "world_pos": [0.5, 0.25, 0.0]},
+        {"texture_name": "wrinkles", "texture_type": "WrinkledTexture", "octaves": 6, "omega": 0.5, "scale": [0.5, 0.5, 0.5]},
+        {"texture_name": "marbled", "texture_type": "MixTexture", "t1": "white", "t2": "wrinkles"},  # amount: float "wrinkles"? unknown -> 0.5
+        {"texture_name": "rippled", "texture_type": "ScaleTexture", "t1": "grad", "t2": "waves"},
     ]
     cfg["materials"] = [
         {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_kd"},
         {"material_type": "MatteMaterial", "material_name": "m_planar", "kd": "planar_check", "sigma": "f_sigma"},
         {"material_type": "PlasticMaterial", "material_name": "m_solid", "kd": "solid_check", "ks": "white", "roughness": "f_rough_check"},
-        {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "roughness": "f_lo"},
-        {"material_type": "MatteMaterial", "material_name": "m_grad", "kd": "grad"},
+        {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "ks": "rippled", "roughness": "f_lo"},
+        {"material_type": "MatteMaterial", "material_name": "m_grad", "kd": "marbled", "sigma": "f_wrinkle"},
         {"material_type": "MetalMaterial", "material_name": "m_metal", "roughness": "f_rough_check", "k": "tinted"},
         {"material_type": "MirrorMaterial", "material_name": "m_mirror", "kr": "cyl"},
     ]

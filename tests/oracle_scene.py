@@ -89,7 +89,7 @@ def _spectrum(cfg, key, default):
 
 
 TEX_ROW = 48
-TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV = range(7)
+TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV, TEX_WINDY, TEX_WRINKLED = range(9)
 
 
 class Textures:
@@ -165,6 +165,12 @@ class Textures:
             for k, v in enumerate((v00, v01, v10, v11)):
                 r[8 + 3 * k: 11 + 3 * k] = v if is_rgb else [v, 0.0, 0.0]
             self._mapping(r, t)
+        elif ty in ("WindyTexture", "WrinkledTexture"):   # IdentityMapping3D::new(to_world) (renderprocess.rs:376-388)
+            r, i = self._row(TEX_WINDY if ty == "WindyTexture" else TEX_WRINKLED, is_rgb)
+            m, _ = to_world(t)
+            r[28:44] = m.reshape(16)
+            if ty == "WrinkledTexture":
+                r[20], r[21] = float(int(t.get("octaves", 8))), float(t.get("omega", 0.5))
         elif ty == "UVTexture" and is_rgb:
             r, i = self._row(TEX_UV, True)
             self._mapping(r, t)

@@ -107,7 +107,7 @@ def test_host_evaluator_is_the_oracles_bit_for_bit(tmp_path):
     rows = product_rows(table)
     rng = np.random.default_rng(11)
     kinds = set(int(k) for k in table[:, 0])
-    assert kinds == set(range(7)), kinds          # the scene covers every in-scope texture kind
+    assert kinds == set(range(9)), kinds          # the scene covers every in-scope texture kind
     assert set(int(k) for k in table[:, 2]) == {0, 1, 2, 3}
     assert set(int(k) for k in table[table[:, 0] == S.TEX_CHECKER2D][:, 3]) == {0, 1}   # point-sampled and closed-form
     filtered = 0
@@ -223,3 +223,34 @@ def test_out_of_scope_textures_are_refused(tmp_path):
         S.load(str(p3))
     with pytest.raises(capi.RrtError):
         R.json_texture_probe(str(p3))
+
+
+def test_noise_textures_known_answers():
+    """WindyTexture / WrinkledTexture over Perlin noise, fBm and turbulence (texture/mod.rs:75-188, windy.rs, wrinkled.rs)."""
+    t = _tex(cfg_float=[{"texture_name": "w0", "texture_type": "WrinkledTexture", "octaves": 0},
+                        {"texture_name": "w3", "texture_type": "WrinkledTexture", "octaves": 3, "omega": 0.5},
+                        {"texture_name": "wind", "texture_type": "WindyTexture"},
+                        {"texture_name": "w8", "texture_type": "WrinkledTexture"}])
+    f = t.f
+    z3 = [0.0] * 3
+    p = (1.37, -2.61, 0.42)
+    # no octaves at all: the partial-octave term alone, lerp(smooth_step(0) = 0, 0.2, |noise|) = 0.2 (:178-184)
+    assert oracle_probe(t.table(), (0, 0), p)[f["w0"]][0] == 0.2
+    # a footprint of several units clamps the octave count to 0 (:165): 0.2 + 0.2 (1 + 1/2 + 1/4) for three octaves,
+    # and fBm's only term is weighted by smooth_step(0) = 0: the wind texture is 0
+    wide = [5.0, 0.0, 0.0, 0.0, 5.0, 0.0, 0, 0, 0, 0]
+    v = oracle_probe(t.table(), (0, 0), p, wide)
+    assert v[f["w3"]][0] == pytest.approx(0.55, abs=1e-15) and v[f["wind"]][0] == 0.0
+    # lattice points: Perlin noise is 0 there, so the first octave adds nothing; with a footprint of 0.25 units
+    # n = -1 - 0.5 log2(1/16) = 1: one full octave (0 at a lattice point), then the partial term with smooth_step(0) = 0
+    # -> 0.2 * omega, then the clamped octaves 1..2: 0.2 (1/2 + 1/4)
+    quarter = [0.25, 0.0, 0.0, 0.0, 0.25, 0.0, 0, 0, 0, 0]
+    v = oracle_probe(t.table(), (0, 0), (3.0, -2.0, 7.0), quarter)
+    assert v[f["w3"]][0] == pytest.approx(0.5 * 0.2 + 0.2 * (0.5 + 0.25), abs=1e-15)
+    # without differentials every octave is summed (log2(0) = -inf): |noise| <= 1 bounds turbulence by the geometric sum
+    vals = np.array([oracle_probe(t.table(), (0, 0), q)[f["w8"]][0] for q in np.random.default_rng(2).uniform(-9, 9, (200, 3))])
+    assert 0.0 < vals.min() and vals.max() < 2.0 and vals.std() > 0.02
+    # a float texture's value reaches a material scalar through component 0; the rgb flavour is grey
+    t2 = _tex(cfg_rgb=[{"texture_name": "w", "texture_type": "WrinkledTexture", "octaves": 4}])
+    g = oracle_probe(t2.table(), (0, 0), p)[t2.rgb["w"]]
+    assert g[0] == g[1] == g[2] > 0
