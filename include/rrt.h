@@ -200,7 +200,10 @@ typedef struct rrt_texture {
 /* Which texture drives each parameter of a material; -1 = the constant held in rrt_material.               */
 typedef enum rrt_material_slot {
     RRT_SLOT_KD = 0, RRT_SLOT_KS, RRT_SLOT_KR, RRT_SLOT_KT, RRT_SLOT_METAL_ETA, RRT_SLOT_METAL_K, RRT_SLOT_SIGMA,
-    RRT_SLOT_ROUGHNESS, RRT_SLOT_U_ROUGHNESS, RRT_SLOT_V_ROUGHNESS, RRT_SLOT_ETA, RRT_MATERIAL_SLOTS
+    RRT_SLOT_ROUGHNESS, RRT_SLOT_U_ROUGHNESS, RRT_SLOT_V_ROUGHNESS, RRT_SLOT_ETA,
+    RRT_SLOT_BUMP_MAP, /* Material::bump (material/mod.rs:22-65): a float texture displaces the shading frame; triangle
+                        * meshes only (a bump-mapped sphere is refused)                                       */
+    RRT_MATERIAL_SLOTS
 } rrt_material_slot;
 
 /* lights/point.rs, lights/distant.rs, lights/diffuse.rs (make_light, renderprocess.rs:967-1053).

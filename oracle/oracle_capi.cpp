@@ -429,6 +429,7 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
         mat.eta = a[23];
         mat.remap_roughness = a[24] != 0.0;
         for (int k = 0; k < 11; ++k) mat.tex[k] = (int32_t)a[26 + k];
+        mat.bump_tex = (int32_t)a[37];
         rs.materials.push_back(mat);
     }
 }

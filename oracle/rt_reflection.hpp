@@ -743,6 +743,7 @@ struct Material {
     bool remap_roughness = false;
     // texture ids of kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta (-1: the constant above)
     int32_t tex[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    int32_t bump_tex = -1;  // bump_map: a float texture (material/*.rs, fetch_float_texture_opt)
     bool textured() const {
         for (int k = 0; k < 11; ++k)
             if (tex[k] >= 0) return true;
@@ -763,6 +764,33 @@ inline Material material_at(const Material& m, const std::vector<Texture>& table
     for (int k = 0; k < 5; ++k)
         if (m.tex[6 + k] >= 0) *fs[k] = vals[m.tex[6 + k]].c[0];
     return r;
+}
+// Material::bump (material/mod.rs:22-65): the shading frame of `si` after displacement by the float texture
+// m.bump_tex.  Literal: du = |dudx| * 0.5 + |dudy| (the 0.5 binds to the first term only, :27), dv = (|dvdx| + |dvdy|) * 0.5;
+// the shifted evaluations move p along shading.dpdu / dpdv and uv by (du, 0) / (0, dv) (the shifted normal is not
+// read by any in-scope texture); set_shading_geometry(.., false) keeps the geometric normal's side.
+inline void material_bump(const Material& m, const std::vector<Texture>& table, SI* si, const RayDiff* ray) {
+    if (m.bump_tex < 0) return;
+    Rgb vals[kMaxTextures];
+    const TexPoint q = compute_differentials(*si, ray);
+    double du = std::fabs(q.dudx) * 0.5 + std::fabs(q.dudy);
+    if (du == 0.0) du = 0.0005;
+    TexPoint e = q;
+    e.p = si->p + si->sh.dpdu * du;
+    e.uv = P2(si->uv.x + du, si->uv.y + 0.0);
+    tex_eval_all(table, e, vals);
+    const double u_displace = vals[m.bump_tex].c[0];
+    double dv = (std::fabs(q.dvdx) + std::fabs(q.dvdy)) * 0.5;
+    if (dv == 0.0) dv = 0.0005;
+    e.p = si->p + si->sh.dpdv * dv;
+    e.uv = P2(si->uv.x + 0.0, si->uv.y + dv);
+    tex_eval_all(table, e, vals);
+    const double v_displace = vals[m.bump_tex].c[0];
+    tex_eval_all(table, q, vals);
+    const double displace = vals[m.bump_tex].c[0];
+    V3 dpdu = si->sh.dpdu + v3div(si->sh.n * (u_displace - displace), du) + si->sh.dndu * displace;
+    V3 dpdv = si->sh.dpdv + v3div(si->sh.n * (v_displace - displace), dv) + si->sh.dndv * displace;
+    si_set_shading_geometry(*si, dpdu, dpdv, si->sh.dndu, si->sh.dndv, false);
 }
 // Fills si-dependent Bsdf exactly as the material's compute_scattering_functions would
 // (bump maps are out of scope).  `allow_multiple_lobes` as passed by the integrator.

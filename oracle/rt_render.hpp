@@ -258,6 +258,7 @@ struct Integrator {
             (void)specular_bounce;  // isect.le() == 0 (Q22) and there are no infinite lights in scope
             if (!found || bounces >= max_depth) break;
             Bsdf bsdf;
+            material_bump(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, &isect, bounces == 0 ? &camera : nullptr);
             material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, bounces == 0 ? &camera : nullptr),
                           isect, true, &bsdf);
             if (!bsdf.present) {
@@ -308,6 +309,7 @@ struct Integrator {
         if (first_hit) *first_hit = rec;
         if (!found) return l;  // Light::le of point / distant lights is zero
         Bsdf bsdf;
+        material_bump(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, &isect, camera);
         material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, camera), isect, false, &bsdf);
         if (!bsdf.present) return li_direct(sc, ray_new_od(isect.p, ray.d), sampler, depth, st, nullptr);
         if (!sc.lights.empty())

@@ -763,11 +763,17 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
         bool alive = found && !(ip.kind == RRT_INTEGRATOR_PATH && p.bounces >= ip.max_depth);
         if (alive) {
             Surface s;
-            make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
+            BumpPartials bp;
+            if (TEXTURED)
+                make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s, sc.bump ? &bp : nullptr);
+            else
+                make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
             Bsdf bsdf;
             if (TEXTURED) {
                 const MaterialRec* m = sc.materials + s.material;
                 MaterialRec textured;
+                if (m->bump_needed)
+                    material_bump(sc, *m, (sc.ray_diffs != nullptr && p.bounces == 0) ? sc.ray_diffs + pid : nullptr, &s, bp);
                 if (m->needed) {
                     // the camera ray is the only one with differentials (path.rs:163, directlighting.rs:91-94)
                     material_at(sc, *m, s, (sc.ray_diffs != nullptr && p.bounces == 0) ? sc.ray_diffs + pid : nullptr, &textured);
@@ -1485,7 +1491,10 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
             r.eta = m.eta;
             for (int k = 0; k < RRT_MATERIAL_SLOTS; ++k) {
                 r.tex[k] = material_slots.empty() ? -1 : material_slots[i * RRT_MATERIAL_SLOTS + k];
-                r.needed |= texture_closure(texs.data(), r.tex[k]);
+                if (k == RRT_SLOT_BUMP_MAP)
+                    r.bump_needed = texture_closure(texs.data(), r.tex[k]);
+                else
+                    r.needed |= texture_closure(texs.data(), r.tex[k]);
             }
             mats[i] = r;
         }
@@ -1536,7 +1545,15 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
         if ((rc = I.up(texs, &S.textures, err)) != RRT_OK) return rc;
         uint32_t reached = 0;
-        for (const MaterialRec& m : mats) reached |= m.needed;
+        for (const MaterialRec& m : mats) {
+            reached |= m.needed | m.bump_needed;
+            S.bump |= m.bump_needed != 0 ? 1u : 0u;
+        }
+        for (const Primitive& p : scene.prims)
+            if (p.kind == SHAPE_SPHERE && mats[p.material].bump_needed) {
+                if (err) *err = "a bump map on a sphere is outside the hot-path scope (triangle meshes only)";
+                return RRT_ERR_UNSUPPORTED;
+            }
         I.textured = reached != 0;
         // make_surface fills uv / dpdu / dpdv only when someone reads them
         S.n_textures = I.textured ? (uint32_t)texs.size() : 0u;

@@ -391,7 +391,12 @@ bool make_material(const Value& m, const TextureTable& t, rrt_material* out, int
     } else {
         return false;  // Disney / Translucent / Mix / Debug: outside the hot path
     }
-    if (m.get("bump_map") && m.get("bump_map")->is_string()) throw std::runtime_error("bump maps are outside the hot-path scope");
+    if (const Value* bm = m.get("bump_map"); bm && bm->is_string()) {  // fetch_float_texture_opt(.., "bump_map", None)
+        auto it = t.f.find(bm->str);
+        if (it == t.f.end()) throw std::runtime_error("float texture '" + bm->str + "' does not exist");
+        if (it->second == -2) throw std::runtime_error("texture '" + bm->str + "' has a type outside the hot-path scope");
+        slots[RRT_SLOT_BUMP_MAP] = it->second;  // the table row itself, constant or not
+    }
     *out = r;
     return true;
 }

@@ -52,9 +52,9 @@ class Texture(C.Structure):
 
 
 MAX_TEXTURES = 32
-MATERIAL_SLOTS = 11
+MATERIAL_SLOTS = 12
 (SLOT_KD, SLOT_KS, SLOT_KR, SLOT_KT, SLOT_METAL_ETA, SLOT_METAL_K, SLOT_SIGMA, SLOT_ROUGHNESS, SLOT_U_ROUGHNESS,
- SLOT_V_ROUGHNESS, SLOT_ETA) = range(11)
+ SLOT_V_ROUGHNESS, SLOT_ETA, SLOT_BUMP_MAP) = range(12)
 TEX_CONSTANT, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV, TEX_WINDY, TEX_WRINKLED = range(9)
 TEXMAP_UV, TEXMAP_PLANAR, TEXMAP_SPHERICAL, TEXMAP_CYLINDRICAL = range(4)
 

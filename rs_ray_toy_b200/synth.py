@@ -280,7 +280,7 @@ def write_floor_obj(path, half=6.0, y=-2.4, cx=35.2, cz=0.0, uv_scale=8.0):
 
 def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
     """SURVEY.md §8f row 3 (procedural part): config 1's cubes on a floor, plus three spheres, with every in-scope texture
-    type driving a material parameter — Checkerboard 2D over mesh uvs (closed-form filter: the loader's default, fed by
+    type driving a material parameter or a bump map — Checkerboard 2D over mesh uvs (closed-form filter: the loader's default, fed by
     the camera ray's differentials) and over a planar mapping (point-sampled),
     Checkerboard 3D with a texture transform, Bilerp (float and rgb), Scale, Mix (whose amount is looked up under
     "t2", renderprocess.rs:319), UV, spherical and cylindrical mappings — on Matte / Plastic / Metal / Mirror."""
@@ -302,6 +302,9 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         {"texture_name": "f_sigma", "texture_type": "ScaleTexture", "t1": "f_ramp", "t2": "f_sixty"},  # f_sixty unknown: 1.0
         {"texture_name": "dark", "texture_type": "BilerpTexture", "v00": 0.3, "v01": 0.3},   # float amount for the rgb Mix below
         {"texture_name": "f_wrinkle", "texture_type": "WrinkledTexture", "octaves": 5, "omega": 0.6, "scale": [0.7, 0.7, 0.7]},
+        # bump maps (Material::bump): a uv-mapped ramp scaled down to millimetres on the floor, the noise on a cube
+        {"texture_name": "f_small", "texture_type": "BilerpTexture", "v00": 0.05, "v01": 0.05},
+        {"texture_name": "f_bumps", "texture_type": "ScaleTexture", "t1": "f_ramp", "t2": "f_small"},
     ]
     cfg["rgb_texture"] = [
         _const_rgb_texture("white", (0.85, 0.85, 0.8)),
@@ -332,8 +335,8 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         {"texture_name": "rippled", "texture_type": "ScaleTexture", "t1": "grad", "t2": "waves"},
     ]
     cfg["materials"] = [
-        {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_kd"},
-        {"material_type": "MatteMaterial", "material_name": "m_planar", "kd": "planar_check", "sigma": "f_sigma"},
+        {"material_type": "MatteMaterial", "material_name": "m_floor", "kd": "floor_kd", "bump_map": "f_bumps"},
+        {"material_type": "MatteMaterial", "material_name": "m_planar", "kd": "planar_check", "sigma": "f_sigma", "bump_map": "f_wrinkle"},
         {"material_type": "PlasticMaterial", "material_name": "m_solid", "kd": "solid_check", "ks": "white", "roughness": "f_rough_check"},
         {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "ks": "rippled", "roughness": "f_lo"},
         {"material_type": "MatteMaterial", "material_name": "m_grad", "kd": "marbled", "sigma": "f_wrinkle"},

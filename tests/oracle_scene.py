@@ -235,7 +235,7 @@ class Textures:
 
 MAT_ROW = 40
 # texture-id slots of a material row (26 + k): kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta
-T_KD, T_KS, T_KR, T_KT, T_ETA_RGB, T_K_RGB, T_SIGMA, T_ROUGH, T_UR, T_VR, T_ETA = range(11)
+T_KD, T_KS, T_KR, T_KT, T_ETA_RGB, T_K_RGB, T_SIGMA, T_ROUGH, T_UR, T_VR, T_ETA, T_BUMP = range(12)
 
 
 def material_row(cfg, tex: Textures):
@@ -246,7 +246,7 @@ def material_row(cfg, tex: Textures):
     r = np.zeros(MAT_ROW)
     r[0] = kind
     r[21] = r[22] = -1.0
-    r[26:37] = -1
+    r[26:38] = -1
 
     def rgb(lo, slot, key, default):
         r[lo:lo + 3], r[26 + slot] = tex.rgbval(cfg, key, default)
@@ -277,6 +277,14 @@ def material_row(cfg, tex: Textures):
         flt(21, T_UR, "u_roughness", 0.0)
         flt(22, T_VR, "v_roughness", 0.0)
     r[24] = 1.0 if cfg.get("remap_roughness", False) else 0.0
+    bump = cfg.get("bump_map")            # fetch_float_texture_opt(.., "bump_map", None) (renderprocess.rs:704-705)
+    r[37] = -1
+    if isinstance(bump, str):
+        if bump not in tex.f:
+            raise ValueError(f"float texture {bump!r} does not exist (the reference panics: renderprocess.rs:634)")
+        if tex.f[bump] == -2:
+            raise ValueError(f"texture {bump!r} has a type outside the restated subset")
+        r[37] = tex.f[bump]
     return r
 
 

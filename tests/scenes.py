@@ -108,7 +108,7 @@ def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthre
     s.add_prims(g1, n_tris - half, -1)
     s.build(4)
     mats = np.zeros((2, S.MAT_ROW))
-    mats[:, 26:37] = -1
+    mats[:, 26:38] = -1
     mats[0, 0] = 0
     mats[0, 1:4] = (0.6, 0.55, 0.5)
     mats[1, 0] = 1

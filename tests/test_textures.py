@@ -191,7 +191,7 @@ def test_loaders_agree(tmp_path):
         assert np.array_equal(row[20:28], np.array(list(t.map)))
         if t.kind == R.TEX_CHECKER3D or t.mapping >= R.TEXMAP_SPHERICAL:
             assert np.array_equal(row[28:44], np.array(list(t.world_to_texture)))
-    assert np.array_equal(sc.materials[:, 26:37].astype(np.int32), slots)
+    assert np.array_equal(sc.materials[:, 26:38].astype(np.int32), slots)
     for row, m in zip(sc.materials, mats):
         assert int(row[0]) == m.kind
         assert np.array_equal(row[1:4], list(m.kd)) and np.array_equal(row[4:7], list(m.ks))
