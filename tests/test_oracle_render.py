@@ -334,3 +334,25 @@ def test_sample_all_lights_is_one_estimate_per_light(tmp_path):
     m1, m2 = one["rgb"].mean(axis=(0, 1)), every["rgb"].mean(axis=(0, 1))
     assert np.allclose(m1, m2, rtol=0.05), (m1, m2)
     assert not np.allclose(one["rgb"], every["rgb"])
+
+
+def test_bump_map_known_cases(tmp_path):
+    """Material::bump (material/mod.rs:22-65) on the sample scene's cubes (per-face vertex normals: dndu = dndv = 0).
+    A constant displacement leaves the shading tangents as they were — dpdu + n (d - d) / du + dndu d — and the
+    normal becomes normalize(ss x ts) instead of the face normal the triangle code had put there (interaction.rs:186-202,
+    authoritative orientation): the same direction to rounding, so the image moves by rounding only; a ramp tilts every
+    normal and changes it."""
+    path = synth.scene_c1(str(tmp_path), xres=96, yres=54, nsamp=5)
+    mats = lambda extra: [{"material_type": "MetalMaterial", "material_name": "mat_metal"},
+                          {"material_type": "PlasticMaterial", "material_name": "mat_plastic"},
+                          dict({"material_type": "MatteMaterial", "material_name": "mat_matte"}, **extra)]
+    plain = S.load(path, {"materials": mats({})}).render(seed=1)
+    ftex = [{"texture_name": "flat", "texture_type": "BilerpTexture", "v00": 0.3, "v01": 0.3},
+            {"texture_name": "ramp", "texture_type": "BilerpTexture", "v00": 0.0},          # corners 0 1 0 1: d = t
+            {"texture_name": "tilt", "texture_type": "ScaleTexture", "t1": "ramp", "t2": "flat"}]
+    flat = S.load(path, {"float_texture": ftex, "materials": mats({"bump_map": "flat"})}).render(seed=1)
+    rel = np.sqrt(np.mean((plain["rgb"] - flat["rgb"]) ** 2)) / np.sqrt(np.mean(plain["rgb"] ** 2))
+    assert rel < 1e-9, rel
+    tilt = S.load(path, {"float_texture": ftex, "materials": mats({"bump_map": "tilt"})}).render(seed=1)
+    assert not np.allclose(plain["rgb"], tilt["rgb"])
+    assert tilt["stats"]["camera_rays"] == plain["stats"]["camera_rays"]
