@@ -201,8 +201,7 @@ typedef struct rrt_texture {
 typedef enum rrt_material_slot {
     RRT_SLOT_KD = 0, RRT_SLOT_KS, RRT_SLOT_KR, RRT_SLOT_KT, RRT_SLOT_METAL_ETA, RRT_SLOT_METAL_K, RRT_SLOT_SIGMA,
     RRT_SLOT_ROUGHNESS, RRT_SLOT_U_ROUGHNESS, RRT_SLOT_V_ROUGHNESS, RRT_SLOT_ETA,
-    RRT_SLOT_BUMP_MAP, /* Material::bump (material/mod.rs:22-65): a float texture displaces the shading frame; triangle
-                        * meshes only (a bump-mapped sphere is refused)                                       */
+    RRT_SLOT_BUMP_MAP, /* Material::bump (material/mod.rs:22-65): a float texture displaces the shading frame         */
     RRT_MATERIAL_SLOTS
 } rrt_material_slot;
 

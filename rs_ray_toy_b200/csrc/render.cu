@@ -1549,11 +1549,6 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
             reached |= m.needed | m.bump_needed;
             S.bump |= m.bump_needed != 0 ? 1u : 0u;
         }
-        for (const Primitive& p : scene.prims)
-            if (p.kind == SHAPE_SPHERE && mats[p.material].bump_needed) {
-                if (err) *err = "a bump map on a sphere is outside the hot-path scope (triangle meshes only)";
-                return RRT_ERR_UNSUPPORTED;
-            }
         I.textured = reached != 0;
         // make_surface fills uv / dpdu / dpdv only when someone reads them
         S.n_textures = I.textured ? (uint32_t)texs.size() : 0u;

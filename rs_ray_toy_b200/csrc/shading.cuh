@@ -127,6 +127,24 @@ __device__ __forceinline__ void xf_surface_bump_partials(const M34& m, const M34
     s->shdndv = xf_normal_inv(inv, s->shdndv);
 }
 
+// sphere.rs:205-232: shading.dpdv and dndu / dndv from the second derivatives (Weingarten equations), carried to the
+// sphere's world space like the rest of the SurfaceInteraction (sphere.rs:245-255)
+static __device__ __noinline__ void sphere_bump_partials(const SphereInfo& sp, V3 p, V3 dpdu, V3 dpdv, double cos_phi, double sin_phi,
+                                                         BumpPartials* bp) {
+    const double dtheta = sp.theta_max - sp.theta_min;
+    const V3 d2pduu = v3(p.x, p.y, 0.0) * -sp.phi_max * sp.phi_max;
+    const V3 d2pduv = v3(-sin_phi, cos_phi, 0.0) * dtheta * p.z * sp.phi_max;
+    const V3 d2pdvv = p * -dtheta * dtheta;
+    const double E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+    const V3 N = normalize(cross(dpdu, dpdv));
+    const double e = dot(N, d2pduu), ff = dot(N, d2pduv), gg = dot(N, d2pdvv);
+    const double inv_EGF2 = 1.0 / (E * G - F * F);
+    bp->shdpdv = dpdv;
+    bp->shdndu = dpdu * ((ff * F - e * G) * inv_EGF2) + dpdv * ((e * F - ff * E) * inv_EGF2);
+    bp->shdndv = dpdu * ((gg * F - ff * G) * inv_EGF2) + dpdv * ((ff * F - gg * E) * inv_EGF2);
+    xf_surface_bump_partials(sp.o2w, sp.w2o, bp);
+}
+
 // Rebuilds the surface frame of hit (prim_id, t, u, v) for the world ray (o, d).
 static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
                                           Surface* out, BumpPartials* bp = nullptr) {
@@ -248,6 +266,7 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
         const double cos_phi = p.x * inv_z_radius, sin_phi = p.y * inv_z_radius;
         const V3 dpdu = v3(-sp.phi_max * p.y, sp.phi_max * p.x, 0.0);
         const V3 dpdv = v3(p.z * cos_phi, p.z * sin_phi, -sp.radius * sin(theta)) * (sp.theta_max - sp.theta_min);
+        if (bp) sphere_bump_partials(sp, p, dpdu, dpdv, cos_phi, sin_phi, bp);  // out of line: bump-mapped scenes only
         s.p = p;
         s.wo = -od;
         s.n = normalize(cross(dpdu, dpdv));

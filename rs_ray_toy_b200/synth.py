@@ -340,7 +340,7 @@ def scene_textured(directory, xres=192, yres=108, nsamp=9, integrator="Path", ma
         {"material_type": "PlasticMaterial", "material_name": "m_solid", "kd": "solid_check", "ks": "white", "roughness": "f_rough_check"},
         {"material_type": "PlasticMaterial", "material_name": "m_mixed", "kd": "mixed", "ks": "rippled", "roughness": "f_lo"},
         {"material_type": "MatteMaterial", "material_name": "m_grad", "kd": "marbled", "sigma": "f_wrinkle"},
-        {"material_type": "MetalMaterial", "material_name": "m_metal", "roughness": "f_rough_check", "k": "tinted"},
+        {"material_type": "MetalMaterial", "material_name": "m_metal", "roughness": "f_rough_check", "k": "tinted", "bump_map": "f_wrinkle"},
         {"material_type": "MirrorMaterial", "material_name": "m_mirror", "kr": "cyl"},
     ]
     cfg["objs"].append({"filename": "floor.obj", "obj_name": "floor_01"})
