@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "rt_bvh.hpp"
+#include "rt_sampling.hpp"
 
 using namespace orc;
 
@@ -326,6 +327,45 @@ void orc_kat_bounds(const double* p1, const double* p2, const double* p3, double
     b3_bounding_sphere(b, &c, &r);
     out10[6] = c.x; out10[7] = c.y; out10[8] = c.z; out10[9] = r;
 }
+// test_bnd2 (geometry.rs:1974-1980): the points of `for p in b.into_iter()`, and Bounds2i::inside of each
+uint64_t orc_kat_bounds2i_iter(int64_t x0, int64_t y0, int64_t x1, int64_t y1, int64_t* out_xy_inside, uint64_t cap) {
+    Bounds2iIter it(x0, y0, x1, y1);
+    uint64_t n = 0;
+    int64_t px, py;
+    while (it.next(&px, &py)) {
+        if (n < cap) {
+            out_xy_inside[3 * n] = px;
+            out_xy_inside[3 * n + 1] = py;
+            out_xy_inside[3 * n + 2] = bounds2i_inside(px, py, x0, y0, x1, y1) ? 1 : 0;
+        }
+        ++n;
+    }
+    return n;
+}
+// PixelSampler<Stratified> for one pixel: the 1D tables [ndims][n], the 2D tables [ndims][n][2] as start_pixel leaves
+// them, and for every sample the first four overflow draws (a get_1d past the tables).
+void orc_kat_stratified(uint64_t seed, int64_t xres, int64_t px, int64_t py, uint32_t xs, uint32_t ys, uint32_t ndims,
+                        int32_t jitter, double* out1d, double* out2d, double* overflow4) {
+    StratifiedParams sp;
+    sp.xs = xs; sp.ys = ys; sp.ndims = ndims; sp.jitter = jitter != 0; sp.seed = seed; sp.xres = xres;
+    StratifiedSampler sm;
+    sm.sp = &sp;
+    sm.samples_per_pixel = (uint64_t)xs * ys;
+    sm.start_pixel(px, py);
+    const uint32_t n = xs * ys;
+    for (uint32_t d = 0; d < ndims; ++d)
+        for (uint32_t i = 0; i < n; ++i) {
+            out1d[d * n + i] = sm.s1[d][i];
+            out2d[2 * (d * n + i)] = sm.s2[d][i].x;
+            out2d[2 * (d * n + i) + 1] = sm.s2[d][i].y;
+        }
+    uint32_t k = 1;
+    while (sm.start_next_sample()) {
+        for (uint32_t d = 0; d < ndims; ++d) sm.get_1d();
+        for (int j = 0; j < 4; ++j) overflow4[4 * k + j] = sm.get_1d();
+        ++k;
+    }
+}
 uint32_t orc_kat_left_shift3(uint32_t x) { return left_shift3(x); }
 uint32_t orc_kat_morton(double x, double y, double z) { return encode_morton3(V3(x, y, z)); }
 void orc_kat_radix_sort(uint32_t n, uint32_t* idx, uint32_t* codes) {
@@ -634,6 +674,18 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
         job.samples_per_pixel = (uint64_t)prm[23];
         job.halton.init(job.film.crop[2] - job.film.crop[0], job.film.crop[3] - job.film.crop[1], prm[24] != 0.0);
         job.perms = compute_radical_inverse_permutations((uint64_t)prm[25]);
+        // prm[38] sampler kind (0 Halton, 1 Stratified: make_sampler, renderprocess.rs:1306-1325), 39 jitter,
+        // 40 xsamp, 41 ysamp, 42 dimension
+        job.sampler_kind = (int)prm[38];
+        if (job.sampler_kind == 1) {
+            job.stratified.xs = (uint32_t)prm[40];
+            job.stratified.ys = (uint32_t)prm[41];
+            job.stratified.ndims = (uint32_t)prm[42];
+            job.stratified.jitter = prm[39] != 0.0;
+            job.stratified.seed = (uint64_t)prm[25];
+            job.stratified.xres = job.film.xres;
+            job.samples_per_pixel = (uint64_t)job.stratified.xs * job.stratified.ys;
+        }
         job.integrator.kind = (uint32_t)prm[26];
         job.integrator.max_depth = (uint32_t)prm[27];
         job.integrator.rr_threshold = prm[28];

@@ -277,4 +277,26 @@ B3 xf_bounds(const Xform& t, const B3& b);  // transform.rs:539-616
 // false = Tier-F (Q6 fixed: d is carried unnormalised so t is shared between spaces).
 Ray xf_ray(const Xform& t, const Ray& r, bool renorm);
 
+// Bounds2Iterator (geometry.rs:1489-1526): starts one to the left of p_min, every next() steps x and wraps to the next
+// row at p_max.x; the walk ends when y reaches p_max.y.  (An empty-width bound would never leave x = p_min.x; tile
+// bounds are never empty.)  Also Bounds2i::inside (:1418-1423), closed on both ends — what test_bnd2 asserts.
+struct Bounds2iIter {
+    int64_t x, y, x0, x1, y1;
+    Bounds2iIter(int64_t bx0, int64_t by0, int64_t bx1, int64_t by1) : x(bx0 - 1), y(by0), x0(bx0), x1(bx1), y1(by1) {}
+    bool next(int64_t* px, int64_t* py) {
+        x += 1;
+        if (x == x1) {
+            x = x0;
+            y += 1;
+        }
+        if (y == y1) return false;
+        *px = x;
+        *py = y;
+        return true;
+    }
+};
+inline bool bounds2i_inside(int64_t px, int64_t py, int64_t x0, int64_t y0, int64_t x1, int64_t y1) {
+    return px >= x0 && px <= x1 && py >= y0 && py <= y1;
+}
+
 }  // namespace orc

@@ -17,7 +17,7 @@
 
 namespace orc {
 
-enum IntegratorKind : uint32_t { INTEGRATOR_PATH = 0, INTEGRATOR_DIRECT = 1 };
+enum IntegratorKind : uint32_t { INTEGRATOR_PATH = 0, INTEGRATOR_DIRECT = 1, INTEGRATOR_DEBUG = 2 };
 
 struct RenderStats {
     uint64_t camera_rays = 0, extension_rays = 0, shadow_rays = 0, bounces = 0, zero_weight = 0, asserts = 0;
@@ -202,7 +202,7 @@ struct RenderScene {
         return ld;
     }
     // uniform_sample_one_light (integrator/mod.rs:359-401)
-    Rgb uniform_sample_one_light(const SI& si, const Bsdf& bsdf, HaltonSampler& sampler, const Distribution1D* distrib,
+    Rgb uniform_sample_one_light(const SI& si, const Bsdf& bsdf, Sampler& sampler, const Distribution1D* distrib,
                                  RenderStats* st) const {
         size_t n_lights = lights.size();
         if (n_lights == 0) return Rgb();
@@ -223,7 +223,7 @@ struct RenderScene {
     // requests its 2D sample arrays on a throwaway sampler (`pre_sampler`, integrator/mod.rs:50-51) — the tile samplers
     // are built afresh and hold none, get_2d_array returns an empty slice (samplers/mod.rs:108-111), and every light
     // takes the single-sample branch (:321-335): two get_2d per light, one estimate, no division.
-    Rgb uniform_sample_all_lights(const SI& si, const Bsdf& bsdf, HaltonSampler& sampler, RenderStats* st) const {
+    Rgb uniform_sample_all_lights(const SI& si, const Bsdf& bsdf, Sampler& sampler, RenderStats* st) const {
         Rgb l;
         for (size_t j = 0; j < lights.size(); ++j) {
             P2 u_light = sampler.get_2d();
@@ -243,7 +243,7 @@ struct Integrator {
 
     // PathIntegrator::li (path.rs:51-226)
     // `camera` carries the differentials of the camera ray; every later ray is spawn_ray(..).into(): none
-    Rgb li_path(const RenderScene& sc, const RayDiff& camera, HaltonSampler& sampler, RenderStats* st, HitRecord* first_hit) const {
+    Rgb li_path(const RenderScene& sc, const RayDiff& camera, Sampler& sampler, RenderStats* st, HitRecord* first_hit) const {
         Ray ray = camera.ray;
         Rgb l, beta(1.0);
         bool specular_bounce = false;
@@ -299,7 +299,7 @@ struct Integrator {
     }
     // DirectLightingIntegrator::li with UniformSampleOne (directlighting.rs:72-132).  The specular
     // recursion (integrator/mod.rs:150-301) is followed without ray differentials.
-    Rgb li_direct(const RenderScene& sc, Ray ray, HaltonSampler& sampler, uint32_t depth, RenderStats* st,
+    Rgb li_direct(const RenderScene& sc, Ray ray, Sampler& sampler, uint32_t depth, RenderStats* st,
                   HitRecord* first_hit, const RayDiff* camera = nullptr) const {
         Rgb l;
         SI isect;
@@ -329,6 +329,43 @@ struct Integrator {
         }
         return l;
     }
+    // IntersectDebugIntegrator::li (integrator/intersect_debug.rs:56-89): a constant 0.1 for any hit, plus
+    // uniform_sample_all_lights as it runs (Q30), plus the specular recursion of integrator/mod.rs:150-301 (each half
+    // draws its get_2d whether or not the BSDF has a specular lobe).  compute_scattering_functions is called with
+    // allow_multiple_lobes = false.
+    Rgb li_debug(const RenderScene& sc, Ray ray, Sampler& sampler, uint32_t depth, RenderStats* st, HitRecord* first_hit,
+                 const RayDiff* camera = nullptr) const {
+        SI isect;
+        HitRecord rec;
+        if (st) st->extension_rays += 1;
+        bool found = sc.intersect_with_record(ray, &isect, &rec, st);
+        if (first_hit) *first_hit = rec;
+        if (!found) return Rgb();
+        Rgb l(0.1);
+        Bsdf bsdf;
+        material_bump(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, &isect, camera);
+        material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, camera), isect, false, &bsdf);
+        Rgb sl;
+        if (!sc.lights.empty()) {
+            // estimate_direct with no BSDF: f stays zero, nothing is added (integrator/mod.rs:430-447) — but the
+            // two get_2d per light are still drawn
+            sl += sc.uniform_sample_all_lights(isect, bsdf, sampler, st);
+        }
+        if (depth + 1 < max_depth) {
+            for (int pass = 0; pass < 2; ++pass) {
+                if (!bsdf.present) break;  // specular_reflect / specular_transmit return zero before drawing
+                uint8_t ty = BXDF_SPECULAR | (pass == 0 ? BXDF_REFLECTION : BXDF_TRANSMISSION);
+                V3 wi;
+                double pdf = 0.0;
+                uint8_t sampled = 0;
+                Rgb f = bsdf.sample_f(isect.wo, &wi, sampler.get_2d(), &pdf, ty, &sampled);
+                V3 ns = isect.sh.n;
+                if (pdf > 0.0 && !f.is_black() && absdot(wi, ns) != 0.0)
+                    sl += f * li_debug(sc, ray_new_od(isect.p, wi), sampler, depth + 1, st, nullptr) * absdot(wi, ns) / pdf;
+            }
+        }
+        return l + sl;
+    }
 };
 
 struct RenderJob {
@@ -337,6 +374,8 @@ struct RenderJob {
     RealisticCamera camera;
     Integrator integrator;
     HaltonParams halton;
+    StratifiedParams stratified;
+    int sampler_kind = 0;  // 0 Halton, 1 Stratified
     std::vector<uint16_t> perms;
     uint64_t samples_per_pixel = 16;  // `nsamp`: nsamp - 1 samples are rendered (Q10)
     RenderStats stats;
@@ -368,13 +407,17 @@ struct RenderJob {
                 tb[2] = std::min(tb[0] + tile_size, sb[2]);
                 tb[3] = std::min(tb[1] + tile_size, sb[3]);
                 if (crop_px && (tb[2] <= crop_px[0] || tb[0] >= crop_px[2] || tb[3] <= crop_px[1] || tb[1] >= crop_px[3])) continue;
-                HaltonSampler sampler;
-                sampler.hp = &halton;
-                sampler.perms = perms.data();
-                sampler.samples_per_pixel = samples_per_pixel;
+                Sampler sampler;
+                sampler.kind = sampler_kind;
+                sampler.h.hp = &halton;
+                sampler.h.perms = perms.data();
+                sampler.h.samples_per_pixel = samples_per_pixel;
+                sampler.s.sp = &stratified;
+                sampler.s.samples_per_pixel = samples_per_pixel;
                 FilmTile* tile = new FilmTile(film, tb);
-                for (int64_t py = tb[1]; py < tb[3]; ++py)
-                    for (int64_t px = tb[0]; px < tb[2]; ++px) {
+                Bounds2iIter pixels(tb[0], tb[1], tb[2], tb[3]);  // `for pixel in tile_bounds.into_iter()`
+                int64_t px, py;
+                while (pixels.next(&px, &py)) {
                         sampler.start_pixel(px, py);
                         // pixel_bounds = full resolution (renderprocess.rs:1410)
                         if (!(px >= 0 && px < film.xres && py >= 0 && py < film.yres)) continue;
@@ -389,13 +432,15 @@ struct RenderJob {
                             RayDiff rd;
                             double w = camera.generate_ray_differential(cs, &rd);
                             // integrator/mod.rs:92-94
-                            rd.scale_differentials(1.0 / std::sqrt((double)sampler.samples_per_pixel));
+                            rd.scale_differentials(1.0 / std::sqrt((double)sampler.samples_per_pixel()));
                             Rgb l;
                             HitRecord first;
                             if (w > 0.0) {
                                 st.camera_rays += 1;
                                 if (integrator.kind == INTEGRATOR_PATH)
                                     l = integrator.li_path(scene, rd, sampler, &st, &first);
+                                else if (integrator.kind == INTEGRATOR_DEBUG)
+                                    l = integrator.li_debug(scene, rd.ray, sampler, 1, &st, &first, &rd);
                                 else
                                     l = integrator.li_direct(scene, rd.ray, sampler, 1, &st, &first, &rd);
                             } else {
@@ -403,7 +448,7 @@ struct RenderJob {
                             }
                             if (l.has_nan() || l.y() < -1e-5 || std::isinf(l.y())) l = Rgb();
                             if (want_dump)
-                                tdump[tid].push_back(HitDump{(int32_t)px, (int32_t)py, (int32_t)sampler.current_sample_index,
+                                tdump[tid].push_back(HitDump{(int32_t)px, (int32_t)py, (int32_t)sampler.current_sample_index(),
                                                              w > 0.0 ? first.prim : -2, w > 0.0 && first.prim >= 0 ? first.t : 0.0, w});
                             tile->add_sample(cs.p_film, l, w);
                         }

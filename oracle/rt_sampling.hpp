@@ -309,4 +309,113 @@ struct HaltonSampler {
     }
 };
 
+// ---- samplers/stratified.rs + PixelSampler (samplers/mod.rs:131-252) ---------------------------
+// PixelSampler<Stratified>: `n_sampled_dimensions` 1D and as many 2D dimensions are generated for the whole pixel
+// in start_pixel (one stratified set per dimension, then shuffled); a get_1d / get_2d beyond them draws a fresh
+// U[-1, 1) (sic, Q12: `rng.gen_range(-1.0..1.0)`, samplers/mod.rs:211-226).  Sample arrays are never filled in the
+// tile samplers (Q30), so they are not restated.  Q10 applies: start_next_sample pre-increments, sample 0 is never
+// rendered, `xsamp * ysamp` = 16 gives 15 samples.
+//
+// The deliberate departure, as for Halton: every draw of the reference comes from an unseeded thread_rng (rand 0.8.3,
+// ChaCha12), so two runs of the reference disagree.  Here the draws come from PCG32 streams that are a pure function of
+// (seed, pixel, dimension) — stream 2d / 2d+1 for the 1D / 2D tables of dimension d, one more for the overflow draws —
+// which keeps the result independent of tiles and threads and lets the device regenerate one dimension on its own.
+// What is pinned by the reference is the DISTRIBUTION (stratum layout, jitter, shuffle, the dropped sample 0), which
+// tests/test_reference_image.py checks against samples/scene.png statistically.
+struct StratifiedParams {
+    uint32_t xs = 4, ys = 4, ndims = 4;
+    bool jitter = true;
+    uint64_t seed = 1;
+    int64_t xres = 0;
+};
+inline uint64_t stratified_stream(const StratifiedParams& sp, int64_t px, int64_t py, uint32_t k) {
+    // one PCG32 sequence id per (pixel, table); pixels outside the image (negative coordinates) are never sampled
+    return (uint64_t)(py * sp.xres + px) * 64u + k;
+}
+inline double pcg_unit(Pcg32& r) {  // rng.gen_range(0.0..1.0): 53 random bits
+    uint64_t hi = r.next(), lo = r.next();
+    return (double)(((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+struct StratifiedSampler {
+    const StratifiedParams* sp = nullptr;
+    uint64_t samples_per_pixel = 0, current_sample_index = 0;
+    uint32_t d1 = 0, d2 = 0;
+    int64_t px = 0, py = 0;
+    std::vector<std::vector<double>> s1;
+    std::vector<std::vector<P2>> s2;
+    Pcg32 overflow{0};
+    // stratified.rs:34-91 (start_pixel_ps) — 1D tables first, then 2D tables
+    void start_pixel(int64_t x, int64_t y) {
+        px = x;
+        py = y;
+        const uint32_t n = sp->xs * sp->ys;
+        s1.assign(sp->ndims, std::vector<double>(samples_per_pixel));
+        s2.assign(sp->ndims, std::vector<P2>(samples_per_pixel));
+        for (uint32_t d = 0; d < sp->ndims; ++d) {
+            Pcg32 r(sp->seed, stratified_stream(*sp, x, y, 2 * d));
+            const double inv = 1.0 / (double)n;  // stratified_sample1d (:93-100)
+            for (uint32_t i = 0; i < n; ++i) {
+                double delta = sp->jitter ? pcg_unit(r) : 0.5;
+                s1[d][i] = std::fmin(((double)i + delta) * inv, ONE_MINUS_EPSILON);
+            }
+            for (uint32_t i = 0; i < n; ++i) {  // shuffle (sampling.rs:181-193), one dimension
+                uint32_t other = i + r.below(n - i);
+                std::swap(s1[d][i], s1[d][other]);
+            }
+        }
+        for (uint32_t d = 0; d < sp->ndims; ++d) {
+            Pcg32 r(sp->seed, stratified_stream(*sp, x, y, 2 * d + 1));
+            const double dx = 1.0 / (double)sp->xs, dy = 1.0 / (double)sp->ys;  // stratified_sample2d (:102-118)
+            uint32_t k = 0;
+            for (uint32_t yy = 0; yy < sp->ys; ++yy)
+                for (uint32_t xx = 0; xx < sp->xs; ++xx) {
+                    double jx = sp->jitter ? pcg_unit(r) : 0.5;
+                    double jy = sp->jitter ? pcg_unit(r) : 0.5;
+                    s2[d][k].x = std::fmin(((double)xx + jx) * dx, ONE_MINUS_EPSILON);
+                    s2[d][k].y = std::fmin(((double)yy + jy) * dy, ONE_MINUS_EPSILON);
+                    ++k;
+                }
+            for (uint32_t i = 0; i < n; ++i) {
+                uint32_t other = i + r.below(n - i);
+                std::swap(s2[d][i], s2[d][other]);
+            }
+        }
+        current_sample_index = 0;
+        d1 = d2 = 0;
+    }
+    bool start_next_sample() {  // samplers/mod.rs:186-190 over :71-76 (Q10)
+        d1 = d2 = 0;
+        current_sample_index += 1;
+        // the overflow stream restarts per (pixel, sample): a pure function, like everything above
+        overflow = Pcg32(sp->seed ^ (0x9e3779b97f4a7c15ULL * (current_sample_index + 1)), stratified_stream(*sp, px, py, 63));
+        return current_sample_index < samples_per_pixel;
+    }
+    double get_1d() {
+        if (d1 < s1.size()) return s1[d1++][current_sample_index];
+        return pcg_unit(overflow) * 2.0 - 1.0;
+    }
+    P2 get_2d() {
+        if (d2 < s2.size()) {
+            P2 p = s2[d2][current_sample_index];
+            d2 += 1;
+            return p;
+        }
+        double a = pcg_unit(overflow) * 2.0 - 1.0, b = pcg_unit(overflow) * 2.0 - 1.0;
+        return P2(a, b);
+    }
+};
+
+// Sampler (samplers/mod.rs:448-546: the enum the integrators hold)
+struct Sampler {
+    int kind = 0;  // 0 Halton, 1 Stratified
+    HaltonSampler h;
+    StratifiedSampler s;
+    void start_pixel(int64_t px, int64_t py) { kind == 0 ? h.start_pixel(px, py) : s.start_pixel(px, py); }
+    bool start_next_sample() { return kind == 0 ? h.start_next_sample() : s.start_next_sample(); }
+    double get_1d() { return kind == 0 ? h.get_1d() : s.get_1d(); }
+    P2 get_2d() { return kind == 0 ? h.get_2d() : s.get_2d(); }
+    uint64_t samples_per_pixel() const { return kind == 0 ? h.samples_per_pixel : s.samples_per_pixel; }
+    uint64_t current_sample_index() const { return kind == 0 ? h.current_sample_index : s.current_sample_index; }
+};
+
 }  // namespace orc

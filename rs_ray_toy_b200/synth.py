@@ -236,6 +236,26 @@ def scene_c1(directory, xres=640, yres=360, nsamp=17, integrator="Path", max_dep
     return path
 
 
+def scene_c1_as_shipped(directory):
+    """Config 1 exactly as the reference ships it (samples/scene.json): the same geometry, lights, film and camera as
+    scene_c1, plus what scene_c1 leaves out — the unreferenced WindyTexture / ImageTexture("s_01.png") declarations,
+    the `Debug` material, `Integrator {Debug, light_strategy all}` and `Sampler {StratifiedSampler}` (4 x 4, jittered,
+    4 sampled dimensions by default).  tests/test_reference_image.py checks this dict against the reference's file
+    when /root/reference is present.  s_01.png is NOT written: no material names that texture."""
+    import json
+    import os
+    cfg = json.loads(open(scene_c1(directory)).read())
+    cfg["float_texture"] = [{"texture_name": "windy_01", "texture_type": "WindyTexture", "world_pos": [1, 1, 1]}]
+    cfg["rgb_texture"] = [{"texture_name": "s_01", "texture_type": "ImageTexture", "filename": "s_01.png"}]
+    cfg["materials"].append({"material_type": "Debug", "material_name": "mat_debug"})
+    cfg["Integrator"] = {"integrator_type": "Debug", "light_strategy": "all"}
+    cfg["Sampler"] = {"sampler_type": "StratifiedSampler"}
+    path = os.path.join(directory, "scene_as_shipped.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_area_lights(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
     """Config 1's cubes lit by two DiffuseAreaLights: a sphere emitter above the cubes and
     triangle 4 of cube.obj (the light shape is the raw mesh triangle, Q7), plus one point light.  The emitters

@@ -337,7 +337,7 @@ def light_row(cfg, meshes=None):
 def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=False):
     """make_film / make_camera / make_sampler / make_integrator (renderprocess.rs:1306-1499)."""
     film, cam, smp, integ = cfg["Film"], cfg["Camera"], cfg["Sampler"], cfg["Integrator"]
-    p = np.zeros(40)
+    p = np.zeros(48)
     p[0], p[1] = int(film.get("xres", 1280)), int(film.get("yres", 720))
     p[2] = float(film.get("diagonal", 35.0))
     flt = film["Filter"]
@@ -355,10 +355,15 @@ def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=Fal
     p[18], p[19] = float(cam.get("shutter_open", 0.0)), float(cam.get("shutter_close", 1.0))
     p[20], p[21] = float(cam.get("aperture_diameter", 1.0)), float(cam.get("focus_distance", 10.0))
     p[22] = 1.0 if cam.get("simple_weighting", True) else 0.0
-    if smp.get("sampler_type") != "HaltonSampler":
-        raise ValueError("only HaltonSampler is reproducible (SURVEY.md Q12)")
-    p[23] = int(smp.get("nsamp", 16))
-    p[24] = 1.0 if smp.get("sample_at_center", False) else 0.0
+    if smp.get("sampler_type") == "StratifiedSampler":      # make_sampler (renderprocess.rs:1308-1314)
+        p[38], p[39] = 1, 1.0 if smp.get("jitter", True) else 0.0
+        p[40], p[41], p[42] = int(smp.get("xsamp", 4)), int(smp.get("ysamp", 4)), int(smp.get("dimension", 4))
+        p[23] = p[40] * p[41]
+    elif smp.get("sampler_type") == "HaltonSampler":
+        p[23] = int(smp.get("nsamp", 16))
+        p[24] = 1.0 if smp.get("sample_at_center", False) else 0.0
+    else:
+        raise ValueError(f"Unsupported Sampler type (the reference panics: renderprocess.rs:1322)")
     p[25] = seed
     it = integ.get("integrator_type", "AO")
     if it == "Path":
@@ -366,6 +371,8 @@ def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=Fal
     elif it == "DirectLighting":
         p[26], p[27], p[28] = 1, int(integ.get("max_depth", 5)), 1.0
         p[37] = 1.0 if integ.get("light_strategy", "one") == "all" else 0.0   # renderprocess.rs:1413-1417
+    elif it == "Debug":                                       # renderprocess.rs:1471-1481
+        p[26], p[27], p[28] = 2, int(integ.get("max_depth", 5)), 1.0
     else:
         raise ValueError(f"integrator {it!r} is outside the restated subset")
     p[29], p[30] = tile_mod, tile_rank

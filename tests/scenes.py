@@ -141,7 +141,7 @@ def oracle_c5(n_tris, edge, xres, yres, nsamp, seed_render=1, max_depth=5, nthre
         L.orc_set_textures(s.h, 4, rows.ctypes.data)
     L.orc_set_materials(s.h, 2, mats.ctypes.data)
     L.orc_set_lights(s.h, 2, lights.ctypes.data)
-    prm = np.zeros(40)
+    prm = np.zeros(48)
     prm[0], prm[1], prm[2] = xres, yres, 35.0
     prm[3], prm[4], prm[5], prm[6], prm[7], prm[8] = 0, 0.5, 0.5, 2.0, 1.0, np.inf
     prm[9:12] = (0.5, 0.5, -2.5)

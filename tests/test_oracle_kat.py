@@ -75,9 +75,21 @@ def test_primitive_kat():
 
 
 def test_bnd2_tile_iteration():
-    # geometry.rs:1974-1980: every point of the row-major iteration is inside [48,64) x [0,16)
-    pts = [(x, y) for y in range(0, 16) for x in range(48, 64)]
-    assert len(pts) == 256 and all(48 <= x < 64 and 0 <= y < 16 for x, y in pts)
+    """geometry.rs:1974-1980 (test_bnd2): every point `Bounds2i::into_iter` yields is `inside` the bound.  The oracle's
+    Bounds2iIter (the iterator its render loop walks a tile with) must also yield the row-major walk of
+    [48,64) x [0,16), which is what geometry.rs:1494-1526 produces."""
+    import ctypes as C
+    L = O.lib()
+    L.orc_kat_bounds2i_iter.restype = C.c_uint64
+    L.orc_kat_bounds2i_iter.argtypes = [C.c_int64] * 4 + [C.c_void_p, C.c_uint64]
+    out = np.zeros((400, 3), dtype=np.int64)
+    n = L.orc_kat_bounds2i_iter(48, 0, 64, 16, out.ctypes.data, 400)
+    assert n == 256 and (out[:n, 2] == 1).all()
+    assert [tuple(r) for r in out[:n, :2]] == [(x, y) for y in range(0, 16) for x in range(48, 64)]
+    # ragged last tile of a 640 x 360 image (rows 352..359) and a one-pixel bound
+    n = L.orc_kat_bounds2i_iter(624, 352, 640, 360, out.ctypes.data, 400)
+    assert n == 128 and tuple(out[0, :2]) == (624, 352) and tuple(out[n - 1, :2]) == (639, 359)
+    assert L.orc_kat_bounds2i_iter(5, 7, 6, 8, out.ctypes.data, 400) == 1 and tuple(out[0, :2]) == (5, 7)
 
 
 def test_left_shift3_and_morton():
