@@ -262,15 +262,39 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
             "image_mean_rgb": [float(x) for x in img.mean(axis=(0, 1))],
             "dtype": "f64 shading and film, fp32 box culling",
         }
-        if world == 1 and not args.no_cpu_baseline and config == "c4":
+        # ---- end to end: the call a consumer makes — rrt_render_clear + rrt_render_run + rrt_render_read_film into host
+        # memory (scene and lens resident; down: the 4-f64-per-pixel film, converted to RGB on the host).  N = 1 only:
+        # with more ranks the frame above already ends in the NCCL film reduce.
+        if world == 1 and not args.no_e2e:
+            t0 = time.perf_counter()
+            r.clear()
+            r.run()
+            img_e2e = r.film()
+            e2e_s = time.perf_counter() - t0
+            out["e2e"] = {"value": samples / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(((img.shape[1] + 15) // 16) * ((img.shape[0] + 15) // 16) * 4),   # the tile list
+                          "d2h_bytes_per_step": int(img.shape[0] * img.shape[1] * 4 * 8),
+                          "api": "rrt_render_clear + rrt_render_run + rrt_render_read_film (host RGB film)",
+                          "same_image": bool(np.array_equal(img_e2e, img))}
+        if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, str(ROOT / "tests"))
             import oracle_lib as O
-            import oracle_scene as S
-            crop = (880, 460, 1040, 620)   # centred 160x160 pixels, full spp
-            ls = S.load(path)
-            t0 = time.perf_counter()
-            ref = ls.render(seed=1, crop=crop)
-            cdt = time.perf_counter() - t0   # includes the camera's exit-pupil set-up (a few seconds)
+            if config == "c4":
+                import oracle_scene as S
+                crop = (880, 460, 1040, 620)   # centred 160x160 pixels, full spp
+                ls = S.load(path)
+                t0 = time.perf_counter()
+                ref = ls.render(seed=1, crop=crop)
+                cdt = time.perf_counter() - t0   # includes the camera's exit-pupil set-up (a few seconds)
+                prim_bytes = 16   # sphere: centre + radius
+                what = "centred 160x160-pixel crop of the frame at full spp"
+            else:
+                import scenes
+                crop = (1888, 1048, 1952, 1112)   # centred 64x64 pixels, full spp (256): 1 Mi camera samples
+                t0 = time.perf_counter()
+                ref = scenes.oracle_c5(1 << 22, 0.006, 3840, 2160, 257, crop=crop)
+                cdt = time.perf_counter() - t0   # includes the oracle's HLBVH build over 4 Mi triangles and the exit-pupil set-up
+                prim_bytes = 36   # triangle: 9 x fp32
+                what = "centred 64x64-pixel crop of the frame at full spp"
             rs = ref["stats"]
             n_s = rs["camera_rays"] + rs["zero_weight"]
             gpu_crop = img[crop[1]:crop[3], crop[0]:crop[2]]
@@ -280,19 +304,19 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
             nt = (rs["closest_prims"] + rs["any_prims"]) / max(n_s, 1)
             rays_ps = (rs["extension_rays"] + rs["shadow_rays"]) / max(n_s, 1)
             bbar = rs["bounces"] / max(n_s, 1)
-            # sum over a sample's rays of (32 + 16|1 + 32 Nv + 16 Nt[sphere]) + film 16 + 2*96*B
+            # sum over a sample's rays of (32 + 16|1 + 32 Nv + S_prim Nt) + film 16 + 2*96*B
             bytes_ps = (32 + 16) * rs["extension_rays"] / max(n_s, 1) + (32 + 1) * rs["shadow_rays"] / max(n_s, 1) + \
-                32 * nv + 16 * nt + 16 + 2 * 96 * bbar
-            peak, _ = measured_peak()
+                32 * nv + prim_bytes * nt + 16 + 2 * 96 * bbar
+            peak, peak_src = measured_peak()
             out["cpu_baseline"] = {"value": n_s / cdt / 1e6, "unit": "Msamples/s", "cores": O.hardware_threads(), "kind": "port",
-                                   "sample": f"centred 160x160-pixel crop of the frame at full spp ({n_s} camera samples), oracle "
-                                             "Tier F, one thread per tile; includes the camera's exit-pupil set-up",
-                                   "crop_rel_rmse_gpu_vs_oracle": rmse}
+                                   "sample": f"{what} ({n_s} camera samples), oracle Tier F, one thread per tile; the time "
+                                             "includes the oracle's tree build and the camera's exit-pupil set-up",
+                                   "seconds": cdt, "crop_rel_rmse_gpu_vs_oracle": rmse}
             out["roofline"] = {"bound": "hbm", "unit": "GB/s", "algorithmic_bytes_per_sample": bytes_ps,
                                "nodes_visited_per_sample_oracle": nv, "prims_tested_per_sample_oracle": nt,
                                "rays_per_sample_oracle": rays_ps, "bounces_per_sample_oracle": bbar,
-                               "achieved": out["value"] * 1e6 * bytes_ps / 1e9, "peak": peak,
-                               "frac": out["value"] * 1e6 * bytes_ps / 1e9 / peak}
+                               "achieved": out["value"] * 1e6 * bytes_ps / 1e9, "peak": peak, "peak_source": peak_src,
+                               "frac": out["value"] * 1e6 * bytes_ps / 1e9 / peak, "traffic": None}
     r.close()
     del keep
     return out
@@ -305,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--rays", type=int, default=N_RAYS, help=argparse.SUPPRESS)
     ap.add_argument("--path-config", default="both", choices=["both", "c4", "c5", "none"],
                     help="second half of the metric: path-traced Msamples/s on config 4 (1080p, 64 spp) and config 5 "
@@ -376,6 +401,26 @@ def main():
     value = n_rays * world * args.steps / (total_ms_max * 1e-3) / 1e6
     n_hit = int((d_hits.view(torch.int64)[0::4] & 0xFFFFFFFF != 0xFFFFFFFF).sum().item())
 
+    # ---- the other half of a1/a2: any-hit (BVHAccel::intersect_p) on the same batch, device resident ----
+    d_occ = torch.empty(n_rays, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        agg.intersect_p_device(n_rays, d_rays.data_ptr(), d_occ.data_ptr(), stream.cuda_stream)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(args.steps):
+        agg.intersect_p_device(n_rays, d_rays.data_ptr(), d_occ.data_ptr(), stream.cuda_stream)
+    a1.record(stream)
+    barrier()
+    t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    any_value = n_rays * world * args.steps / (float(t.item()) * 1e-3) / 1e6
+    n_occ = int(d_occ.sum(dtype=torch.int64).item())
+    if n_occ != n_hit:
+        raise SystemExit(f"bench.py: any-hit and closest-hit disagree on which rays hit ({n_occ} vs {n_hit})")
+    del d_occ
+
     # ---- end to end: host buffers through rrt_intersect (H2D + kernel + D2H per step) ----
     for _ in range(2):
         agg.intersect(h_rays, out=h_hits)
@@ -423,6 +468,8 @@ def main():
                          "nodes_visited_per_ray_oracle": NV_C3, "prims_tested_per_ray_oracle": NT_C3,
                          "compulsory_dram_bytes_per_ray": 64 + 32 + stats["device_bytes"] / n_rays},
             "hit_fraction": n_hit / n_rays,
+            "any_hit": {"metric": "Mrays/s incoherent any-hit (intersect_p)", "value": any_value, "unit": UNIT,
+                        "note": "same batch and scene through rrt_intersect_p_device, t_max = inf; occluded count equals the closest-hit count"},
             "scene": stats,
         }
         line["path_traced"] = pt

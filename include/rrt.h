@@ -117,20 +117,6 @@ int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]);
  * interior node (32 or 64), 1 if built on the device, reserved }.                                            */
 int rrt_scene_build_info(const rrt_scene* scene, uint64_t out4[4]);
 
-/* Host-only probe of the device LBVH builder's per-element code (lbvh_core.h runs unchanged on the host; this
- * is a checker for the CPU tests, not a product path): world bounds in (6 doubles each), out: the emitted
- * Node64 array (16 x 4-byte words per node: 12 fp32 planes as laid out in device_layout.h, child0, child1, pad),
- * the primitive order, and info3 = { nodes, max depth, leaves }.  *n_nodes is set also when capacity is short. */
-int rrt_lbvh_host_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
-                        uint32_t* n_nodes, uint32_t* node_words16, uint32_t* order, uint32_t info3[3]);
-
-/* Host-only probe of the literal tier's tree builder (BVHAccel::new with HLBVH, bvh.rs:307-751) on a
- * list of primitive world bounds (6 doubles each: p_min, p_max).  Returns the flattened
- * LinearBVHNode array: node_bounds6[6 * i], node_meta3[3 * i] = (offset, n_primitives, axis), and the
- * reordered primitive list.  *n_nodes receives the node count (also when capacity is too small).   */
-int rrt_hlbvh_literal_probe(uint32_t n, const double* bounds6, uint32_t max_prims_in_node, uint32_t capacity_nodes,
-                            uint32_t* n_nodes, double* node_bounds6, uint32_t* node_meta3, uint32_t* ordered);
-
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* Scene::intersect -> BVHAccel::intersect (scene.rs:69-72, bvh.rs:183-236) over a batch.
  * rays / hits are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t,
@@ -260,21 +246,6 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
  * Optional: a scene without these calls has constant-valued materials.                                        */
 int rrt_scene_set_textures(rrt_scene* scene, uint32_t n, const rrt_texture* textures);
 int rrt_scene_set_material_textures(rrt_scene* scene, uint32_t n_materials, const int32_t* slots);
-/* Host-only evaluation of a texture table at (uv, p) with the product's own evaluator (csrc/texture_core.h, the
- * code the shade kernel runs): out[3 * i + c] for every texture i.  `diff` (may be NULL = none) holds the
- * screen-space differentials dpdx[3] dpdy[3] dudx dvdx dudy dvdy.  For the CPU test-suite.                    */
-int rrt_texture_host_probe(uint32_t n, const rrt_texture* textures, const double uv[2], const double p[3],
-                           const double* diff, double* out);
-/* Host-only HaltonSampler probe (csrc/halton.cuh, the code the kernels run): for each i the sample index of
- * (px, py, sample) (Halton::get_index_for_sample, halton.rs:75-105) and its value in dimension dim
- * (sample_dimension, :107-128) for a film of xres x yres and the given permutation seed.  use_tables = 1 takes the
- * table-driven paths the device takes (per-dimension constants, exact multiply-shift division, per-pixel index
- * terms), 0 the generic digit loops: both must give the same bits.                                            */
-int rrt_halton_host_probe(int64_t xres, int64_t yres, uint64_t seed, int use_tables, uint64_t n, const int64_t* px,
-                          const int64_t* py, const uint64_t* sample, const uint32_t* dim, uint64_t* index_out, double* value_out);
-/* Host-only SurfaceInteraction::compute_differentials with the product's code (csrc/texture_core.h): in = p[3] n[3]
- * dpdu[3] dpdv[3] rx_origin[3] rx_direction[3] ry_origin[3] ry_direction[3]; out = dpdx[3] dpdy[3] dudx dvdx dudy dvdy. */
-int rrt_differentials_host_probe(const double in24[24], double out10[10]);
 /* deploy_render's loader: parses scene.json (+ the .obj files it names, relative to it) into a
  * committed scene and the integrator that renders it.  `overrides_json` (may be NULL) replaces
  * top-level keys (e.g. {"Integrator": {...}, "Sampler": {...}}) before the factories run.       */
@@ -284,14 +255,6 @@ int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_js
  * integrator also keeps the reference's shadow-ray construction (Q9) and instance-ray rule (Q6). */
 int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed,
                              uint32_t build_flags, rrt_scene** scene, rrt_render** render);
-/* Host-only view of what the loader reads (no device is touched): out8 = primitives, meshes,
- * spheres, instances, materials, lights, max_prims_in_node, lens values; desc = the render
- * description (lens_data pointer left NULL).  Used by the CPU test-suite and by tooling.          */
-int rrt_scene_json_probe(const char* path, const char* overrides_json, uint64_t out8[8], rrt_render_desc* desc);
-/* Host-only view of the loader's texture table and materials: textures (room for RRT_MAX_TEXTURES, may be NULL),
- * the first max_materials materials and their RRT_MATERIAL_SLOTS texture indices each (may be NULL).          */
-int rrt_scene_json_texture_probe(const char* path, const char* overrides_json, uint32_t* n_textures, rrt_texture* textures,
-                                 uint32_t max_materials, uint32_t* n_materials, rrt_material* materials, int32_t* slots);
 /* make_integrator for an assembled scene.                                                       */
 int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render** out);
 void rrt_render_destroy(rrt_render* render);

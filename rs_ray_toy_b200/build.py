@@ -34,7 +34,7 @@ def is_stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [PKG.parent / "include" / "rrt.h", Path(__file__)]
+    deps = list(CSRC.glob("*")) + [PKG.parent / "include" / "rrt.h", PKG.parent / "include" / "rrt_test.h", Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -14,6 +14,7 @@ import os
 # RRT_LIB selects an experiment build of the same library (tools/sweep.py); default = the product
 LIB_PATH = Path(os.environ["RRT_LIB"]) if os.environ.get("RRT_LIB") else PKG / "librrt_sm100.so"
 HEADER = PKG.parent / "include" / "rrt.h"
+TEST_HEADER = PKG.parent / "include" / "rrt_test.h"   # host-only probes for the CPU tests, not for bindings
 
 RRT_OK = 0
 RRT_ERR_INVALID = -1
@@ -37,8 +38,8 @@ _lib = None
 
 
 def declared_symbols() -> list[str]:
-    """Every function name include/rrt.h declares (used by the export test)."""
-    text = HEADER.read_text()
+    """Every function name include/rrt.h and include/rrt_test.h declare (used by the export test)."""
+    text = HEADER.read_text() + TEST_HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(rrt_[a-z0-9_]+)\s*\(", text)))
 
@@ -76,6 +77,7 @@ def lib() -> C.CDLL:
         "rrt_intersect_p_device": (i32, [vp, u64, vp, vp, vp]),
         "rrt_intersect": (i32, [vp, u64, vp, vp]),
         "rrt_intersect_p": (i32, [vp, u64, vp, vp]),
+        "rrt_tri_screen_host_probe": (i32, [u64, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

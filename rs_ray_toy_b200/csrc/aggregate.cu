@@ -26,6 +26,7 @@
 #include "bvh_lbvh.hpp"
 #include "device_layout.h"
 #include "sphere_core.cuh"
+#include "tri_screen.h"
 
 namespace rrt {
 
@@ -360,6 +361,7 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #define RRT_MINBLOCKS_Q 8  // Node32 kernels: 64 registers (measured best, profiles/r1_sweep8.txt)
 #endif
 constexpr int kRefill = RRT_REFILL;
+constexpr int kScreenRows = RRT_PRETEST ? 9 : 0;  // ScreenRay rows behind the traversal stack (tri_screen.h)
 
 
 // GEN: the scene holds spheres that need the object-space test (PRIM_SPHERE_GENERAL); every other scene runs the
@@ -399,6 +401,9 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
         node = my_stack[sp * kBlock]; \
     } while (0)
 #endif
+    // the fp32 screen's per-ray constants (ScreenRay) live behind the stack, [row][thread] as well: nine floats that
+    // are written once per ray and read once per screened record — registers are what this kernel is short of
+    float* const my_screen = reinterpret_cast<float*>(sstack + stack_levels * kBlock * (RRT_STALE_SKIP ? 2 : 1)) + threadIdx.x;
     int sp = 1;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
     int32_t leaf = kNoLeaf;   // parked leaf reference (head of the queue)
@@ -486,6 +491,14 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
 #pragma unroll
                     for (int k = 0; k < RRT_LEAFQ - 1; ++k) lq[k] = kNoLeaf;
 #endif
+                    if (!WIDE && RRT_PRETEST) {
+                        const ScreenRay R = make_screen_ray(o.x, o.y, o.z, d.x, d.y, d.z);
+                        my_screen[0 * kBlock] = R.ox; my_screen[1 * kBlock] = R.oy; my_screen[2 * kBlock] = R.oz;
+                        my_screen[3 * kBlock] = R.dx; my_screen[4 * kBlock] = R.dy; my_screen[5 * kBlock] = R.dz;
+                        my_screen[6 * kBlock] = R.mo;
+                        my_screen[7 * kBlock] = R.md;
+                        my_screen[8 * kBlock] = R.kmd;
+                    }
                     const bool live = prepare_ray(A, o, d, best_t, &t_shift, &rf) && !(best_t < 0.0);
                     node = live ? A.root : kDone;
                     tcull = __double2float_ru(best_t - (double)t_shift);
@@ -612,7 +625,30 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
             if (leaf != kNoLeaf) {
                 const uint32_t ref = ~(uint32_t)leaf;
                 const uint32_t first = ref >> 3, cnt = (ref & 7u) + 1u;
-                for (uint32_t k = 0; k < cnt; ++k) {
+                // phase A (fp32-exact records only): screen every record of the leaf in fp32; what is left over
+                // goes to the f64 tests of phase B.  Spheres are never screened.
+                uint32_t cand = (1u << cnt) - 1u;
+                if (!WIDE && RRT_PRETEST) {
+                    ScreenRay R;
+                    R.ox = my_screen[0 * kBlock]; R.oy = my_screen[1 * kBlock]; R.oz = my_screen[2 * kBlock];
+                    R.dx = my_screen[3 * kBlock]; R.dy = my_screen[4 * kBlock]; R.dz = my_screen[5 * kBlock];
+                    R.mo = my_screen[6 * kBlock];
+                    R.md = my_screen[7 * kBlock];
+                    R.kmd = my_screen[8 * kBlock];
+                    R.bt = __double2float_ru(best_t);  // closest so far, or the shadow ray's t_max
+                    cand = 0u;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const float4* p = reinterpret_cast<const float4*>(static_cast<const PrimRec48*>(A.prims) + first + k);
+                        const float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+                        const bool out = __float_as_uint(r2.z) == PRIM_TRIANGLE &&
+                                         tri_surely_missed(R, V4f{r0.x, r0.y, r0.z, r0.w}, V4f{r1.x, r1.y, r1.z, r1.w}, V4f{r2.x, r2.y, r2.z, r2.w});
+                        cand |= out ? 0u : (1u << k);
+                    }
+                }
+                // phase B: the deciding arithmetic, f64, reference operation order
+                while (cand != 0u) {
+                    const uint32_t k = (uint32_t)__ffs((int)cand) - 1u;
+                    cand &= cand - 1u;
                     D3 a, b, c;
                     uint32_t pid, kind;
                     load_prim<WIDE>(A.prims, first + k, &a, &b, &c, &pid, &kind);
@@ -1320,7 +1356,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     // the only shared memory is the traversal stack (one entry per tree level + the marker);
     // everything else of the 256 KB stays L1
     stack_levels_ = (int)tree.max_depth + 2;
-    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
+    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t);
     int carve = (int)(((quantise ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
     for (auto fn : {(const void*)trace_kernel<false, false, false, false>, (const void*)trace_kernel<false, true, false, false>,
@@ -1401,7 +1437,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
                                          : (view_.wide ? trace_kernel<ANY, true, false, true> : trace_kernel<ANY, false, false, true>))
                       : (view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true, false> : trace_kernel<ANY, false, true, false>)
                                          : (view_.wide ? trace_kernel<ANY, true, false, false> : trace_kernel<ANY, false, false, false>));
-    const size_t smem = (size_t)stack_levels_ * kBlock * sizeof(int32_t) * (RRT_STALE_SKIP ? 2 : 1);
+    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t);
     int per_sm = 0;
     RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
     if (per_sm < 1) per_sm = 1;

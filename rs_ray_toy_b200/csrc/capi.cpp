@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -21,6 +22,8 @@
 #include "png_min.hpp"
 #include "render.hpp"
 #include "scene_json.hpp"
+#include "tri_screen.h"
+#include "rrt_test.h"
 
 namespace {
 
@@ -138,7 +141,11 @@ int host_batch(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, void* ou
             rc = scene->agg->any_hit(cnt, s.d_rays, static_cast<uint8_t*>(s.d_out), s.stream, &err, &launched);
         else
             rc = scene->agg->closest_hit(cnt, s.d_rays, static_cast<rrt_hit*>(s.d_out), s.stream, &err, &launched);
-        if (rc != RRT_OK) return fail(rc, err);
+        if (rc != RRT_OK) {
+            // copies of earlier chunks into the caller's buffer may still be in flight: drain them before returning
+            for (auto& t : ctx->slots) cudaStreamSynchronize(t.stream);
+            return fail(rc, err);
+        }
         ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
         CAPI_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + done * out_elem, s.d_out, cnt * out_elem,
                                   cudaMemcpyDeviceToHost, s.stream));
@@ -447,6 +454,7 @@ int rrt_intersect_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_ra
     if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_intersect_device: scene is not committed");
     if (n == 0) return RRT_OK;
     if (!d_rays || !d_hits) return fail(RRT_ERR_INVALID, "rrt_intersect_device: null buffer");
+    CAPI_CUDA(cudaSetDevice(scene->ctx->device));  // the scratch buffers and the grid size belong to the scene's device
     std::string err;
     int launched = 0;
     int rc = scene->agg->closest_hit(n, d_rays, d_hits, cuda_stream, &err, &launched);
@@ -460,6 +468,7 @@ int rrt_intersect_p_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_
     if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_intersect_p_device: scene is not committed");
     if (n == 0) return RRT_OK;
     if (!d_rays || !d_occluded) return fail(RRT_ERR_INVALID, "rrt_intersect_p_device: null buffer");
+    CAPI_CUDA(cudaSetDevice(scene->ctx->device));
     std::string err;
     int launched = 0;
     int rc = scene->agg->any_hit(n, d_rays, d_occluded, cuda_stream, &err, &launched);
@@ -745,6 +754,21 @@ int rrt_intersect(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, rrt_h
 }
 int rrt_intersect_p(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, uint8_t* occluded) {
     return host_batch<true>(scene, n, rays, occluded);
+}
+
+int rrt_tri_screen_host_probe(uint64_t n, const double* o3, const double* d3, const double* best_t, const float* verts9,
+                              uint8_t* out) {
+    if (!o3 || !d3 || !best_t || !verts9 || !out) return fail(RRT_ERR_INVALID, "rrt_tri_screen_host_probe: null argument");
+    for (uint64_t i = 0; i < n; ++i) {
+        rrt::ScreenRay R = rrt::make_screen_ray(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2], d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+        float bt = (float)best_t[i];  // __double2float_ru
+        if ((double)bt < best_t[i]) bt = std::nextafterf(bt, INFINITY);
+        R.bt = bt;
+        const float* v = verts9 + 9 * i;
+        // the PrimRec48 lanes: v0.xyz v1.x | v1.yz v2.xy | v2.z prim_id kind pad
+        out[i] = rrt::tri_surely_missed(R, rrt::V4f{v[0], v[1], v[2], v[3]}, rrt::V4f{v[4], v[5], v[6], v[7]}, rrt::V4f{v[8], 0.f, 0.f, 0.f}) ? 1 : 0;
+    }
+    return RRT_OK;
 }
 
 }  // extern "C"

@@ -83,8 +83,11 @@ struct Queues {
     uint32_t* sh_path;
     Rgb* sh_contrib;
     uint8_t* sh_occluded;
-    uint32_t* counters;  // [0] ext cur, [1] ext next, [2] shadow, [3] generate cursor, [4..15] statistics,
+    uint32_t* counters;  // [0] ext cur, [1] ext next, [2] shadow, [3] generate cursor,
                          // [16..23] shade bins, [24..31] shade bin cursors
+    unsigned long long* stats;  // 64-bit frame totals: [0] camera rays, [1] extension rays, [2] shadow rays, [3] bounces,
+                                // [4] zero-weight samples, [5] fp32-decided lens walks, [6] undecided ones (a 4K frame
+                                // at 256 spp traces 1.9 G extension rays: 32 bits would wrap at 512 spp)
     uint8_t* shade_key;   // per extension-queue entry: 0 = miss, 1 + material kind otherwise
     uint32_t* shade_perm; // extension-queue entries grouped by shade_key
 };
@@ -366,10 +369,10 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
         n_unsure += __shfl_xor_sync(FULL, n_unsure, off);
     }
     if (lane == 0) {
-        if (n_camera) atomicAdd(q.counters + 4, n_camera);
-        if (n_zero) atomicAdd(q.counters + 8, n_zero);
-        if (n_quick) atomicAdd(q.counters + 9, n_quick);
-        if (n_unsure) atomicAdd(q.counters + 10, n_unsure);
+        if (n_camera) atomicAdd(q.stats + 0, (unsigned long long)n_camera);
+        if (n_zero) atomicAdd(q.stats + 4, (unsigned long long)n_zero);
+        if (n_quick) atomicAdd(q.stats + 5, (unsigned long long)n_quick);
+        if (n_unsure) atomicAdd(q.stats + 6, (unsigned long long)n_unsure);
     }
 }
 
@@ -647,10 +650,10 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
         n_unsure += __shfl_xor_sync(FULL, n_unsure, off);
     }
     if (lane == 0) {
-        if (n_camera) atomicAdd(q.counters + 4, n_camera);
-        if (n_zero) atomicAdd(q.counters + 8, n_zero);
-        if (n_quick) atomicAdd(q.counters + 9, n_quick);
-        if (n_unsure) atomicAdd(q.counters + 10, n_unsure);
+        if (n_camera) atomicAdd(q.stats + 0, (unsigned long long)n_camera);
+        if (n_zero) atomicAdd(q.stats + 4, (unsigned long long)n_zero);
+        if (n_quick) atomicAdd(q.stats + 5, (unsigned long long)n_quick);
+        if (n_unsure) atomicAdd(q.stats + 6, (unsigned long long)n_unsure);
     }
 }
 
@@ -959,9 +962,9 @@ __global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, 
 
 // Between rounds: statistics, then the next round's queue becomes current and the others empty.
 __global__ void advance_kernel(Queues q, int cur) {
-    q.counters[5] += q.counters[cur];  // extension rays traced
-    q.counters[6] += q.counters[2];    // shadow rays traced
-    q.counters[7] += q.counters[cur ^ 1];  // bounces
+    q.stats[1] += q.counters[cur];      // extension rays traced
+    q.stats[2] += q.counters[2];        // shadow rays traced
+    q.stats[3] += q.counters[cur ^ 1];  // bounces
     q.counters[cur] = 0;
     q.counters[2] = 0;
     for (int b = 0; b < 2 * kShadeBins; ++b) q.counters[16 + b] = 0;
@@ -1246,9 +1249,35 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         if (err) *err = "Camera lens_data must hold 4 values per element (camera.rs:77), at most 32 elements";
         return RRT_ERR_INVALID;
     }
-    if (d.nsamp < 1) {
-        if (err) *err = "HaltonSampler nsamp must be >= 1";
+    if (d.nsamp < 1 || d.nsamp > (1ull << 32)) {
+        if (err) *err = "HaltonSampler nsamp must be in 1 .. 2^32";
         return RRT_ERR_INVALID;
+    }
+    if (d.max_depth > 64) {
+        if (err) *err = "max_depth must be in 0 .. 64";
+        return RRT_ERR_INVALID;
+    }
+    if (!(d.filter_radius[0] > 0.0) || !(d.filter_radius[1] > 0.0) || !std::isfinite(d.filter_radius[0]) ||
+        !std::isfinite(d.filter_radius[1]) || !std::isfinite(d.filter_alpha)) {
+        if (err) *err = "Filter radius must be finite and > 0";
+        return RRT_ERR_INVALID;
+    }
+    for (uint32_t i = 0; i < d.n_lens_values; ++i)
+        if (!std::isfinite(d.lens_data[i])) {
+            if (err) *err = "Camera lens_data holds a non-finite value";
+            return RRT_ERR_INVALID;
+        }
+    {
+        // Halton dimensions a camera sample can read: 5 for the camera sample, then per hit 1 (light choice) + 4
+        // (u_light, u_scattering) + 2 (BSDF sample) + 1 (Russian roulette) on a path of max_depth + 1 hits; with
+        // light_strategy "all" 4 per light.  The device tables hold kHaltonDims of the reference's 1000 primes
+        // (the reference panics beyond them): more is refused here, never clamped.
+        const uint64_t per_hit = d.integrator_kind == RRT_INTEGRATOR_PATH ? 8u : (d.light_strategy ? 4u * (uint64_t)lights.size() : 5u);
+        const uint64_t hits = d.integrator_kind == RRT_INTEGRATOR_PATH ? (uint64_t)d.max_depth + 1u : 1u;
+        if (5u + per_hit * hits > (uint64_t)kHaltonDims) {
+            if (err) *err = "this integrator setting reads more Halton dimensions than the device tables hold (" + std::to_string(kHaltonDims) + ")";
+            return RRT_ERR_UNSUPPORTED;
+        }
     }
     if (lights.size() > 16) {
         if (err) *err = "more than 16 lights";
@@ -1336,7 +1365,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         F.sb[3] = std::max(as_i64(p1y), as_i64(p2y));
     }
     RND_CUDA(cudaMalloc(&d_film_, film_doubles() * sizeof(double)));
-    RND_CUDA(cudaMemset(d_film_, 0, film_doubles() * sizeof(double)));
+    RND_CUDA(cudaMemsetAsync(d_film_, 0, film_doubles() * sizeof(double), I.stream));
 
     // ---- Sampler (halton.rs:23-59) ----
     I.ht = make_halton_tables(d.xres, d.yres, d.sample_at_center != 0);
@@ -1599,7 +1628,10 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     if ((rc = dev_alloc((void**)&I.q.shade_key, kSlots)) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.shade_perm, kSlots * sizeof(uint32_t))) != RRT_OK) return rc;
     if ((rc = dev_alloc((void**)&I.q.counters, 64 * sizeof(uint32_t))) != RRT_OK) return rc;
-    RND_CUDA(cudaMemset(I.q.counters, 0, 64 * sizeof(uint32_t)));
+    if ((rc = dev_alloc((void**)&I.q.stats, 8 * sizeof(unsigned long long))) != RRT_OK) return rc;
+    RND_CUDA(cudaMemsetAsync(I.q.stats, 0, 8 * sizeof(unsigned long long), I.stream));
+    RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 64 * sizeof(uint32_t), I.stream));
+    RND_CUDA(cudaStreamSynchronize(I.stream));
     stats_.setup_usec =
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
     return RRT_OK;
@@ -1608,7 +1640,8 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
 int Renderer::clear(std::string* err) {
     if (!impl_) return RRT_ERR_INVALID;
     RND_CUDA(cudaSetDevice(impl_->device));
-    RND_CUDA(cudaMemset(d_film_, 0, film_doubles() * sizeof(double)));
+    // stream-ordered with the render kernels (I.stream is non-blocking: a legacy-stream memset would not be)
+    RND_CUDA(cudaMemsetAsync(d_film_, 0, film_doubles() * sizeof(double), impl_->stream));
     stats_ = RenderStats{};
     impl_->dump_count = 0;
     return RRT_OK;
@@ -1710,19 +1743,19 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
         stats_.chunks += 1;
     }
     RND_CUDA(cudaGetLastError());
-    uint32_t hc[16];
-    RND_CUDA(cudaMemcpyAsync(hc, I.q.counters, sizeof(hc), cudaMemcpyDeviceToHost, I.stream));
+    unsigned long long hc[8];
+    RND_CUDA(cudaMemcpyAsync(hc, I.q.stats, sizeof(hc), cudaMemcpyDeviceToHost, I.stream));
     RND_CUDA(cudaStreamSynchronize(I.stream));
-    RND_CUDA(cudaMemsetAsync(I.q.counters + 4, 0, 12 * sizeof(uint32_t), I.stream));
+    RND_CUDA(cudaMemsetAsync(I.q.stats, 0, 8 * sizeof(unsigned long long), I.stream));
     if (I.dump_enabled) I.dump_count += total;
-    stats_.camera_rays += hc[4];
-    stats_.extension_rays += hc[5];
-    stats_.shadow_rays += hc[6];
-    stats_.bounces += hc[7];
-    stats_.zero_weight += hc[8];
-    stats_.samples += (uint64_t)hc[4] + hc[8];
-    stats_.f32_neighbours += hc[9];
-    stats_.f32_unsure += hc[10];
+    stats_.camera_rays += hc[0];
+    stats_.extension_rays += hc[1];
+    stats_.shadow_rays += hc[2];
+    stats_.bounces += hc[3];
+    stats_.zero_weight += hc[4];
+    stats_.samples += hc[0] + hc[4];
+    stats_.f32_neighbours += hc[5];
+    stats_.f32_unsure += hc[6];
     stats_.launches += launches;
     stats_.render_usec +=
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();

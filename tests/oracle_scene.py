@@ -457,7 +457,8 @@ def oracle_render(scene, prm, lens, nthreads=None, want_dump=False):
     rgb = np.zeros((yres, xres, 3))
     raw = np.zeros((yres, xres, 4))
     stats = np.zeros(16, dtype=np.uint64)
-    cap = npix * max(1, int(prm[23]) - 1) if want_dump else 0
+    dump_pix = npix if prm[31] == 0.0 else int(max(0, prm[34] - prm[32]) * max(0, prm[35] - prm[33]))   # a crop dumps its own pixels only
+    cap = dump_pix * max(1, int(prm[23]) - 1) if want_dump else 0
     dump = np.zeros((max(cap, 1), 6))
     cnt = C.c_uint64(0)
     nthreads = O.hardware_threads() if nthreads is None else nthreads

@@ -345,3 +345,43 @@ def test_direct_lighting_sample_all_lights(ctx, tmp_path):
         one = Render.load(ctx, path, seed=1)
         one.run()
         assert one.stats()["shadow_rays"] < out["shadow_rays"][0]
+
+
+def test_full_size_config5(ctx):
+    """BASELINE config 5 at FULL size — the 4,194,304-triangle soup, 3840 x 2160, Halton nsamp 257 (256 rendered), Path
+    max_depth 5 — against the oracle on what the oracle finishes in seconds: (1) a 64 Ki-ray slice of incoherent
+    bounce rays on the 4 Mi-triangle aggregate (primitive, t, u, v; any-hit), (2) a centred 48 x 48-pixel crop of
+    the frame at full spp: every camera ray's first primitive and t, the filter weights, the ray counts, the film."""
+    import scenes
+    agg, gpu = synth.scene_c5_api(ctx)           # defaults = config 5 as bench.py renders it
+    p, idx = synth.soup_triangles(1 << 22, 0.006, synth.SEED_C5_SOUP)
+    rays = synth.bounce_rays(p, idx, 1 << 16, seed=77)
+    hits = agg.intersect(rays)
+    occ = agg.intersect_p(rays)
+    oscene = scenes.oracle_soup(p, idx)
+    ref = oscene.intersect(rays)
+    c = scenes.compare_closest(hits, ref["prim"], ref["t"])
+    assert c["mismatch_excl_ties"] == 0 and c["t_bad"] == 0, c
+    occ_ref, _ = oscene.intersect_p(rays)
+    assert np.array_equal(occ.astype(bool), np.asarray(occ_ref).astype(bool))
+    del oscene
+    crop = (1896, 1056, 1944, 1104)
+    gpu.enable_hit_dump()
+    gpu.run(crop=crop)
+    ref = scenes.oracle_c5(1 << 22, 0.006, 3840, 2160, 257, crop=crop, want_dump=True)
+    rgb, raw = gpu.film(want_raw=True)
+    st = gpu.stats()
+    sl = (slice(crop[1], crop[3]), slice(crop[0], crop[2]))
+    assert np.array_equal(raw[sl][..., 3], ref["raw"][sl][..., 3])
+    assert st["camera_rays"] == ref["stats"]["camera_rays"] and st["zero_weight"] == ref["stats"]["zero_weight"]
+    assert st["camera_rays"] + st["zero_weight"] == 48 * 48 * 256
+    d, r = gpu.hit_dump(), ref["dump"]
+    d = d[~np.isnan(d[:, 0])]
+    assert d.shape == r.shape and np.array_equal(d[:, :3], r[:, :3])
+    assert np.array_equal(d[:, 3], r[:, 3])                      # first-hit primitive of every camera ray
+    hit = r[:, 3] >= 0
+    assert np.allclose(d[hit, 4], r[hit, 4], rtol=1e-5, atol=0)   # its t (north_star: 1e-5 relative)
+    assert abs(st["extension_rays"] - ref["stats"]["extension_rays"]) <= 8
+    assert abs(st["shadow_rays"] - ref["stats"]["shadow_rays"]) <= 8
+    assert rel_rmse(rgb[sl], ref["rgb"][sl]) <= REL_RMSE
+    gpu.close()

@@ -17,20 +17,24 @@ from rs_ray_toy_b200.build import build_library  # noqa: E402
 out_dir = ROOT / "rs_ray_toy_b200" / "variants"
 out_dir.mkdir(exist_ok=True)
 rays = os.environ.get("SWEEP_RAYS", str(1 << 24))
-for spec in sys.argv[1:]:
+build_only = "--build-only" in sys.argv   # on the build machine: compile the variants, the GPU box only times them
+for spec in [a for a in sys.argv[1:] if not a.startswith("--")]:
     defs, _, envs = spec.partition(";")
     defines = [f"RRT_{d}" for d in defs.split(",") if d]
     tag = "base" if not defines else "_".join(d.replace("=", "") for d in defines)
-    lib = out_dir / f"librrt_{tag}.so"
+    lib = out_dir / f"librrt_{tag}.so" if defines else ROOT / "rs_ray_toy_b200" / "librrt_sm100.so"
     if not lib.exists():
         build_library(force=True, defines=defines, out=lib)
     regs = [l for l in (lib.parent / (lib.stem + "_ptxas.txt")).read_text().splitlines() if "registers" in l][:2]
+    if build_only:
+        print(tag, "built", flush=True)
+        continue
     env = dict(os.environ, RRT_LIB=str(lib))
     for kv in envs.split(","):
         if kv:
             k, v = kv.split("=")
             env[k] = v
-    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--path-config", "none",
                         "--rays", rays], env=env, capture_output=True, text=True)
     try:
         j = json.loads(r.stdout.strip().splitlines()[-1])
