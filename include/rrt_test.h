@@ -62,6 +62,12 @@ int rrt_scene_json_texture_probe(const char* path, const char* overrides_json, u
 int rrt_tri_screen_host_probe(uint64_t n, const double* o3, const double* d3, const double* best_t, const float* verts9,
                               uint8_t* out);
 
+/* Host-only probe of the device StratifiedSampler (csrc/stratified.cuh, the code the kernels run): for one pixel the
+ * 1D tables out1d[ndims][xs * ys], the 2D tables out2d[ndims][xs * ys][2] as PixelSampler::start_pixel leaves them, and
+ * for every sample k >= 1 the first four draws past the sampled dimensions overflow4[k][4].                           */
+int rrt_stratified_host_probe(uint64_t seed, int64_t xres, int64_t px, int64_t py, uint32_t xs, uint32_t ys, uint32_t ndims,
+                              int jitter, double* out1d, double* out2d, double* overflow4);
+
 #ifdef __cplusplus
 }
 #endif

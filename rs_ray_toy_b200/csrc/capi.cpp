@@ -22,6 +22,7 @@
 #include "png_min.hpp"
 #include "render.hpp"
 #include "scene_json.hpp"
+#include "stratified.cuh"
 #include "tri_screen.h"
 #include "rrt_test.h"
 
@@ -767,6 +768,28 @@ int rrt_tri_screen_host_probe(uint64_t n, const double* o3, const double* d3, co
         const float* v = verts9 + 9 * i;
         // the PrimRec48 lanes: v0.xyz v1.x | v1.yz v2.xy | v2.z prim_id kind pad
         out[i] = rrt::tri_surely_missed(R, rrt::V4f{v[0], v[1], v[2], v[3]}, rrt::V4f{v[4], v[5], v[6], v[7]}, rrt::V4f{v[8], 0.f, 0.f, 0.f}) ? 1 : 0;
+    }
+    return RRT_OK;
+}
+
+int rrt_stratified_host_probe(uint64_t seed, int64_t xres, int64_t px, int64_t py, uint32_t xs, uint32_t ys, uint32_t ndims,
+                              int jitter, double* out1d, double* out2d, double* overflow4) {
+    if (!out1d || !out2d || !overflow4) return fail(RRT_ERR_INVALID, "rrt_stratified_host_probe: null argument");
+    if (xs == 0 || ys == 0 || xs * ys > rrt::kStratMaxSamples || ndims > rrt::kStratMaxDims)
+        return fail(RRT_ERR_UNSUPPORTED, "rrt_stratified_host_probe: table size outside the device sampler's range");
+    rrt::StratParams sp{xs, ys, ndims, jitter ? 1u : 0u, seed, xres};
+    const uint32_t n = xs * ys;
+    for (uint32_t d = 0; d < ndims; ++d)
+        for (uint32_t i = 0; i < n; ++i) {
+            out1d[d * n + i] = rrt::strat_table_1d(sp, px, py, d, i);
+            const rrt::P2 p = rrt::strat_table_2d(sp, px, py, d, i);
+            out2d[2 * (d * n + i)] = p.x;
+            out2d[2 * (d * n + i) + 1] = p.y;
+        }
+    for (uint32_t k = 1; k < n; ++k) {
+        uint32_t state = 0;
+        for (uint32_t d = 0; d < ndims; ++d) rrt::strat_get_1d(sp, px, py, k, &state);
+        for (int j = 0; j < 4; ++j) overflow4[4 * k + j] = rrt::strat_get_1d(sp, px, py, k, &state);
     }
     return RRT_OK;
 }
