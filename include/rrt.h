@@ -212,7 +212,12 @@ typedef struct rrt_light {
 } rrt_light;
 
 typedef enum rrt_filter_kind { RRT_FILTER_BOX = 0, RRT_FILTER_GAUSSIAN = 1, RRT_FILTER_TRIANGLE = 2 } rrt_filter_kind;
-typedef enum rrt_integrator_kind { RRT_INTEGRATOR_PATH = 0, RRT_INTEGRATOR_DIRECT = 1 } rrt_integrator_kind;
+/* PathIntegrator (integrator/path.rs), DirectLightingIntegrator (integrator/directlighting.rs, with its specular
+ * recursion, integrator/mod.rs:150-301), IntersectDebugIntegrator (integrator/intersect_debug.rs:56-89: a constant 0.1 per
+ * hit + uniform_sample_all_lights + the same recursion — what samples/scene.json asks for).                          */
+typedef enum rrt_integrator_kind { RRT_INTEGRATOR_PATH = 0, RRT_INTEGRATOR_DIRECT = 1, RRT_INTEGRATOR_DEBUG = 2 } rrt_integrator_kind;
+/* make_sampler (renderprocess.rs:1306-1325) */
+typedef enum rrt_sampler_kind { RRT_SAMPLER_HALTON = 0, RRT_SAMPLER_STRATIFIED = 1 } rrt_sampler_kind;
 
 /* make_film / make_camera / make_sampler / make_integrator arguments (renderprocess.rs:1306-1499). */
 typedef struct rrt_render_desc {
@@ -235,6 +240,12 @@ typedef struct rrt_render_desc {
     /* Integrator */
     uint32_t integrator_kind, max_depth;
     double rr_threshold;
+    /* Sampler, continued (fields added after round 1 sit at the end: older callers' zeroes mean HaltonSampler) */
+    uint32_t sampler_kind;            /* rrt_sampler_kind                                        */
+    uint32_t strat_xsamp, strat_ysamp;/* StratifiedSampler: xsamp * ysamp samples per pixel, of which the first is
+                                       * never rendered (Q10); `nsamp` is ignored                 */
+    uint32_t strat_dimension;         /* sampled dimensions; a draw past them is U[-1, 1) (Q12)  */
+    uint32_t strat_jitter, pad1;      /* `seed` also seeds the jitter / shuffle streams (csrc/stratified.cuh) */
 } rrt_render_desc;
 
 typedef struct rrt_render rrt_render; /* Box<dyn Integrator> + its film, camera and sampler      */

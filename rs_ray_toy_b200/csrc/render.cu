@@ -26,6 +26,7 @@
 #include "render.hpp"
 #include "scene_tables.cuh"
 #include "shading.cuh"
+#include "stratified.cuh"
 
 namespace rrt {
 namespace {
@@ -59,6 +60,9 @@ struct IntegratorParams {
     uint32_t n_lights, n_samples;  // n_samples = nsamp - 1 rendered samples per pixel (Q10)
     double light_pdf;              // Distribution1D::discrete_pdf of the uniform distribution
     double light_cdf[17];          // up to 16 lights (path.rs:47-49, sampling.rs:10-40)
+    uint32_t sampler_kind, init_dim;  // rrt_sampler_kind; the sampler state right after get_camerasample
+    uint32_t n_samples_all, pad_ip;   // DirectLighting: 1 = LightStrategy::UniformSampleAll
+    StratParams strat;
 };
 
 // Per camera sample state (one record per slot of the chunk)
@@ -88,6 +92,7 @@ struct Queues {
     unsigned long long* stats;  // 64-bit frame totals: [0] camera rays, [1] extension rays, [2] shadow rays, [3] bounces,
                                 // [4] zero-weight samples, [5] fp32-decided lens walks, [6] undecided ones (a 4K frame
                                 // at 256 spp traces 1.9 G extension rays: 32 bits would wrap at 512 spp)
+    const double* cam_samples;  // StratifiedSampler: p_film.xy, p_lens.xy per chunk slot (strat_camera_kernel), else null
     uint8_t* shade_key;   // per extension-queue entry: 0 = miss, 1 + material kind otherwise
     uint32_t* shade_perm; // extension-queue entries grouped by shade_key
 };
@@ -199,10 +204,17 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     } else {
                         px = (int32_t)x;
                         py = (int32_t)y;
+                        if (q.cam_samples != nullptr) {  // StratifiedSampler: drawn by strat_camera_kernel
+                            const double* cs4 = q.cam_samples + 4 * (size_t)slot;
+                            hidx = 0;
+                            pf = P2{cs4[0], cs4[1]};
+                            pl = P2{cs4[2], cs4[3]};
+                        } else {
                         hidx = halton_index(ht, x, y, sn);
                         // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
                         pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
                         pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                        }
                         have = true;
                         stage = GEN_MAIN;
                         need_begin = true;
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
             P->pfy = pf.y;
             P->weight = final_w;
             P->hidx = hidx;
-            P->dim = 5;
+            P->dim = ip.init_dim;
             P->bounces = 0;
             P->px = px;
             P->py = py;
@@ -403,7 +415,7 @@ __device__ __forceinline__ P2 neighbour_film_point(P2 pf, int stage) {
          : stage == GEN_XM ? P2{pf.x + -0.05, pf.y}
          : stage == GEN_YP ? P2{pf.x, pf.y + 0.05} : P2{pf.x, pf.y + -0.05};
 }
-__device__ __forceinline__ void finish_camera_sample(Path* P, const GenSample& g, double final_w) {
+__device__ __forceinline__ void finish_camera_sample(Path* P, const GenSample& g, double final_w, uint32_t init_dim) {
     P->beta = rgb(1.0);
     P->L = rgb(0.0);
     P->eta_scale = 1.0;
@@ -411,7 +423,7 @@ __device__ __forceinline__ void finish_camera_sample(Path* P, const GenSample& g
     P->pfy = g.pf.y;
     P->weight = final_w;
     P->hidx = g.hidx;
-    P->dim = 5;
+    P->dim = init_dim;
     P->bounces = 0;
     P->px = g.px;
     P->py = g.py;
@@ -481,16 +493,23 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     if (!valid) {
                         paths[slot].state = 0;  // no sample in this slot
                     } else {
-                        const uint64_t hidx = halton_index(ht, x, y, sn);
                         fs.slot = slot;
                         fs.sn = sn;
                         fs.px = (int32_t)x;
                         fs.py = (int32_t)y;
                         fs.nb_ok = 0;
-                        fs.hidx = hidx;
-                        // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
-                        fs.pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
-                        fs.pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                        if (q.cam_samples != nullptr) {  // StratifiedSampler: drawn by strat_camera_kernel
+                            const double* cs4 = q.cam_samples + 4 * (size_t)slot;
+                            fs.hidx = 0;
+                            fs.pf = P2{cs4[0], cs4[1]};
+                            fs.pl = P2{cs4[2], cs4[3]};
+                        } else {
+                            const uint64_t hidx = halton_index(ht, x, y, sn);
+                            fs.hidx = hidx;
+                            // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
+                            fs.pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
+                            fs.pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                        }
                         fhave = true;
                         fstage = GEN_MAIN;
                     }
@@ -538,7 +557,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                 Path* P = paths + fs.slot;
                 P->o = v3(0, 0, 0);
                 P->d = v3(0, 0, 0);
-                finish_camera_sample(P, fs, 0.0);
+                finish_camera_sample(P, fs, 0.0, ip.init_dim);
                 n_zero += 1;
                 fhave = false;
             }
@@ -624,7 +643,7 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
                     }
                     need_begin = !done;
                     if (done) {
-                        finish_camera_sample(paths + cs.slot, cs, final_w);
+                        finish_camera_sample(paths + cs.slot, cs, final_w, ip.init_dim);
                         if (final_w > 0.0) {
                             emit = true;
                             n_camera += 1;
@@ -943,6 +962,261 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
     }
 }
 
+// ---- StratifiedSampler: the camera samples of a chunk ---------------------------------------------------------
+// get_camerasample (samplers/mod.rs:28-34) with PixelSampler<Stratified>: p_film = pixel + get_2d(), p_lens = get_2d() +
+// 0.5 (Q11), time = get_1d().  One thread per chunk slot regenerates the two (or fewer: `dimension` may be < 2) table
+// entries it needs (stratified.cuh); the generate kernels read the result instead of drawing Halton values.
+__device__ __forceinline__ bool chunk_slot_sample(const FilmParams& film, const IntegratorParams& ip, const Frame& fr, uint64_t sidx,
+                                                  int64_t* px, int64_t* py, uint32_t* sn) {
+    const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
+    const uint32_t tslot = (uint32_t)(sidx / per_tile);
+    const uint32_t within = (uint32_t)(sidx % per_tile);
+    const uint32_t pix = within / ip.n_samples;
+    *sn = within % ip.n_samples + 1u;  // sample numbers 1..n-1 (Q10)
+    const uint32_t tile = fr.tiles[tslot];
+    const int64_t x = film.sb[0] + (int64_t)(tile % fr.n_tiles_x) * kTile + (pix % kTile);
+    const int64_t y = film.sb[1] + (int64_t)(tile / fr.n_tiles_x) * kTile + (pix / kTile);
+    *px = x;
+    *py = y;
+    bool valid = x < film.sb[2] && y < film.sb[3] && x >= 0 && x < film.xres && y >= 0 && y < film.yres;
+    if (valid && fr.use_crop) valid = x >= fr.crop[0] && x < fr.crop[2] && y >= fr.crop[1] && y < fr.crop[3];
+    return valid;
+}
+__global__ void __launch_bounds__(128) strat_camera_kernel(FilmParams film, IntegratorParams ip, Frame fr, uint64_t base, uint32_t count,
+                                                            double* __restrict__ out4) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= count) return;
+    int64_t x, y;
+    uint32_t sn;
+    if (!chunk_slot_sample(film, ip, fr, base + slot, &x, &y, &sn)) return;
+    uint32_t st = 0;
+    const P2 a = strat_get_2d(ip.strat, x, y, sn, &st);
+    const P2 b = strat_get_2d(ip.strat, x, y, sn, &st);
+    double* o = out4 + 4 * (size_t)slot;
+    o[0] = (double)x + a.x;
+    o[1] = (double)y + a.y;
+    o[2] = b.x + 0.5;
+    o[3] = b.y + 0.5;
+}
+
+// ---- DirectLighting / IntersectDebug with their specular recursion ---------------------------------------------
+// DirectLightingIntegrator::li (directlighting.rs:72-132) and IntersectDebugIntegrator::li (intersect_debug.rs:56-89)
+// share one shape: at a hit, direct light (uniform_sample_one_light or uniform_sample_all_lights as it runs, Q30; Debug
+// adds a constant 0.1), then — while depth + 1 < max_depth — `specular_reflect` and `specular_transmit`
+// (integrator/mod.rs:150-301), each of which draws a get_2d, samples the BSDF's specular lobe and recurses.
+//
+// The recursion is a depth-first walk and the sampler is consumed in that order: the transmit half's get_2d comes AFTER
+// everything the reflected subtree drew.  A path therefore carries ONE ray at a time plus a small stack of pending
+// transmit branches (direction and weight are fixed at the hit: a specular lobe does not read its sample), and the
+// transmit draw is accounted when the branch is popped.  A round of the wavefront advances every live path by one ray;
+// the host loops until the extension queue is empty (at most 2^(max_depth - 1) - 1 + ... rays per camera sample).
+// The children's radiance enters the parent as f * li * |cos| / pdf: here every contribution is multiplied by the
+// product of those factors along its branch (`weight`), which is the same sum up to rounding.
+// Recursive rays carry no differentials (the oracle's li_direct / li_debug do the same).
+constexpr uint32_t kWhittedStack = 8;  // pending transmit branches per camera sample: max_depth <= 9 with specular materials
+struct WhittedBranch {
+    V3 o, d;
+    Rgb w;
+    uint32_t depth, valid;
+};
+struct WhittedSampler {
+    uint64_t hidx;
+    uint32_t dim;
+    int32_t px, py;
+    uint32_t sample;
+};
+__device__ __forceinline__ double wh_1d(const HaltonTables& ht, const uint16_t* perms, const IntegratorParams& ip, WhittedSampler& s) {
+    if (ip.sampler_kind == RRT_SAMPLER_STRATIFIED) return strat_get_1d(ip.strat, s.px, s.py, s.sample, &s.dim);
+    return halton_sample(ht, perms, s.hidx, s.dim++);
+}
+__device__ __forceinline__ P2 wh_2d(const HaltonTables& ht, const uint16_t* perms, const IntegratorParams& ip, WhittedSampler& s) {
+    if (ip.sampler_kind == RRT_SAMPLER_STRATIFIED) return strat_get_2d(ip.strat, s.px, s.py, s.sample, &s.dim);
+    const P2 u = {halton_sample(ht, perms, s.hidx, s.dim), halton_sample(ht, perms, s.hidx, s.dim + 1)};
+    s.dim += 2;
+    return u;
+}
+__device__ __forceinline__ void wh_skip_2d(const IntegratorParams& ip, WhittedSampler& s) {  // a get_2d nobody reads
+    if (ip.sampler_kind == RRT_SAMPLER_STRATIFIED) strat_skip_2d(ip.strat, &s.dim);
+    else s.dim += 2;
+}
+
+template <bool TEXTURED>
+__global__ void __launch_bounds__(128, 2) whitted_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
+                                                        IntegratorParams ip, Path* __restrict__ paths, WhittedBranch* __restrict__ stacks,
+                                                        Queues q, int cur) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = q.counters[cur];
+    bool emit_ext = false;
+    V3 eo = v3(0, 0, 0), ed = v3(0, 0, 0);
+    uint32_t pid = 0;
+    if (qi < n) {
+        pid = q.ext_path[cur][qi];
+        Path* const P = paths + pid;
+        WhittedBranch* const stack = stacks + (size_t)pid * kWhittedStack;
+        V3 ro = P->o, rd = P->d;
+        Rgb weight = P->beta;
+        uint32_t depth = P->state == 1 ? 1u : P->bounces;  // the reference's `depth`: 1 for the camera ray
+        uint32_t sp = P->pad;                              // pending branches
+        WhittedSampler smp{P->hidx, P->dim, P->px, P->py, P->sample};
+        const rrt_hit h = q.hits[qi];
+        const bool found = h.prim_id != RRT_NO_HIT;
+        if (P->state == 1) {  // the camera ray
+            P->first_prim = found ? (int32_t)h.prim_id : -1;
+            P->first_t = found ? h.t : 0.0;
+            P->state = 3;
+        }
+        bool cont = false;
+        if (found) {
+            Surface s;
+            BumpPartials bp;
+            const bool camera_ray = depth == 1 && sp == 0 && sc.ray_diffs != nullptr;
+            if (TEXTURED)
+                make_surface(sc, h.prim_id, h.t, h.u, h.v, ro, rd, &s, sc.bump ? &bp : nullptr);
+            else
+                make_surface(sc, h.prim_id, h.t, h.u, h.v, ro, rd, &s);
+            Bsdf bsdf;
+            if (TEXTURED) {
+                const MaterialRec* m = sc.materials + s.material;
+                MaterialRec textured;
+                if (m->bump_needed) material_bump(sc, *m, camera_ray ? sc.ray_diffs + pid : nullptr, &s, bp);
+                if (m->needed) {
+                    material_at(sc, *m, s, camera_ray ? sc.ray_diffs + pid : nullptr, &textured);
+                    m = &textured;
+                }
+                make_bsdf(*m, s, false, &bsdf);  // compute_scattering_functions(.., allow_multiple_lobes = false, ..)
+            } else {
+                make_bsdf(sc.materials[s.material], s, false, &bsdf);
+            }
+            const bool debug = ip.kind == RRT_INTEGRATOR_DEBUG;
+            if (!bsdf.present && !debug) {
+                // directlighting.rs:96-99: `return self.li(&mut isect.spawn_ray(ray.d), ..)` — on through the surface
+                ro = s.p;
+                rd = normalize(rd);
+                cont = true;
+            } else {
+                if (debug) P->L = P->L + weight * 0.1;  // intersect_debug.rs:67: `l = Spectrum::new([0.1, 0.1, 0.1])`
+                // ---- direct light ----
+                const bool all = debug || ip.n_samples_all != 0u;
+                const uint32_t n_est = ip.n_lights == 0 ? 0u : (all ? ip.n_lights : 1u);
+                for (uint32_t e = 0; e < n_est; ++e) {
+                    uint32_t light_num = e;
+                    double choice_pdf = 1.0;
+                    if (!all) {  // uniform_sample_one_light with no distribution (integrator/mod.rs:371-384)
+                        const double ul = wh_1d(ht, perms, ip, smp);
+                        const uint64_t k = as_u64(ul * (double)ip.n_lights);
+                        light_num = k > ip.n_lights - 1 ? ip.n_lights - 1 : (uint32_t)k;
+                        choice_pdf = 1.0 / (double)ip.n_lights;
+                    }
+                    const LightRec& lt = sc.lights[light_num];
+                    V3 wi = v3(0, 0, 0), p1 = v3(0, 0, 0);
+                    Rgb li;
+                    double light_pdf = 1.0;
+                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA;
+                    if (area) {
+                        const P2 u_light = wh_2d(ht, perms, ip, smp);
+                        li = area_sample_li(lt, s.p, u_light, &wi, &light_pdf, &p1);
+                    } else {
+                        wh_skip_2d(ip, smp);  // u_light: drawn, never read by a delta light
+                        if (lt.kind == RRT_LIGHT_POINT) {
+                            wi = normalize(lt.p_light - s.p);
+                            p1 = lt.p_light;
+                            li = lt.intensity / length_sq(lt.p_light - s.p);
+                        } else {
+                            wi = lt.w_light;
+                            p1 = s.p + lt.w_light * (2.0 * lt.world_radius);
+                            li = lt.intensity;
+                        }
+                    }
+                    wh_skip_2d(ip, smp);  // u_scattering: read only by estimate_direct's BSDF-sampling half (dead, Q22)
+                    if (bsdf.present && light_pdf > 0.0 && !is_black(li)) {
+                        const Rgb f = bsdf_f(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR) * absdot(wi, s.shn);
+                        if (!is_black(f)) {
+                            Rgb ld;
+                            if (area) {
+                                const double wgt = power_heuristic(1, light_pdf, 1, bsdf_pdf(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR));
+                                ld = li * f * wgt / light_pdf;
+                            } else {
+                                ld = f * li / 1.0;
+                            }
+                            if (!all) ld = ld / choice_pdf;
+                            const uint32_t slot_sh = atomicAdd(q.counters + 2, 1u);
+                            write_ray(q.sh_rays + slot_sh, s.p, sc.literal ? normalize(p1 - s.p) : p1 - s.p, 1.0 - kShadowEps);
+                            q.sh_path[slot_sh] = pid;
+                            q.sh_contrib[slot_sh] = weight * ld;
+                        }
+                    }
+                }
+                // ---- specular_reflect, specular_transmit (integrator/mod.rs:150-301) ----
+                if (bsdf.present && depth + 1 < ip.max_depth) {
+                    const P2 u = {0.5, 0.5};  // a specular lobe does not read its sample; the draws are accounted below
+                    V3 wi_r = v3(0, 0, 0), wi_t = v3(0, 0, 0);
+                    double pdf_r = 0.0, pdf_t = 0.0;
+                    uint32_t ty = 0;
+                    const Rgb f_r = bsdf_sample_f(bsdf, s.wo, &wi_r, u, &pdf_r, BXDF_SPECULAR | BXDF_REFLECTION, &ty);
+                    const bool ok_r = pdf_r > 0.0 && !is_black(f_r) && absdot(wi_r, s.shn) != 0.0;
+                    const Rgb f_t = bsdf_sample_f(bsdf, s.wo, &wi_t, u, &pdf_t, BXDF_SPECULAR | BXDF_TRANSMISSION, &ty);
+                    const bool ok_t = pdf_t > 0.0 && !is_black(f_t) && absdot(wi_t, s.shn) != 0.0;
+                    wh_skip_2d(ip, smp);  // specular_reflect's get_2d
+                    if (ok_r) {
+                        // the reflected subtree runs first; the transmit half waits on the stack with its draw still to come
+                        WhittedBranch b;
+                        b.o = s.p;
+                        b.d = ok_t ? normalize(wi_t) : v3(0, 0, 0);
+                        b.w = ok_t ? weight * (f_t * absdot(wi_t, s.shn) / pdf_t) : rgb(0.0);
+                        b.depth = depth + 1;
+                        b.valid = ok_t ? 1u : 0u;
+                        stack[sp++] = b;
+                        ro = s.p;
+                        rd = normalize(wi_r);  // spawn_ray -> Ray::new_od normalises
+                        weight = weight * (f_r * absdot(wi_r, s.shn) / pdf_r);
+                        depth += 1;
+                        cont = true;
+                    } else {
+                        wh_skip_2d(ip, smp);  // specular_transmit's get_2d follows at once
+                        if (ok_t) {
+                            ro = s.p;
+                            rd = normalize(wi_t);
+                            weight = weight * (f_t * absdot(wi_t, s.shn) / pdf_t);
+                            depth += 1;
+                            cont = true;
+                        }
+                    }
+                }
+            }
+        }
+        // this branch is finished: back to the innermost pending transmit half
+        while (!cont && sp > 0) {
+            const WhittedBranch b = stack[--sp];
+            wh_skip_2d(ip, smp);  // its get_2d, drawn after the reflected subtree
+            if (b.valid) {
+                ro = b.o;
+                rd = b.d;
+                weight = b.w;
+                depth = b.depth;
+                cont = true;
+            }
+        }
+        P->dim = smp.dim;
+        P->pad = sp;
+        if (cont) {
+            P->o = ro;
+            P->d = rd;
+            P->beta = weight;
+            P->bounces = depth;
+            emit_ext = true;
+            eo = ro;
+            ed = rd;
+        } else {
+            P->state = 2;
+        }
+    }
+    const uint32_t es = queue_slot(q.counters + (cur ^ 1), emit_ext);
+    if (emit_ext) {
+        write_ray(q.ext_rays[cur ^ 1] + es, eo, ed, kInfD);
+        q.ext_path[cur ^ 1][es] = pid;
+    }
+}
+
 // Unoccluded light samples join their path's radiance (`l += ld`, path.rs:121 / directlighting.rs:113)
 // `shared_paths`: several light samples may belong to one path (UniformSampleAll): they are added with atomics.
 __global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, Queues q, int shared_paths) {
@@ -1111,6 +1385,10 @@ struct Renderer::Impl {
     bool textured = false, want_diffs = false;
     bool all_lights = false;        // DirectLighting, UniformSampleAll
     uint32_t shadow_per_hit = 1;
+    bool whitted = false;           // DirectLighting with specular recursion / Debug / StratifiedSampler: whitted_kernel
+    uint32_t whitted_rounds = 1;    // upper bound of rays per camera sample
+    WhittedBranch* d_stacks = nullptr;
+    double* d_cam_samples = nullptr;
     // RRT_GEN_F32: 2 = screened generate kernel (fp32 walks decide blocked samples and neighbour rays; the default),
     // 1 = the lane-state-machine kernel with fp32 neighbour walks, 0 = every lens trace in f64 (the parity tests' A/B switch)
     int gen_mode = 2;
@@ -1249,7 +1527,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         if (err) *err = "Camera lens_data must hold 4 values per element (camera.rs:77), at most 32 elements";
         return RRT_ERR_INVALID;
     }
-    if (d.nsamp < 1 || d.nsamp > (1ull << 32)) {
+    if (d.sampler_kind != RRT_SAMPLER_STRATIFIED && (d.nsamp < 1 || d.nsamp > (1ull << 32))) {
         if (err) *err = "HaltonSampler nsamp must be in 1 .. 2^32";
         return RRT_ERR_INVALID;
     }
@@ -1306,21 +1584,61 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
             }
         }
     }
-    bool specular_material = false;
+    bool specular_material = false, splitting_material = false;
     for (const rrt_material& m : materials) {
         if (m.kind > RRT_MAT_GLASS) {
             if (err) *err = "material kind outside the hot-path scope";
             return RRT_ERR_UNSUPPORTED;
         }
-        specular_material |= m.kind == RRT_MAT_MIRROR || m.kind == RRT_MAT_GLASS;
+        const bool smooth_glass = m.kind == RRT_MAT_GLASS && !(m.u_roughness > 0.0) && !(m.v_roughness > 0.0);
+        specular_material |= m.kind == RRT_MAT_MIRROR || smooth_glass;
+        splitting_material |= smooth_glass;  // a specular reflection AND a specular transmission lobe: the recursion forks
     }
-    if (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.max_depth > 1 && specular_material) {
-        if (err) *err = "DirectLighting's specular recursion (integrator/mod.rs:150-301) is outside the hot-path scope";
-        return RRT_ERR_UNSUPPORTED;
-    }
-    if (d.integrator_kind > RRT_INTEGRATOR_DIRECT) {
+    if (d.integrator_kind > RRT_INTEGRATOR_DEBUG) {
         if (err) *err = "integrator kind outside the hot-path scope";
         return RRT_ERR_UNSUPPORTED;
+    }
+    if (d.sampler_kind > RRT_SAMPLER_STRATIFIED) {
+        if (err) *err = "unknown sampler kind";
+        return RRT_ERR_INVALID;
+    }
+    const bool stratified = d.sampler_kind == RRT_SAMPLER_STRATIFIED;
+    if (stratified) {
+        if (d.strat_xsamp == 0 || d.strat_ysamp == 0 || (uint64_t)d.strat_xsamp * d.strat_ysamp > kStratMaxSamples ||
+            d.strat_dimension > kStratMaxDims) {
+            if (err) *err = "StratifiedSampler: xsamp * ysamp must be in 1 .. 256 and dimension <= 60";
+            return RRT_ERR_UNSUPPORTED;
+        }
+        if (d.integrator_kind == RRT_INTEGRATOR_PATH) {
+            // Beyond `dimension` sampled dimensions the reference's PixelSampler hands out U[-1, 1) (Q12): a Path
+            // integrator samples its BSDFs and its Russian roulette with those.  DirectLighting and Debug are the
+            // integrators the reference's own scene files pair with this sampler.
+            if (err) *err = "StratifiedSampler is available with the DirectLighting and Debug integrators";
+            return RRT_ERR_UNSUPPORTED;
+        }
+    }
+    // the integrators that recurse through specular lobes run the depth-first wavefront (whitted_kernel)
+    const bool whitted = d.integrator_kind == RRT_INTEGRATOR_DEBUG || stratified ||
+                         (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.max_depth > 1 && specular_material);
+    uint64_t whitted_hits = 1;  // hits one camera sample can shade
+    if (whitted && specular_material && d.max_depth > 1) {
+        if (splitting_material) {
+            if (d.max_depth > kWhittedStack + 1) {
+                if (err) *err = "max_depth above 9 with a specular glass: the pending-branch stack holds 8 entries";
+                return RRT_ERR_UNSUPPORTED;
+            }
+            whitted_hits = (1ull << (d.max_depth - 1)) - 1;
+        } else {
+            whitted_hits = d.max_depth - 1;
+        }
+    }
+    if (whitted && d.sampler_kind == RRT_SAMPLER_HALTON) {
+        const bool all = d.integrator_kind == RRT_INTEGRATOR_DEBUG || d.light_strategy != 0;
+        const uint64_t per_hit = (all ? 4u * (uint64_t)lights.size() : (lights.empty() ? 0u : 5u)) + 4u;  // + the two specular draws
+        if (5u + per_hit * whitted_hits > (uint64_t)kHaltonDims) {
+            if (err) *err = "this integrator setting reads more Halton dimensions than the device tables hold (" + std::to_string(kHaltonDims) + ")";
+            return RRT_ERR_UNSUPPORTED;
+        }
     }
     RND_CUDA(cudaSetDevice(device));
     impl_ = new Impl();
@@ -1479,7 +1797,24 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
     P.max_depth = d.max_depth;
     P.rr_threshold = d.rr_threshold;
     P.n_lights = (uint32_t)lights.size();
-    P.n_samples = (uint32_t)(d.nsamp - 1);
+    P.n_samples = stratified ? d.strat_xsamp * d.strat_ysamp - 1u : (uint32_t)(d.nsamp - 1);
+    P.sampler_kind = d.sampler_kind;
+    P.n_samples_all = d.light_strategy ? 1u : 0u;
+    P.init_dim = 5;  // Halton: dimensions 0-4 belong to the camera sample
+    if (stratified) {
+        P.strat = StratParams{d.strat_xsamp, d.strat_ysamp, d.strat_dimension, d.strat_jitter ? 1u : 0u, d.seed, d.xres};
+        // get_camerasample: two get_2d, one get_1d (stratified.cuh's packed counters)
+        uint32_t d1 = 0, d2 = 0, ov = 0;
+        for (int k = 0; k < 2; ++k) {
+            if (d2 < d.strat_dimension) d2 += 1;
+            else ov += 2;
+        }
+        if (d1 < d.strat_dimension) d1 += 1;
+        else ov += 1;
+        P.init_dim = d1 | (d2 << 8) | (ov << 16);
+    }
+    I.whitted = whitted;
+    I.whitted_rounds = (uint32_t)std::min<uint64_t>(whitted_hits, 1u << 20);
     {
         const size_t n = lights.size();
         for (double& c : P.light_cdf) c = 0.0;
@@ -1603,17 +1938,23 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         const uint64_t frame = ntx * nty * kTile * kTile * std::max<uint64_t>(1, I.ip.n_samples);
         I.chunk = (uint32_t)std::min<uint64_t>(kChunk, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
         // UniformSampleAll: up to n_lights shadow rays per hit — the chunk shrinks so that the shadow queue does not grow
-        I.all_lights = d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.light_strategy == 1 && !lights.empty();
+        I.all_lights = (d.integrator_kind == RRT_INTEGRATOR_DEBUG || (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.light_strategy == 1)) && !lights.empty();
         I.shadow_per_hit = I.all_lights ? (uint32_t)lights.size() : 1u;
         if (I.all_lights) I.chunk = std::max<uint32_t>(1u << 16, (I.chunk / I.shadow_per_hit) & ~65535u);
     }
+    if (I.whitted) I.chunk = std::min<uint32_t>(I.chunk, 1u << 21);  // 640 B of branch stack per slot
     const size_t kSlots = I.chunk;
     if ((rc = dev_alloc((void**)&I.d_paths, (size_t)kSlots * sizeof(Path))) != RRT_OK) return rc;
+    if (I.whitted && (rc = dev_alloc((void**)&I.d_stacks, kSlots * kWhittedStack * sizeof(WhittedBranch))) != RRT_OK) return rc;
+    if (stratified) {
+        if ((rc = dev_alloc((void**)&I.d_cam_samples, kSlots * 4 * sizeof(double))) != RRT_OK) return rc;
+        I.q.cam_samples = I.d_cam_samples;
+    }
     if (const char* e = std::getenv("RRT_GEN_F32")) I.gen_mode = std::atoi(e);
     if (I.want_diffs) {
         if ((rc = dev_alloc((void**)&I.d_diffs, (size_t)kSlots * sizeof(RayDiffRec))) != RRT_OK) return rc;
         I.sc.ray_diffs = I.d_diffs;
-        I.diff_scale = 1.0 / std::sqrt((double)d.nsamp);
+        I.diff_scale = 1.0 / std::sqrt(stratified ? (double)(d.strat_xsamp * d.strat_ysamp) : (double)d.nsamp);
     }
     for (int k = 0; k < 2; ++k) {
         if ((rc = dev_alloc((void**)&I.q.ext_rays[k], kSlots * sizeof(rrt_ray))) != RRT_OK) return rc;
@@ -1697,11 +2038,15 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
         }
         RND_CUDA(cudaMemsetAsync(I.d_dump + 6 * I.dump_count, 0xFF, total * 6 * sizeof(double), I.stream));  // NaN = empty slot
     }
-    const uint32_t rounds = I.ip.kind == RRT_INTEGRATOR_PATH ? I.ip.max_depth + 1 : 1;
+    const uint32_t rounds = I.whitted ? I.whitted_rounds : (I.ip.kind == RRT_INTEGRATOR_PATH ? I.ip.max_depth + 1 : 1);
     uint64_t launches = 0;
     for (uint64_t base = 0; base < total; base += I.chunk) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(I.chunk, total - base);
         RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
+        if (I.d_cam_samples) {
+            strat_camera_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.film, I.ip, fr, base, count, I.d_cam_samples);
+            launches += 1;
+        }
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
         if (I.gen_mode == 2 && I.d_diffs == nullptr)
@@ -1717,6 +2062,11 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             int rc = I.agg->closest_hit_indirect(count, I.q.counters + cur, I.q.ext_rays[cur], I.q.hits, I.stream, err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;
+            if (I.whitted) {
+                auto shade = I.textured ? whitted_kernel<true> : whitted_kernel<false>;
+                shade<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.d_stacks, I.q, cur);
+                launches += 1;
+            } else {
 #if RRT_SHADE_SORT
             shade_bin_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.sc, I.q, cur);
             shade_scatter_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.q, cur);
@@ -1727,15 +2077,25 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
                                           : (I.textured ? shade_kernel<true, false> : shade_kernel<false, false>);
                 shade<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
             }
+            launches += 1;
+            }
             rc = I.agg->any_hit_indirect((uint64_t)count * I.shadow_per_hit, I.q.counters + 2, I.q.sh_rays, I.q.sh_occluded, I.stream,
                                          err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;
-            resolve_kernel<<<(unsigned)(((uint64_t)count * I.shadow_per_hit + 255) / 256), 256, 0, I.stream>>>(I.d_paths, I.q,
-                                                                                                            I.all_lights ? 1 : 0);
+            resolve_kernel<<<(unsigned)(((uint64_t)count * I.shadow_per_hit + 255) / 256), 256, 0, I.stream>>>(
+                I.d_paths, I.q, (I.all_lights || I.whitted) ? 1 : 0);
             advance_kernel<<<1, 1, 0, I.stream>>>(I.q, cur);
-            launches += 3;
+            launches += 2;
             cur ^= 1;
+            if (I.whitted && r + 1 < rounds) {
+                // the depth-first walk ends when no path has a ray left: ask the device (these integrators are the
+                // reference-compatibility path, not the throughput path)
+                uint32_t left = 0;
+                RND_CUDA(cudaMemcpyAsync(&left, I.q.counters + cur, sizeof(left), cudaMemcpyDeviceToHost, I.stream));
+                RND_CUDA(cudaStreamSynchronize(I.stream));
+                if (left == 0) break;
+            }
         }
         deposit_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.film, I.d_paths, count, static_cast<double*>(d_film_),
                                                                    I.dump_enabled ? I.d_dump : nullptr, I.dump_count + base);

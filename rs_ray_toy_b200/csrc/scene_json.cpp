@@ -568,8 +568,11 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
         }
         d.filter_radius[0] = d.filter_radius[1] = def;
         if (const Value* r = flt->get("radius"); r && r->is_array() && r->arr.size() >= 2) {
+            if (!r->arr[0]->is_number() || !r->arr[1]->is_number()) throw std::runtime_error("Film.Filter.radius entries must be numbers");
             d.filter_radius[0] = r->arr[0]->num;
             d.filter_radius[1] = r->arr[1]->num;
+            if (!(d.filter_radius[0] > 0.0) || !(d.filter_radius[1] > 0.0) || !std::isfinite(d.filter_radius[0]) || !std::isfinite(d.filter_radius[1]))
+                throw std::runtime_error("Film.Filter.radius must be finite and > 0");
         }
         d.filter_alpha = read_f64(*flt, "alpha", 2.0);
     }
@@ -583,27 +586,51 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
     d.simple_weighting = read_bool(*cc, "simple_weighting", true) ? 1 : 0;
     const Value* lens = cc->get("lens_data");
     if (!lens || !lens->is_array()) throw std::runtime_error("Camera.lens_data is required (renderprocess.rs:1379)");
-    for (const auto& x : lens->arr) out->lens_data.push_back(x->num);
+    for (const auto& x : lens->arr) {
+        if (!x->is_number()) throw std::runtime_error("Camera.lens_data entries must be numbers");
+        out->lens_data.push_back(x->num);
+    }
     d.lens_data = out->lens_data.data();
     d.n_lens_values = (uint32_t)out->lens_data.size();
+    auto checked_u32 = [](int64_t v, int64_t lo, int64_t hi, const char* what) -> uint32_t {
+        if (v < lo || v > hi) throw std::runtime_error(std::string(what) + " is out of range");
+        return (uint32_t)v;
+    };
     const std::string st = read_string(*sc, "sampler_type", "");
-    if (st != "HaltonSampler")
-        throw std::runtime_error("Sampler '" + st + "': only HaltonSampler is reproducible; StratifiedSampler draws from an unseeded RNG");
-    d.nsamp = (uint64_t)read_i64(*sc, "nsamp", 16);
-    d.sample_at_center = read_bool(*sc, "sample_at_center", false) ? 1 : 0;
     d.seed = seed;
+    if (st == "HaltonSampler") {
+        const int64_t nsamp = read_i64(*sc, "nsamp", 16);
+        if (nsamp < 1 || nsamp > (int64_t)1 << 32) throw std::runtime_error("Sampler.nsamp is out of range (1 .. 2^32)");
+        d.nsamp = (uint64_t)nsamp;
+        d.sample_at_center = read_bool(*sc, "sample_at_center", false) ? 1 : 0;
+        d.sampler_kind = RRT_SAMPLER_HALTON;
+    } else if (st == "StratifiedSampler") {  // renderprocess.rs:1308-1314
+        d.sampler_kind = RRT_SAMPLER_STRATIFIED;
+        d.strat_jitter = read_bool(*sc, "jitter", true) ? 1 : 0;
+        d.strat_xsamp = checked_u32(read_i64(*sc, "xsamp", 4), 1, 256, "Sampler.xsamp");
+        d.strat_ysamp = checked_u32(read_i64(*sc, "ysamp", 4), 1, 256, "Sampler.ysamp");
+        d.strat_dimension = checked_u32(read_i64(*sc, "dimension", 4), 0, 255, "Sampler.dimension");
+        d.nsamp = (uint64_t)d.strat_xsamp * d.strat_ysamp;
+    } else {
+        throw std::runtime_error("Unsupported Sampler type '" + st + "' (the reference panics: renderprocess.rs:1322)");
+    }
     const std::string it = read_string(*ic, "integrator_type", "AO");
     if (it == "Path") {
         d.integrator_kind = RRT_INTEGRATOR_PATH;
-        d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
+        d.max_depth = checked_u32(read_i64(*ic, "max_depth", 5), 0, 64, "Integrator.max_depth");
         d.rr_threshold = read_f64(*ic, "rr_threshold", 1.0);
     } else if (it == "DirectLighting") {
         d.light_strategy = read_string(*ic, "light_strategy", "one") == "all" ? 1u : 0u;  // renderprocess.rs:1413-1417
         d.integrator_kind = RRT_INTEGRATOR_DIRECT;
-        d.max_depth = (uint32_t)read_i64(*ic, "max_depth", 5);
+        d.max_depth = checked_u32(read_i64(*ic, "max_depth", 5), 0, 64, "Integrator.max_depth");
+        d.rr_threshold = 1.0;
+    } else if (it == "Debug") {  // renderprocess.rs:1471-1481: max_depth only; always uniform_sample_all_lights
+        d.integrator_kind = RRT_INTEGRATOR_DEBUG;
+        d.light_strategy = 1u;
+        d.max_depth = checked_u32(read_i64(*ic, "max_depth", 5), 0, 64, "Integrator.max_depth");
         d.rr_threshold = 1.0;
     } else {
-        throw std::runtime_error("integrator '" + it + "' is outside the hot-path scope (Path, DirectLighting)");
+        throw std::runtime_error("integrator '" + it + "' is outside the hot-path scope (Path, DirectLighting, Debug)");
     }
 }
 

@@ -33,6 +33,8 @@ class RenderDesc(C.Structure):
         ("seed", C.c_uint64),
         ("integrator_kind", C.c_uint32), ("max_depth", C.c_uint32),
         ("rr_threshold", C.c_double),
+        ("sampler_kind", C.c_uint32), ("strat_xsamp", C.c_uint32), ("strat_ysamp", C.c_uint32),
+        ("strat_dimension", C.c_uint32), ("strat_jitter", C.c_uint32), ("pad1", C.c_uint32),
     ]
 
 

@@ -193,7 +193,10 @@ def test_crop_and_api_scene(ctx, tmp_path):
 def test_unsupported_inputs_are_refused(ctx, tmp_path):
     from rs_ray_toy_b200 import capi
     path = synth.scene_c1(str(tmp_path / "c1"), xres=64, yres=36, nsamp=3)
-    for ov, status in (({"Sampler": {"sampler_type": "StratifiedSampler"}}, capi.RRT_ERR_IO),
+    for ov, status in (({"Sampler": {"sampler_type": "SobolSampler"}}, capi.RRT_ERR_IO),
+                       ({"Sampler": {"sampler_type": "HaltonSampler", "nsamp": -3}}, capi.RRT_ERR_IO),
+                       ({"Integrator": {"integrator_type": "Path", "max_depth": -1}}, capi.RRT_ERR_IO),
+                       ({"Film": {"xres": 64, "yres": 36, "Filter": {"filter_type": "GaussianFilter", "radius": [0.0, 2.0]}}}, capi.RRT_ERR_IO),
                        ({"Integrator": {"integrator_type": "SPPM"}}, capi.RRT_ERR_IO),
                        ({"infinite_lights": [{"light_type": "infinite"}]}, capi.RRT_ERR_IO)):
         with pytest.raises(capi.RrtError) as e:
