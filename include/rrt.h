@@ -168,8 +168,12 @@ typedef enum rrt_texture_kind {
     RRT_TEX_CONSTANT = 0, RRT_TEX_BILERP = 1, RRT_TEX_SCALE = 2, RRT_TEX_MIX = 3, RRT_TEX_CHECKER2D = 4,
     RRT_TEX_CHECKER3D = 5, RRT_TEX_UV = 6,
     RRT_TEX_WINDY = 7,    /* windy.rs: |fbm(0.1 p, 3 octaves)| * fbm(p, 6 octaves) over Perlin noise (texture/mod.rs:75-155) */
-    RRT_TEX_WRINKLED = 8  /* wrinkled.rs: turbulence(p, omega = map[1], octaves = map[0]) (texture/mod.rs:157-188)     */
+    RRT_TEX_WRINKLED = 8, /* wrinkled.rs: turbulence(p, omega = map[1], octaves = map[0]) (texture/mod.rs:157-188)     */
+    RRT_TEX_IMAGE = 9     /* imagemap.rs + mipmap.rs: an rgb texture over an image added with rrt_scene_add_image*: t1 = the
+                           * image's index, aa = do_trilinear, v[0][0] = max_aniso (default 8), v[0][1] = wrap (rrt_image_wrap);
+                           * EWA or trilinear MIPMap lookups exactly as the reference runs them (csrc/mipmap_core.h: Q31, Q32) */
 } rrt_texture_kind;
+typedef enum rrt_image_wrap { RRT_WRAP_REPEAT = 0, RRT_WRAP_BLACK = 1, RRT_WRAP_CLAMP = 2 } rrt_image_wrap;
 typedef enum rrt_texture_mapping {
     RRT_TEXMAP_UV = 0, RRT_TEXMAP_PLANAR = 1, RRT_TEXMAP_SPHERICAL = 2, RRT_TEXMAP_CYLINDRICAL = 3
 } rrt_texture_mapping;
@@ -195,7 +199,11 @@ typedef enum rrt_material_slot {
  * A DiffuseAreaLight samples a shape of its own — make_light_shape (renderprocess.rs:1078-1095): a Sphere with its
  * own transform, or one triangle of a loaded mesh (untransformed vertices, Q7).  That shape is not in the aggregate
  * and the loader attaches no area light to any primitive (Q22): the emitter is sampled by next-event estimation only. */
-typedef enum rrt_light_kind { RRT_LIGHT_POINT = 0, RRT_LIGHT_DISTANT = 1, RRT_LIGHT_DIFFUSE_AREA = 2 } rrt_light_kind;
+/* RRT_LIGHT_INFINITE: lights/infinite.rs — an environment map sampled through its luminance distribution, with the
+ * BSDF-sampling half of estimate_direct live (integrator/mod.rs:484-556): `env_image` = index of an image added with
+ * rrt_scene_add_image*, `to_world` = light_to_world, `shape_to_world_inv` = world_to_light (make_to_world's own inverse).
+ * `intensity` is carried but, like the reference (Q34), never multiplied in.                                         */
+typedef enum rrt_light_kind { RRT_LIGHT_POINT = 0, RRT_LIGHT_DISTANT = 1, RRT_LIGHT_DIFFUSE_AREA = 2, RRT_LIGHT_INFINITE = 3 } rrt_light_kind;
 typedef enum rrt_light_shape_kind { RRT_LIGHT_SHAPE_SPHERE = 0, RRT_LIGHT_SHAPE_TRIANGLE = 1 } rrt_light_shape_kind;
 typedef struct rrt_light {
     uint32_t kind;
@@ -208,7 +216,8 @@ typedef struct rrt_light {
     double radius, z_min, z_max, phi_max_deg;          /* sphere (sampling ignores the clipping; area() does not) */
     double tri_p[9];      /* triangle: p0 p1 p2                                                 */
     double tri_n[9];      /* triangle: vertex normals (when tri_has_n)                          */
-    uint32_t tri_has_n, pad;
+    uint32_t tri_has_n;
+    uint32_t env_image;   /* infinite: image index                                              */
 } rrt_light;
 
 typedef enum rrt_filter_kind { RRT_FILTER_BOX = 0, RRT_FILTER_GAUSSIAN = 1, RRT_FILTER_TRIANGLE = 2 } rrt_filter_kind;
@@ -252,6 +261,14 @@ typedef struct rrt_render rrt_render; /* Box<dyn Integrator> + its film, camera 
 
 int rrt_scene_set_materials(rrt_scene* scene, uint32_t n, const rrt_material* materials);
 int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
+/* Scene::infinite_lights (scene.rs:17-30, make_all_lights renderprocess.rs:945-960): the second light list, which only
+ * PathIntegrator reads — an escaped camera ray or specular bounce adds every entry's Light::le (path.rs:79-88).       */
+int rrt_scene_set_infinite_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights);
+/* Images for RRT_TEX_IMAGE textures and RRT_LIGHT_INFINITE lights: 8-bit RGB, rows top first (what
+ * `image::io::Reader::open(..).decode().into_rgb8()` hands load_image, renderprocess.rs:535-566), or a PNG file read by the
+ * library (non-interlaced, 8 bits per channel or palette).  *index receives the image's number.                      */
+int rrt_scene_add_image(rrt_scene* scene, uint32_t width, uint32_t height, const uint8_t* rgb8, uint32_t* index);
+int rrt_scene_add_image_png(rrt_scene* scene, const char* path, uint32_t* index);
 /* The texture table (n <= RRT_MAX_TEXTURES) and, per material set with rrt_scene_set_materials, the
  * RRT_MATERIAL_SLOTS texture indices of its parameters (slots[material * RRT_MATERIAL_SLOTS + slot], -1 = constant).
  * Optional: a scene without these calls has constant-valued materials.                                        */

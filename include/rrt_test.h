@@ -68,6 +68,17 @@ int rrt_tri_screen_host_probe(uint64_t n, const double* o3, const double* d3, co
 int rrt_stratified_host_probe(uint64_t seed, int64_t xres, int64_t px, int64_t py, uint32_t xs, uint32_t ys, uint32_t ndims,
                               int jitter, double* out1d, double* out2d, double* overflow4);
 
+/* Host-only probes of the image path.  rrt_png_host_probe: the library's PNG reader (csrc/image_host.cpp) -> 8-bit RGB.
+ * rrt_mipmap_host_probe: MIPMap::create on the host, then for each of n queries (st[2], dstdx[2], dstdy[2]) the device
+ * lookups of csrc/mipmap_core.h run on the host: lookup_d -> out6[0..2], lookup_w(st, width = dstdx[0]) -> out6[3..5];
+ * info = levels, then (u_res, v_res) per level.  rrt_envlight_host_probe: InfiniteAreaLight::new's distribution, then per
+ * query (ref point[3], u[2], w[3]): sample_li -> Li[3], wi[3], pdf; pdf_li(w); le(w)[3]; p1.x.                        */
+int rrt_png_host_probe(const char* path, uint32_t* width, uint32_t* height, uint8_t* rgb8, uint64_t capacity);
+int rrt_mipmap_host_probe(uint32_t width, uint32_t height, const uint8_t* rgb8, int trilinear, double max_aniso, uint32_t wrap,
+                          uint64_t n, const double* q6, double* out6, uint64_t info[32]);
+int rrt_envlight_host_probe(uint32_t width, uint32_t height, const uint8_t* rgb8, const double to_world16[16],
+                            const double to_local16[16], double world_radius, uint64_t n, const double* in8, double* out12);
+
 #ifdef __cplusplus
 }
 #endif

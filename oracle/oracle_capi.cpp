@@ -4,6 +4,7 @@
 // CPU restatement.  Nothing in the product links or loads this file.
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -414,7 +415,15 @@ int32_t orc_hardware_threads() { return (int32_t)std::thread::hardware_concurren
 #include "rt_render.hpp"
 
 namespace {
+struct EnvImage {
+    uint64_t w = 0, h = 0;
+    std::vector<uint8_t> rgb8;
+};
 struct RenderSetup {
+    std::vector<std::unique_ptr<MipMap>> images;  // ImageTexture mip maps (stable addresses)
+    std::vector<EnvImage> env_images;             // InfiniteAreaLight maps, kept raw until the world bound is known
+    std::vector<Light> inf_specs;                 // the scene file's `infinite_lights` list
+    std::vector<Xform> inf_xf;
     std::vector<Texture> textures;
     std::vector<Material> materials;
     std::vector<Light> light_specs;  // distant: w_light holds the raw (from - to) until render time
@@ -477,6 +486,84 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
 // 7-22 light_to_world m (row-major) | 23 pad.  (The inverse is not needed: vectors use m.)
 // Texture table, 48 doubles per texture (tests/oracle_scene.py texture_rows): 0 kind | 1 is_rgb | 2 mapping | 3 aa |
 // 4 t1 | 5 t2 | 6 amount | 8-19 v[4][3] | 20-27 map[8] | 28-43 IdentityMapping3D matrix (row-major).
+// load_image (renderprocess.rs:535-566): 8-bit RGB rows as decoded (top row first); returns the image's index.
+int32_t orc_add_image(void* sp, uint64_t w, uint64_t h, const uint8_t* rgb8, int32_t trilinear, double max_aniso, uint32_t wrap) {
+    try {
+        RenderSetup& rs = setup_of(sp);
+        auto m = std::make_unique<MipMap>();
+        m->create(w, h, texels_from_rgb8(rgb8, w, h), trilinear != 0, max_aniso, wrap);
+        rs.images.push_back(std::move(m));
+        return (int32_t)rs.images.size() - 1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+int32_t orc_add_env_image(void* sp, uint64_t w, uint64_t h, const uint8_t* rgb8) {
+    RenderSetup& rs = setup_of(sp);
+    EnvImage e;
+    e.w = w;
+    e.h = h;
+    e.rgb8.assign(rgb8, rgb8 + 3 * w * h);
+    rs.env_images.push_back(std::move(e));
+    return (int32_t)rs.env_images.size() - 1;
+}
+// MIPMap probe: out = levels, then per level u_res, v_res; lookups: for each of n points (st, dstdx, dstdy: 6 doubles)
+// lookup_d -> rgb and lookup_w(st, width = dstdx.x) -> rgb (6 doubles per point)
+int32_t orc_mipmap_probe(void* sp, int32_t image, uint64_t n, const double* q6, double* out6, uint64_t* info) {
+    try {
+        RenderSetup& rs = setup_of(sp);
+        const MipMap& m = *rs.images.at((size_t)image);
+        info[0] = m.levels();
+        for (uint64_t l = 0; l < m.levels() && l < 15; ++l) {
+            info[1 + 2 * l] = m.pyramid[l].u_res;
+            info[2 + 2 * l] = m.pyramid[l].v_res;
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            const double* a = q6 + 6 * i;
+            Rgb d = m.lookup_d(P2(a[0], a[1]), P2(a[2], a[3]), P2(a[4], a[5]));
+            Rgb w = m.lookup_w(P2(a[0], a[1]), a[2]);
+            for (int k = 0; k < 3; ++k) {
+                out6[6 * i + k] = d.c[k];
+                out6[6 * i + 3 + k] = w.c[k];
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+// InfiniteAreaLight probe: per query (ref point[3], u[2], w[3]) -> sample_li: Li[3], wi[3], pdf; pdf_li(w); le(w)[3]; p1.x
+int32_t orc_envlight_probe(uint64_t w, uint64_t h, const uint8_t* rgb8, const double* to_world16, const double* to_local16,
+                           const double* wb6, uint64_t n, const double* in8, double* out12) {
+    try {
+        InfiniteLight il;
+        Xform l2w, w2l;
+        std::memcpy(l2w.m.m, to_world16, 16 * sizeof(double));
+        std::memcpy(l2w.inv.m, to_local16, 16 * sizeof(double));
+        w2l = xf_inverse(l2w);
+        B3 wb;
+        wb.lo = V3(wb6[0], wb6[1], wb6[2]);
+        wb.hi = V3(wb6[3], wb6[4], wb6[5]);
+        il.init(rgb8, w, h, l2w, w2l, wb);
+        for (uint64_t i = 0; i < n; ++i) {
+            const double* a = in8 + 8 * i;
+            double* o = out12 + 12 * i;
+            V3 wi, p1;
+            double pdf = 0.0;
+            Rgb li = il.sample_li(V3(a[0], a[1], a[2]), P2(a[3], a[4]), &wi, &pdf, &p1);
+            V3 dir(a[5], a[6], a[7]);
+            Rgb le = il.le(dir);
+            o[0] = li.c[0]; o[1] = li.c[1]; o[2] = li.c[2]; o[3] = wi.x; o[4] = wi.y; o[5] = wi.z; o[6] = pdf;
+            o[7] = il.pdf_li(dir); o[8] = le.c[0]; o[9] = le.c[1]; o[10] = le.c[2]; o[11] = p1.x;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 void orc_set_textures(void* sp, uint32_t n, const double* t) {
     RenderSetup& rs = setup_of(sp);
     rs.textures.clear();
@@ -497,6 +584,13 @@ void orc_set_textures(void* sp, uint32_t n, const double* t) {
         for (int k = 0; k < 8; ++k) x.map[k] = a[20 + k];
         std::memcpy(x.w2t.m.m, a + 28, 16 * sizeof(double));
         x.w2t.inv = x.w2t.m;  // unused
+        if (x.kind == TEX_IMAGE) {
+            if (x.t1 < 0 || (size_t)x.t1 >= rs.images.size()) {
+                g_err = "image texture names an image that was not added";
+                return;
+            }
+            x.image = rs.images[(size_t)x.t1].get();
+        }
         rs.textures.push_back(x);
     }
 }
@@ -574,9 +668,24 @@ void orc_set_lights(void* sp, uint32_t n, const double* l) {
             }
             lt.tri_has_n = a[78] != 0.0;
         }
+        if (lt.kind == LIGHT_INFINITE) {
+            lt.env_image = (int)a[23];
+            std::memcpy(x.inv.m, a + 40, 16 * sizeof(double));  // world_to_light as make_to_world composed it
+        }
         rs.light_specs.push_back(lt);
         rs.light_xf.push_back(x);
     }
+}
+// the scene file's `infinite_lights` list (same rows): PathIntegrator reads it for escaped rays (path.rs:84)
+void orc_set_infinite_lights(void* sp, uint32_t n, const double* l) {
+    RenderSetup& rs = setup_of(sp);
+    std::vector<Light> keep = rs.light_specs;
+    std::vector<Xform> keep_xf = rs.light_xf;
+    orc_set_lights(sp, n, l);
+    rs.inf_specs = rs.light_specs;
+    rs.inf_xf = rs.light_xf;
+    rs.light_specs = keep;
+    rs.light_xf = keep_xf;
 }
 
 // DiffuseAreaLight::sample_li probe for one light row (80 doubles): out10 = wi[3], pdf, p_shape[3], L[3].
@@ -625,6 +734,15 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
         for (const GeoPrim& g : s->geom.geos)
             if (g.material < 0 || (size_t)g.material >= rs.materials.size()) throw std::runtime_error("material index out of range");
         B3 wb = s->bvh.world_bound();
+        std::vector<std::unique_ptr<InfiniteLight>> env_lights;
+        auto make_infinite = [&](const Light& lt, const Xform& to_world) -> const InfiniteLight* {
+            if (lt.env_image < 0 || (size_t)lt.env_image >= rs.env_images.size()) throw std::runtime_error("infinite light names no map");
+            const EnvImage& e = rs.env_images[(size_t)lt.env_image];
+            auto il = std::make_unique<InfiniteLight>();
+            il->init(e.rgb8.data(), e.w, e.h, to_world, xf_inverse(to_world), wb);
+            env_lights.push_back(std::move(il));
+            return env_lights.back().get();
+        };
         for (size_t i = 0; i < rs.light_specs.size(); ++i) {
             Light lt = rs.light_specs[i];
             if (lt.kind == LIGHT_POINT) {
@@ -655,11 +773,18 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
                 }
                 lg.geos.push_back(g);
                 lt.probe_geo = (int)lg.geos.size() - 1;
+            } else if (lt.kind == LIGHT_INFINITE) {
+                lt.inf = make_infinite(lt, rs.light_xf[i]);
             } else {
                 lt.w_light = normalize_vec(xf_vector(rs.light_xf[i], lt.w_light));  // distant.rs:30
                 b3_bounding_sphere(wb, &lt.world_center, &lt.world_radius);
             }
             job.scene.lights.push_back(lt);
+        }
+        for (size_t i = 0; i < rs.inf_specs.size(); ++i) {  // Scene::infinite_lights: only Light::le is ever asked of them
+            Light lt = rs.inf_specs[i];
+            if (lt.kind == LIGHT_INFINITE) lt.inf = make_infinite(lt, rs.inf_xf[i]);
+            job.scene.infinite_lights.push_back(lt);
         }
         Filter f;
         f.kind = (uint32_t)prm[3];
@@ -703,6 +828,7 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
                 raw[4 * i + 2] = job.film.pixels[i].xyz[2];
                 raw[4 * i + 3] = job.film.pixels[i].filter_weight_sum;
             }
+        job.stats.asserts += mip_panics().exchange(0);
         if (stats16) {
             const RenderStats& st = job.stats;
             uint64_t v[16] = {st.camera_rays, st.extension_rays, st.shadow_rays, st.bounces, st.zero_weight, st.asserts,

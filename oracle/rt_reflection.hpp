@@ -469,6 +469,11 @@ struct Bsdf {
     }
 };
 
+}  // namespace orc
+#include "rt_mipmap.hpp"  // needs Rgb
+namespace orc {
+
+
 // ---- materials (material/*.rs) with constant-valued parameters -------------------------------------
 enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4, MAT_NONE = 5 };
 // ---- textures (texture/{bilerp,mix,scale,checkerboard,uv}.rs, texture/mod.rs mappings) --------------------------
@@ -480,7 +485,8 @@ enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MA
 // UV, planar, spherical and cylindrical 2D mappings with their screen-space differentials, IdentityMapping3D.
 enum TexKind : uint32_t {
     TEX_CONST = 0, TEX_BILERP = 1, TEX_SCALE = 2, TEX_MIX = 3, TEX_CHECKER2D = 4, TEX_CHECKER3D = 5, TEX_UV = 6,
-    TEX_WINDY = 7, TEX_WRINKLED = 8  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D in w2t
+    TEX_WINDY = 7, TEX_WRINKLED = 8,  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D in w2t
+    TEX_IMAGE = 9                     // imagemap.rs: MIPMap::lookup_d of the mapped point (t1 = image index)
 };
 enum TexMapping : uint32_t { MAP_UV = 0, MAP_PLANAR = 1, MAP_SPHERICAL = 2, MAP_CYLINDRICAL = 3 };
 struct Texture {
@@ -490,6 +496,7 @@ struct Texture {
     Rgb v[4];
     double map[8] = {1, 1, 0, 0, 0, 0, 0, 0};  // uv: su sv du dv; planar: vs[3] vt[3] ds dt
     Xform w2t;                                  // checkerboard 3D: IdentityMapping3D's transform; spherical / cylindrical
+    const MipMap* image = nullptr;              // TEX_IMAGE
 };
 constexpr int kMaxTextures = 32;
 
@@ -717,6 +724,11 @@ inline void tex_eval_all(const std::vector<Texture>& table, const TexPoint& q, R
                 vals[i] = Rgb(turbulence(w, dx, dy, t.map[1], rust_as_u64(t.map[0])));
                 break;
             }
+            case TEX_IMAGE: {  // imagemap.rs:74-81
+                P2 st = tex_map2d(t, q, &dstdx, &dstdy);
+                vals[i] = t.image->lookup_d(st, dstdx, dstdy);
+                break;
+            }
             case TEX_UV: {  // uv.rs:20-27 (Spectrum<3>::from_rgb copies, spectrum.rs:2740-2742)
                 P2 st = tex_map2d(t, q, &dstdx, &dstdy);
                 vals[i] = Rgb(st.x - std::floor(st.x), st.y - std::floor(st.y), 0.0);
@@ -932,7 +944,7 @@ inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_l
 }
 
 // ---- lights (lights/{point,distant,diffuse}.rs) -----------------------------------------------------
-enum LightKind : uint32_t { LIGHT_POINT = 0, LIGHT_DISTANT = 1, LIGHT_DIFFUSE_AREA = 2 };
+enum LightKind : uint32_t { LIGHT_POINT = 0, LIGHT_DISTANT = 1, LIGHT_DIFFUSE_AREA = 2, LIGHT_INFINITE = 3 };
 struct Light {
     uint32_t kind = LIGHT_POINT;
     Rgb intensity;        // point: I ; distant: L (already l * scale) ; diffuse area: lemit
@@ -948,6 +960,8 @@ struct Light {
     V3 tp[3], tn[3];
     bool tri_has_n = false;
     int probe_geo = -1;       // index of the shape in RenderScene::light_shapes (Shape::pdf_ref's intersect)
+    const InfiniteLight* inf = nullptr;  // LIGHT_INFINITE (lights/infinite.rs)
+    int env_image = -1;
     double area() const {
         if (shape_kind == 0) return sphere.phi_max * sphere.radius * (sphere.z_max - sphere.z_min);  // sphere.rs:261-263
         return 0.5 * length(cross(tp[1] - tp[0], tp[2] - tp[0]));                                     // triangle.rs:419-424

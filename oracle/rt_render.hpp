@@ -45,6 +45,7 @@ struct RenderScene {
     std::vector<Material> materials;
     std::vector<Texture> textures;  // the scene file's float and rgb textures, definition order
     std::vector<Light> lights;
+    std::vector<Light> infinite_lights;  // Scene::infinite_lights: read by PathIntegrator for escaped rays only (path.rs:84)
     Geometry light_shapes;  // the area lights' shapes, for Shape::pdf_ref (they are not in the aggregate)
     bool fix_q9 = false;
 
@@ -154,11 +155,13 @@ struct RenderScene {
     // estimate_direct (integrator/mod.rs:403-558), specular = false, no media
     Rgb estimate_direct(const SI& si, const Bsdf& bsdf, const Light& light, P2 u_light, P2 u_scattering, RenderStats* st) const {
         const uint8_t flags = BXDF_ALL & ~BXDF_SPECULAR;
-        const bool delta = light.kind != LIGHT_DIFFUSE_AREA;
+        const bool delta = light.kind != LIGHT_DIFFUSE_AREA && light.kind != LIGHT_INFINITE;
         Rgb ld;
         V3 wi, p1;
         double light_pdf = 0.0, scattering_pdf = 0.0;
-        Rgb li = delta ? sample_li(light, si.p, &wi, &light_pdf, &p1) : area_sample_li(light, si.p, u_light, &wi, &light_pdf, &p1);
+        Rgb li = delta ? sample_li(light, si.p, &wi, &light_pdf, &p1)
+                       : (light.kind == LIGHT_INFINITE ? light.inf->sample_li(si.p, u_light, &wi, &light_pdf, &p1)
+                                                       : area_sample_li(light, si.p, u_light, &wi, &light_pdf, &p1));
         if (light_pdf > 0.0 && !li.is_black()) {
             Rgb f;
             if (bsdf.present) {
@@ -177,26 +180,29 @@ struct RenderScene {
                 }
             }
         }
-        // Sample BSDF with multiple importance sampling (:484-556).  For an area light the ray found this way can
-        // only add radiance through `light_isect.primitive.get_arealight()`, which is None for every primitive the
-        // loader creates (Q22), or through Light::le, which is zero for everything but an infinite light: the whole
-        // half is traced and then contributes nothing.  Restated (and counted) for completeness.
+        // Sample BSDF with multiple importance sampling (:484-556).  For a DiffuseAreaLight the ray found this way can
+        // only add radiance through `light_isect.primitive.get_arealight()`, None for every primitive the loader creates
+        // (Q22): traced, counted, contributes nothing.  For an InfiniteAreaLight an ESCAPED ray picks up Light::le.
         if (!delta && bsdf.present) {
             uint8_t sampled = 0;
             Rgb f = bsdf.sample_f(si.wo, &wi, u_scattering, &scattering_pdf, flags, &sampled);
             f = f * absdot(wi, si.sh.n);
             bool sampled_specular = (sampled & BXDF_SPECULAR) != 0;
             if (!f.is_black() && scattering_pdf > 0.0) {
+                double weight = 1.0;
                 if (!sampled_specular) {
-                    light_pdf = area_pdf_li(light, si.p, wi);
+                    light_pdf = light.kind == LIGHT_INFINITE ? light.inf->pdf_li(wi) : area_pdf_li(light, si.p, wi);
                     if (light_pdf == 0.0) return ld;
+                    weight = power_heuristic(1, scattering_pdf, 1, light_pdf);
                 }
                 Ray ray = ray_new_od(si.p, wi);
                 SI light_isect;
                 HitRecord h;
                 if (st) st->mis_probe_rays += 1;
-                bvh->intersect(ray, &h, &light_isect, nullptr);
-                // found: get_arealight() is None -> li = 0; not found: Light::le = 0 (lights/mod.rs:37-39)
+                const bool found_surface = bvh->intersect(ray, &h, &light_isect, nullptr);
+                Rgb li2;  // found: get_arealight() is None -> zero; escaped: Light::le (zero but for an infinite light)
+                if (!found_surface && light.kind == LIGHT_INFINITE) li2 = light.inf->le(ray.d);
+                if (!li2.is_black()) ld += li2 * f * weight / scattering_pdf;
             }
         }
         return ld;
@@ -255,7 +261,10 @@ struct Integrator {
             if (st) st->extension_rays += 1;
             bool found = sc.intersect_with_record(ray, &isect, &rec, st);
             if (bounces == 0 && first_hit) *first_hit = rec;
-            (void)specular_bounce;  // isect.le() == 0 (Q22) and there are no infinite lights in scope
+            // path.rs:79-88: isect.le() == 0 (Q22); an escaped camera ray or specular bounce sees the infinite lights
+            if ((bounces == 0 || specular_bounce) && !found)
+                for (const Light& il : sc.infinite_lights)
+                    if (il.kind == LIGHT_INFINITE) l += beta * il.inf->le(ray.d);
             if (!found || bounces >= max_depth) break;
             Bsdf bsdf;
             material_bump(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, &isect, bounces == 0 ? &camera : nullptr);
@@ -307,7 +316,13 @@ struct Integrator {
         if (st) st->extension_rays += 1;
         bool found = sc.intersect_with_record(ray, &isect, &rec, st);
         if (first_hit) *first_hit = rec;
-        if (!found) return l;  // Light::le of point / distant lights is zero
+        if (!found) {
+            // directlighting.rs:83-88: `for light in &scene.lights { l += light.le(ray); return l; }` — the FIRST light's
+            // Le only (the return sits inside the loop); zero unless that light is an infinite one.  (With no lights at
+            // all the reference goes on with a default interaction and recurses without end; here: black.)
+            if (!sc.lights.empty() && sc.lights[0].kind == LIGHT_INFINITE) l += sc.lights[0].inf->le(ray.d);
+            return l;
+        }
         Bsdf bsdf;
         material_bump(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, &isect, camera);
         material_bsdf(material_at(sc.materials[sc.geom->geos[isect.geo].material], sc.textures, isect, camera), isect, false, &bsdf);

@@ -90,7 +90,7 @@ def _build(verbose, defines):
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
     tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *[str(o) for o, _, _ in results], "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *[str(o) for o, _, _ in results], "-lcudart", "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

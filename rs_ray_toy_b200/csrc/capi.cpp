@@ -99,6 +99,7 @@ struct rrt_scene {
     std::vector<rrt_light> lights;
     std::vector<rrt_texture> textures;
     std::vector<int32_t> material_slots;  // RRT_MATERIAL_SLOTS per material, or empty
+    rrt::SceneExtras extras;              // images, Scene::infinite_lights
     std::unique_ptr<rrt::RayTracer> agg;  // DeviceAggregate (Tier F) or LiteralAggregate (Tier L)
     bool committed = false;
     uint32_t build_flags = 0;
@@ -498,6 +499,44 @@ int rrt_scene_set_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights) 
     return RRT_OK;
 }
 
+int rrt_scene_set_infinite_lights(rrt_scene* scene, uint32_t n, const rrt_light* lights) {
+    if (!scene || (n && !lights)) return fail(RRT_ERR_INVALID, "rrt_scene_set_infinite_lights: null argument");
+    try {
+        scene->extras.infinite_lights.assign(lights, lights + n);
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_scene_add_image(rrt_scene* scene, uint32_t width, uint32_t height, const uint8_t* rgb8, uint32_t* index) {
+    if (!scene || !rgb8 || !index) return fail(RRT_ERR_INVALID, "rrt_scene_add_image: null argument");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(RRT_ERR_INVALID, "rrt_scene_add_image: size out of range");
+    try {
+        rrt::Image8 img;
+        img.width = width;
+        img.height = height;
+        img.rgb.assign(rgb8, rgb8 + (size_t)width * height * 3);
+        scene->extras.images.push_back(std::move(img));
+        *index = (uint32_t)scene->extras.images.size() - 1;
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+int rrt_scene_add_image_png(rrt_scene* scene, const char* path, uint32_t* index) {
+    if (!scene || !path || !index) return fail(RRT_ERR_INVALID, "rrt_scene_add_image_png: null argument");
+    try {
+        rrt::Image8 img;
+        std::string err;
+        if (!rrt::read_png_rgb8(path, &img, &err)) return fail(RRT_ERR_IO, err);
+        scene->extras.images.push_back(std::move(img));
+        *index = (uint32_t)scene->extras.images.size() - 1;
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
 int rrt_scene_set_textures(rrt_scene* scene, uint32_t n, const rrt_texture* textures) {
     if (!scene || (n && !textures)) return fail(RRT_ERR_INVALID, "rrt_scene_set_textures: null argument");
     if (n > RRT_MAX_TEXTURES) return fail(RRT_ERR_UNSUPPORTED, "rrt_scene_set_textures: more than RRT_MAX_TEXTURES textures");
@@ -569,7 +608,7 @@ int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render*
         r->scene = scene;
         std::string err;
         rc = r->renderer.create(scene->ctx->device, scene->host, scene->agg.get(), scene->materials, scene->lights,
-                                scene->textures, scene->material_slots, wb, *desc, &err);
+                                scene->textures, scene->material_slots, wb, *desc, &err, &scene->extras);
         if (rc != RRT_OK) return fail(rc, err);
         scene->ctx->launches.fetch_add(r->renderer.stats().launches, std::memory_order_relaxed);
         *out = r.release();
@@ -604,6 +643,44 @@ int rrt_scene_load_json_tier(rrt_ctx* ctx, const char* path, const char* overrid
     s->lights = loaded.lights;
     s->textures = loaded.textures;
     s->material_slots = loaded.material_slots;
+    s->extras.infinite_lights = loaded.infinite_lights;
+    {
+        // decode the images.  A texture no material reaches is never evaluated: when its file is missing (the sample
+        // scene declares such an ImageTexture) it becomes a black constant instead of an error.
+        std::vector<char> image_used(loaded.image_paths.size(), 0);
+        for (const rrt_light& l : s->lights)
+            if (l.kind == RRT_LIGHT_INFINITE) image_used[l.env_image] = 1;
+        for (const rrt_light& l : s->extras.infinite_lights)
+            if (l.kind == RRT_LIGHT_INFINITE) image_used[l.env_image] = 1;
+        std::vector<char> reached(s->textures.size(), 0);
+        for (int32_t t : s->material_slots)
+            if (t >= 0) reached[(size_t)t] = 1;
+        for (size_t i = s->textures.size(); i-- > 0;) {
+            if (!reached[i]) continue;
+            const rrt_texture& x = s->textures[i];
+            const bool pair = x.kind == RRT_TEX_SCALE || x.kind == RRT_TEX_MIX || x.kind == RRT_TEX_CHECKER2D || x.kind == RRT_TEX_CHECKER3D;
+            if (pair) reached[(size_t)x.t1] = reached[(size_t)x.t2] = 1;
+            if (x.kind == RRT_TEX_MIX) reached[(size_t)x.amount] = 1;
+            if (x.kind == RRT_TEX_IMAGE) image_used[(size_t)x.t1] = 1;
+        }
+        for (size_t i = 0; i < loaded.image_paths.size(); ++i) {
+            rrt::Image8 img;
+            std::string ierr;
+            if (!rrt::read_png_rgb8(loaded.image_paths[i], &img, &ierr)) {
+                if (image_used[i]) {
+                    rrt_scene_destroy(s);
+                    return fail(RRT_ERR_IO, ierr);
+                }
+                for (rrt_texture& x : s->textures)
+                    if (x.kind == RRT_TEX_IMAGE && (size_t)x.t1 == i) {
+                        x.kind = RRT_TEX_CONSTANT;
+                        x.t1 = -1;
+                        x.v[0][0] = x.v[0][1] = x.v[0][2] = 0.0;
+                    }
+            }
+            s->extras.images.push_back(std::move(img));
+        }
+    }
     rc = rrt_scene_commit(s, loaded.max_prims_in_node, build_flags);
     if (rc != RRT_OK) {
         rrt_scene_destroy(s);
@@ -790,6 +867,80 @@ int rrt_stratified_host_probe(uint64_t seed, int64_t xres, int64_t px, int64_t p
         uint32_t state = 0;
         for (uint32_t d = 0; d < ndims; ++d) rrt::strat_get_1d(sp, px, py, k, &state);
         for (int j = 0; j < 4; ++j) overflow4[4 * k + j] = rrt::strat_get_1d(sp, px, py, k, &state);
+    }
+    return RRT_OK;
+}
+
+int rrt_png_host_probe(const char* path, uint32_t* width, uint32_t* height, uint8_t* rgb8, uint64_t capacity) {
+    if (!path || !width || !height) return fail(RRT_ERR_INVALID, "rrt_png_host_probe: null argument");
+    rrt::Image8 img;
+    std::string err;
+    if (!rrt::read_png_rgb8(path, &img, &err)) return fail(RRT_ERR_IO, err);
+    *width = img.width;
+    *height = img.height;
+    if (rgb8 && capacity >= img.rgb.size()) std::memcpy(rgb8, img.rgb.data(), img.rgb.size());
+    return RRT_OK;
+}
+
+int rrt_mipmap_host_probe(uint32_t width, uint32_t height, const uint8_t* rgb8, int trilinear, double max_aniso, uint32_t wrap,
+                          uint64_t n, const double* q6, double* out6, uint64_t info[32]) {
+    if (!rgb8 || (n && (!q6 || !out6)) || !info) return fail(RRT_ERR_INVALID, "rrt_mipmap_host_probe: null argument");
+    rrt::Image8 img;
+    img.width = width;
+    img.height = height;
+    img.rgb.assign(rgb8, rgb8 + (size_t)width * height * 3);
+    rrt::HostMipMap m;
+    std::string err;
+    if (!rrt::make_mipmap(img, trilinear != 0, max_aniso, wrap, &m, &err)) return fail(RRT_ERR_UNSUPPORTED, err);
+    const std::vector<double> lut = rrt::mip_weight_lut();
+    const rrt::MipView v = m.host_view(lut.data());
+    info[0] = v.n_levels;
+    for (uint32_t l = 0; l < v.n_levels && l < 15; ++l) {
+        info[1 + 2 * l] = v.level[l].u_res;
+        info[2 + 2 * l] = v.level[l].v_res;
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        const double* a = q6 + 6 * i;
+        const rrt::Rgb d = rrt::mip_lookup_d(v, rrt::P2{a[0], a[1]}, rrt::P2{a[2], a[3]}, rrt::P2{a[4], a[5]});
+        const rrt::Rgb w = rrt::mip_lookup_w(v, rrt::P2{a[0], a[1]}, a[2]);
+        out6[6 * i] = d.r; out6[6 * i + 1] = d.g; out6[6 * i + 2] = d.b;
+        out6[6 * i + 3] = w.r; out6[6 * i + 4] = w.g; out6[6 * i + 5] = w.b;
+    }
+    return RRT_OK;
+}
+
+int rrt_envlight_host_probe(uint32_t width, uint32_t height, const uint8_t* rgb8, const double to_world16[16],
+                            const double to_local16[16], double world_radius, uint64_t n, const double* in8, double* out12) {
+    if (!rgb8 || !to_world16 || !to_local16 || (n && (!in8 || !out12))) return fail(RRT_ERR_INVALID, "rrt_envlight_host_probe: null argument");
+    rrt::Image8 img;
+    img.width = width;
+    img.height = height;
+    img.rgb.assign(rgb8, rgb8 + (size_t)width * height * 3);
+    rrt::HostMipMap m;
+    std::string err;
+    if (!rrt::make_mipmap(img, false, 8.0, rrt::MIPWRAP_REPEAT, &m, &err)) return fail(RRT_ERR_UNSUPPORTED, err);
+    const std::vector<double> lut = rrt::mip_weight_lut();
+    rrt::EnvLightView e{};
+    e.lmap = m.host_view(lut.data());
+    rrt::HostDist2D dist;
+    rrt::make_env_distribution(e.lmap, &dist);
+    e.dist = dist.host_view();
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) {
+            e.to_world.m[4 * r + c] = to_world16[4 * r + c];
+            e.to_local.m[4 * r + c] = to_local16[4 * r + c];
+        }
+    e.world_radius = world_radius;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double* a = in8 + 8 * i;  // ref point, u (2), direction w (3)
+        double* o = out12 + 12 * i;
+        rrt::V3 wi = rrt::v3(0, 0, 0), p1 = rrt::v3(0, 0, 0);
+        double pdf = 0.0;
+        const rrt::Rgb li = rrt::env_sample_li(e, rrt::v3(a[0], a[1], a[2]), rrt::P2{a[3], a[4]}, &wi, &pdf, &p1);
+        const rrt::V3 w = rrt::v3(a[5], a[6], a[7]);
+        const rrt::Rgb le = rrt::env_le(e, w);
+        o[0] = li.r; o[1] = li.g; o[2] = li.b; o[3] = wi.x; o[4] = wi.y; o[5] = wi.z; o[6] = pdf;
+        o[7] = rrt::env_pdf_li(e, w); o[8] = le.r; o[9] = le.g; o[10] = le.b; o[11] = p1.x;
     }
     return RRT_OK;
 }

@@ -749,7 +749,10 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
 #endif
 // TEXTURED = some material parameter is driven by a texture: the kernel for constant-valued scenes carries none of it.
 // ALL_LIGHTS = DirectLighting with LightStrategy::UniformSampleAll: one light sample per light and hit (Q30).
-template <bool TEXTURED, bool ALL_LIGHTS>
+// ENV = the scene has an InfiniteAreaLight: escaped rays read it (path.rs:79-88) and, when it is among `lights`, its
+// next-event estimate has a live BSDF-sampling half (integrator/mod.rs:484-556) — a second shadow-queue entry per hit,
+// whose ray only has to ESCAPE: a hit can add nothing (get_arealight() is None for every primitive, Q22).
+template <bool TEXTURED, bool ALL_LIGHTS, bool ENV = false>
 __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
                                                      IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
     uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -775,6 +778,15 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
         if (p.bounces == 0) {
             P->first_prim = found ? (int32_t)h.prim_id : -1;
             P->first_t = found ? h.t : 0.0;
+        }
+        bool specular_bounce = false;
+        if (ENV) {
+            specular_bounce = P->pad != 0u;
+            if (!found && (p.bounces == 0 || specular_bounce)) {  // path.rs:79-88: `for light in &scene.infinite_lights`
+                Rgb le = rgb(0.0);
+                for (uint32_t k = 0; k < sc.n_escape_envs; ++k) le = le + p.beta * env_le(sc.envs[sc.escape_envs[k]], p.d);
+                P->L = P->L + le;
+            }
         }
 #ifdef RRT_DEBUG_PIXEL_X  // diagnostic build only (tools/debug_render_rays.py --gpu-log): every extension ray of one pixel
         if (P->px == RRT_DEBUG_PIXEL_X && P->py == RRT_DEBUG_PIXEL_Y)
@@ -842,8 +854,12 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                     V3 wi = v3(0, 0, 0), p1 = v3(0, 0, 0);
                     Rgb li;
                     double light_pdf = 1.0;
-                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA;
-                    if (area) {  // diffuse.rs:62-79; u_light is dimensions dim, dim + 1 of this sample
+                    const bool env = ENV && lt.kind == RRT_LIGHT_INFINITE;
+                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA || env;  // not a delta light: MIS weights
+                    if (env) {  // infinite.rs:129-179
+                        const P2 u_light = {halton_sample(ht, perms, p.hidx, p.dim), halton_sample(ht, perms, p.hidx, p.dim + 1)};
+                        li = env_sample_li(sc.envs[lt.env], s.p, u_light, &wi, &light_pdf, &p1);
+                    } else if (area) {  // diffuse.rs:62-79; u_light is dimensions dim, dim + 1 of this sample
                         const P2 u_light = {halton_sample(ht, perms, p.hidx, p.dim), halton_sample(ht, perms, p.hidx, p.dim + 1)};
                         li = area_sample_li(lt, s.p, u_light, &wi, &light_pdf, &p1);
                     } else if (lt.kind == RRT_LIGHT_POINT) {  // point.rs:55-77
@@ -855,15 +871,16 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                         p1 = s.p + lt.w_light * (2.0 * lt.world_radius);
                         li = lt.intensity;
                     }
+                    const uint32_t dim_scattering = p.dim + 2;
                     p.dim += 4;  // u_light, u_scattering: always drawn (integrator/mod.rs:385-386)
                     if (light_pdf > 0.0 && !is_black(li)) {
                         const Rgb f = bsdf_f(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR) * absdot(wi, s.shn);
                         if (!is_black(f)) {
                             // delta light: ld = f * li / light_pdf(=1); area light: li * f * w / light_pdf with
                             // w = power_heuristic(light_pdf, bsdf pdf).  Then / the light-choice pdf, then * beta.
-                            // estimate_direct's second, BSDF-sampling half (:484-556) is not run: the ray it traces
-                            // can only add radiance through get_arealight(), None for every primitive (Q22), or
-                            // through Light::le, zero for these lights — the oracle traces and counts those rays.
+                            // For a DiffuseAreaLight estimate_direct's second, BSDF-sampling half (:484-556) is not run: the
+                            // ray it traces can only add radiance through get_arealight(), None for every primitive (Q22)
+                            // — the oracle traces and counts those rays.
                             Rgb ld;
                             if (area) {
                                 const double weight = power_heuristic(1, light_pdf, 1, bsdf_pdf(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR));
@@ -878,7 +895,7 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                             // of the light.  Tier L: Ray::new normalises d and keeps t_max = 1 - eps
                             // (interaction.rs:66-77), so only boxes within one unit are ever entered.
                             sd = sc.literal ? normalize(p1 - s.p) : p1 - s.p;
-                            if (ALL_LIGHTS) {
+                            if (ALL_LIGHTS || ENV) {
                                 // several shadow rays per hit: each takes its own slot (resolve_kernel adds them
                                 // to the path with atomics in this mode)
                                 const uint32_t slot_sh = atomicAdd(q.counters + 2, 1u);
@@ -887,6 +904,35 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                                 q.sh_contrib[slot_sh] = contrib;
                             } else {
                                 emit_sh = true;
+                            }
+                        }
+                    }
+                    if (env) {
+                        // ---- the BSDF-sampling half for the infinite light (integrator/mod.rs:484-556) ----
+                        V3 wi2 = v3(0, 0, 0);
+                        double sc_pdf = 0.0;
+                        uint32_t sampled = 0;
+                        const P2 u_sc = {halton_sample(ht, perms, p.hidx, dim_scattering), halton_sample(ht, perms, p.hidx, dim_scattering + 1)};
+                        const Rgb f2 = bsdf_sample_f(bsdf, s.wo, &wi2, u_sc, &sc_pdf, BXDF_ALL & ~BXDF_SPECULAR, &sampled) * absdot(wi2, s.shn);
+                        if (!is_black(f2) && sc_pdf > 0.0) {
+                            double weight = 1.0;
+                            bool live = true;
+                            if (!(sampled & BXDF_SPECULAR)) {
+                                const double lp = env_pdf_li(sc.envs[lt.env], wi2);
+                                live = lp != 0.0;  // `return ld`
+                                weight = power_heuristic(1, sc_pdf, 1, lp);
+                            }
+                            if (live) {
+                                const V3 rd = normalize(wi2);  // spawn_ray: Ray::new_od normalises
+                                const Rgb li2 = env_le(sc.envs[lt.env], rd);
+                                if (!is_black(li2)) {
+                                    Rgb ld2 = li2 * f2 * weight / sc_pdf;
+                                    if (!ALL_LIGHTS) ld2 = ld2 / ip.light_pdf;
+                                    const uint32_t slot_sh = atomicAdd(q.counters + 2, 1u);
+                                    write_ray(q.sh_rays + slot_sh, s.p, rd, kInfD);  // counts only if nothing is hit
+                                    q.sh_path[slot_sh] = pid;
+                                    q.sh_contrib[slot_sh] = ip.kind == RRT_INTEGRATOR_PATH ? p.beta * ld2 : ld2;
+                                }
                             }
                         }
                     }
@@ -932,6 +978,7 @@ __global__ void __launch_bounds__(128, RRT_SHADE_MINBLOCKS) shade_kernel(ShadeSc
                                 emit_ext = true;
                                 eo = p.o;
                                 ed = p.d;
+                                if (ENV) P->pad = (flags & BXDF_SPECULAR) ? 1u : 0u;  // specular_bounce (path.rs:148)
                             }
                         }
                     }
@@ -1066,6 +1113,10 @@ __global__ void __launch_bounds__(128, 2) whitted_kernel(ShadeScene sc, HaltonTa
             P->state = 3;
         }
         bool cont = false;
+        if (!found && ip.kind == RRT_INTEGRATOR_DIRECT && ip.n_lights > 0 && sc.lights[0].kind == RRT_LIGHT_INFINITE) {
+            // directlighting.rs:83-88: `for light in &scene.lights { l += light.le(ray); return l; }` — the first light only
+            P->L = P->L + weight * env_le(sc.envs[sc.lights[0].env], rd);
+        }
         if (found) {
             Surface s;
             BumpPartials bp;
@@ -1111,8 +1162,12 @@ __global__ void __launch_bounds__(128, 2) whitted_kernel(ShadeScene sc, HaltonTa
                     V3 wi = v3(0, 0, 0), p1 = v3(0, 0, 0);
                     Rgb li;
                     double light_pdf = 1.0;
-                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA;
-                    if (area) {
+                    const bool env = lt.kind == RRT_LIGHT_INFINITE;
+                    const bool area = lt.kind == RRT_LIGHT_DIFFUSE_AREA || env;
+                    if (env) {
+                        const P2 u_light = wh_2d(ht, perms, ip, smp);
+                        li = env_sample_li(sc.envs[lt.env], s.p, u_light, &wi, &light_pdf, &p1);
+                    } else if (area) {
                         const P2 u_light = wh_2d(ht, perms, ip, smp);
                         li = area_sample_li(lt, s.p, u_light, &wi, &light_pdf, &p1);
                     } else {
@@ -1127,7 +1182,38 @@ __global__ void __launch_bounds__(128, 2) whitted_kernel(ShadeScene sc, HaltonTa
                             li = lt.intensity;
                         }
                     }
-                    wh_skip_2d(ip, smp);  // u_scattering: read only by estimate_direct's BSDF-sampling half (dead, Q22)
+                    // u_scattering: read only by estimate_direct's BSDF-sampling half — dead for a DiffuseAreaLight (Q22),
+                    // live for an InfiniteAreaLight (below)
+                    P2 u_sc = {0.0, 0.0};
+                    if (env) u_sc = wh_2d(ht, perms, ip, smp);
+                    else wh_skip_2d(ip, smp);
+                    if (env && bsdf.present) {
+                        V3 wi2 = v3(0, 0, 0);
+                        double sc_pdf = 0.0;
+                        uint32_t sampled = 0;
+                        const Rgb f2 = bsdf_sample_f(bsdf, s.wo, &wi2, u_sc, &sc_pdf, BXDF_ALL & ~BXDF_SPECULAR, &sampled) * absdot(wi2, s.shn);
+                        if (!is_black(f2) && sc_pdf > 0.0) {
+                            double wgt = 1.0;
+                            bool live = true;
+                            if (!(sampled & BXDF_SPECULAR)) {
+                                const double lp = env_pdf_li(sc.envs[lt.env], wi2);
+                                live = lp != 0.0;
+                                wgt = power_heuristic(1, sc_pdf, 1, lp);
+                            }
+                            if (live) {
+                                const V3 pd = normalize(wi2);
+                                const Rgb li2 = env_le(sc.envs[lt.env], pd);
+                                if (!is_black(li2)) {
+                                    Rgb ld2 = li2 * f2 * wgt / sc_pdf;
+                                    if (!all) ld2 = ld2 / choice_pdf;
+                                    const uint32_t slot_sh = atomicAdd(q.counters + 2, 1u);
+                                    write_ray(q.sh_rays + slot_sh, s.p, pd, kInfD);  // counts only if the ray escapes
+                                    q.sh_path[slot_sh] = pid;
+                                    q.sh_contrib[slot_sh] = weight * ld2;
+                                }
+                            }
+                        }
+                    }
                     if (bsdf.present && light_pdf > 0.0 && !is_black(li)) {
                         const Rgb f = bsdf_f(bsdf, s.wo, wi, BXDF_ALL & ~BXDF_SPECULAR) * absdot(wi, s.shn);
                         if (!is_black(f)) {
@@ -1385,6 +1471,8 @@ struct Renderer::Impl {
     bool textured = false, want_diffs = false;
     bool all_lights = false;        // DirectLighting, UniformSampleAll
     uint32_t shadow_per_hit = 1;
+    bool env_in_lights = false;     // an InfiniteAreaLight is sampled for direct light: two shadow-queue entries per hit
+    bool env_mode = false;          // ... or seen by escaped rays: shade_kernel<.., SHADE_ENV>
     bool whitted = false;           // DirectLighting with specular recursion / Debug / StratifiedSampler: whitted_kernel
     uint32_t whitted_rounds = 1;    // upper bound of rays per camera sample
     WhittedBranch* d_stacks = nullptr;
@@ -1470,7 +1558,8 @@ bool validate_textures(const rrt_texture* t, uint32_t n, std::string* err) {
     if (n > (uint32_t)kMaxTextures) return bad(n, "more than RRT_MAX_TEXTURES textures");
     for (uint32_t i = 0; i < n; ++i) {
         const rrt_texture& x = t[i];
-        if (x.kind > RRT_TEX_WRINKLED) return bad(i, "kind outside the hot-path scope");
+        if (x.kind > RRT_TEX_IMAGE) return bad(i, "kind outside the hot-path scope");
+        if (x.kind == RRT_TEX_IMAGE && (x.t1 < 0 || x.v[0][1] < 0.0 || x.v[0][1] > 2.0)) return bad(i, "image texture: t1 = image index, v[0][1] = wrap mode");
         if (x.kind == RRT_TEX_WRINKLED && !(x.map[0] >= 0.0 && x.map[0] <= 64.0)) return bad(i, "octaves must be in 0..64");
         if (x.mapping > RRT_TEXMAP_CYLINDRICAL) return bad(i, "mapping outside the hot-path scope");
         const bool pair = x.kind == RRT_TEX_SCALE || x.kind == RRT_TEX_MIX || x.kind == RRT_TEX_CHECKER2D || x.kind == RRT_TEX_CHECKER3D;
@@ -1517,7 +1606,8 @@ void differentials_host_eval(const double in24[24], double out10[10]) {
 
 int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
                      const std::vector<rrt_light>& lights, const std::vector<rrt_texture>& textures,
-                     const std::vector<int32_t>& material_slots, const double wb[6], const rrt_render_desc& d, std::string* err) {
+                     const std::vector<int32_t>& material_slots, const double wb[6], const rrt_render_desc& d, std::string* err,
+                     const SceneExtras* extras) {
     auto t_start = std::chrono::steady_clock::now();
     if (d.xres <= 0 || d.yres <= 0 || d.xres > 32768 || d.yres > 32768) {
         if (err) *err = "Film resolution out of range";
@@ -1618,8 +1708,18 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         }
     }
     // the integrators that recurse through specular lobes run the depth-first wavefront (whitted_kernel)
+    bool env_light = false;
+    for (const rrt_light& l : lights) env_light |= l.kind == RRT_LIGHT_INFINITE;
+    if (extras)
+        for (const rrt_light& l : extras->infinite_lights) env_light |= l.kind == RRT_LIGHT_INFINITE;
+    if (env_light && agg->literal()) {
+        // the BSDF-sampled ray of estimate_direct goes through Scene::intersect; in the literal tier the shadow queue runs
+        // intersect_p, which tests other triangles (Q4)
+        if (err) *err = "InfiniteAreaLight is available in the fast tier only";
+        return RRT_ERR_UNSUPPORTED;
+    }
     const bool whitted = d.integrator_kind == RRT_INTEGRATOR_DEBUG || stratified ||
-                         (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.max_depth > 1 && specular_material);
+                         (d.integrator_kind == RRT_INTEGRATOR_DIRECT && ((d.max_depth > 1 && specular_material) || env_light));
     uint64_t whitted_hits = 1;  // hits one camera sample can shade
     if (whitted && specular_material && d.max_depth > 1) {
         if (splitting_material) {
@@ -1898,12 +1998,108 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
                     if (err) *err = "area light shape must be a sphere or a triangle (renderprocess.rs:1078-1095)";
                     return RRT_ERR_INVALID;
                 }
+            } else if (l.kind == RRT_LIGHT_INFINITE) {
+                r.env = -1;  // set below, once the maps are built
             } else if (l.kind != RRT_LIGHT_POINT) {
                 if (err) *err = "light kind outside the hot-path scope";
                 return RRT_ERR_UNSUPPORTED;
             }
             lts[i] = r;
         }
+        // ---- images: one MIPMap per ImageTexture (its wrap mode shapes the pyramid), one per InfiniteAreaLight ----
+        static const std::vector<Image8> no_images;
+        static const std::vector<rrt_light> no_lights;
+        const std::vector<Image8>& images = extras ? extras->images : no_images;
+        const std::vector<rrt_light>& inf_lights = extras ? extras->infinite_lights : no_lights;
+        const double* d_lut = nullptr;
+        auto upload_mip = [&](const HostMipMap& hm, MipView* out) -> int {
+            if (!d_lut) {
+                int rc2 = I.up(mip_weight_lut(), &d_lut, err);
+                if (rc2 != RRT_OK) return rc2;
+            }
+            *out = hm.host_view(d_lut);
+            for (size_t k = 0; k < hm.levels.size(); ++k) {
+                const double* dp = nullptr;
+                int rc2 = I.up(hm.levels[k], &dp, err);
+                if (rc2 != RRT_OK) return rc2;
+                out->level[k].data = dp;
+            }
+            return RRT_OK;
+        };
+        std::vector<MipView> mips;
+        for (size_t i = 0; i < texs.size(); ++i) {
+            if (texs[i].kind != TEXK_IMAGE) continue;
+            const rrt_texture& x = textures[i];
+            if ((size_t)x.t1 >= images.size()) {
+                if (err) *err = "image texture names an image that was not added (rrt_scene_add_image)";
+                return RRT_ERR_INVALID;
+            }
+            HostMipMap hm;
+            std::string merr;
+            const double aniso = x.v[0][0] > 0.0 ? x.v[0][0] : 8.0;
+            if (!make_mipmap(images[(size_t)x.t1], x.aa != 0, aniso, (uint32_t)x.v[0][1], &hm, &merr)) {
+                if (err) *err = "image texture: " + merr;
+                return RRT_ERR_UNSUPPORTED;
+            }
+            if (x.aa == 0 && hm.levels.size() < 2) {
+                // every EWA lookup interpolates levels lod and lod + 1: with one level the reference indexes past the
+                // end of its pyramid and panics (Q32)
+                if (err) *err = "image texture: an EWA-filtered image needs two MIPMap levels (at least 128 texels on its shorter side after the power-of-two resampling); the reference panics on smaller ones";
+                return RRT_ERR_UNSUPPORTED;
+            }
+            MipView v;
+            int rc2 = upload_mip(hm, &v);
+            if (rc2 != RRT_OK) return rc2;
+            texs[i].t1 = (int32_t)mips.size();
+            mips.push_back(v);
+        }
+        std::vector<EnvLightView> envs;
+        auto make_env = [&](const rrt_light& l, int32_t* index) -> int {
+            if ((size_t)l.env_image >= images.size()) {
+                if (err) *err = "infinite light names an image that was not added (rrt_scene_add_image)";
+                return RRT_ERR_INVALID;
+            }
+            HostMipMap hm;
+            std::string merr;
+            if (!make_mipmap(images[(size_t)l.env_image], false, 8.0, MIPWRAP_REPEAT, &hm, &merr)) {
+                if (err) *err = "infinite light: " + merr;
+                return RRT_ERR_UNSUPPORTED;
+            }
+            const std::vector<double> lut = mip_weight_lut();
+            HostDist2D dist;
+            make_env_distribution(hm.host_view(lut.data()), &dist);
+            EnvLightView e{};
+            int rc2 = upload_mip(hm, &e.lmap);
+            if (rc2 != RRT_OK) return rc2;
+            e.dist = dist.host_view();
+            if ((rc2 = I.up(dist.func, &e.dist.func, err)) != RRT_OK) return rc2;
+            if ((rc2 = I.up(dist.cdf, &e.dist.cdf, err)) != RRT_OK) return rc2;
+            if ((rc2 = I.up(dist.func_int, &e.dist.func_int, err)) != RRT_OK) return rc2;
+            if ((rc2 = I.up(dist.mcdf, &e.dist.mcdf, err)) != RRT_OK) return rc2;
+            Mat4 m, mi;
+            std::memcpy(m.m, l.to_world, sizeof(m.m));
+            std::memcpy(mi.m, l.shape_to_world_inv, sizeof(mi.m));
+            e.to_world = m34_of(m);
+            e.to_local = m34_of(mi);
+            e.world_radius = radius;
+            *index = (int32_t)envs.size();
+            envs.push_back(e);
+            return RRT_OK;
+        };
+        for (size_t i = 0; i < lights.size(); ++i)
+            if (lights[i].kind == RRT_LIGHT_INFINITE) {
+                int rc2 = make_env(lights[i], &lts[i].env);
+                if (rc2 != RRT_OK) return rc2;
+                I.env_in_lights = true;
+            }
+        std::vector<int32_t> escape;
+        for (const rrt_light& l : inf_lights)
+            if (l.kind == RRT_LIGHT_INFINITE) {  // every other kind's Light::le is zero
+                int32_t k = -1;
+                int rc2 = make_env(l, &k);
+                if (rc2 != RRT_OK) return rc2;
+                escape.push_back(k);
+            }
         ShadeScene& S = I.sc;
         int rc;
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
@@ -1918,9 +2114,14 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         S.n_textures = I.textured ? (uint32_t)texs.size() : 0u;
         for (size_t i = 0; i < texs.size(); ++i)
             I.want_diffs |= ((reached >> i) & 1u) && ((texs[i].kind == TEXK_CHECKER2D && texs[i].aa != 0) ||
-                                                      texs[i].kind == TEXK_WINDY || texs[i].kind == TEXK_WRINKLED);
+                                                      texs[i].kind == TEXK_WINDY || texs[i].kind == TEXK_WRINKLED || texs[i].kind == TEXK_IMAGE);
         if ((rc = I.up(lts, &S.lights, err)) != RRT_OK) return rc;
         S.n_lights = (uint32_t)lts.size();
+        if (!mips.empty() && (rc = I.up(mips, &S.mips, err)) != RRT_OK) return rc;
+        if (!envs.empty() && (rc = I.up(envs, &S.envs, err)) != RRT_OK) return rc;
+        if (!escape.empty() && (rc = I.up(escape, &S.escape_envs, err)) != RRT_OK) return rc;
+        S.n_escape_envs = (uint32_t)escape.size();
+        I.env_mode = I.env_in_lights || !escape.empty();
         S.literal = agg->literal() ? 1u : 0u;
     }
 
@@ -1939,8 +2140,10 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         I.chunk = (uint32_t)std::min<uint64_t>(kChunk, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
         // UniformSampleAll: up to n_lights shadow rays per hit — the chunk shrinks so that the shadow queue does not grow
         I.all_lights = (d.integrator_kind == RRT_INTEGRATOR_DEBUG || (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.light_strategy == 1)) && !lights.empty();
-        I.shadow_per_hit = I.all_lights ? (uint32_t)lights.size() : 1u;
-        if (I.all_lights) I.chunk = std::max<uint32_t>(1u << 16, (I.chunk / I.shadow_per_hit) & ~65535u);
+        uint32_t n_env = 0;  // an InfiniteAreaLight's estimate has two shadow-queue entries
+        for (const rrt_light& l : lights) n_env += l.kind == RRT_LIGHT_INFINITE ? 1u : 0u;
+        I.shadow_per_hit = I.all_lights ? (uint32_t)lights.size() + n_env : (n_env ? 2u : 1u);
+        if (I.shadow_per_hit > 1) I.chunk = std::max<uint32_t>(1u << 16, (I.chunk / I.shadow_per_hit) & ~65535u);
     }
     if (I.whitted) I.chunk = std::min<uint32_t>(I.chunk, 1u << 21);  // 640 B of branch stack per slot
     const size_t kSlots = I.chunk;
@@ -2073,8 +2276,9 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             launches += 2;
 #endif
             {
-                auto shade = I.all_lights ? (I.textured ? shade_kernel<true, true> : shade_kernel<false, true>)
-                                          : (I.textured ? shade_kernel<true, false> : shade_kernel<false, false>);
+                auto shade = I.env_mode ? (I.textured ? shade_kernel<true, false, true> : shade_kernel<false, false, true>)
+                             : I.all_lights ? (I.textured ? shade_kernel<true, true> : shade_kernel<false, true>)
+                                            : (I.textured ? shade_kernel<true, false> : shade_kernel<false, false>);
                 shade<<<(count + 127) / 128, 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur);
             }
             launches += 1;
@@ -2084,7 +2288,7 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             if (rc != RRT_OK) return rc;
             launches += n;
             resolve_kernel<<<(unsigned)(((uint64_t)count * I.shadow_per_hit + 255) / 256), 256, 0, I.stream>>>(
-                I.d_paths, I.q, (I.all_lights || I.whitted) ? 1 : 0);
+                I.d_paths, I.q, (I.all_lights || I.whitted || I.env_mode) ? 1 : 0);
             advance_kernel<<<1, 1, 0, I.stream>>>(I.q, cur);
             launches += 2;
             cur ^= 1;

@@ -9,6 +9,7 @@
 #include "../../include/rrt.h"
 #include "aggregate.hpp"
 #include "host_scene.hpp"
+#include "image_host.hpp"
 
 namespace rrt {
 
@@ -25,6 +26,13 @@ void texture_host_eval(const rrt_texture* t, uint32_t n, const double uv[2], con
 // compute_differentials of texture_core.h on the host (rrt_differentials_host_probe)
 void differentials_host_eval(const double in24[24], double out10[10]);
 
+// What a scene carries besides geometry, materials, lights and the texture table: decoded images (ImageTexture,
+// InfiniteAreaLight) and the second light list (Scene::infinite_lights).
+struct SceneExtras {
+    std::vector<Image8> images;
+    std::vector<rrt_light> infinite_lights;
+};
+
 class Renderer {
   public:
     Renderer() = default;
@@ -37,7 +45,7 @@ class Renderer {
     int create(int device, const HostScene& scene, const RayTracer* agg, const std::vector<rrt_material>& materials,
                const std::vector<rrt_light>& lights, const std::vector<rrt_texture>& textures,
                const std::vector<int32_t>& material_slots, const double world_bound6[6], const rrt_render_desc& desc,
-               std::string* err);
+               std::string* err, const SceneExtras* extras = nullptr);
     // Integrator::render for this rank's tiles
     int run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, std::string* err);
     int clear(std::string* err);

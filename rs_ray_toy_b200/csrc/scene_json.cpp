@@ -181,6 +181,7 @@ void parse_obj(const std::string& path, TriangleMesh* mesh) {
 // replaces the earlier entry for later lookups (HashMap::insert).
 struct TextureTable {
     std::vector<rrt_texture> rows;
+    std::vector<std::string> image_files;  // as written in the scene file; rrt_texture::t1 of an image row indexes this
     std::map<std::string, int32_t> f, rgb;  // name -> row; -2 = defined, but of a type outside the hot-path scope
 
     int32_t push(uint32_t kind) {
@@ -300,10 +301,17 @@ struct TextureTable {
                 rows[i].map[0] = (double)(uint64_t)read_i64(tc, "octaves", 8);
                 rows[i].map[1] = read_f64(tc, "omega", 0.5);
             }
+        } else if (type == "ImageTexture" && is_rgb) {  // make_tex_info + load_image (:517-566); `gamma` and `scale` are read
+            i = push(RRT_TEX_IMAGE);                    // and never used there
+            rows[i].aa = read_bool(tc, "do_trilinear", false) ? 1u : 0u;
+            rows[i].v[0][0] = read_f64(tc, "max_aniso", 8.0);
+            const std::string wrap = read_string(tc, "wrap", "repeat");
+            rows[i].v[0][1] = wrap == "black" ? (double)RRT_WRAP_BLACK : (wrap == "clamp" ? (double)RRT_WRAP_CLAMP : (double)RRT_WRAP_REPEAT);
+            rows[i].t1 = (int32_t)image_files.size();
+            image_files.push_back(read_string(tc, "filename", "DefaultTexture"));
+            mapping(i, tc, to_world);
         } else if (type == "ImageTexture" || (type == "UVTexture" && !is_rgb)) {
-            if (type == "UVTexture") return;  // not a float texture type: "Unsupported Texture Type", nothing inserted
-            names[name] = -2;                  // an error only if something uses it
-            return;
+            return;  // not a float texture type: "Unsupported Texture Type", nothing inserted
         } else {
             return;  // "Unsupported Texture Type": nothing inserted
         }
@@ -481,9 +489,10 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
                 }
             }
         }
-    // ---- make_all_lights ----
-    if (const Value* a = root->get("lights"); a && a->is_array())
-        for (const auto& lc : a->arr) {
+    // ---- make_all_lights (renderprocess.rs:921-966): `lights` and `infinite_lights` go through the same make_light ----
+    auto resolve_path = [&](const std::string& file) { return file.size() && file[0] == '/' ? file : dir + "/" + file; };
+    for (const std::string& f : tex.image_files) out->image_paths.push_back(resolve_path(f));
+    auto make_light = [&](const json::ValuePtr& lc) -> rrt_light {
             rrt_light l;
             std::memset(&l, 0, sizeof(l));
             const std::string type = read_string(*lc, "light_type", "");
@@ -535,13 +544,24 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
                 } else {
                     throw std::runtime_error("Failed to parse a Shape (renderprocess.rs:1094)");
                 }
+            } else if (type == "infinite") {  // renderprocess.rs:1032-1046
+                l.kind = RRT_LIGHT_INFINITE;
+                double li[3], sc[3];
+                read_spectrum(*lc, "l", li, 1.0);
+                read_spectrum(*lc, "scale", sc, 1.0);
+                for (int k = 0; k < 3; ++k) l.intensity[k] = li[k] * sc[k];  // carried; the reference never uses it (Q34)
+                std::memcpy(l.shape_to_world_inv, xf.inv.m, sizeof(l.shape_to_world_inv));  // world_to_light
+                l.env_image = (uint32_t)out->image_paths.size();
+                out->image_paths.push_back(resolve_path(read_string(*lc, "mapname", "")));
             } else {
-                throw std::runtime_error("light type '" + type + "' is outside the hot-path scope (point, distant, diffuse)");
+                throw std::runtime_error("light type '" + type + "' is outside the hot-path scope (point, distant, diffuse, infinite)");
             }
-            out->lights.push_back(l);
-        }
-    if (const Value* a = root->get("infinite_lights"); a && a->is_array() && !a->arr.empty())
-        throw std::runtime_error("infinite lights are outside the hot-path scope");
+            return l;
+    };
+    if (const Value* a = root->get("lights"); a && a->is_array())
+        for (const auto& lc : a->arr) out->lights.push_back(make_light(lc));
+    if (const Value* a = root->get("infinite_lights"); a && a->is_array())
+        for (const auto& lc : a->arr) out->infinite_lights.push_back(make_light(lc));
 
     // ---- make_integrator: film, camera, sampler, integrator ----
     const Value *ic = root->get("Integrator"), *sc = root->get("Sampler"), *fc = root->get("Film"), *cc = root->get("Camera");

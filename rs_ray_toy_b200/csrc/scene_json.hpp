@@ -17,6 +17,10 @@ struct LoadedScene {
     std::vector<rrt_light> lights;
     std::vector<rrt_texture> textures;      // make_textures: float textures, then rgb textures, definition order
     std::vector<int32_t> material_slots;    // RRT_MATERIAL_SLOTS per material
+    std::vector<rrt_light> infinite_lights;  // Scene::infinite_lights (make_all_lights, renderprocess.rs:945-960)
+    // image files named by ImageTextures (rrt_texture::t1) and infinite lights (rrt_light::env_image), resolved against
+    // the scene file's directory; the caller decodes them (rrt_scene_add_image_png) in this order
+    std::vector<std::string> image_paths;
     std::vector<double> lens_data;  // desc.lens_data points here
     rrt_render_desc desc;
     uint32_t max_prims_in_node = 4;

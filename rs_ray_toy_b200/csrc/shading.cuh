@@ -67,7 +67,8 @@ struct LightRec {
     M34 o2w, w2o;     // sphere
     double radius;
     V3 tp[3], tn[3];  // triangle vertices and vertex normals
-    uint32_t tri_has_n, pad;
+    uint32_t tri_has_n;
+    int32_t env;      // InfiniteAreaLight: index into ShadeScene::envs
 };
 struct ShadeScene {
     const PrimInfo* prims;
@@ -89,6 +90,10 @@ struct ShadeScene {
     const LightRec* lights;
     uint32_t n_lights;
     uint32_t literal;  // Tier L: instance / sphere rays are renormalised like the reference (Q6)
+    const MipView* mips;        // one per ImageTexture (TextureRec::t1)
+    const EnvLightView* envs;   // the InfiniteAreaLights of `lights` and of `infinite_lights`
+    const int32_t* escape_envs; // Scene::infinite_lights: indices into envs (PathIntegrator, path.rs:84)
+    uint32_t n_escape_envs, pad_sc;
 };
 
 // What the integrator reads of a SurfaceInteraction (interaction.rs:95-113)
@@ -725,15 +730,15 @@ static __device__ __noinline__ void material_bump(const ShadeScene& sc, const Ma
     TexPoint e = q;
     e.p = s->p + s->shdpdu * du;
     e.uv = P2{add(s->uv.x, du), add(s->uv.y, 0.0)};
-    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, e, vals);
+    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, e, vals, sc.mips);
     const double u_displace = vals[b].r;
     double dv = mul(add(fabs(q.dvdx), fabs(q.dvdy)), 0.5);
     if (dv == 0.0) dv = 0.0005;
     e.p = s->p + bp.shdpdv * dv;
     e.uv = P2{add(s->uv.x, 0.0), add(s->uv.y, dv)};
-    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, e, vals);
+    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, e, vals, sc.mips);
     const double v_displace = vals[b].r;
-    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, q, vals);
+    texture_eval_table(sc.textures, sc.n_textures, m.bump_needed, q, vals, sc.mips);
     const double displace = vals[b].r;
     const V3 dpdu = s->shdpdu + (s->shn * sub(u_displace, displace)) / du + bp.shdndu * displace;
     const V3 dpdv = bp.shdpdv + (s->shn * sub(v_displace, displace)) / dv + bp.shdndv * displace;
@@ -750,7 +755,7 @@ static __device__ __noinline__ void material_at(const ShadeScene& sc, const Mate
     Rgb vals[kMaxTextures];
     TexPoint q = tex_point(s.uv, s.p);
     if (diff) compute_differentials(s.n, s.dpdu, s.dpdv, *diff, &q);
-    texture_eval_table(sc.textures, sc.n_textures, m.needed, q, vals);
+    texture_eval_table(sc.textures, sc.n_textures, m.needed, q, vals, sc.mips);
     MaterialRec r = m;
     Rgb* const colours[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.metal_eta, &r.metal_k};
 #pragma unroll

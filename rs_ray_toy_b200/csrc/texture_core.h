@@ -12,6 +12,7 @@
 // `spawn_ray(..).into()`, has_differentials = false) and only a closed-form checkerboard reads them; with zero
 // differentials that filter reduces to its point sample (checkerboard.rs:69-83).
 #pragma once
+#include "mipmap_core.h"
 #include "noise_perm.h"
 #include "rmath.cuh"
 
@@ -19,7 +20,8 @@ namespace rrt {
 
 enum : uint32_t {
     TEXK_CONSTANT = 0, TEXK_BILERP = 1, TEXK_SCALE = 2, TEXK_MIX = 3, TEXK_CHECKER2D = 4, TEXK_CHECKER3D = 5, TEXK_UV = 6,
-    TEXK_WINDY = 7, TEXK_WRINKLED = 8  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D's matrix in w2t
+    TEXK_WINDY = 7, TEXK_WRINKLED = 8,  // map[0] = octaves, map[1] = omega (Wrinkled); IdentityMapping3D's matrix in w2t
+    TEXK_IMAGE = 9                      // imagemap.rs:74-81: MIPMap::lookup_d of the mapped point; t1 = index of its MipView
 };
 enum : uint32_t { TEXM_UV = 0, TEXM_PLANAR = 1, TEXM_SPHERICAL = 2, TEXM_CYLINDRICAL = 3 };
 constexpr int kMaxTextures = 32;
@@ -220,7 +222,8 @@ RRT_HD double bump_int(double x) {
 }
 
 // vals[i] for every texture i < n whose bit is set in `needed` (children included by the caller's mask)
-RRT_HD void texture_eval_table(const TextureRec* table, uint32_t n, uint32_t needed, const TexPoint& q, Rgb* vals) {
+RRT_HD void texture_eval_table(const TextureRec* table, uint32_t n, uint32_t needed, const TexPoint& q, Rgb* vals,
+                               const MipView* mips = nullptr) {
     for (uint32_t i = 0; i < n; ++i) {
         if (!((needed >> i) & 1u)) continue;
         const TextureRec& t = table[i];
@@ -279,6 +282,11 @@ RRT_HD void texture_eval_table(const TextureRec* table, uint32_t n, uint32_t nee
             case TEXK_WRINKLED: {  // wrinkled.rs:22-28
                 const V3 w = xf_point(t.w2t, q.p), dx = xf_vector(t.w2t, q.dpdx), dy = xf_vector(t.w2t, q.dpdy);
                 out = rgb(turbulence(w, dx, dy, t.map[1], as_u64(t.map[0])));
+                break;
+            }
+            case TEXK_IMAGE: {  // ImageTexture::evaluate (imagemap.rs:74-81)
+                const P2 st = texture_st(t, q, true, &dstdx, &dstdy);
+                out = mips != nullptr ? mip_lookup_d(mips[t.t1], st, dstdx, dstdy) : rgb(0.0);
                 break;
             }
             default: {  // UVTexture (uv.rs:20-27)

@@ -115,7 +115,7 @@ class Light(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("shape_kind", C.c_uint32), ("intensity", C.c_double * 3), ("dir", C.c_double * 3),
                 ("to_world", C.c_double * 16), ("shape_to_world", C.c_double * 16), ("shape_to_world_inv", C.c_double * 16),
                 ("radius", C.c_double), ("z_min", C.c_double), ("z_max", C.c_double), ("phi_max_deg", C.c_double),
-                ("tri_p", C.c_double * 9), ("tri_n", C.c_double * 9), ("tri_has_n", C.c_uint32), ("pad", C.c_uint32)]
+                ("tri_p", C.c_double * 9), ("tri_n", C.c_double * 9), ("tri_has_n", C.c_uint32), ("env_image", C.c_uint32)]
 
 
 COPPER_N = (0.19998972096819712, 0.922085788777433, 1.0998762520488314)
@@ -156,6 +156,32 @@ def distant_light(l=(1.0, 1.0, 1.0), frm=(0.0, 0.0, 0.0), to=(0.0, 0.0, 1.0), to
     return lt
 
 
+def infinite_light(image_index: int, light_to_world=None, l=(1.0, 1.0, 1.0)) -> Light:
+    """InfiniteAreaLight over an image added with add_image (lights/infinite.rs); `light_to_world` = (m, inverse)."""
+    lt = Light(kind=3, intensity=tuple(l), env_image=image_index)
+    m, inv = light_to_world if light_to_world is not None else (np.eye(4), np.eye(4))
+    lt.to_world[:] = np.asarray(m).reshape(16).tolist()
+    lt.shape_to_world_inv[:] = np.asarray(inv).reshape(16).tolist()
+    return lt
+
+
+def add_image(agg: GpuAggregate, rgb8: np.ndarray) -> int:
+    """rrt_scene_add_image: 8-bit RGB rows (top first) for RRT_TEX_IMAGE textures / infinite lights -> image index."""
+    L = lib()
+    a = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    idx = C.c_uint32()
+    capi.check(L.rrt_scene_add_image(agg.h, a.shape[1], a.shape[0], a.ctypes.data, C.byref(idx)))
+    return idx.value
+
+
+def set_infinite_lights(agg: GpuAggregate, lights) -> None:
+    """rrt_scene_set_infinite_lights: Scene::infinite_lights (escaped rays of the Path integrator)."""
+    L = lib()
+    lts = (Light * max(1, len(lights)))(*lights)
+    capi.check(L.rrt_scene_set_infinite_lights(agg.h, len(lights), C.cast(lts, C.c_void_p)))
+
+
 def area_light_sphere(lemit=(1.0, 1.0, 1.0), radius=1.0, obj_to_world=None) -> Light:
     """DiffuseAreaLight over make_sphere's Sphere (renderprocess.rs:999-1017, 1097-1106)."""
     l = Light()
@@ -189,6 +215,12 @@ def _bind(L):
     L.rrt_scene_set_materials.argtypes = [vp, u32, vp]
     L.rrt_scene_set_lights.restype = i32
     L.rrt_scene_set_lights.argtypes = [vp, u32, vp]
+    L.rrt_scene_set_infinite_lights.restype = i32
+    L.rrt_scene_set_infinite_lights.argtypes = [vp, u32, vp]
+    L.rrt_scene_add_image.restype = i32
+    L.rrt_scene_add_image.argtypes = [vp, u32, u32, vp, C.POINTER(u32)]
+    L.rrt_scene_add_image_png.restype = i32
+    L.rrt_scene_add_image_png.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
     L.rrt_scene_set_textures.restype = i32
     L.rrt_scene_set_textures.argtypes = [vp, u32, vp]
     L.rrt_scene_set_material_textures.restype = i32

@@ -256,6 +256,65 @@ def scene_c1_as_shipped(directory):
     return path
 
 
+def write_test_png(path, width, height, seed=0, alpha=False):
+    """A synthetic 8-bit PNG (smooth gradients + a grid + noise, so that filtering matters) written with PIL — the
+    harness's encoder; the product decodes with its own reader (csrc/png_read.cpp)."""
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    r = 127.5 * (1 + np.sin(x * 0.21 + seed)) * (y / max(1, height - 1))
+    g = 255.0 * ((x // 7 + y // 5) % 2) * 0.6 + 40
+    b = 255.0 * (x / max(1, width - 1)) ** 2
+    img = np.stack([r, g, b], axis=-1) + rng.uniform(-12, 12, (height, width, 3))
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    if alpha:
+        img = np.concatenate([img, np.full((height, width, 1), 200, dtype=np.uint8)], axis=-1)
+    Image.fromarray(img, "RGBA" if alpha else "RGB").save(path)
+    return path
+
+
+def scene_env_and_images(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=4):
+    """Config 1's cubes with what SURVEY §8f rows 2-3 still lacked: an InfiniteAreaLight (environment map, listed both in
+    `lights` — next-event estimation with a live BSDF-sampling half — and in `infinite_lights` — radiance of escaped
+    camera rays) and ImageTextures (a 300 x 140 map that MIPMap::create resamples to 512 x 256, trilinear and EWA, with
+    UV / planar mappings) driving kd and ks, next to a point light.  Mirror and plastic cubes reflect the map."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    cfg = json.loads(open(scene_c1(directory, xres=xres, yres=yres, nsamp=nsamp, integrator=integrator, max_depth=max_depth)).read())
+    # sizes: a MIPMap needs two levels or more for its EWA lookups (with one level the reference indexes past the end
+    # of its pyramid and panics, Q32), and a level is kept only while both sides are >= 64 texels
+    write_test_png(os.path.join(directory, "env.png"), 200, 90, seed=3, alpha=True)
+    write_test_png(os.path.join(directory, "tex_a.png"), 300, 140, seed=1)
+    write_test_png(os.path.join(directory, "tex_b.png"), 256, 128, seed=2)
+    cfg["rgb_texture"] = [
+        {"texture_name": "img_ewa", "texture_type": "ImageTexture", "filename": "tex_a.png",
+         "mapping": {"mapping": "uv", "su": 3.0, "sv": 2.0, "du": 0.25, "dv": 0.5}},
+        {"texture_name": "img_tri", "texture_type": "ImageTexture", "filename": "tex_b.png", "do_trilinear": True, "wrap": "clamp",
+         "mapping": {"mapping": "planar", "v1": [0.0, 0.31, 0.0], "v2": [0.0, 0.0, 0.27], "udelta": 0.1, "vdelta": 0.2}},
+        {"texture_name": "img_black", "texture_type": "ImageTexture", "filename": "tex_b.png", "wrap": "black", "max_aniso": 2.0}]
+    cfg["materials"] = [{"material_type": "MatteMaterial", "material_name": "mat_matte", "kd": "img_ewa"},
+                        {"material_type": "PlasticMaterial", "material_name": "mat_plastic", "kd": "img_tri", "ks": "img_black"},
+                        {"material_type": "MirrorMaterial", "material_name": "mat_mirror"}]
+    env = {"light_type": "infinite", "mapname": "env.png", "l": {"values": [2.0, 2.0, 2.0]},
+           "rotation_axis": [0.0, 1.0, 0.0], "rotation_angle": 40.0}
+    cfg["lights"] = [env, {"light_type": "point", "spectrum": {"values": [300, 300, 300]}}]
+    cfg["infinite_lights"] = [env]
+    prim = cfg["Aggregate"]["primitives"][0]
+    inst = prim["instances"]
+    prims = []
+    for k, name in enumerate(("mat_matte", "mat_plastic", "mat_mirror")):
+        q = dict(prim)
+        q["material_name"] = name
+        q["instances"] = [inst[k]]
+        prims.append(q)
+    cfg["Aggregate"]["primitives"] = prims
+    path = os.path.join(directory, "scene_env.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_area_lights(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
     """Config 1's cubes lit by two DiffuseAreaLights: a sphere emitter above the cubes and
     triangle 4 of cube.obj (the light shape is the raw mesh triangle, Q7), plus one point light.  The emitters

@@ -89,7 +89,8 @@ def _spectrum(cfg, key, default):
 
 
 TEX_ROW = 48
-TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV, TEX_WINDY, TEX_WRINKLED = range(9)
+TEX_CONST, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV, TEX_WINDY, TEX_WRINKLED, TEX_IMAGE = range(10)
+WRAP = {"repeat": 0, "black": 1, "clamp": 2}
 
 
 class Textures:
@@ -101,6 +102,7 @@ class Textures:
 
     def __init__(self, cfg):
         self.rows, self.f, self.rgb = [], {}, {}
+        self.images = []   # (row, filename, do_trilinear, max_aniso, wrap): decoded once the scene exists
         for t in cfg.get("float_texture", []) or []:
             self._add(t, False)
         for t in cfg.get("rgb_texture", []) or []:
@@ -174,6 +176,11 @@ class Textures:
         elif ty == "UVTexture" and is_rgb:
             r, i = self._row(TEX_UV, True)
             self._mapping(r, t)
+        elif ty == "ImageTexture" and is_rgb:   # make_tex_info / load_image (renderprocess.rs:517-566): `gamma`, `scale` unused
+            r, i = self._row(TEX_IMAGE, True)
+            self._mapping(r, t)
+            self.images.append((i, t.get("filename", "DefaultTexture"), bool(t.get("do_trilinear", False)),
+                                float(t.get("max_aniso", 8.0)), WRAP.get(t.get("wrap", "repeat"), 0)))
         elif ty == "ScaleTexture":
             c1 = self._child(names, t.get("t1", "ErrorTextureName"), one, is_rgb)
             c2 = self._child(names, t.get("t2", "ErrorTextureName"), one, is_rgb)
@@ -329,9 +336,26 @@ def light_row(cfg, meshes=None):
                 r[78] = 1
         else:
             raise ValueError("Failed to parse a Shape (renderprocess.rs:1094)")
+    elif t == "infinite":   # renderprocess.rs:1032-1046; r[23] = index of the decoded map (set by LoadedScene)
+        r[0] = 3
+        l, sc = np.array(_spectrum(cfg, "l", 1.0)), np.array(_spectrum(cfg, "scale", 1.0))
+        r[1:4] = l * sc
+        _, inv = to_world(cfg)
+        r[40:56] = inv.reshape(16)
+        r[23] = -1
     else:
         raise ValueError(f"light type {t!r} is outside the restated subset")
     return r
+
+
+def decode_rgb8(path):
+    """image::io::Reader::open(..).decode().into_rgb8(): 8-bit RGB rows, top row first (alpha dropped)."""
+    from PIL import Image
+    im = Image.open(path)
+    if im.mode not in ("RGB", "RGBA", "L", "LA", "P"):
+        raise ValueError(f"{path}: image mode {im.mode} is outside the restated subset")
+    a = np.ascontiguousarray(np.array(im.convert("RGBA"))[..., :3] if im.mode in ("RGBA", "LA", "P") else np.array(im.convert("RGB")), dtype=np.uint8)
+    return a
 
 
 def render_params(cfg, seed=1, tile_mod=1, tile_rank=0, crop=None, want_dump=False):
@@ -434,13 +458,40 @@ class LoadedScene:
                     s.add_prims(g0, nt, -1)
         s.build(int(agg.get("max_prims_in_node", 4)))
         self.lights = np.array([light_row(l, meshes) for l in (cfg.get("lights", []) or [])]).reshape(-1, LIGHT_ROW)
+        self.infinite_lights = np.array([light_row(l, meshes) for l in (cfg.get("infinite_lights", []) or [])]).reshape(-1, LIGHT_ROW)
         L = O.lib()
+        L.orc_add_image.restype = C.c_int32
+        L.orc_add_image.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_double, C.c_uint32]
+        L.orc_add_env_image.restype = C.c_int32
+        L.orc_add_env_image.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_set_infinite_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        reached = set(int(t) for t in self.materials[:, 26:38].reshape(-1) if t >= 0)
+        for i in range(len(tex.rows) - 1, -1, -1):       # children have smaller indices
+            if i in reached and tex.rows[i][0] in (TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D):
+                reached |= {int(tex.rows[i][4]), int(tex.rows[i][5])} | ({int(tex.rows[i][6])} if tex.rows[i][0] == TEX_MIX else set())
+        for (row, fname, tri, aniso, wrap) in tex.images:
+            if row not in reached and not (root / fname).exists():
+                tex.rows[row][0] = TEX_CONST       # never evaluated (the sample scene declares such a texture)
+                tex.rows[row][8:11] = 0.0
+                continue
+            img = decode_rgb8(root / fname)
+            k = L.orc_add_image(s.h, img.shape[1], img.shape[0], img.ctypes.data, int(tri), aniso, wrap)
+            if k < 0:
+                raise RuntimeError(L.orc_last_error().decode())
+            tex.rows[row][4] = k
+        self.textures = tex.table()
+        for rows, cfgs in ((self.lights, cfg.get("lights", []) or []), (self.infinite_lights, cfg.get("infinite_lights", []) or [])):
+            for r, lc in zip(rows, cfgs):
+                if r[0] == 3:
+                    img = decode_rgb8(root / lc.get("mapname", ""))
+                    r[23] = L.orc_add_env_image(s.h, img.shape[1], img.shape[0], img.ctypes.data)
         L.orc_set_materials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_textures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_set_textures(s.h, self.textures.shape[0], self.textures.ctypes.data)
         L.orc_set_materials(s.h, self.materials.shape[0], self.materials.ctypes.data)
         L.orc_set_lights(s.h, self.lights.shape[0], self.lights.ctypes.data)
+        L.orc_set_infinite_lights(s.h, self.infinite_lights.shape[0], self.infinite_lights.ctypes.data)
 
     def render(self, seed=1, nthreads=None, tile_mod=1, tile_rank=0, crop=None, want_dump=False):
         prm, lens = render_params(self.cfg, seed, tile_mod, tile_rank, crop, want_dump)

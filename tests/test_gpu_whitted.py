@@ -130,3 +130,60 @@ def test_limits_are_refused_not_approximated(ctx, tmp_path):
                                           "Integrator": {"integrator_type": "Debug"}})
     with pytest.raises(capi.RrtError):
         Render.load(ctx, path, overrides={"Integrator": {"integrator_type": "Debug", "max_depth": 12}})
+
+
+@pytest.mark.parametrize("integrator", ["Path", "DirectLighting-one", "DirectLighting-all", "Debug"])
+def test_environment_light_and_image_textures(ctx, tmp_path, integrator):
+    """an InfiniteAreaLight in `lights` (next-event estimation + the live BSDF-sampling half of
+    estimate_direct, whose ray only has to escape) and in `infinite_lights` (escaped camera rays and specular bounces of
+    the Path integrator; DirectLighting reads the FIRST entry of `lights` on a miss), and ImageTextures through the
+    reference's MIPMap (EWA, trilinear, three wrap modes; Q31 / Q32 included) — against the oracle.  Transcendentals
+    differ in the last place between the device and libm, and MIPMap levels / texel indices are floors of them: the bar
+    is north_star's image tolerance, the counts are exact."""
+    path = synth.scene_env_and_images(str(tmp_path / "e"), xres=192, yres=108, nsamp=9)
+    kind, _, strategy = integrator.partition("-")
+    ov = {"Integrator": {"integrator_type": kind, "max_depth": 4, "light_strategy": strategy or "one"}}
+    ref = S.load(path, ov).render(seed=1, want_dump=True)
+    gpu = Render.load(ctx, path, overrides=ov, seed=1)
+    gpu.enable_hit_dump()
+    gpu.run()
+    rgb, raw = gpu.film(want_raw=True)
+    st = gpu.stats()
+    assert np.array_equal(raw[..., 3], ref["raw"][..., 3])
+    assert st["camera_rays"] == ref["stats"]["camera_rays"]
+    d, r = gpu.hit_dump(), ref["dump"]
+    assert np.array_equal(d[:, :4], r[:, :4])
+    assert abs(st["extension_rays"] - ref["stats"]["extension_rays"]) <= 8
+    # the device's shadow queue also carries the BSDF-sampled probes the oracle counts apart
+    assert abs(st["shadow_rays"] - ref["stats"]["shadow_rays"] - ref["stats"]["mis_probe_rays"]) <= 8
+    if kind != "Debug":
+        assert ref["stats"]["mis_probe_rays"] > 0
+    assert ref["rgb"].mean() > 1e-3
+    assert rel_rmse(rgb, ref["rgb"]) <= 1e-3
+    # the environment really is what lights the miss pixels (Path, DirectLighting): the corner of the frame is sky
+    if kind != "Debug":
+        assert ref["rgb"][:8, :8].mean() > 0
+    gpu.close()
+
+
+def test_image_inputs_are_checked(ctx, tmp_path):
+    import json as js
+    path = synth.scene_env_and_images(str(tmp_path / "c"), xres=64, yres=36, nsamp=3)
+    cfg = js.loads(open(path).read())
+    # a referenced image that does not exist: an I/O error; an unreferenced one: ignored (the sample scene has one)
+    bad = [dict(t) for t in cfg["rgb_texture"]]
+    bad[0]["filename"] = "nowhere.png"
+    with pytest.raises(capi.RrtError) as e:
+        Render.load(ctx, path, overrides={"rgb_texture": bad})
+    assert e.value.status == capi.RRT_ERR_IO
+    extra = cfg["rgb_texture"] + [{"texture_name": "unused", "texture_type": "ImageTexture", "filename": "nowhere.png"}]
+    Render.load(ctx, path, overrides={"rgb_texture": extra}).close()
+    # an EWA-filtered image with a single MIPMap level: the reference panics at the first filtered lookup
+    synth.write_test_png(str(tmp_path / "c" / "small.png"), 100, 60, seed=9)
+    small = [dict(t) for t in cfg["rgb_texture"]]
+    small[0]["filename"] = "small.png"
+    with pytest.raises(capi.RrtError) as e:
+        Render.load(ctx, path, overrides={"rgb_texture": small})
+    assert e.value.status == capi.RRT_ERR_UNSUPPORTED
+    with pytest.raises(capi.RrtError):    # the literal tier's shadow queue cannot carry the probe ray (Q4)
+        Render.load(ctx, path, literal=True)
