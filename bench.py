@@ -209,7 +209,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
         r = Render.load(ctx, path, seed=1)
         keep = None
     else:
-        keep, r = synth.scene_c5_api(ctx)
+        keep, r = synth.scene_c5_api(ctx, commit=(lambda a: parallel.commit_replicated(a, 4)) if world > 1 else None)
     setup_s = time.perf_counter() - t_setup
     # config 5 is 2.1 G camera samples (about 7 s on one B200): one timed frame after a warm-up on a 1/64 crop
     frames = max(1, min(args.steps, 3)) if config == "c4" else 1
@@ -218,7 +218,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
         r.clear()
         r.run(tile_mod=world, tile_rank=rank)
         if world > 1:
-            parallel.reduce_film(r, dst=0)
+            parallel.gather_film(r, world, rank, dst=0)
 
     if config == "c4":
         frame()  # warm-up frame
@@ -226,7 +226,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
         r.clear()
         r.run(tile_mod=world, tile_rank=rank, crop=(1680, 945, 2160, 1215))
         if world > 1:
-            parallel.reduce_film(r, dst=0)
+            parallel.gather_film(r, world, rank, dst=0)
         r.clear()
     launches0 = ctx.launch_count
     barrier()
@@ -254,7 +254,7 @@ def path_traced(args, ctx, rank, world, local_rank, barrier, config):
             "metric": "Msamples/s path-traced", "unit": "Msamples/s", "value": samples / (dt / frames) / 1e6,
             "ms_per_frame": dt / frames * 1e3, "frames": frames, "n_gpus": world, "scaling": "strong",
             "config": {"workload": PT_CONFIGS[config], "parallelism": f"16x16 sample tiles dealt t % {world} == rank, "
-                       "scene replicated, one NCCL reduce(sum) of the 4-f64-per-pixel film per frame"},
+                       "scene replicated (one rank builds the tree, the others receive it), one NCCL gather of the ranks' own tiles per frame"},
             "samples_per_frame": samples, "camera_rays": cam, "extension_rays": ext, "shadow_rays": sh,
             "rays_per_sample": (ext + sh) / max(samples, 1.0), "mean_bounces": bnc / max(cam, 1.0),
             "Mrays_per_s": (ext + sh) / (dt / frames) / 1e6, "setup_s": setup_s,

@@ -110,6 +110,12 @@ int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t buil
 int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out);
 /* Primitive::world_bound (bvh.rs:177-182): out6 = p_min, p_max.                                 */
 int rrt_world_bound(const rrt_scene* scene, double out6[6]);
+/* The committed aggregate — tree, primitive records, instance tables — as one relocatable blob, so that ONE rank builds
+ * and the others replicate ("scene replicated per GPU"): rrt_scene_export_tree with buffer = NULL returns the
+ * size; rrt_scene_commit_from_tree commits a scene that received the SAME rrt_scene_add_* calls without building a tree
+ * of its own (the blob's primitive count is checked).  Fast tier only.                                             */
+int rrt_scene_export_tree(const rrt_scene* scene, void* buffer, uint64_t capacity, uint64_t* bytes);
+int rrt_scene_commit_from_tree(rrt_scene* scene, const void* blob, uint64_t bytes);
 /* Build statistics: nodes, leaves, max depth, bytes uploaded, host build seconds (x1e6).        */
 int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]);
 
@@ -308,6 +314,21 @@ int rrt_render_film_device(rrt_render* render, void** d_film, uint64_t* n_double
  * buffer of n_doubles f64 on `cuda_stream` — the hand-off to a collective that sums ranks' films
  * (merge_film_tile across ranks, film.rs:248-263).                                              */
 int rrt_render_film_copy(rrt_render* render, void* d_buffer, int to_render, void* cuda_stream);
+/* The film GATHER of a multi-GPU frame (renderprocess.rs tiling dealt to ranks; merge_film_tile, film.rs:248-263).  With a
+ * filter radius <= 0.5 the tiles t % tile_mod == tile_rank own their pixels, so a rank ships only those: 1 / G of the film.
+ *   rrt_render_owned_doubles : size of that rank's packed tiles (1024 doubles per 16 x 16 tile);
+ *   rrt_render_pack_owned    : film -> caller-owned DEVICE buffer, on `cuda_stream` (ordered after the render);
+ *   rrt_render_unpack_owned  : DEVICE buffer -> film (the root calls it once per sender, with the sender's rank);
+ *   rrt_film_gather          : ONE process driving n renderers on n devices, renders[r] having run (n, r): packs every
+ *                              rank's tiles, copies them to renders[root]'s device (peer copy over NVLink) and unpacks.
+ * Processes-per-GPU callers move the packed buffers with their own collective (NCCL gather; rs_ray_toy_b200/parallel.py).
+ * Wider filters splat across tile borders: RRT_ERR_UNSUPPORTED here, use rrt_render_film_copy + a sum.               */
+int rrt_render_owned_doubles(const rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, uint64_t* n_doubles);
+int rrt_render_pack_owned(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, void* d_buffer, uint64_t capacity_doubles,
+                          void* cuda_stream);
+int rrt_render_unpack_owned(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, const void* d_buffer,
+                            uint64_t capacity_doubles, void* cuda_stream);
+int rrt_film_gather(rrt_render* const* renders, uint32_t n, uint32_t root);
 /* out16: camera rays, extension rays, shadow rays, bounces, zero-weight samples, samples, kernels
  * launched, render microseconds, set-up microseconds, chunks, neighbour lens rays decided by the fp32
  * walk, neighbour lens rays it handed to the f64 walk, ...                                       */

@@ -146,6 +146,21 @@ class GpuAggregate:
         self.committed = True
         return self
 
+    def export_tree(self) -> np.ndarray:
+        """rrt_scene_export_tree: the committed aggregate (tree + records + tables) as one uint8 blob."""
+        n = C.c_uint64()
+        capi.check(self.L.rrt_scene_export_tree(self.h, None, 0, C.byref(n)))
+        blob = np.empty(n.value, dtype=np.uint8)
+        capi.check(self.L.rrt_scene_export_tree(self.h, blob.ctypes.data, blob.size, C.byref(n)))
+        return blob
+
+    def commit_from_tree(self, blob: np.ndarray):
+        """rrt_scene_commit_from_tree: commit with a tree another rank built over the same primitives."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        capi.check(self.L.rrt_scene_commit_from_tree(self.h, b.ctypes.data, b.size))
+        self.committed = True
+        return self
+
     @property
     def num_prims(self) -> int:
         n = C.c_uint32()

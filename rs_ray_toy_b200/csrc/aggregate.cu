@@ -1352,10 +1352,18 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     stats_.n_prims = n;
     stats_.build_usec =
         (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
-    // L1-heavy kernels: no shared memory is used, give the whole carve-out to L1.
-    // the only shared memory is the traversal stack (one entry per tree level + the marker);
-    // everything else of the 256 KB stays L1
     stack_levels_ = (int)tree.max_depth + 2;
+    node_bytes_ = node_bytes;
+    prim_bytes_ = prim_bytes;
+    inst_bytes_ = d_inst_ ? 12 * scene.instances.size() * sizeof(double) : 0;
+    gsphere_bytes_ = gspheres.size() * sizeof(GenSphere);
+    configure_kernels(quantise);
+    return RRT_OK;
+}
+
+// the only shared memory is the traversal stack (one entry per tree level + the marker, [+ the screen's rows]);
+// everything else of the 256 KB stays L1
+void DeviceAggregate::configure_kernels(bool quantise) {
     const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t);
     int carve = (int)(((quantise ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
@@ -1370,6 +1378,108 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
+}
+
+namespace {
+struct BlobHeader {
+    uint64_t magic, version;
+    AggView view;          // device pointers are meaningless in the blob
+    AggregateStats stats;
+    int32_t stack_levels, sort_rays;
+    uint64_t node_bytes, prim_bytes, inst_bytes, gsphere_bytes;
+};
+constexpr uint64_t kBlobMagic = 0x3130454552545252ull;  // "RRTREE01"
+}  // namespace
+
+int DeviceAggregate::export_blob(void* buffer, uint64_t capacity, uint64_t* bytes, std::string* err) const {
+    const uint64_t total = sizeof(BlobHeader) + node_bytes_ + prim_bytes_ + inst_bytes_ + gsphere_bytes_;
+    *bytes = total;
+    if (!buffer) return RRT_OK;
+    if (capacity < total) {
+        if (err) *err = "export_blob: buffer too small";
+        return RRT_ERR_INVALID;
+    }
+    BlobHeader h{};
+    h.magic = kBlobMagic;
+    h.version = 1;
+    h.view = view_;
+    h.view.nodes = h.view.prims = h.view.gspheres = nullptr;
+    h.view.inst_w2p = nullptr;
+    h.stats = stats_;
+    h.stack_levels = stack_levels_;
+    h.sort_rays = sort_rays_ ? 1 : 0;
+    h.node_bytes = node_bytes_;
+    h.prim_bytes = prim_bytes_;
+    h.inst_bytes = inst_bytes_;
+    h.gsphere_bytes = gsphere_bytes_;
+    char* out = static_cast<char*>(buffer);
+    std::memcpy(out, &h, sizeof(h));
+    out += sizeof(h);
+    RRT_CUDA(cudaSetDevice(device_));
+    RRT_CUDA(cudaMemcpy(out, d_nodes_, node_bytes_, cudaMemcpyDeviceToHost));
+    out += node_bytes_;
+    RRT_CUDA(cudaMemcpy(out, d_prims_, prim_bytes_, cudaMemcpyDeviceToHost));
+    out += prim_bytes_;
+    if (inst_bytes_) RRT_CUDA(cudaMemcpy(out, d_inst_, inst_bytes_, cudaMemcpyDeviceToHost));
+    out += inst_bytes_;
+    if (gsphere_bytes_) RRT_CUDA(cudaMemcpy(out, d_gspheres_, gsphere_bytes_, cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+int DeviceAggregate::import_blob(int device, const void* blob, uint64_t bytes, uint64_t n_prims_expected, std::string* err) {
+    auto t_start = std::chrono::steady_clock::now();
+    BlobHeader h;
+    if (bytes < sizeof(h)) {
+        if (err) *err = "import_blob: truncated";
+        return RRT_ERR_INVALID;
+    }
+    std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != kBlobMagic || h.version != 1 ||
+        bytes != sizeof(h) + h.node_bytes + h.prim_bytes + h.inst_bytes + h.gsphere_bytes) {
+        if (err) *err = "import_blob: not a tree exported by this library version";
+        return RRT_ERR_INVALID;
+    }
+    if (h.stats.n_prims != n_prims_expected) {
+        if (err) *err = "import_blob: the tree was built over " + std::to_string(h.stats.n_prims) + " primitives, the scene holds " + std::to_string(n_prims_expected);
+        return RRT_ERR_INVALID;
+    }
+    if (h.stack_levels < 2 || h.stack_levels > kStack) {
+        if (err) *err = "import_blob: bad stack depth";
+        return RRT_ERR_INVALID;
+    }
+    device_ = device;
+    RRT_CUDA(cudaSetDevice(device));
+    const char* in = static_cast<const char*>(blob) + sizeof(h);
+    RRT_CUDA(cudaMalloc(&d_nodes_, h.node_bytes));
+    RRT_CUDA(cudaMemcpy(d_nodes_, in, h.node_bytes, cudaMemcpyHostToDevice));
+    in += h.node_bytes;
+    RRT_CUDA(cudaMalloc(&d_prims_, h.prim_bytes));
+    RRT_CUDA(cudaMemcpy(d_prims_, in, h.prim_bytes, cudaMemcpyHostToDevice));
+    in += h.prim_bytes;
+    if (h.inst_bytes) {
+        RRT_CUDA(cudaMalloc(&d_inst_, h.inst_bytes));
+        RRT_CUDA(cudaMemcpy(d_inst_, in, h.inst_bytes, cudaMemcpyHostToDevice));
+    }
+    in += h.inst_bytes;
+    if (h.gsphere_bytes) {
+        RRT_CUDA(cudaMalloc(&d_gspheres_, h.gsphere_bytes));
+        RRT_CUDA(cudaMemcpy(d_gspheres_, in, h.gsphere_bytes, cudaMemcpyHostToDevice));
+    }
+    view_ = h.view;
+    view_.nodes = d_nodes_;
+    view_.prims = d_prims_;
+    view_.inst_w2p = static_cast<const double*>(d_inst_);
+    view_.gspheres = d_gspheres_;
+    stats_ = h.stats;
+    stack_levels_ = h.stack_levels;
+    sort_rays_ = h.sort_rays != 0;
+    node_bytes_ = h.node_bytes;
+    prim_bytes_ = h.prim_bytes;
+    inst_bytes_ = h.inst_bytes;
+    gsphere_bytes_ = h.gsphere_bytes;
+    stats_.build_usec =
+        (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_start).count();
+    configure_kernels(view_.quantised != 0);
     return RRT_OK;
 }
 

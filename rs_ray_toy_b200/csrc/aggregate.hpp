@@ -78,6 +78,11 @@ class DeviceAggregate : public RayTracer {
     int any_hit_indirect(uint64_t capacity, const uint32_t* d_count, const rrt_ray* d_rays, uint8_t* d_occluded,
                          void* stream, std::string* err, int* launches = nullptr) const override;
 
+    // The committed aggregate as a relocatable blob (header + node / record / instance / sphere tables) and back: one rank
+    // builds, the others upload.  `buffer` = nullptr: only *bytes is set.
+    int export_blob(void* buffer, uint64_t capacity, uint64_t* bytes, std::string* err) const;
+    int import_blob(int device, const void* blob, uint64_t bytes, uint64_t n_prims_expected, std::string* err);
+
     const AggView& view() const { return view_; }
     const AggregateStats& stats() const override { return stats_; }
 
@@ -108,7 +113,9 @@ class DeviceAggregate : public RayTracer {
     void* d_prims_ = nullptr;
     void* d_inst_ = nullptr;
     void* d_gspheres_ = nullptr;
+    uint64_t node_bytes_ = 0, prim_bytes_ = 0, inst_bytes_ = 0, gsphere_bytes_ = 0;
     int device_ = 0;
+    void configure_kernels(bool quantised);
 };
 
 }  // namespace rrt

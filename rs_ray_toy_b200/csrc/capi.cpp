@@ -452,6 +452,32 @@ int rrt_scene_stats(const rrt_scene* scene, uint64_t out8[8]) {
     return RRT_OK;
 }
 
+int rrt_scene_export_tree(const rrt_scene* scene, void* buffer, uint64_t capacity, uint64_t* bytes) {
+    if (!scene || !bytes) return fail(RRT_ERR_INVALID, "rrt_scene_export_tree: null argument");
+    if (!scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_export_tree: scene is not committed");
+    const rrt::DeviceAggregate* agg = dynamic_cast<const rrt::DeviceAggregate*>(scene->agg.get());
+    if (!agg) return fail(RRT_ERR_UNSUPPORTED, "rrt_scene_export_tree: the literal tier's aggregate is not exported");
+    std::string err;
+    int rc = agg->export_blob(buffer, capacity, bytes, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_scene_commit_from_tree(rrt_scene* scene, const void* blob, uint64_t bytes) {
+    if (!scene || !blob) return fail(RRT_ERR_INVALID, "rrt_scene_commit_from_tree: null argument");
+    if (scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_commit_from_tree: scene is already committed");
+    try {
+        std::unique_ptr<rrt::DeviceAggregate> agg(new rrt::DeviceAggregate());
+        std::string err;
+        int rc = agg->import_blob(scene->ctx->device, blob, bytes, scene->host.prims.size(), &err);
+        if (rc != RRT_OK) return fail(rc, err);
+        scene->agg = std::move(agg);
+        scene->committed = true;
+        scene->build_flags = RRT_BUILD_FAST;
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
+    return RRT_OK;
+}
+
 int rrt_intersect_device(const rrt_scene* scene, uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, void* cuda_stream) {
     if (!scene || !scene->committed) return fail(RRT_ERR_INVALID, "rrt_intersect_device: scene is not committed");
     if (n == 0) return RRT_OK;
@@ -811,6 +837,57 @@ int rrt_render_film_copy(rrt_render* render, void* d_buffer, int to_render, void
     std::string err;
     int rc = render->renderer.copy_film_device(d_buffer, to_render != 0, cuda_stream, &err);
     return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_render_owned_doubles(const rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, uint64_t* n_doubles) {
+    if (!render || !n_doubles) return fail(RRT_ERR_INVALID, "rrt_render_owned_doubles: null argument");
+    if (tile_mod == 0 || tile_rank >= tile_mod) return fail(RRT_ERR_INVALID, "rrt_render_owned_doubles: tile_rank must be < tile_mod");
+    *n_doubles = render->renderer.owned_tiles(tile_mod, tile_rank) * 1024;
+    return RRT_OK;
+}
+int rrt_render_pack_owned(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, void* d_buffer, uint64_t capacity_doubles,
+                          void* cuda_stream) {
+    if (!render || !d_buffer) return fail(RRT_ERR_INVALID, "rrt_render_pack_owned: null argument");
+    std::string err;
+    int rc = render->renderer.pack_owned(tile_mod, tile_rank, d_buffer, capacity_doubles, false, cuda_stream, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_render_unpack_owned(rrt_render* render, uint32_t tile_mod, uint32_t tile_rank, const void* d_buffer,
+                            uint64_t capacity_doubles, void* cuda_stream) {
+    if (!render || !d_buffer) return fail(RRT_ERR_INVALID, "rrt_render_unpack_owned: null argument");
+    std::string err;
+    int rc = render->renderer.pack_owned(tile_mod, tile_rank, const_cast<void*>(d_buffer), capacity_doubles, true, cuda_stream, &err);
+    return rc == RRT_OK ? RRT_OK : fail(rc, err);
+}
+int rrt_film_gather(rrt_render* const* renders, uint32_t n, uint32_t root) {
+    if (!renders || n == 0 || root >= n) return fail(RRT_ERR_INVALID, "rrt_film_gather: bad arguments");
+    for (uint32_t r = 0; r < n; ++r)
+        if (!renders[r]) return fail(RRT_ERR_INVALID, "rrt_film_gather: null renderer");
+    rrt::Renderer& dst = renders[root]->renderer;
+    for (uint32_t r = 0; r < n; ++r) {
+        if (r == root) continue;
+        rrt::Renderer& src = renders[r]->renderer;
+        if (src.xres() != dst.xres() || src.yres() != dst.yres()) return fail(RRT_ERR_INVALID, "rrt_film_gather: films differ in size");
+        const uint64_t nd = src.owned_tiles(n, r) * 1024;
+        if (nd == 0) continue;
+        void *d_src = nullptr, *d_dst = nullptr;
+        std::string err;
+        CAPI_CUDA(cudaSetDevice(src.device()));
+        CAPI_CUDA(cudaMalloc(&d_src, nd * sizeof(double)));
+        int rc = src.pack_owned(n, r, d_src, nd, false, nullptr, &err);
+        if (rc == RRT_OK) {
+            CAPI_CUDA(cudaStreamSynchronize(nullptr));
+            CAPI_CUDA(cudaSetDevice(dst.device()));
+            CAPI_CUDA(cudaMalloc(&d_dst, nd * sizeof(double)));
+            CAPI_CUDA(cudaMemcpyPeer(d_dst, dst.device(), d_src, src.device(), nd * sizeof(double)));
+            rc = dst.pack_owned(n, r, d_dst, nd, true, nullptr, &err);
+            CAPI_CUDA(cudaStreamSynchronize(nullptr));
+            cudaFree(d_dst);
+        }
+        cudaSetDevice(src.device());
+        cudaFree(d_src);
+        if (rc != RRT_OK) return fail(rc, err);
+    }
+    return RRT_OK;
 }
 int rrt_render_stats(const rrt_render* render, uint64_t out16[16]) {
     if (!render || !out16) return fail(RRT_ERR_INVALID, "rrt_render_stats: null argument");

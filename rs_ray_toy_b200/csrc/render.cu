@@ -1378,6 +1378,28 @@ __global__ void __launch_bounds__(256) deposit_kernel(FilmParams film, const Pat
     }
 }
 
+// ---- film gather: the pixels of one rank's tiles, packed ------------------------------------------------------------
+// With a filter radius <= 0.5 a sample lands in the pixel it was drawn in, so the pixels of the tiles t % G == r are
+// written by rank r alone (film.rs:216-226) and the frame is a GATHER of 1 / G of the film per rank, not a sum.
+// Packed layout: owned tile k (t = r + k G) -> 256 slots of 4 doubles, row-major inside the tile; slots outside the
+// image stay zero.
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const double* __restrict__ film, int64_t xres, int64_t yres, uint32_t n_tiles_x,
+                                                          uint32_t tile_mod, uint32_t tile_rank, uint32_t n_owned, double* __restrict__ out,
+                                                          int unpack) {
+    const uint32_t k = blockIdx.x;
+    if (k >= n_owned) return;
+    const uint32_t t = tile_rank + k * tile_mod;
+    const int64_t x = (int64_t)(t % n_tiles_x) * kTile + (threadIdx.x % kTile), y = (int64_t)(t / n_tiles_x) * kTile + (threadIdx.x / kTile);
+    double4* slot = reinterpret_cast<double4*>(out) + (size_t)k * 256 + threadIdx.x;
+    if (x < xres && y < yres) {
+        double4* px = reinterpret_cast<double4*>(const_cast<double*>(film)) + (size_t)(y * xres + x);
+        if (unpack) *px = *slot;
+        else *slot = *px;
+    } else if (!unpack) {
+        *slot = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+}
+
 // RealisticCamera::bound_exit_pupil (camera.rs:442-488) for all 64 film slabs at once: every
 // (slab, sample) pair is one lens trace; successful rear-element points are min/max-reduced.
 // The reference's running `inside(pupil_bounds)` shortcut cannot change the box (a point inside
@@ -2367,6 +2389,49 @@ int Renderer::copy_film_device(void* buffer, bool to_render, void* stream, std::
     RND_CUDA(cudaSetDevice(impl_->device));
     RND_CUDA(cudaMemcpyAsync(to_render ? d_film_ : buffer, to_render ? buffer : d_film_, film_doubles() * sizeof(double),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return RRT_OK;
+}
+
+int Renderer::device() const { return impl_ ? impl_->device : -1; }
+
+uint64_t Renderer::owned_tiles(uint32_t tile_mod, uint32_t tile_rank) const {
+    if (!impl_ || tile_mod == 0 || tile_rank >= tile_mod) return 0;
+    const FilmParams& F = impl_->film;
+    const uint64_t n = (uint64_t)((F.sb[2] - F.sb[0] + kTile - 1) / kTile) * (uint64_t)((F.sb[3] - F.sb[1] + kTile - 1) / kTile);
+    return n > tile_rank ? (n - tile_rank + tile_mod - 1) / tile_mod : 0;
+}
+
+int Renderer::pack_owned(uint32_t tile_mod, uint32_t tile_rank, void* d_buffer, uint64_t capacity_doubles, bool unpack, void* stream,
+                         std::string* err) {
+    if (!impl_ || !d_buffer) return RRT_ERR_INVALID;
+    const FilmParams& F = impl_->film;
+    if (F.rx > 0.5 || F.ry > 0.5 || F.sb[0] != 0 || F.sb[1] != 0) {
+        if (err) *err = "tiles own their pixels only with a filter radius <= 0.5: wider filters need the film reduce";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    const uint64_t n = owned_tiles(tile_mod, tile_rank);
+    if (tile_mod == 0 || tile_rank >= tile_mod || capacity_doubles < n * 1024) {
+        if (err) *err = "pack_owned: bad tile range or buffer too small";
+        return RRT_ERR_INVALID;
+    }
+    if (n == 0) return RRT_OK;
+    RND_CUDA(cudaSetDevice(impl_->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the film is written on the renderer's own stream: order this copy after it
+    cudaEvent_t ev;
+    RND_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    RND_CUDA(cudaEventRecord(ev, impl_->stream));
+    RND_CUDA(cudaStreamWaitEvent(s, ev, 0));
+    const uint32_t ntx = (uint32_t)((F.sb[2] - F.sb[0] + kTile - 1) / kTile);
+    pack_tiles_kernel<<<(unsigned)n, 256, 0, s>>>(static_cast<const double*>(d_film_), F.xres, F.yres, ntx, tile_mod, tile_rank, (uint32_t)n,
+                                                  static_cast<double*>(d_buffer), unpack ? 1 : 0);
+    RND_CUDA(cudaGetLastError());
+    if (unpack) {  // later renders / reads on the renderer's stream see the unpacked pixels
+        RND_CUDA(cudaEventRecord(ev, s));
+        RND_CUDA(cudaStreamWaitEvent(impl_->stream, ev, 0));
+    }
+    RND_CUDA(cudaEventDestroy(ev));
+    stats_.launches += 1;
     return RRT_OK;
 }
 

@@ -51,6 +51,12 @@ class Renderer {
     int clear(std::string* err);
     int read_film(double* rgb, double* raw, std::string* err);
     int copy_film_device(void* buffer, bool to_render, void* stream, std::string* err);
+    // The pixels of the tiles t % tile_mod == tile_rank, packed (1024 doubles per tile) into / out of a device buffer on
+    // `stream`: the film GATHER of a multi-GPU frame with a filter radius <= 0.5.
+    uint64_t owned_tiles(uint32_t tile_mod, uint32_t tile_rank) const;
+    int pack_owned(uint32_t tile_mod, uint32_t tile_rank, void* d_buffer, uint64_t capacity_doubles, bool unpack, void* stream,
+                   std::string* err);
+    int device() const;
     void* film_device() const { return d_film_; }
     int64_t xres() const { return xres_; }
     int64_t yres() const { return yres_; }

@@ -257,6 +257,14 @@ def _bind(L):
     L.rrt_rgb_to_png.argtypes = [vp, u32, u32, C.c_char_p, vp]
     L.rrt_render_film_copy.restype = i32
     L.rrt_render_film_copy.argtypes = [vp, vp, i32, vp]
+    L.rrt_render_owned_doubles.restype = i32
+    L.rrt_render_owned_doubles.argtypes = [vp, u32, u32, C.POINTER(C.c_uint64)]
+    L.rrt_render_pack_owned.restype = i32
+    L.rrt_render_pack_owned.argtypes = [vp, u32, u32, vp, C.c_uint64, vp]
+    L.rrt_render_unpack_owned.restype = i32
+    L.rrt_render_unpack_owned.argtypes = [vp, u32, u32, vp, C.c_uint64, vp]
+    L.rrt_film_gather.restype = i32
+    L.rrt_film_gather.argtypes = [vp, u32, u32]
     L.rrt_render_stats.restype = i32
     L.rrt_render_stats.argtypes = [vp, vp]
     L.rrt_render_hit_dump.restype = i32
@@ -385,6 +393,18 @@ class Render:
     def film_copy(self, d_buffer: int, to_render: bool, stream: int = 0):
         """Accumulation film -> device buffer (to_render False) or back (True); 4*xres*yres f64."""
         capi.check(self.L.rrt_render_film_copy(self.h, C.c_void_p(d_buffer), int(to_render), C.c_void_p(stream)))
+
+    def owned_doubles(self, tile_mod: int, tile_rank: int) -> int:
+        n = C.c_uint64()
+        capi.check(self.L.rrt_render_owned_doubles(self.h, tile_mod, tile_rank, C.byref(n)))
+        return int(n.value)
+
+    def pack_owned(self, tile_mod: int, tile_rank: int, d_buffer: int, capacity_doubles: int, stream: int = 0):
+        """The pixels of this rank's tiles -> a packed device buffer (the multi-GPU film gather's send side)."""
+        capi.check(self.L.rrt_render_pack_owned(self.h, tile_mod, tile_rank, C.c_void_p(d_buffer), capacity_doubles, C.c_void_p(stream)))
+
+    def unpack_owned(self, tile_mod: int, tile_rank: int, d_buffer: int, capacity_doubles: int, stream: int = 0):
+        capi.check(self.L.rrt_render_unpack_owned(self.h, tile_mod, tile_rank, C.c_void_p(d_buffer), capacity_doubles, C.c_void_p(stream)))
 
     def stats(self) -> dict:
         out = np.zeros(16, dtype=np.uint64)

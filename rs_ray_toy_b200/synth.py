@@ -620,7 +620,7 @@ def c5_texture_rows():
 
 
 def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=257, seed=SEED_C5_SOUP, max_depth=5,
-                 textured=False):
+                 textured=False, commit=None):
     """Config 5: a `n_tris` random-soup mesh (half Matte, half Plastic), one point light at the origin
     (Q17) and one distant light, camera outside the unit cube looking at its centre.  Returns
     (aggregate, Render).  `textured` drives the Matte kd and the Plastic roughness by c5_texture_rows()
@@ -634,7 +634,10 @@ def scene_c5_api(ctx, n_tris=1 << 22, edge=0.006, xres=3840, yres=2160, nsamp=25
     m1 = agg.add_mesh(p[3 * half:], idx[half:] - 3 * half)
     agg.add_triangles(m0, 0)
     agg.add_triangles(m1, 1)
-    agg.commit(4)
+    if commit is None:
+        agg.commit(4)
+    else:
+        commit(agg)   # e.g. parallel.commit_replicated: one rank builds the tree, the others receive it
     desc = default_render_desc(xres, yres, nsamp, cam_pos=(0.5, 0.5, -2.5), cam_look=(0.5, 0.5, 0.5), focus_distance=3.0,
                                max_depth=max_depth, seed=1)
     textures = slots = None

@@ -388,3 +388,49 @@ def test_full_size_config5(ctx):
     assert abs(st["shadow_rays"] - ref["stats"]["shadow_rays"]) <= 8
     assert rel_rmse(rgb[sl], ref["rgb"][sl]) <= REL_RMSE
     gpu.close()
+
+
+def test_film_gather_and_tree_replication(ctx, tmp_path):
+    """The multi-GPU plumbing of the C ABI on one device: (1) rrt_scene_export_tree / rrt_scene_commit_from_tree — a
+    scene committed from another scene's tree answers every ray identically; (2) rrt_film_gather — G renderers, each
+    having rendered its tiles t % G == r, gathered onto renderer 0 by moving only the owned tiles' pixels: the frame
+    equals the single-renderer frame bit for bit (box filter 0.5: every pixel has one owner)."""
+    import ctypes as C
+    import scenes
+    from rs_ray_toy_b200 import capi
+    from rs_ray_toy_b200.aggregate import GpuAggregate
+    p, idx = scenes.soup(30000)
+    a = scenes.gpu_soup(ctx, p, idx)
+    blob = a.export_tree()
+    b = GpuAggregate(ctx)
+    b.add_triangles(b.add_mesh(p, idx), 0)
+    b.commit_from_tree(blob)
+    rays = synth.bounce_rays(p, idx, 50000, seed=3)
+    assert np.array_equal(a.intersect(rays), b.intersect(rays)) and np.array_equal(a.intersect_p(rays), b.intersect_p(rays))
+    c = GpuAggregate(ctx)
+    c.add_triangles(c.add_mesh(p[:300], idx[:100]), 0)
+    with pytest.raises(capi.RrtError):      # a tree over other primitives
+        c.commit_from_tree(blob)
+    with pytest.raises(capi.RrtError):
+        c.commit_from_tree(blob[:1000])
+
+    path = synth.scene_c4(str(tmp_path / "c4"), n_spheres=1500, xres=200, yres=120, nsamp=5, extent=10.0)
+    full = Render.load(ctx, path, seed=1)
+    full.run()
+    _, raw_full = full.film(want_raw=True)
+    L = capi.lib()
+    for G in (2, 3):
+        parts = [Render.load(ctx, path, seed=1) for _ in range(G)]
+        for r, part in enumerate(parts):
+            part.run(tile_mod=G, tile_rank=r)
+        assert sum(part.owned_doubles(G, r) for r, part in enumerate(parts)) == 1024 * 13 * 8   # ceil(200/16) x ceil(120/16) tiles
+        handles = (C.c_void_p * G)(*[part.h for part in parts])
+        capi.check(L.rrt_film_gather(handles, G, 0))
+        assert np.array_equal(parts[0].film(want_raw=True)[1], raw_full)
+        for part in parts:
+            part.close()
+    # a filter wider than a pixel: tiles do not own their pixels, the gather refuses and the caller sums films instead
+    wide = Render.load(ctx, path, overrides={"Film": {"xres": 200, "yres": 120, "diagonal": 35, "Filter": {"filter_type": "GaussianFilter"}}}, seed=1)
+    with pytest.raises(capi.RrtError) as e:
+        wide.owned_doubles(2, 0) and wide.pack_owned(2, 0, 1, 1 << 40)
+    assert e.value.status == capi.RRT_ERR_UNSUPPORTED
