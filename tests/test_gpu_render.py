@@ -80,9 +80,14 @@ def test_config1_literal_tier(ctx, tmp_path):
     rgb = gpu.film()
     diff = np.abs(rgb - ref["rgb"]).max(axis=2)
     flipped = diff > 1e-9
-    assert flipped.sum() <= 1e-4 * flipped.size, int(flipped.sum())
+    n_flipped = int(flipped.sum())
+    whole = rel_rmse(rgb, ref["rgb"])
+    print(f"literal tier: {n_flipped} of {flipped.size} pixels excluded as Q3 flips; whole-image relative RMSE {whole:.3e}")
+    assert n_flipped <= 6, n_flipped          # the measured count: a larger one is a regression, not chaos
     masked = np.where(flipped[..., None], ref["rgb"], rgb)
     assert rel_rmse(masked, ref["rgb"]) < 1e-6
+    # north_star's image bound (1e-3) holds for the image WITHOUT the excluded pixels by three orders of magnitude; with
+    # them the frame stays under 5e-3 (six pixels that took the other branch of a Q3 tie, each a whole light sample off)
     out = compare(gpu, ref, rmse_bound=5e-3)
     # and it is a different image from the fixed tier (shadows: Q4 / Q9)
     fixed = Render.load(ctx, path, seed=1)
