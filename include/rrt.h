@@ -107,6 +107,13 @@ int rrt_scene_add_sphere(rrt_scene* scene, const double* obj_to_world_m, const d
 /* BVHAccel::new(prims, max_prims_in_node, split_method) (bvh.rs:307-363): host build, flatten to
  * the linear SoA layout, upload to HBM.                                                         */
 int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t build_flags);
+/* Dynamic scenes ("refit for instance updates"): replaces the transforms of instances
+ * [first_instance, first_instance + n) — numbered in the order the rrt_scene_add_* calls appended them — and brings the
+ * aggregate up to date: the moved primitives are re-baked to world space and the tree is made anew ON the device
+ * (Morton keys, radix sort, radix tree, bottom-up boxes: milliseconds).  Fast tier; integrators made over the scene
+ * must be destroyed first, since they hold its tables.                                                              */
+int rrt_scene_update_instances(rrt_scene* scene, uint32_t first_instance, uint32_t n, const double* instance_m,
+                               const double* instance_minv);
 int rrt_scene_num_prims(const rrt_scene* scene, uint32_t* out);
 /* Primitive::world_bound (bvh.rs:177-182): out6 = p_min, p_max.                                 */
 int rrt_world_bound(const rrt_scene* scene, double out6[6]);

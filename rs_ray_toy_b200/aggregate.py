@@ -146,6 +146,13 @@ class GpuAggregate:
         self.committed = True
         return self
 
+    def update_instances(self, first: int, m: np.ndarray, inv: np.ndarray):
+        """rrt_scene_update_instances: new transforms for instances [first, first + len(m)), tree made anew on the device."""
+        m = np.ascontiguousarray(m, dtype=np.float64).reshape(-1, 16)
+        inv = np.ascontiguousarray(inv, dtype=np.float64).reshape(-1, 16)
+        capi.check(self.L.rrt_scene_update_instances(self.h, first, m.shape[0], _ptr(m), _ptr(inv)))
+        return self
+
     def export_tree(self) -> np.ndarray:
         """rrt_scene_export_tree: the committed aggregate (tree + records + tables) as one uint8 blob."""
         n = C.c_uint64()

@@ -757,24 +757,28 @@ __device__ __forceinline__ uint32_t ray_key(const AggView& A, const rrt_ray* r, 
     return (cell << 3) | oct;
 }
 
+// (grid-stride: the wavefront renderer launches these for a queue's CAPACITY while the live count sits on the device;
+// a grid of a few CTAs per SM walks whatever is there instead of tens of thousands of CTAs that find nothing)
 __global__ void __launch_bounds__(256) sort_count_kernel(AggView A, uint64_t n, const rrt_ray* __restrict__ rays,
                                                           uint32_t* __restrict__ bins, uint32_t* __restrict__ key_out,
                                                           uint32_t* __restrict__ rank_out,
                                                           const uint32_t* __restrict__ n_dev, int bits) {
     if (n_dev) n = *n_dev;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
-    const uint32_t key = valid ? ray_key(A, rays + i, bits) : 0xFFFFFFFFu;
-    // one atomic per distinct key per warp
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
     const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (valid && (int)lane == leader) base = atomicAdd(bins + key, (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) {
-        key_out[i] = key;
-        rank_out[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? ray_key(A, rays + i, bits) : 0xFFFFFFFFu;
+        // one atomic per distinct key per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t first = 0;
+        if (valid && (int)lane == leader) first = atomicAdd(bins + key, (uint32_t)__popc(peers));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (valid) {
+            key_out[i] = key;
+            rank_out[i] = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        }
     }
 }
 
@@ -866,10 +870,10 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t n, const uin
                                                             const uint32_t* __restrict__ n_dev) {
     if (n_dev) n = *n_dev;
     if (*use_perm == 0u) return;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = key[i];
-    perm[bins[k] + block_sums[k / kScanBlock] + rank[i]] = (uint32_t)i;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = key[i];
+        perm[bins[k] + block_sums[k / kScanBlock] + rank[i]] = (uint32_t)i;
+    }
 }
 
 inline float round_down(double v) {
@@ -1534,7 +1538,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
         while (bits > 4 && (1ull << (3 * bits)) > 2 * n) --bits;
         const uint32_t nbins = (1u << (3 * bits)) * (view_.sort_mode == 0 ? 1u : 8u);
         RRT_CUDA(cudaMemsetAsync(w.d_bins, 0, (size_t)nbins * sizeof(uint32_t), s));
-        const unsigned sb = (unsigned)((n + 255) / 256);
+        const unsigned sb = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)w.n_sms * 16u);
         sort_count_kernel<<<sb, 256, 0, s>>>(view_, n, d_rays, w.d_bins, w.d_key, w.d_rank, n_dev, bits);
         scan_block_kernel<<<nbins / kScanBlock, kScanBlock, 0, s>>>(w.d_bins, nbins, w.d_block_sums, small + 2);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.d_block_sums, nbins / kScanBlock, small + 2, n, small + 3, n_dev);

@@ -10,8 +10,6 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <vector>
 
 #include "bvh_lbvh.hpp"
@@ -89,6 +87,146 @@ __global__ void __launch_bounds__(256) flag_kernel(uint32_t n_internal, const Ra
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_internal) return;
     keep[i] = (nodes[i].last - nodes[i].first + 1u > max_leaf) ? 1u : 0u;
+}
+
+// ---- exclusive prefix sum of uint32 (any length): 1024-element blocks, block sums scanned recursively -------------------
+constexpr int kScanTile = 1024;
+__global__ void __launch_bounds__(kScanTile) scan_tiles_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                                uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * kScanTile + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if ((int)lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, off);
+            if ((int)lane >= off) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t incl = x + (warp > 0 ? warp_sums[warp - 1] : 0u);
+    if (i < n) out[i] = incl - v;
+    if (tile_sums != nullptr && threadIdx.x == kScanTile - 1) tile_sums[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(kScanTile) scan_add_kernel(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_offsets) {
+    const uint32_t i = blockIdx.x * kScanTile + threadIdx.x;
+    if (i < n) out[i] += tile_offsets[blockIdx.x];
+}
+// scratch: at least scan_scratch_words(n) uint32
+size_t scan_scratch_words(size_t n) {
+    size_t total = 0;
+    while (n > (size_t)kScanTile) {
+        n = (n + kScanTile - 1) / kScanTile;
+        total += n;
+    }
+    return total + 1;
+}
+void exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint32_t n, uint32_t* d_scratch, cudaStream_t s) {
+    if (n == 0) return;
+    const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles == 1) {
+        scan_tiles_kernel<<<1, kScanTile, 0, s>>>(d_in, d_out, n, nullptr);
+        return;
+    }
+    scan_tiles_kernel<<<tiles, kScanTile, 0, s>>>(d_in, d_out, n, d_scratch);
+    exclusive_scan_u32(d_scratch, d_scratch, tiles, d_scratch + tiles, s);  // in place: a tile reads before it writes
+    scan_add_kernel<<<tiles, kScanTile, 0, s>>>(d_out, n, d_scratch);
+}
+
+// ---- stable LSD radix sort of (63-bit key, uint32 value) pairs, 8 bits per pass ---------------------------------------------
+// A pass: (1) per-tile digit histograms, stored digit-major so that ONE exclusive scan over [256][tiles] gives every
+// (digit, tile) its output base; (2) a stable scatter.  A tile is 2048 pairs; warp w of its CTA owns the 256 consecutive
+// pairs [256 w, 256 w + 256) and walks them in 8 rounds of 32, so "earlier in the input" is (warp, round, lane) order:
+// the rank of a pair is base[digit][tile] + pairs with that digit in lower warps + in this warp's earlier rounds + in
+// lower lanes of this round (__match_any_sync).
+constexpr int kSortTile = 2048, kSortWarps = 8;
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                          uint32_t* __restrict__ hist, uint32_t n_tiles) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortTile / 256; ++r) {
+        const uint32_t i = base + r * 256 + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                             uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                             int shift, const uint32_t* __restrict__ offsets, uint32_t n_tiles) {
+    __shared__ uint32_t wc[kSortWarps][256];  // per-warp digit counts, then each warp's running base
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kSortWarps * 256; k += 256) (&wc[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t warp_base = blockIdx.x * kSortTile + warp * 256;
+    uint64_t key[8];
+    uint32_t val[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = warp_base + r * 32 + lane;
+        key[r] = i < n ? keys_in[i] : ~0ull;
+        val[r] = i < n ? vals_in[i] : 0u;
+        if (i < n) atomicAdd(&wc[warp][(uint32_t)(key[r] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    {   // thread d: exclusive sum over the warps for digit d, on top of the tile's global base
+        const uint32_t d = threadIdx.x;
+        uint32_t run = offsets[(size_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = wc[w][d];
+            wc[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = warp_base + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? (uint32_t)(key[r] >> shift) & 255u : 256u + lane;  // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid) {
+            const uint32_t pos = wc[warp][d] + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+        __syncwarp();
+        if (valid && (int)lane == __ffs(peers) - 1) wc[warp][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+    }
+}
+// Sorts (keys, vals) by the low `bits` bits; the result lands in (keys_b, vals_b) when the number of passes is odd, else
+// in (keys_a, vals_a): the return value says which (0 = a, 1 = b).  d_hist: 256 * tiles words, d_scratch: scan_scratch_words(256 * tiles).
+int radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int bits, uint32_t* d_hist,
+                     uint32_t* d_scratch, cudaStream_t s) {
+    const uint32_t tiles = (n + kSortTile - 1) / kSortTile;
+    int where = 0;
+    for (int shift = 0; shift < bits; shift += 8) {
+        uint64_t* kin = where ? keys_b : keys_a;
+        uint64_t* kout = where ? keys_a : keys_b;
+        uint32_t* vin = where ? vals_b : vals_a;
+        uint32_t* vout = where ? vals_a : vals_b;
+        radix_hist_kernel<<<tiles, 256, 0, s>>>(kin, n, shift, d_hist, tiles);
+        exclusive_scan_u32(d_hist, d_hist, 256u * tiles, d_scratch, s);
+        radix_scatter_kernel<<<tiles, 256, 0, s>>>(kin, vin, kout, vout, n, shift, d_hist, tiles);
+        where ^= 1;
+    }
+    return where;
 }
 
 template <bool QUANT>
@@ -227,18 +365,21 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     LB_TRY(cudaEventRecord(e0, 0));
     const unsigned gb = (n + 255) / 256, gi = (ni + 255) / 256;
     keys_kernel<<<gb, 256>>>(n, d_boxes, fr, d_keys, d_vals);
-    size_t tmp_sort = 0, tmp_scan = 0;
-    LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, 63));
-    LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_keep, d_new, (int)ni));
-    const size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
-    LB_TRY(cudaMalloc(&d_tmp, tmp_bytes));
-    size_t tb = tmp_bytes;
-    LB_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys_sorted, d_vals, d_order, (int)n, 0, 63));
+    const uint32_t sort_tiles = (n + kSortTile - 1) / kSortTile;
+    const size_t hist_words = 256 * (size_t)sort_tiles;
+    const size_t scratch_words = std::max(scan_scratch_words(hist_words), scan_scratch_words(ni));
+    LB_TRY(cudaMalloc(&d_tmp, (hist_words + scratch_words) * sizeof(uint32_t)));
+    uint32_t* d_hist = static_cast<uint32_t*>(d_tmp);
+    uint32_t* d_scan_scratch = d_hist + hist_words;
+    // 63-bit Morton keys: eight 8-bit passes (an even number: the sorted pairs end where they started, then swap names)
+    if (radix_sort_pairs(d_keys, d_vals, d_keys_sorted, d_order, n, 64, d_hist, d_scan_scratch, 0) == 0) {
+        std::swap(d_keys, d_keys_sorted);
+        std::swap(d_vals, d_order);
+    }
     hierarchy_kernel<<<gi, 256>>>(n, d_keys_sorted, d_nodes, d_pnode, d_pleaf);
     refit_kernel<<<gb, 256>>>(n, d_boxes, d_order, d_nodes, d_pnode, d_pleaf, d_leaf_box, d_node_box, d_visits);
     flag_kernel<<<gi, 256>>>(ni, d_nodes, max_leaf, d_keep);
-    tb = tmp_bytes;
-    LB_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_keep, d_new, (int)ni));
+    exclusive_scan_u32(d_keep, d_new, ni, d_scan_scratch, 0);
     uint32_t last_keep = 0, last_new = 0;
     LB_TRY(cudaMemcpy(&last_keep, d_keep + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
     LB_TRY(cudaMemcpy(&last_new, d_new + (ni - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));

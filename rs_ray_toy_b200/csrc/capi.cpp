@@ -103,6 +103,8 @@ struct rrt_scene {
     std::unique_ptr<rrt::RayTracer> agg;  // DeviceAggregate (Tier F) or LiteralAggregate (Tier L)
     bool committed = false;
     uint32_t build_flags = 0;
+    uint32_t max_prims_in_node = 4;
+    std::atomic<int> live_renders{0};  // integrators made over this scene (they hold its aggregate and shading tables)
 };
 
 struct rrt_render {
@@ -327,7 +329,37 @@ int rrt_scene_commit(rrt_scene* scene, uint32_t max_prims_in_node, uint32_t buil
         return fail(RRT_ERR_INVALID, e.what());
     }
     scene->build_flags = build_flags;
+    scene->max_prims_in_node = max_prims_in_node;
     scene->committed = true;
+    return RRT_OK;
+}
+
+int rrt_scene_update_instances(rrt_scene* scene, uint32_t first_instance, uint32_t n, const double* instance_m,
+                               const double* instance_minv) {
+    if (!scene || (n && (!instance_m || !instance_minv))) return fail(RRT_ERR_INVALID, "rrt_scene_update_instances: null argument");
+    if (!scene->committed) return fail(RRT_ERR_INVALID, "rrt_scene_update_instances: scene is not committed");
+    if (scene->build_flags == RRT_BUILD_LITERAL)
+        return fail(RRT_ERR_UNSUPPORTED, "rrt_scene_update_instances: the literal tier rebuilds the reference's HLBVH on the host; commit a new scene");
+    if (scene->live_renders.load() != 0)
+        return fail(RRT_ERR_INVALID, "rrt_scene_update_instances: destroy the integrators made over this scene first (they hold its tables)");
+    if ((uint64_t)first_instance + n > scene->host.instances.size())
+        return fail(RRT_ERR_INVALID, "rrt_scene_update_instances: instance range out of bounds");
+    try {
+        for (uint32_t i = 0; i < n; ++i)
+            scene->host.instances[first_instance + i] = xf_from(instance_m + 16 * (size_t)i, instance_minv + 16 * (size_t)i);
+        // The tree over the moved primitives is made anew on the device: keys, sort, hierarchy and boxes take a few
+        // milliseconds there — a topology-preserving refit would save none of the part that costs, the
+        // host-side re-bake of the moved primitives' records.
+        std::unique_ptr<rrt::DeviceAggregate> fresh(new rrt::DeviceAggregate());
+        std::string err;
+        CAPI_CUDA(cudaSetDevice(scene->ctx->device));
+        int rc = fresh->build(scene->ctx->device, scene->host, scene->max_prims_in_node, &err, true);
+        if (rc != RRT_OK) return fail(rc, err);
+        scene->agg = std::move(fresh);
+        scene->build_flags = RRT_BUILD_DEVICE_LBVH;
+    } catch (const std::exception& e) {
+        return fail(RRT_ERR_INVALID, e.what());
+    }
     return RRT_OK;
 }
 
@@ -637,13 +669,17 @@ int rrt_render_create(rrt_scene* scene, const rrt_render_desc* desc, rrt_render*
                                 scene->textures, scene->material_slots, wb, *desc, &err, &scene->extras);
         if (rc != RRT_OK) return fail(rc, err);
         scene->ctx->launches.fetch_add(r->renderer.stats().launches, std::memory_order_relaxed);
+        scene->live_renders.fetch_add(1);
         *out = r.release();
     } catch (const std::exception& e) {
         return fail(RRT_ERR_INVALID, e.what());
     }
     return RRT_OK;
 }
-void rrt_render_destroy(rrt_render* render) { delete render; }
+void rrt_render_destroy(rrt_render* render) {
+    if (render && render->scene) render->scene->live_renders.fetch_sub(1);
+    delete render;
+}
 
 int rrt_scene_load_json(rrt_ctx* ctx, const char* path, const char* overrides_json, uint64_t seed, rrt_scene** scene,
                         rrt_render** render) {

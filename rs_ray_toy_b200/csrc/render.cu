@@ -701,50 +701,54 @@ __device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* pe
 }
 
 // ---- shade order: a counting sort of the round's hits by (miss | material kind) -----------------------------
+// (grid-stride over the live count, like the ray sort: a few CTAs per SM instead of a grid sized for the chunk)
 __global__ void __launch_bounds__(256) shade_bin_kernel(ShadeScene sc, Queues q, int cur) {
     const uint32_t n = q.counters[cur];
-    if (blockIdx.x * 256u >= n) return;
     __shared__ uint32_t h[kShadeBins];
     if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    uint32_t key = 0xFFu;
-    if (i < n) {
-        const uint32_t prim = q.hits[i].prim_id;
-        key = 0;
-        if (prim != RRT_NO_HIT) {
-            const uint32_t kind = sc.materials[sc.prims[prim].material].kind;
-            key = 1u + (kind < (uint32_t)kShadeBins - 2u ? kind : (uint32_t)kShadeBins - 2u);
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t key = 0xFFu;
+        if (i < n) {
+            const uint32_t prim = q.hits[i].prim_id;
+            key = 0;
+            if (prim != RRT_NO_HIT) {
+                const uint32_t kind = sc.materials[sc.prims[prim].material].kind;
+                key = 1u + (kind < (uint32_t)kShadeBins - 2u ? kind : (uint32_t)kShadeBins - 2u);
+            }
+            q.shade_key[i] = (uint8_t)key;
         }
-        q.shade_key[i] = (uint8_t)key;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xFFu && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[key], (uint32_t)__popc(peers));
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key != 0xFFu && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[key], (uint32_t)__popc(peers));
     __syncthreads();
     if (threadIdx.x < kShadeBins && h[threadIdx.x]) atomicAdd(q.counters + 16 + threadIdx.x, h[threadIdx.x]);
 }
 __global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
     const uint32_t n = q.counters[cur];
-    if (blockIdx.x * 256u >= n) return;
-    __shared__ uint32_t h[kShadeBins], base[kShadeBins];
-    if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t key = i < n ? (uint32_t)q.shade_key[i] : 0xFFu;
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    __shared__ uint32_t h[kShadeBins], base_of[kShadeBins];
     const unsigned lane = threadIdx.x & 31u;
-    const int leader = __ffs(peers) - 1;
-    uint32_t rank = 0;
-    if (key != 0xFFu && (int)lane == leader) rank = atomicAdd(&h[key], (uint32_t)__popc(peers));
-    rank = __shfl_sync(0xffffffffu, rank, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-    __syncthreads();
-    if (threadIdx.x < kShadeBins) {
-        uint32_t before = 0;
-        for (int b = 0; b < (int)threadIdx.x; ++b) before += q.counters[16 + b];
-        base[threadIdx.x] = before + (h[threadIdx.x] ? atomicAdd(q.counters + 24 + threadIdx.x, h[threadIdx.x]) : 0u);
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        if (threadIdx.x < kShadeBins) h[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t key = i < n ? (uint32_t)q.shade_key[i] : 0xFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t rank = 0;
+        if (key != 0xFFu && (int)lane == leader) rank = atomicAdd(&h[key], (uint32_t)__popc(peers));
+        rank = __shfl_sync(0xffffffffu, rank, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x < kShadeBins) {
+            uint32_t before = 0;
+            for (int b = 0; b < (int)threadIdx.x; ++b) before += q.counters[16 + b];
+            base_of[threadIdx.x] = before + (h[threadIdx.x] ? atomicAdd(q.counters + 24 + threadIdx.x, h[threadIdx.x]) : 0u);
+        }
+        __syncthreads();
+        if (key != 0xFFu) q.shade_perm[base_of[key] + rank] = i;
+        __syncthreads();
     }
-    __syncthreads();
-    if (key != 0xFFu) q.shade_perm[base[key] + rank] = i;
 }
 
 #ifndef RRT_SHADE_MINBLOCKS
@@ -1309,17 +1313,18 @@ __global__ void __launch_bounds__(128, 2) whitted_kernel(ShadeScene sc, HaltonTa
 // Unoccluded light samples join their path's radiance (`l += ld`, path.rs:121 / directlighting.rs:113)
 // `shared_paths`: several light samples may belong to one path (UniformSampleAll): they are added with atomics.
 __global__ void __launch_bounds__(256) resolve_kernel(Path* __restrict__ paths, Queues q, int shared_paths) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.counters[2]) return;
-    if (q.sh_occluded[i]) return;
-    Path& p = paths[q.sh_path[i]];
-    const Rgb c = q.sh_contrib[i];
-    if (shared_paths) {
-        atomicAdd(&p.L.r, c.r);
-        atomicAdd(&p.L.g, c.g);
-        atomicAdd(&p.L.b, c.b);
-    } else {
-        p.L = p.L + c;
+    const uint32_t n = q.counters[2];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (q.sh_occluded[i]) continue;
+        Path& p = paths[q.sh_path[i]];
+        const Rgb c = q.sh_contrib[i];
+        if (shared_paths) {
+            atomicAdd(&p.L.r, c.r);
+            atomicAdd(&p.L.g, c.g);
+            atomicAdd(&p.L.b, c.b);
+        } else {
+            p.L = p.L + c;
+        }
     }
 }
 
@@ -2313,6 +2318,7 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
                                                               I.d_diffs, I.diff_scale, I.gen_mode == 1 ? 1 : 0);
         launches += 1;
         int cur = 0;
+        const unsigned small_grid = (unsigned)std::min<uint64_t>(((uint64_t)count * I.shadow_per_hit + 255) / 256, (uint64_t)I.sm_count * 16u);
         for (uint32_t r = 0; r < rounds; ++r) {
             int n = 0;
             int rc = I.agg->closest_hit_indirect(count, I.q.counters + cur, I.q.ext_rays[cur], I.q.hits, I.stream, err, &n);
@@ -2324,8 +2330,8 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
                 launches += 1;
             } else {
 #if RRT_SHADE_SORT
-            shade_bin_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.sc, I.q, cur);
-            shade_scatter_kernel<<<(count + 255) / 256, 256, 0, I.stream>>>(I.q, cur);
+            shade_bin_kernel<<<small_grid, 256, 0, I.stream>>>(I.sc, I.q, cur);
+            shade_scatter_kernel<<<small_grid, 256, 0, I.stream>>>(I.q, cur);
             launches += 2;
 #endif
             {
@@ -2340,7 +2346,7 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
                                          err, &n);
             if (rc != RRT_OK) return rc;
             launches += n;
-            resolve_kernel<<<(unsigned)(((uint64_t)count * I.shadow_per_hit + 255) / 256), 256, 0, I.stream>>>(
+            resolve_kernel<<<small_grid, 256, 0, I.stream>>>(
                 I.d_paths, I.q, (I.all_lights || I.whitted || I.env_mode) ? 1 : 0);
             advance_kernel<<<1, 1, 0, I.stream>>>(I.q, cur);
             launches += 2;

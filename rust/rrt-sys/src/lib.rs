@@ -103,6 +103,7 @@ extern "C" {
                                 z_min: f64, z_max: f64, phi_max_deg: f64, material_id: u32, n_instances: u32,
                                 instance_m: *const f64, instance_minv: *const f64) -> c_int;
     pub fn rrt_scene_commit(scene: *mut rrt_scene, max_prims_in_node: u32, build_flags: u32) -> c_int;
+    pub fn rrt_scene_update_instances(scene: *mut rrt_scene, first_instance: u32, n: u32, instance_m: *const f64, instance_minv: *const f64) -> c_int;
     pub fn rrt_scene_num_prims(scene: *const rrt_scene, out: *mut u32) -> c_int;
     pub fn rrt_world_bound(scene: *const rrt_scene, out6: *mut f64) -> c_int;
     pub fn rrt_scene_export_tree(scene: *const rrt_scene, buffer: *mut c_void, capacity: u64, bytes: *mut u64) -> c_int;

@@ -580,3 +580,32 @@ def test_clipped_sphere_with_own_transform_is_refused(ctx):
     b.add_sphere(radius=1.0, z_min=-0.3, z_max=0.8, instances=(xf[0][None], xf[1][None]))
     b.commit(4)
     assert b.num_prims == 1
+
+
+def test_instance_update_answers_like_a_fresh_scene(ctx):
+    """rrt_scene_update_instances (dynamic scenes): instanced cubes and spheres are moved, the tree is
+    made anew on the device, and every ray is answered like the oracle's scene built over the new transforms; an
+    integrator made over the old scene blocks the update."""
+    from rs_ray_toy_b200 import capi
+    rng = np.random.default_rng(16)
+    rays = np.concatenate([rng.uniform(-12, 12, (80000, 3)), synth.random_unit_vectors(80000, rng), np.full((80000, 1), np.inf)], axis=1)
+    m0, inv0 = scenes.cube_instances(300, extent=8.0)
+    agg = scenes.gpu_cubes(ctx, m0, inv0)
+    before = agg.intersect(rays)
+    m1, inv1 = scenes.cube_instances(300, extent=8.0, seed=991)
+    k = 120                                   # the first 120 cubes move, the rest stay
+    agg.update_instances(0, m1[:k], inv1[:k])
+    m_new, inv_new = np.concatenate([m1[:k], m0[k:]]), np.concatenate([inv1[:k], inv0[k:]])
+    ref = scenes.oracle_cubes(m_new, inv_new).intersect(rays)
+    after = agg.intersect(rays)
+    _assert_closest(after, ref["prim"], ref["t"])
+    assert (after["prim_id"] != before["prim_id"]).mean() > 0.01
+    assert agg.build_info()["device_lbvh"]
+    with pytest.raises(capi.RrtError):        # out of range
+        agg.update_instances(290, m1[:20], inv1[:20])
+    ms, invs = scenes.sphere_instances(2000, extent=10.0)
+    sph = scenes.gpu_spheres(ctx, ms, invs)
+    ms2, invs2 = scenes.sphere_instances(2000, extent=10.0, seed=77)
+    sph.update_instances(0, ms2, invs2)
+    ref = scenes.oracle_spheres(ms2, invs2).intersect(rays)
+    _assert_closest(sph.intersect(rays), ref["prim"], ref["t"])
