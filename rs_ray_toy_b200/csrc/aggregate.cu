@@ -360,6 +360,12 @@ constexpr int32_t kNoLeaf = 0;         // leaf references are negative, so 0 mea
 #ifndef RRT_MINBLOCKS_Q
 #define RRT_MINBLOCKS_Q 8  // Node32 kernels: 64 registers (measured best, profiles/r1_sweep8.txt)
 #endif
+#ifndef RRT_STAGE_TOP
+#define RRT_STAGE_TOP 0  // K > 0: the K topmost interior nodes (breadth-first) are copied to shared memory by every CTA and
+                         // read from there — north_star's "shared-memory staging of top-level nodes".  Measured and not
+                         // adopted (profiles/r2_sweep_stage_top.txt): those nodes are the hottest lines of L1 already.
+#endif
+constexpr int kStageTop = RRT_STAGE_TOP;
 constexpr int kRefill = RRT_REFILL;
 constexpr int kScreenRows = RRT_PRETEST ? 9 : 0;  // ScreenRay rows behind the traversal stack (tri_screen.h)
 
@@ -404,6 +410,16 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
     // the fp32 screen's per-ray constants (ScreenRay) live behind the stack, [row][thread] as well: nine floats that
     // are written once per ray and read once per screened record — registers are what this kernel is short of
     float* const my_screen = reinterpret_cast<float*>(sstack + stack_levels * kBlock * (RRT_STALE_SKIP ? 2 : 1)) + threadIdx.x;
+#if RRT_STAGE_TOP
+    // the K topmost nodes (indices 0 .. K-1 after the host's breadth-first relabelling), one copy per CTA
+    uint4* const s_top = reinterpret_cast<uint4*>(sstack + (stack_levels * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock);
+    if (QUANT) {
+        const uint4* src = static_cast<const uint4*>(A.nodes);
+        const int n_stage = A.n_staged;
+        for (int k = threadIdx.x; k < 2 * n_stage; k += kBlock) s_top[k] = __ldg(src + k);
+        __syncthreads();
+    }
+#endif
     int sp = 1;
     int32_t node = kDone;     // >= 0 interior index, < 0 leaf reference, kDone = nothing left
     int32_t leaf = kNoLeaf;   // parked leaf reference (head of the queue)
@@ -534,7 +550,18 @@ __global__ void __launch_bounds__(kBlock, QUANT ? RRT_MINBLOCKS_Q : RRT_MINBLOCK
                 if (QUANT) {
                     // one 256-bit load: 12 quantised planes + two child references; a plane becomes the float
                     // 1 + q / 32768 with one byte permute (device_layout.h)
+#if RRT_STAGE_TOP
+                    F8 v;
+                    if (node < A.n_staged) {
+                        const uint4 lo = s_top[2 * node], hi = s_top[2 * node + 1];
+                        v = F8{__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w),
+                               __uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
+                    } else {
+                        v = ldg256(reinterpret_cast<const char*>(A.nodes) + (size_t)node * sizeof(Node32));
+                    }
+#else
                     const F8 v = ldg256(reinterpret_cast<const char*>(A.nodes) + (size_t)node * sizeof(Node32));
+#endif
                     const uint32_t w0 = __float_as_uint(v.a), w1 = __float_as_uint(v.b), w2 = __float_as_uint(v.c);
                     const uint32_t w3 = __float_as_uint(v.d), w4 = __float_as_uint(v.e), w5 = __float_as_uint(v.f);
                     ch_x = __float_as_int(v.g);
@@ -1252,6 +1279,32 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         }
     }
 
+    // ---- RRT_STAGE_TOP experiment: the K topmost interior nodes first, in breadth-first order ----
+    int n_staged = 0;
+    if (kStageTop > 0 && quantise && !on_device_ok && nodes.size() > (size_t)kStageTop) {
+        std::vector<uint32_t> top;
+        top.push_back(0);
+        for (size_t h = 0; h < top.size() && top.size() < (size_t)kStageTop; ++h) {
+            const Node64& nd = nodes[top[h]];
+            if (nd.child0 >= 0 && top.size() < (size_t)kStageTop) top.push_back((uint32_t)nd.child0);
+            if (nd.child1 >= 0 && top.size() < (size_t)kStageTop) top.push_back((uint32_t)nd.child1);
+        }
+        std::vector<int32_t> new_index(nodes.size(), -1);
+        for (size_t k = 0; k < top.size(); ++k) new_index[top[k]] = (int32_t)k;
+        int32_t next = (int32_t)top.size();
+        for (size_t i = 0; i < nodes.size(); ++i)
+            if (new_index[i] < 0) new_index[i] = next++;
+        std::vector<Node64> moved(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            Node64 nd = nodes[i];
+            if (nd.child0 >= 0) nd.child0 = new_index[nd.child0];
+            if (nd.child1 >= 0) nd.child1 = new_index[nd.child1];
+            moved[new_index[i]] = nd;
+        }
+        nodes.swap(moved);
+        n_staged = (int)top.size();
+    }
+    view_.n_staged = n_staged;
     // ---- quantise the host tree: Node64 (fp32 planes) -> Node32 (15-bit planes on the grid) ----
     std::vector<Node32> nodes32;
     if (quantise && !on_device_ok) {
@@ -1368,7 +1421,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
 // the only shared memory is the traversal stack (one entry per tree level + the marker, [+ the screen's rows]);
 // everything else of the 256 KB stays L1
 void DeviceAggregate::configure_kernels(bool quantise) {
-    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t);
+    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t) + (size_t)kStageTop * sizeof(Node32);
     int carve = (int)(((quantise ? RRT_MINBLOCKS_Q : RRT_MINBLOCKS) * smem * 100 + 227 * 1024 - 1) / (227 * 1024)) + 2;
     if (carve > 100) carve = 100;
     for (auto fn : {(const void*)trace_kernel<false, false, false, false>, (const void*)trace_kernel<false, true, false, false>,
@@ -1551,7 +1604,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
                                          : (view_.wide ? trace_kernel<ANY, true, false, true> : trace_kernel<ANY, false, false, true>))
                       : (view_.quantised ? (view_.wide ? trace_kernel<ANY, true, true, false> : trace_kernel<ANY, false, true, false>)
                                          : (view_.wide ? trace_kernel<ANY, true, false, false> : trace_kernel<ANY, false, false, false>));
-    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t);
+    const size_t smem = ((size_t)stack_levels_ * (RRT_STALE_SKIP ? 2 : 1) + kScreenRows) * kBlock * sizeof(int32_t) + (size_t)kStageTop * sizeof(Node32);
     int per_sm = 0;
     RRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem));
     if (per_sm < 1) per_sm = 1;

@@ -34,6 +34,7 @@ struct AggView {
     int32_t wide;        // 1 => PrimRec96
     int32_t has_spheres;
     int32_t sort_mode;   // ray-queue key: 0 cell, 1 cell|octant, 2 octant|cell
+    int32_t n_staged;    // RRT_STAGE_TOP builds: nodes [0, n_staged) are the topmost ones in breadth-first order
 };
 
 // What the C ABI and the renderer need from an aggregate: batches of closest-hit / any-hit
