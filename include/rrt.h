@@ -152,9 +152,14 @@ int rrt_intersect_p(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, uin
  * as a wavefront of generate / extend / shade / shadow / accumulate kernels.                    */
 
 /* Material::compute_scattering_functions inputs with constant-valued textures
- * (material/{matte,plastic,metal,mirror,glass}.rs; make_materials, renderprocess.rs:664-871).   */
+ * (material/{matte,plastic,metal,mirror,glass,translucent,disney,debug_material}.rs; make_materials,
+ * renderprocess.rs:664-871).  MixMaterial has no record: the reference panics while loading one (Q25).            */
 typedef enum rrt_material_kind {
-    RRT_MAT_MATTE = 0, RRT_MAT_PLASTIC = 1, RRT_MAT_METAL = 2, RRT_MAT_MIRROR = 3, RRT_MAT_GLASS = 4
+    RRT_MAT_MATTE = 0, RRT_MAT_PLASTIC = 1, RRT_MAT_METAL = 2, RRT_MAT_MIRROR = 3, RRT_MAT_GLASS = 4,
+    RRT_MAT_TRANSLUCENT = 5, /* translucent.rs: kd, ks, roughness; reflect = kr, transmit = kt; up to four lobes     */
+    RRT_MAT_DISNEY = 6,      /* disney.rs: color = kd, roughness, eta and the Disney block below; up to eight lobes.
+                              * thin = 0 with a non-black scatter_distance asks for the BSSRDF: refused             */
+    RRT_MAT_DEBUG = 7        /* debug_material.rs: no parameters                                                    */
 } rrt_material_kind;
 typedef struct rrt_material {
     uint32_t kind;
@@ -165,7 +170,13 @@ typedef struct rrt_material {
     double roughness;                 /* Plastic / Metal                                        */
     double u_roughness, v_roughness;  /* Metal: < 0 = None (use roughness); Glass: values; non-zero = rough
                                        * glass, MicrofacetReflection + MicrofacetTransmission (glass.rs:77-108) */
-    double eta;                       /* Glass index                                            */
+    double eta;                       /* Glass / Disney index                                   */
+    /* DisneyMaterial (disney.rs:464-483; the loader's defaults, renderprocess.rs:810-836, are 0 but for
+     * sheen_tint 0.5, clearcoat_gloss 1, diff_trans 1, roughness 0.5, eta 1.5, color 0.5)                          */
+    double metallic, specular_tint, anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss, spec_trans,
+           flatness, diff_trans;
+    double scatter_distance[3];
+    uint32_t thin, pad;
 } rrt_material;
 
 /* Textures a material parameter can name (make_textures, renderprocess.rs:298-515): the scene's float and rgb
@@ -205,6 +216,10 @@ typedef enum rrt_material_slot {
     RRT_SLOT_KD = 0, RRT_SLOT_KS, RRT_SLOT_KR, RRT_SLOT_KT, RRT_SLOT_METAL_ETA, RRT_SLOT_METAL_K, RRT_SLOT_SIGMA,
     RRT_SLOT_ROUGHNESS, RRT_SLOT_U_ROUGHNESS, RRT_SLOT_V_ROUGHNESS, RRT_SLOT_ETA,
     RRT_SLOT_BUMP_MAP, /* Material::bump (material/mod.rs:22-65): a float texture displaces the shading frame         */
+    /* DisneyMaterial's scalars in rrt_material order, then scatter_distance (color = KD, roughness, eta as above)   */
+    RRT_SLOT_METALLIC, RRT_SLOT_SPECULAR_TINT, RRT_SLOT_ANISOTROPIC, RRT_SLOT_SHEEN, RRT_SLOT_SHEEN_TINT,
+    RRT_SLOT_CLEARCOAT, RRT_SLOT_CLEARCOAT_GLOSS, RRT_SLOT_SPEC_TRANS, RRT_SLOT_FLATNESS, RRT_SLOT_DIFF_TRANS,
+    RRT_SLOT_SCATTER_DISTANCE,
     RRT_MATERIAL_SLOTS
 } rrt_material_slot;
 

@@ -455,14 +455,16 @@ uint64_t orc_raylog_take(double* out, uint64_t cap_records) {
     return n;
 }
 
-// Material table.  26 doubles per material:
+// Material table.  72 doubles per material (tests/oracle_scene.py material_row):
 //  0 kind (MaterialKind) | 1-3 kd | 4-6 ks | 7-9 kr | 10-12 kt | 13-15 metal eta | 16-18 metal k |
-//  19 sigma | 20 roughness | 21 u_roughness (<0 = None) | 22 v_roughness | 23 glass eta | 24 remap | 25 pad
+//  19 sigma | 20 roughness | 21 u_roughness (<0 = None) | 22 v_roughness | 23 glass eta | 24 remap | 25 pad |
+//  26-36 texture ids of those parameters | 37 bump map | 40-49 Disney metallic specular_tint anisotropic sheen sheen_tint
+//  clearcoat clearcoat_gloss spec_trans flatness diff_trans | 50-52 scatter_distance | 53 thin | 54-64 their texture ids
 void orc_set_materials(void* sp, uint32_t n, const double* m) {
     RenderSetup& rs = setup_of(sp);
     rs.materials.clear();
     for (uint32_t i = 0; i < n; ++i) {
-        const double* a = m + 40 * (size_t)i;
+        const double* a = m + 72 * (size_t)i;
         Material mat;
         mat.kind = (uint32_t)a[0];
         mat.kd = Rgb(a[1], a[2], a[3]);
@@ -479,6 +481,12 @@ void orc_set_materials(void* sp, uint32_t n, const double* m) {
         mat.remap_roughness = a[24] != 0.0;
         for (int k = 0; k < 11; ++k) mat.tex[k] = (int32_t)a[26 + k];
         mat.bump_tex = (int32_t)a[37];
+        double* ds[10] = {&mat.metallic, &mat.specular_tint, &mat.anisotropic, &mat.sheen, &mat.sheen_tint, &mat.clearcoat,
+                          &mat.clearcoat_gloss, &mat.spec_trans, &mat.flatness, &mat.diff_trans};
+        for (int k = 0; k < 10; ++k) *ds[k] = a[40 + k];
+        mat.scatter_distance = Rgb(a[50], a[51], a[52]);
+        mat.thin = a[53] != 0.0;
+        for (int k = 0; k < 11; ++k) mat.dtex[k] = (int32_t)a[54 + k];
         rs.materials.push_back(mat);
     }
 }
@@ -781,6 +789,9 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
             }
             job.scene.lights.push_back(lt);
         }
+        for (const Material& m : rs.materials)  // checked here: the worker threads have nobody to catch for them
+            if (m.kind == MAT_DISNEY && !m.thin && (m.dtex[10] >= 0 || !m.scatter_distance.is_black()))
+                throw std::runtime_error("oracle: DisneyMaterial with scatter_distance builds a BSSRDF (outside the restated path)");
         for (size_t i = 0; i < rs.inf_specs.size(); ++i) {  // Scene::infinite_lights: only Light::le is ever asked of them
             Light lt = rs.inf_specs[i];
             if (lt.kind == LIGHT_INFINITE) lt.inf = make_infinite(lt, rs.inf_xf[i]);

@@ -141,7 +141,11 @@ struct TrowbridgeReitz {
         return (-1.0 + std::sqrt(1.0 + a2t2)) / 2.0;
     }
     double g1(V3 w) const { return 1.0 / (1.0 + lambda(w)); }
-    double g(V3 wo, V3 wi) const { return 1.0 / (1.0 + lambda(wo) + lambda(wi)); }
+    bool separable_g = false;  // DisneyMicrofacetDistribution (disney.rs:329-360): g = g1(wo) * g1(wi)
+    double g(V3 wo, V3 wi) const {
+        if (separable_g) return g1(wo) * g1(wi);
+        return 1.0 / (1.0 + lambda(wo) + lambda(wi));
+    }
     double pdf(V3 wo, V3 wh) const { return d(wh) * g1(wo) * absdot(wo, wh) / abs_cos_theta(wo); }
     // microfacet.rs:270-313
     static void sample11(double cos_t, double u1, double u2, double* slope_x, double* slope_y) {
@@ -193,6 +197,29 @@ struct TrowbridgeReitz {
     }
 };
 
+// reflection.rs:13-30 and misc.rs:223-228 (lerp(t, a, b) = a * (1 - t) + b * t)
+inline double schlick_weight(double cos_theta_) {
+    double m = clamp_t(1.0 - cos_theta_, 0.0, 1.0);
+    return (m * m) * (m * m) * m;
+}
+inline double lerp_f(double t, double a, double b) { return a * (1.0 - t) + b * t; }
+inline Rgb lerp_rgb(double t, Rgb a, Rgb b) { return a * (1.0 - t) + b * t; }
+inline double fr_schlick(double r0, double cos_theta_) { return lerp_f(schlick_weight(cos_theta_), r0, 1.0); }
+inline Rgb fr_schlick_spectrum(Rgb r0, double cos_theta_) { return lerp_rgb(schlick_weight(cos_theta_), r0, Rgb(1.0)); }
+inline double schlick_r0_from_eta(double eta) {
+    double q = (eta - 1.0) / (eta + 1.0);
+    return q * q;
+}
+// material/disney.rs:20-31.  gtr1 divides by log10(alpha^2) where pbrt has the natural log: kept (Q36).
+inline double gtr1(double cos_theta_, double alpha) {
+    double alpha2 = alpha * alpha;
+    return (alpha2 - 1.0) / (PI * std::log10(alpha2) * (1.0 + (alpha2 - 1.0) * cos_theta_ * cos_theta_));
+}
+inline double smith_g_ggx(double cos_theta_, double alpha) {
+    double alpha2 = alpha * alpha, cos_theta2 = cos_theta_ * cos_theta_;
+    return 1.0 / (cos_theta_ + std::sqrt(alpha2 + cos_theta2 - alpha2 * cos_theta2));
+}
+
 // ---- BxDFs ---------------------------------------------------------------------------------------------
 enum : uint8_t {
     BXDF_REFLECTION = 1,
@@ -203,13 +230,17 @@ enum : uint8_t {
     BXDF_ALL = 31,
     BXDF_NONE = 0
 };
-enum FresnelKind : uint8_t { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
+enum FresnelKind : uint8_t { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2, FR_DISNEY = 3 };
 struct Fresnel {
     uint8_t kind = FR_NOOP;
-    double eta_i = 1, eta_t = 1;   // dielectric
+    double eta_i = 1, eta_t = 1;   // dielectric; DisneyFresnel: eta_t = eta
     Rgb c_eta_i, c_eta_t, c_k;     // conductor
+    Rgb r0;                        // DisneyFresnel (disney.rs:305-326)
+    double metallic = 0;
     // reflection.rs:603-619
     Rgb evaluate(double cos_i) const {
+        if (kind == FR_DISNEY)
+            return lerp_rgb(metallic, Rgb(fr_dielectric(cos_i, 1.0, eta_t)), fr_schlick_spectrum(r0, cos_i));
         if (kind == FR_DIELECTRIC) return Rgb(fr_dielectric(cos_i, eta_i, eta_t));
         if (kind == FR_CONDUCTOR) return fr_conductor(std::fabs(cos_i), c_eta_i, c_eta_t, c_k);
         return Rgb(1.0);
@@ -222,7 +253,15 @@ enum BxdfKind : uint8_t {
     BX_SPECULAR_REFL,
     BX_SPECULAR_TRANS,
     BX_FRESNEL_SPECULAR,
-    BX_MICROFACET_TRANS
+    BX_MICROFACET_TRANS,
+    BX_LAMBERT_TRANS,      // reflection.rs:843-898
+    BX_DISNEY_DIFFUSE,     // disney.rs:33-75
+    BX_DISNEY_FAKESS,      // disney.rs:77-131   (a = roughness)
+    BX_DISNEY_RETRO,       // disney.rs:133-180  (a = roughness)
+    BX_DISNEY_SHEEN,       // disney.rs:182-224
+    BX_DISNEY_CLEARCOAT,   // disney.rs:226-303  (a = weight, b = gloss)
+    BX_DEBUG_DIFFUSE,      // debug_material.rs:10-20
+    BX_DEBUG_SPECULAR      // debug_material.rs:22-32: a "specular" lobe that is cosine-sampled
 };
 struct Bxdf {
     uint8_t kind = BX_LAMBERTIAN;
@@ -240,6 +279,16 @@ struct Bxdf {
             case BX_SPECULAR_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
             case BX_SPECULAR_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
             case BX_MICROFACET_TRANS: return BXDF_GLOSSY | BXDF_TRANSMISSION;  // reflection.rs:1143-1145
+            case BX_LAMBERT_TRANS: return BXDF_DIFFUSE | BXDF_TRANSMISSION;
+            case BX_DISNEY_DIFFUSE:
+            case BX_DISNEY_FAKESS:
+            case BX_DISNEY_RETRO:
+            case BX_DISNEY_SHEEN:
+            case BX_DEBUG_DIFFUSE: return BXDF_DIFFUSE | BXDF_REFLECTION;
+            // disney.rs:300-302: neither REFLECTION nor TRANSMISSION, so Bsdf::f never adds this lobe; it is only
+            // ever seen through sample_f / pdf (Q37)
+            case BX_DISNEY_CLEARCOAT: return BXDF_DIFFUSE | BXDF_GLOSSY;
+            case BX_DEBUG_SPECULAR: return BXDF_SPECULAR | BXDF_REFLECTION;
             default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
         }
     }
@@ -290,13 +339,60 @@ struct Bxdf {
                        std::fabs(distrib.d(wh) * distrib.g(wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
                                  (cos_i * cos_o * sqrt_denom * sqrt_denom));
             }
+            case BX_LAMBERT_TRANS: return t / PI;
+            case BX_DEBUG_DIFFUSE: return Rgb(0.0, 1.0, 0.0);
+            case BX_DEBUG_SPECULAR: return Rgb(0.0, 0.0, 1.0);
+            case BX_DISNEY_DIFFUSE: {
+                double fo = schlick_weight(abs_cos_theta(wo)), fi = schlick_weight(abs_cos_theta(wi));
+                return r / PI * (1.0 - fo / 2.0) * (1.0 - fi / 2.0);
+            }
+            case BX_DISNEY_FAKESS:
+            case BX_DISNEY_RETRO:
+            case BX_DISNEY_SHEEN:
+            case BX_DISNEY_CLEARCOAT: {
+                V3 wh = wi + wo;
+                if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return Rgb();
+                wh = normalize_vec(wh);
+                if (kind == BX_DISNEY_CLEARCOAT) {
+                    double dr = gtr1(abs_cos_theta(wh), b);
+                    double fr = fr_schlick(0.04, dot(wo, wh));
+                    double gr = smith_g_ggx(abs_cos_theta(wo), 0.25) * smith_g_ggx(abs_cos_theta(wi), 0.25);
+                    return Rgb(a * gr * fr * dr / 4.0);
+                }
+                double cos_theta_d = dot(wi, wh);
+                if (kind == BX_DISNEY_SHEEN) return r * schlick_weight(cos_theta_d);
+                double fo = schlick_weight(abs_cos_theta(wo)), fi = schlick_weight(abs_cos_theta(wi));
+                if (kind == BX_DISNEY_RETRO) {
+                    double r_r = 2.0 * a * cos_theta_d * cos_theta_d;
+                    return r / PI * r_r * (fo + fi + fo * fi * (r_r - 1.0));
+                }
+                double fss_90 = cos_theta_d * cos_theta_d * a;
+                double fss = lerp_f(fo, 1.0, fss_90) * lerp_f(fi, 1.0, fss_90);
+                double ss = 1.25 * (fss * (1.0 / (abs_cos_theta(wo) + abs_cos_theta(wi)) - 0.5) + 0.5);
+                return r / PI * ss;
+            }
             default: return Rgb();
         }
     }
     double pdf(V3 wo, V3 wi) const {
         switch (kind) {
             case BX_LAMBERTIAN:
+            case BX_DISNEY_DIFFUSE:
+            case BX_DISNEY_FAKESS:
+            case BX_DISNEY_RETRO:
+            case BX_DISNEY_SHEEN:
+            case BX_DEBUG_DIFFUSE:
+            case BX_DEBUG_SPECULAR:
             case BX_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / PI : 0.0;  // reflection.rs:480-486
+            case BX_LAMBERT_TRANS: return !same_hemisphere(wo, wi) ? abs_cos_theta(wi) / PI : 0.0;
+            case BX_DISNEY_CLEARCOAT: {  // disney.rs:283-299
+                if (!same_hemisphere(wo, wi)) return 0.0;
+                V3 wh = wi + wo;
+                if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return 0.0;
+                wh = normalize_vec(wh);
+                double dr = gtr1(abs_cos_theta(wh), b);
+                return dr * abs_cos_theta(wh) / (4.0 * dot(wo, wh));
+            }
             case BX_MICROFACET_REFL: {
                 if (!same_hemisphere(wo, wi)) return 0.0;
                 V3 wh = normalize_vec(wo + wi);
@@ -317,9 +413,34 @@ struct Bxdf {
     Rgb sample_f(V3 wo, V3* wi, P2 u, double* pdf, uint8_t* sampled_type) const {
         switch (kind) {
             case BX_LAMBERTIAN:
+            case BX_DISNEY_DIFFUSE:
+            case BX_DISNEY_FAKESS:
+            case BX_DISNEY_RETRO:
+            case BX_DISNEY_SHEEN:
+            case BX_DEBUG_DIFFUSE:
+            case BX_DEBUG_SPECULAR:
             case BX_OREN_NAYAR: {  // reflection.rs:428-443
                 *wi = cosine_sample_hemisphere(u);
                 if (wo.z < 0.0) wi->z *= -1.0;
+                *pdf = this->pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case BX_LAMBERT_TRANS: {  // reflection.rs:857-871
+                *wi = cosine_sample_hemisphere(u);
+                if (wo.z > 0.0) wi->z *= -1.0;
+                *pdf = this->pdf(wo, *wi);
+                return f(wo, *wi);
+            }
+            case BX_DISNEY_CLEARCOAT: {  // disney.rs:254-282; the sqrt covers the denominator only (Q36)
+                if (wo.z == 0.0) return Rgb();
+                double alpha2 = b * b;
+                double cos_t = (1.0 - std::pow(alpha2, 1.0 - u.x)) / std::sqrt(rmax(1.0 - alpha2, 0.0));
+                double sin_t = std::sqrt(rmax(1.0 - cos_t * cos_t, 0.0));
+                double phi = 2.0 * PI * u.y;
+                V3 wh(sin_t * std::cos(phi), sin_t * std::sin(phi), cos_t);
+                if (!same_hemisphere(wo, wh)) wh = -wh;
+                *wi = reflect(wo, wh);
+                if (!same_hemisphere(wo, *wi)) return Rgb();
                 *pdf = this->pdf(wo, *wi);
                 return f(wo, *wi);
             }
@@ -475,7 +596,13 @@ namespace orc {
 
 
 // ---- materials (material/*.rs) with constant-valued parameters -------------------------------------
-enum MaterialKind : uint32_t { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4, MAT_NONE = 5 };
+enum MaterialKind : uint32_t {
+    MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_MIRROR = 3, MAT_GLASS = 4,
+    MAT_TRANSLUCENT = 5,  // translucent.rs: kd, ks, roughness; reflect = kr, transmit = kt
+    MAT_DISNEY = 6,       // disney.rs: color = kd, roughness, eta + the Disney block below
+    MAT_DEBUG = 7,        // debug_material.rs
+    MAT_NONE = 15
+};
 // ---- textures (texture/{bilerp,mix,scale,checkerboard,uv}.rs, texture/mod.rs mappings) --------------------------
 // A material parameter is a texture.  The loader flattens the float and rgb textures of a scene file into one
 // table in definition order (a texture can only name textures defined before it: make_textures looks names up
@@ -613,7 +740,6 @@ inline double noise_weight(double t) {  // :132-136
     double t3 = t * t * t, t4 = t3 * t;
     return 6.0 * t4 * t - 15.0 * t4 + 10.0 * t3;
 }
-inline double lerp_f(double t, double a, double b) { return a * (1.0 - t) + b * t; }  // misc.rs:223-228
 inline double noise3(V3 p) {  // noise_flt, :75-107
     int32_t ix = rust_f64_as_i32(std::floor(p.x)), iy = rust_f64_as_i32(std::floor(p.y)), iz = rust_f64_as_i32(std::floor(p.z));
     double dx = p.x - (double)ix, dy = p.y - (double)iy, dz = p.z - (double)iz;
@@ -756,9 +882,16 @@ struct Material {
     // texture ids of kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta (-1: the constant above)
     int32_t tex[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     int32_t bump_tex = -1;  // bump_map: a float texture (material/*.rs, fetch_float_texture_opt)
+    // DisneyMaterial (disney.rs:464-483; loader defaults renderprocess.rs:810-836)
+    double metallic = 0.0, specular_tint = 0.0, anisotropic = 0.0, sheen = 0.0, sheen_tint = 0.5, clearcoat = 0.0,
+           clearcoat_gloss = 1.0, spec_trans = 0.0, flatness = 0.0, diff_trans = 1.0;
+    Rgb scatter_distance;
+    bool thin = false;
+    // texture ids of the ten scalars above, in that order, then scatter_distance
+    int32_t dtex[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     bool textured() const {
         for (int k = 0; k < 11; ++k)
-            if (tex[k] >= 0) return true;
+            if (tex[k] >= 0 || dtex[k] >= 0) return true;
         return false;
     }
 };
@@ -775,6 +908,11 @@ inline Material material_at(const Material& m, const std::vector<Texture>& table
     double* fs[5] = {&r.sigma, &r.roughness, &r.u_roughness, &r.v_roughness, &r.eta};
     for (int k = 0; k < 5; ++k)
         if (m.tex[6 + k] >= 0) *fs[k] = vals[m.tex[6 + k]].c[0];
+    double* ds[10] = {&r.metallic, &r.specular_tint, &r.anisotropic, &r.sheen, &r.sheen_tint, &r.clearcoat,
+                      &r.clearcoat_gloss, &r.spec_trans, &r.flatness, &r.diff_trans};
+    for (int k = 0; k < 10; ++k)
+        if (m.dtex[k] >= 0) *ds[k] = vals[m.dtex[k]].c[0];
+    if (m.dtex[10] >= 0) r.scatter_distance = vals[m.dtex[10]];
     return r;
 }
 // Material::bump (material/mod.rs:22-65): the shading frame of `si` after displacement by the float texture
@@ -937,6 +1075,156 @@ inline void material_bsdf(const Material& m, const SI& si, bool allow_multiple_l
                 }
                 bsdf->add(b);
             }
+            return;
+        }
+        case MAT_TRANSLUCENT: {  // translucent.rs:51-107; reflect = kr, transmit = kt
+            const double eta = 1.5;
+            bsdf->init(si, eta);
+            Rgb r = m.kr.clamp(0.0, kInf), t = m.kt.clamp(0.0, kInf);
+            if (r.is_black() && t.is_black()) {
+                bsdf->present = false;
+                return;
+            }
+            Rgb kd = m.kd.clamp(0.0, kInf);
+            if (!kd.is_black()) {
+                if (!r.is_black()) {
+                    Bxdf b;
+                    b.kind = BX_LAMBERTIAN;
+                    b.r = r * kd;
+                    bsdf->add(b);
+                }
+                if (!t.is_black()) {
+                    Bxdf b;
+                    b.kind = BX_LAMBERT_TRANS;
+                    b.t = t * kd;
+                    bsdf->add(b);
+                }
+            }
+            Rgb ks = m.ks.clamp(0.0, kInf);
+            if (!ks.is_black() && (!r.is_black() || !t.is_black())) {
+                double rough = m.roughness;
+                if (m.remap_roughness) rough = roughness_to_alpha(rough);
+                if (!r.is_black()) {
+                    Bxdf b;
+                    b.kind = BX_MICROFACET_REFL;
+                    b.r = r * ks;
+                    b.distrib.alpha_x = b.distrib.alpha_y = rough;
+                    b.fresnel.kind = FR_DIELECTRIC;
+                    b.fresnel.eta_i = 1.0;
+                    b.fresnel.eta_t = eta;
+                    bsdf->add(b);
+                }
+                if (!t.is_black()) {
+                    Bxdf b;
+                    b.kind = BX_MICROFACET_TRANS;
+                    b.t = t * ks;
+                    b.distrib.alpha_x = b.distrib.alpha_y = rough;
+                    b.eta_a = 1.0;
+                    b.eta_b = eta;
+                    bsdf->add(b);
+                }
+            }
+            return;
+        }
+        case MAT_DISNEY: {  // disney.rs:524-680
+            bsdf->init(si, 1.0);
+            const Rgb c = m.kd.clamp(0.0, kInf);
+            const double metallic_weight = m.metallic, e = m.eta, strans = m.spec_trans;
+            const double diffuse_weight = (1.0 - metallic_weight) * (1.0 - strans);
+            const double dt = m.diff_trans, rough = m.roughness;
+            const double lum = c.y();
+            const Rgb c_tint = lum > 0.0 ? c / lum : Rgb(1.0);
+            const double sheen_weight = m.sheen;
+            Rgb c_sheen;
+            if (sheen_weight > 0.0) c_sheen = lerp_rgb(m.sheen_tint, Rgb(1.0), c_tint);
+            if (diffuse_weight > 0.0) {
+                if (m.thin) {
+                    const double flat = m.flatness;
+                    Bxdf b;
+                    b.kind = BX_DISNEY_DIFFUSE;
+                    b.r = c * diffuse_weight * (1.0 - flat) * (1.0 - dt);
+                    bsdf->add(b);
+                    Bxdf s;
+                    s.kind = BX_DISNEY_FAKESS;
+                    s.r = c * diffuse_weight * flat * (1.0 - dt);
+                    s.a = rough;
+                    bsdf->add(s);
+                } else {
+                    if (!m.scatter_distance.is_black())
+                        throw std::runtime_error("oracle: DisneyMaterial with scatter_distance builds a BSSRDF (outside the restated path)");
+                    Bxdf b;
+                    b.kind = BX_DISNEY_DIFFUSE;
+                    b.r = c * diffuse_weight;
+                    bsdf->add(b);
+                }
+                Bxdf rr;
+                rr.kind = BX_DISNEY_RETRO;
+                rr.r = c * diffuse_weight;
+                rr.a = rough;
+                bsdf->add(rr);
+                if (sheen_weight > 0.0) {
+                    Bxdf sh;
+                    sh.kind = BX_DISNEY_SHEEN;
+                    sh.r = c_sheen * sheen_weight * diffuse_weight;
+                    bsdf->add(sh);
+                }
+            }
+            const double aspect = std::sqrt(1.0 - m.anisotropic * 0.9);
+            const double ax = rmax((rough * rough) / aspect, 0.001), ay = rmax((rough * rough) * aspect, 0.001);
+            const Rgb c_spec_0 = lerp_rgb(metallic_weight, lerp_rgb(m.specular_tint, Rgb(1.0), c_tint) * schlick_r0_from_eta(e), c);
+            {
+                Bxdf b;
+                b.kind = BX_MICROFACET_REFL;
+                b.r = Rgb(1.0);
+                b.distrib.alpha_x = ax;
+                b.distrib.alpha_y = ay;
+                b.distrib.separable_g = true;
+                b.fresnel.kind = FR_DISNEY;
+                b.fresnel.r0 = c_spec_0;
+                b.fresnel.metallic = metallic_weight;
+                b.fresnel.eta_t = e;
+                bsdf->add(b);
+            }
+            const double cc = m.clearcoat;
+            if (cc > 0.0) {
+                Bxdf b;
+                b.kind = BX_DISNEY_CLEARCOAT;
+                b.a = cc;
+                b.b = lerp_f(m.clearcoat_gloss, 0.1, 0.001);
+                bsdf->add(b);
+            }
+            if (strans > 0.0) {
+                Bxdf b;
+                b.kind = BX_MICROFACET_TRANS;
+                b.t = c.sqrt() * strans;
+                b.eta_a = 1.0;
+                b.eta_b = e;
+                if (m.thin) {  // a plain TrowbridgeReitzDistribution over the IOR-scaled roughness
+                    const double r_scaled = (0.65 * e - 0.35) * rough;
+                    b.distrib.alpha_x = rmax((r_scaled * r_scaled) / aspect, 0.001);
+                    b.distrib.alpha_y = rmax((r_scaled * r_scaled) * aspect, 0.001);
+                } else {
+                    b.distrib.alpha_x = ax;
+                    b.distrib.alpha_y = ay;
+                    b.distrib.separable_g = true;
+                }
+                bsdf->add(b);
+            }
+            if (m.thin) {
+                Bxdf b;
+                b.kind = BX_LAMBERT_TRANS;
+                b.t = c * dt;
+                bsdf->add(b);
+            }
+            return;
+        }
+        case MAT_DEBUG: {  // debug_material.rs:37-50
+            bsdf->init(si, 1.0);
+            Bxdf d, sp;
+            d.kind = BX_DEBUG_DIFFUSE;
+            sp.kind = BX_DEBUG_SPECULAR;
+            bsdf->add(d);
+            bsdf->add(sp);
             return;
         }
         default: return;  // no material: si.bsdf stays None

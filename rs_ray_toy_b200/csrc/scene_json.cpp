@@ -396,8 +396,38 @@ bool make_material(const Value& m, const TextureTable& t, rrt_material* out, int
         r.eta = tex_f(m, t, "eta", 1.5, &slots[RRT_SLOT_ETA]);
         r.u_roughness = tex_f(m, t, "u_roughness", 0.0, &slots[RRT_SLOT_U_ROUGHNESS]);
         r.v_roughness = tex_f(m, t, "v_roughness", 0.0, &slots[RRT_SLOT_V_ROUGHNESS]);
+    } else if (type == "TranslucentMaterial") {  // renderprocess.rs:695-720
+        r.kind = RRT_MAT_TRANSLUCENT;
+        tex_rgb(m, t, "kd", r.kd, c25, &slots[RRT_SLOT_KD]);
+        tex_rgb(m, t, "ks", r.ks, c25, &slots[RRT_SLOT_KS]);
+        r.roughness = tex_f(m, t, "roughness", 0.1, &slots[RRT_SLOT_ROUGHNESS]);
+        tex_rgb(m, t, "reflect", r.kr, c25, &slots[RRT_SLOT_KR]);
+        tex_rgb(m, t, "transmit", r.kt, c25, &slots[RRT_SLOT_KT]);
+    } else if (type == "DisneyMaterial") {  // renderprocess.rs:810-860
+        r.kind = RRT_MAT_DISNEY;
+        const double c0[3] = {0.0, 0.0, 0.0};
+        tex_rgb(m, t, "color", r.kd, c5, &slots[RRT_SLOT_KD]);
+        r.metallic = tex_f(m, t, "metallic", 0.0, &slots[RRT_SLOT_METALLIC]);
+        r.eta = tex_f(m, t, "eta", 1.5, &slots[RRT_SLOT_ETA]);
+        r.roughness = tex_f(m, t, "roughness", 0.5, &slots[RRT_SLOT_ROUGHNESS]);
+        r.specular_tint = tex_f(m, t, "specular_tint", 0.0, &slots[RRT_SLOT_SPECULAR_TINT]);
+        r.anisotropic = tex_f(m, t, "anisotropic", 0.0, &slots[RRT_SLOT_ANISOTROPIC]);
+        r.sheen = tex_f(m, t, "sheen", 0.0, &slots[RRT_SLOT_SHEEN]);
+        r.sheen_tint = tex_f(m, t, "sheen_tint", 0.5, &slots[RRT_SLOT_SHEEN_TINT]);
+        r.clearcoat = tex_f(m, t, "clearcoat", 0.0, &slots[RRT_SLOT_CLEARCOAT]);
+        r.clearcoat_gloss = tex_f(m, t, "clearcoat_gloss", 1.0, &slots[RRT_SLOT_CLEARCOAT_GLOSS]);
+        r.spec_trans = tex_f(m, t, "spec_trans", 0.0, &slots[RRT_SLOT_SPEC_TRANS]);
+        tex_rgb(m, t, "scatter_distance", r.scatter_distance, c0, &slots[RRT_SLOT_SCATTER_DISTANCE]);
+        r.thin = read_bool(m, "thin", false) ? 1 : 0;
+        r.flatness = tex_f(m, t, "flatness", 0.0, &slots[RRT_SLOT_FLATNESS]);
+        r.diff_trans = tex_f(m, t, "diff_trans", 1.0, &slots[RRT_SLOT_DIFF_TRANS]);
+    } else if (type == "Debug") {  // renderprocess.rs:861-863: no parameters, no bump map
+        r.kind = RRT_MAT_DEBUG;
+        r.remap_roughness = 0;
+        *out = r;
+        return true;
     } else {
-        return false;  // Disney / Translucent / Mix / Debug: outside the hot path
+        return false;  // "Unsupported Material Type" (renderprocess.rs:864-866): no entry; MixMaterial is handled by the caller
     }
     if (const Value* bm = m.get("bump_map"); bm && bm->is_string()) {  // fetch_float_texture_opt(.., "bump_map", None)
         auto it = t.f.find(bm->str);
@@ -430,6 +460,10 @@ void load_scene_json(const std::string& path, const std::string& overrides_json,
         for (const auto& mc : a->arr) {
             rrt_material m;
             int32_t slots[RRT_MATERIAL_SLOTS];
+            if (read_string(*mc, "material_type", "") == "MixMaterial" && material_index.count(read_string(*mc, "mat1", "")) &&
+                material_index.count(read_string(*mc, "mat2", "")))
+                // renderprocess.rs:681-692 indexes scene_global.materials, still empty while make_materials runs (Q25)
+                throw std::runtime_error("MixMaterial over two existing materials: the reference panics while loading (Q25)");
             if (make_material(*mc, tex, &m, slots)) {
                 material_index[read_string(*mc, "material_name", "DefaultMaterialName")] = (uint32_t)out->materials.size();
                 out->materials.push_back(m);

@@ -5,7 +5,9 @@
 // :622-1026 and the Trowbridge–Reitz distribution of src/microfacet.rs:253-425).
 //
 // A material kind fixes its lobe list, so there is no per-hit allocation (the reference builds a
-// Vec<Arc<dyn BxDF>> per hit): at most two lobes live in registers.  Quirks kept (Appendix A):
+// Vec<Arc<dyn BxDF>> per hit): at most two lobes live in registers.  Scenes with a Translucent, Disney or Debug
+// material (translucent.rs, disney.rs, debug_material.rs: up to eight lobes, Bsdf::MAX_BxDFS) run the NL = 8
+// instantiation of everything below; every other scene runs NL = 2, whose code is what it was before those existed.  Quirks kept (Appendix A):
 // Q15 (Bsdf::sample_f: other lobes' pdfs added only when the chosen lobe is not reflective, the
 // recomputed multi-lobe f discarded), Q16 (Plastic's specular lobe gated on kd), Q5a (sphere hit
 // point taken on the instance-space ray), FresnelSpecular's type = SPECULAR | ALL.
@@ -57,6 +59,14 @@ struct MaterialRec {  // rrt_material, flattened
     uint32_t needed;   // closure of the parameter textures (the bump map's own closure: bump_needed)
     uint32_t bump_needed, pad;
 };
+// DisneyMaterial's own parameters (disney.rs:464-483), a table beside `materials` that only the NL = 8 kernels read
+struct DisneyRec {
+    double v[10];      // metallic specular_tint anisotropic sheen sheen_tint clearcoat clearcoat_gloss spec_trans flatness diff_trans
+    int32_t tex[10];   // texture index per parameter, -1 = the constant
+    uint32_t thin, pad;
+};
+enum { DZ_METALLIC = 0, DZ_SPECULAR_TINT, DZ_ANISOTROPIC, DZ_SHEEN, DZ_SHEEN_TINT, DZ_CLEARCOAT, DZ_CLEARCOAT_GLOSS, DZ_SPEC_TRANS,
+       DZ_FLATNESS, DZ_DIFF_TRANS };
 struct LightRec {
     uint32_t kind, shape_kind;
     Rgb intensity;    // point: I; distant: L; diffuse area: lemit
@@ -94,6 +104,7 @@ struct ShadeScene {
     const EnvLightView* envs;   // the InfiniteAreaLights of `lights` and of `infinite_lights`
     const int32_t* escape_envs; // Scene::infinite_lights: indices into envs (PathIntegrator, path.rs:84)
     uint32_t n_escape_envs, pad_sc;
+    const DisneyRec* disney;    // one per material when some material is Translucent / Disney / Debug, else null
 };
 
 // What the integrator reads of a SurfaceInteraction (interaction.rs:95-113)
@@ -366,8 +377,19 @@ static __device__ double roughness_to_alpha(double roughness) {
 // ---- lobes -----------------------------------------------------------------------------------------------
 enum : uint32_t { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY = 8, BXDF_SPECULAR = 16, BXDF_ALL = 31 };
 enum : uint32_t { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR, LOBE_MICROFACET, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC,
-                  LOBE_MICROFACET_TRANS };
-enum : uint32_t { FRESNEL_NOOP = 0, FRESNEL_DIELECTRIC = 1, FRESNEL_CONDUCTOR = 2 };
+                  LOBE_MICROFACET_TRANS,
+                  // NL = 8 only
+                  LOBE_LAMBERT_TRANS,     // reflection.rs:843-898
+                  LOBE_DISNEY_DIFFUSE,    // disney.rs:33-75
+                  LOBE_DISNEY_FAKESS,     // disney.rs:77-131   (eta_a = roughness)
+                  LOBE_DISNEY_RETRO,      // disney.rs:133-180  (eta_a = roughness)
+                  LOBE_DISNEY_SHEEN,      // disney.rs:182-224
+                  LOBE_DISNEY_CLEARCOAT,  // disney.rs:226-303  (eta_a = weight, eta_b = gloss)
+                  LOBE_DEBUG_DIFFUSE,     // debug_material.rs:10-20
+                  LOBE_DEBUG_SPECULAR };  // debug_material.rs:22-32: typed specular, cosine-sampled
+// FRESNEL_DISNEY (disney.rs:305-326): cond_eta = r0, a = metallic, b = eta.  NL = 8 lobes may also carry
+// FRESNEL_SEPARABLE_G: DisneyMicrofacetDistribution's g = g1(wo) * g1(wi) (disney.rs:329-360).
+enum : uint32_t { FRESNEL_NOOP = 0, FRESNEL_DIELECTRIC = 1, FRESNEL_CONDUCTOR = 2, FRESNEL_DISNEY = 3, FRESNEL_SEPARABLE_G = 256 };
 
 struct Lobe {
     uint32_t kind, fresnel;
@@ -377,6 +399,7 @@ struct Lobe {
     double eta_a, eta_b;   // specular transmission / FresnelSpecular indices; Oren–Nayar A, B
     double alpha_x, alpha_y;
 };
+template <bool BIG = false>
 __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
     switch (l.kind) {
         case LOBE_LAMBERT:
@@ -385,13 +408,41 @@ __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
         case LOBE_SPEC_REFL: return BXDF_REFLECTION | BXDF_SPECULAR;
         case LOBE_SPEC_TRANS: return BXDF_SPECULAR | BXDF_TRANSMISSION;
         case LOBE_MICROFACET_TRANS: return BXDF_GLOSSY | BXDF_TRANSMISSION;  // reflection.rs:1143-1145
-        default: return BXDF_SPECULAR | BXDF_ALL;  // reflection.rs:801-803
+        default: break;
     }
+    if (BIG) {
+        switch (l.kind) {
+            case LOBE_LAMBERT_TRANS: return BXDF_DIFFUSE | BXDF_TRANSMISSION;
+            case LOBE_DISNEY_DIFFUSE:
+            case LOBE_DISNEY_FAKESS:
+            case LOBE_DISNEY_RETRO:
+            case LOBE_DISNEY_SHEEN:
+            case LOBE_DEBUG_DIFFUSE: return BXDF_DIFFUSE | BXDF_REFLECTION;
+            // disney.rs:300-302: neither REFLECTION nor TRANSMISSION — Bsdf::f never adds the clearcoat lobe, it is
+            // only seen through sample_f and pdf (Q37)
+            case LOBE_DISNEY_CLEARCOAT: return BXDF_DIFFUSE | BXDF_GLOSSY;
+            case LOBE_DEBUG_SPECULAR: return BXDF_SPECULAR | BXDF_REFLECTION;
+            default: break;
+        }
+    }
+    return BXDF_SPECULAR | BXDF_ALL;  // FresnelSpecular, reflection.rs:801-803
 }
-__device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type(l) & flags) == lobe_type(l); }
+template <bool BIG = false>
+__device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type<BIG>(l) & flags) == lobe_type<BIG>(l); }
+// reflection.rs:13-24, misc.rs:223-228 (lerp(t, a, b) = a * (1 - t) + b * t)
+__device__ __forceinline__ double schlick_weight(double c) {
+    const double m = clampd(1.0 - c, 0.0, 1.0);
+    return (m * m) * (m * m) * m;
+}
+__device__ __forceinline__ double lerp_f(double t, double a, double b) { return a * (1.0 - t) + b * t; }
+__device__ __forceinline__ Rgb lerp_rgb(double t, Rgb a, Rgb b) { return a * (1.0 - t) + b * t; }
+template <bool BIG = false>
 static __device__ Rgb lobe_fresnel(const Lobe& l, double cos_i) {  // reflection.rs:603-619
-    if (l.fresnel == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
-    if (l.fresnel == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
+    const uint32_t fk = BIG ? (l.fresnel & 255u) : l.fresnel;
+    if (BIG && fk == FRESNEL_DISNEY)
+        return lerp_rgb(l.a, rgb(fr_dielectric(cos_i, 1.0, l.b)), lerp_rgb(schlick_weight(cos_i), l.cond_eta, rgb(1.0)));
+    if (fk == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
+    if (fk == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
     return rgb(1.0);
 }
 // TrowbridgeReitzDistribution (microfacet.rs:364-390)
@@ -413,6 +464,20 @@ static __device__ double tr_lambda(const Lobe& l, V3 w) {
 }
 static __device__ double tr_pdf(const Lobe& l, V3 wo, V3 wh) {  // microfacet.rs:30-36, sample_visible_area
     return tr_d(l, wh) * (1.0 / (1.0 + tr_lambda(l, wo))) * absdot(wo, wh) / abs_cos_theta(wo);
+}
+template <bool BIG = false>
+__device__ __forceinline__ double tr_g(const Lobe& l, V3 wo, V3 wi) {
+    if (BIG && (l.fresnel & FRESNEL_SEPARABLE_G)) return (1.0 / (1.0 + tr_lambda(l, wo))) * (1.0 / (1.0 + tr_lambda(l, wi)));
+    return 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
+}
+// disney.rs:20-31; gtr1 divides by log10(alpha^2) where pbrt has the natural logarithm: kept (Q36)
+static __device__ double gtr1(double cos_t, double alpha) {
+    const double alpha2 = alpha * alpha;
+    return (alpha2 - 1.0) / (kPi * log10(alpha2) * (1.0 + (alpha2 - 1.0) * cos_t * cos_t));
+}
+static __device__ double smith_g_ggx(double cos_t, double alpha) {
+    const double alpha2 = alpha * alpha, cos2 = cos_t * cos_t;
+    return 1.0 / (cos_t + sqrt(alpha2 + cos2 - alpha2 * cos2));
 }
 // microfacet.rs:270-362
 static __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, double u2) {
@@ -456,7 +521,45 @@ static __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, d
     return normalize(v3(-slope_x, -slope_y, 1.0));
 }
 
+template <bool BIG = false>
 RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+    if (BIG) {
+        switch (l.kind) {
+            case LOBE_LAMBERT_TRANS: return l.t / kPi;
+            case LOBE_DEBUG_DIFFUSE: return Rgb{0.0, 1.0, 0.0};
+            case LOBE_DEBUG_SPECULAR: return Rgb{0.0, 0.0, 1.0};
+            case LOBE_DISNEY_DIFFUSE: {
+                const double fo = schlick_weight(abs_cos_theta(wo)), fi = schlick_weight(abs_cos_theta(wi));
+                return l.r / kPi * (1.0 - fo / 2.0) * (1.0 - fi / 2.0);
+            }
+            case LOBE_DISNEY_FAKESS:
+            case LOBE_DISNEY_RETRO:
+            case LOBE_DISNEY_SHEEN:
+            case LOBE_DISNEY_CLEARCOAT: {
+                V3 wh = wi + wo;
+                if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return rgb(0.0);
+                wh = normalize(wh);
+                if (l.kind == LOBE_DISNEY_CLEARCOAT) {
+                    const double dr = gtr1(abs_cos_theta(wh), l.eta_b);
+                    const double fr = lerp_f(schlick_weight(dot(wo, wh)), 0.04, 1.0);
+                    const double gr = smith_g_ggx(abs_cos_theta(wo), 0.25) * smith_g_ggx(abs_cos_theta(wi), 0.25);
+                    return rgb(l.eta_a * gr * fr * dr / 4.0);
+                }
+                const double cos_theta_d = dot(wi, wh);
+                if (l.kind == LOBE_DISNEY_SHEEN) return l.r * schlick_weight(cos_theta_d);
+                const double fo = schlick_weight(abs_cos_theta(wo)), fi = schlick_weight(abs_cos_theta(wi));
+                if (l.kind == LOBE_DISNEY_RETRO) {
+                    const double r_r = 2.0 * l.eta_a * cos_theta_d * cos_theta_d;
+                    return l.r / kPi * r_r * (fo + fi + fo * fi * (r_r - 1.0));
+                }
+                const double fss_90 = cos_theta_d * cos_theta_d * l.eta_a;
+                const double fss = lerp_f(fo, 1.0, fss_90) * lerp_f(fi, 1.0, fss_90);
+                const double ss = 1.25 * (fss * (1.0 / (abs_cos_theta(wo) + abs_cos_theta(wi)) - 0.5) + 0.5);
+                return l.r / kPi * ss;
+            }
+            default: break;
+        }
+    }
     switch (l.kind) {
         case LOBE_LAMBERT: return l.r / kPi;
         case LOBE_OREN_NAYAR: {  // reflection.rs:916-941
@@ -481,8 +584,8 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
             if (cos_i == 0.0 || cos_o == 0.0) return rgb(0.0);
             if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return rgb(0.0);
             wh = normalize(wh);
-            Rgb fr = lobe_fresnel(l, dot(wi, faceforward(wh, v3(0.0, 0.0, 1.0))));
-            double g = 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
+            Rgb fr = lobe_fresnel<BIG>(l, dot(wi, faceforward(wh, v3(0.0, 0.0, 1.0))));
+            double g = tr_g<BIG>(l, wo, wi);
             return l.r * tr_d(l, wh) * g * fr / (4.0 * cos_i * cos_o);
         }
         case LOBE_MICROFACET_TRANS: {  // MicrofacetTransmission::f (reflection.rs:1058-1099), TransportMode::Radiance
@@ -495,7 +598,7 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
             const Rgb fr = rgb(fr_dielectric(dot(wo, wh), l.eta_a, l.eta_b));
             const double sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
             const double factor = 1.0 / eta;
-            const double g = 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
+            const double g = tr_g<BIG>(l, wo, wi);
             return (rgb(1.0) - fr) * l.t *
                    fabs(tr_d(l, wh) * g * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
                         (cos_i * cos_o * sqrt_denom * sqrt_denom));
@@ -503,7 +606,28 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
         default: return rgb(0.0);
     }
 }
+template <bool BIG = false>
 RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+    if (BIG) {
+        switch (l.kind) {
+            case LOBE_DISNEY_DIFFUSE:
+            case LOBE_DISNEY_FAKESS:
+            case LOBE_DISNEY_RETRO:
+            case LOBE_DISNEY_SHEEN:
+            case LOBE_DEBUG_DIFFUSE:
+            case LOBE_DEBUG_SPECULAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;  // reflection.rs:480-486
+            case LOBE_LAMBERT_TRANS: return !same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
+            case LOBE_DISNEY_CLEARCOAT: {  // disney.rs:283-299
+                if (!same_hemisphere(wo, wi)) return 0.0;
+                V3 wh = wi + wo;
+                if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return 0.0;
+                wh = normalize(wh);
+                const double dr = gtr1(abs_cos_theta(wh), l.eta_b);
+                return dr * abs_cos_theta(wh) / (4.0 * dot(wo, wh));
+            }
+            default: break;
+        }
+    }
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
@@ -524,14 +648,50 @@ RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     }
 }
 // BxDF::sample_f of each lobe; *pdf is left untouched on the early-outs (the caller zeroed it)
+template <bool BIG = false>
 RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+    if (BIG) {
+        switch (l.kind) {
+            case LOBE_DISNEY_DIFFUSE:
+            case LOBE_DISNEY_FAKESS:
+            case LOBE_DISNEY_RETRO:
+            case LOBE_DISNEY_SHEEN:
+            case LOBE_DEBUG_DIFFUSE:
+            case LOBE_DEBUG_SPECULAR: {  // BxDF's default sample_f, reflection.rs:428-443
+                *wi = cosine_sample_hemisphere(u);
+                if (wo.z < 0.0) wi->z *= -1.0;
+                *pdf = lobe_pdf<BIG>(l, wo, *wi);
+                return lobe_f<BIG>(l, wo, *wi);
+            }
+            case LOBE_LAMBERT_TRANS: {  // reflection.rs:857-871
+                *wi = cosine_sample_hemisphere(u);
+                if (wo.z > 0.0) wi->z *= -1.0;
+                *pdf = lobe_pdf<BIG>(l, wo, *wi);
+                return lobe_f<BIG>(l, wo, *wi);
+            }
+            case LOBE_DISNEY_CLEARCOAT: {  // disney.rs:254-282; the square root covers the denominator only (Q36)
+                if (wo.z == 0.0) return rgb(0.0);
+                const double alpha2 = l.eta_b * l.eta_b;
+                const double cos_t = (1.0 - pow(alpha2, 1.0 - u.x)) / sqrt(rmax(1.0 - alpha2, 0.0));
+                const double sin_t = sqrt(rmax(1.0 - cos_t * cos_t, 0.0));
+                const double phi = 2.0 * kPi * u.y;
+                V3 wh = v3(sin_t * cos(phi), sin_t * sin(phi), cos_t);
+                if (!same_hemisphere(wo, wh)) wh = -wh;
+                *wi = reflect_about(wo, wh);
+                if (!same_hemisphere(wo, *wi)) return rgb(0.0);
+                *pdf = lobe_pdf<BIG>(l, wo, *wi);
+                return lobe_f<BIG>(l, wo, *wi);
+            }
+            default: break;
+        }
+    }
     switch (l.kind) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: {  // reflection.rs:428-443
             *wi = cosine_sample_hemisphere(u);
             if (wo.z < 0.0) wi->z *= -1.0;
-            *pdf = lobe_pdf(l, wo, *wi);
-            return lobe_f(l, wo, *wi);
+            *pdf = lobe_pdf<BIG>(l, wo, *wi);
+            return lobe_f<BIG>(l, wo, *wi);
         }
         case LOBE_MICROFACET: {  // reflection.rs:991-1015
             if (wo.z == 0.0) return rgb(0.0);
@@ -541,12 +701,12 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             *wi = reflect_about(wo, wh);
             if (!same_hemisphere(wo, *wi)) return rgb(0.0);
             *pdf = tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
-            return lobe_f(l, wo, *wi);
+            return lobe_f<BIG>(l, wo, *wi);
         }
         case LOBE_SPEC_REFL: {  // reflection.rs:638-649
             *wi = v3(-wo.x, -wo.y, wo.z);
             *pdf = 1.0;
-            return lobe_fresnel(l, wi->z) * l.r / abs_cos_theta(*wi);
+            return lobe_fresnel<BIG>(l, wi->z) * l.r / abs_cos_theta(*wi);
         }
         case LOBE_SPEC_TRANS: {  // reflection.rs:686-714, TransportMode::Radiance
             bool entering = wo.z > 0.0;
@@ -564,8 +724,8 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             if (dot(wo, wh) < 0.0) return rgb(0.0);
             const double eta = wo.z > 0.0 ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
             if (!refract_dir(wo, wh, eta, wi)) return rgb(0.0);
-            *pdf = lobe_pdf(l, wo, *wi);
-            return lobe_f(l, wo, *wi);
+            *pdf = lobe_pdf<BIG>(l, wo, *wi);
+            return lobe_f<BIG>(l, wo, *wi);
         }
         default: {  // FresnelSpecular, reflection.rs:751-797
             double fr = fr_dielectric(wo.z, l.eta_a, l.eta_b);
@@ -587,48 +747,58 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
     }
 }
 
-// ---- Bsdf over at most two lobes (reflection.rs:205-404) --------------------------------------------------
-struct Bsdf {
+// ---- Bsdf over at most NL lobes (reflection.rs:205-404) ---------------------------------------------------
+template <int NL>
+struct BsdfT {
     V3 ns, ng, ss, ts;
     double eta;
     int n_lobes;
     bool present;
-    Lobe lobes[2];
+    Lobe lobes[NL];
 };
-__device__ __forceinline__ V3 to_local(const Bsdf& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
-__device__ __forceinline__ V3 to_world(const Bsdf& b, V3 v) {
+using Bsdf = BsdfT<2>;
+using BsdfBig = BsdfT<8>;  // Bsdf::MAX_BxDFS (reflection.rs:207)
+template <int NL>
+__device__ __forceinline__ V3 to_local(const BsdfT<NL>& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+template <int NL>
+__device__ __forceinline__ V3 to_world(const BsdfT<NL>& b, V3 v) {
     return v3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
               b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-static __device__ int bsdf_num_components(const Bsdf& b, uint32_t flags) {
+template <int NL>
+static __device__ int bsdf_num_components(const BsdfT<NL>& b, uint32_t flags) {
     int n = 0;
-    for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches(b.lobes[i], flags) ? 1 : 0;
+    for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches<(NL > 2)>(b.lobes[i], flags) ? 1 : 0;
     return n;
 }
-RRT_SHADE_FN Rgb bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+template <int NL>
+RRT_SHADE_FN Rgb bsdf_f(const BsdfT<NL>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    constexpr bool BIG = NL > 2;
     V3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);
     bool reflect = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0;
     Rgb f = rgb(0.0);
     for (int i = 0; i < b.n_lobes; ++i) {
         const Lobe& l = b.lobes[i];
-        const uint32_t ty = lobe_type(l);
-        if (lobe_matches(l, flags) && ((reflect && (ty & BXDF_REFLECTION)) || (!reflect && (ty & BXDF_TRANSMISSION))))
-            f = f + lobe_f(l, wo, wi);
+        const uint32_t ty = lobe_type<BIG>(l);
+        if (lobe_matches<BIG>(l, flags) && ((reflect && (ty & BXDF_REFLECTION)) || (!reflect && (ty & BXDF_TRANSMISSION))))
+            f = f + lobe_f<BIG>(l, wo, wi);
     }
     return f;
 }
 // Bsdf::pdf (reflection.rs:382-404)
-RRT_SHADE_FN double bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+template <int NL>
+RRT_SHADE_FN double bsdf_pdf(const BsdfT<NL>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    constexpr bool BIG = NL > 2;
     if (b.n_lobes == 0) return 0.0;
     V3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
     if (wo.z == 0.0) return 0.0;
     double pdf = 0.0;
     int matching = 0;
     for (int i = 0; i < b.n_lobes; ++i)
-        if (lobe_matches(b.lobes[i], flags)) {
+        if (lobe_matches<BIG>(b.lobes[i], flags)) {
             matching += 1;
-            pdf += lobe_pdf(b.lobes[i], wo, wi);
+            pdf += lobe_pdf<BIG>(b.lobes[i], wo, wi);
         }
     return matching > 0 ? pdf / (double)matching : 0.0;
 }
@@ -678,7 +848,9 @@ RRT_SHADE_FN Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, doubl
     return dot(ns, -*wi) > 0.0 ? l.intensity : rgb(0.0);  // AreaLight::l (diffuse.rs:134-140)
 }
 
-RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+template <int NL>
+RRT_SHADE_FN Rgb bsdf_sample_f(const BsdfT<NL>& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+    constexpr bool BIG = NL > 2;
     const int matching = bsdf_num_components(b, flags);
     if (matching == 0) {
         *pdf = 0.0;
@@ -689,7 +861,7 @@ RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* p
     int comp = c64 > (uint64_t)matching ? matching : (int)c64;
     int count = comp, chosen = 0;
     for (int i = 0; i < b.n_lobes; ++i)
-        if (lobe_matches(b.lobes[i], flags)) {
+        if (lobe_matches<BIG>(b.lobes[i], flags)) {
             if (count == 0) {
                 chosen = i;
                 break;
@@ -701,16 +873,16 @@ RRT_SHADE_FN Rgb bsdf_sample_f(const Bsdf& b, V3 wo_w, V3* wi_w, P2 u, double* p
     V3 wi = v3(0, 0, 0), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);  // NB: *pdf is not touched here either (reflection.rs:343-345)
     *pdf = 0.0;
-    *sampled_type = lobe_type(l);
-    Rgb f = lobe_sample_f(l, wo, &wi, ur, pdf, sampled_type);
+    *sampled_type = lobe_type<BIG>(l);
+    Rgb f = lobe_sample_f<BIG>(l, wo, &wi, ur, pdf, sampled_type);
     if (*pdf == 0.0) {
         *sampled_type = 0;
         return rgb(0.0);
     }
     *wi_w = to_world(b, wi);
-    if (!(lobe_type(l) & BXDF_REFLECTION) && matching > 1) {
+    if (!(lobe_type<BIG>(l) & BXDF_REFLECTION) && matching > 1) {
         for (int i = 0; i < b.n_lobes; ++i)
-            if (i != chosen && lobe_matches(b.lobes[i], flags)) *pdf += lobe_pdf(b.lobes[i], wo, wi);
+            if (i != chosen && lobe_matches<BIG>(b.lobes[i], flags)) *pdf += lobe_pdf<BIG>(b.lobes[i], wo, wi);
     }
     if (matching > 1) *pdf /= (double)matching;
     return f;  // Q15: the multi-lobe re-evaluation is computed into a shadowed variable and dropped
@@ -768,8 +940,28 @@ static __device__ __noinline__ void material_at(const ShadeScene& sc, const Mate
     *out = r;
 }
 
-// Material::compute_scattering_functions once the parameters are values
-RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, Bsdf* b) {
+// material_at for the NL = 8 kernels: DisneyMaterial's own parameters too (disney.rs:538-551 evaluates every texture)
+static __device__ __noinline__ void material_at_big(const ShadeScene& sc, const MaterialRec& m, const Surface& s, const RayDiffRec* diff,
+                                                    MaterialRec* out, DisneyRec* dz) {
+    Rgb vals[kMaxTextures];
+    TexPoint q = tex_point(s.uv, s.p);
+    if (diff) compute_differentials(s.n, s.dpdu, s.dpdv, *diff, &q);
+    texture_eval_table(sc.textures, sc.n_textures, m.needed, q, vals, sc.mips);
+    MaterialRec r = m;
+    Rgb* const colours[6] = {&r.kd, &r.ks, &r.kr, &r.kt, &r.metal_eta, &r.metal_k};
+    for (int k = 0; k < 6; ++k)
+        if (m.tex[k] >= 0) *colours[k] = vals[m.tex[k]];
+    double* const scalars[5] = {&r.sigma, &r.roughness, &r.u_roughness, &r.v_roughness, &r.eta};
+    for (int k = 0; k < 5; ++k)
+        if (m.tex[6 + k] >= 0) *scalars[k] = vals[m.tex[6 + k]].r;
+    *out = r;
+    for (int k = 0; k < 10; ++k)
+        if (dz->tex[k] >= 0) dz->v[k] = vals[dz->tex[k]].r;
+}
+
+// Material::compute_scattering_functions once the parameters are values.  `dz`: the material's DisneyRec (NL = 8 only).
+template <int NL>
+RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, BsdfT<NL>* b, const DisneyRec* dz = nullptr) {
     b->ns = s.shn;
     b->ss = normalize(s.shdpdu);
     b->ng = s.n;
@@ -786,6 +978,146 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
     l.a = l.b = 1.0;
     l.eta_a = l.eta_b = 1.0;
     l.alpha_x = l.alpha_y = 0.0;
+    if (NL > 2 && m.kind >= 5) {
+        if (m.kind == 5) {  // TranslucentMaterial (translucent.rs:51-107): reflect = kr, transmit = kt
+            const double eta = 1.5;
+            b->eta = eta;
+            const Rgb r = clamp_rgb(m.kr, 0.0, kInfD), t = clamp_rgb(m.kt, 0.0, kInfD);
+            if (is_black(r) && is_black(t)) {
+                b->present = false;
+                return;
+            }
+            const Rgb kd = clamp_rgb(m.kd, 0.0, kInfD);
+            if (!is_black(kd)) {
+                if (!is_black(r)) {
+                    l.kind = LOBE_LAMBERT;
+                    l.r = r * kd;
+                    b->lobes[b->n_lobes++] = l;
+                }
+                if (!is_black(t)) {
+                    l.kind = LOBE_LAMBERT_TRANS;
+                    l.r = rgb(0.0);
+                    l.t = t * kd;
+                    b->lobes[b->n_lobes++] = l;
+                }
+            }
+            const Rgb ks = clamp_rgb(m.ks, 0.0, kInfD);
+            if (!is_black(ks) && (!is_black(r) || !is_black(t))) {
+                double rough = m.roughness;
+                if (m.remap_roughness) rough = roughness_to_alpha(rough);
+                l.alpha_x = l.alpha_y = rough;
+                if (!is_black(r)) {
+                    l.kind = LOBE_MICROFACET;
+                    l.r = r * ks;
+                    l.t = rgb(0.0);
+                    l.fresnel = FRESNEL_DIELECTRIC;
+                    l.a = 1.0;
+                    l.b = eta;
+                    b->lobes[b->n_lobes++] = l;
+                }
+                if (!is_black(t)) {
+                    l.kind = LOBE_MICROFACET_TRANS;
+                    l.fresnel = FRESNEL_NOOP;
+                    l.r = rgb(0.0);
+                    l.t = t * ks;
+                    l.eta_a = 1.0;
+                    l.eta_b = eta;
+                    b->lobes[b->n_lobes++] = l;
+                }
+            }
+            return;
+        }
+        if (m.kind == 7) {  // DebugMaterial (debug_material.rs:37-50)
+            l.kind = LOBE_DEBUG_DIFFUSE;
+            b->lobes[b->n_lobes++] = l;
+            l.kind = LOBE_DEBUG_SPECULAR;
+            b->lobes[b->n_lobes++] = l;
+            return;
+        }
+        // DisneyMaterial (disney.rs:524-680); a BSSRDF-producing record was refused when the scene was set up
+        const Rgb c = clamp_rgb(m.kd, 0.0, kInfD);
+        const double metallic_weight = dz->v[DZ_METALLIC], e = m.eta, strans = dz->v[DZ_SPEC_TRANS];
+        const double diffuse_weight = (1.0 - metallic_weight) * (1.0 - strans);
+        const double dt = dz->v[DZ_DIFF_TRANS], rough = m.roughness;
+        const double luminance = lum(c);
+        const Rgb c_tint = luminance > 0.0 ? c / luminance : rgb(1.0);
+        const double sheen_weight = dz->v[DZ_SHEEN];
+        Rgb c_sheen = rgb(0.0);
+        if (sheen_weight > 0.0) c_sheen = lerp_rgb(dz->v[DZ_SHEEN_TINT], rgb(1.0), c_tint);
+        if (diffuse_weight > 0.0) {
+            if (dz->thin) {
+                const double flat = dz->v[DZ_FLATNESS];
+                l.kind = LOBE_DISNEY_DIFFUSE;
+                l.r = c * diffuse_weight * (1.0 - flat) * (1.0 - dt);
+                b->lobes[b->n_lobes++] = l;
+                l.kind = LOBE_DISNEY_FAKESS;
+                l.r = c * diffuse_weight * flat * (1.0 - dt);
+                l.eta_a = rough;
+                b->lobes[b->n_lobes++] = l;
+            } else {
+                l.kind = LOBE_DISNEY_DIFFUSE;
+                l.r = c * diffuse_weight;
+                b->lobes[b->n_lobes++] = l;
+            }
+            l.kind = LOBE_DISNEY_RETRO;
+            l.r = c * diffuse_weight;
+            l.eta_a = rough;
+            b->lobes[b->n_lobes++] = l;
+            if (sheen_weight > 0.0) {
+                l.kind = LOBE_DISNEY_SHEEN;
+                l.r = c_sheen * sheen_weight * diffuse_weight;
+                b->lobes[b->n_lobes++] = l;
+            }
+        }
+        const double aspect = sqrt(1.0 - dz->v[DZ_ANISOTROPIC] * 0.9);
+        const double ax = rmax((rough * rough) / aspect, 0.001), ay = rmax((rough * rough) * aspect, 0.001);
+        const double q0 = (e - 1.0) / (e + 1.0);  // schlick_r0_from_eta (reflection.rs:28-30)
+        const Rgb c_spec_0 = lerp_rgb(metallic_weight, lerp_rgb(dz->v[DZ_SPECULAR_TINT], rgb(1.0), c_tint) * (q0 * q0), c);
+        l.kind = LOBE_MICROFACET;
+        l.r = rgb(1.0);
+        l.alpha_x = ax;
+        l.alpha_y = ay;
+        l.fresnel = FRESNEL_DISNEY | FRESNEL_SEPARABLE_G;
+        l.cond_eta = c_spec_0;
+        l.a = metallic_weight;
+        l.b = e;
+        l.eta_a = l.eta_b = 1.0;
+        b->lobes[b->n_lobes++] = l;
+        l.fresnel = FRESNEL_NOOP;
+        l.cond_eta = rgb(0.0);
+        l.a = l.b = 1.0;
+        const double cc = dz->v[DZ_CLEARCOAT];
+        if (cc > 0.0) {
+            l.kind = LOBE_DISNEY_CLEARCOAT;
+            l.r = rgb(0.0);
+            l.eta_a = cc;
+            l.eta_b = lerp_f(dz->v[DZ_CLEARCOAT_GLOSS], 0.1, 0.001);
+            b->lobes[b->n_lobes++] = l;
+        }
+        if (strans > 0.0) {
+            l.kind = LOBE_MICROFACET_TRANS;
+            l.r = rgb(0.0);
+            l.t = sqrt_rgb(c) * strans;
+            l.eta_a = 1.0;
+            l.eta_b = e;
+            if (dz->thin) {  // a plain TrowbridgeReitzDistribution over the IOR-scaled roughness (Burley 2015, figure 15)
+                const double r_scaled = (0.65 * e - 0.35) * rough;
+                l.alpha_x = rmax((r_scaled * r_scaled) / aspect, 0.001);
+                l.alpha_y = rmax((r_scaled * r_scaled) * aspect, 0.001);
+            } else {
+                l.fresnel = FRESNEL_SEPARABLE_G;
+            }
+            b->lobes[b->n_lobes++] = l;
+            l.fresnel = FRESNEL_NOOP;
+        }
+        if (dz->thin) {
+            l.kind = LOBE_LAMBERT_TRANS;
+            l.r = rgb(0.0);
+            l.t = c * dt;
+            b->lobes[b->n_lobes++] = l;
+        }
+        return;
+    }
     switch (m.kind) {
         case 0: {  // MatteMaterial (matte.rs:36-61)
             Rgb r = clamp_rgb(m.kd, 0.0, kInfD);

@@ -44,7 +44,11 @@ class Material(C.Structure):
                 ("kd", C.c_double * 3), ("ks", C.c_double * 3), ("kr", C.c_double * 3), ("kt", C.c_double * 3),
                 ("metal_eta", C.c_double * 3), ("metal_k", C.c_double * 3),
                 ("sigma", C.c_double), ("roughness", C.c_double), ("u_roughness", C.c_double),
-                ("v_roughness", C.c_double), ("eta", C.c_double)]
+                ("v_roughness", C.c_double), ("eta", C.c_double),
+                ("metallic", C.c_double), ("specular_tint", C.c_double), ("anisotropic", C.c_double), ("sheen", C.c_double),
+                ("sheen_tint", C.c_double), ("clearcoat", C.c_double), ("clearcoat_gloss", C.c_double),
+                ("spec_trans", C.c_double), ("flatness", C.c_double), ("diff_trans", C.c_double),
+                ("scatter_distance", C.c_double * 3), ("thin", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class Texture(C.Structure):
@@ -54,9 +58,10 @@ class Texture(C.Structure):
 
 
 MAX_TEXTURES = 32
-MATERIAL_SLOTS = 12
+MATERIAL_SLOTS = 23
 (SLOT_KD, SLOT_KS, SLOT_KR, SLOT_KT, SLOT_METAL_ETA, SLOT_METAL_K, SLOT_SIGMA, SLOT_ROUGHNESS, SLOT_U_ROUGHNESS,
- SLOT_V_ROUGHNESS, SLOT_ETA, SLOT_BUMP_MAP) = range(12)
+ SLOT_V_ROUGHNESS, SLOT_ETA, SLOT_BUMP_MAP, SLOT_METALLIC, SLOT_SPECULAR_TINT, SLOT_ANISOTROPIC, SLOT_SHEEN, SLOT_SHEEN_TINT,
+ SLOT_CLEARCOAT, SLOT_CLEARCOAT_GLOSS, SLOT_SPEC_TRANS, SLOT_FLATNESS, SLOT_DIFF_TRANS, SLOT_SCATTER_DISTANCE) = range(23)
 TEX_CONSTANT, TEX_BILERP, TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D, TEX_UV, TEX_WINDY, TEX_WRINKLED = range(9)
 TEXMAP_UV, TEXMAP_PLANAR, TEXMAP_SPHERICAL, TEXMAP_CYLINDRICAL = range(4)
 
@@ -142,6 +147,27 @@ def mirror(kr=(0.9,) * 3) -> Material:
 
 def glass(kr=(1.0,) * 3, kt=(1.0,) * 3, eta=1.5) -> Material:
     return Material(kind=4, kr=tuple(kr), kt=tuple(kt), eta=eta, u_roughness=0.0, v_roughness=0.0)
+
+
+def translucent(kd=(0.25,) * 3, ks=(0.25,) * 3, roughness=0.1, reflect=(0.25,) * 3, transmit=(0.25,) * 3, remap=False) -> Material:
+    """TranslucentMaterial (material/translucent.rs; defaults renderprocess.rs:695-706)."""
+    return Material(kind=5, remap_roughness=int(remap), kd=tuple(kd), ks=tuple(ks), kr=tuple(reflect), kt=tuple(transmit),
+                    roughness=roughness, u_roughness=-1, v_roughness=-1)
+
+
+def disney(color=(0.5,) * 3, metallic=0.0, eta=1.5, roughness=0.5, specular_tint=0.0, anisotropic=0.0, sheen=0.0, sheen_tint=0.5,
+           clearcoat=0.0, clearcoat_gloss=1.0, spec_trans=0.0, scatter_distance=(0.0,) * 3, thin=False, flatness=0.0,
+           diff_trans=1.0) -> Material:
+    """DisneyMaterial (material/disney.rs; defaults renderprocess.rs:810-836)."""
+    return Material(kind=6, kd=tuple(color), metallic=metallic, eta=eta, roughness=roughness, specular_tint=specular_tint,
+                    anisotropic=anisotropic, sheen=sheen, sheen_tint=sheen_tint, clearcoat=clearcoat,
+                    clearcoat_gloss=clearcoat_gloss, spec_trans=spec_trans, scatter_distance=tuple(scatter_distance),
+                    thin=int(thin), flatness=flatness, diff_trans=diff_trans, u_roughness=-1, v_roughness=-1)
+
+
+def debug_material() -> Material:
+    """DebugMaterial (material/debug_material.rs)."""
+    return Material(kind=7, u_roughness=-1, v_roughness=-1)
 
 
 def point_light(intensity=(1.0, 1.0, 1.0)) -> Light:

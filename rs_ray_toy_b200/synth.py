@@ -315,6 +315,81 @@ def scene_env_and_images(directory, xres=192, yres=108, nsamp=9, integrator="Pat
     return path
 
 
+def scene_more_materials(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5, env=False):
+    """Config 1's cubes plus five spheres carrying the materials SURVEY §8f row 3 still lacked: TranslucentMaterial (four
+    lobes, one with a textured kd and remapped roughness), DisneyMaterial in five settings (default-ish with sheen and
+    clearcoat; metallic and anisotropic; thin with all eight lobes; specular transmission; texture-driven color,
+    metallic and roughness) and the Debug material.  Point lights, plus an environment map when `env`."""
+    import json
+    import os
+    os.makedirs(directory, exist_ok=True)
+    cfg = json.loads(open(scene_c1(directory, xres=xres, yres=yres, nsamp=nsamp, integrator=integrator, max_depth=max_depth)).read())
+    # a material parameter is a texture NAME (fetch_float_texture / fetch_rgb_texture, renderprocess.rs:614-661: an inline
+    # number is ignored and the default used), so every value below is declared as a constant texture first
+    ftex, ctex = [], []
+
+    def f(v):  # one texture per distinct value: the device table holds 32 rows
+        name = "f_" + str(v).replace(".", "_")
+        if all(t["texture_name"] != name for t in ftex):
+            ftex.append(_const_float_texture(name, v))
+        return name
+
+    def c(r, g, b):
+        name = f"c_{len(ctex)}"
+        ctex.append(_const_rgb_texture(name, (r, g, b)))
+        return name
+
+    cfg["materials"] = [
+        {"material_type": "TranslucentMaterial", "material_name": "m_trans", "kd": c(0.3, 0.5, 0.4), "ks": c(0.3, 0.3, 0.3),
+         "reflect": c(0.5, 0.5, 0.5), "transmit": c(0.6, 0.5, 0.7), "roughness": f(0.2)},
+        {"material_type": "TranslucentMaterial", "material_name": "m_trans_tex", "kd": "c_checks", "roughness": f(0.3),
+         "remap_roughness": True, "transmit": c(0.9, 0.9, 0.9)},
+        {"material_type": "DisneyMaterial", "material_name": "m_disney", "color": c(0.6, 0.3, 0.2), "roughness": f(0.4), "sheen": f(0.6),
+         "sheen_tint": f(0.3), "clearcoat": f(0.8), "clearcoat_gloss": f(0.7), "specular_tint": f(0.4)},
+        {"material_type": "DisneyMaterial", "material_name": "m_disney_metal", "color": c(0.9, 0.7, 0.3), "metallic": f(0.85),
+         "anisotropic": f(0.6), "roughness": f(0.35)},
+        {"material_type": "DisneyMaterial", "material_name": "m_disney_thin", "color": c(0.3, 0.7, 0.5), "thin": True, "spec_trans": f(0.5),
+         "flatness": f(0.4), "diff_trans": f(0.6), "sheen": f(0.5), "clearcoat": f(0.5), "roughness": f(0.45), "eta": f(1.3)},
+        {"material_type": "DisneyMaterial", "material_name": "m_disney_glass", "color": c(0.8, 0.85, 0.9), "spec_trans": f(0.7),
+         "roughness": f(0.25), "eta": f(1.45)},
+        {"material_type": "DisneyMaterial", "material_name": "m_disney_tex", "color": "c_checks", "metallic": "f_checks",
+         "roughness": "f_rough", "clearcoat": f(0.3)},
+        {"material_type": "Debug", "material_name": "m_debug"},
+        # a MixMaterial whose second name is unknown is skipped by the reference's loader (renderprocess.rs:681-693)
+        {"material_type": "MixMaterial", "material_name": "m_mix", "mat1": "m_trans", "mat2": "nowhere"}]
+    cfg["float_texture"] = ftex + [
+        _const_float_texture("f_lo", 0.15), _const_float_texture("f_hi", 0.9),
+        {"texture_name": "f_checks", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "f_lo", "t2": "f_hi",
+         "mapping": {"mapping": "uv", "su": 6.0, "sv": 6.0, "du": 0.0, "dv": 0.0}},
+        {"texture_name": "f_rough", "texture_type": "BilerpTexture", "v00": 0.15, "v01": 0.7}]
+    cfg["rgb_texture"] = ctex + [
+        _const_rgb_texture("c_red", (0.7, 0.2, 0.1)), _const_rgb_texture("c_blue", (0.1, 0.3, 0.8)),
+        {"texture_name": "c_checks", "texture_type": "CheckerBoardTexture", "aamode": "none", "t1": "c_red", "t2": "c_blue",
+         "mapping": {"mapping": "uv", "su": 4.0, "sv": 4.0, "du": 0.0, "dv": 0.0}}]
+    prim = cfg["Aggregate"]["primitives"][0]
+    inst = prim["instances"]
+    prims = []
+    for k, name in enumerate(("m_trans", "m_disney", "m_disney_thin")):
+        q = dict(prim)
+        q["material_name"] = name
+        q["instances"] = [inst[k]]
+        prims.append(q)
+    spheres = [("m_trans_tex", [33.0, 1.8, -1.2]), ("m_disney_metal", [33.4, -1.6, 1.9]), ("m_disney_glass", [37.0, 2.6, 0.2]),
+               ("m_disney_tex", [36.0, 0.2, 5.2]), ("m_debug", [34.0, 2.9, 4.6]), ("m_mix", [31.0, 0.0, 0.0])]
+    for name, pos in spheres:
+        prims.append({"primitive_type": "sphere", "material_name": name, "radius": 0.85, "world_pos": pos})
+    cfg["Aggregate"]["primitives"] = prims
+    if env:
+        write_test_png(os.path.join(directory, "env.png"), 200, 90, seed=3)
+        e = {"light_type": "infinite", "mapname": "env.png", "l": {"values": [1.5, 1.5, 1.5]}}
+        cfg["lights"] = [e] + cfg["lights"][:1]
+        cfg["infinite_lights"] = [e]
+    path = os.path.join(directory, "scene_materials.json")
+    with open(path, "w") as f:
+        json.dump(cfg, f, indent=1)
+    return path
+
+
 def scene_area_lights(directory, xres=192, yres=108, nsamp=9, integrator="Path", max_depth=5):
     """Config 1's cubes lit by two DiffuseAreaLights: a sphere emitter above the cubes and
     triangle 4 of cube.obj (the light shape is the raw mesh triangle, Q7), plus one point light.  The emitters

@@ -15,7 +15,7 @@ pub const RRT_BUILD_FAST: u32 = 0;
 pub const RRT_BUILD_LITERAL: u32 = 1;
 pub const RRT_BUILD_DEVICE_LBVH: u32 = 2;
 pub const RRT_MAX_TEXTURES: usize = 32;
-pub const RRT_MATERIAL_SLOTS: usize = 12;
+pub const RRT_MATERIAL_SLOTS: usize = 23;
 
 #[repr(C)] pub struct rrt_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rrt_scene { _p: [u8; 0] }
@@ -28,13 +28,18 @@ pub struct rrt_ray { pub o: [f64; 3], pub d: [f64; 3], pub t_max: f64, pub time:
 #[repr(C)] #[derive(Copy, Clone, Debug, Default)]
 pub struct rrt_hit { pub prim_id: u32, pub reserved: u32, pub t: f64, pub u: f64, pub v: f64 }
 
-/// material/{matte,plastic,metal,mirror,glass}.rs with constant parameters (kind: 0 Matte .. 4 Glass)
+/// material/{matte,plastic,metal,mirror,glass,translucent,disney,debug_material}.rs with constant parameters
+/// (kind: 0 Matte .. 4 Glass, 5 Translucent, 6 Disney, 7 Debug)
 #[repr(C)] #[derive(Copy, Clone, Debug)]
 pub struct rrt_material {
     pub kind: u32, pub remap_roughness: u32,
     pub kd: [f64; 3], pub ks: [f64; 3], pub kr: [f64; 3], pub kt: [f64; 3],
     pub metal_eta: [f64; 3], pub metal_k: [f64; 3],
     pub sigma: f64, pub roughness: f64, pub u_roughness: f64, pub v_roughness: f64, pub eta: f64,
+    pub metallic: f64, pub specular_tint: f64, pub anisotropic: f64, pub sheen: f64, pub sheen_tint: f64,
+    pub clearcoat: f64, pub clearcoat_gloss: f64, pub spec_trans: f64, pub flatness: f64, pub diff_trans: f64,
+    pub scatter_distance: [f64; 3],
+    pub thin: u32, pub pad: u32,
 }
 /// one row of the flattened texture table (kind: 0 Constant .. 8 Wrinkled, 9 Image)
 #[repr(C)] #[derive(Copy, Clone, Debug)]
@@ -79,7 +84,7 @@ pub struct rrt_render_desc {
 // the C sizes (tests/test_capi_exports.py compares them with sizeof on the C side)
 const _: () = assert!(size_of::<rrt_ray>() == 64);
 const _: () = assert!(size_of::<rrt_hit>() == 32);
-const _: () = assert!(size_of::<rrt_material>() == 192);
+const _: () = assert!(size_of::<rrt_material>() == 304);
 const _: () = assert!(size_of::<rrt_texture>() == 312);
 const _: () = assert!(size_of::<rrt_light>() == 624);
 const _: () = assert!(size_of::<rrt_render_desc>() == 256);

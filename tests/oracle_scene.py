@@ -14,7 +14,8 @@ import numpy as np
 
 import oracle_lib as O
 
-MAT_KIND = {"MatteMaterial": 0, "PlasticMaterial": 1, "MetalMaterial": 2, "MirrorMaterial": 3, "GlassMaterial": 4}
+MAT_KIND = {"MatteMaterial": 0, "PlasticMaterial": 1, "MetalMaterial": 2, "MirrorMaterial": 3, "GlassMaterial": 4,
+            "TranslucentMaterial": 5, "DisneyMaterial": 6, "Debug": 7}
 FILTER_KIND = {"BoxFilter": 0, "GaussianFilter": 1, "TriangleFilter": 2}
 
 
@@ -240,13 +241,16 @@ class Textures:
         return d, -1
 
 
-MAT_ROW = 40
+MAT_ROW = 72
+# Disney block of a material row: 40 + k the value, 54 + k its texture id (k = 10: scatter_distance, value at 50:53)
+DISNEY_PARAMS = (("metallic", 0.0), ("specular_tint", 0.0), ("anisotropic", 0.0), ("sheen", 0.0), ("sheen_tint", 0.5),
+                 ("clearcoat", 0.0), ("clearcoat_gloss", 1.0), ("spec_trans", 0.0), ("flatness", 0.0), ("diff_trans", 1.0))
 # texture-id slots of a material row (26 + k): kd ks kr kt eta_rgb k_rgb sigma roughness u_roughness v_roughness eta
 T_KD, T_KS, T_KR, T_KT, T_ETA_RGB, T_K_RGB, T_SIGMA, T_ROUGH, T_UR, T_VR, T_ETA, T_BUMP = range(12)
 
 
 def material_row(cfg, tex: Textures):
-    """make_materials (renderprocess.rs:664-871) -> the oracle's 40-double material record."""
+    """make_materials (renderprocess.rs:664-871) -> the oracle's 72-double material record."""
     kind = MAT_KIND.get(cfg.get("material_type", ""))
     if kind is None:
         return None
@@ -254,6 +258,7 @@ def material_row(cfg, tex: Textures):
     r[0] = kind
     r[21] = r[22] = -1.0
     r[26:38] = -1
+    r[54:65] = -1
 
     def rgb(lo, slot, key, default):
         r[lo:lo + 3], r[26 + slot] = tex.rgbval(cfg, key, default)
@@ -283,6 +288,22 @@ def material_row(cfg, tex: Textures):
         flt(23, T_ETA, "eta", 1.5)
         flt(21, T_UR, "u_roughness", 0.0)
         flt(22, T_VR, "v_roughness", 0.0)
+    elif kind == 5:                       # renderprocess.rs:695-720
+        rgb(1, T_KD, "kd", 0.25)
+        rgb(4, T_KS, "ks", 0.25)
+        flt(20, T_ROUGH, "roughness", 0.1)
+        rgb(7, T_KR, "reflect", 0.25)
+        rgb(10, T_KT, "transmit", 0.25)
+    elif kind == 6:                       # renderprocess.rs:810-860
+        rgb(1, T_KD, "color", 0.5)
+        flt(23, T_ETA, "eta", 1.5)
+        flt(20, T_ROUGH, "roughness", 0.5)
+        for k, (key, default) in enumerate(DISNEY_PARAMS):
+            r[40 + k], r[54 + k] = tex.fval(cfg, key, default)
+        r[50:53], r[64] = tex.rgbval(cfg, "scatter_distance", 0.0)
+        r[53] = 1.0 if cfg.get("thin", False) else 0.0
+    if kind == 7:                         # DebugMaterial takes no parameters, not even a bump map (renderprocess.rs:861-863)
+        return r
     r[24] = 1.0 if cfg.get("remap_roughness", False) else 0.0
     bump = cfg.get("bump_map")            # fetch_float_texture_opt(.., "bump_map", None) (renderprocess.rs:704-705)
     r[37] = -1
@@ -415,6 +436,9 @@ class LoadedScene:
         tex = Textures(cfg)
         rows, self.mat_index = [], {}
         for m in cfg.get("materials", []) or []:
+            if m.get("material_type") == "MixMaterial" and m.get("mat1", "") in self.mat_index and m.get("mat2", "") in self.mat_index:
+                # renderprocess.rs:681-692 indexes scene_global.materials, which is still empty while make_materials runs (Q25)
+                raise ValueError("MixMaterial over two existing materials: the reference panics while loading (Q25)")
             row = material_row(m, tex)
             if row is not None:
                 self.mat_index[m.get("material_name", "DefaultMaterialName")] = len(rows)
@@ -465,7 +489,7 @@ class LoadedScene:
         L.orc_add_env_image.restype = C.c_int32
         L.orc_add_env_image.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_set_infinite_lights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-        reached = set(int(t) for t in self.materials[:, 26:38].reshape(-1) if t >= 0)
+        reached = set(int(t) for t in np.concatenate([self.materials[:, 26:38], self.materials[:, 54:65]], axis=1).reshape(-1) if t >= 0)
         for i in range(len(tex.rows) - 1, -1, -1):       # children have smaller indices
             if i in reached and tex.rows[i][0] in (TEX_SCALE, TEX_MIX, TEX_CHECKER2D, TEX_CHECKER3D):
                 reached |= {int(tex.rows[i][4]), int(tex.rows[i][5])} | ({int(tex.rows[i][6])} if tex.rows[i][0] == TEX_MIX else set())

@@ -205,14 +205,14 @@ def test_product_loader_matches_oracle_loader(tmp_path):
         assert (d.aperture_diameter, d.focus_distance, d.nsamp) == (prm[20], prm[21], prm[23])
         assert (d.integrator_kind, d.max_depth, d.rr_threshold) == (prm[26], prm[27], prm[28])
     # the sample scene as shipped: Debug integrator (always "all" lights), StratifiedSampler defaults, the Debug material
-    # and the unreferenced ImageTexture skipped by both loaders
+    # (declared, named by no primitive) and the unreferenced ImageTexture skipped by both loaders
     shipped = synth.scene_c1_as_shipped(str(tmp_path / "c1s"))
     info, d = render.json_probe(shipped)
     prm, _ = S.render_params(S.load(shipped).cfg)
     assert (d.sampler_kind, d.strat_xsamp, d.strat_ysamp, d.strat_dimension, d.strat_jitter) == (1, 4, 4, 4, 1) == \
         (prm[38], prm[40], prm[41], prm[42], prm[39])
     assert (d.integrator_kind, d.max_depth, d.light_strategy, d.nsamp) == (2, 5, 1, 16) and prm[26] == 2 and prm[23] == 16
-    assert info["materials"] == 3 and info["lights"] == 3
+    assert info["materials"] == 4 == S.load(shipped).materials.shape[0] and info["lights"] == 3
     _, d = render.json_probe(shipped, {"Sampler": {"sampler_type": "StratifiedSampler", "xsamp": 3, "ysamp": 5, "dimension": 2, "jitter": False}})
     assert (d.strat_xsamp, d.strat_ysamp, d.strat_dimension, d.strat_jitter, d.nsamp) == (3, 5, 2, 0, 15)
     ov = {"Integrator": {"integrator_type": "Path", "max_depth": 3, "rr_threshold": 0.5}}

@@ -191,11 +191,42 @@ def test_loaders_agree(tmp_path):
         assert np.array_equal(row[20:28], np.array(list(t.map)))
         if t.kind == R.TEX_CHECKER3D or t.mapping >= R.TEXMAP_SPHERICAL:
             assert np.array_equal(row[28:44], np.array(list(t.world_to_texture)))
-    assert np.array_equal(sc.materials[:, 26:38].astype(np.int32), slots)
+    assert np.array_equal(np.concatenate([sc.materials[:, 26:38], sc.materials[:, 54:65]], axis=1).astype(np.int32), slots)
     for row, m in zip(sc.materials, mats):
         assert int(row[0]) == m.kind
         assert np.array_equal(row[1:4], list(m.kd)) and np.array_equal(row[4:7], list(m.ks))
         assert row[19] == m.sigma and row[20] == m.roughness
+
+
+def test_loaders_agree_on_translucent_disney_debug_and_mix(tmp_path):
+    """make_materials' remaining arms (renderprocess.rs:678-720, 810-866): the product's loader and the oracle's build the
+    same records — defaults, texture slots, the Disney block — skip a MixMaterial that names an unknown material and
+    refuse the one the reference panics on (Q25)."""
+    path = synth.scene_more_materials(str(tmp_path))
+    sc = S.load(path)
+    tex, mats, slots = R.json_texture_probe(path)
+    assert len(mats) == sc.materials.shape[0] == 8          # m_mix has no entry
+    assert [m.kind for m in mats] == [5, 5, 6, 6, 6, 6, 6, 7]
+    assert np.array_equal(np.concatenate([sc.materials[:, 26:38], sc.materials[:, 54:65]], axis=1).astype(np.int32), slots)
+    names = [n for n, _ in S.DISNEY_PARAMS]
+    for row, m in zip(sc.materials, mats):
+        assert int(row[0]) == m.kind
+        assert np.array_equal(row[1:4], list(m.kd)) and np.array_equal(row[4:7], list(m.ks))
+        assert np.array_equal(row[7:10], list(m.kr)) and np.array_equal(row[10:13], list(m.kt))
+        assert row[20] == m.roughness and row[24] == m.remap_roughness
+        if m.kind == 6:
+            assert row[23] == m.eta and row[53] == m.thin
+            assert [row[40 + k] for k in range(10)] == [getattr(m, n) for n in names]
+            assert np.array_equal(row[50:53], list(m.scatter_distance))
+    assert slots[6, R.SLOT_KD] >= 0 and slots[6, R.SLOT_METALLIC] >= 0 and slots[6, R.SLOT_ROUGHNESS] >= 0
+    cfg = json.loads(open(path).read())
+    cfg["materials"][-1]["mat2"] = "m_disney"
+    p2 = tmp_path / "mix.json"
+    p2.write_text(json.dumps(cfg))
+    with pytest.raises(ValueError, match="Q25"):
+        S.load(str(p2))
+    with pytest.raises(capi.RrtError, match="Q25"):
+        R.json_texture_probe(str(p2))
 
 
 def test_out_of_scope_textures_are_refused(tmp_path):
