@@ -933,11 +933,18 @@ void orc_halton_perms(uint64_t seed, uint16_t* out, uint32_t n) {
     std::memcpy(out, perms.data(), std::min<size_t>(n, perms.size()) * sizeof(uint16_t));
 }
 // BSDF probe for unit tests: evaluates f, pdf and one sample of a material's Bsdf in a frame with
-// shading normal +z, dpdu +x.  out: f(3), pdf, sample f(3), wi(3), pdf, sampled_type
-void orc_bsdf_probe(const double* m26, const double* wo3, const double* wi3, const double* u2, int32_t allow_multiple,
+// shading normal +z, dpdu +x.  `m72`: one orc_set_materials row.  out: f(3), pdf, sample f(3), wi(3), pdf, sampled_type
+void orc_bsdf_probe(const double* m72, const double* wo3, const double* wi3, const double* u2, int32_t allow_multiple,
                     double* out12) {
     Material mat;
-    const double* a = m26;
+    const double* a = m72;
+    {
+        double* ds[10] = {&mat.metallic, &mat.specular_tint, &mat.anisotropic, &mat.sheen, &mat.sheen_tint, &mat.clearcoat,
+                          &mat.clearcoat_gloss, &mat.spec_trans, &mat.flatness, &mat.diff_trans};
+        for (int k = 0; k < 10; ++k) *ds[k] = a[40 + k];
+        mat.scatter_distance = Rgb(a[50], a[51], a[52]);
+        mat.thin = a[53] != 0.0;
+    }
     mat.kind = (uint32_t)a[0];
     mat.kd = Rgb(a[1], a[2], a[3]); mat.ks = Rgb(a[4], a[5], a[6]); mat.kr = Rgb(a[7], a[8], a[9]);
     mat.kt = Rgb(a[10], a[11], a[12]); mat.eta_rgb = Rgb(a[13], a[14], a[15]); mat.k_rgb = Rgb(a[16], a[17], a[18]);

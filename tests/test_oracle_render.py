@@ -93,6 +93,122 @@ def test_bsdf_known_answers():
     assert np.allclose(out[4:7] * out[9] / out[10], 0.5)
 
 
+def _const_tex(values):
+    """A Textures table of constant float / rgb textures named after their position: (name -> value)."""
+    ft = [{"texture_name": n, "texture_type": "BilerpTexture", "v00": v, "v01": v} for n, v in values.items() if not isinstance(v, tuple)]
+    ct = [{"texture_name": n, "texture_type": "BilerpTexture", "v00": {"values": list(v)}, "v01": {"values": list(v)}}
+          for n, v in values.items() if isinstance(v, tuple)]
+    return S.Textures({"float_texture": ft, "rgb_texture": ct})
+
+
+def test_translucent_disney_debug_known_answers():
+    """The lobes of translucent.rs / disney.rs / debug_material.rs through Bsdf::f / pdf / sample_f, against the formulas
+    written out independently in numpy — including what the reference does differently from pbrt: the clearcoat lobe is
+    typed neither reflection nor transmission, so f() never contains it (Q37), and gtr1 divides by log10 (Q36)."""
+    wo = np.array([0.3, 0.2, np.sqrt(1 - 0.13)])
+    wi = np.array([-0.5, 0.1, np.sqrt(1 - 0.26)])
+    wt = wi * np.array([1, 1, -1.0])
+    sw = lambda c: np.clip(1 - c, 0, 1) ** 5
+    # ---- Translucent without its glossy pair: Lambertian reflection r * kd and Lambertian transmission t * kd
+    tex = _const_tex({"kd": (0.3, 0.5, 0.4), "black": (0.0, 0.0, 0.0), "r": (0.5, 0.6, 0.7), "t": (0.6, 0.5, 0.2)})
+    row = S.material_row({"material_type": "TranslucentMaterial", "kd": "kd", "ks": "black", "reflect": "r", "transmit": "t"}, tex)
+    out = _probe(row, wo, wi, (0.25, 0.6))
+    assert np.allclose(out[:3], np.array([0.5, 0.6, 0.7]) * [0.3, 0.5, 0.4] / np.pi, rtol=1e-14)
+    assert np.isclose(out[3], wi[2] / np.pi / 2, rtol=1e-14) and out[11] == 5 and out[9] > 0
+    out = _probe(row, wo, wt, (0.75, 0.6))       # the second lobe: sampled below the surface, DIFFUSE | TRANSMISSION
+    assert np.allclose(out[:3], np.array([0.6, 0.5, 0.2]) * [0.3, 0.5, 0.4] / np.pi, rtol=1e-14)
+    assert np.isclose(out[3], wi[2] / np.pi / 2, rtol=1e-14) and out[11] == 6 and out[9] < 0
+    assert np.isclose(out[10], -out[9] / np.pi / 2, rtol=1e-14)     # Q15: the other lobe's pdf (0 there) is added, then / 2
+    # all four lobes; a black reflect AND transmit -> no Bsdf at all (f = 0, nothing sampled)
+    row4 = S.material_row({"material_type": "TranslucentMaterial", "kd": "kd", "reflect": "r", "transmit": "t"}, tex)
+    kinds = [int(_probe(row4, wo, wi, ((k + 0.5) / 4, 0.4))[11]) for k in range(4)]
+    assert kinds == [5, 6, 9, 10]
+    none = _probe(S.material_row({"material_type": "TranslucentMaterial", "reflect": "black", "transmit": "black"}, tex), wo, wi, (0.3, 0.3))
+    assert not none.any()
+
+    # ---- Disney, solid: DisneyDiffuse + DisneyRetro + MicrofacetReflection(DisneyFresnel, separable G)
+    col, rough, eta, metallic, tint, aniso = np.array([0.6, 0.3, 0.2]), 0.4, 1.5, 0.3, 0.4, 0.5
+    tex = _const_tex({"col": tuple(col), "rough": rough, "metallic": metallic, "tint": tint, "aniso": aniso, "sheen": 0.6, "stint": 0.3,
+                      "cc": 0.8, "ccg": 0.7, "strans": 0.5, "flat": 0.4, "dt": 0.6})
+    base = {"material_type": "DisneyMaterial", "color": "col", "roughness": "rough", "metallic": "metallic", "specular_tint": "tint",
+            "anisotropic": "aniso"}
+    row = S.material_row(base, tex)
+    out = _probe(row, wo, wi, (0.1, 0.6))
+    dw = 1 - metallic
+    fo, fi = sw(wo[2]), sw(wi[2])
+    wh = (wo + wi) / np.linalg.norm(wo + wi)
+    cd = wi @ wh
+    diffuse = col * dw / np.pi * (1 - fo / 2) * (1 - fi / 2)
+    rr = 2 * rough * cd * cd
+    retro = col * dw / np.pi * rr * (fo + fi + fo * fi * (rr - 1))
+    aspect = np.sqrt(1 - aniso * 0.9)
+    ax, ay = max(rough ** 2 / aspect, 1e-3), max(rough ** 2 * aspect, 1e-3)
+
+    def D(h):
+        c2 = h[2] ** 2
+        s2 = 1 - c2
+        return 1 / (np.pi * ax * ay * c2 * c2 * (1 + (s2 / c2) * (h[0] ** 2 / s2 / ax ** 2 + h[1] ** 2 / s2 / ay ** 2)) ** 2)
+
+    def lam(w):
+        s2 = 1 - w[2] ** 2
+        a2 = (w[0] ** 2 * ax ** 2 + w[1] ** 2 * ay ** 2) / s2
+        return (-1 + np.sqrt(1 + a2 * s2 / w[2] ** 2)) / 2
+
+    def fr_diel(c, ei, et):
+        st = ei / et * np.sqrt(max(0, 1 - c * c))
+        ct = np.sqrt(max(0, 1 - st * st))
+        rl = (et * c - ei * ct) / (et * c + ei * ct)
+        rp = (ei * c - et * ct) / (ei * c + et * ct)
+        return (rl * rl + rp * rp) / 2
+
+    lum = col @ [0.212671, 0.715160, 0.072169]
+    ctint = col / lum
+    r0 = ((eta - 1) / (eta + 1)) ** 2
+    cspec0 = (1 - metallic) * ((1 - tint) * np.ones(3) + tint * ctint) * r0 + metallic * col
+    ch = wi @ wh
+    fres = (1 - metallic) * fr_diel(ch, 1.0, eta) + metallic * ((1 - sw(ch)) * cspec0 + sw(ch))
+    G = 1 / (1 + lam(wo)) / (1 + lam(wi))          # separable, not 1 / (1 + lam + lam)
+    spec = D(wh) * G * fres / (4 * wo[2] * wi[2])
+    assert np.allclose(out[:3], diffuse + retro + spec, rtol=1e-12)
+    pdf_spec = D(wh) / (1 + lam(wo)) * abs(wo @ wh) / wo[2] / (4 * (wo @ wh))
+    assert np.isclose(out[3], (2 * wi[2] / np.pi + pdf_spec) / 3, rtol=1e-12)
+    # sheen adds c_sheen * sheen * diffuse_weight * schlick(cos_d)
+    with_sheen = _probe(S.material_row(dict(base, sheen="sheen", sheen_tint="stint"), tex), wo, wi, (0.1, 0.6))
+    csheen = (1 - 0.3) * np.ones(3) + 0.3 * ctint
+    assert np.allclose(with_sheen[:3] - out[:3], csheen * 0.6 * dw * sw(cd), rtol=1e-9)
+    # clearcoat: in the lobe count and the pdf, never in f (Q37); pdf through gtr1 with log10 (Q36)
+    cc = _probe(S.material_row(dict(base, clearcoat="cc", clearcoat_gloss="ccg"), tex), wo, wi, (0.9, 0.6))
+    assert np.array_equal(cc[:3], out[:3])
+    gloss = 0.1 * (1 - 0.7) + 0.001 * 0.7
+    a2 = gloss * gloss
+    gtr1 = (a2 - 1) / (np.pi * np.log10(a2) * (1 + (a2 - 1) * wh[2] ** 2))
+    pdf_cc = gtr1 * wh[2] / (4 * (wo @ wh))
+    assert np.isclose(cc[3], (2 * wi[2] / np.pi + pdf_spec + pdf_cc) / 4, rtol=1e-12)
+    assert cc[11] == 12                                     # u0 = 0.9 of four lobes: the clearcoat, DIFFUSE | GLOSSY
+    swi = cc[7:10]
+    swh = (wo + swi) / np.linalg.norm(wo + swi)
+    gs = lambda c: 1 / (c + np.sqrt(0.0625 + c * c - 0.0625 * c * c))
+    f_cc = 0.8 * gs(wo[2]) * gs(swi[2]) * (0.04 * (1 - sw(wo @ swh)) + sw(wo @ swh)) * \
+        ((a2 - 1) / (np.pi * np.log10(a2) * (1 + (a2 - 1) * swh[2] ** 2))) / 4
+    assert np.allclose(cc[4:7], f_cc, rtol=1e-9)            # sample_f hands back the chosen lobe's f alone (Q15)
+    # ---- Disney, thin, everything on: the eight lobes in the order disney.rs adds them
+    thin = dict(base, thin=True, sheen="sheen", clearcoat="cc", spec_trans="strans", flatness="flat", diff_trans="dt")
+    rowt = S.material_row(thin, tex)
+    kinds = [int(_probe(rowt, wo, wi, ((k + 0.5) / 8, 0.4))[11]) for k in range(8)]
+    assert kinds == [5, 5, 5, 5, 9, 12, 10, 6]
+    below = _probe(rowt, wo, wt, (0.99, 0.4))
+    dwt = (1 - metallic) * (1 - 0.5)
+    assert np.isclose(below[4] , col[0] * 0.6 / np.pi, rtol=1e-14)   # LambertianTransmission(c * diff_trans)
+    flat_f = _probe(rowt, wo, wi, (0.01, 0.4))
+    assert np.allclose(flat_f[4:7] / (col * dwt * (1 - 0.4) * (1 - 0.6) / np.pi),
+                       (1 - sw(wo[2]) / 2) * (1 - sw(flat_f[9]) / 2), rtol=1e-12)
+    # ---- Debug: two constant lobes, the "specular" one cosine-sampled like the diffuse one
+    row = S.material_row({"material_type": "Debug"}, S.Textures({}))
+    out = _probe(row, wo, wi, (0.75, 0.6))
+    assert out[:3].tolist() == [0.0, 1.0, 1.0] and np.isclose(out[3], wi[2] / np.pi)
+    assert out[4:7].tolist() == [0.0, 0.0, 1.0] and out[11] == 17 and np.isclose(out[10], out[9] / np.pi / 2)
+
+
 def test_rough_glass_known_answers():
     """GlassMaterial with non-zero roughness (glass.rs:77-108): MicrofacetReflection + MicrofacetTransmission
     (reflection.rs:1028-1146) over an anisotropic Trowbridge-Reitz distribution, against the textbook formulas
