@@ -956,14 +956,16 @@ DeviceAggregate::~DeviceAggregate() {
     if (d_prims_) cudaFree(d_prims_);
     if (d_inst_) cudaFree(d_inst_);
     if (d_gspheres_) cudaFree(d_gspheres_);
-    Workspace& w = ws_;
-    if (w.d_bins) cudaFree(w.d_bins);
-    if (w.d_block_sums) cudaFree(w.d_block_sums);
-    if (w.d_small) cudaFree(w.d_small);
-    if (w.d_key) cudaFree(w.d_key);
-    if (w.d_rank) cudaFree(w.d_rank);
-    if (w.d_perm) cudaFree(w.d_perm);
-    if (w.last_use) cudaEventDestroy(w.last_use);
+    for (auto& kv : ws_) {
+        Workspace& w = kv.second;
+        if (w.d_bins) cudaFree(w.d_bins);
+        if (w.d_block_sums) cudaFree(w.d_block_sums);
+        if (w.d_small) cudaFree(w.d_small);
+        if (w.d_key) cudaFree(w.d_key);
+        if (w.d_rank) cudaFree(w.d_rank);
+        if (w.d_perm) cudaFree(w.d_perm);
+        if (w.last_use) cudaEventDestroy(w.last_use);
+    }
 }
 
 int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prims_in_node, std::string* err, bool device_lbvh) {
@@ -1540,8 +1542,7 @@ int DeviceAggregate::import_blob(int device, const void* blob, uint64_t bytes, u
     return RRT_OK;
 }
 
-int DeviceAggregate::ensure_workspace(uint64_t n, std::string* err) const {
-    Workspace& w = ws_;
+int DeviceAggregate::ensure_workspace(Workspace& w, uint64_t n, std::string* err) const {
     if (!w.d_small) {
         RRT_CUDA(cudaMalloc(&w.d_bins, (size_t)kSortBins * sizeof(uint32_t)));
         RRT_CUDA(cudaMalloc(&w.d_block_sums, (size_t)(kSortBins / kScanBlock) * sizeof(uint32_t)));
@@ -1576,11 +1577,11 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     std::lock_guard<std::mutex> lock(ws_mutex_);
-    int rc = ensure_workspace(n, err);
+    Workspace& w = (ws_.count(stream) || ws_.size() < kMaxWorkspaces) ? ws_[stream] : ws_.begin()->second;
+    int rc = ensure_workspace(w, n, err);
     if (rc != RRT_OK) return rc;
-    Workspace& w = ws_;
-    // the scratch buffers are shared by every call on this aggregate: order this call after the last one
-    if (w.used) RRT_CUDA(cudaStreamWaitEvent(s, w.last_use, 0));
+    // a workspace that another stream used last (only past kMaxWorkspaces streams): order this call after that one
+    if (w.used && w.last_stream != stream) RRT_CUDA(cudaStreamWaitEvent(s, w.last_use, 0));
     uint32_t* small = static_cast<uint32_t*>(w.d_small);  // [0..1] cursor, [2] max_bin, [3] use_perm
     RRT_CUDA(cudaMemsetAsync(small, 0, 128, s));
     const bool sorting = sort_rays_ && n >= 4096;
@@ -1639,6 +1640,7 @@ int DeviceAggregate::trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, u
 #endif
     RRT_CUDA(cudaEventRecord(w.last_use, s));
     w.used = true;
+    w.last_stream = stream;
     if (launches) *launches = count;
     return RRT_OK;
 }

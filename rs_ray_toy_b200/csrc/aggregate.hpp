@@ -3,6 +3,7 @@
 // the opaque stream pointer) so capi.cpp can be compiled by the plain host compiler.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -88,21 +89,25 @@ class DeviceAggregate : public RayTracer {
     const AggregateStats& stats() const override { return stats_; }
 
   private:
-    // Scratch for the ray sort + the persistent kernel's cursor, shared by all calls (stream-ordered).
+    // Scratch for the ray sort + the persistent kernel's cursor: one per stream that calls in (the host-buffer pipeline
+    // of capi.cpp runs three), so that a chunk's sort does not wait for the previous chunk's walk; past kMaxWorkspaces
+    // streams the first one is shared, ordered by an event.
+    static constexpr size_t kMaxWorkspaces = 8;
     struct Workspace {
         uint32_t *d_bins = nullptr, *d_block_sums = nullptr, *d_key = nullptr, *d_rank = nullptr, *d_perm = nullptr;
         void* d_small = nullptr;
         uint64_t capacity = 0;
         struct CUevent_st* last_use = nullptr;
         bool used = false;
+        void* last_stream = nullptr;
         int n_sms = 0;
         void* window_stream = (void*)-1;  // the stream that last received the L2 access-policy window
     };
-    int ensure_workspace(uint64_t n, std::string* err) const;
+    int ensure_workspace(Workspace& w, uint64_t n, std::string* err) const;
     template <bool ANY>
     int trace(uint64_t n, const rrt_ray* d_rays, rrt_hit* d_hits, uint8_t* d_occ, void* stream, std::string* err,
               int* launches, const uint32_t* n_dev) const;
-    mutable Workspace ws_;
+    mutable std::map<void*, Workspace> ws_;
     mutable std::mutex ws_mutex_;
     bool sort_rays_ = true;
     int stack_levels_ = 2;

@@ -44,7 +44,8 @@ int cuda_fail(const char* what, cudaError_t e) {
         if (e_ != cudaSuccess) return cuda_fail(#call, e_); \
     } while (0)
 
-constexpr int kSlots = 3;  // pipeline depth of the host-buffer calls
+constexpr int kSlots = 4;  // pipeline depth of the host-buffer calls: with three, the small chunks that end a batch wait for the
+                           // slot of a full chunk three places earlier (profiles/r2_e2e_trace.txt); 96 MiB of device memory each
 // rays per pipeline slot (64 B each); RRT_HOST_CHUNK overrides for experiments
 uint64_t chunk_rays() {
     static const uint64_t v = [] {
@@ -55,6 +56,28 @@ uint64_t chunk_rays() {
     return v;
 }
 #define kChunkRays (chunk_rays())
+// The pipeline's fill (first H2D, nothing to trace yet) and drain (last kernel + D2H, nothing left to upload) are each one
+// chunk long, so the chunks at both ends of a batch are small and double towards the middle: 128 Ki, 128 Ki, 256 Ki, 512 Ki,
+// 1 Mi ... 1 Mi, 512 Ki, 256 Ki, 128 Ki.  Measured on a 16 Mi-ray batch: 701 -> 726 Mrays/s (profiles/r2_e2e_taper.txt); the
+// link's own floor for 1 GiB up + 0.5 GiB down at once is 20.5 ms = 819 Mrays/s (profiles/r2_pcie_probe.txt), and the
+// uploads run at 49.5 GB/s while hits stream down (55.5 GB/s alone): 21.7 ms + the last chunk's walk (0.5 ms: a batch of
+// any size takes that long) is what is left (profiles/r2_e2e_trace.txt).  RRT_HOST_TAPER=0: off.
+uint64_t tapered_chunk(uint64_t done, uint64_t n) {
+    static const bool taper = [] {
+        const char* e = std::getenv("RRT_HOST_TAPER");
+        return !(e && e[0] == '0');
+    }();
+    const uint64_t full = kChunkRays, left = n - done;
+    uint64_t c = full;
+    if (taper) {
+        const uint64_t floor_c = full >> 3 ? full >> 3 : 1;
+        const uint64_t up = done > floor_c ? done : floor_c;               // doubling from the start
+        const uint64_t down = left / 2 > floor_c ? left / 2 : floor_c;     // halving towards the end
+        c = up < c ? up : c;
+        c = down < c ? down : c;
+    }
+    return left < c ? left : c;
+}
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -135,11 +158,26 @@ int host_batch(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, void* ou
     std::string err;
     uint64_t done = 0;
     int k = 0;
+    // RRT_HOST_TRACE=1 (diagnostic): the device-side timeline of the pipeline, one line per chunk on stderr
+    static const bool tracing = std::getenv("RRT_HOST_TRACE") != nullptr;
+    struct Marks { cudaEvent_t e[4]; uint64_t cnt; };
+    std::vector<Marks> marks;
+    auto mark = [&](int which, cudaStream_t st) {
+        if (!tracing) return;
+        cudaEventCreate(&marks.back().e[which]);
+        cudaEventRecord(marks.back().e[which], st);
+    };
     while (done < n) {
         Slot& s = ctx->slots[k % kSlots];
-        uint64_t cnt = n - done < kChunkRays ? n - done : kChunkRays;
+        const uint64_t cnt = tapered_chunk(done, n);
+        if (tracing) {
+            marks.push_back(Marks{});
+            marks.back().cnt = cnt;
+        }
+        mark(0, s.stream);
         // a slot is reused only after its previous D2H has drained (stream order)
         CAPI_CUDA(cudaMemcpyAsync(s.d_rays, rays + done, cnt * sizeof(rrt_ray), cudaMemcpyHostToDevice, s.stream));
+        mark(1, s.stream);
         int launched = 0;
         if (ANY)
             rc = scene->agg->any_hit(cnt, s.d_rays, static_cast<uint8_t*>(s.d_out), s.stream, &err, &launched);
@@ -151,12 +189,24 @@ int host_batch(const rrt_scene* scene, uint64_t n, const rrt_ray* rays, void* ou
             return fail(rc, err);
         }
         ctx->launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
+        mark(2, s.stream);
         CAPI_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + done * out_elem, s.d_out, cnt * out_elem,
                                   cudaMemcpyDeviceToHost, s.stream));
+        mark(3, s.stream);
         done += cnt;
         ++k;
     }
     for (auto& s : ctx->slots) CAPI_CUDA(cudaStreamSynchronize(s.stream));
+    if (tracing) {
+        for (size_t i = 0; i < marks.size(); ++i) {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], marks[0].e[0], marks[i].e[j]);
+            fprintf(stderr, "RRT_HOST_TRACE chunk %2zu %8llu rays: slot free %7.3f  h2d done %7.3f  traced %7.3f  d2h done %7.3f ms\n", i,
+                    (unsigned long long)marks[i].cnt, t[0], t[1], t[2], t[3]);
+            }
+        for (auto& m : marks)
+            for (auto& e : m.e) cudaEventDestroy(e);
+    }
     return RRT_OK;
 }
 
