@@ -991,14 +991,19 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     struct World {
         double v[9];
     };
-    std::vector<World> world(n);
-    std::vector<Aabb> boxes(n);
+    // (default-initialised buffers: the worker threads below touch — and so place — their own pages; a value-initialised
+    // std::vector would zero half a gigabyte on one thread first: measured 170 -> see profiles/r2_build_timing.txt)
+    RawBuf<World> world(n);
+    RawBuf<Aabb> boxes_buf(n);
+    Aabb* const boxes = boxes_buf.get();
     std::atomic<int> not_fp32{0}, clipped_with_own_transform{0};
-    std::vector<uint8_t> general(n, 0);  // spheres that need the object-space test (sphere_core.cuh)
+    RawBuf<uint8_t> general(n);  // spheres that need the object-space test (sphere_core.cuh)
     parallel_ranges(n, [&](size_t i0, size_t i1) {
     bool all_fp32 = true;
     for (size_t i = i0; i < i1; ++i) {
         const Primitive& pr = scene.prims[i];
+        new (&boxes[i]) Aabb();
+        general[i] = 0;
         if (pr.kind == SHAPE_TRIANGLE) {
             scene.world_triangle(i, world[i].v);
             for (int k = 0; k < 3; ++k) boxes[i].grow(&world[i].v[3 * k]);
@@ -1101,7 +1106,15 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     lap("bake to world space");
     // ---- frame: world box, fp32 margin, Node32 grid, node format ----
     Aabb world_box;
-    for (size_t i = 0; i < n; ++i) world_box.grow(boxes[i]);
+    {
+        std::mutex m;
+        parallel_ranges(n, [&](size_t i0, size_t i1) {
+            Aabb part;
+            for (size_t i = i0; i < i1; ++i) part.grow(boxes[i]);
+            std::lock_guard<std::mutex> lock(m);
+            world_box.grow(part);
+        });
+    }
     const NodeFrame frame = make_node_frame(world_box);
     const double scale = frame.scale, delta = frame.delta;
     const double* grid_lo = frame.grid_lo;
@@ -1113,11 +1126,19 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     bool quantise = RRT_NODE32 == 2;
     if (RRT_NODE32 == 1) {
         const double cells = 2.0 * ((double)grid_ext[0] + (double)grid_ext[1] + (double)grid_ext[2]) / 32768.0;
+        // (summed per contiguous range, then over the ranges in order: the same total whatever the thread count is not
+        // guaranteed to the last bit, and does not need to be — it is compared with 5 %)
         double growth = 0.0;
-        for (size_t i = 0; i < n; ++i) {
-            const double hp = (boxes[i].hi[0] - boxes[i].lo[0]) + (boxes[i].hi[1] - boxes[i].lo[1]) + (boxes[i].hi[2] - boxes[i].lo[2]);
-            growth += std::fmin(1.0, cells / std::fmax(hp, 1e-300));
-        }
+        std::mutex m;
+        parallel_ranges(n, [&](size_t i0, size_t i1) {
+            double part = 0.0;
+            for (size_t i = i0; i < i1; ++i) {
+                const double hp = (boxes[i].hi[0] - boxes[i].lo[0]) + (boxes[i].hi[1] - boxes[i].lo[1]) + (boxes[i].hi[2] - boxes[i].lo[2]);
+                part += std::fmin(1.0, cells / std::fmax(hp, 1e-300));
+            }
+            std::lock_guard<std::mutex> lock(m);
+            growth += part;
+        });
         quantise = growth / (double)n < 0.05;
     }
     if (const char* e = std::getenv("RRT_QUANTISE")) quantise = atoi(e) != 0;
@@ -1135,7 +1156,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     LbvhResult lb;
     bool on_device_ok = on_device;
     if (on_device) {
-        int rc = build_lbvh_device(device, boxes, std::min(max_leaf, lbvh_leaf), delta, quantise, grid_lo, grid_ext, &lb, err);
+        int rc = build_lbvh_device(device, AabbSpan(boxes, n), std::min(max_leaf, lbvh_leaf), delta, quantise, grid_lo, grid_ext, &lb, err);
         if (rc != RRT_OK) return rc;
         tree.max_depth = lb.max_depth + 1;
         tree.n_leaves = lb.n_leaves;
@@ -1151,7 +1172,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         SahParams sp;
         sp.max_leaf = max_prims_in_node == 0 ? 4 : max_prims_in_node;
         if (const char* e = std::getenv("RRT_SAH_CI")) sp.cost_intersect = atof(e);
-        build_sah(boxes, sp, &tree);
+        build_sah(AabbSpan(boxes, n), sp, &tree);
     }
     if (tree.max_depth + 2 > (uint32_t)kStack) {
         if (on_device_ok) cudaFree(lb.d_nodes);
@@ -1164,12 +1185,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     std::vector<Node64> nodes;
     nodes.reserve(tree.nodes.size() / 2 + 2);
     const bool wide = !all_fp32;
-    std::vector<PrimRec48> rec48;
-    std::vector<PrimRec96> rec96;
-    if (wide)
-        rec96.resize(n);
-    else
-        rec48.resize(n);
+    RawBuf<PrimRec48> rec48(wide ? 0 : n);  // every slot is written below: one record per primitive
+    RawBuf<PrimRec96> rec96(wide ? n : 0);
     size_t n_rec = 0;  // host tree: records are appended leaf by leaf
     auto make_record = [&](uint32_t pi, size_t slot) {
         {
@@ -1340,7 +1357,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     RRT_CUDA(cudaSetDevice(device));
     const size_t node_bytes = on_device_ok ? lb.node_bytes : (quantise ? nodes32.size() * sizeof(Node32) : nodes.size() * sizeof(Node64));
     const void* node_src = quantise ? (const void*)nodes32.data() : (const void*)nodes.data();
-    size_t prim_bytes = wide ? rec96.size() * sizeof(PrimRec96) : rec48.size() * sizeof(PrimRec48);
+    size_t prim_bytes = wide ? n * sizeof(PrimRec96) : n * sizeof(PrimRec48);
     if (on_device_ok) {
         d_nodes_ = lb.d_nodes;
     } else {
@@ -1348,7 +1365,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
         RRT_CUDA(cudaMemcpy(d_nodes_, node_src, node_bytes, cudaMemcpyHostToDevice));
     }
     RRT_CUDA(cudaMalloc(&d_prims_, prim_bytes));
-    RRT_CUDA(cudaMemcpy(d_prims_, wide ? (const void*)rec96.data() : (const void*)rec48.data(), prim_bytes,
+    RRT_CUDA(cudaMemcpy(d_prims_, wide ? (const void*)rec96.get() : (const void*)rec48.get(), prim_bytes,
                         cudaMemcpyHostToDevice));
     bool has_spheres = false;
     for (const Primitive& pr : scene.prims) has_spheres |= pr.kind == SHAPE_SPHERE;
@@ -1406,7 +1423,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
     stats_.n_leaves = tree.n_leaves;
     stats_.max_depth = tree.max_depth;
     stats_.device_bytes = node_bytes + prim_bytes;
-    stats_.n_records = wide ? rec96.size() : rec48.size();
+    stats_.n_records = n;
     stats_.wide_records = wide;
     stats_.n_prims = n;
     stats_.build_usec =

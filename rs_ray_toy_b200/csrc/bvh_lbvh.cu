@@ -8,6 +8,8 @@
 #include <array>
 #include <thread>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -264,9 +266,16 @@ __global__ void __launch_bounds__(256) depth_kernel(uint32_t n, const RadixNode*
 
 }  // namespace
 
-int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_leaf, double delta, bool quantise,
+int build_lbvh_device(int device, AabbSpan boxes, uint32_t max_leaf, double delta, bool quantise,
                       const double grid_lo[3], const float grid_ext[3], LbvhResult* out, std::string* err) {
     const auto t0 = std::chrono::steady_clock::now();
+    const bool timing = std::getenv("RRT_BUILD_TIMING") != nullptr;
+    auto lap = [&, t_last = t0](const char* what) mutable {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "RRT_BUILD_TIMING   lbvh: %-18s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const uint32_t n = (uint32_t)boxes.size();
     if (n < 2 || n <= max_leaf) {
         if (err) *err = "device LBVH needs more primitives than one leaf holds";
@@ -274,7 +283,7 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     }
     LB_CUDA(cudaSetDevice(device));
     // fp32 boxes rounded outward + the centroid frame
-    std::vector<BoxF> hb(n);
+    RawBuf<BoxF> hb(n);
     double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
     {
         unsigned nt = std::thread::hardware_concurrency();
@@ -303,6 +312,7 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
                 chi[k] = std::fmax(chi[k], part[t][3 + k]);
             }
     }
+    lap("fp32 boxes (host)");
     CentroidFrame fr;
     for (int k = 0; k < 3; ++k) {
         fr.lo[k] = down_f(clo[k]);
@@ -324,11 +334,10 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     RadixNode* d_nodes = nullptr;
     int32_t *d_pnode = nullptr, *d_pleaf = nullptr;
     void *d_tmp = nullptr, *d_emit = nullptr;
+    char* d_arena = nullptr;  // every scratch array of the build: ONE allocation (15 cudaMalloc + 15 cudaFree cost 30-80 ms)
     auto cleanup = [&]() {
-        for (void* p : {(void*)d_boxes, (void*)d_leaf_box, (void*)d_node_box, (void*)d_keys, (void*)d_keys_sorted, (void*)d_vals,
-                        (void*)d_order, (void*)d_visits, (void*)d_keep, (void*)d_new, (void*)d_out2, (void*)d_nodes, (void*)d_pnode,
-                        (void*)d_pleaf, d_tmp})
-            if (p) cudaFree(p);
+        if (d_arena) cudaFree(d_arena);
+        d_arena = nullptr;
     };
 #define LB_TRY(call)                                                            \
     do {                                                                        \
@@ -341,21 +350,44 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
         }                                                                       \
     } while (0)
     const uint32_t ni = n - 1;
-    LB_TRY(cudaMalloc(&d_boxes, (size_t)n * sizeof(BoxF)));
-    LB_TRY(cudaMalloc(&d_leaf_box, (size_t)n * sizeof(BoxF)));
-    LB_TRY(cudaMalloc(&d_node_box, (size_t)ni * sizeof(BoxF)));
-    LB_TRY(cudaMalloc(&d_keys, (size_t)n * sizeof(uint64_t)));
-    LB_TRY(cudaMalloc(&d_keys_sorted, (size_t)n * sizeof(uint64_t)));
-    LB_TRY(cudaMalloc(&d_vals, (size_t)n * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_order, (size_t)n * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_visits, (size_t)ni * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_keep, (size_t)ni * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_new, (size_t)ni * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_out2, 2 * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&d_nodes, (size_t)ni * sizeof(RadixNode)));
-    LB_TRY(cudaMalloc(&d_pnode, (size_t)ni * sizeof(int32_t)));
-    LB_TRY(cudaMalloc(&d_pleaf, (size_t)n * sizeof(int32_t)));
-    LB_TRY(cudaMemcpy(d_boxes, hb.data(), (size_t)n * sizeof(BoxF), cudaMemcpyHostToDevice));
+    const uint32_t sort_tiles = (n + kSortTile - 1) / kSortTile;
+    const size_t hist_words = 256 * (size_t)sort_tiles;
+    const size_t scratch_words = std::max(scan_scratch_words(hist_words), scan_scratch_words(ni));
+    {
+        size_t total = 0;
+        auto reserve = [&](size_t bytes) {
+            const size_t at = total;
+            total += (bytes + 255) & ~(size_t)255;
+            return at;
+        };
+        const size_t o_boxes = reserve((size_t)n * sizeof(BoxF)), o_leaf_box = reserve((size_t)n * sizeof(BoxF)),
+                     o_node_box = reserve((size_t)ni * sizeof(BoxF)), o_keys = reserve((size_t)n * sizeof(uint64_t)),
+                     o_keys_sorted = reserve((size_t)n * sizeof(uint64_t)), o_vals = reserve((size_t)n * sizeof(uint32_t)),
+                     o_order = reserve((size_t)n * sizeof(uint32_t)), o_visits = reserve((size_t)ni * sizeof(uint32_t)),
+                     o_keep = reserve((size_t)ni * sizeof(uint32_t)), o_new = reserve((size_t)ni * sizeof(uint32_t)),
+                     o_out2 = reserve(2 * sizeof(uint32_t)), o_nodes = reserve((size_t)ni * sizeof(RadixNode)),
+                     o_pnode = reserve((size_t)ni * sizeof(int32_t)), o_pleaf = reserve((size_t)n * sizeof(int32_t)),
+                     o_tmp = reserve((hist_words + scratch_words) * sizeof(uint32_t));
+        LB_TRY(cudaMalloc(&d_arena, total));
+        d_boxes = reinterpret_cast<BoxF*>(d_arena + o_boxes);
+        d_leaf_box = reinterpret_cast<BoxF*>(d_arena + o_leaf_box);
+        d_node_box = reinterpret_cast<BoxF*>(d_arena + o_node_box);
+        d_keys = reinterpret_cast<uint64_t*>(d_arena + o_keys);
+        d_keys_sorted = reinterpret_cast<uint64_t*>(d_arena + o_keys_sorted);
+        d_vals = reinterpret_cast<uint32_t*>(d_arena + o_vals);
+        d_order = reinterpret_cast<uint32_t*>(d_arena + o_order);
+        d_visits = reinterpret_cast<uint32_t*>(d_arena + o_visits);
+        d_keep = reinterpret_cast<uint32_t*>(d_arena + o_keep);
+        d_new = reinterpret_cast<uint32_t*>(d_arena + o_new);
+        d_out2 = reinterpret_cast<uint32_t*>(d_arena + o_out2);
+        d_nodes = reinterpret_cast<RadixNode*>(d_arena + o_nodes);
+        d_pnode = reinterpret_cast<int32_t*>(d_arena + o_pnode);
+        d_pleaf = reinterpret_cast<int32_t*>(d_arena + o_pleaf);
+        d_tmp = d_arena + o_tmp;
+    }
+    lap("cudaMalloc (arena)");
+    LB_TRY(cudaMemcpy(d_boxes, hb.get(), (size_t)n * sizeof(BoxF), cudaMemcpyHostToDevice));
+    lap("boxes H2D");
     LB_TRY(cudaMemset(d_visits, 0, (size_t)ni * sizeof(uint32_t)));
     LB_TRY(cudaMemset(d_out2, 0, 2 * sizeof(uint32_t)));
 
@@ -365,10 +397,6 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     LB_TRY(cudaEventRecord(e0, 0));
     const unsigned gb = (n + 255) / 256, gi = (ni + 255) / 256;
     keys_kernel<<<gb, 256>>>(n, d_boxes, fr, d_keys, d_vals);
-    const uint32_t sort_tiles = (n + kSortTile - 1) / kSortTile;
-    const size_t hist_words = 256 * (size_t)sort_tiles;
-    const size_t scratch_words = std::max(scan_scratch_words(hist_words), scan_scratch_words(ni));
-    LB_TRY(cudaMalloc(&d_tmp, (hist_words + scratch_words) * sizeof(uint32_t)));
     uint32_t* d_hist = static_cast<uint32_t*>(d_tmp);
     uint32_t* d_scan_scratch = d_hist + hist_words;
     // 63-bit Morton keys: eight 8-bit passes (an even number: the sorted pairs end where they started, then swap names)
@@ -396,6 +424,7 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    lap("kernels");
     uint32_t out2[2] = {0, 0};
     LB_TRY(cudaMemcpy(out2, d_out2, sizeof(out2), cudaMemcpyDeviceToHost));
     out->order.resize(n);
@@ -407,7 +436,9 @@ int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_l
         out->root_lo[k] = root.lo[k];
         out->root_hi[k] = root.hi[k];
     }
+    lap("order D2H");
     cleanup();
+    lap("cudaFree (arena)");
     out->d_nodes = d_emit;
     out->node_bytes = (size_t)n_kept * node_size;
     out->n_nodes = n_kept;
@@ -426,7 +457,7 @@ int lbvh_host_probe(const std::vector<Aabb>& boxes, uint32_t max_leaf, double de
                     uint32_t* leaves_out) {
     const uint32_t n = (uint32_t)boxes.size();
     if (n < 2 || n <= max_leaf) return RRT_ERR_UNSUPPORTED;
-    std::vector<BoxF> hb(n);
+    RawBuf<BoxF> hb(n);
     double clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) {

@@ -48,7 +48,7 @@ struct LbvhResult {
     uint64_t total_usec = 0;      // including allocations and transfers
 };
 
-int build_lbvh_device(int device, const std::vector<Aabb>& boxes, uint32_t max_leaf, double delta, bool quantise,
+int build_lbvh_device(int device, AabbSpan boxes, uint32_t max_leaf, double delta, bool quantise,
                       const double grid_lo[3], const float grid_ext[3], LbvhResult* out, std::string* err);
 
 int lbvh_host_probe(const std::vector<Aabb>& boxes, uint32_t max_leaf, double delta, bool quantise, const double grid_lo[3],

@@ -17,7 +17,7 @@ inline double half_area(const Aabb& b) {
 }
 
 struct Builder {
-    const std::vector<Aabb>& boxes;
+    AabbSpan boxes;
     SahParams prm;
     std::vector<float> cen;  // 3 * n centroids (fp32 is plenty for binning)
     std::vector<Bvh2Node> nodes;
@@ -27,7 +27,7 @@ struct Builder {
     std::atomic<uint32_t> n_leaves{0};
     int max_threads = 1;
 
-    explicit Builder(const std::vector<Aabb>& b, const SahParams& p) : boxes(b), prm(p) {}
+    explicit Builder(AabbSpan b, const SahParams& p) : boxes(b), prm(p) {}
 
     void make_leaf(uint32_t ni, uint32_t begin, uint32_t end) {
         nodes[ni].first = begin;
@@ -147,7 +147,7 @@ uint32_t depth_of(const std::vector<Bvh2Node>& nodes, uint32_t root) {
 
 }  // namespace
 
-void build_sah(const std::vector<Aabb>& boxes, const SahParams& params, Bvh2* out) {
+void build_sah(AabbSpan boxes, const SahParams& params, Bvh2* out) {
     const uint32_t n = (uint32_t)boxes.size();
     Builder b(boxes, params);
     if (b.prm.max_leaf < 1) b.prm.max_leaf = 1;

@@ -32,6 +32,6 @@ struct SahParams {
     int n_threads = 0;          // 0 = hardware_concurrency
 };
 
-void build_sah(const std::vector<Aabb>& boxes, const SahParams& params, Bvh2* out);
+void build_sah(AabbSpan boxes, const SahParams& params, Bvh2* out);
 
 }  // namespace rrt

@@ -5,6 +5,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -41,6 +43,31 @@ struct Aabb {
         }
     }
     bool empty() const { return lo[0] > hi[0]; }
+};
+
+// n objects of a trivially destructible type in malloc'd memory, NOT initialised: for the commit's per-primitive arrays,
+// which its worker threads fill (and whose pages they so place) in parallel.
+template <class T>
+struct RawBuf {
+    T* p = nullptr;
+    explicit RawBuf(size_t n) : p(static_cast<T*>(std::malloc((n ? n : 1) * sizeof(T)))) {
+        if (!p) throw std::bad_alloc();
+    }
+    ~RawBuf() { std::free(p); }
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    T& operator[](size_t i) const { return p[i]; }
+    T* get() const { return p; }
+};
+// A view of n boxes (a std::vector converts to it): the commit keeps its per-primitive arrays in buffers whose pages are
+// first touched by the worker threads, not zero-filled by one.
+struct AabbSpan {
+    const Aabb* data_ = nullptr;
+    size_t n_ = 0;
+    AabbSpan(const Aabb* p, size_t n) : data_(p), n_(n) {}
+    AabbSpan(const std::vector<Aabb>& v) : data_(v.data()), n_(v.size()) {}
+    size_t size() const { return n_; }
+    const Aabb& operator[](size_t i) const { return data_[i]; }
 };
 
 struct TriangleMesh {
