@@ -1258,43 +1258,78 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             r.child1 = r.child0;
             nodes.push_back(r);
         } else {
-            // explicit stack DFS: (tree node, slot of the Node64 to fill)
+            // Two passes.  (1) One thread walks the tree depth first and only DECIDES: the slot of every interior node
+            // (sibling interiors get adjacent slots — one 128-byte line —, the left subtree's descendants follow, then
+            // the right subtree's) and the first record of every leaf, in the order the walk meets them.  (2) All
+            // threads fill the slots and the records.  (Filling inside the walk cost 1.3 s for 4 Mi triangles.)
+            struct Plan {
+                uint32_t tn;             // tree node this slot holds
+                int32_t child0, child1;  // slot of an interior child, or the leaf reference
+            };
+            struct LeafPlan {
+                uint32_t tn, first;
+            };
+            std::vector<Plan> plan;
+            std::vector<LeafPlan> leaves;
+            plan.reserve(tree.nodes.size() / 2 + 2);
+            leaves.reserve(tree.nodes.size() / 2 + 2);
+            auto plan_leaf = [&](uint32_t tn) -> int32_t {
+                const Bvh2Node& nd = tree.nodes[tn];
+                const uint32_t first = (uint32_t)n_rec;
+                leaves.push_back({tn, first});
+                n_rec += nd.count;
+                return make_leaf_ref(first, nd.count);
+            };
             struct Item {
                 uint32_t tn;
                 uint32_t out;
             };
             std::vector<Item> st;
-            nodes.emplace_back();
+            plan.push_back({0, 0, 0});
             st.push_back({tree.root, 0});
             while (!st.empty()) {
-                Item it = st.back();
+                const Item it = st.back();
                 st.pop_back();
                 const Bvh2Node& nd = tree.nodes[it.tn];
-                Node64 o;
-                std::memset(&o, 0, sizeof(o));
                 const Bvh2Node& l = tree.nodes[nd.left];
                 const Bvh2Node& r = tree.nodes[nd.right];
-                set_child(o, 0, l.box);
-                set_child(o, 1, r.box);
-                // sibling interiors get adjacent slots (one 128-byte line); the left subtree's
-                // descendants follow, then the right subtree's
+                Plan o{it.tn, 0, 0};
                 uint32_t left_slot = 0, right_slot = 0;
-                if (l.count > 0) o.child0 = emit_leaf(l);
-                if (r.count > 0) o.child1 = emit_leaf(r);
+                if (l.count > 0) o.child0 = plan_leaf((uint32_t)nd.left);
+                if (r.count > 0) o.child1 = plan_leaf((uint32_t)nd.right);
                 if (l.count == 0) {
-                    left_slot = (uint32_t)nodes.size();
-                    nodes.emplace_back();
+                    left_slot = (uint32_t)plan.size();
+                    plan.push_back({0, 0, 0});
                     o.child0 = (int32_t)left_slot;
                 }
                 if (r.count == 0) {
-                    right_slot = (uint32_t)nodes.size();
-                    nodes.emplace_back();
+                    right_slot = (uint32_t)plan.size();
+                    plan.push_back({0, 0, 0});
                     o.child1 = (int32_t)right_slot;
                 }
-                nodes[it.out] = o;
+                plan[it.out] = o;
                 if (r.count == 0) st.push_back({(uint32_t)nd.right, right_slot});
                 if (l.count == 0) st.push_back({(uint32_t)nd.left, left_slot});
             }
+            nodes.resize(plan.size());
+            parallel_ranges(plan.size(), [&](size_t i0, size_t i1) {
+                for (size_t i = i0; i < i1; ++i) {
+                    const Bvh2Node& nd = tree.nodes[plan[i].tn];
+                    Node64 o;
+                    std::memset(&o, 0, sizeof(o));
+                    set_child(o, 0, tree.nodes[nd.left].box);
+                    set_child(o, 1, tree.nodes[nd.right].box);
+                    o.child0 = plan[i].child0;
+                    o.child1 = plan[i].child1;
+                    nodes[i] = o;
+                }
+            });
+            parallel_ranges(leaves.size(), [&](size_t i0, size_t i1) {
+                for (size_t i = i0; i < i1; ++i) {
+                    const Bvh2Node& nd = tree.nodes[leaves[i].tn];
+                    for (uint32_t k = 0; k < nd.count; ++k) make_record(tree.order[nd.first + k], (size_t)leaves[i].first + k);
+                }
+            });
         }
     }
 
@@ -1338,7 +1373,8 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             if (q > 32767.0) q = 32767.0;
             return 0x8000u | (uint32_t)q;
         };
-        for (size_t i = 0; i < nodes.size(); ++i) {
+        parallel_ranges(nodes.size(), [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; ++i) {
             const Node64& s = nodes[i];
             Node32 o;
             o.p[0] = quant(s.c0_lox, 0, false) | (quant(s.c0_hix, 0, true) << 16);
@@ -1351,6 +1387,7 @@ int DeviceAggregate::build(int device, const HostScene& scene, uint32_t max_prim
             o.child1 = s.child1;
             nodes32[i] = o;
         }
+        });
     }
     lap("pack nodes + records");
     // ---- upload ----
