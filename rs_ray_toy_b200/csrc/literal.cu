@@ -63,7 +63,7 @@ __device__ __forceinline__ void xf_ray_literal(const M34& inv, V3* o, V3* d) {
 __device__ bool prim_intersect_literal(const ShadeScene& sc, uint32_t prim, V3 o, V3 d, double* t, double* u, double* v) {
     const PrimInfo pi = sc.prims[prim];
     if (pi.instance >= 0) xf_ray_literal(sc.instances[pi.instance].inv, &o, &d);
-    if (pi.kind == 0) {  // Triangle::intersect (triangle.rs:226-265)
+    if ((pi.kind & kPrimKindMask) == 0) {  // Triangle::intersect (triangle.rs:226-265)
         const MeshInfo mi = sc.meshes[pi.shape];
         const uint32_t* vi = sc.mesh_vi + mi.vi_off + 3ull * pi.tri;
         const double* pb = sc.mesh_p + 3 * mi.p_off;
@@ -114,7 +114,7 @@ __device__ bool prim_intersect_literal(const ShadeScene& sc, uint32_t prim, V3 o
 // Shape::intersect_p: Triangle uses E2 = p2 - p1 (Q4, triangle.rs:175) and ignores t_max
 __device__ bool prim_intersect_p_literal(const ShadeScene& sc, uint32_t prim, V3 o, V3 d) {
     const PrimInfo pi = sc.prims[prim];
-    if (pi.kind != 0) {
+    if ((pi.kind & kPrimKindMask) != 0) {
         // sphere.rs:50-109: for a full sphere the any-hit accept rule is the closest-hit one (the clip
         // test runs on an uninitialised p_hit = 0, phi = 0 and never fires, Q5c)
         double t, u, v;

@@ -39,17 +39,6 @@ inline M34 m34_of(const Mat4& m) {
 
 // Fills the geometry pointers of `S`; every allocation is appended to `allocations` (the caller frees).
 inline int upload_geometry_tables(const HostScene& scene, ShadeScene* S, std::vector<void*>* allocations, std::string* err) {
-    std::vector<PrimInfo> prims(scene.prims.size());
-    for (size_t i = 0; i < scene.prims.size(); ++i) {
-        const Primitive& p = scene.prims[i];
-        PrimInfo pi{};
-        pi.kind = p.kind == SHAPE_TRIANGLE ? 0u : 1u;
-        pi.material = p.material;
-        pi.instance = p.instance;
-        pi.shape = p.shape;
-        pi.tri = p.tri;
-        prims[i] = pi;
-    }
     std::vector<MeshInfo> meshes(scene.meshes.size());
     std::vector<double> mp, mn, muv;
     std::vector<uint32_t> mvi, mni, muvi;
@@ -73,6 +62,28 @@ inline int upload_geometry_tables(const HostScene& scene, ShadeScene* S, std::ve
         muv.insert(muv.end(), m.uv.begin(), m.uv.end());
         muvi.insert(muvi.end(), m.uvi.begin(), m.uvi.end());
         meshes[i] = mi;
+    }
+    if (mp.size() / 3 >= (1ull << 32)) {
+        if (err) *err = "more than 2^32 mesh vertices";
+        return RRT_ERR_UNSUPPORTED;
+    }
+    std::vector<PrimInfo> prims(scene.prims.size());
+    for (size_t i = 0; i < scene.prims.size(); ++i) {
+        const Primitive& p = scene.prims[i];
+        PrimInfo pi{};
+        pi.kind = p.kind == SHAPE_TRIANGLE ? 0u : 1u;
+        pi.material = p.material;
+        pi.instance = p.instance;
+        pi.shape = p.shape;
+        pi.tri = p.tri;
+        if (p.kind == SHAPE_TRIANGLE) {
+            const MeshInfo& mi = meshes[p.shape];
+            const TriangleMesh& m = scene.meshes[p.shape];
+            for (int k = 0; k < 3; ++k) pi.gv[k] = (uint32_t)(mi.p_off + m.vi[3 * (size_t)p.tri + k]);
+            if (mi.has_uv) pi.kind |= kPrimHasUv;
+            if (mi.has_n && mi.has_ni) pi.kind |= kPrimHasNormals;
+        }
+        prims[i] = pi;
     }
     std::vector<SphereInfo> spheres(scene.spheres.size());
     for (size_t i = 0; i < scene.spheres.size(); ++i) {

@@ -28,13 +28,16 @@ namespace rrt {
 
 // ---- scene tables in HBM ---------------------------------------------------------------------------
 struct PrimInfo {       // one per entry of the primitive list (prim_id order)
-    uint32_t kind;      // 0 triangle, 1 sphere
+    uint32_t kind;      // low byte: 0 triangle, 1 sphere; kPrimHasUv / kPrimHasNormals: the mesh has uv / vertex normals
     uint32_t material;
     int32_t instance;   // -1 = bare GeometricPrimitive
     uint32_t shape;     // triangle: mesh id; sphere: sphere id
     uint32_t tri;       // triangle number inside the mesh
-    uint32_t pad[3];
+    // triangle: its three vertices as indices into the pooled mesh_p — the hit's vertex loads then depend on this record
+    // alone instead of on the chain prims -> meshes -> mesh_vi -> mesh_p (two dependent gathers fewer per hit)
+    uint32_t gv[3];
 };
+constexpr uint32_t kPrimKindMask = 0xffu, kPrimHasUv = 0x100u, kPrimHasNormals = 0x200u;
 struct MeshInfo {
     uint64_t p_off, vi_off, n_off, ni_off, uv_off, uvi_off;  // element offsets into the pooled arrays
     uint32_t has_n, has_ni, has_uv, has_uvi;
@@ -175,11 +178,10 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
     Surface s;
     s.material = pi.material;
     const bool textured = sc.n_textures != 0;
-    if (pi.kind == 0) {
-        const MeshInfo mi = sc.meshes[pi.shape];
-        const uint32_t* vi = sc.mesh_vi + mi.vi_off + 3ull * pi.tri;
-        const uint32_t v0 = vi[0], v1 = vi[1], v2 = vi[2];
-        const V3 p0 = ld3(sc.mesh_p + 3 * mi.p_off, v0), p1 = ld3(sc.mesh_p + 3 * mi.p_off, v1), p2 = ld3(sc.mesh_p + 3 * mi.p_off, v2);
+    if ((pi.kind & kPrimKindMask) == 0) {
+        const V3 p0 = ld3(sc.mesh_p, pi.gv[0]), p1 = ld3(sc.mesh_p, pi.gv[1]), p2 = ld3(sc.mesh_p, pi.gv[2]);
+        MeshInfo mi = {};  // read only for meshes that carry uv or normals
+        if (pi.kind & (kPrimHasUv | kPrimHasNormals)) mi = sc.meshes[pi.shape];
         // triangle.rs:113-129 get_uvs
         P2 uv0 = {0.0, 0.0}, uv1 = {1.0, 0.0}, uv2 = {1.0, 1.0};
         if (mi.has_uv) {
