@@ -289,6 +289,26 @@ def test_device_pointer_entry_points(ctx):
     assert np.array_equal(d_occ.cpu().numpy().astype(bool), ref["prim_id"] != 0xFFFFFFFF)
 
 
+@pytest.mark.parametrize("n", [1, 4097, 131072 + 5, 1048576 + 3, 3000001])
+def test_host_buffer_pipeline_at_ragged_sizes(ctx, n):
+    """rrt_intersect / rrt_intersect_p over host buffers run a pipeline of tapered chunks (128 Ki ... 1 Mi ... 128 Ki rays,
+    csrc/capi.cpp): whatever the batch length, every ray's answer is the device-resident call's."""
+    import torch
+    from rs_ray_toy_b200.aggregate import HIT_DTYPE, pack_rays
+    p, idx = scenes.soup(30000)
+    agg = scenes.gpu_soup(ctx, p, idx)
+    rays = synth.bounce_rays(p, idx, n, seed=21)
+    host = agg.intersect(rays)
+    occ = agg.intersect_p(rays)
+    d_rays = torch.from_numpy(pack_rays(rays).view(np.float64).copy()).cuda()
+    d_hits = torch.zeros(n * 4, dtype=torch.float64, device="cuda")
+    agg.intersect_device(n, d_rays.data_ptr(), d_hits.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    dev = d_hits.cpu().numpy().view(HIT_DTYPE).reshape(-1)
+    assert np.array_equal(host, dev)
+    assert np.array_equal(np.asarray(occ).astype(bool), dev["prim_id"] != 0xFFFFFFFF)
+
+
 # ---- Tier L: the reference's own tree, order and accept rules, every quirk kept ------------------------
 def _literal_pair(ctx, kind, n, **kw):
     import oracle_lib as O
