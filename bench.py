@@ -460,7 +460,7 @@ def main():
             "dtype": "f64 deciding arithmetic (Moller-Trumbore / quadratic), fp32 box culling", "data": "synthetic",
             "config": workload_config(world, n_rays),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_rays * 64, "d2h_bytes_per_step": n_rays * 32,
-                    "api": "rrt_intersect (pinned host rays -> hits), 1 Mi-ray chunks on 3 streams"},
+                    "api": "rrt_intersect (pinned host rays -> hits), chunks of 128 Ki .. 1 Mi rays (tapered at both ends of the batch) on 4 streams"},
             "launches_per_step": launches / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
