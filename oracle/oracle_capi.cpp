@@ -828,6 +828,7 @@ int32_t orc_render(void* sp, const double* prm, const double* lens_data, uint32_
         job.integrator.sample_all_lights = prm[37] != 0.0;
         job.want_dump = prm[36] != 0.0 && dump != nullptr;
         int64_t crop[4] = {(int64_t)prm[32], (int64_t)prm[33], (int64_t)prm[34], (int64_t)prm[35]};
+        mip_panics().store(0);  // lookups made outside a render (the MIPMap probes of tests/test_images.py) are not this frame's
         job.render(std::max(1, nthreads), std::max<uint32_t>(1, (uint32_t)prm[29]), (uint32_t)prm[30],
                    prm[31] != 0.0 ? crop : nullptr);
         size_t npix = job.film.pixels.size();
