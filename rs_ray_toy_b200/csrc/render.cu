@@ -879,6 +879,11 @@ struct Renderer::Impl {
     bool env_in_lights = false;     // an InfiniteAreaLight is sampled for direct light: two shadow-queue entries per hit
     bool env_mode = false;          // ... or seen by escaped rays: shade_kernel<.., SHADE_ENV>
     bool big_bsdf = false;          // a Translucent / Disney / Debug material: the eight-lobe kernels
+    // constant-valued materials, no environment light, one light sample per hit: one shade launch per material kind
+    // (render_kernels.cuh "shading by material kind"; RRT_SHADE_BY_KIND=0 keeps the one general kernel, the A/B switch)
+    bool shade_by_kind = false;
+    uint32_t kind_mask = 0;         // bit k: some primitive carries a material of kind k
+    unsigned kind_grid[4] = {0, 0, 0, 0};  // resident grid of shade_range_kernel<0 / 1 / 2 / general>
     bool whitted = false;           // DirectLighting with specular recursion / Debug / StratifiedSampler: whitted_kernel
     uint32_t whitted_rounds = 1;    // upper bound of rays per camera sample
     WhittedBranch* d_stacks = nullptr;
@@ -1081,6 +1086,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         }
     }
     bool specular_material = false, splitting_material = false, big_bsdf = false;
+    uint32_t kind_mask = 0;
     for (size_t i = 0; i < materials.size(); ++i) {
         const rrt_material& m = materials[i];
         if (m.kind > RRT_MAT_DEBUG) {
@@ -1090,6 +1096,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         bool used = false;  // a material no primitive names (config 1 as shipped declares a Debug material) costs nothing
         for (const Primitive& p : scene.prims) used |= p.material == i;
         big_bsdf |= used && m.kind >= RRT_MAT_TRANSLUCENT;
+        if (used) kind_mask |= 1u << m.kind;
         if (m.kind == RRT_MAT_DISNEY && !m.thin) {
             // disney.rs:588-606: a non-black scatter_distance swaps the diffuse lobe for a SpecularTransmission and hands
             // the integrator a SeparableBSSRDF — subsurface transport is outside the hot path
@@ -1558,6 +1565,7 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         if ((rc = I.up(mats, &S.materials, err)) != RRT_OK) return rc;
         if (big_bsdf && (rc = I.up(disney, &S.disney, err)) != RRT_OK) return rc;
         I.big_bsdf = big_bsdf;
+        I.kind_mask = kind_mask;
         if ((rc = I.up(texs, &S.textures, err)) != RRT_OK) return rc;
         uint32_t reached = 0;
         for (const MaterialRec& m : mats) {
@@ -1609,6 +1617,14 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         I.q.cam_samples = I.d_cam_samples;
     }
     if (const char* e = std::getenv("RRT_GEN_F32")) I.gen_mode = std::atoi(e);
+    I.shade_by_kind = RRT_SHADE_SORT && !I.whitted && !I.big_bsdf && !I.env_mode && !I.all_lights && !I.textured;
+    if (const char* e = std::getenv("RRT_SHADE_BY_KIND")) I.shade_by_kind = I.shade_by_kind && std::atoi(e) != 0;
+    if (I.shade_by_kind)
+        for (int k = 0; k < 4; ++k) {
+            int per_sm = 0;
+            RND_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shade_range_kernel_for(k < 3 ? k : -1), 128, 0));
+            I.kind_grid[k] = (unsigned)(I.sm_count * std::max(per_sm, 1));
+        }
     if (I.want_diffs) {
         if ((rc = dev_alloc((void**)&I.d_diffs, (size_t)kSlots * sizeof(RayDiffRec))) != RRT_OK) return rc;
         I.sc.ray_diffs = I.d_diffs;
@@ -1731,7 +1747,20 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             shade_scatter_kernel<<<small_grid, 256, 0, I.stream>>>(I.q, cur);
             launches += 2;
 #endif
-            {
+            if (I.shade_by_kind) {
+                shade_miss_kernel_fn()<<<small_grid, 256, 0, I.stream>>>(I.d_paths, I.q, cur);
+                for (int k = 0; k < 3; ++k)
+                    if ((I.kind_mask >> k) & 1u) {
+                        shade_range_kernel_for(k)<<<I.kind_grid[k], 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur, 1 + k,
+                                                                                       1 + k);
+                        launches += 1;
+                    }
+                if (I.kind_mask >> 3) {  // Mirror, Glass: the general code over their bins
+                    shade_range_kernel_for(-1)<<<I.kind_grid[3], 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur, 4,
+                                                                                    kShadeBins - 1);
+                    launches += 1;
+                }
+            } else {
                 ShadeFn shade = I.big_bsdf   ? shade_kernel_big(I.env_mode)
                                 : I.env_mode   ? (I.textured ? shade_kernel_textured_env() : shade_kernel<false, false, true>)
                                 : I.all_lights ? (I.textured ? shade_kernel_textured(true) : shade_kernel<false, true>)

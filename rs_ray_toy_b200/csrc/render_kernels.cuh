@@ -133,19 +133,45 @@ __device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* pe
 // next-event estimate has a live BSDF-sampling half (integrator/mod.rs:484-556) — a second shadow-queue entry per hit,
 // whose ray only has to ESCAPE: a hit can add nothing (get_arealight() is None for every primitive, Q22).
 // BIG = some material is Translucent / Disney / Debug: the Bsdf holds eight lobes (shading.cuh); TEXTURED is set with it.
-template <bool TEXTURED, bool ALL_LIGHTS, bool ENV = false, bool BIG = false>
-__global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
-                                                     IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
-    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = q.counters[cur];
-    if (RRT_SHADE_SORT && qi < n) qi = q.shade_perm[qi];
+// KIND: -1 = a hit of any material kind (or a miss); 0 / 1 / 2 = every entry this call sees is a hit on a Matte / Plastic /
+// Metal material (shade_range_kernel below): the Bsdf type narrows to that kind's lobe set (shading.cuh "lobe sets").
+template <int KIND>
+struct KindBsdf {
+    using type = Bsdf;
+};
+template <>
+struct KindBsdf<0> {
+    using type = BsdfT<1, kLobesMatte>;
+};
+template <>
+struct KindBsdf<1> {
+    using type = BsdfT<2, kLobesPlastic>;
+};
+template <>
+struct KindBsdf<2> {
+    using type = BsdfT<1, kLobesMetal>;
+};
+template <bool BIG, int KIND>
+struct ShadeBsdf {
+    using type = typename KindBsdf<KIND>::type;
+};
+template <int KIND>
+struct ShadeBsdf<true, KIND> {
+    using type = BsdfBig;
+};
+
+// One extension-queue entry `qi` (`valid` = the lane has one): every lane of the warp must call this (warp-aggregated appends).
+template <bool TEXTURED, bool ALL_LIGHTS, bool ENV, bool BIG, int KIND>
+__device__ __forceinline__ void shade_one(const ShadeScene& sc, const HaltonTables& ht, const uint16_t* __restrict__ perms,
+                                          const IntegratorParams& ip, Path* __restrict__ paths, const Queues& q, int cur, uint32_t qi,
+                                          bool valid) {
     bool emit_ext = false, emit_sh = false;
     V3 eo = v3(0, 0, 0), ed = v3(0, 0, 0), so = v3(0, 0, 0), sd = v3(0, 0, 0);
     Rgb contrib = rgb(0.0);
     uint32_t pid = 0;
-    if (qi < n) {
-        pid = q.ext_path[cur][qi];
-        Path* const P = paths + pid;
+    if (valid) {
+        pid = (cur ? q.ext_path[1] : q.ext_path[0])[qi];  // (static indices: a run-time index into a kernel parameter
+        Path* const P = paths + pid;                      //  makes nvcc keep a copy of the whole struct in local memory)
         PathCore p;
         p.o = P->o;
         p.d = P->d;
@@ -181,9 +207,11 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
             BumpPartials bp;
             if (TEXTURED)
                 make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s, sc.bump ? &bp : nullptr);
+            else if (KIND >= 0)  // its one call site: inlined, the scene tables read straight from the parameter bank
+                make_surface_body(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s, nullptr);
             else
                 make_surface(sc, h.prim_id, h.t, h.u, h.v, p.o, p.d, &s);
-            BsdfT<BIG ? 8 : 2> bsdf;
+            typename ShadeBsdf<BIG, KIND>::type bsdf;
             if (TEXTURED) {
                 const MaterialRec* m = sc.materials + s.material;
                 MaterialRec textured;
@@ -202,7 +230,7 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
                 }
                 make_bsdf(*m, s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf, BIG ? &dz : nullptr);
             } else {
-                make_bsdf(sc.materials[s.material], s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
+                make_bsdf<KIND>(sc.materials[s.material], s, ip.kind == RRT_INTEGRATOR_PATH, &bsdf);
             }
             if (!bsdf.present) {
                 alive = false;  // path.rs:101-106 (usize underflow in the reference, Q21): the path ends here
@@ -219,17 +247,13 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
                     if (ALL_LIGHTS) {
                         light_num = estimate;
                     } else if (ip.kind == RRT_INTEGRATOR_PATH) {
-                        // Distribution1D::sample_discrete (sampling.rs:87-122): bisection over the CDF
-                        uint32_t first = 0, len = ip.n_lights + 1;
-                        while (len > 0) {
-                            uint32_t half = len >> 1, middle = first + half;
-                            if (ip.light_cdf[middle] <= ul) {
-                                first = middle + 1;
-                                len -= half + 1;
-                            } else {
-                                len = half;
-                            }
-                        }
+                        // Distribution1D::sample_discrete (sampling.rs:87-122) bisects the CDF for the first entry above ul.
+                        // The CDF is non-decreasing, so that partition point is the number of entries <= ul — counted over the
+                        // 17 slots with static indices: a run-time index into a kernel parameter makes nvcc copy the whole
+                        // IntegratorParams to local memory at kernel entry (36 stores per thread, 5 % of the kernel's stalls)
+                        uint32_t first = 0;
+#pragma unroll
+                        for (uint32_t k = 0; k < 17; ++k) first += (k <= ip.n_lights && ip.light_cdf[k] <= ul) ? 1u : 0u;
                         light_num = first == 0 ? 0 : first - 1;
                         if (light_num > ip.n_lights - 1) light_num = ip.n_lights - 1;
                     } else {
@@ -385,8 +409,8 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
     }
     const uint32_t es = queue_slot(q.counters + (cur ^ 1), emit_ext);
     if (emit_ext) {
-        write_ray(q.ext_rays[cur ^ 1] + es, eo, ed, kInfD);
-        q.ext_path[cur ^ 1][es] = pid;
+        write_ray((cur ? q.ext_rays[0] : q.ext_rays[1]) + es, eo, ed, kInfD);
+        (cur ? q.ext_path[0] : q.ext_path[1])[es] = pid;
     }
     const uint32_t ss = queue_slot(q.counters + 2, emit_sh);
     if (emit_sh) {
@@ -394,6 +418,109 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
         q.sh_path[ss] = pid;
         q.sh_contrib[ss] = contrib;
     }
+}
+
+// One thread per entry of the round's extension queue (in shade order: grouped by miss / material kind).
+template <bool TEXTURED, bool ALL_LIGHTS, bool ENV = false, bool BIG = false>
+__global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms,
+                                                     IntegratorParams ip, Path* __restrict__ paths, Queues q, int cur) {
+    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = q.counters[cur];
+    if (RRT_SHADE_SORT && qi < n) qi = q.shade_perm[qi];
+    shade_one<TEXTURED, ALL_LIGHTS, ENV, BIG, -1>(sc, ht, perms, ip, paths, q, cur, qi, qi < n);
+}
+
+// ---- shading by material kind (constant-valued scenes without environment lights: the throughput path) ----------------
+// shade_bin / shade_scatter group a round's entries as [misses | kind 0 | kind 1 | ...] (q.counters[16 + bin] entries each).
+// One launch per bin that the scene can fill walks that bin's slice of the order with a resident grid:
+//  * shade_miss_kernel (render_shade_kind.cu): an escaped ray ends its path (path.rs:79-93 without infinite lights) — a few registers' worth of work
+//    that no longer occupies a slot of the 158-register kernel;
+//  * shade_range_kernel<KIND> for Matte, Plastic and Metal: the Bsdf is one or two statically known lobes in registers, the
+//    code a fraction of the general kernel's (which carries every lobe of every material behind calls);
+//  * shade_range_kernel<-1> over the bins of the other kinds (Mirror, Glass): the general code.
+// Bin b of the order starts at the sum of the counts before it.
+__device__ __forceinline__ void shade_bin_range(const Queues& q, int bin_first, int bin_last, uint32_t* start, uint32_t* end) {
+    uint32_t s = 0;
+    for (int b = 0; b < bin_first; ++b) s += q.counters[16 + b];
+    uint32_t e = s;
+    for (int b = bin_first; b <= bin_last; ++b) e += q.counters[16 + b];
+    *start = s;
+    *end = e;
+}
+#ifndef RRT_SHADE_PREFETCH
+#define RRT_SHADE_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef RRT_SHADE_KIND_MINBLOCKS
+#define RRT_SHADE_KIND_MINBLOCKS 4
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(128, KIND >= 0 ? RRT_SHADE_KIND_MINBLOCKS : RRT_SHADE_MINBLOCKS)
+shade_range_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms, IntegratorParams ip, Path* __restrict__ paths, Queues q,
+                   int cur, int bin_first, int bin_last) {
+    uint32_t start, end;
+    shade_bin_range(q, bin_first, bin_last, &start, &end);
+    const uint32_t stride = gridDim.x * blockDim.x;
+#if RRT_SHADE_PREFETCH
+    // A hit's loads form a chain — order -> (path id -> Path) and (hit -> PrimInfo -> vertices / instance) — of four trips
+    // to HBM, and a warp has nothing else to do meanwhile.  The walk is a software pipeline over the thread's own items:
+    // while item n is shaded, item n + 3's order entry, item n + 2's path id and primitive, and item n + 1's PrimInfo are
+    // in flight, and item n + 1's Path, vertices and instance are prefetched into L2.
+    const uint32_t* const ext_path_cur = cur ? q.ext_path[1] : q.ext_path[0];
+    uint32_t i = start + blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t qi0 = i < end ? q.shade_perm[i] : 0u;
+    uint32_t qi1 = i + stride < end ? q.shade_perm[i + stride] : 0u;
+    uint32_t qi2 = i + 2u * stride < end ? q.shade_perm[i + 2u * stride] : 0u;
+    uint32_t pid1 = 0u, prim1 = RRT_NO_HIT;
+    if (i + stride < end) {
+        pid1 = ext_path_cur[qi1];
+        prim1 = q.hits[qi1].prim_id;
+    }
+    for (uint32_t base = start + blockIdx.x * blockDim.x; base < end; base += stride, i += stride) {  // uniform per CTA
+        const bool valid = i < end;
+        const uint32_t qi3 = i + 3u * stride < end ? q.shade_perm[i + 3u * stride] : 0u;
+        uint32_t pid2 = 0u, prim2 = RRT_NO_HIT;
+        if (i + 2u * stride < end) {
+            pid2 = ext_path_cur[qi2];
+            prim2 = q.hits[qi2].prim_id;
+        }
+        uint32_t gv0 = 0u, gv1 = 0u, gv2 = 0u, pk1 = 0xffu;
+        int32_t inst1 = -1;
+        if (prim1 != RRT_NO_HIT) {
+            const PrimInfo* const pp = sc.prims + prim1;
+            pk1 = pp->kind;
+            inst1 = pp->instance;
+            gv0 = pp->gv[0];
+            gv1 = pp->gv[1];
+            gv2 = pp->gv[2];
+            prefetch_l2(paths + pid1);
+            prefetch_l2(reinterpret_cast<const char*>(paths + pid1) + 128);
+        }
+        shade_one<false, false, false, false, KIND>(sc, ht, perms, ip, paths, q, cur, qi0, valid);
+        if (prim1 != RRT_NO_HIT) {
+            if ((pk1 & kPrimKindMask) == 0u) {
+                prefetch_l2(sc.mesh_p + 3ull * gv0);
+                prefetch_l2(sc.mesh_p + 3ull * gv1);
+                prefetch_l2(sc.mesh_p + 3ull * gv2);
+            }
+            if (inst1 >= 0) {
+                prefetch_l2(sc.instances + inst1);
+                prefetch_l2(reinterpret_cast<const char*>(sc.instances + inst1) + 128);
+            }
+        }
+        qi0 = qi1;
+        qi1 = qi2;
+        qi2 = qi3;
+        pid1 = pid2;
+        prim1 = prim2;
+    }
+#else
+    for (uint32_t base = start + blockIdx.x * blockDim.x; base < end; base += stride) {  // uniform per CTA
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < end;
+        shade_one<false, false, false, false, KIND>(sc, ht, perms, ip, paths, q, cur, valid ? q.shade_perm[i] : 0u, valid);
+    }
+#endif
 }
 
 // ---- DirectLighting / IntersectDebug with their specular recursion ---------------------------------------------
@@ -661,6 +788,10 @@ __global__ void __launch_bounds__(128, BIG ? 1 : 2) whitted_kernel(ShadeScene sc
 // ---- where the instantiations live ---------------------------------------------------------------------------
 using ShadeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, Queues, int);
 using WhittedFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, WhittedBranch*, Queues, int);
+using ShadeRangeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, Queues, int, int, int);
+using ShadeMissFn = void (*)(Path*, Queues, int);
+ShadeRangeFn shade_range_kernel_for(int kind);   // render_shade_kind.cu: 0 Matte, 1 Plastic, 2 Metal; anything else = the general code
+ShadeMissFn shade_miss_kernel_fn();              // render_shade_kind.cu
 ShadeFn shade_kernel_textured(bool all_lights);  // render_shade_tex.cu
 ShadeFn shade_kernel_textured_env();             // render_shade_env.cu
 ShadeFn shade_kernel_big(bool env);              // render_shade_big.cu: Translucent / Disney / Debug materials

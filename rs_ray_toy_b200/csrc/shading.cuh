@@ -165,8 +165,8 @@ static __device__ __noinline__ void sphere_bump_partials(const SphereInfo& sp, V
 }
 
 // Rebuilds the surface frame of hit (prim_id, t, u, v) for the world ray (o, d).
-static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
-                                          Surface* out, BumpPartials* bp = nullptr) {
+__device__ __forceinline__ void make_surface_body(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
+                                                  Surface* out, BumpPartials* bp) {
     const PrimInfo pi = sc.prims[prim_id];
     V3 lo = o, ld = d;
     if (pi.instance >= 0) {  // TransformedPrimitive::intersect (primitives.rs:126-139), Q6 fixed: d keeps its length
@@ -308,6 +308,12 @@ static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t 
     }
     *out = s;
 }
+// Out of line for the general kernels (measured: 160 registers without spills, +3 %); the kernels specialised by material
+// kind inline the body.
+static __device__ __noinline__ void make_surface(const ShadeScene& sc, uint32_t prim_id, double t, double bu, double bv, V3 o, V3 d,
+                                                 Surface* out, BumpPartials* bp = nullptr) {
+    make_surface_body(sc, prim_id, t, bu, bv, o, d, out, bp);
+}
 
 // ---- reflection.rs helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ double cos2_theta(V3 w) { return w.z * w.z; }
@@ -393,6 +399,28 @@ enum : uint32_t { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR, LOBE_MICROFACET, LOBE_SPEC_
 // FRESNEL_SEPARABLE_G: DisneyMicrofacetDistribution's g = g1(wo) * g1(wi) (disney.rs:329-360).
 enum : uint32_t { FRESNEL_NOOP = 0, FRESNEL_DIELECTRIC = 1, FRESNEL_CONDUCTOR = 2, FRESNEL_DISNEY = 3, FRESNEL_SEPARABLE_G = 256 };
 
+// ---- lobe sets ---------------------------------------------------------------------------------------------------
+// A material kind fixes which lobe kinds (bits 0..15) and Fresnel terms (bits 16..) its Bsdf can hold.  Every function
+// below takes that set as a template parameter: kLobesAll is the general code (out of line, the Bsdf in local memory — what
+// the textured / eight-lobe / environment kernels and the "any kind" shade kernel run); a narrower set prunes the other
+// lobes' code at compile time, is inlined into its caller and indexes the lobes statically, so that the Bsdf of a Matte,
+// Plastic or Metal hit lives in registers (shade_range_kernel<KIND>, render_kernels.cuh).  Same functions, same operation
+// order: a specialised kernel's results are bit-identical to the general one's.
+constexpr uint32_t kLobesAll = 0xffffffffu;
+__host__ __device__ constexpr uint32_t lobe_bit(uint32_t k) { return 1u << k; }
+__host__ __device__ constexpr uint32_t fresnel_bit(uint32_t f) { return 1u << (16u + f); }
+constexpr uint32_t kLobesMatte = lobe_bit(LOBE_LAMBERT) | lobe_bit(LOBE_OREN_NAYAR) | fresnel_bit(FRESNEL_NOOP);
+constexpr uint32_t kLobesPlastic = lobe_bit(LOBE_LAMBERT) | lobe_bit(LOBE_MICROFACET) | fresnel_bit(FRESNEL_NOOP) | fresnel_bit(FRESNEL_DIELECTRIC);
+constexpr uint32_t kLobesMetal = lobe_bit(LOBE_MICROFACET) | fresnel_bit(FRESNEL_CONDUCTOR);
+#define RRT_LOBE_IN(MASK, K) ((((MASK) >> (K)) & 1u) != 0u)
+#define RRT_FRESNEL_IN(MASK, F) ((((MASK) >> (16u + (F))) & 1u) != 0u)
+__host__ __device__ constexpr bool lobe_set_is_single(uint32_t mask) { return (mask & 0xffffu) != 0u && ((mask & 0xffffu) & ((mask & 0xffffu) - 1u)) == 0u; }
+__host__ __device__ constexpr uint32_t lobe_set_first(uint32_t mask) {
+    uint32_t k = 0;
+    while (k < 16u && !((mask >> k) & 1u)) ++k;
+    return k;
+}
+
 struct Lobe {
     uint32_t kind, fresnel;
     Rgb r, t;           // reflectance / transmittance
@@ -401,9 +429,14 @@ struct Lobe {
     double eta_a, eta_b;   // specular transmission / FresnelSpecular indices; Oren–Nayar A, B
     double alpha_x, alpha_y;
 };
-template <bool BIG = false>
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t lobe_kind(const Lobe& l) {  // a one-lobe set knows its kind at compile time
+    if (MASK != kLobesAll && lobe_set_is_single(MASK)) return lobe_set_first(MASK);
+    return l.kind;
+}
+template <bool BIG = false, uint32_t MASK = kLobesAll>
 __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
-    switch (l.kind) {
+    switch (lobe_kind<MASK>(l)) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: return BXDF_DIFFUSE | BXDF_REFLECTION;
         case LOBE_MICROFACET: return BXDF_GLOSSY | BXDF_REFLECTION;
@@ -413,7 +446,7 @@ __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
         default: break;
     }
     if (BIG) {
-        switch (l.kind) {
+        switch (lobe_kind<MASK>(l)) {
             case LOBE_LAMBERT_TRANS: return BXDF_DIFFUSE | BXDF_TRANSMISSION;
             case LOBE_DISNEY_DIFFUSE:
             case LOBE_DISNEY_FAKESS:
@@ -429,8 +462,8 @@ __device__ __forceinline__ uint32_t lobe_type(const Lobe& l) {
     }
     return BXDF_SPECULAR | BXDF_ALL;  // FresnelSpecular, reflection.rs:801-803
 }
-template <bool BIG = false>
-__device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type<BIG>(l) & flags) == lobe_type<BIG>(l); }
+template <bool BIG = false, uint32_t MASK = kLobesAll>
+__device__ __forceinline__ bool lobe_matches(const Lobe& l, uint32_t flags) { return (lobe_type<BIG, MASK>(l) & flags) == lobe_type<BIG, MASK>(l); }
 // reflection.rs:13-24, misc.rs:223-228 (lerp(t, a, b) = a * (1 - t) + b * t)
 __device__ __forceinline__ double schlick_weight(double c) {
     const double m = clampd(1.0 - c, 0.0, 1.0);
@@ -438,13 +471,13 @@ __device__ __forceinline__ double schlick_weight(double c) {
 }
 __device__ __forceinline__ double lerp_f(double t, double a, double b) { return a * (1.0 - t) + b * t; }
 __device__ __forceinline__ Rgb lerp_rgb(double t, Rgb a, Rgb b) { return a * (1.0 - t) + b * t; }
-template <bool BIG = false>
+template <bool BIG = false, uint32_t MASK = kLobesAll>
 static __device__ Rgb lobe_fresnel(const Lobe& l, double cos_i) {  // reflection.rs:603-619
     const uint32_t fk = BIG ? (l.fresnel & 255u) : l.fresnel;
     if (BIG && fk == FRESNEL_DISNEY)
         return lerp_rgb(l.a, rgb(fr_dielectric(cos_i, 1.0, l.b)), lerp_rgb(schlick_weight(cos_i), l.cond_eta, rgb(1.0)));
-    if (fk == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
-    if (fk == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
+    if (RRT_FRESNEL_IN(MASK, FRESNEL_DIELECTRIC) && fk == FRESNEL_DIELECTRIC) return rgb(fr_dielectric(cos_i, l.a, l.b));
+    if (RRT_FRESNEL_IN(MASK, FRESNEL_CONDUCTOR) && fk == FRESNEL_CONDUCTOR) return fr_conductor(fabs(cos_i), rgb(1.0), l.cond_eta, l.cond_k);
     return rgb(1.0);
 }
 // TrowbridgeReitzDistribution (microfacet.rs:364-390)
@@ -468,7 +501,7 @@ static __device__ double tr_pdf(const Lobe& l, V3 wo, V3 wh) {  // microfacet.rs
     return tr_d(l, wh) * (1.0 / (1.0 + tr_lambda(l, wo))) * absdot(wo, wh) / abs_cos_theta(wo);
 }
 template <bool BIG = false>
-__device__ __forceinline__ double tr_g(const Lobe& l, V3 wo, V3 wi) {
+__device__ __forceinline__ double tr_g(const Lobe& l, V3 wo, V3 wi) {  // (a narrowed lobe set is never BIG)
     if (BIG && (l.fresnel & FRESNEL_SEPARABLE_G)) return (1.0 / (1.0 + tr_lambda(l, wo))) * (1.0 / (1.0 + tr_lambda(l, wi)));
     return 1.0 / (1.0 + tr_lambda(l, wo) + tr_lambda(l, wi));
 }
@@ -523,8 +556,8 @@ static __device__ V3 tr_sample_visible(V3 wi, double ax, double ay, double u1, d
     return normalize(v3(-slope_x, -slope_y, 1.0));
 }
 
-template <bool BIG = false>
-RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+template <bool BIG, uint32_t MASK>
+__device__ __forceinline__ Rgb lobe_f_body(const Lobe& l, V3 wo, V3 wi) {
     if (BIG) {
         switch (l.kind) {
             case LOBE_LAMBERT_TRANS: return l.t / kPi;
@@ -562,9 +595,12 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
             default: break;
         }
     }
-    switch (l.kind) {
-        case LOBE_LAMBERT: return l.r / kPi;
+    switch (lobe_kind<MASK>(l)) {
+        case LOBE_LAMBERT:
+            if (!RRT_LOBE_IN(MASK, LOBE_LAMBERT)) break;
+            return l.r / kPi;
         case LOBE_OREN_NAYAR: {  // reflection.rs:916-941
+            if (!RRT_LOBE_IN(MASK, LOBE_OREN_NAYAR)) break;
             double sin_i = sin_theta(wi), sin_o = sin_theta(wo), max_cos = 0.0;
             if (sin_i > 1e-4 && sin_o > 1e-4) {
                 double d_cos = cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo);
@@ -581,16 +617,18 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
             return l.r / kPi * (l.eta_a + l.eta_b * max_cos * sin_alpha * tan_beta);
         }
         case LOBE_MICROFACET: {  // reflection.rs:970-990
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET)) break;
             double cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
             V3 wh = wi + wo;
             if (cos_i == 0.0 || cos_o == 0.0) return rgb(0.0);
             if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return rgb(0.0);
             wh = normalize(wh);
-            Rgb fr = lobe_fresnel<BIG>(l, dot(wi, faceforward(wh, v3(0.0, 0.0, 1.0))));
+            Rgb fr = lobe_fresnel<BIG, MASK>(l, dot(wi, faceforward(wh, v3(0.0, 0.0, 1.0))));
             double g = tr_g<BIG>(l, wo, wi);
             return l.r * tr_d(l, wh) * g * fr / (4.0 * cos_i * cos_o);
         }
         case LOBE_MICROFACET_TRANS: {  // MicrofacetTransmission::f (reflection.rs:1058-1099), TransportMode::Radiance
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET_TRANS)) break;
             if (same_hemisphere(wo, wi)) return rgb(0.0);
             const double cos_o = wo.z, cos_i = wi.z;
             if (cos_i == 0.0 || cos_o == 0.0) return rgb(0.0);
@@ -605,11 +643,19 @@ RRT_SHADE_FN Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
                    fabs(tr_d(l, wh) * g * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor /
                         (cos_i * cos_o * sqrt_denom * sqrt_denom));
         }
-        default: return rgb(0.0);
+        default: break;
     }
+    return rgb(0.0);
 }
-template <bool BIG = false>
-RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+template <bool BIG>
+RRT_SHADE_FN Rgb lobe_f_out(const Lobe& l, V3 wo, V3 wi) { return lobe_f_body<BIG, kLobesAll>(l, wo, wi); }
+template <bool BIG = false, uint32_t MASK = kLobesAll>
+__device__ __forceinline__ Rgb lobe_f(const Lobe& l, V3 wo, V3 wi) {
+    if constexpr (MASK == kLobesAll) return lobe_f_out<BIG>(l, wo, wi);
+    else return lobe_f_body<BIG, MASK>(l, wo, wi);
+}
+template <bool BIG, uint32_t MASK>
+__device__ __forceinline__ double lobe_pdf_body(const Lobe& l, V3 wo, V3 wi) {
     if (BIG) {
         switch (l.kind) {
             case LOBE_DISNEY_DIFFUSE:
@@ -630,15 +676,17 @@ RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
             default: break;
         }
     }
-    switch (l.kind) {
+    switch (lobe_kind<MASK>(l)) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: return same_hemisphere(wo, wi) ? abs_cos_theta(wi) / kPi : 0.0;
         case LOBE_MICROFACET: {
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET)) break;
             if (!same_hemisphere(wo, wi)) return 0.0;
             V3 wh = normalize(wo + wi);
             return tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
         }
         case LOBE_MICROFACET_TRANS: {  // reflection.rs:1127-1142
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET_TRANS)) break;
             if (same_hemisphere(wo, wi)) return 0.0;
             const double eta = wo.z > 0.0 ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
             const V3 wh = normalize(wo + wi * eta);
@@ -646,12 +694,20 @@ RRT_SHADE_FN double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
             const double dwh_dwi = fabs((eta * eta * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
             return tr_pdf(l, wo, wh) * dwh_dwi;
         }
-        default: return 0.0;
+        default: break;
     }
+    return 0.0;
+}
+template <bool BIG>
+RRT_SHADE_FN double lobe_pdf_out(const Lobe& l, V3 wo, V3 wi) { return lobe_pdf_body<BIG, kLobesAll>(l, wo, wi); }
+template <bool BIG = false, uint32_t MASK = kLobesAll>
+__device__ __forceinline__ double lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+    if constexpr (MASK == kLobesAll) return lobe_pdf_out<BIG>(l, wo, wi);
+    else return lobe_pdf_body<BIG, MASK>(l, wo, wi);
 }
 // BxDF::sample_f of each lobe; *pdf is left untouched on the early-outs (the caller zeroed it)
-template <bool BIG = false>
-RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+template <bool BIG, uint32_t MASK>
+__device__ __forceinline__ Rgb lobe_sample_f_body(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
     if (BIG) {
         switch (l.kind) {
             case LOBE_DISNEY_DIFFUSE:
@@ -687,15 +743,17 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             default: break;
         }
     }
-    switch (l.kind) {
+    switch (lobe_kind<MASK>(l)) {
         case LOBE_LAMBERT:
         case LOBE_OREN_NAYAR: {  // reflection.rs:428-443
+            if (!RRT_LOBE_IN(MASK, LOBE_LAMBERT) && !RRT_LOBE_IN(MASK, LOBE_OREN_NAYAR)) break;
             *wi = cosine_sample_hemisphere(u);
             if (wo.z < 0.0) wi->z *= -1.0;
-            *pdf = lobe_pdf<BIG>(l, wo, *wi);
-            return lobe_f<BIG>(l, wo, *wi);
+            *pdf = lobe_pdf<BIG, MASK>(l, wo, *wi);
+            return lobe_f<BIG, MASK>(l, wo, *wi);
         }
         case LOBE_MICROFACET: {  // reflection.rs:991-1015
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET)) break;
             if (wo.z == 0.0) return rgb(0.0);
             V3 wh = wo.z < 0.0 ? -tr_sample_visible(-wo, l.alpha_x, l.alpha_y, u.x, u.y)
                                : tr_sample_visible(wo, l.alpha_x, l.alpha_y, u.x, u.y);
@@ -703,14 +761,16 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             *wi = reflect_about(wo, wh);
             if (!same_hemisphere(wo, *wi)) return rgb(0.0);
             *pdf = tr_pdf(l, wo, wh) / (4.0 * dot(wo, wh));
-            return lobe_f<BIG>(l, wo, *wi);
+            return lobe_f<BIG, MASK>(l, wo, *wi);
         }
         case LOBE_SPEC_REFL: {  // reflection.rs:638-649
+            if (!RRT_LOBE_IN(MASK, LOBE_SPEC_REFL)) break;
             *wi = v3(-wo.x, -wo.y, wo.z);
             *pdf = 1.0;
-            return lobe_fresnel<BIG>(l, wi->z) * l.r / abs_cos_theta(*wi);
+            return lobe_fresnel<BIG, MASK>(l, wi->z) * l.r / abs_cos_theta(*wi);
         }
         case LOBE_SPEC_TRANS: {  // reflection.rs:686-714, TransportMode::Radiance
+            if (!RRT_LOBE_IN(MASK, LOBE_SPEC_TRANS)) break;
             bool entering = wo.z > 0.0;
             double ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
             if (!refract_dir(wo, faceforward(v3(0.0, 0.0, 1.0), wo), ei / et, wi)) return rgb(0.0);
@@ -720,16 +780,18 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             return ft / abs_cos_theta(*wi);
         }
         case LOBE_MICROFACET_TRANS: {  // reflection.rs:1100-1126
+            if (!RRT_LOBE_IN(MASK, LOBE_MICROFACET_TRANS)) break;
             if (wo.z == 0.0) return rgb(0.0);
             const V3 wh = wo.z < 0.0 ? -tr_sample_visible(-wo, l.alpha_x, l.alpha_y, u.x, u.y)
                                      : tr_sample_visible(wo, l.alpha_x, l.alpha_y, u.x, u.y);
             if (dot(wo, wh) < 0.0) return rgb(0.0);
             const double eta = wo.z > 0.0 ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
             if (!refract_dir(wo, wh, eta, wi)) return rgb(0.0);
-            *pdf = lobe_pdf<BIG>(l, wo, *wi);
-            return lobe_f<BIG>(l, wo, *wi);
+            *pdf = lobe_pdf<BIG, MASK>(l, wo, *wi);
+            return lobe_f<BIG, MASK>(l, wo, *wi);
         }
         default: {  // FresnelSpecular, reflection.rs:751-797
+            if (!RRT_LOBE_IN(MASK, LOBE_FRESNEL_SPEC)) break;
             double fr = fr_dielectric(wo.z, l.eta_a, l.eta_b);
             if (u.x < fr) {
                 *wi = v3(-wo.x, -wo.y, wo.z);
@@ -747,10 +809,22 @@ RRT_SHADE_FN Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, 
             return ft / abs_cos_theta(*wi);
         }
     }
+    return rgb(0.0);  // (a lobe kind outside MASK: unreachable)
+}
+template <bool BIG>
+RRT_SHADE_FN Rgb lobe_sample_f_out(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+    return lobe_sample_f_body<BIG, kLobesAll>(l, wo, wi, u, pdf, sampled_type);
+}
+template <bool BIG = false, uint32_t MASK = kLobesAll>
+__device__ __forceinline__ Rgb lobe_sample_f(const Lobe& l, V3 wo, V3* wi, P2 u, double* pdf, uint32_t* sampled_type) {
+    if constexpr (MASK == kLobesAll) return lobe_sample_f_out<BIG>(l, wo, wi, u, pdf, sampled_type);
+    else return lobe_sample_f_body<BIG, MASK>(l, wo, wi, u, pdf, sampled_type);
 }
 
 // ---- Bsdf over at most NL lobes (reflection.rs:205-404) ---------------------------------------------------
-template <int NL>
+// MASK = the lobe set (above).  A narrowed set walks its lobes with a compile-time bound and static indices (RRT_FOR_LOBES:
+// the loop over NL <= 2 slots unrolls), the general one with the run-time count as it always did.
+template <int NL, uint32_t MASK = kLobesAll>
 struct BsdfT {
     V3 ns, ng, ss, ts;
     double eta;
@@ -760,49 +834,67 @@ struct BsdfT {
 };
 using Bsdf = BsdfT<2>;
 using BsdfBig = BsdfT<8>;  // Bsdf::MAX_BxDFS (reflection.rs:207)
-template <int NL>
-__device__ __forceinline__ V3 to_local(const BsdfT<NL>& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
-template <int NL>
-__device__ __forceinline__ V3 to_world(const BsdfT<NL>& b, V3 v) {
+#define RRT_FOR_LOBES(i, b)                                     \
+    _Pragma("unroll (MASK != kLobesAll ? NL : 1)")              \
+    for (int i = 0; i < (MASK != kLobesAll ? NL : (b).n_lobes); ++i) \
+        if (MASK == kLobesAll || i < (b).n_lobes)
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ V3 to_local(const BsdfT<NL, MASK>& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ V3 to_world(const BsdfT<NL, MASK>& b, V3 v) {
     return v3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
               b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-template <int NL>
-static __device__ int bsdf_num_components(const BsdfT<NL>& b, uint32_t flags) {
+template <int NL, uint32_t MASK>
+static __device__ int bsdf_num_components(const BsdfT<NL, MASK>& b, uint32_t flags) {
     int n = 0;
-    for (int i = 0; i < b.n_lobes; ++i) n += lobe_matches<(NL > 2)>(b.lobes[i], flags) ? 1 : 0;
+    RRT_FOR_LOBES(i, b) n += lobe_matches<(NL > 2), MASK>(b.lobes[i], flags) ? 1 : 0;
     return n;
 }
-template <int NL>
-RRT_SHADE_FN Rgb bsdf_f(const BsdfT<NL>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ Rgb bsdf_f_body(const BsdfT<NL, MASK>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     constexpr bool BIG = NL > 2;
     V3 wi = to_local(b, wi_w), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);
     bool reflect = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0;
     Rgb f = rgb(0.0);
-    for (int i = 0; i < b.n_lobes; ++i) {
+    RRT_FOR_LOBES(i, b) {
         const Lobe& l = b.lobes[i];
-        const uint32_t ty = lobe_type<BIG>(l);
-        if (lobe_matches<BIG>(l, flags) && ((reflect && (ty & BXDF_REFLECTION)) || (!reflect && (ty & BXDF_TRANSMISSION))))
-            f = f + lobe_f<BIG>(l, wo, wi);
+        const uint32_t ty = lobe_type<BIG, MASK>(l);
+        if (lobe_matches<BIG, MASK>(l, flags) && ((reflect && (ty & BXDF_REFLECTION)) || (!reflect && (ty & BXDF_TRANSMISSION))))
+            f = f + lobe_f<BIG, MASK>(l, wo, wi);
     }
     return f;
 }
-// Bsdf::pdf (reflection.rs:382-404)
 template <int NL>
-RRT_SHADE_FN double bsdf_pdf(const BsdfT<NL>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+RRT_SHADE_FN Rgb bsdf_f_out(const BsdfT<NL, kLobesAll>& b, V3 wo_w, V3 wi_w, uint32_t flags) { return bsdf_f_body(b, wo_w, wi_w, flags); }
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ Rgb bsdf_f(const BsdfT<NL, MASK>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    if constexpr (MASK == kLobesAll) return bsdf_f_out(b, wo_w, wi_w, flags);
+    else return bsdf_f_body(b, wo_w, wi_w, flags);
+}
+// Bsdf::pdf (reflection.rs:382-404)
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ double bsdf_pdf_body(const BsdfT<NL, MASK>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
     constexpr bool BIG = NL > 2;
     if (b.n_lobes == 0) return 0.0;
     V3 wo = to_local(b, wo_w), wi = to_local(b, wi_w);
     if (wo.z == 0.0) return 0.0;
     double pdf = 0.0;
     int matching = 0;
-    for (int i = 0; i < b.n_lobes; ++i)
-        if (lobe_matches<BIG>(b.lobes[i], flags)) {
+    RRT_FOR_LOBES(i, b)
+        if (lobe_matches<BIG, MASK>(b.lobes[i], flags)) {
             matching += 1;
-            pdf += lobe_pdf<BIG>(b.lobes[i], wo, wi);
+            pdf += lobe_pdf<BIG, MASK>(b.lobes[i], wo, wi);
         }
     return matching > 0 ? pdf / (double)matching : 0.0;
+}
+template <int NL>
+RRT_SHADE_FN double bsdf_pdf_out(const BsdfT<NL, kLobesAll>& b, V3 wo_w, V3 wi_w, uint32_t flags) { return bsdf_pdf_body(b, wo_w, wi_w, flags); }
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ double bsdf_pdf(const BsdfT<NL, MASK>& b, V3 wo_w, V3 wi_w, uint32_t flags) {
+    if constexpr (MASK == kLobesAll) return bsdf_pdf_out(b, wo_w, wi_w, flags);
+    else return bsdf_pdf_body(b, wo_w, wi_w, flags);
 }
 // sampling.rs:233-242
 __device__ __forceinline__ V3 uniform_sample_sphere(P2 u) {
@@ -850,8 +942,9 @@ RRT_SHADE_FN Rgb area_sample_li(const LightRec& l, V3 ref_p, P2 u, V3* wi, doubl
     return dot(ns, -*wi) > 0.0 ? l.intensity : rgb(0.0);  // AreaLight::l (diffuse.rs:134-140)
 }
 
-template <int NL>
-RRT_SHADE_FN Rgb bsdf_sample_f(const BsdfT<NL>& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ Rgb bsdf_sample_f_body(const BsdfT<NL, MASK>& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags,
+                                                  uint32_t* sampled_type) {
     constexpr bool BIG = NL > 2;
     const int matching = bsdf_num_components(b, flags);
     if (matching == 0) {
@@ -862,32 +955,56 @@ RRT_SHADE_FN Rgb bsdf_sample_f(const BsdfT<NL>& b, V3 wo_w, V3* wi_w, P2 u, doub
     uint64_t c64 = as_u64(floor(u.x * (double)matching));
     int comp = c64 > (uint64_t)matching ? matching : (int)c64;
     int count = comp, chosen = 0;
-    for (int i = 0; i < b.n_lobes; ++i)
-        if (lobe_matches<BIG>(b.lobes[i], flags)) {
+    bool searching = true;
+    RRT_FOR_LOBES(i, b)
+        if (searching && lobe_matches<BIG, MASK>(b.lobes[i], flags)) {
             if (count == 0) {
                 chosen = i;
-                break;
+                searching = false;
+                if (MASK == kLobesAll) break;
             }
             count -= 1;
         }
-    const Lobe& l = b.lobes[chosen];
     P2 ur = {rmin(u.x * (double)matching - (double)comp, kOneMinusEps), u.y};
     V3 wi = v3(0, 0, 0), wo = to_local(b, wo_w);
     if (wo.z == 0.0) return rgb(0.0);  // NB: *pdf is not touched here either (reflection.rs:343-345)
     *pdf = 0.0;
-    *sampled_type = lobe_type<BIG>(l);
-    Rgb f = lobe_sample_f<BIG>(l, wo, &wi, ur, pdf, sampled_type);
+    Rgb f = rgb(0.0);
+    uint32_t chosen_type = 0;
+    if constexpr (MASK == kLobesAll) {
+        const Lobe& l = b.lobes[chosen];
+        chosen_type = lobe_type<BIG, MASK>(l);
+        *sampled_type = chosen_type;
+        f = lobe_sample_f<BIG, MASK>(l, wo, &wi, ur, pdf, sampled_type);
+    } else {  // static lobe indices: each slot's code is the one lobe kind that slot can hold
+#pragma unroll
+        for (int i = 0; i < NL; ++i)
+            if (i == chosen) {
+                chosen_type = lobe_type<BIG, MASK>(b.lobes[i]);
+                *sampled_type = chosen_type;
+                f = lobe_sample_f<BIG, MASK>(b.lobes[i], wo, &wi, ur, pdf, sampled_type);
+            }
+    }
     if (*pdf == 0.0) {
         *sampled_type = 0;
         return rgb(0.0);
     }
     *wi_w = to_world(b, wi);
-    if (!(lobe_type<BIG>(l) & BXDF_REFLECTION) && matching > 1) {
-        for (int i = 0; i < b.n_lobes; ++i)
-            if (i != chosen && lobe_matches<BIG>(b.lobes[i], flags)) *pdf += lobe_pdf<BIG>(b.lobes[i], wo, wi);
+    if (!(chosen_type & BXDF_REFLECTION) && matching > 1) {
+        RRT_FOR_LOBES(i, b)
+            if (i != chosen && lobe_matches<BIG, MASK>(b.lobes[i], flags)) *pdf += lobe_pdf<BIG, MASK>(b.lobes[i], wo, wi);
     }
     if (matching > 1) *pdf /= (double)matching;
     return f;  // Q15: the multi-lobe re-evaluation is computed into a shadowed variable and dropped
+}
+template <int NL>
+RRT_SHADE_FN Rgb bsdf_sample_f_out(const BsdfT<NL, kLobesAll>& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+    return bsdf_sample_f_body(b, wo_w, wi_w, u, pdf, flags, sampled_type);
+}
+template <int NL, uint32_t MASK>
+__device__ __forceinline__ Rgb bsdf_sample_f(const BsdfT<NL, MASK>& b, V3 wo_w, V3* wi_w, P2 u, double* pdf, uint32_t flags, uint32_t* sampled_type) {
+    if constexpr (MASK == kLobesAll) return bsdf_sample_f_out(b, wo_w, wi_w, u, pdf, flags, sampled_type);
+    else return bsdf_sample_f_body(b, wo_w, wi_w, u, pdf, flags, sampled_type);
 }
 
 // Material::bump (material/mod.rs:22-65): the shading frame after displacement by the material's bump map.  Literal:
@@ -962,8 +1079,10 @@ static __device__ __noinline__ void material_at_big(const ShadeScene& sc, const 
 }
 
 // Material::compute_scattering_functions once the parameters are values.  `dz`: the material's DisneyRec (NL = 8 only).
-template <int NL>
-RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, BsdfT<NL>* b, const DisneyRec* dz = nullptr) {
+// KIND >= 0: the caller knows every hit it shades carries a material of that kind (0 Matte, 1 Plastic, 2 Metal).
+template <int KIND, int NL, uint32_t MASK>
+__device__ __forceinline__ void make_bsdf_body(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, BsdfT<NL, MASK>* b,
+                                               const DisneyRec* dz) {
     b->ns = s.shn;
     b->ss = normalize(s.shdpdu);
     b->ng = s.n;
@@ -1120,7 +1239,7 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
         }
         return;
     }
-    switch (m.kind) {
+    switch (KIND >= 0 ? (uint32_t)KIND : m.kind) {
         case 0: {  // MatteMaterial (matte.rs:36-61)
             Rgb r = clamp_rgb(m.kd, 0.0, kInfD);
             double sig = clampd(m.sigma, 0.0, 90.0);
@@ -1227,6 +1346,16 @@ RRT_SHADE_FN void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_m
             return;
         }
     }
+}
+template <int NL>
+RRT_SHADE_FN void make_bsdf_out(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, BsdfT<NL, kLobesAll>* b, const DisneyRec* dz) {
+    make_bsdf_body<-1>(m, s, allow_multiple_lobes, b, dz);
+}
+template <int KIND = -1, int NL, uint32_t MASK>
+__device__ __forceinline__ void make_bsdf(const MaterialRec& m, const Surface& s, bool allow_multiple_lobes, BsdfT<NL, MASK>* b,
+                                          const DisneyRec* dz = nullptr) {
+    if constexpr (MASK == kLobesAll) make_bsdf_out(m, s, allow_multiple_lobes, b, dz);
+    else make_bsdf_body<KIND>(m, s, allow_multiple_lobes, b, dz);
 }
 
 }  // namespace rrt
