@@ -11,7 +11,7 @@
 //   resolve   : unoccluded contributions are added to their path's radiance
 //   deposit   : FilmTile::add_sample through the filter table, per-pixel f64 atomics
 //
-// A chunk of up to kChunk camera samples runs generate, then max_depth + 1 rounds of
+// A chunk of up to kChunk camera samples (render_kernels.cuh: few, large chunks) runs generate, then max_depth + 1 rounds of
 // extend/shade/shadow/resolve, then deposit; every count lives on the device, so the whole frame
 // is one stream of launches with no host synchronisation until the end.
 #include <cuda_runtime.h>
@@ -705,26 +705,75 @@ __global__ void advance_kernel(Queues q, int cur) {
     for (int b = 0; b < 2 * kShadeBins; ++b) q.counters[16 + b] = 0;
 }
 
+#ifndef RRT_DEPOSIT_WARP_SUM
+#define RRT_DEPOSIT_WARP_SUM 1
+#endif
 // FilmTile::add_sample (film.rs:77-130) straight into the frame's film: radiance guards of
 // integrator/mod.rs:105-122, luminance clamp, filter-table splat.  4 doubles per pixel:
 // sum of L * weight * filter (RGB) and sum of filter weights.
 __global__ void __launch_bounds__(256) deposit_kernel(FilmParams film, const Path* __restrict__ paths, uint32_t count,
                                                        double* __restrict__ pixels, double* __restrict__ dump, uint64_t dump_base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const Path p = paths[i];
-    if (p.state == 0) return;
-    Rgb l = p.L;
+    const bool live = i < count && paths[i].state != 0;
+    Path p;
+    if (live) p = paths[i];
+    Rgb l = live ? p.L : rgb(0.0);
     if (has_nan(l) || lum(l) < -1e-5 || isinf(lum(l))) l = rgb(0.0);
-    if (lum(l) > film.max_sample_luminance) l = l * (film.max_sample_luminance / lum(l));
-    const double dx = p.pfx - 0.5, dy = p.pfy - 0.5;
+    if (live && lum(l) > film.max_sample_luminance) l = l * (film.max_sample_luminance / lum(l));
+    const double dx = live ? p.pfx - 0.5 : 0.0, dy = live ? p.pfy - 0.5 : 0.0;
     int64_t p0x = as_i64(ceil(dx - film.rx)), p0y = as_i64(ceil(dy - film.ry));
     int64_t p1x = as_i64(dx + film.rx) + 1, p1y = as_i64(dy + film.ry) + 1;  // Q14: truncation toward zero
     p0x = p0x > 0 ? p0x : 0;
     p0y = p0y > 0 ? p0y : 0;
     p1x = p1x < film.xres ? p1x : film.xres;
     p1y = p1y < film.yres ? p1y : film.yres;
-    const Rgb lw = l * p.weight;
+    const Rgb lw = live ? l * p.weight : rgb(0.0);
+#if RRT_DEPOSIT_WARP_SUM
+    // A sample under a filter of radius <= 0.5 lands in ONE pixel, and a warp's 32 consecutive chunk slots are samples of
+    // the same pixel or two (chunk_slot_sample: pixel-major): 128 atomics on four addresses.  Runs of lanes with the same
+    // pixel add their contributions up first (a segmented shuffle reduction, lane order) and the run's first lane adds
+    // the sums: 4 atomics per run.
+    const bool single = live && p1x - p0x == 1 && p1y - p0y == 1;
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        double w = 0.0;
+        Rgb c = rgb(0.0);
+        uint32_t key = 0xffffffffu - lane;  // no neighbour shares it
+        if (single) {
+            const double fy = fabs(((double)p0y - dy) * film.inv_ry * 16.0), fx = fabs(((double)p0x - dx) * film.inv_rx * 16.0);
+            int64_t iy = as_i64(floor(fy)), ix = as_i64(floor(fx));
+            iy = iy < 15 ? iy : 15;
+            ix = ix < 15 ? ix : 15;
+            w = film.table[iy * 16 + ix];
+            c = lw * w;
+            key = (uint32_t)(p0y * film.xres + p0x);
+        }
+        const uint32_t key_before = __shfl_up_sync(0xffffffffu, key, 1);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t k2 = __shfl_down_sync(0xffffffffu, key, off);
+            const double r2 = __shfl_down_sync(0xffffffffu, c.r, off), g2 = __shfl_down_sync(0xffffffffu, c.g, off);
+            const double b2 = __shfl_down_sync(0xffffffffu, c.b, off), w2 = __shfl_down_sync(0xffffffffu, w, off);
+            if (lane + off < 32u && k2 == key) {
+                c.r += r2;
+                c.g += g2;
+                c.b += b2;
+                w += w2;
+            }
+        }
+        if (single && (lane == 0u || key_before != key)) {
+            double* px = pixels + 4 * (size_t)key;
+            atomicAdd(px + 0, c.r);
+            atomicAdd(px + 1, c.g);
+            atomicAdd(px + 2, c.b);
+            atomicAdd(px + 3, w);
+        }
+    }
+    if (!live) return;
+    if (single) p1y = p0y;  // done above
+#else
+    if (!live) return;
+#endif
     for (int64_t y = p0y; y < p1y; ++y) {
         const double fy = fabs(((double)y - dy) * film.inv_ry * 16.0);
         int64_t iy = as_i64(floor(fy));
@@ -1600,7 +1649,18 @@ int Renderer::create(int device, const HostScene& scene, const RayTracer* agg, c
         const FilmParams& F = I.film;
         const uint64_t ntx = (uint64_t)(F.sb[2] - F.sb[0] + kTile - 1) / kTile, nty = (uint64_t)(F.sb[3] - F.sb[1] + kTile - 1) / kTile;
         const uint64_t frame = ntx * nty * kTile * kTile * std::max<uint64_t>(1, I.ip.n_samples);
-        I.chunk = (uint32_t)std::min<uint64_t>(kChunk, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
+        uint64_t cap = kChunk;
+        if (const char* e = std::getenv("RRT_CHUNK_LOG2")) cap = 1ull << std::min(std::max(std::atoi(e), 16), 28);
+        {
+            // at most half of the free device memory (path record, two extension queues, hits, shade order, one shadow-queue
+            // entry per light sample, the traversal kernels' sort workspace; + differentials / branch stacks when used)
+            size_t free_b = 0, total_b = 0;
+            RND_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const uint64_t per_slot = sizeof(Path) + 2 * (sizeof(rrt_ray) + 4) + sizeof(rrt_hit) + 5 + 32 + 2 * 93 + sizeof(RayDiffRec);
+            const uint64_t fit = (uint64_t)(free_b / 2) / per_slot;
+            cap = std::min<uint64_t>(cap, std::max<uint64_t>(1u << 16, fit & ~65535ull));
+        }
+        I.chunk = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1u << 16, (frame + 65535ull) & ~65535ull));
         // UniformSampleAll: up to n_lights shadow rays per hit — the chunk shrinks so that the shadow queue does not grow
         I.all_lights = (d.integrator_kind == RRT_INTEGRATOR_DEBUG || (d.integrator_kind == RRT_INTEGRATOR_DIRECT && d.light_strategy == 1)) && !lights.empty();
         uint32_t n_env = 0;  // an InfiniteAreaLight's estimate has two shadow-queue entries

@@ -16,10 +16,16 @@
 namespace rrt {
 namespace rk {
 
+// Camera samples in flight.  Every launch of a round pays a fixed cost — the persistent kernels' ramp and the tail in which the
+// last long rays finish on a mostly idle GPU: about 35 us per launch, 100 launches per chunk — so a frame wants few, large
+// chunks: 4K x 256 spp ran 554 / 641 / 693 / 723 Msamples/s with 2^23 / 2^24 / 2^25 / 2^26 slots, 1080p x 64 spp 529 / 582 / 611 /
+// 627 (profiles/r2_sweep_chunk_and_deposit.txt).  A slot is about 0.5 KB of path state and queue entries: 2^26 of them are 33 GB of the
+// 180 GB, and Renderer::create caps the chunk at the frame and at half of the free device memory (RRT_CHUNK_LOG2 in the
+// environment lowers it).
 #ifndef RRT_CHUNK_LOG2
-#define RRT_CHUNK_LOG2 23
+#define RRT_CHUNK_LOG2 26
 #endif
-constexpr uint32_t kChunk = 1u << RRT_CHUNK_LOG2;  // camera samples in flight
+constexpr uint32_t kChunk = 1u << RRT_CHUNK_LOG2;
 constexpr int kTile = 16;              // integrator/mod.rs:55
 
 struct FilmParams {

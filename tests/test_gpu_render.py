@@ -321,6 +321,32 @@ def test_f32_lens_walks_change_nothing(ctx, tmp_path, monkeypatch):
             assert np.allclose(f0, f1, rtol=1e-12, atol=0), flag
 
 
+def test_shading_by_material_kind_changes_nothing(ctx, tmp_path, monkeypatch):
+    """Constant-valued scenes shade a round's hits with one launch per material kind: an escaped-ray kernel, kernels whose
+    Bsdf is narrowed to the lobe set of Matte / Plastic / Metal at compile time (csrc/shading.cuh "lobe sets"), and the
+    general code over the bins of Mirror and Glass.  RRT_SHADE_BY_KIND=0 keeps the one general kernel.  Same functions, same
+    operation order: every camera sample's first hit, every ray count and the film (to the rounding of its unordered
+    atomic sums) must not move — on a scene with all five kinds (Lambert and Oren-Nayar Matte, smooth and rough glass) under
+    the Path integrator, and on config 1's meshes under DirectLighting."""
+    cases = [synth.scene_c4(str(tmp_path / "c4"), n_spheres=4000, xres=384, yres=216, nsamp=17, extent=12.0, extra_materials=True),
+             synth.scene_c1(str(tmp_path / "c1"), xres=320, yres=180, nsamp=9, integrator="DirectLighting", max_depth=1)]
+    for path in cases:
+        runs = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("RRT_SHADE_BY_KIND", flag)
+            gpu = Render.load(ctx, path, seed=1)
+            gpu.enable_hit_dump()
+            gpu.run()
+            runs[flag] = (gpu.hit_dump(), gpu.film(), gpu.stats())
+        (d0, f0, s0), (d1, f1, s1) = runs["0"], runs["1"]
+        assert s1["launches"] > s0["launches"], (s0, s1)   # the per-kind launches did run
+        for k in ("camera_rays", "zero_weight", "extension_rays", "shadow_rays", "bounces"):
+            assert s0[k] == s1[k], (k, s0, s1)
+        assert s0["bounces"] > 0 or "c1" in path
+        assert np.array_equal(d0, d1)
+        assert np.allclose(f0, f1, rtol=1e-12, atol=1e-300), float(np.abs(f0 - f1).max())
+
+
 @pytest.mark.parametrize("integrator", ["Path", "DirectLighting"])
 def test_clipped_and_stretched_spheres(ctx, tmp_path, integrator):
     """SURVEY §8a6 through the renderer: spheres clipped in z / phi (their inside seen through the opening: hits at the
