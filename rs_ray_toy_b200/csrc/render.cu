@@ -591,6 +591,8 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
 
 // ---- shade order: a counting sort of the round's hits by (miss | material kind) -----------------------------
 // (grid-stride over the live count, like the ray sort: a few CTAs per SM instead of a grid sized for the chunk)
+// (Ending an escaped ray's path here, while it is binned, instead of in shade_miss_kernel was measured: 5-6 % of a FRAME
+// slower, profiles/r2_sweep_miss_in_bin.txt — the scattered Path accesses do not belong in this streaming pass.)
 __global__ void __launch_bounds__(256) shade_bin_kernel(ShadeScene sc, Queues q, int cur) {
     const uint32_t n = q.counters[cur];
     __shared__ uint32_t h[kShadeBins];

@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
 // ---- shading by material kind (constant-valued scenes without environment lights: the throughput path) ----------------
 // shade_bin / shade_scatter group a round's entries as [misses | kind 0 | kind 1 | ...] (q.counters[16 + bin] entries each).
 // One launch per bin that the scene can fill walks that bin's slice of the order with a resident grid:
-//  * shade_miss_kernel (render_shade_kind.cu): an escaped ray ends its path (path.rs:79-93 without infinite lights) — a few registers' worth of work
-//    that no longer occupies a slot of the 158-register kernel;
+//  * shade_miss_kernel (render_shade_kind.cu): an escaped ray ends its path (path.rs:79-93 without infinite lights) — a few
+//    registers' worth of work that no longer occupies a slot of the 158-register kernel;
 //  * shade_range_kernel<KIND> for Matte, Plastic and Metal: the Bsdf is one or two statically known lobes in registers, the
 //    code a fraction of the general kernel's (which carries every lobe of every material behind calls);
 //  * shade_range_kernel<-1> over the bins of the other kinds (Mirror, Glass): the general code.
@@ -796,8 +796,8 @@ using ShadeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorPa
 using WhittedFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, WhittedBranch*, Queues, int);
 using ShadeRangeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, Queues, int, int, int);
 using ShadeMissFn = void (*)(Path*, Queues, int);
-ShadeRangeFn shade_range_kernel_for(int kind);   // render_shade_kind.cu: 0 Matte, 1 Plastic, 2 Metal; anything else = the general code
 ShadeMissFn shade_miss_kernel_fn();              // render_shade_kind.cu
+ShadeRangeFn shade_range_kernel_for(int kind);   // render_shade_kind.cu: 0 Matte, 1 Plastic, 2 Metal; anything else = the general code
 ShadeFn shade_kernel_textured(bool all_lights);  // render_shade_tex.cu
 ShadeFn shade_kernel_textured_env();             // render_shade_env.cu
 ShadeFn shade_kernel_big(bool env);              // render_shade_big.cu: Translucent / Disney / Debug materials

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) shade_miss_kernel(Path* __restrict__ path
         P->state = 2;
     }
 }
+ShadeMissFn shade_miss_kernel_fn() { return shade_miss_kernel; }
 
 ShadeRangeFn shade_range_kernel_for(int kind) {
     switch (kind) {
@@ -26,7 +27,6 @@ ShadeRangeFn shade_range_kernel_for(int kind) {
         default: return shade_range_kernel<-1>;
     }
 }
-ShadeMissFn shade_miss_kernel_fn() { return shade_miss_kernel; }
 
 }  // namespace rk
 }  // namespace rrt

@@ -339,7 +339,9 @@ def test_shading_by_material_kind_changes_nothing(ctx, tmp_path, monkeypatch):
             gpu.run()
             runs[flag] = (gpu.hit_dump(), gpu.film(), gpu.stats())
         (d0, f0, s0), (d1, f1, s1) = runs["0"], runs["1"]
-        assert s1["launches"] > s0["launches"], (s0, s1)   # the per-kind launches did run
+        # the per-kind launches did run: four (Matte, Plastic, Metal, Mirror + Glass) for one general launch per round on the
+        # sphere field; config 1's primitives are all Matte, one launch either way
+        assert s1["launches"] > s0["launches"] or "c1" in path, (s0, s1)
         for k in ("camera_rays", "zero_weight", "extension_rays", "shadow_rays", "bounces"):
             assert s0[k] == s1[k], (k, s0, s1)
         assert s0["bounces"] > 0 or "c1" in path
