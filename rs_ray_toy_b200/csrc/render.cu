@@ -591,8 +591,6 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
 
 // ---- shade order: a counting sort of the round's hits by (miss | material kind) -----------------------------
 // (grid-stride over the live count, like the ray sort: a few CTAs per SM instead of a grid sized for the chunk)
-// (Ending an escaped ray's path here, while it is binned, instead of in shade_miss_kernel was measured: 5-6 % of a FRAME
-// slower, profiles/r2_sweep_miss_in_bin.txt — the scattered Path accesses do not belong in this streaming pass.)
 __global__ void __launch_bounds__(256) shade_bin_kernel(ShadeScene sc, Queues q, int cur) {
     const uint32_t n = q.counters[cur];
     __shared__ uint32_t h[kShadeBins];
@@ -1810,7 +1808,6 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
             launches += 2;
 #endif
             if (I.shade_by_kind) {
-                shade_miss_kernel_fn()<<<small_grid, 256, 0, I.stream>>>(I.d_paths, I.q, cur);
                 for (int k = 0; k < 3; ++k)
                     if ((I.kind_mask >> k) & 1u) {
                         shade_range_kernel_for(k)<<<I.kind_grid[k], 128, 0, I.stream>>>(I.sc, I.ht, I.d_perms, I.ip, I.d_paths, I.q, cur, 1 + k,
@@ -1822,6 +1819,7 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
                                                                                     kShadeBins - 1);
                     launches += 1;
                 }
+                launches -= 1;  // (the common `+= 1` below belongs to the one-launch branch)
             } else {
                 ShadeFn shade = I.big_bsdf   ? shade_kernel_big(I.env_mode)
                                 : I.env_mode   ? (I.textured ? shade_kernel_textured_env() : shade_kernel<false, false, true>)

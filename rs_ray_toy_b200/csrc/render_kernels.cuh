@@ -439,8 +439,10 @@ __global__ void __launch_bounds__(128, BIG ? 1 : RRT_SHADE_MINBLOCKS) shade_kern
 // ---- shading by material kind (constant-valued scenes without environment lights: the throughput path) ----------------
 // shade_bin / shade_scatter group a round's entries as [misses | kind 0 | kind 1 | ...] (q.counters[16 + bin] entries each).
 // One launch per bin that the scene can fill walks that bin's slice of the order with a resident grid:
-//  * shade_miss_kernel (render_shade_kind.cu): an escaped ray ends its path (path.rs:79-93 without infinite lights) — a few
-//    registers' worth of work that no longer occupies a slot of the 158-register kernel;
+//  * the misses need NOTHING: without infinite lights an escaped ray adds no radiance (path.rs:79-93), its path simply gets no
+//    next ray; the generate kernels have already written the "no first hit" record (first_prim = -1, first_t = 0) a camera ray
+//    that escapes would leave, and nothing on this flow tells a live Path from a finished one (`state` is read as "slot holds a
+//    sample" by deposit and as the camera-ray marker by whitted_kernel only);
 //  * shade_range_kernel<KIND> for Matte, Plastic and Metal: the Bsdf is one or two statically known lobes in registers, the
 //    code a fraction of the general kernel's (which carries every lobe of every material behind calls);
 //  * shade_range_kernel<-1> over the bins of the other kinds (Mirror, Glass): the general code.
@@ -795,8 +797,6 @@ __global__ void __launch_bounds__(128, BIG ? 1 : 2) whitted_kernel(ShadeScene sc
 using ShadeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, Queues, int);
 using WhittedFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, WhittedBranch*, Queues, int);
 using ShadeRangeFn = void (*)(ShadeScene, HaltonTables, const uint16_t*, IntegratorParams, Path*, Queues, int, int, int);
-using ShadeMissFn = void (*)(Path*, Queues, int);
-ShadeMissFn shade_miss_kernel_fn();              // render_shade_kind.cu
 ShadeRangeFn shade_range_kernel_for(int kind);   // render_shade_kind.cu: 0 Matte, 1 Plastic, 2 Metal; anything else = the general code
 ShadeFn shade_kernel_textured(bool all_lights);  // render_shade_tex.cu
 ShadeFn shade_kernel_textured_env();             // render_shade_env.cu
