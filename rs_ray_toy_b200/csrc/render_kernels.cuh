@@ -110,8 +110,9 @@ __device__ __forceinline__ uint32_t queue_slot(uint32_t* counter, bool want) {
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
-// The part of a Path the shade kernel works on: it reads and writes these fields only, the rest of the 200-byte
-// record (film position, weight, radiance, pixel) stays in memory.
+// The part of a path the shade kernel works on: beta, eta_scale, hidx, dim and bounces are read from and written to the Path
+// record, o and d come from the extension-queue entry that was traced; the rest of the 200-byte record (film position,
+// weight, radiance, pixel) stays in memory.
 struct PathCore {
     V3 o, d;
     Rgb beta;
@@ -130,6 +131,9 @@ __device__ __forceinline__ P2 next_2d(const HaltonTables& ht, const uint16_t* pe
     return u;
 }
 
+#ifndef RRT_SHADE_RAY_FROM_QUEUE
+#define RRT_SHADE_RAY_FROM_QUEUE 1
+#endif
 #ifndef RRT_SHADE_MINBLOCKS
 #define RRT_SHADE_MINBLOCKS 3
 #endif
@@ -179,8 +183,19 @@ __device__ __forceinline__ void shade_one(const ShadeScene& sc, const HaltonTabl
         pid = (cur ? q.ext_path[1] : q.ext_path[0])[qi];  // (static indices: a run-time index into a kernel parameter
         Path* const P = paths + pid;                      //  makes nvcc keep a copy of the whole struct in local memory)
         PathCore p;
+#if RRT_SHADE_RAY_FROM_QUEUE
+        {
+            // the ray that was traced IS the path's current (o, d): read it from the queue entry — indexed like the hit, so the
+            // surface frame waits for (order -> hit, ray -> primitive) and not for the path record — and never store it in Path
+            const double2* const rp = reinterpret_cast<const double2*>((cur ? q.ext_rays[1] : q.ext_rays[0]) + qi);
+            const double2 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+            p.o = v3(r0.x, r0.y, r1.x);
+            p.d = v3(r1.y, r2.x, r2.y);
+        }
+#else
         p.o = P->o;
         p.d = P->d;
+#endif
         p.beta = P->beta;
         p.eta_scale = P->eta_scale;
         p.hidx = P->hidx;
@@ -402,16 +417,16 @@ __device__ __forceinline__ void shade_one(const ShadeScene& sc, const HaltonTabl
                 }
             }
         }
-        if (alive) {
+        if (alive) {  // (a path that ends here is not read again: deposit wants its L, weight and film point only)
+#if !RRT_SHADE_RAY_FROM_QUEUE
             P->o = p.o;
             P->d = p.d;
+#endif
             P->beta = p.beta;
             P->eta_scale = p.eta_scale;
             P->bounces = p.bounces;
-        } else {
-            P->state = 2;
+            P->dim = p.dim;
         }
-        P->dim = p.dim;
     }
     const uint32_t es = queue_slot(q.counters + (cur ^ 1), emit_ext);
     if (emit_ext) {
@@ -459,11 +474,19 @@ __device__ __forceinline__ void shade_bin_range(const Queues& q, int bin_first, 
 #define RRT_SHADE_PREFETCH 0
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// CTAs per SM of shade_range_kernel<Matte / Plastic / Metal>: 4 = 128 registers, 3 = 168 (profiles/r2_sweep_shade_by_kind.txt,
+// r2_sweep_shade_ray_from_queue.txt)
 #ifndef RRT_SHADE_KIND_MINBLOCKS
 #define RRT_SHADE_KIND_MINBLOCKS 4
 #endif
+#ifndef RRT_SHADE_MINBLOCKS_PLASTIC
+#define RRT_SHADE_MINBLOCKS_PLASTIC 3  // the two-lobe and the conductor kernels spill 250-380 B at 128 registers: config 4 +1.9 % at 3
+#endif
+#ifndef RRT_SHADE_MINBLOCKS_METAL
+#define RRT_SHADE_MINBLOCKS_METAL 3
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128, KIND >= 0 ? RRT_SHADE_KIND_MINBLOCKS : RRT_SHADE_MINBLOCKS)
+__global__ void __launch_bounds__(128, KIND == 0 ? RRT_SHADE_KIND_MINBLOCKS : KIND == 1 ? RRT_SHADE_MINBLOCKS_PLASTIC : KIND == 2 ? RRT_SHADE_MINBLOCKS_METAL : RRT_SHADE_MINBLOCKS)
 shade_range_kernel(ShadeScene sc, HaltonTables ht, const uint16_t* __restrict__ perms, IntegratorParams ip, Path* __restrict__ paths, Queues q,
                    int cur, int bin_first, int bin_last) {
     uint32_t start, end;
