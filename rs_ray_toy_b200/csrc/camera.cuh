@@ -138,6 +138,19 @@ __device__ __forceinline__ LensF lens_f32(const LensElement* el, int i) {
     return LensF{(float)el[i].curvature_radius, (float)el[i].thickness, kLensBand * ap, ap * ap * (1.0f + kLensBand),
                  ap * ap * (1.0f - kLensBand), (float)(el[i].eta / ((i > 0 && eta_prev != 0.0) ? eta_prev : 1.0))};
 }
+// MUFU.RSQ / MUFU.RCP without the subnormal rescue rsqrtf() and __fdividef() compile to (three more instructions each, six
+// per interface).  Every argument here is a squared length, a discriminant or a root of lens-sized magnitudes; one that is
+// subnormal sits inside a band that answers LENS_UNSURE, and an inf / NaN result fails every `!(x > band)` test the same way.
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, RayF ray) {
     float ox = ray.ox, oy = ray.oy, oz = ray.oz, dx = ray.dx, dy = ray.dy, dz = ray.dz;
     float element_z = 0.0f;
@@ -149,7 +162,7 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, R
         float t, nx = 0.0f, ny = 0.0f, nz = 0.0f;
         if (R == 0.0f) {
             if (dz > 0.0f) return LENS_BLOCKED;
-            t = __fdividef(element_z - oz, dz);
+            t = (element_z - oz) * rcp_ftz(dz);
         } else {
             const float qz = oz - element_z;  // the ray origin relative to the element's vertex
             const float cz = qz - R;          // ... and relative to the sphere's centre
@@ -161,9 +174,9 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, R
             const float scale = bb + fabsf(ac4);
             if (disc < -kLensBand * scale) return LENS_BLOCKED;
             if (!(disc > kLensBand * scale)) return LENS_UNSURE;
-            const float root = disc * rsqrtf(disc);
+            const float root = disc * rsqrt_ftz(disc);
             const float q = b < 0.0f ? -0.5f * (b - root) : -0.5f * (b + root);
-            const float ta = __fdividef(q, a), tb = __fdividef(c, q);
+            const float ta = q * rcp_ftz(a), tb = c * rcp_ftz(q);
             const float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
             t = ((dz > 0.0f) != (R < 0.0f)) ? t0 : t1;
             if (t < -e.t_band) return LENS_BLOCKED;  // lengths are judged against the element's aperture radius
@@ -171,7 +184,7 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, R
             nx = fmaf(dx, t, ox);
             ny = fmaf(dy, t, oy);
             nz = fmaf(dz, t, cz);
-            const float inv = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+            const float inv = rsqrt_ftz(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
             nx *= inv; ny *= inv; nz *= inv;
             if (fmaf(nx, dx, fmaf(ny, dy, nz * dz)) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // faceforward(n, -d)
         }
@@ -182,14 +195,14 @@ __device__ __forceinline__ int lens_walk_from_film_f32(const LensF* el, int n, R
         ox = px; oy = py; oz = pz;
         if (R != 0.0f) {
             const float eta = e.eta;
-            const float dinv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            const float dinv = rsqrt_ftz(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             const float wx = -dx * dinv, wy = -dy * dinv, wz = -dz * dinv;
             const float cos_i = fmaf(nx, wx, fmaf(ny, wy, nz * wz));
             const float sin2_t = eta * eta * fmaxf(0.0f, 1.0f - cos_i * cos_i);
             if (sin2_t > 1.0f + kLensBand) return LENS_BLOCKED;
             if (!(sin2_t < 1.0f - kLensBand)) return LENS_UNSURE;
             const float ct2 = 1.0f - sin2_t;
-            const float k = eta * cos_i - ct2 * rsqrtf(ct2);
+            const float k = eta * cos_i - ct2 * rsqrt_ftz(ct2);
             dx = fmaf(nx, k, -wx * eta);
             dy = fmaf(ny, k, -wy * eta);
             dz = fmaf(nz, k, -wz * eta);

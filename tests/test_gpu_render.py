@@ -349,6 +349,26 @@ def test_shading_by_material_kind_changes_nothing(ctx, tmp_path, monkeypatch):
         assert np.allclose(f0, f1, rtol=1e-12, atol=1e-300), float(np.abs(f0 - f1).max())
 
 
+def test_chunk_size_changes_nothing(ctx, tmp_path, monkeypatch):
+    """A frame is rendered in chunks of up to 2^26 camera samples, capped by the frame (every other test's frame is one
+    chunk).  RRT_CHUNK_LOG2=16 cuts this one into 2^16-sample chunks — 19 of them, the last one partial: same camera
+    samples, same ray counts, same film to the rounding of its atomic sums."""
+    path = synth.scene_c4(str(tmp_path / "c4"), n_spheres=3000, xres=320, yres=240, nsamp=17, extent=12.0)
+    runs = {}
+    for log2 in ("26", "16"):
+        monkeypatch.setenv("RRT_CHUNK_LOG2", log2)
+        gpu = Render.load(ctx, path, seed=1)
+        gpu.enable_hit_dump()
+        gpu.run()
+        runs[log2] = (gpu.hit_dump(), gpu.film(), gpu.stats())
+    (d0, f0, s0), (d1, f1, s1) = runs["26"], runs["16"]
+    assert s0["chunks"] == 1 and s1["chunks"] == (320 * 240 * 16 + 65535) // 65536, (s0, s1)
+    for k in ("samples", "camera_rays", "zero_weight", "extension_rays", "shadow_rays", "bounces"):
+        assert s0[k] == s1[k], (k, s0, s1)
+    assert np.array_equal(d0, d1)
+    assert np.allclose(f0, f1, rtol=1e-12, atol=1e-300), float(np.abs(f0 - f1).max())
+
+
 @pytest.mark.parametrize("integrator", ["Path", "DirectLighting"])
 def test_clipped_and_stretched_spheres(ctx, tmp_path, integrator):
     """SURVEY §8a6 through the renderer: spheres clipped in z / phi (their inside seen through the opening: hits at the
