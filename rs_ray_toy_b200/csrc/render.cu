@@ -23,6 +23,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "render_kernels.cuh"
@@ -946,6 +947,8 @@ struct Renderer::Impl {
     double* d_dump = nullptr;
     uint64_t dump_capacity = 0, dump_count = 0;
     bool dump_enabled = false;
+    double* h_film = nullptr;   // pinned staging for read_film
+    size_t h_film_capacity = 0;
     cudaStream_t stream = nullptr;
 
     template <class T>
@@ -965,6 +968,7 @@ Renderer::~Renderer() {
     for (void* p : impl_->allocations) cudaFree(p);
     if (impl_->d_tiles) cudaFree(impl_->d_tiles);
     if (impl_->d_dump) cudaFree(impl_->d_dump);
+    if (impl_->h_film) cudaFreeHost(impl_->h_film);
     if (d_film_) cudaFree(d_film_);
     if (impl_->stream) cudaStreamDestroy(impl_->stream);
     delete impl_;
@@ -1876,9 +1880,22 @@ int Renderer::read_film(double* rgb_out, double* raw, std::string* err) {
     if (!impl_) return RRT_ERR_INVALID;
     RND_CUDA(cudaSetDevice(impl_->device));
     const size_t npix = (size_t)xres_ * (size_t)yres_;
-    std::vector<double> h(4 * npix);
-    RND_CUDA(cudaMemcpy(h.data(), d_film_, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < npix; ++i) {
+    // The frame's way to the host: one pinned staging buffer kept for the renderer's life (a 4K film is 265 MB — a pageable
+    // copy into a fresh zero-filled vector took 0.2 s of a 2.8 s frame), then the per-pixel conversion on every host thread.
+    Impl& I = *impl_;
+    if (I.h_film_capacity < 4 * npix) {
+        if (I.h_film) cudaFreeHost(I.h_film);
+        I.h_film = nullptr;
+        I.h_film_capacity = 0;
+        RND_CUDA(cudaHostAlloc((void**)&I.h_film, 4 * npix * sizeof(double), cudaHostAllocDefault));
+        I.h_film_capacity = 4 * npix;
+    }
+    RND_CUDA(cudaMemcpyAsync(I.h_film, d_film_, 4 * npix * sizeof(double), cudaMemcpyDeviceToHost, I.stream));
+    RND_CUDA(cudaStreamSynchronize(I.stream));
+    const double* const h = I.h_film;
+    const double film_scale = I.film_scale;
+    auto convert = [=](size_t begin, size_t end) {
+    for (size_t i = begin; i < end; ++i) {
         const double* c = &h[4 * i];
         // merge_film_tile (film.rs:248-263): tile contribution -> XYZ; the weight sum is added
         // once per colour channel (Q14)
@@ -1902,8 +1919,18 @@ int Renderer::read_film(double* rgb_out, double* raw, std::string* err) {
                 const double inv = 1.0 / fws;
                 for (int k = 0; k < 3; ++k) rgbv[k] = std::fmax(0.0, rgbv[k] * inv);
             }
-            for (int k = 0; k < 3; ++k) rgb_out[3 * i + k] = (rgbv[k] + 0.0) * impl_->film_scale;
+            for (int k = 0; k < 3; ++k) rgb_out[3 * i + k] = (rgbv[k] + 0.0) * film_scale;
         }
+    }
+    };
+    const size_t n_threads = std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)32, npix / 65536 + 1}));
+    if (n_threads == 1) {
+        convert(0, npix);
+    } else {
+        std::vector<std::thread> pool;
+        const size_t per = (npix + n_threads - 1) / n_threads;
+        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(convert, std::min(npix, t * per), std::min(npix, (t + 1) * per));
+        for (std::thread& t : pool) t.join();
     }
     return RRT_OK;
 }
