@@ -47,19 +47,27 @@ struct IntegratorParams {
     StratParams strat;
 };
 
-// Per camera sample state (one record per slot of the chunk)
-struct Path {
-    V3 o, d;
-    Rgb beta, L;
-    double eta_scale, pfx, pfy, weight;
-    uint64_t hidx;
+// Per camera sample state (one record per slot of the chunk).  Laid out by who touches what, in 32-byte sectors of a
+// sector-aligned 192-byte record: the shade kernels read and write bytes 0-47 (two sectors; the fields used to lie in four),
+// resolve adds to L (one sector), deposit reads state / weight / L / film point (three), the generate kernels stage the
+// camera ray in the last two.
+struct alignas(32) Path {
+    Rgb beta;                // sector 0
+    double eta_scale;
+    uint64_t hidx;           // sector 1
     uint32_t dim, bounces;
+    uint32_t state, pad;     // state: 0 = no sample in this slot, 1 = alive, 2 = finished; pad: ENV's specular-bounce flag
+    double weight;
+    Rgb L;                   // sector 2
+    double pfx;
+    double pfy;              // sector 3
     int32_t px, py;
-    uint32_t sample, state;  // state: 0 = no sample in this slot, 1 = alive, 2 = finished
+    uint32_t sample;
     int32_t first_prim;
-    uint32_t pad;
     double first_t;
+    V3 o, d;                 // sectors 4-5
 };
+static_assert(sizeof(Path) == 192, "Path is six sectors");
 
 struct Queues {
     rrt_ray* ext_rays[2];
@@ -111,7 +119,7 @@ __device__ __forceinline__ uint32_t queue_slot(uint32_t* counter, bool want) {
 
 // ---- shade ---------------------------------------------------------------------------------------------
 // The part of a path the shade kernel works on: beta, eta_scale, hidx, dim and bounces are read from and written to the Path
-// record, o and d come from the extension-queue entry that was traced; the rest of the 200-byte record (film position,
+// record, o and d come from the extension-queue entry that was traced; the rest of the 192-byte record (film position,
 // weight, radiance, pixel) stays in memory.
 struct PathCore {
     V3 o, d;
