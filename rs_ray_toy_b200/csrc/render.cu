@@ -321,6 +321,7 @@ struct GenSample {
     uint64_t hidx;
     P2 pf, pl;
 };
+static_assert(sizeof(GenSample) == sizeof(rrt_ray), "the split generate kernels pass survivors through an extension queue");
 constexpr uint32_t kGenQueue = 64;  // per warp; the screen phase stops at >= 32 entries and adds at most 32 per trip
 
 __device__ __forceinline__ P2 neighbour_film_point(P2 pf, int stage) {
@@ -587,6 +588,260 @@ __global__ void __launch_bounds__(128, RRT_GEN_MINBLOCKS)
         if (n_zero) atomicAdd(q.stats + 4, (unsigned long long)n_zero);
         if (n_quick) atomicAdd(q.stats + 5, (unsigned long long)n_quick);
         if (n_unsure) atomicAdd(q.stats + 6, (unsigned long long)n_unsure);
+    }
+}
+
+__device__ __forceinline__ bool chunk_slot_sample(const FilmParams& film, const IntegratorParams& ip, const Frame& fr, uint64_t sidx,
+                                                  int64_t* px, int64_t* py, uint32_t* sn);
+// ---- generate, screened, as two kernels ------------------------------------------------------------------------
+// The two phases of generate_screened_kernel as kernels of their own, the survivors passing through a list in global
+// memory (a GenSample is 64 bytes: the list borrows the second extension queue, which the first round's shade kernel
+// is the first to write).  The screen kernel is fp32 and integer work, the trace kernel f64: each gets the registers
+// and occupancy that suit it, and every warp of a kernel runs the same loop (the merged kernel's warps sat in different
+// phases of 74 KB of code: a quarter of its stall samples were instruction fetches, profiles/r2_generate_screened_ncu_full.txt).
+#ifndef RRT_GEN_SCREEN_MINBLOCKS
+#define RRT_GEN_SCREEN_MINBLOCKS 8
+#endif
+#ifndef RRT_GEN_TRACE_MINBLOCKS
+#define RRT_GEN_TRACE_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, RRT_GEN_SCREEN_MINBLOCKS)
+    generate_screen_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film, IntegratorParams ip,
+                           Frame fr, uint64_t base, uint32_t count, Path* __restrict__ paths, Queues q, GenSample* __restrict__ survivors) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    __shared__ GenSample s_screen[128];  // the sample a lane is screening
+    __shared__ LensF s_lf[kMaxLensElements];
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_lf[k] = lens_f32(cam.el, k);
+    __syncthreads();
+    GenSample& fs = s_screen[threadIdx.x];
+    uint32_t* const cursor = q.counters + 3;
+    bool exhausted = false;  // warp-uniform: the chunk's cursor has run out
+    bool fhave = false;
+    int fstage = GEN_MAIN;
+    uint32_t n_zero = 0, n_quick = 0, n_unsure = 0;
+    for (;;) {
+        const unsigned pending = __ballot_sync(FULL, fhave);
+        if (exhausted && pending == 0u) break;
+        const unsigned idle = ~pending;
+        if (idle != 0u && !exhausted) {
+            const int want = __popc(idle);
+            uint32_t first = 0;
+            if (lane == 0) first = atomicAdd(cursor, (uint32_t)want);
+            first = __shfl_sync(FULL, first, 0);
+            if ((uint64_t)first + (uint64_t)want >= count) exhausted = true;
+            const uint64_t mine = (uint64_t)first + (uint64_t)__popc(idle & lt);
+            if (!fhave && mine < count) {
+                const uint32_t slot = (uint32_t)mine;
+                int64_t x, y;
+                uint32_t sn;
+                if (!chunk_slot_sample(film, ip, fr, base + slot, &x, &y, &sn)) {
+                    paths[slot].state = 0;  // no sample in this slot
+                } else {
+                    fs.slot = slot;
+                    fs.sn = sn;
+                    fs.px = (int32_t)x;
+                    fs.py = (int32_t)y;
+                    fs.nb_ok = 0;
+                    if (q.cam_samples != nullptr) {  // StratifiedSampler: drawn by strat_camera_kernel
+                        const double* cs4 = q.cam_samples + 4 * (size_t)slot;
+                        fs.hidx = 0;
+                        fs.pf = P2{cs4[0], cs4[1]};
+                        fs.pl = P2{cs4[2], cs4[3]};
+                    } else {
+                        const uint64_t hidx = halton_index(ht, x, y, sn);
+                        fs.hidx = hidx;
+                        // get_camerasample (samplers/mod.rs:28-34): dims 0-1 film, 2-3 lens (+0.5, Q11), 4 time
+                        fs.pf = P2{(double)x + halton_sample(ht, perms, hidx, 0), (double)y + halton_sample(ht, perms, hidx, 1)};
+                        fs.pl = P2{halton_sample(ht, perms, hidx, 2) + 0.5, halton_sample(ht, perms, hidx, 3) + 0.5};
+                    }
+                    fhave = true;
+                    fstage = GEN_MAIN;
+                }
+            }
+        }
+        // one fp32 walk per lane
+        bool push = false, zero = false;
+        uint32_t nb = 0;
+        if (fhave) {
+            bool weight_nonzero;
+            const RayF rf = begin_film_ray_f32(cam, neighbour_film_point(fs.pf, fstage), fs.pl, &weight_nonzero);
+            const int verdict = lens_walk_from_film_f32(s_lf, cam.n_elements, rf);
+            if (verdict == LENS_UNSURE) {
+                push = true;  // undecided: the f64 procedure takes the whole sample
+                n_unsure += 1;
+            } else if (fstage == GEN_MAIN) {
+                if (verdict == LENS_BLOCKED) zero = true;
+                else fstage = GEN_XP;
+            } else {
+                n_quick += 1;
+                const bool ok = verdict == LENS_THROUGH && weight_nonzero;
+                if (fstage == GEN_XP) {
+                    fstage = ok ? GEN_YP : GEN_XM;
+                } else if (fstage == GEN_XM) {
+                    if (ok) fstage = GEN_YP;
+                    else zero = true;
+                } else if (fstage == GEN_YP) {
+                    if (ok) {
+                        push = true;
+                        nb = 1;
+                    } else {
+                        fstage = GEN_YM;
+                    }
+                } else {
+                    if (ok) {
+                        push = true;
+                        nb = 1;
+                    } else {
+                        zero = true;
+                    }
+                }
+            }
+        }
+        if (zero) {
+            Path* P = paths + fs.slot;
+            P->o = v3(0, 0, 0);
+            P->d = v3(0, 0, 0);
+            finish_camera_sample(P, fs, 0.0, ip.init_dim);
+            n_zero += 1;
+            fhave = false;
+        }
+        const uint32_t at = queue_slot(q.counters + 4, push);
+        if (push) {
+            GenSample g = fs;
+            g.nb_ok = nb;
+            survivors[at] = g;
+            fhave = false;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_zero += __shfl_xor_sync(FULL, n_zero, off);
+        n_quick += __shfl_xor_sync(FULL, n_quick, off);
+        n_unsure += __shfl_xor_sync(FULL, n_unsure, off);
+    }
+    if (lane == 0) {
+        if (n_zero) atomicAdd(q.stats + 4, (unsigned long long)n_zero);
+        if (n_quick) atomicAdd(q.stats + 5, (unsigned long long)n_quick);
+        if (n_unsure) atomicAdd(q.stats + 6, (unsigned long long)n_unsure);
+    }
+}
+
+__global__ void __launch_bounds__(128, RRT_GEN_TRACE_MINBLOCKS)
+    generate_trace_kernel(CameraData cam, IntegratorParams ip, Path* __restrict__ paths, Queues q, const GenSample* __restrict__ survivors) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    __shared__ LensElement s_el[kMaxLensElements];
+    __shared__ GenSample s_trace[128];  // the sample a lane is tracing
+    for (int k = threadIdx.x; k < cam.n_elements; k += blockDim.x) s_el[k] = cam.el[k];
+    __syncthreads();
+    GenSample& cs = s_trace[threadIdx.x];
+    const uint32_t n_list = q.counters[4];
+    uint32_t* const cursor = q.counters + 5;
+    bool exhausted = false;  // warp-uniform: the list's cursor has run out
+    bool have = false, need_begin = false;
+    int stage = GEN_MAIN, ei = 0;
+    RayD r = {v3(0, 0, 0), v3(0, 0, 0)};
+    double element_z = 0.0, area = 0.0, film_dz = 0.0, wt = 0.0;
+    uint32_t n_camera = 0, n_zero = 0;
+    for (;;) {
+        const unsigned waiting = __ballot_sync(FULL, !have || need_begin);
+        if (__popc(waiting) >= RRT_GEN_REFILL || waiting == FULL) {
+            const unsigned idle = __ballot_sync(FULL, !have);
+            if (idle != 0u && !exhausted) {
+                const int want = __popc(idle);
+                uint32_t first = 0;
+                if (lane == 0) first = atomicAdd(cursor, (uint32_t)want);
+                first = __shfl_sync(FULL, first, 0);
+                if ((uint64_t)first + (uint64_t)want >= n_list) exhausted = true;
+                const uint64_t mine = (uint64_t)first + (uint64_t)__popc(idle & lt);
+                if (!have && mine < n_list) {
+                    cs = survivors[mine];
+                    have = true;
+                    stage = GEN_MAIN;
+                    need_begin = true;
+                }
+            }
+            if (have && need_begin) {
+                RayD r_film;
+                begin_film_ray(cam, neighbour_film_point(cs.pf, stage), cs.pl, &r_film, &area);
+                film_dz = normalize(r_film.d).z;
+                r = flip_z(r_film);  // trace_lenses_from_film's first statement
+                element_z = 0.0;
+                ei = cam.n_elements - 1;
+                need_begin = false;
+            }
+        }
+        if (__ballot_sync(FULL, have) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        bool emit = false;
+        if (have && !need_begin) {
+            bool blocked = false, through = false;
+            {
+                const LensElement e = s_el[ei];
+                const double eta_prev = ei > 0 ? s_el[ei - 1].eta : 0.0;
+                const double eta_t = (ei > 0 && eta_prev != 0.0) ? eta_prev : 1.0;
+                if (!lens_step_from_film(e, eta_t, &element_z, &r)) blocked = true;
+                else if (--ei < 0) through = true;
+            }
+            if (blocked || through) {
+                const double w = through ? film_ray_weight(cam, film_dz, area) : 0.0;
+                const bool ok = w != 0.0;
+                bool done = false;
+                double final_w = 0.0;
+                if (stage == GEN_MAIN) {
+                    RayD world = {v3(0, 0, 0), v3(0, 0, 0)};
+                    if (ok) camera_ray_to_world(cam, flip_z(r), &world);
+                    paths[cs.slot].o = world.o;
+                    paths[cs.slot].d = world.d;
+                    wt = w;
+                    done = !ok || cs.nb_ok != 0u;  // the screen kernel vouches for the neighbours
+                    final_w = ok ? wt : 0.0;
+                    stage = GEN_XP;
+                } else if (stage == GEN_XP) {
+                    stage = ok ? GEN_YP : GEN_XM;
+                } else if (stage == GEN_XM) {
+                    done = !ok;
+                    stage = GEN_YP;
+                } else if (stage == GEN_YP) {
+                    done = ok;
+                    final_w = wt;
+                    stage = GEN_YM;
+                } else {
+                    done = true;
+                    final_w = ok ? wt : 0.0;
+                }
+                need_begin = !done;
+                if (done) {
+                    finish_camera_sample(paths + cs.slot, cs, final_w, ip.init_dim);
+                    if (final_w > 0.0) {
+                        emit = true;
+                        n_camera += 1;
+                    } else {
+                        n_zero += 1;
+                    }
+                    have = false;
+                }
+            }
+        }
+        const uint32_t es = queue_slot(q.counters + 0, emit);
+        if (emit) {
+            write_ray(q.ext_rays[0] + es, paths[cs.slot].o, paths[cs.slot].d, kInfD);
+            q.ext_path[0][es] = cs.slot;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        n_camera += __shfl_xor_sync(FULL, n_camera, off);
+        n_zero += __shfl_xor_sync(FULL, n_zero, off);
+    }
+    if (lane == 0) {
+        if (n_camera) atomicAdd(q.stats + 0, (unsigned long long)n_camera);
+        if (n_zero) atomicAdd(q.stats + 4, (unsigned long long)n_zero);
     }
 }
 
@@ -938,9 +1193,10 @@ struct Renderer::Impl {
     uint32_t whitted_rounds = 1;    // upper bound of rays per camera sample
     WhittedBranch* d_stacks = nullptr;
     double* d_cam_samples = nullptr;
-    // RRT_GEN_F32: 2 = screened generate kernel (fp32 walks decide blocked samples and neighbour rays; the default),
-    // 1 = the lane-state-machine kernel with fp32 neighbour walks, 0 = every lens trace in f64 (the parity tests' A/B switch)
-    int gen_mode = 2;
+    // RRT_GEN_F32: 3 = the screened generate kernel's two phases as two kernels (fp32 walks decide blocked samples and neighbour
+    // rays, then the survivors' f64 trace; the default), 2 = both phases in one kernel, 1 = the lane-state-machine kernel with
+    // fp32 neighbour walks, 0 = every lens trace in f64 (the parity tests' A/B switch)
+    int gen_mode = 3;
     Queues q{};
     uint32_t* d_tiles = nullptr;
     uint32_t tiles_capacity = 0;
@@ -1780,14 +2036,23 @@ int Renderer::run(uint32_t tile_mod, uint32_t tile_rank, const int64_t* crop, st
     uint64_t launches = 0;
     for (uint64_t base = 0; base < total; base += I.chunk) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(I.chunk, total - base);
-        RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 4 * sizeof(uint32_t), I.stream));
+        RND_CUDA(cudaMemsetAsync(I.q.counters, 0, 6 * sizeof(uint32_t), I.stream));  // queues, generate cursor, survivor list + cursor
         if (I.d_cam_samples) {
             strat_camera_kernel<<<(count + 127) / 128, 128, 0, I.stream>>>(I.film, I.ip, fr, base, count, I.d_cam_samples);
             launches += 1;
         }
         // persistent: one resident wave of CTAs, each warp pulls samples until the chunk is empty
         const uint32_t gen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_MINBLOCKS);
-        if (I.gen_mode == 2 && I.d_diffs == nullptr)
+        if (I.gen_mode == 3 && I.d_diffs == nullptr) {
+            // the screen / trace split: survivors pass through the (still unused) second extension queue
+            GenSample* const survivors = reinterpret_cast<GenSample*>(I.q.ext_rays[1]);
+            const uint32_t screen_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_SCREEN_MINBLOCKS);
+            const uint32_t trace_blocks = std::min<uint32_t>((count + 127) / 128, (uint32_t)I.sm_count * RRT_GEN_TRACE_MINBLOCKS);
+            generate_screen_kernel<<<screen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count, I.d_paths, I.q,
+                                                                        survivors);
+            generate_trace_kernel<<<trace_blocks, 128, 0, I.stream>>>(I.cam, I.ip, I.d_paths, I.q, survivors);
+            launches += 1;
+        } else if (I.gen_mode == 2 && I.d_diffs == nullptr)
             generate_screened_kernel<<<gen_blocks, 128, 0, I.stream>>>(I.cam, I.ht, I.d_perms, I.film, I.ip, fr, base, count,
                                                                        I.d_paths, I.q);
         else

@@ -303,7 +303,7 @@ def test_f32_lens_walks_change_nothing(ctx, tmp_path, monkeypatch):
                synth.scene_c4(str(tmp_path / "c4"), n_spheres=3000, xres=480, yres=270, nsamp=9, extent=12.0)]
     for path in scenes_:
         runs = {}
-        for flag in ("0", "1", "2"):
+        for flag in ("0", "1", "2", "3"):
             monkeypatch.setenv("RRT_GEN_F32", flag)
             gpu = Render.load(ctx, path, seed=1)
             gpu.enable_hit_dump()
@@ -311,7 +311,7 @@ def test_f32_lens_walks_change_nothing(ctx, tmp_path, monkeypatch):
             runs[flag] = (gpu.hit_dump(), gpu.film(), gpu.stats())
         d0, f0, s0 = runs["0"]
         assert s0["f32_neighbours"] == 0 and s0["f32_unsure"] == 0
-        for flag in ("1", "2"):
+        for flag in ("1", "2", "3"):   # 3 = the screened kernel's two phases as kernels of their own
             d1, f1, s1 = runs[flag]
             assert s1["f32_neighbours"] > 2 * s1["camera_rays"] * 0.9, (flag, s1)
             assert s1["f32_unsure"] < 0.05 * s1["f32_neighbours"], (flag, s1)
