@@ -603,7 +603,7 @@ __device__ __forceinline__ bool chunk_slot_sample(const FilmParams& film, const 
 #define RRT_GEN_SCREEN_MINBLOCKS 8
 #endif
 #ifndef RRT_GEN_TRACE_MINBLOCKS
-#define RRT_GEN_TRACE_MINBLOCKS 6
+#define RRT_GEN_TRACE_MINBLOCKS 7
 #endif
 __global__ void __launch_bounds__(128, RRT_GEN_SCREEN_MINBLOCKS)
     generate_screen_kernel(CameraData cam, HaltonTables ht, const uint16_t* __restrict__ perms, FilmParams film, IntegratorParams ip,
