@@ -3,13 +3,15 @@
 // (src/integrator/directlighting.rs:72-132) restructured as a pipeline of kernels over
 // persistent queues in HBM:
 //
-//   generate  : Halton camera sample (halton.cuh) -> lens-system trace (camera.cuh) -> extension ray
+//   generate  : Halton camera sample (halton.cuh) -> lens-system trace (camera.cuh) -> extension ray; two kernels: an fp32
+//               screen that drops the samples the lens blocks, then the survivors' f64 trace
 //   extend    : closest hit of every queued ray          (aggregate.cu, device-side ray count)
 //   shade     : hit -> surface frame -> BSDF; one light sample -> shadow ray + its contribution;
-//               BSDF sample -> next extension ray; Russian roulette           (shading.cuh)
+//               BSDF sample -> next extension ray; Russian roulette           (shading.cuh); the hits are grouped by
+//               material kind and constant-valued scenes run one kernel per kind (render_kernels.cuh)
 //   shadow    : any hit of every shadow ray               (aggregate.cu)
 //   resolve   : unoccluded contributions are added to their path's radiance
-//   deposit   : FilmTile::add_sample through the filter table, per-pixel f64 atomics
+//   deposit   : FilmTile::add_sample through the filter table, per-pixel f64 atomics after a warp-level sum
 //
 // A chunk of up to kChunk camera samples (render_kernels.cuh: few, large chunks) runs generate, then max_depth + 1 rounds of
 // extend/shade/shadow/resolve, then deposit; every count lives on the device, so the whole frame
