@@ -77,6 +77,8 @@ struct Builder {
         nodes[ni].first = begin;
         nodes[ni].count = end - begin;
         nodes[ni].left = nodes[ni].right = -1;
+        nodes[ni].n_interior = 0;
+        nodes[ni].n_prims = end - begin;
         n_leaves.fetch_add(1, std::memory_order_relaxed);
         return 1;  // depth of the subtree, in nodes
     }
@@ -307,6 +309,8 @@ struct Builder {
             dl = build(l, begin, mid, lb, lc);
             dr = build(r, mid, end, rb, rc);
         }
+        nodes[ni].n_interior = 1 + nodes[l].n_interior + nodes[r].n_interior;
+        nodes[ni].n_prims = n;
         return 1 + std::max(dl, dr);
     }
 };

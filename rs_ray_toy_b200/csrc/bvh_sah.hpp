@@ -17,6 +17,9 @@ struct Bvh2Node {
     Aabb box;
     int32_t left = -1, right = -1;  // interior: child node indices
     uint32_t first = 0, count = 0;  // leaf: range in Bvh2::order
+    // subtree totals (a leaf: n_interior = 0, n_prims = count): what lets the packer lay a subtree out without walking
+    // the ones before it (bvh_pack_plan.hpp)
+    uint32_t n_interior = 0, n_prims = 0;
 };
 
 // Allocator whose value-less construct() does nothing: resize() then leaves the elements uninitialised.  The builder
