@@ -148,7 +148,12 @@ RRT_HD uint64_t halton_index(const HaltonTables& h, int64_t px, int64_t py, uint
 RRT_HD double halton_sample(const HaltonTables& h, const uint16_t* perms, uint64_t index, uint32_t dim) {
     if (h.sample_at_pixel_center && dim < 2) return 0.5;
     if (dim == 0) return radical_inverse(h, 0, index >> h.base_exponents[0]);
-    if (dim == 1) return radical_inverse(h, 1, index / (uint64_t)h.base_scales[1]);
+    if (dim == 1) {
+        // (a 64-bit division is ~10x the instructions of a 32-bit one, and a frame's indices fit 32 bits up to 4K x 138 k spp)
+        const uint64_t scale = (uint64_t)h.base_scales[1];
+        const uint64_t q = (index <= 0xFFFFFFFFull && scale <= 0xFFFFFFFFull) ? (uint64_t)((uint32_t)index / (uint32_t)scale) : index / scale;
+        return radical_inverse(h, 1, q);
+    }
     if (dim >= (uint32_t)kHaltonDims) dim = kHaltonDims - 1;  // deeper than any in-scope path; never reached
     return scrambled_radical_inverse(h, (int)dim, index, perms + h.prime_sums[dim]);
 }

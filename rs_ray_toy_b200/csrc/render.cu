@@ -905,8 +905,14 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(Queues q, int cur) {
 __device__ __forceinline__ bool chunk_slot_sample(const FilmParams& film, const IntegratorParams& ip, const Frame& fr, uint64_t sidx,
                                                   int64_t* px, int64_t* py, uint32_t* sn) {
     const uint64_t per_tile = (uint64_t)kTile * kTile * ip.n_samples;
-    const uint32_t tslot = (uint32_t)(sidx / per_tile);
-    const uint32_t within = (uint32_t)(sidx % per_tile);
+    uint32_t tslot, within;
+    if (sidx <= 0xFFFFFFFFull && per_tile <= 0xFFFFFFFFull) {  // (a 4K x 256 spp frame is 2.1 G samples: the 32-bit division, a tenth of the instructions)
+        tslot = (uint32_t)sidx / (uint32_t)per_tile;
+        within = (uint32_t)sidx - tslot * (uint32_t)per_tile;
+    } else {
+        tslot = (uint32_t)(sidx / per_tile);
+        within = (uint32_t)(sidx % per_tile);
+    }
     const uint32_t pix = within / ip.n_samples;
     *sn = within % ip.n_samples + 1u;  // sample numbers 1..n-1 (Q10)
     const uint32_t tile = fr.tiles[tslot];
