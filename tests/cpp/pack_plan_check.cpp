@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
         boxes[i] = b;
     }
     SahParams prm; prm.max_leaf = 4;
+    if (getenv("T")) prm.n_threads = atoi(getenv("T"));   // builder threads (the huge top nodes split their passes over them)
     Bvh2 tree;
     build_sah(AabbSpan(boxes.data(), boxes.size()), prm, &tree);
     // the tree itself: every primitive in exactly one leaf, child boxes inside their parent's, subtree totals right

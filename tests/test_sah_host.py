@@ -29,3 +29,15 @@ def test_sah_tree_and_pack_plan(checker, n):
     r = subprocess.run([str(checker), str(n)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "tree VALID" in r.stdout and "IDENTICAL" in r.stdout, r.stdout
+
+
+def test_sah_tree_does_not_depend_on_the_thread_count(checker):
+    """Nodes of >= 2^18 primitives split their binning pass and their partition (a stable two-sided scatter) over threads:
+    the tree — node count, depth, every slot of the plan — must be the one a single thread builds."""
+    import os
+    outs = []
+    for threads in ("1", "3", "16"):
+        r = subprocess.run([str(checker), "300000"], capture_output=True, text=True, timeout=300, env=dict(os.environ, T=threads))
+        assert r.returncode == 0 and "tree VALID" in r.stdout and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+        outs.append([ln for ln in r.stdout.splitlines() if ln.startswith("tree") or ln.startswith("IDENTICAL")])
+    assert outs[0] == outs[1] == outs[2], outs
